@@ -1,0 +1,171 @@
+/*
+ * oracle/cpo.h -- C interface of the CPU ORACLE.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  It is a single-threaded C++
+ * restatement of the algorithms of willow-ahrens/ChainPartitioners.jl (v1.1.6)
+ * for the hot path "cost oracle over column ranges + the split-point searches
+ * that consume it".  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product
+ * (chainpartitioners.jl_b200/libchainb200.so) never links or calls it.
+ *
+ * Parity pinning: Julia is not installed in the build image, so the reference
+ * itself cannot be executed.  The reference's own tests are randomized
+ * property tests with NO golden vectors; this restatement is pinned by
+ * re-expressing those properties (tests/test_oracle_*.py: brute-force count
+ * definitions of test/test_SparseColorArrays.jl:1-11 and
+ * test/test_SparsePrefixMatrices.jl:14, model-vs-oracle equality and bound
+ * sandwich of test/test_Costs.jl, (eps-)optimality against the brute-force DP
+ * of test/test_Partitioners.jl) on the reference's six fixture matrices
+ * (test/matrices.jl, committed as tests/golden/ npz files) and on random inputs,
+ * plus cross-checks between independent restatements (b-ary vs binary vs
+ * stepwise dominance counts; BisectCost vs LazyBisect).  Exact split vectors
+ * are therefore pinned by control-flow-faithful restatement only.
+ *
+ * All indices are 1-based Int64 exactly as Julia's SparseMatrixCSC stores
+ * them: colptr[0..n] holds values 1..N+1, rowval[0..N-1] holds 1..m.
+ */
+#ifndef CPO_H
+#define CPO_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef long long cpo_i64;
+
+/* cost model kinds (reference file in parentheses) */
+enum {
+  CPO_MODEL_WORK = 0,              /* AffineWorkModel                     (WorkCosts.jl:5-17) */
+  CPO_MODEL_CONNECTIVITY = 1,      /* AffineConnectivityModel             (ConnectivityCosts.jl:7-20) */
+  CPO_MODEL_MONOSYM = 2,           /* AffineMonotonizedSymmetricConn.     (MonotonizedSymmetricConnectivityCosts.jl:5-33) */
+  CPO_MODEL_SYMCONN = 3,           /* AffineSymmetricConnectivityModel    (SymmetricConnectivityCosts.jl:5-19) */
+  CPO_MODEL_HYPEREDGE = 4,         /* AffineHyperedgeCutModel             (HyperedgeCutCosts.jl:7-21) */
+  CPO_MODEL_SYMEDGECUT = 5,        /* AffineSymmetricEdgeCutModel         (SymmetricEdgeCutCosts.jl:5-18) */
+  CPO_MODEL_ENVELOPE = 6,          /* AffineEnvelopeModel                 (EnvelopeCosts.jl:5-20) */
+  CPO_MODEL_COLBLOCK = 7,          /* ColumnBlockComponentCostModel       (BlockCosts.jl:1-17) */
+  CPO_MODEL_BLOCK = 8              /* BlockComponentCostModel             (BlockCosts.jl:19-44) */
+};
+
+/* hints -> dominance structure (SparsePrefixMatrices.jl:450-458) */
+enum { CPO_HINT_NONE = 0, CPO_HINT_RANDOM = 1, CPO_HINT_SPARSE = 2, CPO_HINT_STEP = 3 };
+
+/* color arrays (SparseColorArrays.jl) */
+enum { CPO_COUNT_PIN = 0, CPO_COUNT_NET = 1, CPO_COUNT_DIANET = 2, CPO_COUNT_SELFNET = 3, CPO_COUNT_SELFPIN = 4 };
+
+/* partition_stripe methods */
+enum {
+  CPO_SPLIT_DYNAMIC_BOTTLENECK = 0,   /* DynamicSplitter.jl:15-50 (g = max) */
+  CPO_SPLIT_DYNAMIC_TOTAL = 1,        /* DynamicSplitter.jl:15-50 (g = +)   */
+  CPO_SPLIT_BISECT_COST = 2,          /* BisectCostBottleneckSplitter.jl:6-63 */
+  CPO_SPLIT_LAZY_BISECT_COST = 3,     /* LazyBisectCostBottleneckSplitter.jl: dispatches like Julia (:140 conn, :260 monosym, :8 generic) */
+  CPO_SPLIT_LAZY_BISECT_GENERIC = 4,  /* LazyBisectCostBottleneckSplitter.jl:8-70 forced */
+  CPO_SPLIT_EQUI = 5,                 /* EquiPartitioner.jl:3-9 */
+  CPO_SPLIT_FLIP_BISECT_COST = 6,     /* BisectCostBottleneckSplitter.jl:70-127 */
+  CPO_SPLIT_LAZY_FLIP_BISECT_COST = 7,/* LazyBisectCostBottleneckSplitter.jl:79-138 */
+  CPO_SPLIT_CONVEX_TOTAL = 8,         /* ConvexTotalChunker.jl:26-55 (ConvexTotalSplitter) */
+  CPO_SPLIT_CONCAVE_TOTAL = 9         /* ConcaveTotalChunker.jl:26-55 (ConcaveTotalSplitter) */
+};
+
+/* pack_stripe methods */
+enum {
+  CPO_PACK_DYNAMIC_TOTAL = 0,  /* DynamicChunker.jl:20-56 */
+  CPO_PACK_CONVEX_TOTAL = 1,   /* ConvexTotalChunker.jl:9-24 / :141-165 (constrained) */
+  CPO_PACK_CONCAVE_TOTAL = 2,  /* ConcaveTotalChunker.jl:9-24 */
+  CPO_PACK_OVERLAP = 3,        /* OverlapChunker.jl:6-75 */
+  CPO_PACK_STRICT = 4,         /* StrictChunker.jl:5-54 */
+  CPO_PACK_EQUI = 5            /* EquiPartitioner.jl:15-21 */
+};
+
+/*
+ * A cost model.  coef[] meaning by kind (all evaluated left to right, no FMA):
+ *   WORK        alpha, b_vertex, b_pin
+ *   CONNECTIVITY/ENVELOPE alpha, b_vertex, b_pin, b_net
+ *   MONOSYM     alpha, b_vertex, b_over_pin, b_dia_net, delta_pins
+ *   SYMCONN     alpha, b_vertex, b_pin, b_local_net, b_remote_net
+ *   HYPEREDGE   alpha, b_vertex, b_pin, b_self_net, b_cut_net
+ *   SYMEDGECUT  alpha, b_vertex, b_self_pin, b_cut_pin
+ * is_float = 0: coefficient type Int64 (coef[] integer valued), cost type Int64;
+ * is_float = 1: Float64.
+ * COLBLOCK / BLOCK: tabulated block_component(f, w) (BlockCosts.jl:41-44):
+ *   alpha_col[w]   w = 0..w_tab          (length w_tab+1)
+ *   beta_col[r][w] r = 0..R-1, w=0..w_tab (COLBLOCK: R = 1)
+ *   beta_row[r][u] r = 0..R-1, u=0..u_tab (BLOCK only)
+ */
+typedef struct cpo_model {
+  int32_t kind;
+  int32_t is_float;
+  double coef[8];
+  int32_t R;
+  int32_t w_tab;
+  int32_t u_tab;
+  int32_t _pad;
+  const double* alpha_col;
+  const double* beta_col;
+  const double* beta_row;
+} cpo_model;
+
+/* weight constraint of ConstrainedCost(f, w, w_max) (Costs.jl:105-147):
+ * w(j,j') = w_coef[0] + (j'-j) w_coef[1] + (pos[j']-pos[j]) w_coef[2]  (Int64);
+ * VertexCount() = {0,1,0}.  enabled = 0 means FeasibleCost (no constraint). */
+typedef struct cpo_constraint {
+  int32_t enabled;
+  int32_t _pad;
+  cpo_i64 w_coef[3];
+  cpo_i64 w_max;
+} cpo_constraint;
+
+typedef struct cpo_csc {
+  cpo_i64 m, n, nnz;
+  const cpo_i64* colptr; /* n+1 entries, 1-based values */
+  const cpo_i64* rowval; /* nnz entries, 1-based values */
+} cpo_csc;
+
+const char* cpo_last_error(void);
+
+/* util.jl:67-95 */
+int cpo_adjointpattern(const cpo_csc* A, cpo_i64* colptr_out /* m+1 */, cpo_i64* rowval_out /* nnz */);
+
+/* dominancecount(hint, A; b, H, b') [i,j]  (SparsePrefixMatrices.jl:396-821); b/H/bp <= 0 -> default */
+int cpo_dominancecount(int hint, const cpo_csc* A, int b, int H, int bp,
+                       cpo_i64 Q, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out);
+/* random walk through the Step interface of the stepwise counter; moves[t] in
+ * {0 Same,1 Next,2 Prev,3 Jump} for i and j  (test_SparsePrefixMatrices.jl:74-92) */
+int cpo_dominancecount_walk(const cpo_csc* A, cpo_i64 T, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out);
+
+/* netcount / dianetcount / selfnetcount / selfpincount / pincount [j,j'] (SparseColorArrays.jl) */
+int cpo_colorcount(int which, int hint, const cpo_csc* A,
+                   cpo_i64 Q, const cpo_i64* qj, const cpo_i64* qjp, cpo_i64* out);
+
+/* rowenvelope(A)[j,j'] (EnvelopeMatrices.jl:10-56): out_lo/out_hi */
+int cpo_rowenvelope(const cpo_csc* A, cpo_i64 Q, const cpo_i64* qj, const cpo_i64* qjp,
+                    cpo_i64* out_lo, cpo_i64* out_hi);
+
+/* oracle_stripe(hint, mdl, A[, Pi])(j, j', k): cost_out as double (exact for Int64 costs < 2^53) */
+int cpo_oracle_query(const cpo_model* mdl, int hint, const cpo_csc* A,
+                     const cpo_i64* pi_spl, cpo_i64 pi_K,
+                     cpo_i64 Q, const cpo_i64* qj, const cpo_i64* qjp, const cpo_i64* qk,
+                     double* cost_out);
+
+/* bound_stripe(A, K, mdl) -> (c_lo, c_hi) ./ 1 ; via_oracle != 0 uses the oracle form */
+int cpo_bound_stripe(const cpo_model* mdl, const cpo_csc* A, cpo_i64 K, int via_oracle, double out[2]);
+
+/* partition_stripe(A, K, method(mdl[, eps])) -> spl[K+1] */
+int cpo_partition_stripe(int method, const cpo_model* mdl, const cpo_constraint* con, double eps,
+                         const cpo_csc* A, const cpo_i64* pi_spl, cpo_i64 pi_K, cpo_i64 K, cpo_i64* spl_out,
+                         double* seconds_out /* [2]: oracle build, solve; may be NULL */);
+
+/* pack_stripe(A, method(...)[, Pi]) -> spl[K+1], K; spl_out must hold n+1 entries */
+int cpo_pack_stripe(int method, const cpo_model* mdl, const cpo_constraint* con, double rho, cpo_i64 w_max,
+                    const cpo_csc* A, const cpo_i64* pi_spl, cpo_i64 pi_K,
+                    cpo_i64* spl_out, cpo_i64* K_out, cpo_i64* n_nets_out /* n entries or NULL (overlap) */,
+                    double* seconds_out);
+
+/* bottleneck_value / total_value of a SplitPartition through the oracle (Costs.jl:26-66) */
+int cpo_objective(int total, const cpo_model* mdl, int hint, const cpo_csc* A,
+                  const cpo_i64* pi_spl, cpo_i64 pi_K,
+                  cpo_i64 K, const cpo_i64* spl, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

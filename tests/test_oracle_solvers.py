@@ -1,0 +1,383 @@
+"""Pins the CPU oracle's cost models and split-point searches by the properties the reference's own
+tests check (test/test_Costs.jl, test/test_Partitioners.jl): model == brute-force definition,
+bound sandwich, (eps-)optimality against an independent brute-force DP, chunk constraints -- plus
+the per-algorithm tie-breaking rules of SURVEY.md App. B re-derived independently."""
+import numpy as np
+import pytest
+
+import chainb200 as cp
+from helpers import (brute_chunk_optimum, brute_optimum, check_split, col_rows, cost_matrix, objective, ref_cost,
+                     ref_netcount, sprand)
+
+HINTS = [cp.NoHint(), cp.SparseHint(), cp.StepHint()]
+
+AFFINE_MODELS = [
+    cp.AffineWorkModel(0, 10, 1),
+    cp.AffineWorkModel(0, 1, 0),
+    cp.AffineConnectivityModel(0, 0, 0, 1),
+    cp.AffineConnectivityModel(0, 3, 1, 3),
+    cp.AffineConnectivityModel(0, 10, 1, 100),
+    cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0),
+    cp.AffineConnectivityModel(-0.5, 0.0, 0.0, 1.0),
+    cp.AffineEnvelopeModel(1, 2, 3, 4),
+]
+SQUARE_MODELS = [
+    cp.AffineMonotonizedSymmetricConnectivityModel(10, 10, 10, 10, 0),
+    cp.AffineMonotonizedSymmetricConnectivityModel(10, 10, 10, 100, 8),
+    cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5),
+    cp.AffineSymmetricConnectivityModel(1, 1, 1, 1, 1),
+    cp.AffineSymmetricConnectivityModel(0, 0, 0, 0, 1),
+    cp.AffineHyperedgeCutModel(0, 0, 0, 1, 1),
+    cp.AffineHyperedgeCutModel(0, 0, 0, -1, 0),
+    cp.AffineSymmetricEdgeCutModel(10, 10, 10, 100),
+    cp.AffineSymmetricEdgeCutModel(1, 1, 1, 1),
+]
+
+
+def all_pairs(n):
+    return [(j, jp) for j in range(1, n + 2) for jp in range(j, n + 2)]
+
+
+def test_models_match_definitions(ref):
+    """test_Costs.jl:24-30,66-79: oracle value == model evaluated on brute-force counts."""
+    rng = np.random.default_rng(10)
+    for m in [1, 2, 3, 5, 8, 13, 21]:
+        A = sprand(rng, m, m, 0.3)
+        pairs = all_pairs(m)
+        j = [p[0] for p in pairs]
+        jp = [p[1] for p in pairs]
+        for mdl in AFFINE_MODELS + SQUARE_MODELS:
+            if mdl.kind == cp.MODEL_ENVELOPE:
+                continue
+            exp = [float(ref_cost(mdl, A, a, b)) for a, b in pairs]
+            for hint in HINTS:
+                got = ref.oracle_query(mdl, A, j, jp, hint=hint)
+                assert got.tolist() == exp, (mdl, hint, m)
+        env = cp.AffineEnvelopeModel(1, 2, 3, 4)
+        pe = [p for p in pairs if p[0] < p[1]]
+        got = ref.oracle_query(env, A, [p[0] for p in pe], [p[1] for p in pe])
+        assert got.tolist() == [float(ref_cost(env, A, a, b)) for a, b in pe]
+
+
+def test_block_oracle_random_access(ref):
+    """test_Costs.jl:106-122 + SURVEY E11: BlockComponentCostStepOracle under random access."""
+    rng = np.random.default_rng(11)
+    models = [
+        cp.BlockComponentCostModel(int, 0, 0, (2, cp.identity), (2, lambda x: 2 * x)),
+        cp.BlockComponentCostModel(int, cp.identity, lambda x: 3 * x, (2, cp.identity), (2, lambda x: 2 * x)),
+        cp.BlockComponentCostModel(int, 1, 3, (1, cp.identity), (1, cp.identity)),
+        cp.ColumnBlockComponentCostModel(int, 3, lambda w: 1 + w),
+    ]
+    for m in [3, 7, 12, 20]:
+        for u in [1, 2, 3, 4]:
+            A = sprand(rng, m, m + 2, 0.25)
+            Pi = ref.pack_stripe(ref.adjointpattern(A), cp.EquiChunker(u))
+            pairs = all_pairs(A.n)
+            order = rng.permutation(len(pairs))
+            pairs = [pairs[t] for t in order]
+            for mdl in models:
+                got = ref.oracle_query(mdl, A, [p[0] for p in pairs], [p[1] for p in pairs], Pi=Pi, hint=cp.StepHint())
+                exp = [float(ref_cost(mdl, A, a, b, Pi)) for a, b in pairs]
+                assert got.tolist() == exp
+
+
+def test_bound_sandwich(ref):
+    """test_Costs.jl:26-30: 0 <= c_lo <= bottleneck_value <= c_hi for any K-partition."""
+    rng = np.random.default_rng(12)
+    for m in range(1, 40, 3):
+        A = sprand(rng, m, m, 0.125)
+        for K in [1, 2, 3, 4]:
+            spl = np.concatenate(([1], np.sort(rng.integers(1, m + 2, K - 1)), [m + 1]))
+            Phi = cp.SplitPartition(K, spl)
+            for mdl in [cp.AffineWorkModel(0, 1, 1), cp.AffineConnectivityModel(0, 1, 1, 1),
+                        cp.AffineMonotonizedSymmetricConnectivityModel(10, 10, 10, 100, 8),
+                        cp.AffineConnectivityModel(0.0, 1.0, 1.0, 1.0)]:
+                lo, hi = ref.bound_stripe(A, K, mdl)
+                v = ref.bottleneck_value(A, Phi, mdl)
+                assert 0 <= lo <= v <= hi
+                assert v == max(ref_cost(mdl, A, int(spl[k]), int(spl[k + 1])) for k in range(K))
+
+
+def rightmost_dp(C, n, K, total):
+    """Independent statement of App. B: per layer, the LARGEST j among minimisers."""
+    g = (lambda a, b: a + b) if total else max
+    cst = np.full((K + 1, n + 2), np.inf)
+    ptr = np.zeros((K + 1, n + 2), dtype=np.int64)
+    for jp in range(1, n + 2):
+        cst[1, jp] = C[1, jp]
+        ptr[1, jp] = 1
+    for k in range(2, K + 1):
+        for jp in range(1, n + 2):
+            vals = [g(cst[k - 1, j], C[j, jp]) for j in range(1, jp + 1)]
+            v = min(vals)
+            cst[k, jp] = v
+            ptr[k, jp] = max(j for j, x in zip(range(1, jp + 1), vals) if x == v)
+    spl = [0] * (K + 1)
+    spl[K] = n + 1
+    for k in range(K, 0, -1):
+        spl[k - 1] = int(ptr[k, spl[k]])
+    return spl
+
+
+def test_dynamic_splitters(ref, fixtures):
+    """test_Partitioners.jl:95-113,154-170: Dynamic == Reference optimum; exact rightmost-tie splits."""
+    rng = np.random.default_rng(13)
+    mats = [fixtures["LPnetlib/lpi_itest6"]] + [sprand(rng, m, n, 0.2) for m in [1, 2, 4, 8] for n in [1, 3, 8, 12]]
+    for A in mats:
+        models = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(2, 0, 0, 1)]
+        if A.m == A.n:
+            models.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
+        for mdl in models:
+            C = cost_matrix(mdl, A)
+            for K in [1, 2, 3, 4, 8]:
+                for total, mtd in [(False, cp.DynamicBottleneckSplitter(mdl)), (True, cp.DynamicTotalSplitter(mdl))]:
+                    Phi = ref.partition_stripe(A, K, mtd)
+                    check_split(Phi.spl, A.n, K)
+                    assert objective(C, Phi.spl, total) == brute_optimum(C, A.n, K, total)
+                    assert Phi.spl.tolist() == rightmost_dp(C, A.n, K, total)
+
+
+def test_dynamic_splitter_constrained(ref):
+    """DynamicSplitter.jl:206-247: optimum among width-feasible partitions, or the degenerate one."""
+    rng = np.random.default_rng(14)
+    for n in [1, 3, 6, 10]:
+        A = sprand(rng, 6, n, 0.3)
+        mdl = cp.AffineConnectivityModel(0, 0, 0, 1)
+        C = cost_matrix(mdl, A)
+        for w_max in [2, 4]:
+            Cw = C.copy()
+            for j in range(1, n + 2):
+                for jp in range(j, n + 2):
+                    if jp - j > w_max:
+                        Cw[j, jp] = np.inf
+            for K in [1, 2, 3, 4, 8]:
+                f = cp.ConstrainedCost(mdl, cp.AffineWorkModel(0, 1, 0), w_max)
+                Phi = ref.partition_stripe(A, K, cp.DynamicTotalSplitter(f))
+                opt = brute_optimum(Cw, n, K, True)
+                if np.isinf(opt):
+                    assert Phi.spl.tolist() == [1] * K + [n + 1]
+                else:
+                    check_split(Phi.spl, n, K)
+                    assert objective(Cw, Phi.spl, True) == opt
+
+
+def greedy_probe(C, n, K, c):
+    """every part as long as feasible at threshold c; None if infeasible"""
+    spl = [1]
+    j = 1
+    for k in range(1, K):
+        jp = j
+        while jp + 1 <= n + 1 and C[j, jp + 1] <= c:
+            jp += 1
+        if C[j, jp] > c:
+            return None
+        spl.append(jp)
+        j = jp
+    if C[j, n + 1] > c:
+        return None
+    return spl + [n + 1]
+
+
+def bisect_reference(C, n, K, eps, lo, hi):
+    """Independent statement of App. A "Bisection loop" + App. B row 4 (no windows, no streaming)."""
+    best = [1] + [n + 1] * K
+    while lo * (1 + eps) < hi:
+        c = (lo + hi) / 2
+        s = greedy_probe(C, n, K, c)
+        if s is not None:
+            hi, best = c, s
+        else:
+            lo = c
+    return best
+
+
+@pytest.mark.parametrize("eps", [0.1, 0.01])
+def test_bisect_and_lazy(ref, fixtures, eps):
+    """test_Partitioners.jl:95-113 eps-optimality; SURVEY E3/E4: BisectCost == LazyBisect == greedy definition."""
+    rng = np.random.default_rng(15)
+    mats = [fixtures["LPnetlib/lpi_itest6"]] + [sprand(rng, m, n, 0.2) for m in [1, 3, 8] for n in [1, 2, 4, 8, 16]] + [sprand(rng, 14, 14, 0.3)]
+    for A in mats:
+        models = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0, 10, 1, 100),
+                  cp.AffineConnectivityModel(0.0, 3.0, 1.0, 3.5)]
+        if A.m == A.n:
+            models += [cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5), cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 2)]
+        for mdl in models:
+            C = cost_matrix(mdl, A)
+            for K in [1, 2, 3, 4, 8]:
+                opt = brute_optimum(C, A.n, K, False)
+                lo, hi = ref.bound_stripe(A, K, mdl)
+                lo = max(lo, float(mdl.coef[0]))
+                exp = bisect_reference(C, A.n, K, eps, lo, hi)
+                got = {}
+                for name, mtd in [("bisect", cp.BisectCostBottleneckSplitter(mdl, eps)), ("lazy", cp.LazyBisectCostBottleneckSplitter(mdl, eps))]:
+                    Phi = ref.partition_stripe(A, K, mtd)
+                    check_split(Phi.spl, A.n, K)
+                    assert objective(C, Phi.spl, False) <= opt * (1 + eps) + 1e-9
+                    got[name] = Phi.spl.tolist()
+                assert got["lazy"] == exp, (mdl, K)
+                if mdl.kind != cp.MODEL_WORK or True:
+                    # BisectCost has no c_lo = max(c_lo, alpha) step; identical whenever alpha <= c_lo
+                    assert got["bisect"] == got["lazy"], (mdl, K, A)
+
+
+def leftmost_chunk_dp(C, n, w_max):
+    cst = np.full(n + 2, np.inf)
+    cst[1] = 0
+    ptr = np.zeros(n + 2, dtype=np.int64)
+    for jp in range(2, n + 2):
+        lo = 1 if w_max is None else max(1, jp - w_max)
+        vals = [cst[j] + C[j, jp] for j in range(lo, jp)]
+        v = min(vals)
+        cst[jp] = v
+        ptr[jp] = lo + vals.index(v)
+    spl = [n + 1]
+    while spl[-1] != 1:
+        spl.append(int(ptr[spl[-1]]))
+    return spl[::-1], cst
+
+
+def test_dynamic_total_chunker(ref, fixtures):
+    """test_Partitioners.jl:225-248: width <= w_max, optimal total; App. B: leftmost argmin."""
+    rng = np.random.default_rng(16)
+    mats = [fixtures["LPnetlib/lpi_itest6"]] + [sprand(rng, m, n, 0.3) for m in [2, 5, 9] for n in [1, 2, 5, 11, 17]]
+    for A in mats:
+        Pi = ref.pack_stripe(ref.adjointpattern(A), cp.EquiChunker(2))
+        for mdl in [cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0, 0, 0, 1),
+                    cp.BlockComponentCostModel(int, 0, 0, (10, cp.identity), (2, lambda x: 2 * x)),
+                    cp.BlockComponentCostModel(int, 1, 3, (1, cp.identity), (1, cp.identity)),
+                    cp.ColumnBlockComponentCostModel(int, 3, lambda w: 1 + w)]:
+            C = cost_matrix(mdl, A, Pi)
+            for w_max in [1, 2, 4, 8]:
+                Phi = ref.pack_stripe(A, cp.DynamicTotalChunker(cp.ConstrainedCost(mdl, cp.VertexCount(), w_max)), Pi)
+                check_split(Phi.spl, A.n)
+                assert np.all(np.diff(Phi.spl) <= w_max)
+                exp, cst = leftmost_chunk_dp(C, A.n, w_max)
+                assert objective(C, Phi.spl, True) == brute_chunk_optimum(C, A.n, w_max)
+                assert Phi.spl.tolist() == exp
+            if mdl.kind == cp.MODEL_CONNECTIVITY:
+                Phi = ref.pack_stripe(A, cp.DynamicTotalChunker(mdl))  # unconstrained == ReferenceTotalChunker
+                assert Phi.spl.tolist() == leftmost_chunk_dp(C, A.n, None)[0]
+
+
+def convex_constrained_rule(C, n, w_max):
+    """windows B_t = (1+t w, 1+(t+1) w]; in-window leftmost unless prev strictly better (then rightmost)."""
+    cst = np.full(n + 2, np.inf)
+    cst[1] = 0
+    ptr = np.zeros(n + 2, dtype=np.int64)
+    for jp in range(2, n + 2):
+        t = (jp - 2) // w_max
+        j0 = 1 + t * w_max
+        in_ = list(range(max(jp - w_max, j0), jp))
+        prev = list(range(max(jp - w_max, 1), j0))
+        vin = [cst[j] + C[j, jp] for j in in_]
+        vpr = [cst[j] + C[j, jp] for j in prev]
+        if not vpr or min(vin) <= min(vpr):
+            v = min(vin)
+            ptr[jp] = in_[vin.index(v)]
+        else:
+            v = min(vpr)
+            ptr[jp] = max(j for j, x in zip(prev, vpr) if x == v)
+        cst[jp] = v
+    spl = [n + 1]
+    while spl[-1] != 1:
+        spl.append(int(ptr[spl[-1]]))
+    return spl[::-1]
+
+
+def test_convex_chunkers(ref, fixtures):
+    """test_Partitioners.jl:250-275 (optimal value); SURVEY E5/E6 tie rules for convex costs."""
+    rng = np.random.default_rng(17)
+    mats = [fixtures["LPnetlib/lpi_itest6"]] + [sprand(rng, m, n, 0.3) for m in [2, 5, 9] for n in [1, 2, 5, 11, 17, 30]]
+    for A in mats:
+        for mdl in [cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(1, 0, 0, 1),
+                    cp.AffineConnectivityModel(-0.5, 0.0, 0.0, 1.0)]:
+            C = cost_matrix(mdl, A)
+            Phi = ref.pack_stripe(A, cp.ConvexTotalChunker(mdl))
+            check_split(Phi.spl, A.n)
+            assert objective(C, Phi.spl, True) == brute_chunk_optimum(C, A.n, None)
+            assert Phi.spl.tolist() == leftmost_chunk_dp(C, A.n, None)[0]
+            for w_max in [1, 2, 3, 4, 8]:
+                Phi = ref.pack_stripe(A, cp.ConvexTotalChunker(cp.ConstrainedCost(mdl, cp.VertexCount(), w_max)))
+                check_split(Phi.spl, A.n)
+                assert np.all(np.diff(Phi.spl) <= w_max)
+                assert objective(C, Phi.spl, True) == brute_chunk_optimum(C, A.n, w_max)
+                assert Phi.spl.tolist() == convex_constrained_rule(C, A.n, w_max), (mdl, w_max, A.n)
+
+
+def test_concave_chunker(ref):
+    """test_Partitioners.jl:277-299: concave chunker reaches the optimum on a concave cost (work model
+    with alpha > 0 is both convex and concave: modular)."""
+    rng = np.random.default_rng(18)
+    for n in [1, 2, 5, 11, 17]:
+        A = sprand(rng, 6, n, 0.3)
+        for mdl in [cp.AffineWorkModel(3, 1, 2), cp.AffineWorkModel(0, 0, 0)]:
+            C = cost_matrix(mdl, A)
+            Phi = ref.pack_stripe(A, cp.ConcaveTotalChunker(mdl))
+            check_split(Phi.spl, A.n)
+            assert objective(C, Phi.spl, True) == brute_chunk_optimum(C, A.n, None)
+
+
+def overlap_definition(A, rho, w_max):
+    """greedy from set definitions, `c` frozen at deg(column 1)."""
+    n = A.n
+    c0 = len(col_rows(A, 1))
+    spl, nets = [1], []
+    j = 1
+    for jp in range(2, n + 1):
+        cc = len(set(col_rows(A, j).tolist()) & set(col_rows(A, jp).tolist()))
+        if jp - j == w_max or cc < rho * min(c0, len(col_rows(A, jp))):
+            nets.append(ref_netcount(A, j, jp))
+            spl.append(jp)
+            j = jp
+    nets.append(ref_netcount(A, j, n + 1))
+    spl.append(n + 1)
+    return spl, nets
+
+
+def strict_definition(A, w_max):
+    n = A.n
+    spl = [1]
+    j = 1
+    for jp in range(2, n + 1):
+        same = col_rows(A, j).tolist() == col_rows(A, jp).tolist()
+        if not (same and jp - j != w_max):
+            spl.append(jp)
+            j = jp
+    return spl + [n + 1]
+
+
+def test_overlap_and_strict(ref, fixtures):
+    rng = np.random.default_rng(19)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"]] + [sprand(rng, m, n, p) for m in [3, 6] for n in [1, 2, 9, 25] for p in [0.3, 0.8]]
+    for A in mats:
+        for w_max in [1, 2, 4, 8]:
+            for rho in [0.9, 0.8, 0.7, 0.3]:
+                box = [None]
+                Phi = ref.pack_stripe(A, cp.OverlapChunker(rho, w_max), n_nets=box)
+                exp_spl, exp_nets = overlap_definition(A, rho, w_max)
+                assert Phi.spl.tolist() == exp_spl
+                assert box[0].tolist() == exp_nets
+                assert np.all(np.diff(Phi.spl) <= w_max)
+            Phi = ref.pack_stripe(A, cp.StrictChunker(w_max))
+            assert Phi.spl.tolist() == strict_definition(A, w_max)
+
+
+def test_equi(ref):
+    for n in [1, 5, 17]:
+        A = cp.SparseMatrixCSC(1, n, np.ones(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int64))
+        for K in [1, 2, 3, 8]:
+            spl = ref.partition_stripe(A, K, cp.EquiSplitter()).spl
+            assert spl.tolist() == [(k - 1) * (n // K) + min(n % K, k - 1) + 1 for k in range(1, K + 2)]
+        for w in [1, 2, 4]:
+            assert ref.pack_stripe(A, cp.EquiChunker(w)).spl.tolist() == list(range(1, n + 1, w)) + [n + 1]
+
+
+def test_plaid(ref, fixtures):
+    """AlternatingPartitioner.jl:18-32 on the symmetric fixture (config 5 in miniature)."""
+    A = fixtures["HB/can_292"]
+    s = cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 90)
+    mtd = cp.LazyBisectCostBottleneckSplitter(s, 0.1)
+    Pi, Phi = ref.partition_plaid(A, 8, cp.AlternatingPartitioner(mtd, mtd))
+    check_split(Pi.spl, A.m, 8)
+    check_split(Phi.spl, A.n, 8)
+    assert Pi == Phi  # symmetric pattern: both stripe solves see the same matrix
