@@ -1,2 +1,470 @@
-"""placeholder -- replaced below"""
-__all__ = []
+"""Host-side mirror of ChainPartitioners.jl's functions over the C ABI of libchainb200.so.
+
+``partition_stripe`` / ``pack_stripe`` / ``partition_plaid`` / ``pack_plaid`` / ``oracle_stripe`` /
+``bound_stripe`` / ``bottleneck_value`` / ``total_value`` / ``netcount`` ... take the same arguments, in
+the same order, with the same meaning as the Julia methods they stand for (file:line in
+include/chainb200.h).  All arithmetic runs on the GPU; there is no CPU fallback -- if the CUDA library
+is missing or no device is visible every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import types as T
+
+__all__ = [
+    "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
+    "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
+    "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
+    "launch_count", "init", "synchronize", "library_path", "load_library", "CpbError",
+]
+
+I64 = np.int64
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libchainb200.so")
+_lib = None
+
+ABI_SYMBOLS = [
+    "cpb_last_error", "cpb_version", "cpb_init", "cpb_device_count", "cpb_synchronize", "cpb_matrix_create",
+    "cpb_matrix_create_device", "cpb_matrix_dims", "cpb_matrix_get", "cpb_matrix_destroy", "cpb_adjointpattern",
+    "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
+    "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
+    "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count",
+]
+
+
+class CpbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libchainb200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """Loads libchainb200.so (built in-tree by ``__graft_entry__.build()``); raises if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(this package has no CPU fallback)"
+            )
+        lib = ctypes.CDLL(_LIB_PATH)
+        lib.cpb_last_error.restype = ctypes.c_char_p
+        lib.cpb_launch_count.restype = ctypes.c_int64
+        vp, i64, dbl, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int
+        lib.cpb_matrix_create.argtypes = [i64, i64, i64, vp, vp, ctypes.POINTER(vp)]
+        lib.cpb_matrix_create_device.argtypes = [i64, i64, i64, vp, vp, ctypes.POINTER(vp)]
+        lib.cpb_matrix_dims.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        lib.cpb_matrix_get.argtypes = [vp, vp, vp]
+        lib.cpb_matrix_destroy.argtypes = [vp]
+        lib.cpb_matrix_destroy.restype = None
+        lib.cpb_adjointpattern.argtypes = [vp, ctypes.POINTER(vp)]
+        lib.cpb_oracle_create.argtypes = [vp, ctypes.POINTER(T.CModel), vp, i64, ctypes.POINTER(vp)]
+        lib.cpb_oracle_destroy.argtypes = [vp]
+        lib.cpb_oracle_destroy.restype = None
+        lib.cpb_oracle_query.argtypes = [vp, i64, vp, vp, vp, vp]
+        lib.cpb_oracle_query_device.argtypes = [vp, i64, vp, vp, vp]
+        lib.cpb_count_query.argtypes = [vp, i32, i64, vp, vp, vp]
+        lib.cpb_bound_stripe.argtypes = [vp, i64, ctypes.POINTER(dbl)]
+        lib.cpb_objective.argtypes = [vp, i32, i64, vp, ctypes.POINTER(dbl)]
+        lib.cpb_partition_stripe.argtypes = [vp, i32, ctypes.POINTER(T.CConstraint), dbl, i64, vp]
+        lib.cpb_pack_stripe.argtypes = [vp, vp, i32, ctypes.POINTER(T.CConstraint), dbl, i64, vp, ctypes.POINTER(i64), vp]
+        lib.cpb_profile_get.argtypes = [i32, vp, vp, vp, vp]
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise CpbError(rc, load_library().cpb_last_error().decode())
+
+
+def init(device: int = 0):
+    """One process per GPU: selects the CUDA device of this process."""
+    _check(load_library().cpb_init(int(device)))
+
+
+def synchronize():
+    _check(load_library().cpb_synchronize())
+
+
+def _arr(x) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=I64)
+
+
+def _p(a: Optional[np.ndarray]):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+# ------------------------------------------------------------------------------- matrices
+
+
+class DeviceMatrix:
+    """A SparseMatrixCSC pattern resident in HBM (``cpb_matrix``)."""
+
+    def __init__(self, handle, m, n, nnz):
+        self._h = handle
+        self.m, self.n, self._nnz = int(m), int(n), int(nnz)
+
+    @property
+    def nnz(self):
+        return self._nnz
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def to_host(self) -> T.SparseMatrixCSC:
+        colptr = np.empty(self.n + 1, dtype=I64)
+        rowval = np.empty(self.nnz, dtype=I64)
+        _check(load_library().cpb_matrix_get(self._h, _p(colptr), _p(rowval)))
+        return T.SparseMatrixCSC(self.m, self.n, colptr, rowval)
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.cpb_matrix_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_matrix(A) -> DeviceMatrix:
+    """Uploads ``A`` (host SparseMatrixCSC) once; pass the result wherever a matrix is expected."""
+    if isinstance(A, DeviceMatrix):
+        return A
+    h = ctypes.c_void_p()
+    _check(load_library().cpb_matrix_create(A.m, A.n, A.nnz, _p(A.colptr), _p(A.rowval), ctypes.byref(h)))
+    return DeviceMatrix(h, A.m, A.n, A.nnz)
+
+
+class _Scoped:
+    """device view of a matrix argument; frees the upload on exit if we made it"""
+
+    def __init__(self, A):
+        self.owned = not isinstance(A, DeviceMatrix)
+        self.dm = device_matrix(A)
+
+    def __enter__(self):
+        return self.dm
+
+    def __exit__(self, *exc):
+        if self.owned:
+            self.dm.close()
+
+
+def adjointpattern(A):
+    """util.jl:67-95.  Host matrix in -> host matrix out; DeviceMatrix in -> DeviceMatrix out."""
+    with _Scoped(A) as dm:
+        h = ctypes.c_void_p()
+        _check(load_library().cpb_adjointpattern(dm._h, ctypes.byref(h)))
+        out = DeviceMatrix(h, dm.n, dm.m, dm.nnz)
+        if isinstance(A, DeviceMatrix):
+            return out
+        res = out.to_host()
+        out.close()
+        return res
+
+
+# ------------------------------------------------------------------------------- oracles
+
+
+def _pi(Pi):
+    if Pi is None:
+        return None, 0
+    if not isinstance(Pi, T.SplitPartition):
+        raise TypeError("the row partition must be a SplitPartition (the reference has no MapPartition -> SplitPartition conversion either)")
+    return _arr(Pi.spl), Pi.K
+
+
+class StripeOracle:
+    """``oracle_stripe(hint, mdl, A[, Pi])``: callable ``ocl(j, j'[, k])``; arrays are batched on the GPU."""
+
+    def __init__(self, mdl, A, Pi=None, hint=None, w_tab=None):
+        f, con = T.split_constrained(mdl)
+        self.model, self.constraint = f, con
+        self._own = _Scoped(A)
+        self.dm = self._own.dm
+        self.Pi = Pi
+        tabs = T.model_tables(f, self.dm, con, Pi) if hasattr(f, "to_c") else {}
+        if w_tab is not None:
+            tabs["w_tab"] = int(w_tab)
+        cm, self._keep = f.to_c(**tabs)
+        spl, pK = _pi(Pi)
+        self._h = ctypes.c_void_p()
+        _check(load_library().cpb_oracle_create(self.dm._h, ctypes.byref(cm), _p(spl), pK, ctypes.byref(self._h)))
+
+    def query(self, j, jp, k=None) -> np.ndarray:
+        j, jp = _arr(np.atleast_1d(j)), _arr(np.atleast_1d(jp))
+        out = np.empty(len(j), dtype=np.float64)
+        _check(load_library().cpb_oracle_query(self._h, len(j), _p(j), _p(jp), None, ctypes.c_void_p(out.ctypes.data)))
+        if self.constraint.enabled:  # ConstrainedCostOracle (Costs.jl:141-147)
+            w = self.constraint.w_coef
+            dm_pos = None
+            width = w[0] + (jp - j) * w[1]
+            if w[2]:
+                dm_pos = self.dm.to_host().colptr
+                width = width + (dm_pos[jp - 1] - dm_pos[j - 1]) * w[2]
+            out = np.where(width <= self.constraint.w_max, out, np.inf)
+        return out
+
+    def __call__(self, j, jp, k=None):
+        r = self.query(j, jp, k)
+        if np.ndim(j) == 0:
+            v = r[0]
+            return v if (self.model.is_float or np.isinf(v)) else int(v)
+        return r
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.cpb_oracle_destroy(self._h)
+        self._h = None
+        if self._own is not None:
+            self._own.__exit__()
+            self._own = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def oracle_stripe(*args, **kwargs) -> StripeOracle:
+    """``oracle_stripe([hint,] mdl, A[, Pi]; ...)`` (Costs.jl:3-7).  The hint only selects a CPU data
+    structure in the reference; on the device one index serves all of them, so it is ignored."""
+    args = list(args)
+    hint = args.pop(0) if args and isinstance(args[0], T.AbstractHint) else None
+    mdl, A = args[0], args[1]
+    Pi = args[2] if len(args) > 2 else kwargs.get("Pi")
+    return StripeOracle(mdl, A, Pi, hint, w_tab=kwargs.get("w_tab"))
+
+
+def _as_oracle(A, mdl_or_ocl, Pi=None):
+    if isinstance(mdl_or_ocl, StripeOracle):
+        return mdl_or_ocl, False
+    return StripeOracle(mdl_or_ocl, A, Pi), True
+
+
+def bound_stripe(A, K, mdl_or_ocl, Pi=None):
+    """``bound_stripe(A, K[, Pi], mdl-or-ocl) -> (c_lo, c_hi)`` (Costs.jl:9-19 and the per-model methods)."""
+    ocl, own = _as_oracle(A, mdl_or_ocl, Pi)
+    try:
+        out = (ctypes.c_double * 2)()
+        _check(load_library().cpb_bound_stripe(ocl._h, int(K), out))
+        lo, hi = out[0], out[1]
+        return (lo, hi) if ocl.model.is_float else (int(lo), int(hi))
+    finally:
+        if own:
+            ocl.close()
+
+
+def _objective(total, A, Phi, mdl_or_ocl, Pi):
+    ocl, own = _as_oracle(A, mdl_or_ocl, Pi)
+    try:
+        out = ctypes.c_double()
+        spl = _arr(Phi.spl)
+        _check(load_library().cpb_objective(ocl._h, int(total), Phi.K, _p(spl), ctypes.byref(out)))
+        return out.value if ocl.model.is_float else int(out.value)
+    finally:
+        if own:
+            ocl.close()
+
+
+def bottleneck_value(A, Phi, mdl, Pi=None):
+    """Costs.jl:26-27 for a SplitPartition ``Phi``."""
+    return _objective(False, A, Phi, mdl, Pi)
+
+
+def total_value(A, Phi, mdl, Pi=None):
+    """Costs.jl:28-29 for a SplitPartition ``Phi``."""
+    return _objective(True, A, Phi, mdl, Pi)
+
+
+class _ColorArray:
+    """netcount(A)[j, j'] and friends (SparseColorArrays.jl); ``.query(j, j')`` batches on the GPU."""
+
+    def __init__(self, which, A):
+        self.which = which
+        self._own = _Scoped(A)
+        self.dm = self._own.dm
+
+    def query(self, j, jp) -> np.ndarray:
+        j, jp = _arr(np.atleast_1d(j)), _arr(np.atleast_1d(jp))
+        out = np.empty(len(j), dtype=I64)
+        _check(load_library().cpb_count_query(self.dm._h, self.which, len(j), _p(j), _p(jp), _p(out)))
+        return out
+
+    def __getitem__(self, idx):
+        j, jp = idx
+        r = self.query(j, jp)
+        return int(r[0]) if np.ndim(j) == 0 else r
+
+    __call__ = lambda self, j, jp: self[j, jp]
+
+
+def pincount(A, hint=None):
+    return _ColorArray(0, A)
+
+
+def netcount(A, hint=None):
+    return _ColorArray(1, A)
+
+
+def dianetcount(A, hint=None):
+    return _ColorArray(2, A)
+
+
+def selfnetcount(A, hint=None):
+    return _ColorArray(3, A)
+
+
+def selfpincount(A, hint=None):
+    return _ColorArray(4, A)
+
+
+# ------------------------------------------------------------------------------- solvers
+
+
+def partition_stripe(A, K, method, Pi=None, **kwargs) -> T.SplitPartition:
+    """``partition_stripe(A, K, method[, Pi]; kwargs...)`` -> ``SplitPartition(K, spl)``."""
+    K = int(K)
+    code, spec, eps = T.split_method_code(method)
+    spl = np.empty(K + 1, dtype=I64)
+    with _Scoped(A) as dm:
+        if spec is None:  # EquiSplitter
+            spec = T.AffineWorkModel(0, 0, 0)
+        ocl = StripeOracle(spec, dm, Pi)
+        try:
+            _check(load_library().cpb_partition_stripe(ocl._h, code, ctypes.byref(ocl.constraint), eps, K, _p(spl)))
+        finally:
+            ocl.close()
+    return T.SplitPartition(K, spl)
+
+
+def pack_stripe(A, method, Pi=None, n_nets=None, **kwargs) -> T.SplitPartition:
+    """``pack_stripe(A, method[, Pi]; kwargs...)`` -> ``SplitPartition(K, spl)`` with a free number of chunks."""
+    code, spec, rho, w_max = T.pack_method_code(method)
+    with _Scoped(A) as dm:
+        spl = np.empty(dm.n + 1, dtype=I64)
+        nn = np.zeros(max(dm.n, 1), dtype=I64)
+        Kout = ctypes.c_int64()
+        ocl = None
+        con = T.CConstraint()
+        if spec is not None:
+            ocl = StripeOracle(spec, dm, Pi)
+            con = ocl.constraint
+        try:
+            _check(load_library().cpb_pack_stripe(dm._h, ocl._h if ocl else None, code, ctypes.byref(con), rho, w_max, _p(spl),
+                                                   ctypes.byref(Kout), _p(nn)))
+        finally:
+            if ocl:
+                ocl.close()
+    K = Kout.value
+    if n_nets is not None:
+        n_nets[:] = [nn[:K].copy()]
+    return T.SplitPartition(K, spl[: K + 1].copy())
+
+
+def partition_plaid(A, K, method, adj_A=None, **kwargs):
+    """AlternatingPartitioner.jl:6-88: alternating stripe solves on ``A`` and ``adjointpattern(A)``; both
+    stay resident in HBM for the whole call."""
+    with _Scoped(A) as dA:
+        if isinstance(method, T.SymmetricPartitioner) and len(method.mtds) == 1:
+            Pi = partition_stripe(dA, K, method.mtds[0])
+            return Pi, Pi
+        own_adj = adj_A is None
+        dT = adjointpattern(dA) if own_adj else device_matrix(adj_A)
+        try:
+            if isinstance(method, T.DisjointPartitioner):
+                Phi = partition_stripe(dA, K, method.mtd)
+                Pi = partition_stripe(dT, K, method.mtd2, Phi)
+                return Pi, Phi
+            if isinstance(method, T.AlternatingPartitioner):
+                Phi = partition_stripe(dA, K, method.mtds[0])
+                Pi = partition_stripe(dT, K, method.mtds[1], Phi)
+                for i, mtd in enumerate(method.mtds[2:], start=1):
+                    if i % 2 == 1:
+                        Phi = partition_stripe(dA, K, mtd, Pi)
+                    else:
+                        Pi = partition_stripe(dT, K, mtd, Phi)
+                return Pi, Phi
+            if isinstance(method, T.SymmetricPartitioner):
+                Pi = partition_stripe(dA, K, method.mtds[0])
+                for i, mtd in enumerate(method.mtds[1:], start=1):
+                    Pi = partition_stripe(dA if i % 2 == 1 else dT, K, mtd, Pi)
+                return Pi, Pi
+            raise TypeError(f"partition_plaid: unsupported method {type(method).__name__}")
+        finally:
+            if own_adj or not isinstance(adj_A, DeviceMatrix):
+                dT.close()
+
+
+def pack_plaid(A, method, adj_A=None, **kwargs):
+    """AlternatingPacker.jl:6-53."""
+    with _Scoped(A) as dA:
+        own_adj = adj_A is None
+        dT = adjointpattern(dA) if own_adj else device_matrix(adj_A)
+        try:
+            if isinstance(method, T.DisjointPacker):
+                Phi = pack_stripe(dA, method.mtd)
+                Pi = pack_stripe(dT, method.mtd2, Phi)
+                return Pi, Phi
+            if isinstance(method, T.AlternatingPacker):
+                Phi = pack_stripe(dA, method.mtds[0])
+                Pi = pack_stripe(dT, method.mtds[1], Phi)
+                for i, mtd in enumerate(method.mtds[2:], start=1):
+                    if i % 2 == 1:
+                        Phi = pack_stripe(dA, mtd, Pi)
+                    else:
+                        Pi = pack_stripe(dT, mtd, Phi)
+                return Pi, Phi
+            if isinstance(method, T.SymmetricPacker):
+                Pi = pack_stripe(dA, method.mtds[0])
+                for i, mtd in enumerate(method.mtds[1:], start=1):
+                    Pi = pack_stripe(dA if i % 2 == 1 else dT, mtd, Pi)
+                return Pi, Pi
+            raise TypeError(f"pack_plaid: unsupported method {type(method).__name__}")
+        finally:
+            if own_adj or not isinstance(adj_A, DeviceMatrix):
+                dT.close()
+
+
+# ------------------------------------------------------------------------------- measurement hooks
+
+
+def profile_enable(on: bool = True):
+    load_library().cpb_profile_enable(int(bool(on)))
+
+
+def profile_reset():
+    load_library().cpb_profile_reset()
+
+
+def profile_get() -> dict:
+    cap = 64
+    names = ctypes.create_string_buffer(32 * cap)
+    ms = (ctypes.c_double * cap)()
+    launches = (ctypes.c_int64 * cap)()
+    nbytes = (ctypes.c_double * cap)()
+    k = load_library().cpb_profile_get(cap, names, ms, launches, nbytes)
+    out = {}
+    for t in range(k):
+        nm = names.raw[32 * t : 32 * t + 32].split(b"\0", 1)[0].decode()
+        out[nm] = dict(ms=ms[t], launches=int(launches[t]), bytes=nbytes[t])
+    return out
+
+
+def launch_count() -> int:
+    return int(load_library().cpb_launch_count())

@@ -1,0 +1,352 @@
+// capi.cu -- the C ABI of libchainb200.so (include/chainb200.h): argument checking, handle
+// ownership, error translation.  Nothing throws across this boundary.
+#include <algorithm>
+#include <mutex>
+#include "engine.cuh"
+#include "primitives.cuh"
+
+using namespace cpb;
+
+struct cpb_matrix { Matrix M; };
+struct cpb_oracle { std::unique_ptr<Oracle> O; };
+
+namespace cpb {
+
+static Context g_ctx;
+static std::mutex g_mu;
+static thread_local std::string g_err;
+
+struct PendingProf {
+  std::string name;
+  cudaEvent_t e0, e1;
+  double bytes;
+  i64 launches;
+};
+static std::vector<PendingProf> g_pending;
+
+Context& ctx() { return g_ctx; }
+
+static void init_context(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    throw Error(CPB_ERR_CUDA, std::string("no usable CUDA device (libchainb200 has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) throw Error(CPB_ERR_ARG, "device index out of range");
+  CPB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CPB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (g_ctx.stream && g_ctx.device != device) { cudaStreamDestroy(g_ctx.stream); g_ctx.stream = nullptr; }
+  g_ctx.device = device;
+  g_ctx.sm_count = prop.multiProcessorCount;
+  if (!g_ctx.stream) CPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  CPB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long thr = ~0ull;  // keep freed blocks cached in the pool
+  CPB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  g_ctx.ready = true;
+}
+
+void ensure_context() {
+  if (!g_ctx.ready) init_context(0);
+  else CPB_CUDA(cudaSetDevice(g_ctx.device));
+}
+
+ProfScope::ProfScope(const char* nm, double algorithmic_bytes) : name(nm), bytes(algorithmic_bytes), launches0(ctx().launches), on(ctx().profiling) {
+  if (on) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx().stream);
+  }
+}
+ProfScope::~ProfScope() {
+  if (on) {
+    cudaEventRecord(e1, ctx().stream);
+    g_pending.push_back({name, e0, e1, bytes, ctx().launches - launches0});
+  }
+}
+
+static void resolve_pending() {
+  if (g_pending.empty()) return;
+  cudaStreamSynchronize(g_ctx.stream);
+  for (auto& p : g_pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    ProfEntry& e = g_ctx.prof_entry(p.name);
+    e.ms += ms;
+    e.launches += p.launches;
+    e.bytes += p.bytes;
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+  }
+  g_pending.clear();
+}
+
+}  // namespace cpb
+
+#define CPB_API_BEGIN                         \
+  std::lock_guard<std::mutex> _lk(cpb::g_mu); \
+  try {
+#define CPB_API_END                      \
+  }                                      \
+  catch (const cpb::Error& e) {          \
+    cpb::g_err = e.what();               \
+    return e.code;                       \
+  }                                      \
+  catch (const std::exception& e) {      \
+    cpb::g_err = e.what();               \
+    return CPB_ERR_ARG;                  \
+  }                                      \
+  catch (...) {                          \
+    cpb::g_err = "unknown error";        \
+    return CPB_ERR_ARG;                  \
+  }                                      \
+  return CPB_OK;
+
+extern "C" {
+
+const char* cpb_last_error(void) { return cpb::g_err.c_str(); }
+int cpb_version(void) { return 100; }
+
+int cpb_init(int device) {
+  CPB_API_BEGIN
+  init_context(device);
+  CPB_API_END
+}
+
+int cpb_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+  return count;
+}
+
+int cpb_synchronize(void) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_API_END
+}
+
+static void matrix_from_device(Matrix& M, i64 m, i64 n, i64 nnz, const i64* d_colptr, const i64* d_rowval) {
+  CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
+  CPB_REQUIRE(nnz + n + 1 < ((i64)1 << 31) && m < ((i64)1 << 31) - 2 && n < ((i64)1 << 31) - 2, "matrix too large for the 32-bit device index");
+  M.m = m; M.n = n; M.N = nnz;
+  M.pos.alloc((size_t)n + 1);
+  M.row.alloc((size_t)nnz);
+  DBuf<u32> flags(1);
+  flags.zero();
+  narrow_minus1(d_colptr, M.pos.get(), (size_t)n + 1, 1, nnz + 1, flags.get());
+  narrow_minus1(d_rowval, M.row.get(), (size_t)nnz, 1, m, flags.get());
+  check_monotone(M.pos.get(), (size_t)n + 1, flags.get());
+  u32 hf = 0;
+  i64 ends[2] = {0, 0};
+  CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(&ends[0], d_colptr, sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(&ends[1], d_colptr + n, sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_REQUIRE((hf & 1u) == 0, "colptr/rowval entry out of range (expected 1-based indices)");
+  CPB_REQUIRE((hf & 2u) == 0, "colptr is not non-decreasing");
+  CPB_REQUIRE(ends[0] == 1 && ends[1] == nnz + 1, "colptr[1] must be 1 and colptr[n+1] must be nnz+1");
+}
+
+int cpb_matrix_create_device(int64_t m, int64_t n, int64_t nnz, const int64_t* d_colptr, const int64_t* d_rowval, cpb_matrix** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(out && d_colptr && (d_rowval || nnz == 0), "NULL argument");
+  auto h = std::make_unique<cpb_matrix>();
+  matrix_from_device(h->M, m, n, nnz, (const i64*)d_colptr, (const i64*)d_rowval);
+  *out = h.release();
+  CPB_API_END
+}
+
+int cpb_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, cpb_matrix** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(out && colptr && (rowval || nnz == 0), "NULL argument");
+  CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
+  ProfScope prof("h2d_matrix", (double)(nnz + n + 1) * 8.0);
+  DBuf<i64> dc((size_t)n + 1), dr((size_t)nnz);
+  CPB_CUDA(cudaMemcpyAsync(dc.get(), colptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+  if (nnz) CPB_CUDA(cudaMemcpyAsync(dr.get(), rowval, (size_t)nnz * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+  auto h = std::make_unique<cpb_matrix>();
+  matrix_from_device(h->M, m, n, nnz, dc.get(), dr.get());
+  *out = h.release();
+  CPB_API_END
+}
+
+int cpb_matrix_dims(const cpb_matrix* A, int64_t* m, int64_t* n, int64_t* nnz) {
+  CPB_API_BEGIN
+  CPB_REQUIRE(A, "NULL matrix");
+  if (m) *m = A->M.m;
+  if (n) *n = A->M.n;
+  if (nnz) *nnz = A->M.N;
+  CPB_API_END
+}
+
+int cpb_matrix_get(const cpb_matrix* A, int64_t* colptr_out, int64_t* rowval_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && colptr_out && (rowval_out || A->M.N == 0), "NULL argument");
+  const Matrix& M = A->M;
+  DBuf<i64> dc((size_t)M.n + 1), dr((size_t)M.N);
+  widen_plus(M.pos.get(), dc.get(), (size_t)M.n + 1, 1);
+  widen_plus(M.row.get(), dr.get(), (size_t)M.N, 1);
+  CPB_CUDA(cudaMemcpyAsync(colptr_out, dc.get(), ((size_t)M.n + 1) * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  if (M.N) CPB_CUDA(cudaMemcpyAsync(rowval_out, dr.get(), (size_t)M.N * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_API_END
+}
+
+void cpb_matrix_destroy(cpb_matrix* A) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  if (cpb::g_ctx.ready) cudaSetDevice(cpb::g_ctx.device);
+  delete A;
+}
+
+int cpb_adjointpattern(cpb_matrix* A, cpb_matrix** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && out, "NULL argument");
+  auto B = adjoint_pattern(A->M);
+  auto h = std::make_unique<cpb_matrix>();
+  h->M = std::move(*B);
+  *out = h.release();
+  CPB_API_END
+}
+
+int cpb_oracle_create(cpb_matrix* A, const cpb_model* mdl, const int64_t* pi_spl, int64_t pi_K, cpb_oracle** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && mdl && out, "NULL argument");
+  auto h = std::make_unique<cpb_oracle>();
+  h->O = oracle_create(A->M, mdl, pi_spl, pi_K);
+  *out = h.release();
+  CPB_API_END
+}
+
+void cpb_oracle_destroy(cpb_oracle* f) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  if (cpb::g_ctx.ready) cudaSetDevice(cpb::g_ctx.device);
+  delete f;
+}
+
+int cpb_oracle_query_device(cpb_oracle* f, int64_t Q, const int64_t* d_j, const int64_t* d_jp, double* d_cost_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && (Q == 0 || (d_j && d_jp && d_cost_out)), "NULL argument");
+  oracle_query(*f->O, Q, (const i64*)d_j, (const i64*)d_jp, d_cost_out);
+  CPB_API_END
+}
+
+int cpb_oracle_query(cpb_oracle* f, int64_t Q, const int64_t* j, const int64_t* jp, const int64_t* /*k*/, double* cost_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && Q >= 0 && (Q == 0 || (j && jp && cost_out)), "NULL argument");
+  if (Q > 0) {
+    const i64 n1 = f->O->A->n + 1;
+    for (i64 t = 0; t < Q; ++t) CPB_REQUIRE(j[t] >= 1 && jp[t] >= j[t] && jp[t] <= n1, "query out of range (need 1 <= j <= j' <= n+1)");
+    DBuf<i64> dj(Q), djp(Q);
+    DBuf<double> dc(Q);
+    CPB_CUDA(cudaMemcpyAsync(dj.get(), j, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+    CPB_CUDA(cudaMemcpyAsync(djp.get(), jp, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+    oracle_query(*f->O, Q, dj.get(), djp.get(), dc.get());
+    CPB_CUDA(cudaMemcpyAsync(cost_out, dc.get(), Q * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  }
+  CPB_API_END
+}
+
+int cpb_count_query(cpb_matrix* A, int which, int64_t Q, const int64_t* j, const int64_t* jp, int64_t* out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && Q >= 0 && (Q == 0 || (j && jp && out)), "NULL argument");
+  const i64 n1 = A->M.n + 1;
+  for (i64 t = 0; t < Q; ++t) CPB_REQUIRE(j[t] >= 1 && jp[t] >= j[t] && jp[t] <= n1, "query out of range (need 1 <= j <= j' <= n+1)");
+  DBuf<i64> dj(Q), djp(Q), dout(Q);
+  if (Q) {
+    CPB_CUDA(cudaMemcpyAsync(dj.get(), j, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+    CPB_CUDA(cudaMemcpyAsync(djp.get(), jp, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+  }
+  count_query(A->M, which, Q, dj.get(), djp.get(), dout.get());
+  if (Q) CPB_CUDA(cudaMemcpyAsync(out, dout.get(), Q * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_API_END
+}
+
+int cpb_bound_stripe(cpb_oracle* f, int64_t K, double out[2]) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && out, "NULL argument");
+  oracle_bound(*f->O, K, out);
+  CPB_API_END
+}
+
+int cpb_objective(cpb_oracle* f, int total, int64_t K, const int64_t* spl, double* out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && spl && out, "NULL argument");
+  *out = oracle_objective(*f->O, total != 0, K, spl);
+  CPB_API_END
+}
+
+int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && spl_out, "NULL argument");
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  switch (method) {
+    case CPB_SPLIT_DYNAMIC_BOTTLENECK: solve_dynamic(*f->O, false, con, K, spl_out); break;
+    case CPB_SPLIT_DYNAMIC_TOTAL: solve_dynamic(*f->O, true, con, K, spl_out); break;
+    case CPB_SPLIT_BISECT_COST: solve_bisect(*f->O, false, eps, K, spl_out); break;
+    case CPB_SPLIT_LAZY_BISECT_COST: solve_bisect(*f->O, true, eps, K, spl_out); break;
+    case CPB_SPLIT_EQUI: {  // EquiPartitioner.jl:3-9
+      const i64 n = f->O->A->n;
+      for (i64 k = 1; k <= K + 1; ++k) spl_out[k - 1] = (k - 1) * (n / K) + std::min(n % K, k - 1) + 1;
+      break;
+    }
+    default: throw Error(CPB_ERR_UNSUPPORTED, "unsupported partition_stripe method");
+  }
+  CPB_API_END
+}
+
+int cpb_pack_stripe(cpb_matrix* A, cpb_oracle* f, int method, const cpb_constraint* con, double rho, int64_t w_max,
+                    int64_t* spl_out, int64_t* K_out, int64_t* n_nets_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && spl_out && K_out, "NULL argument");
+  solve_pack(A->M, f ? f->O.get() : nullptr, method, con, rho, w_max, spl_out, K_out, n_nets_out);
+  CPB_API_END
+}
+
+int cpb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  cpb::g_ctx.profiling = on != 0;
+  return CPB_OK;
+}
+
+int cpb_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  if (cpb::g_ctx.ready) cpb::resolve_pending();
+  cpb::g_ctx.prof.clear();
+  cpb::g_ctx.launches = 0;
+  return CPB_OK;
+}
+
+int cpb_profile_get(int cap, char* names, double* ms, int64_t* launches, double* bytes) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  if (cpb::g_ctx.ready) cpb::resolve_pending();
+  int k = 0;
+  for (auto& p : cpb::g_ctx.prof) {
+    if (k >= cap) break;
+    std::memset(names + 32 * k, 0, 32);
+    std::strncpy(names + 32 * k, p.first.c_str(), 31);
+    ms[k] = p.second.ms;
+    launches[k] = p.second.launches;
+    bytes[k] = p.second.bytes;
+    ++k;
+  }
+  return k;
+}
+
+int64_t cpb_launch_count(void) { return cpb::g_ctx.launches; }
+
+}  // extern "C"

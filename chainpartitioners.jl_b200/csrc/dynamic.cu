@@ -1,0 +1,155 @@
+// dynamic.cu -- kernel family "dp_layer": DynamicBottleneckSplitter / DynamicTotalSplitter
+// (DynamicSplitter.jl:15-50; also the Reference*Splitter ground truth, ReferenceSplitter.jl:1-13).
+//
+//   cst[j', 1] = c(1, j', 1)
+//   cst[j', k] = min_j g(cst[j, k-1], c(j, j', k)),   g = max (bottleneck) or + (total),
+//   ties -> the LARGEST j (the reference updates on `<=`, DynamicSplitter.jl:40).
+//
+// One launch per layer k, one thread (bottleneck) or one warp/CTA (total) per j'.  For monotone
+// costs (beta >= 0, asserted by the reference's bound_stripe) the bottleneck recurrence needs no
+// scan over j: f_{k-1}(j) is non-decreasing and c(j, j') non-increasing in j, so the minimum sits at
+// their crossing, found by binary search; the reference's rightmost tie is recovered by a second
+// binary search on the previous row (SURVEY.md section 7 "hard parts", re-verified in tests).
+#include <algorithm>
+#include "engine.cuh"
+
+namespace cpb {
+
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_first(const __grid_constant__ DevOracle o, T* __restrict__ cst, u32* __restrict__ ptr) {
+  const u32 n1 = o.n + 1;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n1; t += stride) {
+    const u32 jp = (u32)t + 1;
+    cst[jp] = dev_cost<T>(o, 1, jp);
+    ptr[jp] = 1;
+  }
+}
+
+// bottleneck layer: a(j) = prev[j] (non-decreasing), b(j) = c(j, j') (non-increasing)
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_bottleneck(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
+                                                       u32* __restrict__ ptr, u32 jp_first) {
+  const u32 n1 = o.n + 1;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + jp_first; t <= n1; t += stride) {
+    const u32 jp = (u32)t;
+    // j* = min{ j in [1, jp] : a(j) >= b(j) }, jp + 1 if none
+    u32 lo = 1, hi = jp + 1;
+    while (lo < hi) {
+      const u32 mid = lo + ((hi - lo) >> 1);
+      if (prev[mid] >= dev_cost<T>(o, mid, jp)) hi = mid; else lo = mid + 1;
+    }
+    const u32 js = lo;
+    T v;
+    u32 arg;
+    if (js > jp) {  // a < b everywhere: h = b is minimised at the right end
+      arg = jp;
+      v = dev_cost<T>(o, jp, jp);
+    } else {
+      const T va = prev[js];
+      bool right = true;
+      T vb = va;
+      if (js > 1) {
+        vb = dev_cost<T>(o, js - 1, jp);
+        right = va <= vb;
+      }
+      if (right) {
+        v = va;
+        // largest j in [js, jp] with a(j) <= v
+        u32 l2 = js, h2 = jp;
+        while (l2 < h2) {
+          const u32 mid = l2 + ((h2 - l2 + 1) >> 1);
+          if (prev[mid] <= v) l2 = mid; else h2 = mid - 1;
+        }
+        arg = l2;
+      } else {
+        v = vb;
+        arg = js - 1;
+      }
+    }
+    cur[jp] = v;
+    ptr[jp] = arg;
+  }
+}
+
+// total layer, one warp per j': scan of all j in [1, j'] with a rightmost-argmin reduction.
+// (O(n^2) oracle queries per layer; the monotone divide & conquer version replaces it for large n.)
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
+                                                  u32* __restrict__ ptr, u32 jp_first) {
+  const u32 n1 = o.n + 1;
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t t = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + jp_first; t <= n1; t += warps) {
+    const u32 jp = (u32)t;
+    T best = 0;
+    u32 arg = 0;
+    for (u32 j = 1 + lane; j <= jp; j += 32) {
+      const T c = prev[j] + dev_cost<T>(o, j, jp);
+      if (arg == 0 || c <= best) { best = c; arg = j; }  // ascending j within a lane: `<=` keeps the largest
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const T ob = __shfl_down_sync(0xffffffffu, best, off);
+      const u32 oa = __shfl_down_sync(0xffffffffu, arg, off);
+      if (oa != 0 && (arg == 0 || ob < best || (ob == best && oa > arg))) { best = ob; arg = oa; }
+    }
+    if (lane == 0) { cur[jp] = best; ptr[jp] = arg; }
+  }
+}
+
+__global__ void k_dp_unravel(const u32* __restrict__ ptr, u32 n2, int K, u32 n1, i64* __restrict__ spl) {
+  // DynamicSplitter.jl:89-99
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    spl[K] = n1;
+    for (int k = K; k >= 1; --k) spl[k - 1] = ptr[(size_t)(k - 1) * n2 + (u32)spl[k]];
+  }
+}
+
+template <class T> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* h_spl_out) {
+  const Matrix& A = *f.A;
+  const u32 n1 = (u32)A.n + 1, n2 = n1 + 1;
+  CPB_REQUIRE((double)K * n2 * 4.0 < 64e9, "DP pointer table would not fit");
+  ProfScope prof("dp_layer");
+  DBuf<T> rowa(n2), rowb(n2);
+  DBuf<u32> ptr((size_t)K * n2);
+  DBuf<i64> spl(K + 1);
+  const unsigned grid = (unsigned)std::min<size_t>(((size_t)n1 + 255) / 256, (size_t)ctx().sm_count * 8);
+  CPB_LAUNCH(k_dp_first<T>, grid, 256, 0, f.dev, rowa.get(), ptr.get());
+  T* prev = rowa.get();
+  T* cur = rowb.get();
+  for (i64 k = 2; k <= K; ++k) {
+    const u32 jp_first = (k == K) ? n1 : 1;  // DynamicSplitter.jl:34
+    u32* p = ptr.get() + (size_t)(k - 1) * n2;
+    if (!total) {
+      const unsigned g = (k == K) ? 1 : grid;
+      CPB_LAUNCH(k_dp_bottleneck<T>, g, 256, 0, f.dev, prev, cur, p, jp_first);
+    } else {
+      const size_t rows = (size_t)n1 - jp_first + 1;
+      const unsigned g = (unsigned)std::min<size_t>((rows * 32 + 255) / 256, (size_t)ctx().sm_count * 8);
+      CPB_LAUNCH(k_dp_total<T>, g, 256, 0, f.dev, prev, cur, p, jp_first);
+    }
+    std::swap(prev, cur);
+  }
+  CPB_LAUNCH(k_dp_unravel, 1, 32, 0, ptr.get(), n2, (int)K, n1, spl.get());
+  CPB_CUDA(cudaMemcpyAsync(h_spl_out, spl.get(), (K + 1) * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  if (con && con->enabled) throw Error(CPB_ERR_UNSUPPORTED, "weight-constrained dynamic splitters are not built yet");
+  if (f.dev.kind == CPB_MODEL_BLOCK || f.dev.kind == CPB_MODEL_COLBLOCK)
+    throw Error(CPB_ERR_UNSUPPORTED, "dynamic splitters need an affine random-access oracle");
+  if (!total) {
+    // the crossing search needs monotone costs: the same beta >= 0 the reference asserts in bound_stripe
+    for (int t = 1; t <= 4; ++t)
+      if (f.mdl.coef[t] < 0 && !(f.mdl.kind == CPB_MODEL_MONOSYM && t == 4))
+        throw Error(CPB_ERR_UNSUPPORTED, "bottleneck DP on the device needs non-negative beta coefficients");
+    if (f.mdl.kind == CPB_MODEL_SYMCONN || f.mdl.kind == CPB_MODEL_HYPEREDGE || f.mdl.kind == CPB_MODEL_SYMEDGECUT)
+      throw Error(CPB_ERR_UNSUPPORTED, "bottleneck DP on the device needs a monotone cost model");
+  }
+  if (f.dev.is_float) dynamic_T<double>(f, total, K, h_spl_out); else dynamic_T<i64>(f, total, K, h_spl_out);
+}
+
+}  // namespace cpb

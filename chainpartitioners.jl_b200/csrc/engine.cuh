@@ -1,0 +1,167 @@
+// engine.cuh -- host-side objects behind the opaque C handles and the device-side cost oracle.
+#pragma once
+#include <memory>
+#include "common.cuh"
+#include "wavelet.cuh"
+#include "../../include/chainb200.h"
+
+namespace cpb {
+
+// ---- cpb_matrix: CSC pattern in HBM, 32-bit, 0-based ------------------------------------------
+struct Matrix {
+  i64 m = 0, n = 0, N = 0;
+  DBuf<u32> pos;  // [n+1] offsets, pos[n] == N
+  DBuf<u32> row;  // [N] row indices
+};
+
+// ---- a dominance ("rank") structure: points sorted by x + wavelet matrix over their link value
+struct RankStruct {
+  WaveletMatrix wm;
+  DBuf<u32> P_own;         // P[x], x = 0..n+1  (own storage)
+  const u32* P = nullptr;  // indexable by 1 <= x <= n+1
+  DevRank dev() const { return DevRank{wm.dev(), P}; }
+};
+
+// SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
+enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
+std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
+// For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
+
+// ---- device-side oracle ------------------------------------------------------------------------
+struct DevOracle {
+  int kind;
+  int is_float;
+  u32 n, m;
+  const u32* pos;      // [n+1] 0-based
+  const u32* overpos;  // [n+1] prefix of max(deg - delta_pins, 0)   (MONOSYM)
+  DevRank net, dianet, selfnet, selfpin;
+  const i64* env;      // segment tree of packed (lo, hi) (ENVELOPE); envH = height
+  int envH;
+  double cf[5];
+  i64 ci[5];
+  // tabulated column-block components (COLBLOCK): alpha_col[w], beta_col[w], w = 0..w_tab
+  const double* tab_alpha_f;
+  const double* tab_beta_f;
+  const i64* tab_alpha_i;
+  const i64* tab_beta_i;
+  int w_tab;
+};
+
+struct Oracle {
+  Matrix* A = nullptr;
+  cpb_model mdl{};
+  std::vector<double> h_alpha_col, h_beta_col, h_beta_row;  // host copies of tables
+  std::unique_ptr<RankStruct> net, dianet, selfnet, selfpin;
+  DBuf<u32> overpos;
+  DBuf<i64> env;
+  int envH = 0;
+  DBuf<double> tab_f;  // alpha_col | beta_col (double)
+  DBuf<i64> tab_i;
+  // BLOCK model: row partition on device
+  DBuf<u32> pi_asg;     // [m] 0-based part of each row
+  DBuf<u32> pi_size;    // [K_pi] part sizes
+  std::vector<i64> h_pi_spl;
+  i64 pi_K = 0;
+  DevOracle dev{};
+};
+
+std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int64_t* pi_spl, i64 pi_K);
+void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost);
+void oracle_bound(Oracle& f, i64 K, double out[2]);
+double oracle_objective(Oracle& f, bool total, i64 K, const int64_t* h_spl);
+void count_query(Matrix& A, int which, i64 Q, const i64* d_j, const i64* d_jp, i64* d_out);
+
+// solvers (bisect.cu / dynamic.cu / chunk.cu)
+void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out);
+void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out);
+void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, double rho, i64 w_max, int64_t* h_spl_out,
+                int64_t* K_out, int64_t* n_nets_out);
+std::unique_ptr<Matrix> adjoint_pattern(const Matrix& A);
+
+#ifdef __CUDACC__
+// --- cost evaluation on the device: left-to-right sums, no FMA (compiled with -fmad=false) -----
+template <class T> struct CoefOf;
+template <> struct CoefOf<i64> {
+  static __device__ __forceinline__ i64 get(const DevOracle& o, int t) { return o.ci[t]; }
+  static __device__ __forceinline__ i64 alpha_col(const DevOracle& o, u32 w) { return o.tab_alpha_i[w]; }
+  static __device__ __forceinline__ i64 beta_col(const DevOracle& o, u32 w) { return o.tab_beta_i[w]; }
+};
+template <> struct CoefOf<double> {
+  static __device__ __forceinline__ double get(const DevOracle& o, int t) { return o.cf[t]; }
+  static __device__ __forceinline__ double alpha_col(const DevOracle& o, u32 w) { return o.tab_alpha_f[w]; }
+  static __device__ __forceinline__ double beta_col(const DevOracle& o, u32 w) { return o.tab_beta_f[w]; }
+};
+
+// nets(j,j') = #distinct rows in columns [j,j')  = #{q < pos[j'] : prev_q < j} - pos[j]   (1-based j, j')
+__device__ __forceinline__ u32 dev_netcount(const DevRank& r, u32 j, u32 jp) {
+  const u32 e = __ldg(r.P + jp);
+  const u32 s = __ldg(r.P + j);
+  return wm_rank_lt(r.wm, e, j) - s;
+}
+
+__device__ __forceinline__ void dev_envelope(const DevOracle& o, u32 j, u32 jp, i64& lo, i64& hi) {
+  // EnvelopeMatrices.jl:35-56 on a packed (lo << 32 | hi) implicit segment tree
+  lo = (i64)o.m + 1;
+  hi = 0;
+  i64 a = (((i64)1 << o.envH) - 1) + (i64)j;
+  i64 b = (((i64)1 << o.envH) - 1) + ((i64)jp - 1);
+  while (a <= b) {
+    const i64 l = __ldg(o.env + a), r = __ldg(o.env + b);
+    lo = min(lo, min(l >> 32, r >> 32));
+    hi = max(hi, max(l & 0xffffffffll, r & 0xffffffffll));
+    a = (a + 1) >> 1;
+    b = (b - 1) >> 1;
+  }
+}
+
+template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32 j, u32 jp) {
+  using C = CoefOf<T>;
+  const i64 nv = (i64)jp - (i64)j;
+  const i64 np = (i64)__ldg(o.pos + (jp - 1)) - (i64)__ldg(o.pos + (j - 1));
+  switch (o.kind) {
+    case CPB_MODEL_WORK:  // WorkCosts.jl:17,30-35
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2);
+    case CPB_MODEL_CONNECTIVITY: {  // ConnectivityCosts.jl:20,58-64
+      const i64 d = dev_netcount(o.net, j, jp);
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)d * C::get(o, 3);
+    }
+    case CPB_MODEL_COLBLOCK: {  // BlockCosts.jl:17
+      const i64 d = dev_netcount(o.net, j, jp);
+      return C::alpha_col(o, (u32)nv) + (T)d * C::beta_col(o, (u32)nv);
+    }
+    case CPB_MODEL_MONOSYM: {  // MonotonizedSymmetricConnectivityCosts.jl:33,107-113
+      const i64 w = (i64)__ldg(o.overpos + (jp - 1)) - (i64)__ldg(o.overpos + (j - 1));
+      const i64 d = dev_netcount(o.dianet, j, jp);
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)w * C::get(o, 2) + (T)d * C::get(o, 3);
+    }
+    case CPB_MODEL_SYMCONN: {  // SymmetricConnectivityCosts.jl:19,47-55
+      const i64 d = dev_netcount(o.net, j, jp);
+      const i64 r = (i64)dev_netcount(o.dianet, j, jp) - nv;
+      const i64 l = d - r;
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)l * C::get(o, 3) + (T)r * C::get(o, 4);
+    }
+    case CPB_MODEL_HYPEREDGE: {  // HyperedgeCutCosts.jl:21,44-51
+      const i64 d = dev_netcount(o.net, j, jp);
+      const i64 l = rank_count_ge(o.selfnet, j, jp);
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)l * C::get(o, 3) + (T)(d - l) * C::get(o, 4);
+    }
+    case CPB_MODEL_SYMEDGECUT: {  // SymmetricEdgeCutCosts.jl:18,37-43
+      const i64 l = rank_count_ge(o.selfpin, j, jp);
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)l * C::get(o, 2) + (T)(np - l) * C::get(o, 3);
+    }
+    case CPB_MODEL_ENVELOPE: {  // EnvelopeCosts.jl:20,66-73
+      i64 lo, hi;
+      dev_envelope(o, j, jp, lo, hi);
+      const i64 d = max(hi - lo, (i64)0);
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)d * C::get(o, 3);
+    }
+  }
+  return T(0);
+}
+
+// cost <= c with the exact mixed Int64/Float64 comparison Julia performs (costs are < 2^53)
+__device__ __forceinline__ bool cost_leq(i64 x, double c) { return (double)x <= c; }
+__device__ __forceinline__ bool cost_leq(double x, double c) { return x <= c; }
+#endif
+
+}  // namespace cpb

@@ -1,0 +1,221 @@
+// links.cu -- kernel family "build_links": turns the CSC pattern into the point sets whose 2-D
+// dominance counts are the reference's color arrays (SparseColorArrays.jl), plus adjointpattern.
+//
+// The reference walks the nonzeros column by column with a per-row "last seen" array hst[m]
+// (NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318) -- a
+// sequential sweep with a cache-missing gather.  Here the same quantities come from ONE stable
+// radix sort of the nonzeros by row (i.e. the transpose order): the previous column holding the
+// same row is simply the left neighbour inside the row run, and first/last columns are the run ends.
+#include "engine.cuh"
+#include "primitives.cuh"
+
+namespace cpb {
+
+// sorted (row, q) pairs of a matrix: the transpose order
+struct TransposeOrder {
+  DBuf<u32> k0, v0, k1, v1;
+  u32* keys = nullptr;  // rows, ascending; ties keep CSC order (ascending column)
+  u32* q = nullptr;     // CSC position of each entry
+};
+
+static void transpose_order(const u32* row, size_t N, u64 max_row, TransposeOrder& t) {
+  t.k0.alloc(N); t.v0.alloc(N); t.k1.alloc(N); t.v1.alloc(N);
+  if (N) CPB_CUDA(cudaMemcpyAsync(t.k0.get(), row, N * sizeof(u32), cudaMemcpyDeviceToDevice, ctx().stream));
+  iota_u32(t.v0.get(), N);
+  const int which = radix_sort_pairs(t.k0.get(), t.v0.get(), t.k1.get(), t.v1.get(), N, bits_for(max_row));
+  t.keys = which ? t.k1.get() : t.k0.get();
+  t.q = which ? t.v1.get() : t.v0.get();
+}
+
+// prev[q] = 1-based previous column holding the same row, 0 if none
+__global__ void k_link_prev(const u32* __restrict__ sk, const u32* __restrict__ sq, const u32* __restrict__ colidx,
+                            u32* __restrict__ prev, size_t N) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
+    u32 link = 0;
+    if (p > 0 && sk[p - 1] == sk[p]) link = __ldg(colidx + sq[p - 1]) + 1u;
+    prev[sq[p]] = link;
+  }
+}
+
+__global__ void k_head_flags(const u32* __restrict__ sk, size_t N, u32* __restrict__ flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p <= N; p += stride)
+    flags[p] = (p < N && (p == 0 || sk[p - 1] != sk[p])) ? 1u : 0u;
+}
+
+// one point per non-empty row: x = last column, val = first column (both 1-based)
+__global__ void k_selfnet_points(const u32* __restrict__ sk, const u32* __restrict__ sq, const u32* __restrict__ colidx,
+                                 const u32* __restrict__ headscan, size_t N, u32* __restrict__ x, u32* __restrict__ val) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
+    const bool head = (p == 0) || (sk[p - 1] != sk[p]);
+    const bool tail = (p + 1 == N) || (sk[p + 1] != sk[p]);
+    if (head | tail) {
+      const u32 run = headscan[p] - (head ? 0u : 1u);
+      const u32 c = __ldg(colidx + sq[p]) + 1u;
+      if (head) val[run] = c;
+      if (tail) x[run] = c;
+    }
+  }
+}
+
+// one point per nonzero (i, j): x = max(i, j), val = min(i, j) (1-based)
+__global__ void k_selfpin_points(const u32* __restrict__ row, const u32* __restrict__ colidx, size_t N, u32* __restrict__ x,
+                                 u32* __restrict__ val) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+    const u32 i = row[q] + 1u, j = colidx[q] + 1u;
+    x[q] = max(i, j);
+    val[q] = min(i, j);
+  }
+}
+
+// add[j] = 1 iff column j lacks its diagonal entry (rows sorted within a column); add[n] = 0
+__global__ void k_diag_missing(const u32* __restrict__ pos, const u32* __restrict__ row, u32 n, u32* __restrict__ add) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += stride) {
+    u32 a = 0;
+    if (j < n) {
+      u32 lo = pos[j], hi = pos[j + 1];
+      while (lo < hi) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (row[mid] < (u32)j) lo = mid + 1; else hi = mid;
+      }
+      a = (lo < pos[j + 1] && row[lo] == (u32)j) ? 0u : 1u;
+    }
+    add[j] = a;
+  }
+}
+
+__global__ void k_aug_pos(const u32* __restrict__ pos, const u32* __restrict__ addscan, u32 n, u32* __restrict__ pos2) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += stride) pos2[j] = pos[j] + addscan[j];
+}
+
+__global__ void k_aug_rows(const u32* __restrict__ row, const u32* __restrict__ colidx, const u32* __restrict__ addscan, size_t N,
+                           u32* __restrict__ row2) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) row2[q + addscan[colidx[q]]] = row[q];
+}
+
+__global__ void k_aug_diag(const u32* __restrict__ pos2, const u32* __restrict__ add, u32 n, u32* __restrict__ row2) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    if (add[j]) row2[pos2[j + 1] - 1] = (u32)j;  // virtual (j, j) entry appended to its column (:87-91)
+}
+
+static unsigned grid_for(size_t n) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 32)); }
+
+static u32 read_u32(const u32* d) {
+  u32 h = 0;
+  CPB_CUDA(cudaMemcpyAsync(&h, d, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return h;
+}
+
+// links over (pos, row) with ncol columns and N entries -> wavelet matrix over prev[]
+static void build_net_like(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, RankStruct& rs) {
+  DBuf<u32> prev(N), colidx(N);
+  {
+    ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
+    TransposeOrder t;
+    transpose_order(row, N, nrow ? nrow - 1 : 0, t);
+    expand_columns(pos, ncol, colidx.get(), N);
+    if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx.get(), prev.get(), N);
+  }
+  rs.wm.build(prev.get(), colidx.get(), N, ncol);  // colidx is dead: reuse as ping-pong scratch
+}
+
+// sorts points by x, builds P and the wavelet matrix over val
+static void build_from_points(DBuf<u32>& x, DBuf<u32>& val, size_t npts, u32 ncol, RankStruct& rs) {
+  DBuf<u32> x2(npts), val2(npts);
+  const int which = radix_sort_pairs(x.get(), val.get(), x2.get(), val2.get(), npts, bits_for(ncol));
+  u32* xs = which ? x2.get() : x.get();
+  u32* vs = which ? val2.get() : val.get();
+  u32* other = which ? val.get() : val2.get();
+  rs.P_own.alloc((size_t)ncol + 2);
+  segment_starts(xs, npts, rs.P_own.get(), ncol + 1);
+  rs.P = rs.P_own.get();
+  rs.wm.build(vs, other, npts, ncol);
+}
+
+std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which) {
+  auto rs = std::make_unique<RankStruct>();
+  const size_t N = (size_t)A.N;
+  const u32 n = (u32)A.n, m = (u32)A.m;
+  switch (which) {
+    case RANK_NET: {
+      build_net_like(A.pos.get(), A.row.get(), m, n, N, *rs);
+      rs->P = A.pos.get() - 1;  // P[x] = pos[x-1] = #{nonzeros in columns < x}
+      break;
+    }
+    case RANK_DIANET: {
+      CPB_REQUIRE(A.m >= A.n, "dianetcount needs m >= n");
+      DBuf<u32> add((size_t)n + 1), colidx(N);
+      CPB_LAUNCH(k_diag_missing, grid_for((size_t)n + 1), 256, 0, A.pos.get(), A.row.get(), n, add.get());
+      DBuf<u32> addscan((size_t)n + 1);
+      exclusive_scan_u32(add.get(), addscan.get(), (size_t)n + 1);
+      const size_t N2 = N + read_u32(addscan.get() + n);
+      rs->P_own.alloc((size_t)n + 2);
+      u32* pos2 = rs->P_own.get() + 1;
+      CPB_CUDA(cudaMemsetAsync(rs->P_own.get(), 0, sizeof(u32), ctx().stream));
+      CPB_LAUNCH(k_aug_pos, grid_for((size_t)n + 1), 256, 0, A.pos.get(), addscan.get(), n, pos2);
+      DBuf<u32> row2(N2);
+      expand_columns(A.pos.get(), n, colidx.get(), N);
+      if (N) CPB_LAUNCH(k_aug_rows, grid_for(N), 256, 0, A.row.get(), colidx.get(), addscan.get(), N, row2.get());
+      if (n) CPB_LAUNCH(k_aug_diag, grid_for(n), 256, 0, pos2, add.get(), n, row2.get());
+      build_net_like(pos2, row2.get(), m, n, N2, *rs);
+      rs->P = rs->P_own.get();  // P[x] = pos2[x-1]
+      break;
+    }
+    case RANK_SELFNET: {
+      TransposeOrder t;
+      transpose_order(A.row.get(), N, m ? m - 1 : 0, t);
+      DBuf<u32> colidx(N), flags(N + 1), headscan(N + 1);
+      expand_columns(A.pos.get(), n, colidx.get(), N);
+      CPB_LAUNCH(k_head_flags, grid_for(N + 1), 256, 0, t.keys, N, flags.get());
+      exclusive_scan_u32(flags.get(), headscan.get(), N + 1);
+      const size_t R = read_u32(headscan.get() + N);
+      DBuf<u32> x(R), val(R);
+      if (N) CPB_LAUNCH(k_selfnet_points, grid_for(N), 256, 0, t.keys, t.q, colidx.get(), headscan.get(), N, x.get(), val.get());
+      build_from_points(x, val, R, n, *rs);
+      break;
+    }
+    case RANK_SELFPIN: {
+      CPB_REQUIRE(A.m <= A.n, "selfpincount needs row indices <= n");
+      DBuf<u32> colidx(N), x(N), val(N);
+      expand_columns(A.pos.get(), n, colidx.get(), N);
+      if (N) CPB_LAUNCH(k_selfpin_points, grid_for(N), 256, 0, A.row.get(), colidx.get(), N, x.get(), val.get());
+      build_from_points(x, val, N, n, *rs);
+      break;
+    }
+    default: throw Error(-1, "bad rank structure kind");
+  }
+  return rs;
+}
+
+// adjointpattern(A) (util.jl:67-95): stable sort by row = CSC of the transpose
+__global__ void k_gather_cols(const u32* __restrict__ sq, const u32* __restrict__ colidx, size_t N, u32* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) out[p] = colidx[sq[p]];
+}
+
+std::unique_ptr<Matrix> adjoint_pattern(const Matrix& A) {
+  auto B = std::make_unique<Matrix>();
+  B->m = A.n; B->n = A.m; B->N = A.N;
+  const size_t N = (size_t)A.N;
+  ProfScope prof("adjointpattern", (double)(2 * N + A.n + A.m + 2) * 4.0);
+  TransposeOrder t;
+  transpose_order(A.row.get(), N, A.m ? A.m - 1 : 0, t);
+  DBuf<u32> colidx(N);
+  expand_columns(A.pos.get(), (u32)A.n, colidx.get(), N);
+  B->row.alloc(N);
+  if (N) CPB_LAUNCH(k_gather_cols, grid_for(N), 256, 0, t.q, colidx.get(), N, B->row.get());
+  B->pos.alloc((size_t)A.m + 1);
+  // pos'[i] = first sorted index with row >= i, i = 0..m
+  segment_starts(t.keys, N, B->pos.get(), (u32)A.m);
+  return B;
+}
+
+}  // namespace cpb

@@ -1,0 +1,279 @@
+// primitives.cu -- device-wide scan, stable radix sort and small index kernels (sm_100a).
+#include <algorithm>
+#include "primitives.cuh"
+
+namespace cpb {
+
+static constexpr unsigned FULL = 0xffffffffu;
+
+int bits_for(u64 v) {
+  int b = 1;
+  while (b < 64 && (v >> b) != 0) ++b;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------ scan
+static constexpr int SC_THREADS = 256;
+static constexpr int SC_CHUNK = SC_THREADS * 4;  // items per block-scan step
+static constexpr int SC_TILE = SC_CHUNK * 8;     // items per CTA
+
+// exclusive scan of one value per thread across a 256-thread CTA; returns the exclusive prefix,
+// `total` receives the CTA-wide sum.  smem: 8 words.
+__device__ __forceinline__ u32 block_excl_scan_256(u32 x, u32* smem, u32& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u32 inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 y = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  u32 wbase = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    u32 s = smem[k];
+    if (k < w) wbase += s;
+    tot += s;
+  }
+  __syncthreads();
+  total = tot;
+  return wbase + inc - x;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_reduce(const u32* __restrict__ in, u32* __restrict__ sums, size_t n) {
+  __shared__ u32 sm[8];
+  const size_t b0 = (size_t)blockIdx.x * SC_TILE;
+  const size_t b1 = min(n, b0 + (size_t)SC_TILE);
+  u32 s = 0;
+  for (size_t i = b0 + threadIdx.x; i < b1; i += SC_THREADS) s += in[i];
+  u32 tot;
+  block_excl_scan_256(s, sm, tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+// scans [b0, b1) with starting carry; safe for in == out
+__device__ __forceinline__ void scan_range(const u32* in, u32* out, size_t b0, size_t b1, u32 carry, u32* sm) {
+  for (size_t c0 = b0; c0 < b1; c0 += SC_CHUNK) {
+    const size_t i0 = c0 + (size_t)threadIdx.x * 4;
+    u32 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < b1) ? in[i0 + k] : 0u;
+    u32 tsum = v[0] + v[1] + v[2] + v[3];
+    u32 tot;
+    u32 ex = block_excl_scan_256(tsum, sm, tot) + carry;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < b1) out[i0 + k] = ex;
+      ex += v[k];
+    }
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_small(const u32* in, u32* out, size_t n) {
+  __shared__ u32 sm[8];
+  scan_range(in, out, 0, n, 0u, sm);
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_apply(const u32* in, u32* out, const u32* __restrict__ tile_off, size_t n) {
+  __shared__ u32 sm[8];
+  const size_t b0 = (size_t)blockIdx.x * SC_TILE;
+  const size_t b1 = min(n, b0 + (size_t)SC_TILE);
+  scan_range(in, out, b0, b1, tile_off[blockIdx.x], sm);
+}
+
+void exclusive_scan_u32(const u32* in, u32* out, size_t n) {
+  if (n == 0) return;
+  if (n <= (size_t)SC_TILE * 8) {
+    CPB_LAUNCH(k_scan_small, 1, SC_THREADS, 0, in, out, n);
+    return;
+  }
+  const size_t tiles = (n + SC_TILE - 1) / SC_TILE;
+  DBuf<u32> sums(tiles);
+  CPB_LAUNCH(k_scan_reduce, (unsigned)tiles, SC_THREADS, 0, in, sums.get(), n);
+  exclusive_scan_u32(sums.get(), sums.get(), tiles);
+  CPB_LAUNCH(k_scan_apply, (unsigned)tiles, SC_THREADS, 0, in, out, sums.get(), n);
+}
+
+// ------------------------------------------------------------------------------ radix sort
+static constexpr int RS_THREADS = 256;
+static constexpr int RS_IPT = 16;
+static constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 keys per CTA, 512 per warp
+static constexpr u32 RS_INVALID = 0xffffffffu;
+
+// per-tile digit histogram, stored digit-major: hist[d * tiles + tile]
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u32* __restrict__ keys, size_t n, int shift, u32* __restrict__ hist, u32 tiles) {
+  __shared__ u32 h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t base = (size_t)blockIdx.x * RS_TILE + (size_t)w * (32 * RS_IPT);
+#pragma unroll 4
+  for (int r = 0; r < RS_IPT; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    const u32 d = (i < n) ? ((keys[i] >> shift) & 255u) : RS_INVALID;
+    const unsigned m = __match_any_sync(FULL, d);
+    if (d != RS_INVALID && lane == __ffs(m) - 1) atomicAdd(&h[d], (u32)__popc(m));
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// stable scatter: rank within warp by match_any rounds, warp bases by a per-digit walk over the
+// 8 warps, tile bases from the scanned histogram.
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
+                                                           u32* __restrict__ keys_out, u32* __restrict__ vals_out, size_t n,
+                                                           int shift, const u32* __restrict__ offs, u32 tiles) {
+  __shared__ u32 wh[8][256];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < 8 * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * RS_TILE + (size_t)w * (32 * RS_IPT);
+  u32 key[RS_IPT], val[RS_IPT], rnk[RS_IPT];
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    const bool ok = i < n;
+    key[r] = ok ? keys_in[i] : 0u;
+    val[r] = ok ? vals_in[i] : 0u;
+  }
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    const u32 d = (i < n) ? ((key[r] >> shift) & 255u) : RS_INVALID;
+    const unsigned m = __match_any_sync(FULL, d);
+    const int leader = __ffs(m) - 1;
+    u32 old = 0;
+    if (d != RS_INVALID && lane == leader) {
+      old = wh[w][d];
+      wh[w][d] = old + (u32)__popc(m);
+    }
+    __syncwarp();
+    old = __shfl_sync(FULL, old, leader);
+    rnk[r] = old + (u32)__popc(m & lt);
+  }
+  __syncthreads();
+  {
+    const u32 d = tid;
+    u32 run = offs[(size_t)d * tiles + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const u32 t = wh[k][d];
+      wh[k][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    if (i < n) {
+      const u32 d = (key[r] >> shift) & 255u;
+      const u32 dst = wh[w][d] + rnk[r];
+      keys_out[dst] = key[r];
+      vals_out[dst] = val[r];
+    }
+  }
+}
+
+int radix_sort_pairs(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
+  if (n == 0) return 0;
+  const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+  DBuf<u32> hist((size_t)256 * tiles);
+  int which = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    u32* ki = which ? keys_tmp : keys;
+    u32* vi = which ? vals_tmp : vals;
+    u32* ko = which ? keys : keys_tmp;
+    u32* vo = which ? vals : vals_tmp;
+    CPB_LAUNCH(k_rs_hist, tiles, RS_THREADS, 0, ki, n, shift, hist.get(), tiles);
+    exclusive_scan_u32(hist.get(), hist.get(), (size_t)256 * tiles);
+    CPB_LAUNCH(k_rs_scatter, tiles, RS_THREADS, 0, ki, vi, ko, vo, n, shift, hist.get(), tiles);
+    which ^= 1;
+  }
+  return which;
+}
+
+// ------------------------------------------------------------------------------ small kernels
+__global__ void k_narrow_minus1(const i64* __restrict__ src, u32* __restrict__ dst, size_t n, i64 lo, i64 hi, u32* flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const i64 v = src[i];
+    bad |= (v < lo) | (v > hi);
+    dst[i] = (u32)(v - 1);
+  }
+  if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+}
+void narrow_minus1(const i64* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flags) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_narrow_minus1, grid, 256, 0, src, dst, n, lo, hi, flags);
+}
+
+__global__ void k_check_monotone(const u32* __restrict__ pos, size_t n, u32* flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += stride) bad |= pos[i] > pos[i + 1];
+  if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 2u);
+}
+void check_monotone(const u32* pos, size_t n, u32* flags) {
+  if (n < 2) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_check_monotone, grid, 256, 0, pos, n, flags);
+}
+
+__global__ void k_iota(u32* dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (u32)i;
+}
+void iota_u32(u32* dst, size_t n) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_iota, grid, 256, 0, dst, n);
+}
+
+__global__ void k_expand_columns(const u32* __restrict__ pos, u32 ncol, u32* __restrict__ colidx, size_t N) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+    // largest j in [0, ncol) with pos[j] <= q   (pos[ncol] == N > q)
+    u32 lo = 0, hi = ncol;
+    while (hi - lo > 1) {
+      const u32 mid = lo + ((hi - lo) >> 1);
+      if (__ldg(pos + mid) <= (u32)q) lo = mid; else hi = mid;
+    }
+    colidx[q] = lo;
+  }
+}
+void expand_columns(const u32* pos, u32 ncol, u32* colidx, size_t N) {
+  if (N == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((N + 255) / 256, (size_t)ctx().sm_count * 32);
+  CPB_LAUNCH(k_expand_columns, grid, 256, 0, pos, ncol, colidx, N);
+}
+
+__global__ void k_segment_starts(const u32* __restrict__ keys, size_t n, u32* __restrict__ P, u32 domain) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += stride) {
+    const i64 lo = (p == 0) ? 0 : (i64)keys[p - 1] + 1;
+    const i64 hi = (p == n) ? (i64)domain : (i64)keys[p];
+    for (i64 x = lo; x <= hi; ++x) P[x] = (u32)p;
+  }
+}
+void segment_starts(const u32* sorted_keys, size_t n, u32* P, u32 domain) {
+  const unsigned grid = (unsigned)std::min<size_t>((n + 1 + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_segment_starts, grid, 256, 0, sorted_keys, n, P, domain);
+}
+
+__global__ void k_widen_plus(const u32* __restrict__ src, i64* __restrict__ dst, size_t n, i64 add) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i64)src[i] + add;
+}
+void widen_plus(const u32* src, i64* dst, size_t n, i64 add) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_widen_plus, grid, 256, 0, src, dst, n, add);
+}
+
+}  // namespace cpb

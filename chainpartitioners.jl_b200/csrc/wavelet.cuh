@@ -1,0 +1,95 @@
+// wavelet.cuh -- the 2-D dominance index of the engine: a wavelet matrix over the "link" value of
+// each point, points ordered by their x coordinate.
+//
+// It replaces all three dominance structures of the reference (SparsePrefixMatrices.jl:396-821:
+// b-ary DominanceCount, BinaryDominanceCount, SparseStepwiseDominanceCount) -- the reference's
+// hints only choose between CPU data structures; the counts are what must match.
+//
+// Layout in HBM (one allocation):   level l (0 = most significant bit), block b:
+//     blocks[(l * nblk + b) * 8 + 0]      = number of 0-bits of level l before element b*224
+//     blocks[(l * nblk + b) * 8 + 1..7]   = the 224 bits of elements b*224 .. b*224+223
+// i.e. one 32-byte sector answers one rank query.  z[l] = total 0-bits of level l.
+#pragma once
+#include "common.cuh"
+
+namespace cpb {
+
+static constexpr int WM_BLOCK = 224;       // elements per 32-byte rank block
+static constexpr int WM_TILE_BLOCKS = 32;  // rank blocks per build tile
+static constexpr int WM_TILE = WM_BLOCK * WM_TILE_BLOCKS;  // 7168 elements per build CTA
+
+struct DevWM {
+  const u32* blocks;  // [L][nblk][8]
+  const u32* z;       // [L]
+  u32 nblk;
+  u32 npts;
+  int L;
+};
+
+// A rank structure = wavelet matrix + the prefix array over x:  P[x] = #{points with x_p < x},
+// x in 1..n+1 (1-based column numbers).
+struct DevRank {
+  DevWM wm;
+  const u32* P;  // indexable for 1 <= x <= n+1
+};
+
+#ifdef __CUDACC__
+// zeros among the first p elements of level l
+__device__ __forceinline__ u32 wm_rank0(const DevWM& w, int l, u32 p) {
+  const u32 b = p / WM_BLOCK;
+  const u32 off = p - b * WM_BLOCK;
+  const uint4* blk = reinterpret_cast<const uint4*>(w.blocks + ((size_t)l * w.nblk + b) * 8);
+  const uint4 a = __ldg(blk);
+  const uint4 c = __ldg(blk + 1);
+  const u32 wd[7] = {a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  u32 ones = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int nb = (int)off - 32 * k;
+    const u32 mask = nb >= 32 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+    ones += __popc(wd[k] & mask);
+  }
+  return a.x + off - ones;
+}
+
+// #{ p < e : val_p < v }  for 0 <= e <= npts, any v >= 0
+__device__ __forceinline__ u32 wm_rank_lt(const DevWM& w, u32 e, u32 v) {
+  if (w.L < 32 && (v >> w.L) != 0) return e;  // v beyond the value range: everything is smaller
+  u32 s = 0, cnt = 0;
+  for (int l = 0; l < w.L; ++l) {
+    const u32 bit = (v >> (w.L - 1 - l)) & 1u;
+    const u32 s0 = wm_rank0(w, l, s);
+    const u32 e0 = wm_rank0(w, l, e);
+    if (bit) {
+      cnt += e0 - s0;
+      const u32 zl = __ldg(w.z + l);
+      s = zl + (s - s0);
+      e = zl + (e - e0);
+    } else {
+      s = s0;
+      e = e0;
+    }
+  }
+  return cnt;
+}
+
+// #{ points : x_p < jp, val_p >= j }   (the reference's lnk(n+2-j, j'), SparseColorArrays.jl:121-125)
+__device__ __forceinline__ u32 rank_count_ge(const DevRank& r, u32 j, u32 jp) {
+  const u32 e = __ldg(r.P + jp);
+  return e - wm_rank_lt(r.wm, e, j);
+}
+#endif
+
+// Host-side owner of a wavelet matrix.
+struct WaveletMatrix {
+  DBuf<u32> blocks;
+  DBuf<u32> z;
+  u32 nblk = 0, npts = 0;
+  int L = 0;
+  // Builds from vals[0..n) (values <= max_value).  `vals` is consumed (used as a ping-pong buffer).
+  void build(u32* vals, u32* scratch, size_t n, u64 max_value);
+  DevWM dev() const { return DevWM{blocks.get(), z.get(), nblk, npts, L}; }
+  size_t bytes() const { return (size_t)L * nblk * 32; }
+};
+
+}  // namespace cpb

@@ -1,0 +1,165 @@
+/*
+ * chainb200.h -- C ABI of libchainb200.so, the B200 (sm_100a) engine for the hot path of
+ * ChainPartitioners.jl: the partition cost oracle over sparse column ranges and the
+ * split-point searches that consume it.
+ *
+ * The reference is pure Julia with no FFI of its own; every entry point below names the Julia
+ * method(s) it replaces (paths relative to the reference's src/).  The Julia-side binding a
+ * maintainer would add is julia/ChainPartitionersB200.jl.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in any signature;
+ *   - all indices are 1-based Int64 exactly as Julia stores SparseMatrixCSC.colptr / .rowval and
+ *     SplitPartition.spl; rows must be sorted and unique within a column (the SparseMatrixCSC
+ *     invariant);
+ *   - "host" pointers may be pageable or pinned; *_device variants take device pointers;
+ *   - every function returns 0 on success, <0 on error (cpb_last_error() gives the message);
+ *     nothing throws across the boundary;
+ *   - handles own device memory only; host arrays are never retained after a call returns;
+ *   - one CUDA stream per library instance; calls are serialised; there is NO CPU fallback: every
+ *     compute entry point fails with CPB_ERR_CUDA when no device is usable.
+ */
+#ifndef CHAINB200_H
+#define CHAINB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPB_OK 0
+#define CPB_ERR_ARG (-1)         /* invalid argument */
+#define CPB_ERR_UNSUPPORTED (-2) /* model/method combination the reference has no method for, or not built yet */
+#define CPB_ERR_CUDA (-3)        /* CUDA runtime error / no device */
+#define CPB_ERR_INFEASIBLE (-4)  /* width constraint cannot be met (reference: @assert j0 < j', DynamicChunker.jl:39) */
+
+/* ---- cost models ------------------------------------------------------------------------- */
+enum {
+  CPB_MODEL_WORK = 0,         /* AffineWorkModel                          WorkCosts.jl:5-17 */
+  CPB_MODEL_CONNECTIVITY = 1, /* AffineConnectivityModel                  ConnectivityCosts.jl:7-20 */
+  CPB_MODEL_MONOSYM = 2,      /* AffineMonotonizedSymmetricConnectivityModel  MonotonizedSymmetricConnectivityCosts.jl:5-33 */
+  CPB_MODEL_SYMCONN = 3,      /* AffineSymmetricConnectivityModel         SymmetricConnectivityCosts.jl:5-19 */
+  CPB_MODEL_HYPEREDGE = 4,    /* AffineHyperedgeCutModel                  HyperedgeCutCosts.jl:7-21 */
+  CPB_MODEL_SYMEDGECUT = 5,   /* AffineSymmetricEdgeCutModel              SymmetricEdgeCutCosts.jl:5-18 */
+  CPB_MODEL_ENVELOPE = 6,     /* AffineEnvelopeModel                      EnvelopeCosts.jl:5-20 */
+  CPB_MODEL_COLBLOCK = 7,     /* ColumnBlockComponentCostModel            BlockCosts.jl:1-17 */
+  CPB_MODEL_BLOCK = 8         /* BlockComponentCostModel                  BlockCosts.jl:19-44 */
+};
+
+/* coef[] by kind, evaluated left to right without FMA contraction (e.g. ConnectivityCosts.jl:20):
+ *   WORK                 alpha, beta_vertex, beta_pin
+ *   CONNECTIVITY/ENVELOPE alpha, beta_vertex, beta_pin, beta_net
+ *   MONOSYM              alpha, beta_vertex, beta_over_pin, beta_dia_net, delta_pins
+ *   SYMCONN              alpha, beta_vertex, beta_pin, beta_local_net, beta_remote_net
+ *   HYPEREDGE            alpha, beta_vertex, beta_pin, beta_self_net, beta_cut_net
+ *   SYMEDGECUT           alpha, beta_vertex, beta_self_pin, beta_cut_pin
+ * is_float = 0: Int64 coefficients and costs (coef[] integer valued, |cost| < 2^53);
+ * is_float = 1: Float64.
+ * COLBLOCK / BLOCK: block_component(f, w) (BlockCosts.jl:41-44) tabulated by the caller, because
+ * Julia functors cannot cross the ABI:
+ *   alpha_col[w], w = 0..w_tab;  beta_col[r*(w_tab+1) + w], r = 0..R-1 (COLBLOCK: R = 1);
+ *   beta_row[r*(u_tab+1) + u], u = 0..u_tab (BLOCK only; u = size of a row part). */
+typedef struct cpb_model {
+  int32_t kind;
+  int32_t is_float;
+  double coef[8];
+  int32_t R;
+  int32_t w_tab;
+  int32_t u_tab;
+  int32_t _pad;
+  const double* alpha_col;
+  const double* beta_col;
+  const double* beta_row;
+} cpb_model;
+
+/* ConstrainedCost(f, w, w_max) (Costs.jl:105-147): w(j,j') = w_coef[0] + (j'-j) w_coef[1] +
+ * (colptr[j']-colptr[j]) w_coef[2]; VertexCount() = {0,1,0} (SparseColorArrays.jl:1-6).
+ * enabled = 0: FeasibleCost (Costs.jl:164-171). */
+typedef struct cpb_constraint {
+  int32_t enabled;
+  int32_t _pad;
+  int64_t w_coef[3];
+  int64_t w_max;
+} cpb_constraint;
+
+/* ---- library ----------------------------------------------------------------------------- */
+const char* cpb_last_error(void);
+int cpb_version(void);
+/* Selects the CUDA device for this process (one process per GPU). Returns CPB_ERR_CUDA if none. */
+int cpb_init(int device);
+int cpb_device_count(void);
+/* Blocks until all queued work of the library stream has finished. */
+int cpb_synchronize(void);
+
+/* ---- matrices ---------------------------------------------------------------------------- */
+typedef struct cpb_matrix cpb_matrix;
+/* Copies a SparseMatrixCSC pattern (A.colptr, A.rowval) to the device (32-bit, 0-based there). */
+int cpb_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, cpb_matrix** out);
+/* Same from device-resident Int64 arrays (inputs already in HBM). */
+int cpb_matrix_create_device(int64_t m, int64_t n, int64_t nnz, const int64_t* d_colptr, const int64_t* d_rowval, cpb_matrix** out);
+int cpb_matrix_dims(const cpb_matrix* A, int64_t* m, int64_t* n, int64_t* nnz);
+/* Copies the pattern back as 1-based Int64 host arrays (colptr: n+1, rowval: nnz). */
+int cpb_matrix_get(const cpb_matrix* A, int64_t* colptr_out, int64_t* rowval_out);
+void cpb_matrix_destroy(cpb_matrix* A);
+/* adjointpattern(A) (util.jl:67-95): CSC pattern of the transpose, built on the device. */
+int cpb_adjointpattern(cpb_matrix* A, cpb_matrix** out);
+
+/* ---- cost oracles ------------------------------------------------------------------------ */
+typedef struct cpb_oracle cpb_oracle;
+/* oracle_stripe(hint, mdl, A[, Pi]) (Costs.jl:3-7, ConnectivityCosts.jl:47-56, Monotonized...:77-92,
+ * SymmetricConnectivityCosts.jl:29-45, HyperedgeCutCosts.jl:32-42, SymmetricEdgeCutCosts.jl:28-35,
+ * EnvelopeCosts.jl:56-64, BlockCosts.jl:58-64).  Builds the link arrays (SparseColorArrays.jl:72-118,
+ * 177-229, 281-318) and the 2-D dominance index (replacing SparsePrefixMatrices.jl:462-534 / 610-655 /
+ * 695-702: one wavelet-matrix index serves every hint).  pi_spl/pi_K: row SplitPartition for BLOCK. */
+int cpb_oracle_create(cpb_matrix* A, const cpb_model* mdl, const int64_t* pi_spl, int64_t pi_K, cpb_oracle** out);
+void cpb_oracle_destroy(cpb_oracle* f);
+/* ocl(j, j', k) for Q queries (ConnectivityCosts.jl:58-64 etc.).  k may be NULL.  Costs are returned
+ * as Float64 (exact for Int64 models below 2^53). */
+int cpb_oracle_query(cpb_oracle* f, int64_t Q, const int64_t* j, const int64_t* jp, const int64_t* k, double* cost_out);
+int cpb_oracle_query_device(cpb_oracle* f, int64_t Q, const int64_t* d_j, const int64_t* d_jp, double* d_cost_out);
+/* Raw counts: which = 0 pincount, 1 netcount, 2 dianetcount, 3 selfnetcount, 4 selfpincount
+ * (SparseColorArrays.jl:9-43, 47-152, 72-99, 156-256, 260-345); builds the structure on first use. */
+int cpb_count_query(cpb_matrix* A, int which, int64_t Q, const int64_t* j, const int64_t* jp, int64_t* out);
+/* bound_stripe(A, K, mdl-or-ocl) ./ 1 (WorkCosts.jl:37-51, ConnectivityCosts.jl:22-35,
+ * MonotonizedSymmetricConnectivityCosts.jl:35-66,94-105, EnvelopeCosts.jl:30-54). */
+int cpb_bound_stripe(cpb_oracle* f, int64_t K, double out[2]);
+/* bottleneck_value / total_value of a SplitPartition (Costs.jl:26-66). */
+int cpb_objective(cpb_oracle* f, int total, int64_t K, const int64_t* spl, double* out);
+
+/* ---- partition_stripe -------------------------------------------------------------------- */
+enum {
+  CPB_SPLIT_DYNAMIC_BOTTLENECK = 0, /* partition_stripe(A, K, DynamicBottleneckSplitter(f))  DynamicSplitter.jl:15-50 */
+  CPB_SPLIT_DYNAMIC_TOTAL = 1,      /* partition_stripe(A, K, DynamicTotalSplitter(f))       DynamicSplitter.jl:15-50 */
+  CPB_SPLIT_BISECT_COST = 2,        /* BisectCostBottleneckSplitter(f, eps)      BisectCostBottleneckSplitter.jl:6-63 */
+  CPB_SPLIT_LAZY_BISECT_COST = 3,   /* LazyBisectCostBottleneckSplitter(f, eps)  LazyBisectCostBottleneckSplitter.jl:8-70,140-258,260-388 */
+  CPB_SPLIT_EQUI = 5                /* EquiSplitter()                            EquiPartitioner.jl:3-9 */
+};
+/* -> spl_out[K+1] (SplitPartition{Int64}(K, spl), Partitions.jl:3-6); con may be NULL. */
+int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out);
+
+/* ---- pack_stripe ------------------------------------------------------------------------- */
+enum {
+  CPB_PACK_DYNAMIC_TOTAL = 0, /* pack_stripe(A, DynamicTotalChunker(ConstrainedCost(f, w, w_max))[, Pi])  DynamicChunker.jl:20-56 */
+  CPB_PACK_CONVEX_TOTAL = 1,  /* pack_stripe(A, ConvexTotalChunker(ConstrainedCost(...)))                 ConvexTotalChunker.jl:141-265 */
+  CPB_PACK_CONCAVE_TOTAL = 2, /* ConcaveTotalChunker.jl:9-114 */
+  CPB_PACK_OVERLAP = 3,       /* pack_stripe(A, OverlapChunker(rho, w_max))                               OverlapChunker.jl:6-75 */
+  CPB_PACK_STRICT = 4,        /* pack_stripe(A, StrictChunker(w_max))                                     StrictChunker.jl:5-54 */
+  CPB_PACK_EQUI = 5           /* pack_stripe(A, EquiChunker(w))                                           EquiPartitioner.jl:15-21 */
+};
+/* f may be NULL for OVERLAP / STRICT / EQUI (A is used).  spl_out must hold n+1 entries; K_out
+ * receives the number of chunks; n_nets_out (n entries or NULL) receives OverlapChunker's n_nets. */
+int cpb_pack_stripe(cpb_matrix* A, cpb_oracle* f, int method, const cpb_constraint* con, double rho, int64_t w_max,
+                    int64_t* spl_out, int64_t* K_out, int64_t* n_nets_out);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------- */
+/* When enabled, phases are bracketed with CUDA events on the library stream. */
+int cpb_profile_enable(int on);
+int cpb_profile_reset(void);
+/* Copies up to cap entries: names (char[32] each), total milliseconds, launches, algorithmic bytes. */
+int cpb_profile_get(int cap, char* names, double* ms, int64_t* launches, double* bytes);
+/* Number of kernels launched by the library since cpb_profile_reset(). */
+int64_t cpb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

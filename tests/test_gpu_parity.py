@@ -1,0 +1,223 @@
+"""GPU parity tests proper (-m gpu): every call goes through the C ABI of libchainb200.so and is
+compared bit-for-bit with the CPU oracle on the same inputs (split vectors and integer counts exact,
+Float64 costs identical because both sides evaluate the same left-to-right sums without FMA)."""
+import numpy as np
+import pytest
+
+import chainb200 as cp
+from chainb200 import synth
+from helpers import sprand
+
+pytestmark = pytest.mark.gpu
+
+AFF = cp.AffineConnectivityModel(0, 10, 1, 100)
+
+
+def rand_pairs(rng, n, Q):
+    j = rng.integers(1, n + 2, Q)
+    jp = rng.integers(1, n + 2, Q)
+    return np.minimum(j, jp), np.maximum(j, jp)
+
+
+def small_matrices(fixtures):
+    rng = np.random.default_rng(100)
+    mats = list(fixtures.values())
+    mats += [sprand(rng, m, n, p) for (m, n, p) in [(1, 1, 1.0), (1, 5, 0.5), (5, 1, 0.5), (3, 3, 0.0), (8, 8, 0.5), (40, 30, 0.2),
+                                                    (30, 40, 0.2), (300, 300, 0.02), (257, 225, 0.1), (1000, 1000, 0.01)]]
+    return mats
+
+
+def test_adjointpattern(ref, fixtures):
+    for A in small_matrices(fixtures) + [synth.erdos_renyi(20000, 10)]:
+        g = cp.adjointpattern(A)
+        r = ref.adjointpattern(A)
+        assert np.array_equal(g.colptr, r.colptr) and np.array_equal(g.rowval, r.rowval)
+        assert (g.m, g.n) == (A.n, A.m)
+
+
+def test_color_arrays(ref, fixtures):
+    rng = np.random.default_rng(101)
+    for A in small_matrices(fixtures) + [synth.laplacian5(40), synth.erdos_renyi(5000, 10)]:
+        j, jp = rand_pairs(rng, A.n, 500)
+        j = np.concatenate([j, [1, 1, A.n + 1]])
+        jp = np.concatenate([jp, [1, A.n + 1, A.n + 1]])
+        assert np.array_equal(cp.pincount(A).query(j, jp), ref.pincount(A, j, jp))
+        assert np.array_equal(cp.netcount(A).query(j, jp), ref.netcount(A, j, jp))
+        assert np.array_equal(cp.selfnetcount(A).query(j, jp), ref.selfnetcount(A, j, jp))
+        if A.m == A.n:
+            assert np.array_equal(cp.dianetcount(A).query(j, jp), ref.dianetcount(A, j, jp))
+            assert np.array_equal(cp.selfpincount(A).query(j, jp), ref.selfpincount(A, j, jp))
+
+
+MODELS = [
+    cp.AffineWorkModel(0, 10, 1),
+    cp.AffineConnectivityModel(0, 10, 1, 100),
+    cp.AffineConnectivityModel(0.5, 0.25, 1.5, 3.0),
+    cp.AffineEnvelopeModel(1, 2, 3, 4),
+]
+SQUARE = [
+    cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 90),
+    cp.AffineMonotonizedSymmetricConnectivityModel(10, 10, 10, 100, 2),
+    cp.AffineSymmetricConnectivityModel(1, 2, 3, 4, 5),
+    cp.AffineHyperedgeCutModel(0, 1, 2, 3, 4),
+    cp.AffineSymmetricEdgeCutModel(10, 10, 10, 100),
+    cp.AffineSymmetricEdgeCutModel(0.5, 1.0, 1.0, 2.5),
+]
+
+
+def test_oracle_queries(ref, fixtures):
+    rng = np.random.default_rng(102)
+    for A in small_matrices(fixtures) + [synth.laplacian5(48)]:
+        j, jp = rand_pairs(rng, A.n, 400)
+        for mdl in MODELS + (SQUARE if A.m == A.n else [cp.AffineHyperedgeCutModel(0, 1, 2, 3, 4)]):
+            if mdl.kind == cp.MODEL_ENVELOPE:
+                keep = j < jp
+                jj, jjp = j[keep], jp[keep]
+            else:
+                jj, jjp = j, jp
+            if len(jj) == 0:
+                continue
+            ocl = cp.oracle_stripe(mdl, A)
+            got = ocl.query(jj, jjp)
+            ocl.close()
+            exp = ref.oracle_query(mdl, A, jj, jjp)
+            assert np.array_equal(got, exp), (mdl, A)
+
+
+def test_column_block_oracle(ref, fixtures):
+    rng = np.random.default_rng(103)
+    mdl = cp.ColumnBlockComponentCostModel(int, 3, lambda w: 1 + w)
+    for A in [fixtures["Pajek/GD99_c"], fixtures["LPnetlib/lp_blend"]]:
+        j = rng.integers(1, A.n + 1, 300)
+        jp = np.minimum(j + rng.integers(0, 9, 300), A.n + 1)
+        ocl = cp.oracle_stripe(mdl, A, w_tab=8)
+        got = ocl.query(j, jp)
+        ocl.close()
+        assert np.array_equal(got, ref.oracle_query(mdl, A, j, jp))
+
+
+def test_bound_and_objective(ref, fixtures):
+    rng = np.random.default_rng(104)
+    for A in small_matrices(fixtures):
+        for K in [1, 2, 3, 8]:
+            spl = np.concatenate(([1], np.sort(rng.integers(1, A.n + 2, K - 1)), [A.n + 1]))
+            Phi = cp.SplitPartition(K, spl)
+            for mdl in [cp.AffineWorkModel(0, 10, 1), AFF, cp.AffineConnectivityModel(0.0, 1.0, 1.0, 1.0)] + (
+                [cp.AffineMonotonizedSymmetricConnectivityModel(10, 10, 10, 100, 8)] if A.m == A.n else []):
+                assert cp.bound_stripe(A, K, mdl) == ref.bound_stripe(A, K, mdl)
+                assert cp.bottleneck_value(A, Phi, mdl) == ref.bottleneck_value(A, Phi, mdl)
+                assert cp.total_value(A, Phi, mdl) == ref.total_value(A, Phi, mdl)
+
+
+def split_methods(f):
+    return [cp.DynamicBottleneckSplitter(f), cp.BisectCostBottleneckSplitter(f, 0.1), cp.BisectCostBottleneckSplitter(f, 0.01),
+            cp.LazyBisectCostBottleneckSplitter(f, 0.1), cp.LazyBisectCostBottleneckSplitter(f, 0.01)]
+
+
+def test_partition_stripe_small(ref, fixtures):
+    """The reference's own regime (test_Partitioners.jl:77-113): fixtures + tiny random matrices, K in {1,2,3,4,8}."""
+    for A in small_matrices(fixtures):
+        models = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), AFF, cp.AffineConnectivityModel(0.0, 3.0, 1.0, 3.5)]
+        if A.m == A.n:
+            models += [cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5), cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 90)]
+        for f in models:
+            for K in [1, 2, 3, 4, 8]:
+                for mtd in split_methods(f):
+                    g = cp.partition_stripe(A, K, mtd)
+                    r = ref.partition_stripe(A, K, mtd)
+                    assert np.array_equal(g.spl, r.spl), (A, f, K, type(mtd).__name__, g.spl, r.spl)
+
+
+def test_dynamic_total_splitter(ref, fixtures):
+    for A in [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], fixtures["LPnetlib/lp_blend"]]:
+        for f in [cp.AffineConnectivityModel(0, 3, 1, 3), AFF, cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0)]:
+            for K in [1, 2, 3, 8]:
+                mtd = cp.DynamicTotalSplitter(f)
+                assert np.array_equal(cp.partition_stripe(A, K, mtd).spl, ref.partition_stripe(A, K, mtd).spl)
+
+
+def test_config1_downscaled(ref):
+    """C1 at 64x64 (n = 4096): DynamicBottleneckSplitter, K = 8, net_model."""
+    A = synth.laplacian5(64)
+    mtd = cp.DynamicBottleneckSplitter(AFF)
+    assert np.array_equal(cp.partition_stripe(A, 8, mtd).spl, ref.partition_stripe(A, 8, mtd).spl)
+
+
+def test_config2_downscaled(ref):
+    """C2 at n = 50,000: BisectCost, K = 64, eps = 0.01."""
+    A = synth.erdos_renyi(50000, 10)
+    for mtd in [cp.BisectCostBottleneckSplitter(AFF, 0.01), cp.LazyBisectCostBottleneckSplitter(AFF, 0.01)]:
+        assert np.array_equal(cp.partition_stripe(A, 64, mtd).spl, ref.partition_stripe(A, 64, mtd).spl)
+
+
+def test_config3_downscaled(ref):
+    """C3 at scale 14: R-MAT, LazyBisect, K = 128, eps = 0.01 (skewed degrees, empty columns)."""
+    A = synth.rmat(14, 16 << 14)
+    mtd = cp.LazyBisectCostBottleneckSplitter(AFF, 0.01)
+    assert np.array_equal(cp.partition_stripe(A, 128, mtd).spl, ref.partition_stripe(A, 128, mtd).spl)
+
+
+def test_config5_downscaled(ref):
+    """C5 at n = 20,000: symmetric plaid partitioning with the monotonized symmetric model."""
+    A = synth.random_geometric(20000)
+    for dp in (90, 4):
+        s = cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, dp)
+        mtd = cp.LazyBisectCostBottleneckSplitter(s, 0.1)
+        Pg, Fg = cp.partition_plaid(A, 32, cp.AlternatingPartitioner(mtd, mtd))
+        Pr, Fr = ref.partition_plaid(A, 32, cp.AlternatingPartitioner(mtd, mtd))
+        assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl)
+
+
+def test_speculation_depth_does_not_change_result(ref, monkeypatch):
+    A = synth.erdos_renyi(20000, 10)
+    mtd = cp.BisectCostBottleneckSplitter(AFF, 0.001)
+    exp = ref.partition_stripe(A, 16, mtd).spl
+    for depth in ("1", "2", "3", "4"):
+        monkeypatch.setenv("CPB_BISECT_DEPTH", depth)
+        assert np.array_equal(cp.partition_stripe(A, 16, mtd).spl, exp), depth
+
+
+def test_device_resident_matrix_and_errors():
+    A = synth.laplacian5(16)
+    dA = cp.device_matrix(A)
+    B = dA.to_host()
+    assert np.array_equal(B.colptr, A.colptr) and np.array_equal(B.rowval, A.rowval)
+    s1 = cp.partition_stripe(dA, 4, cp.DynamicBottleneckSplitter(AFF)).spl
+    s2 = cp.partition_stripe(A, 4, cp.DynamicBottleneckSplitter(AFF)).spl
+    assert np.array_equal(s1, s2)
+    dA.close()
+    bad = cp.SparseMatrixCSC(2, 2, [1, 2, 3], [1, 2])
+    bad.rowval[1] = 7  # out of range row
+    with pytest.raises(cp.CpbError):
+        cp.device_matrix(bad)
+    with pytest.raises(cp.CpbError):  # no bound_stripe method for this model in the reference
+        cp.partition_stripe(A, 4, cp.BisectCostBottleneckSplitter(cp.AffineHyperedgeCutModel(0, 1, 1, 1, 1), 0.1))
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (n = 10^6): size-independent properties of the result."""
+    A = synth.erdos_renyi(1_000_000, 10)
+    K, eps = 64, 0.01
+    dA = cp.device_matrix(A)
+    Phi = cp.partition_stripe(dA, K, cp.BisectCostBottleneckSplitter(AFF, eps))
+    spl = Phi.spl
+    assert spl[0] == 1 and spl[-1] == A.n + 1 and np.all(np.diff(spl) >= 0)
+    lo, hi = cp.bound_stripe(dA, K, AFF)
+    v = cp.bottleneck_value(dA, Phi, AFF)
+    assert lo <= v <= hi
+    # greedy maximality (App. B row 4): extending any part but the last by one column must exceed the
+    # last feasible threshold, which is at most v * (1 + eps) ... so the extended cost is > v
+    ocl = cp.oracle_stripe(AFF, dA)
+    ext = ocl.query(spl[:-2], np.minimum(spl[1:-1] + 1, A.n + 1))
+    assert np.all(ext[spl[1:-1] <= A.n] > v)
+    # Lazy and random-access bisection agree split for split
+    Phi2 = cp.partition_stripe(dA, K, cp.LazyBisectCostBottleneckSplitter(AFF, eps))
+    assert np.array_equal(Phi2.spl, spl)
+    # oracle consistency: nets are sub-additive and monotone under refinement
+    j, jp = rand_pairs(np.random.default_rng(5), A.n, 10000)
+    mid = (j + jp) // 2
+    net = cp.netcount(dA)
+    whole, left, right = net.query(j, jp), net.query(j, mid), net.query(mid, jp)
+    assert np.all(whole <= left + right) and np.all(whole >= np.maximum(left, right))
+    ocl.close()
+    dA.close()
