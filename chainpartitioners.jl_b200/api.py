@@ -20,7 +20,7 @@ __all__ = [
     "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
-    "launch_count", "init", "synchronize", "library_path", "load_library", "CpbError",
+    "launch_count", "timer_start", "timer_stop", "init", "synchronize", "library_path", "load_library", "CpbError",
 ]
 
 I64 = np.int64
@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "cpb_matrix_create_device", "cpb_matrix_dims", "cpb_matrix_get", "cpb_matrix_destroy", "cpb_adjointpattern",
     "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
-    "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count",
+    "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
 ]
 
 
@@ -468,3 +468,14 @@ def profile_get() -> dict:
 
 def launch_count() -> int:
     return int(load_library().cpb_launch_count())
+
+
+def timer_start():
+    """CUDA event on the library stream (device-side stopwatch for bench.py)."""
+    _check(load_library().cpb_timer_start())
+
+
+def timer_stop() -> float:
+    ms = ctypes.c_double()
+    _check(load_library().cpb_timer_stop(ctypes.byref(ms)))
+    return ms.value

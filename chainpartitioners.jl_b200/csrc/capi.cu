@@ -349,4 +349,24 @@ int cpb_profile_get(int cap, char* names, double* ms, int64_t* launches, double*
 
 int64_t cpb_launch_count(void) { return cpb::g_ctx.launches; }
 
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+int cpb_timer_start(void) {
+  CPB_API_BEGIN
+  ensure_context();
+  if (!g_t0) { CPB_CUDA(cudaEventCreate(&g_t0)); CPB_CUDA(cudaEventCreate(&g_t1)); }
+  CPB_CUDA(cudaEventRecord(g_t0, ctx().stream));
+  CPB_API_END
+}
+int cpb_timer_stop(double* ms_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(g_t0 && ms_out, "timer not started");
+  CPB_CUDA(cudaEventRecord(g_t1, ctx().stream));
+  CPB_CUDA(cudaEventSynchronize(g_t1));
+  float ms = 0;
+  CPB_CUDA(cudaEventElapsedTime(&ms, g_t0, g_t1));
+  *ms_out = ms;
+  CPB_API_END
+}
+
 }  // extern "C"

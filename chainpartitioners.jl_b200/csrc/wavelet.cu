@@ -12,20 +12,19 @@
 namespace cpb {
 
 static constexpr unsigned FULL = 0xffffffffu;
-static constexpr int WM_THREADS = 256;
-static constexpr int WM_ROUNDS = WM_TILE / WM_THREADS;  // 28 rounds of 32 lanes per warp (4 blocks x 7 words)
+static constexpr int WM_THREADS = 1024;  // 32 warps: one 224-element rank block (7 rounds of 32 lanes) per warp
+static constexpr int WM_ROUNDS = 7;
 
 // zeros of bit `bit` per tile (first level only)
-__global__ void __launch_bounds__(WM_THREADS) k_wm_count(const u32* __restrict__ cur, u32 n, int bit, u32* __restrict__ tile_zeros) {
+__global__ void __launch_bounds__(256) k_wm_count(const u32* __restrict__ cur, u32 n, int bit, u32* __restrict__ tile_zeros) {
   __shared__ u32 sm[8];
   const size_t base = (size_t)blockIdx.x * WM_TILE;
   u32 c = 0;
-  for (int i = threadIdx.x; i < WM_TILE; i += WM_THREADS) {
+  for (int i = threadIdx.x; i < WM_TILE; i += 256) {
     const size_t idx = base + i;
     if (idx < n) c += ((cur[idx] >> bit) & 1u) ^ 1u;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(FULL, c, o);
+  c = __reduce_add_sync(FULL, c);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -36,79 +35,89 @@ __global__ void __launch_bounds__(WM_THREADS) k_wm_count(const u32* __restrict__
 }
 
 // tile_off: exclusive scan of per-tile zero counts, tile_off[tiles] = z (total zeros of the level)
-__global__ void __launch_bounds__(WM_THREADS) k_wm_level(const u32* __restrict__ cur, u32* __restrict__ nxt, u32 n, int bit, int next_bit,
-                                                         const u32* __restrict__ tile_off, u32 tiles, u32* __restrict__ next_tile_zeros,
-                                                         u32* __restrict__ blocks, u32 nblk, u32* __restrict__ z_out) {
-  __shared__ u32 s_wz[8];
-  __shared__ u32 s_words[8][32];  // per warp: 4 blocks x 8 words, written out coalesced
+__global__ void __launch_bounds__(WM_THREADS, 2) k_wm_level(const u32* __restrict__ cur, u32* __restrict__ nxt, u32 n, int bit, int next_bit,
+                                                            const u32* __restrict__ tile_off, u32 tiles, u32* __restrict__ next_tile_zeros,
+                                                            u32* __restrict__ blocks, u32 nblk, u32* __restrict__ z_out) {
+  __shared__ u32 s_wz[32];
+  __shared__ u32 s_next[4];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const u32 tile = blockIdx.x;
   const size_t tbase = (size_t)tile * WM_TILE;
-  const u32 wbase = w * (WM_ROUNDS * 32);  // element offset of this warp inside the tile
+  const u32 wbase = w * WM_BLOCK;  // element offset of this warp's rank block inside the tile
+  if (tid < 4) s_next[tid] = 0;
 
-  u32 v[WM_ROUNDS];
-  u32 zmask[WM_ROUNDS];
+  u32 v[WM_ROUNDS], ones[WM_ROUNDS], zmask[WM_ROUNDS];
   u32 wz = 0;
 #pragma unroll
   for (int r = 0; r < WM_ROUNDS; ++r) {
     const size_t idx = tbase + wbase + r * 32 + lane;
     const bool ok = idx < n;
     v[r] = ok ? cur[idx] : 0u;
-    const u32 b = (v[r] >> bit) & 1u;
-    const unsigned ones = __ballot_sync(FULL, ok && b);
-    const unsigned valid = __ballot_sync(FULL, ok);
-    zmask[r] = valid & ~ones;
-    if (lane == 0) s_words[w][(r / 7) * 8 + 1 + (r % 7)] = ones;
+    ones[r] = __ballot_sync(FULL, ok && ((v[r] >> bit) & 1u));
+    zmask[r] = __ballot_sync(FULL, ok) & ~ones[r];
     wz += __popc(zmask[r]);
   }
   if (lane == 0) s_wz[w] = wz;
   __syncthreads();
-  u32 zbefore = 0;  // zeros of the tile before this warp
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (k < w) zbefore += s_wz[k];
+  const u32 zbefore = __reduce_add_sync(FULL, lane < w ? s_wz[lane] : 0u);  // zeros of the tile before this warp
+  const u32 tz = __reduce_add_sync(FULL, s_wz[lane]);                        // zeros of the whole tile
   const u32 Z0 = tile_off[tile];
   const u32 ztot = tile_off[tiles];
   if (tile == 0 && tid == 0) *z_out = ztot;
 
-  // rank-block headers: zeros before each of this warp's 4 blocks
+  // this warp's rank block: header (zeros before the block) + 7 bit words, one 32-byte store
   {
-    u32 run = Z0 + zbefore;
+    const u32 blk = tile * WM_TILE_BLOCKS + w;
+    u32 word = Z0 + zbefore;
 #pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      if (lane == 0) s_words[w][bb * 8] = run;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) run += __popc(zmask[bb * 7 + k]);
-    }
-  }
-  __syncwarp();
-  {
-    const u32 blk = tile * WM_TILE_BLOCKS + w * 4 + (lane >> 3);
-    if (blk < nblk) blocks[(size_t)blk * 8 + (lane & 7)] = s_words[w][lane];
+    for (int k = 0; k < WM_ROUNDS; ++k)
+      if (lane == k + 1) word = ones[k];
+    if (lane < 8 && blk < nblk) blocks[(size_t)blk * 8 + lane] = word;
   }
 
-  // stable partition into the next level's order
+  // stable partition into the next level's order.  Zeros of this tile land in [Z0, Z0 + tz), ones in
+  // [O0, O0 + ...): each range straddles at most one boundary between destination tiles, so the
+  // next level's per-tile zero counts need only four counters per CTA.
+  const u32 O0 = ztot + (u32)(tbase - Z0);
+  const u32 bndZ = (Z0 / WM_TILE + 1) * WM_TILE;
+  const u32 bndO = (O0 / WM_TILE + 1) * WM_TILE;
   const unsigned lt = (1u << lane) - 1u;
   u32 zrun = zbefore;
+  u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
   for (int r = 0; r < WM_ROUNDS; ++r) {
     const u32 in_tile = wbase + r * 32 + lane;
-    const size_t idx = tbase + in_tile;
-    const bool ok = idx < n;
+    const bool ok = tbase + in_tile < n;
     const bool is_zero = (zmask[r] >> lane) & 1u;
     const u32 zb = zrun + __popc(zmask[r] & lt);
-    u32 dst;
-    if (is_zero) dst = Z0 + zb;
-    else dst = ztot + (u32)(tbase - Z0) + (in_tile - zb);
-    if (ok) nxt[dst] = v[r];
-    if (next_bit >= 0) {
-      const bool nz = ok && (((v[r] >> next_bit) & 1u) == 0u);
-      const u32 key = nz ? dst / WM_TILE : 0xffffffffu;
-      const unsigned m = __match_any_sync(FULL, key);
-      if (nz && lane == __ffs(m) - 1) atomicAdd(&next_tile_zeros[key], (u32)__popc(m));
+    const u32 dst = is_zero ? Z0 + zb : O0 + (in_tile - zb);
+    if (ok) {
+      nxt[dst] = v[r];
+      if (next_bit >= 0 && ((v[r] >> next_bit) & 1u) == 0u) {
+        if (is_zero) { if (dst < bndZ) ++c0; else ++c1; }
+        else { if (dst < bndO) ++c2; else ++c3; }
+      }
     }
     zrun += __popc(zmask[r]);
   }
+  if (next_bit >= 0) {
+    c0 = __reduce_add_sync(FULL, c0);
+    c1 = __reduce_add_sync(FULL, c1);
+    c2 = __reduce_add_sync(FULL, c2);
+    c3 = __reduce_add_sync(FULL, c3);
+    if (lane == 0) {
+      if (c0) atomicAdd(&s_next[0], c0);
+      if (c1) atomicAdd(&s_next[1], c1);
+      if (c2) atomicAdd(&s_next[2], c2);
+      if (c3) atomicAdd(&s_next[3], c3);
+    }
+    __syncthreads();
+    if (tid < 4 && s_next[tid]) {
+      const u32 t = (tid < 2 ? bndZ : bndO) / WM_TILE - 1 + (tid & 1);
+      atomicAdd(&next_tile_zeros[t], s_next[tid]);
+    }
+  }
+  (void)tz;
 }
 
 void WaveletMatrix::build(u32* vals, u32* scratch, size_t n, u64 max_value) {
@@ -125,7 +134,7 @@ void WaveletMatrix::build(u32* vals, u32* scratch, size_t n, u64 max_value) {
   tz[1].alloc(tiles + 1);
   DBuf<u32> toff(tiles + 1);
   tz[0].zero();
-  if (n > 0) CPB_LAUNCH(k_wm_count, tiles, WM_THREADS, 0, vals, (u32)n, L - 1, tz[0].get());
+  if (n > 0) CPB_LAUNCH(k_wm_count, tiles, 256, 0, vals, (u32)n, L - 1, tz[0].get());
   u32* cur = vals;
   u32* nxt = scratch;
   for (int l = 0; l < L; ++l) {
@@ -135,8 +144,11 @@ void WaveletMatrix::build(u32* vals, u32* scratch, size_t n, u64 max_value) {
     DBuf<u32>& tzn = tz[(l + 1) & 1];
     exclusive_scan_u32(tzc.get(), toff.get(), tiles + 1);  // last input entry is 0 -> toff[tiles] = total
     if (next_bit >= 0) tzn.zero();
-    CPB_LAUNCH(k_wm_level, tiles, WM_THREADS, 0, cur, nxt, (u32)n, bit, next_bit, toff.get(), tiles, tzn.get(),
-               blocks.get() + (size_t)l * nblk * 8, nblk, z.get() + l);
+    {
+      ProfScope pk("k_wm_level", (double)n * 8.0 + (double)nblk * 32.0);
+      CPB_LAUNCH(k_wm_level, tiles, WM_THREADS, 0, cur, nxt, (u32)n, bit, next_bit, toff.get(), tiles, tzn.get(),
+                 blocks.get() + (size_t)l * nblk * 8, nblk, z.get() + l);
+    }
     u32* t = cur; cur = nxt; nxt = t;
   }
 }

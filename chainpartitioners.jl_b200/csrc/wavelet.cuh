@@ -38,10 +38,12 @@ struct DevRank {
 __device__ __forceinline__ u32 wm_rank0(const DevWM& w, int l, u32 p) {
   const u32 b = p / WM_BLOCK;
   const u32 off = p - b * WM_BLOCK;
-  const uint4* blk = reinterpret_cast<const uint4*>(w.blocks + ((size_t)l * w.nblk + b) * 8);
-  const uint4 a = __ldg(blk);
-  const uint4 c = __ldg(blk + 1);
-  const u32 wd[7] = {a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  const u32* blk = w.blocks + ((size_t)l * w.nblk + b) * 8;
+  u32 hdr, wd[7];
+  // one 256-bit load = exactly one 32-byte sector = one L1 wavefront per lane (LDG.E.256 on sm_100a)
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(hdr), "=r"(wd[0]), "=r"(wd[1]), "=r"(wd[2]), "=r"(wd[3]), "=r"(wd[4]), "=r"(wd[5]), "=r"(wd[6])
+      : "l"(blk));
   u32 ones = 0;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
@@ -49,7 +51,7 @@ __device__ __forceinline__ u32 wm_rank0(const DevWM& w, int l, u32 p) {
     const u32 mask = nb >= 32 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
     ones += __popc(wd[k] & mask);
   }
-  return a.x + off - ones;
+  return hdr + off - ones;
 }
 
 // #{ p < e : val_p < v }  for 0 <= e <= npts, any v >= 0

@@ -158,6 +158,10 @@ int cpb_profile_reset(void);
 int cpb_profile_get(int cap, char* names, double* ms, int64_t* launches, double* bytes);
 /* Number of kernels launched by the library since cpb_profile_reset(). */
 int64_t cpb_launch_count(void);
+/* Device-side stopwatch: records a CUDA event on the library stream / records a second one, waits
+ * for it and returns the elapsed milliseconds between the two. */
+int cpb_timer_start(void);
+int cpb_timer_stop(double* ms_out);
 
 #ifdef __cplusplus
 }
