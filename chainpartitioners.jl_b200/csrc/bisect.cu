@@ -191,6 +191,7 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
   const Matrix& A = *f.A;
   CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
+  oracle_ensure_ranks(f);
   double bnd[2];
   oracle_bound(f, K, bnd);  // (c_lo, c_hi) ./ 1
   if (lazy) {
@@ -204,7 +205,7 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   for (RankStruct* rs : {f.net.get(), f.dianet.get(), f.selfnet.get(), f.selfpin.get()})
     if (rs && rs->wm.bytes() > 0 && rs->wm.bytes() <= ((size_t)64 << 20) && env_int("CPB_L2_PREFETCH", 1)) {
       const size_t bytes = rs->wm.bytes();
-      const unsigned grid = (unsigned)std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8);
+      const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8));
       CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
     }
   int depth = std::min(std::max(env_int("CPB_BISECT_DEPTH", 4), 1), BS_MAX_DEPTH);

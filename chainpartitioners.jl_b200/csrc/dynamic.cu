@@ -149,6 +149,7 @@ void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int6
     if (f.mdl.kind == CPB_MODEL_SYMCONN || f.mdl.kind == CPB_MODEL_HYPEREDGE || f.mdl.kind == CPB_MODEL_SYMEDGECUT)
       throw Error(CPB_ERR_UNSUPPORTED, "bottleneck DP on the device needs a monotone cost model");
   }
+  oracle_ensure_ranks(f);
   if (f.dev.is_float) dynamic_T<double>(f, total, K, h_spl_out); else dynamic_T<i64>(f, total, K, h_spl_out);
 }
 

@@ -25,6 +25,8 @@ struct RankStruct {
 // SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
+// prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
+void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx);
 // For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
 
 // ---- device-side oracle ------------------------------------------------------------------------
@@ -62,8 +64,10 @@ struct Oracle {
   DBuf<u32> pi_size;    // [K_pi] part sizes
   std::vector<i64> h_pi_spl;
   i64 pi_K = 0;
+  bool ranks_built = false;
   DevOracle dev{};
 };
+void oracle_ensure_ranks(Oracle& f);
 
 std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int64_t* pi_spl, i64 pi_K);
 void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost);

@@ -114,16 +114,19 @@ static u32 read_u32(const u32* d) {
   return h;
 }
 
+// prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
+void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx) {
+  ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
+  TransposeOrder t;
+  transpose_order(row, N, nrow ? nrow - 1 : 0, t);
+  expand_columns(pos, ncol, colidx, N);
+  if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N);
+}
+
 // links over (pos, row) with ncol columns and N entries -> wavelet matrix over prev[]
 static void build_net_like(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, RankStruct& rs) {
   DBuf<u32> prev(N), colidx(N);
-  {
-    ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
-    TransposeOrder t;
-    transpose_order(row, N, nrow ? nrow - 1 : 0, t);
-    expand_columns(pos, ncol, colidx.get(), N);
-    if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx.get(), prev.get(), N);
-  }
+  compute_prev_links(pos, row, nrow, ncol, N, prev.get(), colidx.get());
   rs.wm.build(prev.get(), colidx.get(), N, ncol);  // colidx is dead: reuse as ping-pong scratch
 }
 

@@ -96,10 +96,9 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
     d.ci[t] = (i64)std::llround(mdl->coef[t]);
     if (!mdl->is_float) CPB_REQUIRE((double)d.ci[t] == mdl->coef[t], "Int64 model with a non-integer coefficient");
   }
-  ProfScope prof("oracle_stripe");
   switch (mdl->kind) {
     case CPB_MODEL_WORK: break;
-    case CPB_MODEL_CONNECTIVITY: f->net = build_rank(A, RANK_NET); break;
+    case CPB_MODEL_CONNECTIVITY: break;
     case CPB_MODEL_COLBLOCK: {
       CPB_REQUIRE(mdl->alpha_col && mdl->beta_col && mdl->w_tab >= 0, "column-block model needs tables");
       const int W = mdl->w_tab + 1;
@@ -121,7 +120,8 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
       d.tab_alpha_i = f->tab_i.get();
       d.tab_beta_i = f->tab_i.get() + W;
       d.w_tab = mdl->w_tab;
-      f->net = build_rank(A, RANK_NET);
+      f->h_alpha_col.assign(mdl->alpha_col, mdl->alpha_col + W);
+      f->h_beta_col.assign(mdl->beta_col, mdl->beta_col + W);
       break;
     }
     case CPB_MODEL_MONOSYM: {
@@ -131,19 +131,13 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
       CPB_LAUNCH(k_overdeg, grid_for((size_t)A.n + 1), 256, 0, A.pos.get(), (u32)A.n, (i64)mdl->coef[4], f->overpos.get());
       exclusive_scan_u32(f->overpos.get(), f->overpos.get(), (size_t)A.n + 1);
       d.overpos = f->overpos.get();
-      f->dianet = build_rank(A, RANK_DIANET);
       break;
     }
     case CPB_MODEL_SYMCONN:
       CPB_REQUIRE(A.m == A.n, "symmetric connectivity model needs a square matrix");  // Symmetric...:32
-      f->net = build_rank(A, RANK_NET);
-      f->dianet = build_rank(A, RANK_DIANET);
       break;
-    case CPB_MODEL_HYPEREDGE:
-      f->net = build_rank(A, RANK_NET);
-      f->selfnet = build_rank(A, RANK_SELFNET);
-      break;
-    case CPB_MODEL_SYMEDGECUT: f->selfpin = build_rank(A, RANK_SELFPIN); break;
+    case CPB_MODEL_HYPEREDGE: break;
+    case CPB_MODEL_SYMEDGECUT: break;
     case CPB_MODEL_ENVELOPE: {
       int H = 0;
       while (((i64)1 << H) < std::max<i64>(A.n, 1)) ++H;  // cllog2(n)
@@ -184,11 +178,31 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
     }
     default: throw Error(CPB_ERR_UNSUPPORTED, "unknown cost model kind");
   }
-  if (f->net) d.net = f->net->dev();
-  if (f->dianet) d.dianet = f->dianet->dev();
-  if (f->selfnet) d.selfnet = f->selfnet->dev();
-  if (f->selfpin) d.selfpin = f->selfpin->dev();
+  // the caller's table pointers are not retained (ABI contract): host copies live in the handle
+  f->mdl.alpha_col = f->mdl.beta_col = f->mdl.beta_row = nullptr;
   return f;
+}
+
+// Builds the dominance indices the model's random-access oracle needs, on first use.  The chunkers
+// (pack_stripe) never call this: they stream the link arrays instead.
+void oracle_ensure_ranks(Oracle& f) {
+  if (f.ranks_built) return;
+  ProfScope prof("oracle_stripe");
+  Matrix& A = *f.A;
+  DevOracle& d = f.dev;
+  switch (f.mdl.kind) {
+    case CPB_MODEL_CONNECTIVITY: case CPB_MODEL_COLBLOCK: f.net = build_rank(A, RANK_NET); break;
+    case CPB_MODEL_MONOSYM: f.dianet = build_rank(A, RANK_DIANET); break;
+    case CPB_MODEL_SYMCONN: f.net = build_rank(A, RANK_NET); f.dianet = build_rank(A, RANK_DIANET); break;
+    case CPB_MODEL_HYPEREDGE: f.net = build_rank(A, RANK_NET); f.selfnet = build_rank(A, RANK_SELFNET); break;
+    case CPB_MODEL_SYMEDGECUT: f.selfpin = build_rank(A, RANK_SELFPIN); break;
+    default: break;
+  }
+  if (f.net) d.net = f.net->dev();
+  if (f.dianet) d.dianet = f.dianet->dev();
+  if (f.selfnet) d.selfnet = f.selfnet->dev();
+  if (f.selfpin) d.selfpin = f.selfpin->dev();
+  f.ranks_built = true;
 }
 
 // ---- oracle_query_batch ---------------------------------------------------------------------------
@@ -208,6 +222,7 @@ __global__ void __launch_bounds__(256) k_oracle_query(const __grid_constant__ De
 void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost) {
   if (Q <= 0) return;
   if (f.dev.kind == CPB_MODEL_BLOCK) throw Error(CPB_ERR_UNSUPPORTED, "random-access queries of the 2-D block model are served through pack_stripe only");
+  oracle_ensure_ranks(f);
   const double L = f.net ? f.net->wm.L : f.dianet ? f.dianet->wm.L : f.selfpin ? f.selfpin->wm.L : 0;
   ProfScope prof("oracle_query_batch", (double)Q * (24.0 + L * 2.0 * 32.0));
   const unsigned grid = (unsigned)std::min<size_t>(((size_t)Q + 255) / 256, (size_t)ctx().sm_count * 16);

@@ -221,3 +221,104 @@ def test_full_size_properties_config2():
     assert np.all(whole <= left + right) and np.all(whole >= np.maximum(left, right))
     ocl.close()
     dA.close()
+
+
+# ------------------------------------------------------------------------------------------ pack_stripe
+def chunk_matrices(fixtures):
+    rng = np.random.default_rng(200)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], fixtures["LPnetlib/lp_blend"], fixtures["HB/west0132"]]
+    mats += [sprand(rng, m, n, p) for (m, n, p) in [(1, 1, 1.0), (3, 1, 0.5), (4, 2, 0.5), (8, 9, 0.4), (30, 41, 0.2), (64, 1500, 0.05), (500, 3000, 0.01)]]
+    mats.append(synth.banded(5000, 8))
+    return mats
+
+
+BLOCK_MODELS = [
+    cp.BlockComponentCostModel(int, 1, 3, (1, cp.identity), (1, cp.identity)),  # runbenchmarks.jl:22
+    cp.BlockComponentCostModel(int, 0, 0, (10, cp.identity), (2, lambda x: 2 * x)),  # test_Partitioners.jl:227
+    cp.BlockComponentCostModel(int, cp.identity, lambda x: 3 * x, (10, cp.identity), (2, lambda x: 2 * x)),
+]
+
+
+def test_pack_stripe_dynamic_total_chunker(ref, fixtures):
+    """DynamicTotalChunker(ConstrainedCost(f, VertexCount(), w_max)): split vectors identical (leftmost ties)."""
+    for A in chunk_matrices(fixtures):
+        Pi = ref.pack_stripe(ref.adjointpattern(A), cp.EquiChunker(2))
+        models = [cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0, 0, 0, 1), AFF, cp.AffineWorkModel(1, 2, 3),
+                  cp.ColumnBlockComponentCostModel(int, 3, lambda w: 1 + w), cp.AffineConnectivityModel(0.5, 0.25, 1.5, 3.0)] + BLOCK_MODELS
+        for f in models:
+            for w_max in [1, 2, 4, 8, 13]:
+                mtd = cp.DynamicTotalChunker(cp.ConstrainedCost(f, cp.VertexCount(), w_max))
+                args = (Pi,) if f.kind == cp.MODEL_BLOCK else ()
+                g = cp.pack_stripe(A, mtd, *args)
+                r = ref.pack_stripe(A, mtd, *args)
+                assert g.K == r.K and np.array_equal(g.spl, r.spl), (A, f, w_max, g.spl[:10], r.spl[:10])
+
+
+def test_pack_stripe_work_weight(ref, fixtures):
+    """ConstrainedCost with an AffineWorkModel weight (test_Partitioners.jl:176-178)."""
+    A = fixtures["LPnetlib/lp_blend"]
+    for w_max in [2, 4, 8]:
+        mtd = cp.DynamicTotalChunker(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineWorkModel(0, 1, 0), w_max))
+        assert np.array_equal(cp.pack_stripe(A, mtd).spl, ref.pack_stripe(A, mtd).spl)
+    mtd = cp.DynamicTotalChunker(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineWorkModel(0, 2, 1), 40))
+    assert np.array_equal(cp.pack_stripe(A, mtd).spl, ref.pack_stripe(A, mtd).spl)
+
+
+def test_pack_stripe_convex(ref, fixtures):
+    """ConvexTotalChunker(ConstrainedCost(connectivity, VertexCount(), w_max)) (bin/test_table_constrained_chunks.jl:32-41)."""
+    for A in chunk_matrices(fixtures):
+        for f in [cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(-0.5, 0.0, 0.0, 1.0)]:
+            for w_max in [1, 2, 3, 4, 8]:
+                mtd = cp.ConvexTotalChunker(cp.ConstrainedCost(f, cp.VertexCount(), w_max))
+                g = cp.pack_stripe(A, mtd)
+                r = ref.pack_stripe(A, mtd)
+                assert np.array_equal(g.spl, r.spl), (A, f, w_max)
+
+
+def test_pack_stripe_overlap_strict_equi(ref, fixtures):
+    for A in chunk_matrices(fixtures):
+        for w_max in [1, 2, 4, 8]:
+            for rho in [0.9, 0.8, 0.7, 0.3]:
+                bg, br = [None], [None]
+                g = cp.pack_stripe(A, cp.OverlapChunker(rho, w_max), n_nets=bg)
+                r = ref.pack_stripe(A, cp.OverlapChunker(rho, w_max), n_nets=br)
+                assert np.array_equal(g.spl, r.spl), (A, rho, w_max)
+                assert np.array_equal(bg[0], br[0])
+            assert np.array_equal(cp.pack_stripe(A, cp.StrictChunker(w_max)).spl, ref.pack_stripe(A, cp.StrictChunker(w_max)).spl)
+            assert np.array_equal(cp.pack_stripe(A, cp.EquiChunker(w_max)).spl, ref.pack_stripe(A, cp.EquiChunker(w_max)).spl)
+
+
+def test_strict_chunker_with_repeated_columns(ref):
+    rng = np.random.default_rng(201)
+    base = sprand(rng, 12, 40, 0.3).to_scipy().tocsc()
+    import scipy.sparse as sp
+
+    cols = np.repeat(np.arange(40), rng.integers(1, 6, 40))
+    A = cp.SparseMatrixCSC.from_scipy(sp.csc_matrix(base[:, cols]))
+    for w_max in [1, 2, 3, 8]:
+        assert np.array_equal(cp.pack_stripe(A, cp.StrictChunker(w_max)).spl, ref.pack_stripe(A, cp.StrictChunker(w_max)).spl)
+
+
+def test_pack_infeasible_and_unsupported():
+    A = synth.banded(200, 4)
+    with pytest.raises(cp.CpbError) as e:
+        cp.pack_stripe(A, cp.DynamicTotalChunker(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineWorkModel(5, 1, 0), 3)))
+    assert e.value.code == -4
+    with pytest.raises(cp.CpbError):
+        cp.pack_stripe(A, cp.ConcaveTotalChunker(cp.AffineWorkModel(1, 1, 1)))
+
+
+def test_config4_downscaled(ref):
+    """C4 at n = 2^15: banded, X = adjointpattern(A), Pi = pack_stripe(A, EquiChunker(4)),
+    DynamicTotalChunker(block_model, 8) and ConvexTotalChunker(connectivity, 8)."""
+    A = synth.banded(1 << 15, 64)
+    X = cp.adjointpattern(A)
+    Pi = cp.pack_stripe(A, cp.EquiChunker(4))
+    g = cp.BlockComponentCostModel(int, 1, 3, (1, cp.identity), (1, cp.identity))
+    m1 = cp.DynamicTotalChunker(g, 8)
+    assert np.array_equal(cp.pack_stripe(X, m1, Pi).spl, ref.pack_stripe(X, m1, Pi).spl)
+    m2 = cp.ConvexTotalChunker(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.VertexCount(), 8))
+    assert np.array_equal(cp.pack_stripe(X, m2).spl, ref.pack_stripe(X, m2).spl)
+    Pg, Fg = cp.pack_plaid(A, cp.AlternatingPacker(cp.OverlapChunker(0.9, 8), m1))
+    Pr, Fr = ref.pack_plaid(A, cp.AlternatingPacker(cp.OverlapChunker(0.9, 8), m1))
+    assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl)
