@@ -6,6 +6,7 @@
 // needs are accumulated by the PREVIOUS level's launch (warp-aggregated atomics on the
 // destination tile), so each level reads the keys once and writes them once:
 //     algorithmic bytes per level = n * (4 + 4) + n / 7 * (32 / 32) ...  
+#include <algorithm>
 #include "primitives.cuh"
 #include "wavelet.cuh"
 
@@ -120,6 +121,13 @@ __global__ void __launch_bounds__(WM_THREADS, 2) k_wm_level(const u32* __restric
   (void)tz;
 }
 
+// S0[v] = wm_descend(0, v) for every value of the L-bit range
+__global__ void k_wm_s0(DevWM w, u32* __restrict__ S0) {
+  const size_t total = (size_t)1 << w.L;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) S0[v] = wm_descend(w, 0u, (u32)v);
+}
+
 void WaveletMatrix::build(u32* vals, u32* scratch, size_t n, u64 max_value) {
   CPB_REQUIRE(n < ((size_t)1 << 31), "too many points for the 32-bit device index");
   L = bits_for(max_value);
@@ -150,6 +158,13 @@ void WaveletMatrix::build(u32* vals, u32* scratch, size_t n, u64 max_value) {
                  blocks.get() + (size_t)l * nblk * 8, nblk, z.get() + l);
     }
     u32* t = cur; cur = nxt; nxt = t;
+  }
+  CPB_REQUIRE(L <= 30, "value range too wide");
+  S0.alloc((size_t)1 << L);
+  {
+    const size_t total = (size_t)1 << L;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)ctx().sm_count * 16));
+    CPB_LAUNCH(k_wm_s0, grid, 256, 0, dev(), S0.get());
   }
 }
 

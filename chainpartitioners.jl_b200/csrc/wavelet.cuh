@@ -21,6 +21,7 @@ static constexpr int WM_TILE = WM_BLOCK * WM_TILE_BLOCKS;  // 7168 elements per 
 struct DevWM {
   const u32* blocks;  // [L][nblk][8]
   const u32* z;       // [L]
+  const u32* S0;      // [2^L]  value-only half of the rank descent (see wm_rank_lt)
   u32 nblk;
   u32 npts;
   int L;
@@ -54,25 +55,29 @@ __device__ __forceinline__ u32 wm_rank0(const DevWM& w, int l, u32 p) {
   return hdr + off - ones;
 }
 
-// #{ p < e : val_p < v }  for 0 <= e <= npts, any v >= 0
-__device__ __forceinline__ u32 wm_rank_lt(const DevWM& w, u32 e, u32 v) {
-  if (w.L < 32 && (v >> w.L) != 0) return e;  // v beyond the value range: everything is smaller
-  u32 s = 0, cnt = 0;
+// sum over the 1-bits of v of the zeros left of the descending position, starting from e
+__device__ __forceinline__ u32 wm_descend(const DevWM& w, u32 e, u32 v) {
+  u32 cnt = 0;
   for (int l = 0; l < w.L; ++l) {
-    const u32 bit = (v >> (w.L - 1 - l)) & 1u;
-    const u32 s0 = wm_rank0(w, l, s);
     const u32 e0 = wm_rank0(w, l, e);
-    if (bit) {
-      cnt += e0 - s0;
-      const u32 zl = __ldg(w.z + l);
-      s = zl + (s - s0);
-      e = zl + (e - e0);
+    if ((v >> (w.L - 1 - l)) & 1u) {
+      cnt += e0;
+      e = __ldg(w.z + l) + (e - e0);
     } else {
-      s = s0;
       e = e0;
     }
   }
   return cnt;
+}
+
+// #{ p < e : val_p < v }  for 0 <= e <= npts, any v >= 0.
+// The textbook descent tracks the interval [s, e) with s starting at 0; s depends on v alone, so its
+// contribution S0[v] = wm_descend(0, v) is tabulated at build time and a query walks ONE chain of L
+// dependent 32-byte loads instead of two.
+__device__ __forceinline__ u32 wm_rank_lt(const DevWM& w, u32 e, u32 v) {
+  if (w.L < 32 && (v >> w.L) != 0) return e;  // v beyond the value range: everything is smaller
+  const u32 s0 = __ldg(w.S0 + v);
+  return wm_descend(w, e, v) - s0;
 }
 
 // #{ points : x_p < jp, val_p >= j }   (the reference's lnk(n+2-j, j'), SparseColorArrays.jl:121-125)
@@ -86,12 +91,13 @@ __device__ __forceinline__ u32 rank_count_ge(const DevRank& r, u32 j, u32 jp) {
 struct WaveletMatrix {
   DBuf<u32> blocks;
   DBuf<u32> z;
+  DBuf<u32> S0;
   u32 nblk = 0, npts = 0;
   int L = 0;
   // Builds from vals[0..n) (values <= max_value).  `vals` is consumed (used as a ping-pong buffer).
   void build(u32* vals, u32* scratch, size_t n, u64 max_value);
-  DevWM dev() const { return DevWM{blocks.get(), z.get(), nblk, npts, L}; }
-  size_t bytes() const { return (size_t)L * nblk * 32; }
+  DevWM dev() const { return DevWM{blocks.get(), z.get(), S0.get(), nblk, npts, L}; }
+  size_t bytes() const { return (size_t)L * nblk * 32; }  // rank blocks only
 };
 
 }  // namespace cpb

@@ -322,3 +322,11 @@ def test_config4_downscaled(ref):
     Pg, Fg = cp.pack_plaid(A, cp.AlternatingPacker(cp.OverlapChunker(0.9, 8), m1))
     Pr, Fr = ref.pack_plaid(A, cp.AlternatingPacker(cp.OverlapChunker(0.9, 8), m1))
     assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl)
+
+
+def test_torch_generators_match_numpy():
+    from chainb200 import synth_torch
+
+    for a, b in [(synth.erdos_renyi(3000, 10), synth_torch.erdos_renyi(3000, 10)), (synth.rmat(10, 16 << 10), synth_torch.rmat(10, 16 << 10)),
+                 (synth.banded(2000, 16), synth_torch.banded(2000, 16)), (synth.random_geometric(3000), synth_torch.random_geometric(3000))]:
+        assert (a.m, a.n) == (b.m, b.n) and np.array_equal(a.colptr, b.colptr) and np.array_equal(a.rowval, b.rowval)
