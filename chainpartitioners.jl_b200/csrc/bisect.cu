@@ -134,11 +134,231 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming probe (kernel "probe_stream"): the device form of the reference's lazy probes
+// (LazyBisectCostBottleneckSplitter.jl:194-229 connectivity, :323-359 monotonized symmetric).
+// The reference streams cch[] = previous column of every nonzero and counts `cch[q] < j` for the
+// current part start j; a part ends where the running cost first exceeds c.  Here one 8-CTA cluster
+// per threshold streams the same link array in super-steps of 8 x 16384 elements: ballots turn
+// `prev < j` into bit masks, a block scan + a DSMEM exchange give the running count at every column
+// boundary inside the tile, and all boundaries of the tile are tested at once.  No dominance index is
+// needed for bisection at all.
+// ------------------------------------------------------------------------------------------------
+static constexpr int SP_THREADS = 1024;
+static constexpr int SP_VEC = 8;                       // 128-bit loads per thread per super-step
+static constexpr int SP_CE = SP_THREADS * SP_VEC * 4;  // 32768 elements per CTA per super-step
+static constexpr int SP_GROUPS = SP_VEC * 32;          // 128-element groups per CTA (one warp-wide uint4 load each)
+
+// `prev < j` count among the first x elements of this CTA's slice, from the per-group masks
+__device__ __forceinline__ u32 stream_prefix(const u32* s_mask, const u32* s_cum, u32 x) {
+  const u32 g = x >> 7, r = x & 127u;
+  u32 cnt = s_cum[g];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int nl = ((int)r - k + 3) >> 2;  // lanes l with 4 l + k < r
+    const u32 msk = nl >= 32 ? 0xffffffffu : (nl <= 0 ? 0u : ((1u << nl) - 1u));
+    cnt += __popc(s_mask[g * 4 + k] & msk);
+  }
+  return cnt;
+}
+
+struct DevStream {
+  const u32* prev;    // [Ne]
+  const u32* colidx;  // [Ne]
+  const u32* P;       // element offsets of the column boundaries, 1 <= x <= n+1
+  const u32* Wt;      // prefix of the pin-like term, 1 <= x <= n+1
+  u32 Ne, n;
+  int same_w;         // Wt == P
+  double cf[4];
+  i64 ci[4];
+};
+
+template <class T> struct StreamCoef;
+template <> struct StreamCoef<i64> { static __device__ __forceinline__ i64 get(const DevStream& s, int t) { return s.ci[t]; } };
+template <> struct StreamCoef<double> { static __device__ __forceinline__ double get(const DevStream& s, int t) { return s.cf[t]; } };
+template <class T> __device__ __forceinline__ T stream_cost(const DevStream& s, i64 nv, i64 w, i64 g) {
+  using C = StreamCoef<T>;  // alpha + n_vertices * b_vertex + n_pins * b_pin + n_nets * b_net, left to right
+  return C::get(s, 0) + (T)nv * C::get(s, 1) + (T)w * C::get(s, 2) + (T)g * C::get(s, 3);
+}
+
+template <class T>
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS, 1)
+    k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
+                   int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c) {
+  __shared__ u32 s_mask[SP_GROUPS * 4 + 4];
+  __shared__ u32 s_cum[SP_GROUPS + 1];
+  __shared__ u32 s_warp[32];
+  __shared__ double s_c;
+  __shared__ int s_valid;
+  __shared__ u32 s_xa[2][BS_CLUSTER];     // per-CTA `prev < j` totals of the tile
+  __shared__ u32 s_xb[2][2][BS_CLUSTER];  // per-CTA (feasible boundaries, boundaries)
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int node = blockIdx.x / BS_CLUSTER;
+  const bool writer = crank == 0 && tid == 0;
+  if (tid == 0) {
+    int valid = st->done ? 0 : 1;
+    double lo = st->c_lo, hi = st->c_hi;
+    int path[BS_MAX_DEPTH];
+    int len = 0;
+    for (int i = node; i > 0; i = (i - 1) >> 1) path[len++] = (i & 1);
+    for (int t = len - 1; t >= 0 && valid; --t) {
+      if (!(lo * eps1 < hi)) { valid = 0; break; }
+      const double c = (lo + hi) / 2;
+      if (path[t]) hi = c; else lo = c;
+    }
+    if (valid && !(lo * eps1 < hi)) valid = 0;
+    s_valid = valid;
+    s_c = (lo + hi) / 2;
+    for (int k = 0; k < 4; ++k) s_mask[SP_GROUPS * 4 + k] = 0;
+  }
+  __syncthreads();
+  if (!s_valid) {
+    if (writer) node_res[node] = 0;
+    return;
+  }
+  const double c = s_c;
+  const u32 n1 = s.n + 1;
+  const u32 Ne = s.Ne;
+  constexpr u32 TE = (u32)SP_CE * BS_CLUSTER;
+  int* spl = node_spl + (size_t)node * (K + 2);
+  if (writer) { spl[1] = 1; spl[K + 1] = (int)n1; }
+  int ph = 0;
+  u32 j = 1;
+  bool broke = false, feasible = false;
+  for (int k = 1; k <= K; ++k) {
+    // largest boundary r >= j with c(j, r) <= c
+    if (!cost_leq(stream_cost<T>(s, 0, 0, 0), c)) { broke = true; break; }  // even the empty part exceeds c
+    const u32 e0 = __ldg(s.P + j);
+    const i64 wj = (i64)__ldg(s.Wt + j);
+    u32 jlast = j;
+    u32 grun = 0;
+    bool first = true;
+    for (u32 e_tile = e0 & ~3u;; e_tile += TE) {  // 16-byte aligned tiles; elements left of e0 are masked out
+      const u32 e_c = e_tile + crank * SP_CE;
+      // ---- bit masks of `prev < j`: 8 warp-wide 128-bit loads, 4 ballots each ----
+#pragma unroll
+      for (int v = 0; v < SP_VEC; ++v) {
+        const u32 g = v * 32 + warp;
+        const u32 idx = e_c + g * 128 + lane * 4;
+        uint4 pv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if ((u64)idx + 4 <= Ne) {
+          pv = __ldg(reinterpret_cast<const uint4*>(s.prev + idx));
+        } else {
+          if (idx < Ne) pv.x = __ldg(s.prev + idx);
+          if (idx + 1 < Ne) pv.y = __ldg(s.prev + idx + 1);
+          if (idx + 2 < Ne) pv.z = __ldg(s.prev + idx + 2);
+        }
+        const bool head = idx < e0;  // only the first few elements of the first tile
+        const unsigned m0 = __ballot_sync(0xffffffffu, pv.x < j && !(head && idx + 0 < e0));
+        const unsigned m1 = __ballot_sync(0xffffffffu, pv.y < j && !(head && idx + 1 < e0));
+        const unsigned m2 = __ballot_sync(0xffffffffu, pv.z < j && !(head && idx + 2 < e0));
+        const unsigned m3 = __ballot_sync(0xffffffffu, pv.w < j && !(head && idx + 3 < e0));
+        if (lane < 4) s_mask[g * 4 + lane] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
+      }
+      __syncthreads();
+      // ---- exclusive scan of the 256 group popcounts by warp 0 (8 groups per lane); the other warps
+      //      go straight to the cluster barrier below ----
+      u32 tot_c = 0;
+      if (warp == 0) {
+        u32 loc[8];
+        u32 sum = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint4 mk = *reinterpret_cast<const uint4*>(&s_mask[(lane * 8 + t) * 4]);
+          loc[t] = sum;
+          sum += __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
+        }
+        u32 inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += y;
+        }
+        const u32 excl = inc - sum;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s_cum[lane * 8 + t] = excl + loc[t];
+        tot_c = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) s_cum[SP_GROUPS] = tot_c;
+      }
+      if (tid < BS_CLUSTER) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
+      cluster.sync();  // also orders s_cum for the boundary phase
+      u32 base_c = 0, tile_tot = 0;
+#pragma unroll
+      for (int p = 0; p < BS_CLUSTER; ++p) {
+        const u32 v = s_xa[ph][p];
+        if (p < (int)crank) base_c += v;
+        tile_tot += v;
+      }
+      // ---- column boundaries whose element offset falls into (e_c, e_c + CE] ----
+      u32 ja, jb;
+      if (first && crank == 0) ja = j + 1;
+      else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
+      if (e_c >= Ne && !(first && crank == 0)) jb = 0;
+      else jb = ((u64)e_c + SP_CE >= Ne) ? n1 : __ldg(s.colidx + e_c + SP_CE) + 1;
+      const u32 nb = (jb >= ja) ? jb - ja + 1 : 0;
+      auto feasible_at = [&](u32 jp) -> bool {
+        const u32 pj = __ldg(s.P + jp);
+        const u32 g = grun + base_c + stream_prefix(s_mask, s_cum, pj - e_c);
+        const i64 w = (i64)(s.same_w ? pj : __ldg(s.Wt + jp)) - wj;
+        return cost_leq(stream_cost<T>(s, (i64)jp - (i64)j, w, (i64)g), c);
+      };
+      // monotone costs: the feasible boundaries of this CTA form a prefix [ja, ja + cnt).  Two strided
+      // passes locate its end: 1024 evenly spaced probes, then the boundaries inside the crossing stride.
+      u32 cnt = 0;
+      if (nb > 0) {
+        const u32 stride = (nb + SP_THREADS - 1) / SP_THREADS;
+        const u32 t0 = (u32)tid * stride;  // offsets 0, stride, 2 stride, ...
+        const int ct = __syncthreads_count(t0 < nb && feasible_at(ja + t0));
+        if (ct > 0) {
+          const u32 base = (u32)(ct - 1) * stride;  // last feasible probe
+          cnt = base + 1;
+          if (stride > 1) {
+            const u32 off = base + 1 + tid;
+            const bool ok = tid < stride - 1 && off < nb && feasible_at(ja + off);
+            cnt += __syncthreads_count(ok);
+          }
+        }
+      }
+      if (tid < BS_CLUSTER) {
+        *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
+        *cluster.map_shared_rank(&s_xb[ph][1][crank], tid) = nb;
+      }
+      cluster.sync();
+      u32 feas = 0, nbs = 0;
+#pragma unroll
+      for (int p = 0; p < BS_CLUSTER; ++p) { feas += s_xb[ph][0][p]; nbs += s_xb[ph][1][p]; }
+      ph ^= 1;
+      first = false;
+      jlast += feas;
+      if (feas < nbs) break;                   // the cost crossed c inside this tile
+      if ((u64)e_tile + TE >= Ne) break;       // streamed to the end: jlast == n + 1
+      grun += tile_tot;
+    }
+    if (k == K) { feasible = (jlast == n1); break; }
+    if (writer) spl[k + 1] = (int)jlast;
+    j = jlast;
+  }
+  if (writer) {
+    node_c[node] = c;
+    node_res[node] = (!broke && feasible) ? 2 : 1;
+  }
+  cluster.sync();
+}
+
+__global__ void k_count_zero(const u32* __restrict__ v, size_t n, u32* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += v[i] == 0u;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // walks the probed subtree by feasibility (BisectCost...:53-59)
 __global__ void k_bisect_advance(int K, int P, double eps1, BisectState* st, int* __restrict__ hint_lo, int* __restrict__ hint_hi,
                                  int* __restrict__ best, const int* __restrict__ node_spl, const int* __restrict__ node_res,
                                  const double* __restrict__ node_c) {
-  __shared__ int s_node, s_res;
   if (st->done) return;
   int node = 0;
   while (node < P) {
@@ -163,7 +383,6 @@ __global__ void k_bisect_advance(int K, int P, double eps1, BisectState* st, int
     st->rounds += 1;
     if (!(st->c_lo * eps1 < st->c_hi)) st->done = 1;
   }
-  (void)s_node; (void)s_res;
 }
 
 // pulls a read-only buffer into L2 ahead of the latency-bound probes (one prefetch per 128-byte line)
@@ -186,47 +405,89 @@ static int env_int(const char* name, int dflt) {
   return s ? std::atoi(s) : dflt;
 }
 
+// nets(1, n+1) = number of non-empty rows = links equal to 0 (ConnectivityCosts.jl:32 needs ocl(1, n+1))
+i64 count_first_occurrences(const LinkStream& ls) {
+  DBuf<u32> cnt(1);
+  cnt.zero();
+  if (ls.Ne) {
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((ls.Ne + 255) / 256, (size_t)ctx().sm_count * 16));
+    CPB_LAUNCH(k_count_zero, grid, 256, 0, ls.prev.get(), ls.Ne, cnt.get());
+  }
+  u32 h = 0;
+  CPB_CUDA(cudaMemcpyAsync(&h, cnt.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return (i64)h;
+}
+
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
   const Matrix& A = *f.A;
   CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
-  oracle_ensure_ranks(f);
+  // Connectivity-type models stream the link array (no dominance index needed); the others walk the index.
+  const bool stream = (f.dev.kind == CPB_MODEL_CONNECTIVITY || f.dev.kind == CPB_MODEL_MONOSYM) && env_int("CPB_PROBE_STREAM", 1) != 0;
+  if (stream) {
+    if (!f.ls) {
+      ProfScope prof("oracle_stripe");
+      f.ls = build_link_stream(*f.A, f.dev.kind == CPB_MODEL_MONOSYM);
+    }
+  } else {
+    oracle_ensure_ranks(f);
+  }
   double bnd[2];
   oracle_bound(f, K, bnd);  // (c_lo, c_hi) ./ 1
   if (lazy) {
     // LazyBisect...:55-57 / :233-235: c_lo = max(c_lo, f(empty part k)) -- alpha for the affine models
     double a0 = f.mdl.coef[0];
-    if (f.mdl.kind == CPB_MODEL_COLBLOCK) a0 = f.mdl.alpha_col[0];
+    if (f.mdl.kind == CPB_MODEL_COLBLOCK) a0 = f.h_alpha_col[0];
     bnd[0] = std::max(bnd[0], a0);
   }
   ProfScope prof("probe");
-  // the rank descents are dependent random sector reads: make them L2 hits when the index fits
-  for (RankStruct* rs : {f.net.get(), f.dianet.get(), f.selfnet.get(), f.selfpin.get()})
-    if (rs && rs->wm.bytes() > 0 && rs->wm.bytes() <= ((size_t)64 << 20) && env_int("CPB_L2_PREFETCH", 1)) {
-      const size_t bytes = rs->wm.bytes();
-      const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8));
-      CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
-    }
+  if (!stream)
+    // the rank descents are dependent random sector reads: make them L2 hits when the index fits
+    for (RankStruct* rs : {f.net.get(), f.dianet.get(), f.selfnet.get(), f.selfpin.get()})
+      if (rs && rs->wm.bytes() > 0 && rs->wm.bytes() <= ((size_t)64 << 20) && env_int("CPB_L2_PREFETCH", 1)) {
+        const size_t bytes = rs->wm.bytes();
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8));
+        CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
+      }
   int depth = std::min(std::max(env_int("CPB_BISECT_DEPTH", 4), 1), BS_MAX_DEPTH);
   const int P = (1 << depth) - 1;
   const double eps1 = 1 + eps;
   DBuf<BisectState> st(1);
   DBuf<int> hint_lo(K + 2), hint_hi(K + 2), best(K + 2), node_spl((size_t)P * (K + 2)), node_res(P);
   DBuf<double> node_c(P);
+  node_spl.zero();
   BisectState h{};
   h.c_lo = bnd[0];
   h.c_hi = bnd[1];
   h.done = !(h.c_lo * eps1 < h.c_hi);
   CPB_CUDA(cudaMemcpyAsync(st.get(), &h, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
   CPB_LAUNCH(k_bisect_init, 1, 256, 0, (int)K, (int)(A.n + 1), hint_lo.get(), hint_hi.get(), best.get());
+  DevStream ds{};
+  if (stream) {
+    ds.prev = f.ls->prev.get();
+    ds.colidx = f.ls->colidx.get();
+    ds.P = f.ls->P;
+    ds.Wt = (f.dev.kind == CPB_MODEL_MONOSYM) ? f.overpos.get() - 1 : A.pos.get() - 1;
+    ds.Ne = (u32)f.ls->Ne;
+    ds.n = (u32)A.n;
+    ds.same_w = ds.Wt == ds.P;
+    for (int t = 0; t < 4; ++t) { ds.cf[t] = f.dev.cf[t]; ds.ci[t] = f.dev.ci[t]; }
+  }
   const int batch = std::max(1, 6 / depth);
   for (int guard = 0; guard < 4096 && !h.done; ++guard) {
     for (int r = 0; r < batch; ++r) {
-      if (f.dev.is_float)
+      if (stream) {
+        if (f.dev.is_float)
+          CPB_LAUNCH(k_probe_stream<double>, P * BS_CLUSTER, SP_THREADS, 0, ds, (int)K, eps1, st.get(), node_spl.get(), node_res.get(), node_c.get());
+        else
+          CPB_LAUNCH(k_probe_stream<i64>, P * BS_CLUSTER, SP_THREADS, 0, ds, (int)K, eps1, st.get(), node_spl.get(), node_res.get(), node_c.get());
+      } else if (f.dev.is_float) {
         CPB_LAUNCH(k_bisect_round<double>, P * BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, eps1, st.get(), hint_lo.get(), hint_hi.get(), node_spl.get(), node_res.get(), node_c.get());
-      else
+      } else {
         CPB_LAUNCH(k_bisect_round<i64>, P * BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, eps1, st.get(), hint_lo.get(), hint_hi.get(), node_spl.get(), node_res.get(), node_c.get());
+      }
       CPB_LAUNCH(k_bisect_advance, 1, 256, 0, (int)K, P, eps1, st.get(), hint_lo.get(), hint_hi.get(), best.get(), node_spl.get(), node_res.get(), node_c.get());
     }
     CPB_CUDA(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));

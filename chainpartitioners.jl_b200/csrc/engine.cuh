@@ -22,6 +22,17 @@ struct RankStruct {
   DevRank dev() const { return DevRank{wm.dev(), P}; }
 };
 
+// the link array itself, in column order (streaming probes; also the input of the wavelet build)
+struct LinkStream {
+  DBuf<u32> prev;    // [Ne] 1-based previous column holding the same row, 0 = none
+  DBuf<u32> colidx;  // [Ne] 0-based column of each element
+  DBuf<u32> P_own;   // own prefix array (diagonal-augmented variant)
+  const u32* P = nullptr;  // P[x] = #{elements in columns < x}, 1 <= x <= n+1
+  size_t Ne = 0;
+};
+struct Matrix;
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia);
+
 // SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
@@ -54,6 +65,7 @@ struct Oracle {
   cpb_model mdl{};
   std::vector<double> h_alpha_col, h_beta_col, h_beta_row;  // host copies of tables
   std::unique_ptr<RankStruct> net, dianet, selfnet, selfpin;
+  std::unique_ptr<LinkStream> ls;  // links for the streaming probes (net or dia-net, by model)
   DBuf<u32> overpos;
   DBuf<i64> env;
   int envH = 0;
@@ -68,6 +80,7 @@ struct Oracle {
   DevOracle dev{};
 };
 void oracle_ensure_ranks(Oracle& f);
+i64 count_first_occurrences(const LinkStream& ls);
 
 std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int64_t* pi_spl, i64 pi_K);
 void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost);

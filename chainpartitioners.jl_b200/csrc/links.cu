@@ -123,11 +123,40 @@ void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N);
 }
 
-// links over (pos, row) with ncol columns and N entries -> wavelet matrix over prev[]
-static void build_net_like(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, RankStruct& rs) {
-  DBuf<u32> prev(N), colidx(N);
-  compute_prev_links(pos, row, nrow, ncol, N, prev.get(), colidx.get());
-  rs.wm.build(prev.get(), colidx.get(), N, ncol);  // colidx is dead: reuse as ping-pong scratch
+// The link array of A (dia = false) or of A + I (dia = true, SparseColorArrays.jl:72-99) in column order,
+// kept for the streaming probes; P[x] = #{elements in columns < x}.
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia) {
+  auto ls = std::make_unique<LinkStream>();
+  const size_t N = (size_t)A.N;
+  const u32 n = (u32)A.n, m = (u32)A.m;
+  if (!dia) {
+    ls->Ne = N;
+    ls->prev.alloc(N);
+    ls->colidx.alloc(N);
+    compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get());
+    ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
+    return ls;
+  }
+  CPB_REQUIRE(A.m >= A.n, "dianetcount needs m >= n");
+  DBuf<u32> add((size_t)n + 1), colidx(N);
+  CPB_LAUNCH(k_diag_missing, grid_for((size_t)n + 1), 256, 0, A.pos.get(), A.row.get(), n, add.get());
+  DBuf<u32> addscan((size_t)n + 1);
+  exclusive_scan_u32(add.get(), addscan.get(), (size_t)n + 1);
+  const size_t N2 = N + read_u32(addscan.get() + n);
+  ls->P_own.alloc((size_t)n + 2);
+  u32* pos2 = ls->P_own.get() + 1;
+  CPB_CUDA(cudaMemsetAsync(ls->P_own.get(), 0, sizeof(u32), ctx().stream));
+  CPB_LAUNCH(k_aug_pos, grid_for((size_t)n + 1), 256, 0, A.pos.get(), addscan.get(), n, pos2);
+  DBuf<u32> row2(N2);
+  expand_columns(A.pos.get(), n, colidx.get(), N);
+  if (N) CPB_LAUNCH(k_aug_rows, grid_for(N), 256, 0, A.row.get(), colidx.get(), addscan.get(), N, row2.get());
+  if (n) CPB_LAUNCH(k_aug_diag, grid_for(n), 256, 0, pos2, add.get(), n, row2.get());
+  ls->Ne = N2;
+  ls->prev.alloc(N2);
+  ls->colidx.alloc(N2);
+  compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get());
+  ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
+  return ls;
 }
 
 // sorts points by x, builds P and the wavelet matrix over val
@@ -148,28 +177,13 @@ std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which) {
   const size_t N = (size_t)A.N;
   const u32 n = (u32)A.n, m = (u32)A.m;
   switch (which) {
-    case RANK_NET: {
-      build_net_like(A.pos.get(), A.row.get(), m, n, N, *rs);
-      rs->P = A.pos.get() - 1;  // P[x] = pos[x-1] = #{nonzeros in columns < x}
-      break;
-    }
+    case RANK_NET:
     case RANK_DIANET: {
-      CPB_REQUIRE(A.m >= A.n, "dianetcount needs m >= n");
-      DBuf<u32> add((size_t)n + 1), colidx(N);
-      CPB_LAUNCH(k_diag_missing, grid_for((size_t)n + 1), 256, 0, A.pos.get(), A.row.get(), n, add.get());
-      DBuf<u32> addscan((size_t)n + 1);
-      exclusive_scan_u32(add.get(), addscan.get(), (size_t)n + 1);
-      const size_t N2 = N + read_u32(addscan.get() + n);
-      rs->P_own.alloc((size_t)n + 2);
-      u32* pos2 = rs->P_own.get() + 1;
-      CPB_CUDA(cudaMemsetAsync(rs->P_own.get(), 0, sizeof(u32), ctx().stream));
-      CPB_LAUNCH(k_aug_pos, grid_for((size_t)n + 1), 256, 0, A.pos.get(), addscan.get(), n, pos2);
-      DBuf<u32> row2(N2);
-      expand_columns(A.pos.get(), n, colidx.get(), N);
-      if (N) CPB_LAUNCH(k_aug_rows, grid_for(N), 256, 0, A.row.get(), colidx.get(), addscan.get(), N, row2.get());
-      if (n) CPB_LAUNCH(k_aug_diag, grid_for(n), 256, 0, pos2, add.get(), n, row2.get());
-      build_net_like(pos2, row2.get(), m, n, N2, *rs);
-      rs->P = rs->P_own.get();  // P[x] = pos2[x-1]
+      // the wavelet build consumes the link array (ping-pong) and the column index (scratch)
+      auto ls = build_link_stream(A, which == RANK_DIANET);
+      rs->wm.build(ls->prev.get(), ls->colidx.get(), ls->Ne, n);
+      rs->P_own = std::move(ls->P_own);
+      rs->P = (which == RANK_DIANET) ? rs->P_own.get() : A.pos.get() - 1;
       break;
     }
     case RANK_SELFNET: {

@@ -259,7 +259,13 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
     }
     case CPB_MODEL_CONNECTIVITY: {
       CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0, "negative beta (ConnectivityCosts.jl:29-31)");
-      c_hi = (T)query_one(f, 1, A.n + 1);
+      if (f.ranks_built) {
+        c_hi = (T)query_one(f, 1, A.n + 1);
+      } else {  // ocl(1, n+1) from the link array alone: nets(1, n+1) = number of non-empty rows
+        if (!f.ls) f.ls = build_link_stream(*f.A, false);
+        const i64 nets_all = count_first_occurrences(*f.ls);
+        c_hi = c[0] + (T)A.n * c[1] + (T)A.N * c[2] + (T)nets_all * c[3];
+      }
       c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
       break;
     }
