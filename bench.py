@@ -32,6 +32,8 @@ N_COLS = int(os.environ.get("CPB_BENCH_N", 1_000_000))
 NNZ_PER_COL = 10
 K_PARTS = 64
 EPS = 0.01
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/), bytes
+TRAFFIC = {}
 METRIC = "partition_stripe throughput (BisectCostBottleneckSplitter, Erdos-Renyi 1Mx1M, K=64)"
 UNIT = "partitions/s"
 
@@ -208,10 +210,9 @@ def main():
     sampler.join(timeout=2)
     assert np.array_equal(Phi.spl, Phi2.spl)
 
-    t_dev = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = t_dev.tolist()
+    from chainb200 import parallel
+
+    dev_ms_max, e2e_ms_max = parallel.max_over_ranks([dev_ms, e2e_ms], device="cuda")
     value = world * args.steps / (dev_ms_max / 1e3)
     e2e_value = world * args.steps / (e2e_ms_max / 1e3)
 
@@ -223,15 +224,23 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        k = prof.get("k_wm_level", {"ms": 0.0, "launches": 0, "bytes": 0.0})
-        achieved = (k["bytes"] / 1e9) / (k["ms"] / 1e3) if k["ms"] > 0 else 0.0
-        per_launch = k["launches"] // max(args.steps, 1) if k["launches"] else 0
-        roofline = {"bound": "hbm", "kernel": "k_wm_level (build_dominance: one bit level of the wavelet-matrix index)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
-                    "peak_source": peak_src,
-                    "launches_per_step": per_launch,
-                    "avg_launch_us": 1e3 * k["ms"] / max(k["launches"], 1) if k["launches"] else None,
-                    "algorithmic_bytes_per_launch": k["bytes"] / max(k["launches"], 1) if k["launches"] else None}
+        # the dominant kernel of the step = the kernel-level profile entry with the largest total time
+        kernels = {nm: v for nm, v in prof.items() if nm.startswith("k_") and v["ms"] > 0}
+        top = max(kernels, key=lambda nm: kernels[nm]["ms"]) if kernels else None
+
+        def roof(nm, note):
+            k = kernels[nm]
+            ach = (k["bytes"] / 1e9) / (k["ms"] / 1e3)
+            return {"bound": "hbm", "kernel": nm, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": TRAFFIC.get(nm),
+                    "peak_source": peak_src, "launches_per_step": k["launches"] / max(args.steps, 1), "avg_launch_us": 1e3 * k["ms"] / max(k["launches"], 1),
+                    "algorithmic_bytes_per_launch": k["bytes"] / max(k["launches"], 1), "share_of_step": k["ms"] / max(dev_ms, 1e-9), "note": note}
+
+        NOTES = {"k_probe_stream": "greedy feasibility probes of 2^4-1 thresholds, one 8-CTA cluster each; latency-bound (K sequential parts x 2 cluster barriers), "
+                                   "bytes = ONE pass over the link array per launch (SURVEY 8d G4) although every threshold streams it (mostly from L2)",
+                 "k_rs_scatter": "stable 8-bit radix scatter of (row, position) pairs inside build_links",
+                 "k_wm_level": "one bit level of the wavelet-matrix dominance index"}
+        roofline = roof(top, NOTES.get(top, "")) if top else None
+        roofline_all = [roof(nm, NOTES.get(nm, "")) for nm in sorted(kernels, key=lambda nm: -kernels[nm]["ms"])]
         phases = {nm: round(v["ms"] / args.steps, 4) for nm, v in prof.items()}
         # CPU baseline on rank 0 only, N = 1 only, bounded sample
         cpu = None
@@ -246,7 +255,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps,
                         "h2d_bytes_per_step": int((A.nnz + A.n + 1) * 8 + 512), "d2h_bytes_per_step": int((K_PARTS + 1) * 8 + 64)},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_all_kernels": roofline_all, "cpu_baseline": cpu, "clocks": sampler.summary(),
                 "phases_ms_per_step": phases, "parity": "split vector identical to the CPU oracle" if cpu else "checked at N=1"}
         print(json.dumps(line))
     if dist is not None:

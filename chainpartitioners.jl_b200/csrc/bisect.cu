@@ -479,6 +479,8 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   for (int guard = 0; guard < 4096 && !h.done; ++guard) {
     for (int r = 0; r < batch; ++r) {
       if (stream) {
+        // algorithmic bytes of one fused pass over the links for P thresholds
+        ProfScope pk("k_probe_stream", (double)(f.ls->Ne + A.n + 1) * 4.0 + (double)P * (K + 1) * 8.0);
         if (f.dev.is_float)
           CPB_LAUNCH(k_probe_stream<double>, P * BS_CLUSTER, SP_THREADS, 0, ds, (int)K, eps1, st.get(), node_spl.get(), node_res.get(), node_c.get());
         else

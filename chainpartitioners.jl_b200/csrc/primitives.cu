@@ -190,7 +190,10 @@ int radix_sort_pairs(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t 
     u32* vo = which ? vals : vals_tmp;
     CPB_LAUNCH(k_rs_hist, tiles, RS_THREADS, 0, ki, n, shift, hist.get(), tiles);
     exclusive_scan_u32(hist.get(), hist.get(), (size_t)256 * tiles);
-    CPB_LAUNCH(k_rs_scatter, tiles, RS_THREADS, 0, ki, vi, ko, vo, n, shift, hist.get(), tiles);
+    {
+      ProfScope pk("k_rs_scatter", (double)n * 16.0);  // read + write one (key, payload) pair per element
+      CPB_LAUNCH(k_rs_scatter, tiles, RS_THREADS, 0, ki, vi, ko, vo, n, shift, hist.get(), tiles);
+    }
     which ^= 1;
   }
   return which;
