@@ -98,6 +98,51 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
   }
 }
 
+// total layer by monotone divide & conquer.  For Monge ("convex", ConvexTotalChunker.jl:121) costs the
+// rightmost argmin opt(j') is non-decreasing in j' (SURVEY.md App. B / E8), so the candidates of the
+// midpoint of a segment are bounded by the argmins of its already solved neighbours.  One launch per
+// level of the implicit balanced tree over t = j' - 1 in [0, n]; one CTA per node scans its candidate
+// range with a rightmost-argmin reduction.  Total work per layer O(n log n) oracle queries.
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
+                                                     u32* __restrict__ ptr, u32 step, u32 first_t, u32 t_stride) {
+  __shared__ T s_best[8];
+  __shared__ u32 s_arg[8];
+  const u32 n = o.n;
+  const u64 t64 = (u64)first_t + (u64)blockIdx.x * t_stride;
+  if (t64 > n) return;
+  const u32 t = (u32)t64;
+  const u32 jp = t + 1;
+  u32 lo = 1, hi = jp;
+  if (step > 0) {  // neighbours t - step and min(t + step, n) are solved
+    lo = ptr[t - step + 1];
+    hi = min(hi, ptr[min(t + step, n) + 1]);
+  }
+  T best = 0;
+  u32 arg = 0;
+  for (u32 j = lo + threadIdx.x; j <= hi; j += blockDim.x) {
+    const T c = prev[j] + dev_cost<T>(o, j, jp);
+    if (arg == 0 || c <= best) { best = c; arg = j; }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const T ob = __shfl_down_sync(0xffffffffu, best, off);
+    const u32 oa = __shfl_down_sync(0xffffffffu, arg, off);
+    if (oa != 0 && (arg == 0 || ob < best || (ob == best && oa > arg))) { best = ob; arg = oa; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { s_best[w] = best; s_arg[w] = arg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      const T ob = s_best[k];
+      const u32 oa = s_arg[k];
+      if (oa != 0 && (arg == 0 || ob < best || (ob == best && oa > arg))) { best = ob; arg = oa; }
+    }
+    cur[jp] = best;
+    ptr[jp] = arg;
+  }
+}
+
 __global__ void k_dp_unravel(const u32* __restrict__ ptr, u32 n2, int K, u32 n1, i64* __restrict__ spl) {
   // DynamicSplitter.jl:89-99
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -111,6 +156,9 @@ template <class T> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* 
   const u32 n1 = (u32)A.n + 1, n2 = n1 + 1;
   CPB_REQUIRE((double)K * n2 * 4.0 < 64e9, "DP pointer table would not fit");
   ProfScope prof("dp_layer");
+  // Monge cost models with non-negative betas: monotone rightmost argmin (see k_dp_total_dc)
+  bool monge = f.mdl.kind == CPB_MODEL_WORK || f.mdl.kind == CPB_MODEL_CONNECTIVITY || f.mdl.kind == CPB_MODEL_MONOSYM;
+  for (int t = 1; t <= 3; ++t) monge = monge && f.mdl.coef[t] >= 0;
   DBuf<T> rowa(n2), rowb(n2);
   DBuf<u32> ptr((size_t)K * n2);
   DBuf<i64> spl(K + 1);
@@ -124,6 +172,20 @@ template <class T> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* 
     if (!total) {
       const unsigned g = (k == K) ? 1 : grid;
       CPB_LAUNCH(k_dp_bottleneck<T>, g, 256, 0, f.dev, prev, cur, p, jp_first);
+    } else if (monge && A.n > 64) {
+      const u32 n = (u32)A.n;
+      // j' = n + 1 (t = n): full scan; the only point the last layer needs (DynamicSplitter.jl:34)
+      CPB_LAUNCH(k_dp_total_dc<T>, 1, 256, 0, f.dev, prev, cur, p, 0u, n, 1u);
+      if (k < K) {
+        CPB_LAUNCH(k_dp_total_dc<T>, 1, 256, 0, f.dev, prev, cur, p, 0u, 0u, 1u);  // j' = 1 (t = 0)
+        u32 D = 1;
+        while (((u64)1 << D) <= n) ++D;  // 2^D > n
+        for (u32 step = (u32)1 << (D - 1); step >= 1; step >>= 1) {
+          // nodes t = step * (2 i + 1) <= n, t != n (already solved)
+          const u64 nodes = ((u64)n / step + 1) / 2;
+          if (nodes > 0) CPB_LAUNCH(k_dp_total_dc<T>, (unsigned)nodes, 256, 0, f.dev, prev, cur, p, step, step, 2 * step);
+        }
+      }
     } else {
       const size_t rows = (size_t)n1 - jp_first + 1;
       const unsigned g = (unsigned)std::min<size_t>((rows * 32 + 255) / 256, (size_t)ctx().sm_count * 8);

@@ -330,3 +330,16 @@ def test_torch_generators_match_numpy():
     for a, b in [(synth.erdos_renyi(3000, 10), synth_torch.erdos_renyi(3000, 10)), (synth.rmat(10, 16 << 10), synth_torch.rmat(10, 16 << 10)),
                  (synth.banded(2000, 16), synth_torch.banded(2000, 16)), (synth.random_geometric(3000), synth_torch.random_geometric(3000))]:
         assert (a.m, a.n) == (b.m, b.n) and np.array_equal(a.colptr, b.colptr) and np.array_equal(a.rowval, b.rowval)
+
+
+def test_dynamic_total_splitter_divide_and_conquer(ref):
+    """DynamicTotalSplitter at sizes where the device uses the monotone divide & conquer layer."""
+    for A, Ks in [(synth.laplacian5(40), [2, 3, 5]), (synth.erdos_renyi(1500, 6), [2, 4]), (synth.banded(1000, 5), [3]), (synth.rmat(10, 16 << 10), [4])]:
+        models = [cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineWorkModel(2, 3, 1)]
+        if A.m == A.n:
+            models.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 2))
+        for f in models:
+            for K in Ks:
+                mtd = cp.DynamicTotalSplitter(f)
+                g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                assert np.array_equal(g.spl, r.spl), (A, f, K, g.spl, r.spl)
