@@ -143,6 +143,33 @@ __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ Dev
   }
 }
 
+// weight-constrained layer (DynamicSplitter.jl:206-247) for weights w = a + b_v (j' - j): the feasible
+// predecessors of j' are the window [max(lo_prev, j' - W), min(j', hi_prev)]; rightmost argmin (`<=`).
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_constrained(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
+                                                        u32* __restrict__ ptr, int total, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, u32 W, int first) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + lo_k; t <= hi_k; t += stride) {
+    const u32 jp = (u32)t;
+    if (first) {  // k = 1: cst[j', 1] = f(1, j', 1)
+      cur[jp] = dev_cost<T>(o, 1, jp);
+      ptr[jp] = 1;
+      continue;
+    }
+    const u32 j0 = max(lo_p, jp > W ? jp - W : 1u);
+    const u32 j1 = min(jp, hi_p);
+    T best = 0;
+    u32 arg = 0;
+    for (u32 j = j0; j <= j1; ++j) {
+      const T c = dev_cost<T>(o, j, jp);
+      const T v = total ? prev[j] + c : max(prev[j], c);
+      if (arg == 0 || v <= best) { best = v; arg = j; }
+    }
+    cur[jp] = best;
+    ptr[jp] = arg;
+  }
+}
+
 __global__ void k_dp_unravel(const u32* __restrict__ ptr, u32 n2, int K, u32 n1, i64* __restrict__ spl) {
   // DynamicSplitter.jl:89-99
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -198,9 +225,51 @@ template <class T> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* 
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 
+template <class T> static void dynamic_constrained_T(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
+  const Matrix& A = *f.A;
+  const i64 n = A.n;
+  CPB_REQUIRE(con->w_coef[2] == 0 && con->w_coef[1] >= 1 && con->w_coef[0] >= 0,
+              "constrained dynamic splitters on the device need a vertex-count weight (VertexCount or AffineWorkModel(a, b_v >= 1, 0))");
+  const i64 W = (con->w_max - con->w_coef[0]) / con->w_coef[1];  // widest feasible part (may be <= 0)
+  // column_constraints (DynamicSplitter.jl:144-173) in closed form for this weight
+  std::vector<i64> lo(K + 1), hi(K + 1);
+  for (i64 k = K, jp = n + 1; k >= 1; --k) { lo[k] = jp; jp = std::max<i64>(1, jp - std::max<i64>(W, 0)); }
+  for (i64 k = 1, j = 1; k <= K; ++k) { hi[k] = std::min<i64>(n + 1, j + std::max<i64>(W, 0)); j = hi[k]; }
+  if (con->w_coef[0] > con->w_max) { for (i64 k = 1; k <= K; ++k) hi[k] = 1; }  // not even the empty part is feasible
+  if (hi[K] < n + 1) {  // :217-222 infeasible -> degenerate partition
+    for (i64 k = 0; k < K; ++k) h_spl_out[k] = 1;
+    h_spl_out[K] = n + 1;
+    return;
+  }
+  const u32 n1 = (u32)n + 1, n2 = n1 + 1;
+  ProfScope prof("dp_layer");
+  DBuf<T> rowa(n2), rowb(n2);
+  DBuf<u32> ptr((size_t)K * n2);
+  DBuf<i64> spl(K + 1);
+  ptr.zero();
+  T* prev = rowa.get();
+  T* cur = rowb.get();
+  for (i64 k = 1; k <= K; ++k) {
+    const size_t cnt = (size_t)(hi[k] - lo[k] + 1);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt + 255) / 256, (size_t)ctx().sm_count * 8));
+    CPB_LAUNCH(k_dp_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, total ? 1 : 0, (u32)lo[k], (u32)hi[k],
+               (u32)(k > 1 ? lo[k - 1] : 1), (u32)(k > 1 ? hi[k - 1] : 1), (u32)std::max<i64>(W, 0), k == 1 ? 1 : 0);
+    std::swap(prev, cur);
+  }
+  CPB_LAUNCH(k_dp_unravel, 1, 32, 0, ptr.get(), n2, (int)K, n1, spl.get());
+  CPB_CUDA(cudaMemcpyAsync(h_spl_out, spl.get(), (K + 1) * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
 void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
-  if (con && con->enabled) throw Error(CPB_ERR_UNSUPPORTED, "weight-constrained dynamic splitters are not built yet");
+  if (con && con->enabled) {
+    if (f.dev.kind == CPB_MODEL_BLOCK || f.dev.kind == CPB_MODEL_COLBLOCK)
+      throw Error(CPB_ERR_UNSUPPORTED, "dynamic splitters need an affine random-access oracle");
+    oracle_ensure_ranks(f);
+    if (f.dev.is_float) dynamic_constrained_T<double>(f, total, con, K, h_spl_out); else dynamic_constrained_T<i64>(f, total, con, K, h_spl_out);
+    return;
+  }
   if (f.dev.kind == CPB_MODEL_BLOCK || f.dev.kind == CPB_MODEL_COLBLOCK)
     throw Error(CPB_ERR_UNSUPPORTED, "dynamic splitters need an affine random-access oracle");
   if (!total) {

@@ -343,3 +343,19 @@ def test_dynamic_total_splitter_divide_and_conquer(ref):
                 mtd = cp.DynamicTotalSplitter(f)
                 g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
                 assert np.array_equal(g.spl, r.spl), (A, f, K, g.spl, r.spl)
+
+
+def test_constrained_dynamic_splitters(ref, fixtures):
+    """AbstractDynamicSplitter{<:ConstrainedCost} (DynamicSplitter.jl:206-247), incl. the degenerate
+    partition [1, 1, ..., n+1] returned for infeasible width constraints (:217-222)."""
+    rng = np.random.default_rng(300)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 1, 0.5), sprand(rng, 6, 10, 0.3), sprand(rng, 40, 200, 0.1)]
+    for A in mats:
+        for f in [cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0)]:
+            for w, w_max in [(cp.AffineWorkModel(0, 1, 0), 2), (cp.AffineWorkModel(0, 1, 0), 4), (cp.VertexCount(), 8), (cp.AffineWorkModel(1, 2, 0), 9),
+                             (cp.AffineWorkModel(5, 1, 0), 3)]:
+                for K in [1, 2, 3, 4, 8, 60]:
+                    for mk in (cp.DynamicTotalSplitter, cp.DynamicBottleneckSplitter):
+                        mtd = mk(cp.ConstrainedCost(f, w, w_max))
+                        g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                        assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, mk.__name__, g.spl, r.spl)
