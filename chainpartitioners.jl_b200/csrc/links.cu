@@ -21,8 +21,7 @@ struct TransposeOrder {
 static void transpose_order(const u32* row, size_t N, u64 max_row, TransposeOrder& t) {
   t.k0.alloc(N); t.v0.alloc(N); t.k1.alloc(N); t.v1.alloc(N);
   if (N) CPB_CUDA(cudaMemcpyAsync(t.k0.get(), row, N * sizeof(u32), cudaMemcpyDeviceToDevice, ctx().stream));
-  iota_u32(t.v0.get(), N);
-  const int which = radix_sort_pairs(t.k0.get(), t.v0.get(), t.k1.get(), t.v1.get(), N, bits_for(max_row));
+  const int which = radix_sort_pairs_iota(t.k0.get(), t.v0.get(), t.k1.get(), t.v1.get(), N, bits_for(max_row));
   t.keys = which ? t.k1.get() : t.k0.get();
   t.q = which ? t.v1.get() : t.v0.get();
 }
