@@ -210,6 +210,28 @@ def main():
     sampler.join(timeout=2)
     assert np.array_equal(Phi.spl, Phi2.spl)
 
+    # ---- cost-oracle query throughput (the other half of BASELINE.json's metric) ----
+    Q = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    qa = torch.randint(1, A.n + 2, (Q,), device="cuda", generator=g, dtype=torch.int64)
+    qb = torch.randint(1, A.n + 2, (Q,), device="cuda", generator=g, dtype=torch.int64)
+    qj, qjp = torch.minimum(qa, qb).contiguous(), torch.maximum(qa, qb).contiguous()
+    qout = torch.empty(Q, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ocl = cp.oracle_stripe(f, dA)
+    ocl.query_device(qj.data_ptr(), qjp.data_ptr(), qout.data_ptr(), Q)  # builds the dominance index, warms up
+    cp.synchronize()
+    q_ms = 0.0
+    for _ in range(3):
+        flush_l2()
+        cp.timer_start()
+        ocl.query_device(qj.data_ptr(), qjp.data_ptr(), qout.data_ptr(), Q)
+        q_ms += cp.timer_stop()
+    queries_per_s = 3 * Q / (q_ms / 1e3)
+    q_check = qout[:4096].cpu().numpy()
+    q_ref_args = (qj[:4096].cpu().numpy(), qjp[:4096].cpu().numpy())
+    ocl.close()
+
     from chainb200 import parallel
 
     dev_ms_max, e2e_ms_max = parallel.max_over_ranks([dev_ms, e2e_ms], device="cuda")
@@ -247,6 +269,9 @@ def main():
         if world == 1:
             per, secs, Phi_ref = cpu_reference_run(A, mtd, 3, 0)
             assert np.array_equal(Phi_ref.spl, Phi.spl), "GPU result differs from the CPU oracle"
+            import pyoracle as ref
+
+            assert np.array_equal(ref.oracle_query(f, A, *q_ref_args, hint=cp.SparseHint()), q_check), "oracle queries differ from the CPU oracle"
             cpu = {"value": 1.0 / per, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"full workload x3 (oracle build {secs[0]*1e3:.1f} ms + bisection {secs[1]*1e3:.1f} ms per step); C++ restatement of the "
                              "Julia reference, single thread (the reference has no threads)"}
@@ -255,6 +280,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps,
                         "h2d_bytes_per_step": int((A.nnz + A.n + 1) * 8 + 512), "d2h_bytes_per_step": int((K_PARTS + 1) * 8 + 64)},
+                "oracle_queries_per_s": queries_per_s * world, "oracle_query_batch": {"Q": Q, "ms": q_ms / 3, "pattern": "uniform random (j <= j') pairs, device-resident"},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_all_kernels": roofline_all, "cpu_baseline": cpu, "clocks": sampler.summary(),
                 "phases_ms_per_step": phases, "parity": "split vector identical to the CPU oracle" if cpu else "checked at N=1"}
         print(json.dumps(line))

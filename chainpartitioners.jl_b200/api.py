@@ -219,6 +219,10 @@ class StripeOracle:
             out = np.where(width <= self.constraint.w_max, out, np.inf)
         return out
 
+    def query_device(self, d_j: int, d_jp: int, d_out: int, Q: int):
+        """Batched queries on device-resident Int64 arrays (raw device pointers), result Float64 on the device."""
+        _check(load_library().cpb_oracle_query_device(self._h, int(Q), ctypes.c_void_p(d_j), ctypes.c_void_p(d_jp), ctypes.c_void_p(d_out)))
+
     def __call__(self, j, jp, k=None):
         r = self.query(j, jp, k)
         if np.ndim(j) == 0:

@@ -359,3 +359,36 @@ def test_constrained_dynamic_splitters(ref, fixtures):
                         mtd = mk(cp.ConstrainedCost(f, w, w_max))
                         g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
                         assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, mk.__name__, g.spl, r.spl)
+
+
+def test_degenerate_inputs(ref):
+    """Empty matrices, empty columns/rows, K > n, single column -- the ragged cases."""
+    z = np.zeros(0, dtype=np.int64)
+    mats = [
+        cp.SparseMatrixCSC(5, 4, np.ones(5, dtype=np.int64), z),                      # no nonzeros at all
+        cp.SparseMatrixCSC(3, 1, np.array([1, 3]), np.array([1, 3])),                 # one column
+        cp.SparseMatrixCSC(1, 6, np.array([1, 1, 2, 2, 2, 3, 3]), np.array([1, 1])),  # one row, mostly empty columns
+        cp.SparseMatrixCSC(4, 4, np.array([1, 1, 1, 1, 5]), np.array([1, 2, 3, 4])),  # everything in the last column
+    ]
+    f = cp.AffineConnectivityModel(0, 3, 1, 3)
+    s = cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 1)
+    for A in mats:
+        j = np.array([1, 1, A.n + 1, max(1, A.n)])
+        jp = np.array([1, A.n + 1, A.n + 1, A.n + 1])
+        assert np.array_equal(cp.netcount(A).query(j, jp), ref.netcount(A, j, jp))
+        assert np.array_equal(cp.selfnetcount(A).query(j, jp), ref.selfnetcount(A, j, jp))
+        for K in [1, 2, 7]:
+            for mtd in [cp.DynamicBottleneckSplitter(f), cp.DynamicTotalSplitter(f), cp.BisectCostBottleneckSplitter(f, 0.1),
+                        cp.LazyBisectCostBottleneckSplitter(f, 0.01), cp.BisectCostBottleneckSplitter(cp.AffineWorkModel(0, 10, 1), 0.1)]:
+                g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                assert np.array_equal(g.spl, r.spl), (A, K, type(mtd).__name__, g.spl, r.spl)
+            if A.m == A.n:
+                mtd = cp.LazyBisectCostBottleneckSplitter(s, 0.1)
+                assert np.array_equal(cp.partition_stripe(A, K, mtd).spl, ref.partition_stripe(A, K, mtd).spl)
+        for w_max in [1, 3]:
+            for mtd in [cp.DynamicTotalChunker(f, w_max), cp.ConvexTotalChunker(cp.ConstrainedCost(f, cp.VertexCount(), w_max)), cp.OverlapChunker(0.5, w_max), cp.StrictChunker(w_max)]:
+                g, r = cp.pack_stripe(A, mtd), ref.pack_stripe(A, mtd)
+                assert np.array_equal(g.spl, r.spl), (A, w_max, type(mtd).__name__, g.spl, r.spl)
+        B = cp.adjointpattern(A)
+        Br = ref.adjointpattern(A)
+        assert np.array_equal(B.colptr, Br.colptr) and np.array_equal(B.rowval, Br.rowval)
