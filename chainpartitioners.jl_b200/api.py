@@ -20,7 +20,7 @@ __all__ = [
     "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
-    "launch_count", "timer_start", "timer_stop", "init", "synchronize", "library_path", "load_library", "CpbError",
+    "launch_count", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
 ]
 
 I64 = np.int64
@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
+    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish",
 ]
 
 
@@ -78,6 +79,10 @@ def load_library():
         lib.cpb_partition_stripe.argtypes = [vp, i32, ctypes.POINTER(T.CConstraint), dbl, i64, vp]
         lib.cpb_pack_stripe.argtypes = [vp, vp, i32, ctypes.POINTER(T.CConstraint), dbl, i64, vp, ctypes.POINTER(i64), vp]
         lib.cpb_profile_get.argtypes = [i32, vp, vp, vp, vp]
+        lib.cpb_bisect_begin.argtypes = [vp, i32, dbl, i64, i32, vp, vp, vp, ctypes.POINTER(vp)]
+        lib.cpb_bisect_probe.argtypes = [vp, i32, i32]
+        lib.cpb_bisect_advance.argtypes = [vp, ctypes.POINTER(i32)]
+        lib.cpb_bisect_finish.argtypes = [vp, vp]
         _lib = lib
     return _lib
 
@@ -443,6 +448,39 @@ def pack_plaid(A, method, adj_A=None, **kwargs):
         finally:
             if own_adj or not isinstance(adj_A, DeviceMatrix):
                 dT.close()
+
+
+class StepwiseBisection:
+    """One BisectCost / LazyBisectCost solve as explicit rounds (``cpb_bisect_*``): the 2^depth - 1
+    speculative thresholds of a round may be probed by different GPUs; the caller exchanges the node
+    buffers (device pointers of caller-owned arrays, e.g. torch tensors) between ``probe`` and ``advance``."""
+
+    def __init__(self, ocl: StripeOracle, method, K: int, depth: int, d_res: int = 0, d_c: int = 0, d_spl: int = 0):
+        code, _, eps = T.split_method_code(method)
+        self.K = int(K)
+        self.nodes = (1 << depth) - 1
+        self._h = ctypes.c_void_p()
+        _check(load_library().cpb_bisect_begin(ocl._h, code, eps, self.K, int(depth), ctypes.c_void_p(d_res), ctypes.c_void_p(d_c),
+                                               ctypes.c_void_p(d_spl), ctypes.byref(self._h)))
+
+    def probe(self, node_lo: int, node_hi: int):
+        _check(load_library().cpb_bisect_probe(self._h, int(node_lo), int(node_hi)))
+
+    def advance(self) -> bool:
+        done = ctypes.c_int()
+        _check(load_library().cpb_bisect_advance(self._h, ctypes.byref(done)))
+        return bool(done.value)
+
+    def finish(self) -> T.SplitPartition:
+        spl = np.empty(self.K + 1, dtype=I64)
+        h, self._h = self._h, None
+        _check(load_library().cpb_bisect_finish(h, _p(spl)))
+        return T.SplitPartition(self.K, spl)
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and _lib is not None:
+            _lib.cpb_bisect_finish(self._h, None)
+            self._h = None
 
 
 # ------------------------------------------------------------------------------- measurement hooks

@@ -29,7 +29,8 @@ namespace cpb {
 static constexpr int BS_THREADS = 128;
 static constexpr int BS_CLUSTER = 8;
 static constexpr int BS_WIDTH = BS_THREADS * BS_CLUSTER;  // candidates per round
-static constexpr int BS_MAX_DEPTH = 4;
+static constexpr int BS_MAX_DEPTH = 8;      // deepest speculation tree (all ranks together)
+static constexpr int BS_LOCAL_DEPTH = 4;    // a single GPU hosts at most 2^4 clusters of 8 CTAs
 
 struct BisectState {
   double c_lo, c_hi;
@@ -74,12 +75,12 @@ template <class T>
 __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
     k_bisect_round(const __grid_constant__ DevOracle o, int K, double eps1, const BisectState* __restrict__ st,
                    const int* __restrict__ hint_lo, const int* __restrict__ hint_hi, int* __restrict__ node_spl,
-                   int* __restrict__ node_res, double* __restrict__ node_c) {
+                   int* __restrict__ node_res, double* __restrict__ node_c, int node_base) {
   __shared__ double s_c;
   __shared__ int s_valid;
   __shared__ int s_cnt[2][BS_CLUSTER];
   cg::cluster_group cluster = cg::this_cluster();
-  const int node = blockIdx.x / BS_CLUSTER;
+  const int node = node_base + blockIdx.x / BS_CLUSTER;
   const bool writer = cluster.block_rank() == 0 && threadIdx.x == 0;
   if (threadIdx.x == 0) {
     int valid = st->done ? 0 : 1;
@@ -184,7 +185,7 @@ template <class T> __device__ __forceinline__ T stream_cost(const DevStream& s, 
 template <class T>
 __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS, 1)
     k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
-                   int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c) {
+                   int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c, int node_base) {
   __shared__ u32 s_mask[SP_GROUPS * 4 + 4];
   __shared__ u32 s_cum[SP_GROUPS + 1];
   __shared__ u32 s_warp[32];
@@ -195,7 +196,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int node = blockIdx.x / BS_CLUSTER;
+  const int node = node_base + blockIdx.x / BS_CLUSTER;
   const bool writer = crank == 0 && tid == 0;
   if (tid == 0) {
     int valid = st->done ? 0 : 1;
@@ -419,14 +420,35 @@ i64 count_first_occurrences(const LinkStream& ls) {
   return (i64)h;
 }
 
-void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
+// ---- one bisection as a sequence of steps, so that the nodes of a round can be probed by different
+//      ranks (chainb200.parallel.partition_stripe_sharded) ----
+struct BisectRun {
+  Oracle* f = nullptr;
+  bool stream = false;
+  i64 K = 0;
+  double eps1 = 1;
+  int depth = 1, P = 1;
+  DBuf<BisectState> st;
+  DBuf<int> hint_lo, hint_hi, best, own_spl, own_res;
+  DBuf<double> own_c;
+  int* node_spl = nullptr;
+  int* node_res = nullptr;
+  double* node_c = nullptr;
+  DevStream ds{};
+  bool done = false;
+};
+
+BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int depth, int* d_node_res, double* d_node_c, int* d_node_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
   const Matrix& A = *f.A;
   CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
+  auto run = std::make_unique<BisectRun>();
+  run->f = &f;
+  run->K = K;
   // Connectivity-type models stream the link array (no dominance index needed); the others walk the index.
-  const bool stream = (f.dev.kind == CPB_MODEL_CONNECTIVITY || f.dev.kind == CPB_MODEL_MONOSYM) && env_int("CPB_PROBE_STREAM", 1) != 0;
-  if (stream) {
+  run->stream = (f.dev.kind == CPB_MODEL_CONNECTIVITY || f.dev.kind == CPB_MODEL_MONOSYM) && env_int("CPB_PROBE_STREAM", 1) != 0;
+  if (run->stream) {
     if (!f.ls) {
       ProfScope prof("oracle_stripe");
       f.ls = build_link_stream(*f.A, f.dev.kind == CPB_MODEL_MONOSYM);
@@ -442,8 +464,7 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     if (f.mdl.kind == CPB_MODEL_COLBLOCK) a0 = f.h_alpha_col[0];
     bnd[0] = std::max(bnd[0], a0);
   }
-  ProfScope prof("probe");
-  if (!stream)
+  if (!run->stream)
     // the rank descents are dependent random sector reads: make them L2 hits when the index fits
     for (RankStruct* rs : {f.net.get(), f.dianet.get(), f.selfnet.get(), f.selfpin.get()})
       if (rs && rs->wm.bytes() > 0 && rs->wm.bytes() <= ((size_t)64 << 20) && env_int("CPB_L2_PREFETCH", 1)) {
@@ -451,21 +472,33 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8));
         CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
       }
-  int depth = std::min(std::max(env_int("CPB_BISECT_DEPTH", 4), 1), BS_MAX_DEPTH);
-  const int P = (1 << depth) - 1;
-  const double eps1 = 1 + eps;
-  DBuf<BisectState> st(1);
-  DBuf<int> hint_lo(K + 2), hint_hi(K + 2), best(K + 2), node_spl((size_t)P * (K + 2)), node_res(P);
-  DBuf<double> node_c(P);
-  node_spl.zero();
+  run->depth = std::min(std::max(depth, 1), BS_MAX_DEPTH);
+  run->P = (1 << run->depth) - 1;
+  run->eps1 = 1 + eps;
+  const int P = run->P;
+  run->st.alloc(1);
+  run->hint_lo.alloc(K + 2);
+  run->hint_hi.alloc(K + 2);
+  run->best.alloc(K + 2);
+  if (d_node_res && d_node_c && d_node_spl) {
+    run->node_res = d_node_res; run->node_c = d_node_c; run->node_spl = d_node_spl;
+  } else {
+    run->own_spl.alloc((size_t)P * (K + 2));
+    run->own_res.alloc(P);
+    run->own_c.alloc(P);
+    run->own_spl.zero();
+    run->node_res = run->own_res.get(); run->node_c = run->own_c.get(); run->node_spl = run->own_spl.get();
+  }
   BisectState h{};
   h.c_lo = bnd[0];
   h.c_hi = bnd[1];
-  h.done = !(h.c_lo * eps1 < h.c_hi);
-  CPB_CUDA(cudaMemcpyAsync(st.get(), &h, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
-  CPB_LAUNCH(k_bisect_init, 1, 256, 0, (int)K, (int)(A.n + 1), hint_lo.get(), hint_hi.get(), best.get());
-  DevStream ds{};
-  if (stream) {
+  h.done = !(h.c_lo * run->eps1 < h.c_hi);
+  run->done = h.done != 0;
+  CPB_CUDA(cudaMemcpyAsync(run->st.get(), &h, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // h is a stack variable
+  CPB_LAUNCH(k_bisect_init, 1, 256, 0, (int)K, (int)(A.n + 1), run->hint_lo.get(), run->hint_hi.get(), run->best.get());
+  if (run->stream) {
+    DevStream& ds = run->ds;
     ds.prev = f.ls->prev.get();
     ds.colidx = f.ls->colidx.get();
     ds.P = f.ls->P;
@@ -475,31 +508,72 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     ds.same_w = ds.Wt == ds.P;
     for (int t = 0; t < 4; ++t) { ds.cf[t] = f.dev.cf[t]; ds.ci[t] = f.dev.ci[t]; }
   }
-  const int batch = std::max(1, 6 / depth);
-  for (int guard = 0; guard < 4096 && !h.done; ++guard) {
-    for (int r = 0; r < batch; ++r) {
-      if (stream) {
-        // algorithmic bytes of one fused pass over the links for P thresholds
-        ProfScope pk("k_probe_stream", (double)(f.ls->Ne + A.n + 1) * 4.0 + (double)P * (K + 1) * 8.0);
-        if (f.dev.is_float)
-          CPB_LAUNCH(k_probe_stream<double>, P * BS_CLUSTER, SP_THREADS, 0, ds, (int)K, eps1, st.get(), node_spl.get(), node_res.get(), node_c.get());
-        else
-          CPB_LAUNCH(k_probe_stream<i64>, P * BS_CLUSTER, SP_THREADS, 0, ds, (int)K, eps1, st.get(), node_spl.get(), node_res.get(), node_c.get());
-      } else if (f.dev.is_float) {
-        CPB_LAUNCH(k_bisect_round<double>, P * BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, eps1, st.get(), hint_lo.get(), hint_hi.get(), node_spl.get(), node_res.get(), node_c.get());
-      } else {
-        CPB_LAUNCH(k_bisect_round<i64>, P * BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, eps1, st.get(), hint_lo.get(), hint_hi.get(), node_spl.get(), node_res.get(), node_c.get());
-      }
-      CPB_LAUNCH(k_bisect_advance, 1, 256, 0, (int)K, P, eps1, st.get(), hint_lo.get(), hint_hi.get(), best.get(), node_spl.get(), node_res.get(), node_c.get());
+  return run.release();
+}
+
+// probes the nodes [node_lo, node_hi) of the current round's speculation tree
+void bisect_probe(BisectRun& run, int node_lo, int node_hi) {
+  node_lo = std::max(node_lo, 0);
+  node_hi = std::min(node_hi, run.P);
+  if (node_hi <= node_lo) return;
+  Oracle& f = *run.f;
+  const int K = (int)run.K;
+  for (int base = node_lo; base < node_hi; base += (1 << BS_LOCAL_DEPTH)) {
+    const int cnt = std::min(node_hi - base, 1 << BS_LOCAL_DEPTH);
+    if (run.stream) {
+      // algorithmic bytes of one fused pass over the links for the thresholds of this launch
+      ProfScope pk("k_probe_stream", (double)(f.ls->Ne + f.A->n + 1) * 4.0 + (double)cnt * (K + 1) * 8.0);
+      if (f.dev.is_float)
+        CPB_LAUNCH(k_probe_stream<double>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, base);
+      else
+        CPB_LAUNCH(k_probe_stream<i64>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, base);
+    } else if (f.dev.is_float) {
+      CPB_LAUNCH(k_bisect_round<double>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, base);
+    } else {
+      CPB_LAUNCH(k_bisect_round<i64>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, base);
     }
-    CPB_CUDA(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
-    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   }
-  CPB_REQUIRE(h.done, "bisection did not terminate (eps too small for Float64?)");
+}
+
+// walks the (complete) tree of the round; `sync` reads back whether the bisection has finished
+bool bisect_advance(BisectRun& run, bool sync) {
+  CPB_LAUNCH(k_bisect_advance, 1, 256, 0, (int)run.K, run.P, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.best.get(),
+             run.node_spl, run.node_res, run.node_c);
+  if (sync) {
+    BisectState h{};
+    CPB_CUDA(cudaMemcpyAsync(&h, run.st.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    run.done = h.done != 0;
+  }
+  return run.done;
+}
+
+void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
+  std::unique_ptr<BisectRun> run(run_ptr);
+  if (!h_spl_out) return;
+  CPB_REQUIRE(run->done, "bisection has not finished");
+  const i64 K = run->K;
   std::vector<int> hb(K + 2);
-  CPB_CUDA(cudaMemcpyAsync(hb.data(), best.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(hb.data(), run->best.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = hb[k];
+}
+
+void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
+  const int depth = std::min(std::max(env_int("CPB_BISECT_DEPTH", BS_LOCAL_DEPTH), 1), BS_LOCAL_DEPTH);
+  BisectRun* run = bisect_begin(f, lazy, eps, K, depth, nullptr, nullptr, nullptr);
+  try {
+    ProfScope prof("probe");
+    for (int guard = 0; guard < 4096 && !run->done; ++guard) {
+      bisect_probe(*run, 0, run->P);
+      bisect_advance(*run, true);
+    }
+    CPB_REQUIRE(run->done, "bisection did not terminate (eps too small for Float64?)");
+  } catch (...) {
+    delete run;
+    throw;
+  }
+  bisect_finish(run, h_spl_out);
 }
 
 }  // namespace cpb

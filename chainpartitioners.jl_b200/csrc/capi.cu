@@ -308,6 +308,38 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
   CPB_API_END
 }
 
+// ---- stepwise bisection (multi-GPU threshold sharding) ----
+int cpb_bisect_begin(cpb_oracle* f, int method, double eps, int64_t K, int depth, int32_t* d_node_res, double* d_node_c,
+                     int32_t* d_node_spl, cpb_bisect** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && out, "NULL argument");
+  CPB_REQUIRE(method == CPB_SPLIT_BISECT_COST || method == CPB_SPLIT_LAZY_BISECT_COST, "stepwise bisection: bisect methods only");
+  *out = reinterpret_cast<cpb_bisect*>(bisect_begin(*f->O, method == CPB_SPLIT_LAZY_BISECT_COST, eps, K, depth, d_node_res, d_node_c, d_node_spl));
+  CPB_API_END
+}
+int cpb_bisect_probe(cpb_bisect* b, int node_lo, int node_hi) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(b, "NULL argument");
+  bisect_probe(*reinterpret_cast<BisectRun*>(b), node_lo, node_hi);
+  CPB_API_END
+}
+int cpb_bisect_advance(cpb_bisect* b, int* done_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(b && done_out, "NULL argument");
+  *done_out = bisect_advance(*reinterpret_cast<BisectRun*>(b), true) ? 1 : 0;
+  CPB_API_END
+}
+int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(b, "NULL argument");
+  bisect_finish(reinterpret_cast<BisectRun*>(b), spl_out);
+  CPB_API_END
+}
+
 int cpb_pack_stripe(cpb_matrix* A, cpb_oracle* f, int method, const cpb_constraint* con, double rho, int64_t w_max,
                     int64_t* spl_out, int64_t* K_out, int64_t* n_nets_out) {
   CPB_API_BEGIN

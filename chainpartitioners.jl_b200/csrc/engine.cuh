@@ -90,6 +90,11 @@ void count_query(Matrix& A, int which, i64 Q, const i64* d_j, const i64* d_jp, i
 
 // solvers (bisect.cu / dynamic.cu / chunk.cu)
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out);
+struct BisectRun;
+BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int depth, int* d_node_res, double* d_node_c, int* d_node_spl);
+void bisect_probe(BisectRun& run, int node_lo, int node_hi);
+bool bisect_advance(BisectRun& run, bool sync);
+void bisect_finish(BisectRun* run, int64_t* h_spl_out);
 void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out);
 void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, double rho, i64 w_max, int64_t* h_spl_out,
                 int64_t* K_out, int64_t* n_nets_out);

@@ -33,3 +33,67 @@ def gather_split_vectors(local: dict, n_problems: int, K: int, device="cpu") -> 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(table, op=dist.ReduceOp.SUM)  # disjoint rows: SUM == gather
     return table.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sharding ONE bisection across ranks (BASELINE.json north_star: "candidate-threshold sets of the
+# bisection ... NCCL carries only the exchange of feasible thresholds").  Every rank holds the matrix
+# and builds the link array; per round the 2^depth - 1 thresholds of the speculation tree are split
+# into contiguous node ranges, one per rank; the per-node results (feasible?, threshold, split
+# vector) are exchanged with one all-gather; every rank then walks the same tree, so all ranks hold
+# the same state and the same final split vector.  The threshold sequence is the reference's, so the
+# result is identical to the single-GPU (and the CPU) one.
+# ---------------------------------------------------------------------------------------------------
+
+
+def node_slots(world: int, local_depth: int = 4):
+    """-> (tree depth, nodes per rank).  Each rank hosts at most 2^local_depth clusters."""
+    depth = local_depth
+    while depth < 8 and ((1 << depth) - 1) < world * ((1 << local_depth) - 1) and (1 << (depth + 1)) - 1 <= world * (1 << local_depth):
+        depth += 1
+    per = -(-((1 << depth) - 1) // world)
+    return depth, per
+
+
+def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulate_ranks: bool = False):
+    """``partition_stripe(A, K, BisectCost/LazyBisectCost...)`` with the threshold tree of every round
+    sharded over ``world`` ranks (torch.distributed must be initialised with a CUDA-capable backend when
+    world > 1).  ``emulate_ranks`` probes all node ranges from this one process (single-GPU test of the
+    sharding logic)."""
+    from . import api
+
+    depth, per = node_slots(world)
+    slots = per * world
+    K = int(K)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res = torch.zeros(slots, dtype=torch.int32, device=dev)
+    thr = torch.zeros(slots, dtype=torch.float64, device=dev)
+    spl = torch.zeros((slots, K + 2), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    _, spec, _ = api.T.split_method_code(method)
+    ocl = api.StripeOracle(spec, A)
+    try:
+        run = api.StepwiseBisection(ocl, method, K, depth, res.data_ptr(), thr.data_ptr(), spl.data_ptr())
+        nodes = run.nodes
+        done = nodes == 0
+        guard = 0
+        while True:
+            if emulate_ranks:
+                for r in range(world):
+                    run.probe(r * per, min((r + 1) * per, nodes))
+            else:
+                run.probe(rank * per, min((rank + 1) * per, nodes))
+            api.synchronize()
+            if world > 1 and not emulate_ranks:
+                lo, hi = rank * per, (rank + 1) * per
+                dist.all_gather_into_tensor(res, res[lo:hi].clone())
+                dist.all_gather_into_tensor(thr, thr[lo:hi].clone())
+                dist.all_gather_into_tensor(spl, spl[lo:hi].clone())
+                torch.cuda.synchronize()
+            done = run.advance()
+            guard += 1
+            if done or guard > 4096:
+                break
+        return run.finish()
+    finally:
+        ocl.close()

@@ -392,3 +392,31 @@ def test_degenerate_inputs(ref):
         B = cp.adjointpattern(A)
         Br = ref.adjointpattern(A)
         assert np.array_equal(B.colptr, Br.colptr) and np.array_equal(B.rowval, Br.rowval)
+
+
+def test_sharded_bisection_emulated_ranks(ref):
+    """The multi-GPU threshold sharding with all node ranges probed from one process: begin / probe(range) /
+    advance / finish through the C ABI with caller-owned (torch) node buffers."""
+    import torch
+
+    from chainb200 import parallel
+
+    torch.cuda.set_device(0)
+    A = synth.erdos_renyi(30000, 10)
+    G = synth.random_geometric(20000)
+    sym = cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 4)
+    for M, K, mtd in [(A, 16, cp.BisectCostBottleneckSplitter(AFF, 0.01)), (A, 64, cp.LazyBisectCostBottleneckSplitter(AFF, 0.001)),
+                      (G, 32, cp.LazyBisectCostBottleneckSplitter(sym, 0.1)), (A, 8, cp.BisectCostBottleneckSplitter(cp.AffineWorkModel(0, 10, 1), 0.01))]:
+        exp = ref.partition_stripe(M, K, mtd).spl
+        for world in (1, 2, 4, 8):
+            got = parallel.partition_stripe_sharded(M, K, mtd, world=world, emulate_ranks=True)
+            assert np.array_equal(got.spl, exp), (type(mtd).__name__, K, world)
+
+
+def test_node_slots():
+    from chainb200 import parallel
+
+    assert parallel.node_slots(1) == (4, 15)
+    for world in (2, 4, 8):
+        depth, per = parallel.node_slots(world)
+        assert per <= 16 and per * world >= (1 << depth) - 1 and depth == 4 + int(np.log2(world))
