@@ -20,7 +20,7 @@ __all__ = [
     "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
-    "launch_count", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
+    "launch_count", "probe_cluster_capacity", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
 ]
 
 I64 = np.int64
@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
-    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish",
+    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_probe_cluster_capacity",
 ]
 
 
@@ -451,16 +451,16 @@ def pack_plaid(A, method, adj_A=None, **kwargs):
 
 
 class StepwiseBisection:
-    """One BisectCost / LazyBisectCost solve as explicit rounds (``cpb_bisect_*``): the 2^depth - 1
-    speculative thresholds of a round may be probed by different GPUs; the caller exchanges the node
+    """One BisectCost / LazyBisectCost solve as explicit rounds (``cpb_bisect_*``): the speculative
+    thresholds of a round (the first ``nodes`` nodes of the bisection tree) may be probed by different GPUs; the caller exchanges the node
     buffers (device pointers of caller-owned arrays, e.g. torch tensors) between ``probe`` and ``advance``."""
 
-    def __init__(self, ocl: StripeOracle, method, K: int, depth: int, d_res: int = 0, d_c: int = 0, d_spl: int = 0):
+    def __init__(self, ocl: StripeOracle, method, K: int, nodes: int, d_res: int = 0, d_c: int = 0, d_spl: int = 0):
         code, _, eps = T.split_method_code(method)
         self.K = int(K)
-        self.nodes = (1 << depth) - 1
+        self.nodes = max(1, min(int(nodes), 255))
         self._h = ctypes.c_void_p()
-        _check(load_library().cpb_bisect_begin(ocl._h, code, eps, self.K, int(depth), ctypes.c_void_p(d_res), ctypes.c_void_p(d_c),
+        _check(load_library().cpb_bisect_begin(ocl._h, code, eps, self.K, self.nodes, ctypes.c_void_p(d_res), ctypes.c_void_p(d_c),
                                                ctypes.c_void_p(d_spl), ctypes.byref(self._h)))
 
     def probe(self, node_lo: int, node_hi: int):
@@ -506,6 +506,12 @@ def profile_get() -> dict:
         nm = names.raw[32 * t : 32 * t + 32].split(b"\0", 1)[0].decode()
         out[nm] = dict(ms=ms[t], launches=int(launches[t]), bytes=nbytes[t])
     return out
+
+
+def probe_cluster_capacity(streaming: bool = True) -> int:
+    out = ctypes.c_int()
+    _check(load_library().cpb_probe_cluster_capacity(int(streaming), ctypes.byref(out)))
+    return out.value
 
 
 def launch_count() -> int:

@@ -427,7 +427,7 @@ struct BisectRun {
   bool stream = false;
   i64 K = 0;
   double eps1 = 1;
-  int depth = 1, P = 1;
+  int P = 1;
   DBuf<BisectState> st;
   DBuf<int> hint_lo, hint_hi, best, own_spl, own_res;
   DBuf<double> own_c;
@@ -438,7 +438,7 @@ struct BisectRun {
   bool done = false;
 };
 
-BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int depth, int* d_node_res, double* d_node_c, int* d_node_spl) {
+BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
   const Matrix& A = *f.A;
@@ -472,8 +472,8 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int depth, int*
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8));
         CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
       }
-  run->depth = std::min(std::max(depth, 1), BS_MAX_DEPTH);
-  run->P = (1 << run->depth) - 1;
+  // the round's speculation tree = the first `nodes` nodes of the bisection tree in heap (BFS) order
+  run->P = std::min(std::max(nodes, 1), (1 << BS_MAX_DEPTH) - 1);
   run->eps1 = 1 + eps;
   const int P = run->P;
   run->st.alloc(1);
@@ -559,9 +559,28 @@ void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
   for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = hb[k];
 }
 
+// how many 8-CTA probe clusters the device can keep resident at once (cluster placement is per GPC)
+int probe_cluster_capacity(bool stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(BS_CLUSTER * 64, 1, 1);
+  cfg.blockDim = dim3(stream ? SP_THREADS : BS_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = BS_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_stream<i64>, &cfg));
+  else CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_bisect_round<i64>, &cfg));
+  return n;
+}
+
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   const int depth = std::min(std::max(env_int("CPB_BISECT_DEPTH", BS_LOCAL_DEPTH), 1), BS_LOCAL_DEPTH);
-  BisectRun* run = bisect_begin(f, lazy, eps, K, depth, nullptr, nullptr, nullptr);
+  BisectRun* run = bisect_begin(f, lazy, eps, K, (1 << depth) - 1, nullptr, nullptr, nullptr);
   try {
     ProfScope prof("probe");
     for (int guard = 0; guard < 4096 && !run->done; ++guard) {

@@ -309,13 +309,20 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
 }
 
 // ---- stepwise bisection (multi-GPU threshold sharding) ----
-int cpb_bisect_begin(cpb_oracle* f, int method, double eps, int64_t K, int depth, int32_t* d_node_res, double* d_node_c,
+int cpb_bisect_begin(cpb_oracle* f, int method, double eps, int64_t K, int nodes, int32_t* d_node_res, double* d_node_c,
                      int32_t* d_node_spl, cpb_bisect** out) {
   CPB_API_BEGIN
   ensure_context();
   CPB_REQUIRE(f && out, "NULL argument");
   CPB_REQUIRE(method == CPB_SPLIT_BISECT_COST || method == CPB_SPLIT_LAZY_BISECT_COST, "stepwise bisection: bisect methods only");
-  *out = reinterpret_cast<cpb_bisect*>(bisect_begin(*f->O, method == CPB_SPLIT_LAZY_BISECT_COST, eps, K, depth, d_node_res, d_node_c, d_node_spl));
+  *out = reinterpret_cast<cpb_bisect*>(bisect_begin(*f->O, method == CPB_SPLIT_LAZY_BISECT_COST, eps, K, nodes, d_node_res, d_node_c, d_node_spl));
+  CPB_API_END
+}
+int cpb_probe_cluster_capacity(int streaming, int* out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(out, "NULL argument");
+  *out = probe_cluster_capacity(streaming != 0);
   CPB_API_END
 }
 int cpb_bisect_probe(cpb_bisect* b, int node_lo, int node_hi) {

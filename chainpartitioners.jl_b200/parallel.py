@@ -46,13 +46,12 @@ def gather_split_vectors(local: dict, n_problems: int, K: int, device="cpu") -> 
 # ---------------------------------------------------------------------------------------------------
 
 
-def node_slots(world: int, local_depth: int = 4):
-    """-> (tree depth, nodes per rank).  Each rank hosts at most 2^local_depth clusters."""
-    depth = local_depth
-    while depth < 8 and ((1 << depth) - 1) < world * ((1 << local_depth) - 1) and (1 << (depth + 1)) - 1 <= world * (1 << local_depth):
-        depth += 1
-    per = -(-((1 << depth) - 1) // world)
-    return depth, per
+def node_slots(world: int, capacity: int = 15):
+    """-> (nodes of the round's speculation tree, nodes per rank).  ``capacity`` = probe clusters one GPU keeps
+    resident (``cpb_probe_cluster_capacity``: 15 on B200 for the streaming probes); the tree is the first
+    world * capacity nodes of the bisection tree in heap order (at most 255)."""
+    per = max(1, min(capacity, 255 // max(world, 1)))
+    return per * world, per
 
 
 def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulate_ranks: bool = False):
@@ -62,7 +61,8 @@ def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulat
     sharding logic)."""
     from . import api
 
-    depth, per = node_slots(world)
+    streaming = getattr(api.T.split_constrained(api.T.split_method_code(method)[1])[0], "kind", -1) in (api.T.MODEL_CONNECTIVITY, api.T.MODEL_MONOSYM)
+    nodes, per = node_slots(world, min(api.probe_cluster_capacity(streaming), 15))
     slots = per * world
     K = int(K)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -73,7 +73,7 @@ def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulat
     _, spec, _ = api.T.split_method_code(method)
     ocl = api.StripeOracle(spec, A)
     try:
-        run = api.StepwiseBisection(ocl, method, K, depth, res.data_ptr(), thr.data_ptr(), spl.data_ptr())
+        run = api.StepwiseBisection(ocl, method, K, nodes, res.data_ptr(), thr.data_ptr(), spl.data_ptr())
         nodes = run.nodes
         done = nodes == 0
         guard = 0

@@ -137,19 +137,23 @@ enum {
 int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out);
 
 /* The same bisection (BisectCostBottleneckSplitter.jl:41-60 / LazyBisect...:237-255) as explicit steps, so that
- * the 2^depth - 1 speculative thresholds of a round can be probed by different GPUs (one process per GPU):
+ * the speculative thresholds of a round -- the first `nodes` nodes (<= 255) of the bisection tree in heap order --
+ * can be probed by different GPUs (one process per GPU):
  *   begin   builds what the probes need, computes bound_stripe, sets up the round state.  d_node_res (int32
  *           per node: 0 = loop condition already false, 1 = infeasible, 2 = feasible), d_node_c (double per
  *           node), d_node_spl ((K+2) int32 per node, 1-based split points in [1..K+1]) are DEVICE buffers for
- *           2^depth - 1 nodes in heap order; pass NULL for library-owned buffers.  depth <= 8.
+ *           `nodes` nodes in heap order; pass NULL for library-owned buffers.
  *   probe   launches the probes of nodes [node_lo, node_hi) of the current round (asynchronous).
  *   advance walks the tree by feasibility; every node of the round must be present in the buffers (after the
  *           caller's all-gather).  done_out = 1 when c_lo (1 + eps) >= c_hi.
  *   finish  copies spl_hi[K+1] out (spl_out may be NULL to abandon) and frees the handle. */
 typedef struct cpb_bisect cpb_bisect;
-int cpb_bisect_begin(cpb_oracle* f, int method, double eps, int64_t K, int depth, int32_t* d_node_res, double* d_node_c,
+int cpb_bisect_begin(cpb_oracle* f, int method, double eps, int64_t K, int nodes, int32_t* d_node_res, double* d_node_c,
                      int32_t* d_node_spl, cpb_bisect** out);
 int cpb_bisect_probe(cpb_bisect* b, int node_lo, int node_hi);
+/* Number of 8-CTA probe clusters (= thresholds) this GPU keeps resident at once; streaming = 1 for the
+ * link-array probes, 0 for the dominance-index probes.  Sizes the per-rank node ranges. */
+int cpb_probe_cluster_capacity(int streaming, int* out);
 int cpb_bisect_advance(cpb_bisect* b, int* done_out);
 int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out);
 

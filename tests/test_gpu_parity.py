@@ -416,7 +416,7 @@ def test_sharded_bisection_emulated_ranks(ref):
 def test_node_slots():
     from chainb200 import parallel
 
-    assert parallel.node_slots(1) == (4, 15)
-    for world in (2, 4, 8):
-        depth, per = parallel.node_slots(world)
-        assert per <= 16 and per * world >= (1 << depth) - 1 and depth == 4 + int(np.log2(world))
+    assert parallel.node_slots(1) == (15, 15)
+    assert parallel.node_slots(2) == (30, 15)
+    assert parallel.node_slots(8) == (120, 15)
+    assert parallel.node_slots(32) == (224, 7)
