@@ -192,7 +192,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   __shared__ double s_c;
   __shared__ int s_valid;
   __shared__ u32 s_xa[2][BS_CLUSTER];     // per-CTA `prev < j` totals of the tile
-  __shared__ u32 s_xb[2][2][BS_CLUSTER];  // per-CTA (feasible boundaries, boundaries)
+  __shared__ u32 s_xb[2][4][BS_CLUSTER];  // per-CTA (feasible boundaries, boundaries, P and Wt at the last feasible one)
+  __shared__ u32 s_pj[2 * SP_THREADS];    // (P, Wt) of every thread's boundary candidate, pass 1 | pass 2
+  __shared__ u32 s_w[2 * SP_THREADS];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -228,16 +230,23 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   int ph = 0;
   u32 j = 1;
   bool broke = false, feasible = false;
+  u32 pcur = __ldg(s.P + 1), wcur = __ldg(s.Wt + 1);  // P[j], Wt[j] of the current part start, carried from the boundary tests
   for (int k = 1; k <= K; ++k) {
     // largest boundary r >= j with c(j, r) <= c
     if (!cost_leq(stream_cost<T>(s, 0, 0, 0), c)) { broke = true; break; }  // even the empty part exceeds c
-    const u32 e0 = __ldg(s.P + j);
-    const i64 wj = (i64)__ldg(s.Wt + j);
+    const u32 e0 = pcur;
+    const i64 wj = (i64)wcur;
     u32 jlast = j;
     u32 grun = 0;
     bool first = true;
     for (u32 e_tile = e0 & ~3u;; e_tile += TE) {  // 16-byte aligned tiles; elements left of e0 are masked out
       const u32 e_c = e_tile + crank * SP_CE;
+      // ---- column boundaries whose element offset falls into (e_c, e_c + CE] (loads issued ahead of the tile) ----
+      u32 ja, jb;
+      if (first && crank == 0) ja = j + 1;
+      else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
+      if (e_c >= Ne && !(first && crank == 0)) jb = 0;
+      else jb = ((u64)e_c + SP_CE >= Ne) ? n1 : __ldg(s.colidx + e_c + SP_CE) + 1;
       // ---- bit masks of `prev < j`: 8 warp-wide 128-bit loads, 4 ballots each ----
 #pragma unroll
       for (int v = 0; v < SP_VEC; ++v) {
@@ -292,44 +301,66 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         if (p < (int)crank) base_c += v;
         tile_tot += v;
       }
-      // ---- column boundaries whose element offset falls into (e_c, e_c + CE] ----
-      u32 ja, jb;
-      if (first && crank == 0) ja = j + 1;
-      else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
-      if (e_c >= Ne && !(first && crank == 0)) jb = 0;
-      else jb = ((u64)e_c + SP_CE >= Ne) ? n1 : __ldg(s.colidx + e_c + SP_CE) + 1;
       const u32 nb = (jb >= ja) ? jb - ja + 1 : 0;
-      auto feasible_at = [&](u32 jp) -> bool {
-        const u32 pj = __ldg(s.P + jp);
+      auto feasible_pw = [&](u32 jp, u32 pj, u32 w) -> bool {
         const u32 g = grun + base_c + stream_prefix(s_mask, s_cum, pj - e_c);
-        const i64 w = (i64)(s.same_w ? pj : __ldg(s.Wt + jp)) - wj;
-        return cost_leq(stream_cost<T>(s, (i64)jp - (i64)j, w, (i64)g), c);
+        return cost_leq(stream_cost<T>(s, (i64)jp - (i64)j, (i64)w - wj, (i64)g), c);
       };
-      // monotone costs: the feasible boundaries of this CTA form a prefix [ja, ja + cnt).  Two strided
-      // passes locate its end: 1024 evenly spaced probes, then the boundaries inside the crossing stride.
-      u32 cnt = 0;
+      // monotone costs: the feasible boundaries of this CTA form a prefix [ja, ja + cnt).  Two strided passes
+      // locate its end (1024 evenly spaced probes, then the boundaries inside the crossing stride); every thread
+      // stashes the (P, Wt) of its candidate so the next part can start without reloading them.
+      u32 cnt = 0, lastp = 0, lastw = 0;
       if (nb > 0) {
         const u32 stride = (nb + SP_THREADS - 1) / SP_THREADS;
-        const u32 t0 = (u32)tid * stride;  // offsets 0, stride, 2 stride, ...
-        const int ct = __syncthreads_count(t0 < nb && feasible_at(ja + t0));
+        const u32 t0 = (u32)tid * stride;
+        bool ok = false;
+        if (t0 < nb) {
+          const u32 pj = __ldg(s.P + ja + t0);
+          const u32 w = s.same_w ? pj : __ldg(s.Wt + ja + t0);
+          s_pj[tid] = pj;
+          s_w[tid] = w;
+          ok = feasible_pw(ja + t0, pj, w);
+        }
+        const int ct = __syncthreads_count(ok);
         if (ct > 0) {
           const u32 base = (u32)(ct - 1) * stride;  // last feasible probe
           cnt = base + 1;
+          lastp = s_pj[ct - 1];
+          lastw = s_w[ct - 1];
           if (stride > 1) {
             const u32 off = base + 1 + tid;
-            const bool ok = tid < stride - 1 && off < nb && feasible_at(ja + off);
-            cnt += __syncthreads_count(ok);
+            ok = false;
+            if (tid < stride - 1 && off < nb) {
+              const u32 pj = __ldg(s.P + ja + off);
+              const u32 w = s.same_w ? pj : __ldg(s.Wt + ja + off);
+              s_pj[SP_THREADS + tid] = pj;
+              s_w[SP_THREADS + tid] = w;
+              ok = feasible_pw(ja + off, pj, w);
+            }
+            const int c2 = __syncthreads_count(ok);
+            if (c2 > 0) {
+              cnt += c2;
+              lastp = s_pj[SP_THREADS + c2 - 1];
+              lastw = s_w[SP_THREADS + c2 - 1];
+            }
           }
         }
       }
       if (tid < BS_CLUSTER) {
         *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
         *cluster.map_shared_rank(&s_xb[ph][1][crank], tid) = nb;
+        *cluster.map_shared_rank(&s_xb[ph][2][crank], tid) = lastp;
+        *cluster.map_shared_rank(&s_xb[ph][3][crank], tid) = lastw;
       }
       cluster.sync();
       u32 feas = 0, nbs = 0;
 #pragma unroll
-      for (int p = 0; p < BS_CLUSTER; ++p) { feas += s_xb[ph][0][p]; nbs += s_xb[ph][1][p]; }
+      for (int p = 0; p < BS_CLUSTER; ++p) {
+        const u32 cp = s_xb[ph][0][p];
+        feas += cp;
+        nbs += s_xb[ph][1][p];
+        if (cp > 0) { pcur = s_xb[ph][2][p]; wcur = s_xb[ph][3][p]; }  // the last CTA with a feasible boundary wins
+      }
       ph ^= 1;
       first = false;
       jlast += feas;
@@ -408,14 +439,9 @@ static int env_int(const char* name, int dflt) {
 
 // nets(1, n+1) = number of non-empty rows = links equal to 0 (ConnectivityCosts.jl:32 needs ocl(1, n+1))
 i64 count_first_occurrences(const LinkStream& ls) {
-  DBuf<u32> cnt(1);
-  cnt.zero();
-  if (ls.Ne) {
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((ls.Ne + 255) / 256, (size_t)ctx().sm_count * 16));
-    CPB_LAUNCH(k_count_zero, grid, 256, 0, ls.prev.get(), ls.Ne, cnt.get());
-  }
+  // counted by k_link_prev while it wrote the links
   u32 h = 0;
-  CPB_CUDA(cudaMemcpyAsync(&h, cnt.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(&h, ls.first_count.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   return (i64)h;
 }
@@ -436,6 +462,7 @@ struct BisectRun {
   double* node_c = nullptr;
   DevStream ds{};
   bool done = false;
+  double c_lo0 = 0, c_hi0 = 0, eps = 0;
 };
 
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
@@ -494,6 +521,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   h.c_hi = bnd[1];
   h.done = !(h.c_lo * run->eps1 < h.c_hi);
   run->done = h.done != 0;
+  run->c_lo0 = h.c_lo; run->c_hi0 = h.c_hi; run->eps = eps;
   CPB_CUDA(cudaMemcpyAsync(run->st.get(), &h, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // h is a stack variable
   CPB_LAUNCH(k_bisect_init, 1, 256, 0, (int)K, (int)(A.n + 1), run->hint_lo.get(), run->hint_hi.get(), run->best.get());
@@ -583,6 +611,17 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   BisectRun* run = bisect_begin(f, lazy, eps, K, (1 << depth) - 1, nullptr, nullptr, nullptr);
   try {
     ProfScope prof("probe");
+    // The gap c_hi - c_lo halves with every probe and the loop stops once it is <= eps * c_lo, so the number
+    // of rounds is bounded from the initial bounds: queue them all without host round trips (rounds past
+    // the end find the state `done` and exit immediately), then read the state back once.
+    if (!run->done && run->c_lo0 > 0 && run->eps > 0 && run->c_hi0 > run->c_lo0 && env_int("CPB_BISECT_QUEUE", 1)) {
+      const double iters = std::ceil(std::log2((run->c_hi0 - run->c_lo0) / (run->eps * run->c_lo0))) + 2;
+      const int rounds = (int)std::min(64.0, std::ceil(std::max(iters, 1.0) / depth) + 1);
+      for (int r = 0; r < rounds; ++r) {
+        bisect_probe(*run, 0, run->P);
+        bisect_advance(*run, r + 1 == rounds);
+      }
+    }
     for (int guard = 0; guard < 4096 && !run->done; ++guard) {
       bisect_probe(*run, 0, run->P);
       bisect_advance(*run, true);

@@ -27,6 +27,7 @@ struct LinkStream {
   DBuf<u32> prev;    // [Ne] 1-based previous column holding the same row, 0 = none
   DBuf<u32> colidx;  // [Ne] 0-based column of each element
   DBuf<u32> P_own;   // own prefix array (diagonal-augmented variant)
+  DBuf<u32> first_count;  // [1] number of links equal to 0 (= non-empty rows)
   const u32* P = nullptr;  // P[x] = #{elements in columns < x}, 1 <= x <= n+1
   size_t Ne = 0;
 };
@@ -37,7 +38,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia);
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
-void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx);
+void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr);
 // For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
 
 // ---- device-side oracle ------------------------------------------------------------------------

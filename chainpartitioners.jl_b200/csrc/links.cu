@@ -28,13 +28,17 @@ static void transpose_order(const u32* row, size_t N, u64 max_row, TransposeOrde
 
 // prev[q] = 1-based previous column holding the same row, 0 if none
 __global__ void k_link_prev(const u32* __restrict__ sk, const u32* __restrict__ sq, const u32* __restrict__ colidx,
-                            u32* __restrict__ prev, size_t N) {
+                            u32* __restrict__ prev, size_t N, u32* __restrict__ first_count) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 firsts = 0;  // links equal to 0 = first occurrence of a row = number of non-empty rows
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
     u32 link = 0;
     if (p > 0 && sk[p - 1] == sk[p]) link = __ldg(colidx + sq[p - 1]) + 1u;
     prev[sq[p]] = link;
+    firsts += link == 0u;
   }
+  firsts = __reduce_add_sync(0xffffffffu, firsts);
+  if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
 }
 
 __global__ void k_head_flags(const u32* __restrict__ sk, size_t N, u32* __restrict__ flags) {
@@ -114,12 +118,15 @@ static u32 read_u32(const u32* d) {
 }
 
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
-void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx) {
+void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
   TransposeOrder t;
   transpose_order(row, N, nrow ? nrow - 1 : 0, t);
   expand_columns(pos, ncol, colidx, N);
-  if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N);
+  DBuf<u32> dummy;
+  if (!first_count) { dummy.alloc(1); first_count = dummy.get(); }
+  CPB_CUDA(cudaMemsetAsync(first_count, 0, sizeof(u32), ctx().stream));
+  if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count);
 }
 
 // The link array of A (dia = false) or of A + I (dia = true, SparseColorArrays.jl:72-99) in column order,
@@ -132,7 +139,8 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia) {
     ls->Ne = N;
     ls->prev.alloc(N);
     ls->colidx.alloc(N);
-    compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get());
+    ls->first_count.alloc(1);
+    compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get());
     ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
     return ls;
   }
@@ -153,7 +161,8 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia) {
   ls->Ne = N2;
   ls->prev.alloc(N2);
   ls->colidx.alloc(N2);
-  compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get());
+  ls->first_count.alloc(1);
+  compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get());
   ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
   return ls;
 }
