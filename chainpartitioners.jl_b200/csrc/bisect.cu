@@ -146,7 +146,10 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
 // needed for bisection at all.
 // ------------------------------------------------------------------------------------------------
 static constexpr int SP_THREADS = 1024;
-static constexpr int SP_VEC = 8;                       // 128-bit loads per thread per super-step
+#ifndef CPB_SP_VEC
+#define CPB_SP_VEC 8
+#endif
+static constexpr int SP_VEC = CPB_SP_VEC;               // 128-bit loads per thread per super-step
 static constexpr int SP_CE = SP_THREADS * SP_VEC * 4;  // 32768 elements per CTA per super-step
 static constexpr int SP_GROUPS = SP_VEC * 32;          // 128-element groups per CTA (one warp-wide uint4 load each)
 
@@ -181,6 +184,14 @@ template <class T> __device__ __forceinline__ T stream_cost(const DevStream& s, 
   using C = StreamCoef<T>;  // alpha + n_vertices * b_vertex + n_pins * b_pin + n_nets * b_net, left to right
   return C::get(s, 0) + (T)nv * C::get(s, 1) + (T)w * C::get(s, 2) + (T)g * C::get(s, 3);
 }
+
+#ifdef CPB_PROBE_TIMING
+__device__ unsigned long long g_probe_t[8];
+__device__ unsigned long long g_probe_n;
+#define PT(i) do { if (node == 0 && crank == 0 && tid == 0) { unsigned long long _t = clock64(); g_probe_t[i] += _t - t_last; t_last = _t; } } while (0)
+#else
+#define PT(i) do {} while (0)
+#endif
 
 template <class T>
 __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS, 1)
@@ -224,7 +235,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   const double c = s_c;
   const u32 n1 = s.n + 1;
   const u32 Ne = s.Ne;
-  constexpr u32 TE = (u32)SP_CE * BS_CLUSTER;
+  u32 nv = SP_VEC, nv_est = SP_VEC;  // 128-bit loads per thread in the next super-step: adapted to the previous parts' sizes
   int* spl = node_spl + (size_t)node * (K + 2);
   if (writer) { spl[1] = 1; spl[K + 1] = (int)n1; }
   int ph = 0;
@@ -238,18 +249,26 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     const i64 wj = (i64)wcur;
     u32 jlast = j;
     u32 grun = 0;
-    bool first = true;
-    for (u32 e_tile = e0 & ~3u;; e_tile += TE) {  // 16-byte aligned tiles; elements left of e0 are masked out
-      const u32 e_c = e_tile + crank * SP_CE;
+    bool first = true, missed = false;
+    for (u32 e_tile = e0 & ~3u;;) {  // 16-byte aligned tiles; elements left of e0 are masked out
+      const u32 CE = (u32)SP_THREADS * 4u * nv;  // elements of this CTA in this super-step
+      const u32 TE = CE * BS_CLUSTER;
+      const u32 ngroups = nv * 32u;
+#ifdef CPB_PROBE_TIMING
+      unsigned long long t_last = clock64();
+      if (node == 0 && crank == 0 && tid == 0) g_probe_n += 1;
+#endif
+      const u32 e_c = e_tile + crank * CE;
       // ---- column boundaries whose element offset falls into (e_c, e_c + CE] (loads issued ahead of the tile) ----
       u32 ja, jb;
       if (first && crank == 0) ja = j + 1;
       else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
       if (e_c >= Ne && !(first && crank == 0)) jb = 0;
-      else jb = ((u64)e_c + SP_CE >= Ne) ? n1 : __ldg(s.colidx + e_c + SP_CE) + 1;
+      else jb = ((u64)e_c + CE >= Ne) ? n1 : __ldg(s.colidx + e_c + CE) + 1;
       // ---- bit masks of `prev < j`: 8 warp-wide 128-bit loads, 4 ballots each ----
 #pragma unroll
       for (int v = 0; v < SP_VEC; ++v) {
+        if (v >= (int)nv) break;
         const u32 g = v * 32 + warp;
         const u32 idx = e_c + g * 128 + lane * 4;
         uint4 pv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -267,18 +286,22 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         const unsigned m3 = __ballot_sync(0xffffffffu, pv.w < j && !(head && idx + 3 < e0));
         if (lane < 4) s_mask[g * 4 + lane] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
       }
+      PT(0);
       __syncthreads();
+      PT(1);
       // ---- exclusive scan of the 256 group popcounts by warp 0 (8 groups per lane); the other warps
       //      go straight to the cluster barrier below ----
       u32 tot_c = 0;
       if (warp == 0) {
-        u32 loc[8];
+        u32 loc[SP_VEC];
         u32 sum = 0;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const uint4 mk = *reinterpret_cast<const uint4*>(&s_mask[(lane * 8 + t) * 4]);
+        for (int t = 0; t < SP_VEC; ++t) {
           loc[t] = sum;
-          sum += __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
+          if (t < (int)nv) {
+            const uint4 mk = *reinterpret_cast<const uint4*>(&s_mask[(lane * nv + t) * 4]);
+            sum += __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
+          }
         }
         u32 inc = sum;
 #pragma unroll
@@ -288,12 +311,19 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         }
         const u32 excl = inc - sum;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) s_cum[lane * 8 + t] = excl + loc[t];
+        for (int t = 0; t < SP_VEC; ++t)
+          if (t < (int)nv) s_cum[lane * nv + t] = excl + loc[t];
         tot_c = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) s_cum[SP_GROUPS] = tot_c;
+        if (lane == 0) {
+          s_cum[ngroups] = tot_c;
+          // sentinel masks behind the last group (prefix lookups at x == CE)
+          s_mask[ngroups * 4] = 0; s_mask[ngroups * 4 + 1] = 0; s_mask[ngroups * 4 + 2] = 0; s_mask[ngroups * 4 + 3] = 0;
+        }
       }
+      PT(2);
       if (tid < BS_CLUSTER) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
       cluster.sync();  // also orders s_cum for the boundary phase
+      PT(3);
       u32 base_c = 0, tile_tot = 0;
 #pragma unroll
       for (int p = 0; p < BS_CLUSTER; ++p) {
@@ -346,6 +376,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
           }
         }
       }
+      PT(4);
       if (tid < BS_CLUSTER) {
         *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
         *cluster.map_shared_rank(&s_xb[ph][1][crank], tid) = nb;
@@ -353,6 +384,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         *cluster.map_shared_rank(&s_xb[ph][3][crank], tid) = lastw;
       }
       cluster.sync();
+      PT(5);
       u32 feas = 0, nbs = 0;
 #pragma unroll
       for (int p = 0; p < BS_CLUSTER; ++p) {
@@ -367,6 +399,16 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       if (feas < nbs) break;                   // the cost crossed c inside this tile
       if ((u64)e_tile + TE >= Ne) break;       // streamed to the end: jlast == n + 1
       grun += tile_tot;
+      e_tile += TE;
+      nv = SP_VEC;                             // the part is longer than estimated: full-size tiles from here on
+      missed = true;
+    }
+    {  // size the next part's first tile from this part (+1/8 slack); a miss (second super-step needed) resets
+       // the estimate to the full tile, from where it shrinks by one vector load per part at most
+      const u32 elems = pcur - e0;
+      const u32 want = (elems + (elems >> 3) + 3u) / ((u32)SP_THREADS * 4u * BS_CLUSTER) + 1u;
+      nv_est = missed ? (u32)SP_VEC : max(min(max(want, 2u), (u32)SP_VEC), nv_est > 2u ? nv_est - 1u : 2u);
+      nv = nv_est;
     }
     if (k == K) { feasible = (jlast == n1); break; }
     if (writer) spl[k + 1] = (int)jlast;
@@ -587,6 +629,17 @@ void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
   for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = hb[k];
 }
 
+#ifdef CPB_PROBE_TIMING
+void probe_timing_dump() {
+  unsigned long long t[8], n;
+  cudaMemcpyFromSymbol(t, g_probe_t, sizeof(t));
+  cudaMemcpyFromSymbol(&n, g_probe_n, sizeof(n));
+  const char* names[6] = {"loads+ballots", "syncthreads", "scan(warp0)", "push+cluster.sync#1", "boundaries", "push+cluster.sync#2"};
+  for (int i = 0; i < 6; ++i) std::printf("probe_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / (double)std::max<unsigned long long>(n, 1));
+  std::printf("probe_timing super-steps %llu\n", n);
+}
+#endif
+
 // how many 8-CTA probe clusters the device can keep resident at once (cluster placement is per GPC)
 int probe_cluster_capacity(bool stream) {
   cudaLaunchConfig_t cfg{};
@@ -632,6 +685,9 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     throw;
   }
   bisect_finish(run, h_spl_out);
+#ifdef CPB_PROBE_TIMING
+  if (env_int("CPB_PROBE_TIMING_DUMP", 0)) probe_timing_dump();
+#endif
 }
 
 }  // namespace cpb
