@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
     "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_probe_cluster_capacity",
+    "cpb_links_partial", "cpb_oracle_set_links",
 ]
 
 
@@ -83,6 +84,8 @@ def load_library():
         lib.cpb_bisect_probe.argtypes = [vp, i32, i32]
         lib.cpb_bisect_advance.argtypes = [vp, ctypes.POINTER(i32)]
         lib.cpb_bisect_finish.argtypes = [vp, vp]
+        lib.cpb_links_partial.argtypes = [vp, i64, i64, vp, ctypes.POINTER(i64)]
+        lib.cpb_oracle_set_links.argtypes = [vp, vp, i64]
         _lib = lib
     return _lib
 
@@ -223,6 +226,16 @@ class StripeOracle:
                 width = width + (dm_pos[jp - 1] - dm_pos[j - 1]) * w[2]
             out = np.where(width <= self.constraint.w_max, out, np.inf)
         return out
+
+    def links_partial(self, row_lo: int, row_hi: int, d_prev: int) -> int:
+        """Multi-GPU link construction: links of the nonzeros with row in [row_lo, row_hi) into the device buffer
+        ``d_prev`` (room for nnz + n uint32); returns the number of link entries."""
+        ne = ctypes.c_int64()
+        _check(load_library().cpb_links_partial(self._h, int(row_lo), int(row_hi), ctypes.c_void_p(d_prev), ctypes.byref(ne)))
+        return ne.value
+
+    def set_links(self, d_prev: int, ne: int):
+        _check(load_library().cpb_oracle_set_links(self._h, ctypes.c_void_p(d_prev), int(ne)))
 
     def query_device(self, d_j: int, d_jp: int, d_out: int, Q: int):
         """Batched queries on device-resident Int64 arrays (raw device pointers), result Float64 on the device."""

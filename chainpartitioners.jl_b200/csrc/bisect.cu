@@ -518,6 +518,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   // Connectivity-type models stream the link array (no dominance index needed); the others walk the index.
   run->stream = (f.dev.kind == CPB_MODEL_CONNECTIVITY || f.dev.kind == CPB_MODEL_MONOSYM) && env_int("CPB_PROBE_STREAM", 1) != 0;
   if (run->stream) {
+    CPB_REQUIRE(f.ls_complete, "partial links were built but never completed (cpb_oracle_set_links)");
     if (!f.ls) {
       ProfScope prof("oracle_stripe");
       f.ls = build_link_stream(*f.A, f.dev.kind == CPB_MODEL_MONOSYM);

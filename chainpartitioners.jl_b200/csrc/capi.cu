@@ -308,6 +308,22 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
   CPB_API_END
 }
 
+// ---- multi-GPU link construction ----
+int cpb_links_partial(cpb_oracle* f, int64_t row_lo, int64_t row_hi, uint32_t* d_prev_out, int64_t* ne_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && ne_out, "NULL argument");
+  *ne_out = oracle_links_partial(*f->O, row_lo, row_hi, d_prev_out);
+  CPB_API_END
+}
+int cpb_oracle_set_links(cpb_oracle* f, const uint32_t* d_prev, int64_t ne) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(f && (d_prev || ne == 0), "NULL argument");
+  oracle_set_links(*f->O, d_prev, ne);
+  CPB_API_END
+}
+
 // ---- stepwise bisection (multi-GPU threshold sharding) ----
 int cpb_bisect_begin(cpb_oracle* f, int method, double eps, int64_t K, int nodes, int32_t* d_node_res, double* d_node_c,
                      int32_t* d_node_spl, cpb_bisect** out) {

@@ -32,13 +32,14 @@ struct LinkStream {
   size_t Ne = 0;
 };
 struct Matrix;
-std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia);
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo = 0, i64 row_hi = ((i64)1 << 62));
 
 // SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
-void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr);
+void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
+                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62));
 // For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
 
 // ---- device-side oracle ------------------------------------------------------------------------
@@ -78,9 +79,12 @@ struct Oracle {
   std::vector<i64> h_pi_spl;
   i64 pi_K = 0;
   bool ranks_built = false;
+  bool ls_complete = true;  // false between cpb_links_partial and cpb_oracle_set_links
   DevOracle dev{};
 };
 void oracle_ensure_ranks(Oracle& f);
+i64 oracle_links_partial(Oracle& f, i64 row_lo, i64 row_hi, u32* d_prev_out);
+void oracle_set_links(Oracle& f, const u32* d_prev, i64 Ne);
 i64 count_first_occurrences(const LinkStream& ls);
 
 std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int64_t* pi_spl, i64 pi_K);

@@ -26,6 +26,18 @@ static void transpose_order(const u32* row, size_t N, u64 max_row, TransposeOrde
   t.q = which ? t.v1.get() : t.v0.get();
 }
 
+// (row, q) pairs of the nonzeros whose row lies in [lo, hi)
+__global__ void k_row_flags(const u32* __restrict__ row, size_t N, u32 lo, u32 hi, u32* __restrict__ flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q <= N; q += stride) flags[q] = (q < N && row[q] >= lo && row[q] < hi) ? 1u : 0u;
+}
+__global__ void k_row_compact(const u32* __restrict__ row, const u32* __restrict__ flags, const u32* __restrict__ scan, size_t N,
+                              u32* __restrict__ keys, u32* __restrict__ vals) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride)
+    if (flags[q]) { keys[scan[q]] = row[q]; vals[scan[q]] = (u32)q; }
+}
+
 // prev[q] = 1-based previous column holding the same row, 0 if none
 __global__ void k_link_prev(const u32* __restrict__ sk, const u32* __restrict__ sq, const u32* __restrict__ colidx,
                             u32* __restrict__ prev, size_t N, u32* __restrict__ first_count) {
@@ -110,7 +122,7 @@ __global__ void k_aug_diag(const u32* __restrict__ pos2, const u32* __restrict__
 
 static unsigned grid_for(size_t n) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 32)); }
 
-static u32 read_u32(const u32* d) {
+static u32 read_u32(const u32* d) {  // (declared above)
   u32 h = 0;
   CPB_CUDA(cudaMemcpyAsync(&h, d, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -118,20 +130,38 @@ static u32 read_u32(const u32* d) {
 }
 
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
-void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count) {
+static u32 read_u32(const u32* d);
+
+// row_lo/row_hi (0-based, half-open) restrict the construction to the nonzeros of a row block: prev[] is
+// written for those nonzeros only and is zero elsewhere (multi-GPU: ranks combine with an element-wise MAX).
+void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
+                        i64 row_lo, i64 row_hi) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
-  TransposeOrder t;
-  transpose_order(row, N, nrow ? nrow - 1 : 0, t);
   expand_columns(pos, ncol, colidx, N);
   DBuf<u32> dummy;
   if (!first_count) { dummy.alloc(1); first_count = dummy.get(); }
   CPB_CUDA(cudaMemsetAsync(first_count, 0, sizeof(u32), ctx().stream));
-  if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count);
+  if (row_lo <= 0 && row_hi >= (i64)nrow) {
+    TransposeOrder t;
+    transpose_order(row, N, nrow ? nrow - 1 : 0, t);
+    if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count);
+    return;
+  }
+  if (N) CPB_CUDA(cudaMemsetAsync(prev, 0, N * sizeof(u32), ctx().stream));
+  DBuf<u32> flags(N + 1), scan(N + 1);
+  CPB_LAUNCH(k_row_flags, grid_for(N + 1), 256, 0, row, N, (u32)std::max<i64>(row_lo, 0), (u32)std::min<i64>(row_hi, nrow), flags.get());
+  exclusive_scan_u32(flags.get(), scan.get(), N + 1);
+  const size_t M = read_u32(scan.get() + N);
+  if (M == 0) return;
+  DBuf<u32> k0(M), v0(M), k1(M), v1(M);
+  CPB_LAUNCH(k_row_compact, grid_for(N), 256, 0, row, flags.get(), scan.get(), N, k0.get(), v0.get());
+  const int which = radix_sort_pairs(k0.get(), v0.get(), k1.get(), v1.get(), M, bits_for(nrow ? nrow - 1 : 0));
+  CPB_LAUNCH(k_link_prev, grid_for(M), 256, 0, which ? k1.get() : k0.get(), which ? v1.get() : v0.get(), colidx, prev, M, first_count);
 }
 
 // The link array of A (dia = false) or of A + I (dia = true, SparseColorArrays.jl:72-99) in column order,
 // kept for the streaming probes; P[x] = #{elements in columns < x}.
-std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia) {
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo, i64 row_hi) {
   auto ls = std::make_unique<LinkStream>();
   const size_t N = (size_t)A.N;
   const u32 n = (u32)A.n, m = (u32)A.m;
@@ -140,7 +170,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia) {
     ls->prev.alloc(N);
     ls->colidx.alloc(N);
     ls->first_count.alloc(1);
-    compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get());
+    compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi);
     ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
     return ls;
   }
@@ -162,7 +192,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia) {
   ls->prev.alloc(N2);
   ls->colidx.alloc(N2);
   ls->first_count.alloc(1);
-  compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get());
+  compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi);
   ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
   return ls;
 }

@@ -54,7 +54,42 @@ def node_slots(world: int, capacity: int = 15):
     return per * world, per
 
 
-def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulate_ranks: bool = False):
+def row_block(m: int, rank: int, world: int):
+    """1-based half-open row range of ``rank``: [lo, hi)."""
+    return 1 + (m * rank) // world, 1 + (m * (rank + 1)) // world
+
+
+def build_links_sharded(ocl, m: int, n: int, nnz: int, rank: int, world: int, emulate_ranks: bool = False):
+    """Link construction by row blocks (north_star: "column blocks of the oracle-construction sweep" -- the sweep
+    is independent per ROW, so rows are the natural shard): every rank sorts only the nonzeros of its rows, the
+    partial link arrays (zero outside the block) are combined with one element-wise MAX all-reduce."""
+    from . import api
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    prev = torch.zeros(nnz + n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    if emulate_ranks:
+        acc = torch.zeros_like(prev)
+        ne = 0
+        for r in range(world):
+            lo, hi = row_block(m, r, world)
+            ne = ocl.links_partial(lo, hi, prev.data_ptr())
+            api.synchronize()
+            acc = torch.maximum(acc, prev)
+            torch.cuda.synchronize()
+        prev = acc
+    else:
+        lo, hi = row_block(m, rank, world)
+        ne = ocl.links_partial(lo, hi, prev.data_ptr())
+        api.synchronize()
+        if world > 1:
+            dist.all_reduce(prev, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+    ocl.set_links(prev.data_ptr(), ne)
+    return prev
+
+
+def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulate_ranks: bool = False, shard_links: bool = True):
     """``partition_stripe(A, K, BisectCost/LazyBisectCost...)`` with the threshold tree of every round
     sharded over ``world`` ranks (torch.distributed must be initialised with a CUDA-capable backend when
     world > 1).  ``emulate_ranks`` probes all node ranges from this one process (single-GPU test of the
@@ -73,6 +108,8 @@ def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulat
     _, spec, _ = api.T.split_method_code(method)
     ocl = api.StripeOracle(spec, A)
     try:
+        if streaming and shard_links and world > 1:
+            build_links_sharded(ocl, ocl.dm.m, ocl.dm.n, ocl.dm.nnz, rank, world, emulate_ranks)
         run = api.StepwiseBisection(ocl, method, K, nodes, res.data_ptr(), thr.data_ptr(), spl.data_ptr())
         nodes = run.nodes
         done = nodes == 0

@@ -136,6 +136,14 @@ enum {
 /* -> spl_out[K+1] (SplitPartition{Int64}(K, spl), Partitions.jl:3-6); con may be NULL. */
 int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out);
 
+/* Link construction sharded by row blocks (the sweep of SparseColorArrays.jl:103-118 / :72-99 touches every row
+ * independently): cpb_links_partial builds the links of the nonzeros whose row lies in [row_lo, row_hi) (1-based,
+ * half-open) into d_prev_out (DEVICE buffer with room for nnz + n uint32; *ne_out <= nnz + n entries are written,
+ * zero for all nonzeros outside the row block); the ranks combine their arrays with an element-wise MAX all-reduce and hand the result back with
+ * cpb_oracle_set_links.  Connectivity-type models only (their probes stream this array). */
+int cpb_links_partial(cpb_oracle* f, int64_t row_lo, int64_t row_hi, uint32_t* d_prev_out, int64_t* ne_out);
+int cpb_oracle_set_links(cpb_oracle* f, const uint32_t* d_prev, int64_t ne);
+
 /* The same bisection (BisectCostBottleneckSplitter.jl:41-60 / LazyBisect...:237-255) as explicit steps, so that
  * the speculative thresholds of a round -- the first `nodes` nodes (<= 255) of the bisection tree in heap order --
  * can be probed by different GPUs (one process per GPU):
