@@ -2,6 +2,7 @@
 // ownership, error translation.  Nothing throws across this boundary.
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include "engine.cuh"
 #include "primitives.cuh"
 
@@ -126,6 +127,55 @@ int cpb_synchronize(void) {
   CPB_API_END
 }
 
+// Host -> device copy of a caller's array.  Pinned (registered) memory goes straight to cudaMemcpyAsync.
+// Pageable memory -- what a Julia Array is -- would be staged by the driver through one internal buffer by
+// one thread (~10 GB/s measured); instead several host threads copy 32 MiB chunks into three pinned staging
+// buffers while the previous chunks are in flight over PCIe.
+static constexpr size_t H2D_CHUNK = (size_t)32 << 20;
+static constexpr int H2D_BUFS = 3;
+static void* g_stage[H2D_BUFS] = {nullptr, nullptr, nullptr};
+static cudaEvent_t g_stage_ev[H2D_BUFS] = {nullptr, nullptr, nullptr};
+static bool g_stage_busy[H2D_BUFS] = {false, false, false};
+
+static void h2d_copy(void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return;
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // unregistered memory may set a sticky-free error on old drivers
+  static const bool disabled = std::getenv("CPB_NO_STAGED_H2D") != nullptr;
+  if (pinned || bytes < 2 * H2D_CHUNK || disabled) {
+    CPB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx().stream));
+    return;
+  }
+  for (int b = 0; b < H2D_BUFS; ++b)
+    if (!g_stage[b]) {
+      CPB_CUDA(cudaHostAlloc(&g_stage[b], H2D_CHUNK, cudaHostAllocDefault));
+      CPB_CUDA(cudaEventCreateWithFlags(&g_stage_ev[b], cudaEventDisableTiming));
+    }
+  const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+  const int T = (int)std::min<unsigned>(8, std::max(1u, hc / 2));
+  size_t off = 0;
+  for (int i = 0; off < bytes; ++i) {
+    const int b = i % H2D_BUFS;
+    const size_t sz = std::min(H2D_CHUNK, bytes - off);
+    if (g_stage_busy[b]) CPB_CUDA(cudaEventSynchronize(g_stage_ev[b]));  // the copy that last used this buffer (maybe in an earlier call) has finished
+    const char* src = (const char*)h_src + off;
+    char* dst = (char*)g_stage[b];
+    std::vector<std::thread> th;
+    const size_t slice = ((sz + T - 1) / T + 63) & ~(size_t)63;
+    for (int t = 1; t < T; ++t) {
+      const size_t o = (size_t)t * slice;
+      if (o < sz) th.emplace_back([=] { std::memcpy(dst + o, src + o, std::min(slice, sz - o)); });
+    }
+    std::memcpy(dst, src, std::min(slice, sz));
+    for (auto& x : th) x.join();
+    CPB_CUDA(cudaMemcpyAsync((char*)d_dst + off, g_stage[b], sz, cudaMemcpyHostToDevice, ctx().stream));
+    CPB_CUDA(cudaEventRecord(g_stage_ev[b], ctx().stream));
+    g_stage_busy[b] = true;
+    off += sz;
+  }
+}
+
 static void matrix_from_device(Matrix& M, i64 m, i64 n, i64 nnz, const i64* d_colptr, const i64* d_rowval) {
   CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
   CPB_REQUIRE(nnz + n + 1 < ((i64)1 << 31) && m < ((i64)1 << 31) - 2 && n < ((i64)1 << 31) - 2, "matrix too large for the 32-bit device index");
@@ -165,8 +215,8 @@ int cpb_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, 
   CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
   ProfScope prof("h2d_matrix", (double)(nnz + n + 1) * 8.0);
   DBuf<i64> dc((size_t)n + 1), dr((size_t)nnz);
-  CPB_CUDA(cudaMemcpyAsync(dc.get(), colptr, ((size_t)n + 1) * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
-  if (nnz) CPB_CUDA(cudaMemcpyAsync(dr.get(), rowval, (size_t)nnz * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+  h2d_copy(dc.get(), colptr, ((size_t)n + 1) * sizeof(i64));
+  h2d_copy(dr.get(), rowval, (size_t)nnz * sizeof(i64));
   auto h = std::make_unique<cpb_matrix>();
   matrix_from_device(h->M, m, n, nnz, dc.get(), dr.get());
   *out = h.release();
