@@ -420,3 +420,25 @@ def test_node_slots():
     assert parallel.node_slots(2) == (30, 15)
     assert parallel.node_slots(8) == (120, 15)
     assert parallel.node_slots(32) == (224, 7)
+
+
+def test_c_abi_example_binary(ref):
+    """The boundary from plain C (examples/c_abi_example.c, built by __graft_entry__.build()): no Python
+    in the call path, exactly what a Julia ccall would do."""
+    import os
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "c_abi_example")
+    if not os.path.exists(exe):
+        pytest.skip("examples/c_abi_example not built")
+    A = synth.erdos_renyi(4000, 8)
+    K, eps = 12, 0.01
+    text = f"{A.m} {A.n} {A.nnz} {K} {eps}\n" + " ".join(map(str, A.colptr.tolist())) + "\n" + " ".join(map(str, A.rowval.tolist())) + "\n"
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
+    mtd = cp.BisectCostBottleneckSplitter(AFF, eps)
+    exp = ref.partition_stripe(A, K, mtd)
+    assert list(map(int, lines["spl"].split())) == exp.spl.tolist()
+    assert tuple(map(float, lines["bound"].split())) == ref.bound_stripe(A, K, AFF)
+    assert float(lines["value"]) == ref.bottleneck_value(A, exp, AFF)
