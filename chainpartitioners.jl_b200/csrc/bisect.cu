@@ -199,7 +199,6 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
                    int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c, int node_base) {
   __shared__ u32 s_mask[SP_GROUPS * 4 + 4];
   __shared__ u32 s_cum[SP_GROUPS + 1];
-  __shared__ u32 s_warp[32];
   __shared__ double s_c;
   __shared__ int s_valid;
   __shared__ u32 s_xa[2][BS_CLUSTER];     // per-CTA `prev < j` totals of the tile
