@@ -667,7 +667,7 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     // The gap c_hi - c_lo halves with every probe and the loop stops once it is <= eps * c_lo, so the number
     // of rounds is bounded from the initial bounds: queue them all without host round trips (rounds past
     // the end find the state `done` and exit immediately), then read the state back once.
-    if (!run->done && run->c_lo0 > 0 && run->eps > 0 && run->c_hi0 > run->c_lo0 && env_int("CPB_BISECT_QUEUE", 1)) {
+    if (!run->done && run->c_lo0 > 0 && run->eps > 0 && run->c_hi0 > run->c_lo0 && env_int("CPB_BISECT_QUEUE", 0)) {
       const double iters = std::ceil(std::log2((run->c_hi0 - run->c_lo0) / (run->eps * run->c_lo0))) + 2;
       const int rounds = (int)std::min(64.0, std::ceil(std::max(iters, 1.0) / depth) + 1);
       for (int r = 0; r < rounds; ++r) {

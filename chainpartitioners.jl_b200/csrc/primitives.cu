@@ -296,22 +296,52 @@ void iota_u32(u32* dst, size_t n) {
   CPB_LAUNCH(k_iota, grid, 256, 0, dst, n);
 }
 
-__global__ void k_expand_columns(const u32* __restrict__ pos, u32 ncol, u32* __restrict__ colidx, size_t N) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
-    // largest j in [0, ncol) with pos[j] <= q   (pos[ncol] == N > q)
-    u32 lo = 0, hi = ncol;
+// colidx[q] = largest j with pos[j] <= q.  A CTA owns 2048 consecutive nonzeros: two global binary searches
+// bound its column range, the offsets of that range are staged in shared memory and every nonzero
+// searches there (<= 11 shared-memory steps instead of ~20 dependent L2 reads).
+static constexpr int EX_TILE = 2048;
+__global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ pos, u32 ncol, u32* __restrict__ colidx, size_t N) {
+  __shared__ u32 s_pos[EX_TILE + 2];
+  __shared__ u32 s_lo, s_hi;
+  const size_t q0 = (size_t)blockIdx.x * EX_TILE;
+  const size_t q1 = min(N, q0 + (size_t)EX_TILE);
+  if (threadIdx.x < 2) {
+    const u32 q = (u32)(threadIdx.x == 0 ? q0 : q1 - 1);
+    u32 lo = 0, hi = ncol;  // largest j in [0, ncol) with pos[j] <= q   (pos[ncol] == N > q)
     while (hi - lo > 1) {
       const u32 mid = lo + ((hi - lo) >> 1);
-      if (__ldg(pos + mid) <= (u32)q) lo = mid; else hi = mid;
+      if (__ldg(pos + mid) <= q) lo = mid; else hi = mid;
     }
-    colidx[q] = lo;
+    if (threadIdx.x == 0) s_lo = lo; else s_hi = lo;
+  }
+  __syncthreads();
+  const u32 c_lo = s_lo, c_hi = s_hi;
+  const u32 ncols = c_hi - c_lo + 1;
+  if (ncols <= (u32)EX_TILE) {
+    for (u32 t = threadIdx.x; t <= ncols; t += blockDim.x) s_pos[t] = __ldg(pos + c_lo + t);  // pos[c_lo .. c_hi + 1]
+    __syncthreads();
+    for (size_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+      u32 lo = 0, hi = ncols;  // s_pos[0] <= q < s_pos[ncols]
+      while (hi - lo > 1) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (s_pos[mid] <= (u32)q) lo = mid; else hi = mid;
+      }
+      colidx[q] = c_lo + lo;
+    }
+  } else {  // very many empty columns inside the tile: search the bounded global range
+    for (size_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+      u32 lo = c_lo, hi = c_hi + 1;
+      while (hi - lo > 1) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (__ldg(pos + mid) <= (u32)q) lo = mid; else hi = mid;
+      }
+      colidx[q] = lo;
+    }
   }
 }
 void expand_columns(const u32* pos, u32 ncol, u32* colidx, size_t N) {
   if (N == 0) return;
-  const unsigned grid = (unsigned)std::min<size_t>((N + 255) / 256, (size_t)ctx().sm_count * 32);
-  CPB_LAUNCH(k_expand_columns, grid, 256, 0, pos, ncol, colidx, N);
+  CPB_LAUNCH(k_expand_columns, (unsigned)((N + EX_TILE - 1) / EX_TILE), 256, 0, pos, ncol, colidx, N);
 }
 
 __global__ void k_segment_starts(const u32* __restrict__ keys, size_t n, u32* __restrict__ P, u32 domain) {
