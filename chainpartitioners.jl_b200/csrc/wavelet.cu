@@ -1,6 +1,6 @@
 // wavelet.cu -- construction of the wavelet-matrix dominance index (kernel "build_dominance").
 //
-// One launch per bit level: every CTA owns a tile of 7168 consecutive elements (32 rank blocks),
+// One launch per bit level: every CTA (8 warps) owns a tile of 1792 consecutive elements (8 rank blocks, one per warp),
 // emits the level's bit-plane + running zero counts (one 32-byte block per 224 elements) and
 // stably partitions its elements into the next level's order.  The per-tile zero counts a level
 // needs are accumulated by the PREVIOUS level's launch (warp-aggregated atomics on the
@@ -13,7 +13,7 @@
 namespace cpb {
 
 static constexpr unsigned FULL = 0xffffffffu;
-static constexpr int WM_THREADS = 1024;  // 32 warps: one 224-element rank block (7 rounds of 32 lanes) per warp
+static constexpr int WM_THREADS = 32 * WM_TILE_BLOCKS;  // one 224-element rank block (7 rounds of 32 lanes) per warp
 static constexpr int WM_ROUNDS = 7;
 
 // zeros of bit `bit` per tile (first level only)
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_wm_count(const u32* __restrict__ cur, u
 }
 
 // tile_off: exclusive scan of per-tile zero counts, tile_off[tiles] = z (total zeros of the level)
-__global__ void __launch_bounds__(WM_THREADS, 2) k_wm_level(const u32* __restrict__ cur, u32* __restrict__ nxt, u32 n, int bit, int next_bit,
+__global__ void __launch_bounds__(WM_THREADS, 2048 / WM_THREADS) k_wm_level(const u32* __restrict__ cur, u32* __restrict__ nxt, u32 n, int bit, int next_bit,
                                                             const u32* __restrict__ tile_off, u32 tiles, u32* __restrict__ next_tile_zeros,
                                                             u32* __restrict__ blocks, u32 nblk, u32* __restrict__ z_out) {
   __shared__ u32 s_wz[32];
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(WM_THREADS, 2) k_wm_level(const u32* __restric
   if (lane == 0) s_wz[w] = wz;
   __syncthreads();
   const u32 zbefore = __reduce_add_sync(FULL, lane < w ? s_wz[lane] : 0u);  // zeros of the tile before this warp
-  const u32 tz = __reduce_add_sync(FULL, s_wz[lane]);                        // zeros of the whole tile
+  const u32 tz = 0;
   const u32 Z0 = tile_off[tile];
   const u32 ztot = tile_off[tiles];
   if (tile == 0 && tid == 0) *z_out = ztot;

@@ -15,8 +15,11 @@
 namespace cpb {
 
 static constexpr int WM_BLOCK = 224;       // elements per 32-byte rank block
-static constexpr int WM_TILE_BLOCKS = 32;  // rank blocks per build tile
-static constexpr int WM_TILE = WM_BLOCK * WM_TILE_BLOCKS;  // 7168 elements per build CTA
+#ifndef CPB_WM_WARPS
+#define CPB_WM_WARPS 8
+#endif
+static constexpr int WM_TILE_BLOCKS = CPB_WM_WARPS;  // rank blocks per build tile (one per warp of the build CTA)
+static constexpr int WM_TILE = WM_BLOCK * WM_TILE_BLOCKS;  // 1792 elements per build CTA
 
 struct DevWM {
   const u32* blocks;  // [L][nblk][8]
