@@ -32,8 +32,10 @@ N_COLS = int(os.environ.get("CPB_BENCH_N", 1_000_000))
 NNZ_PER_COL = 10
 K_PARTS = 64
 EPS = 0.01
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/), bytes
-TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at this workload
+# (profiles/r01_notes.md: k_probe_stream 44.7 MB read + 0.2 MB write; k_rs_scatter 42-82 MB read + 52-56 MB
+# write over the three passes; k_wm_level 40.05 MB read + 1-3 MB write), bytes
+TRAFFIC = {"k_probe_stream": 44.9e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6}
 METRIC = "partition_stripe throughput (BisectCostBottleneckSplitter, Erdos-Renyi 1Mx1M, K=64)"
 UNIT = "partitions/s"
 
@@ -43,14 +45,19 @@ def workload():
     from chainb200 import synth
 
     cache = os.path.join("/tmp", f"cpb_er_{N_COLS}_{NNZ_PER_COL}.npz")
+    A = None
     if os.path.exists(cache):
-        z = np.load(cache)
-        A = cp.SparseMatrixCSC(N_COLS, N_COLS, z["colptr"], z["rowval"])
-    else:
-        A = synth.erdos_renyi(N_COLS, NNZ_PER_COL)
         try:
-            os.makedirs(os.path.dirname(cache), exist_ok=True)
-            np.savez(cache, colptr=A.colptr, rowval=A.rowval)
+            z = np.load(cache)
+            A = cp.SparseMatrixCSC(N_COLS, N_COLS, z["colptr"], z["rowval"])
+        except Exception:
+            A = None
+    if A is None:
+        A = synth.erdos_renyi(N_COLS, NNZ_PER_COL)
+        try:  # atomic publish: concurrent ranks may generate the same matrix
+            tmp = f"{cache}.{os.getpid()}.tmp.npz"
+            np.savez(tmp, colptr=A.colptr, rowval=A.rowval)
+            os.replace(tmp, cache)
         except OSError:
             pass
     f = cp.AffineConnectivityModel(0, 10, 1, 100)

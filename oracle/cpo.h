@@ -18,8 +18,11 @@
  * of test/test_Partitioners.jl) on the reference's six fixture matrices
  * (test/matrices.jl, committed as tests/golden/ npz files) and on random inputs,
  * plus cross-checks between independent restatements (b-ary vs binary vs
- * stepwise dominance counts; BisectCost vs LazyBisect).  Exact split vectors
- * are therefore pinned by control-flow-faithful restatement only.
+ * stepwise dominance counts; BisectCost vs LazyBisect).
+ * PARITY UNPINNED for exact tie-breaking: no reference output exists to compare
+ * with (no golden split vectors in the reference, no Julia here), so exact
+ * split vectors under ties are pinned by control-flow-faithful restatement only;
+ * counts, costs, bounds and objective values are pinned by the properties above.
  *
  * All indices are 1-based Int64 exactly as Julia's SparseMatrixCSC stores
  * them: colptr[0..n] holds values 1..N+1, rowval[0..N-1] holds 1..m.
