@@ -5,7 +5,6 @@
 namespace cpb {
 
 static constexpr unsigned FULL = 0xffffffffu;
-bool vals_iota_hint = false;  // set by radix_sort_pairs_iota: the first pass generates payload = index
 
 int bits_for(u64 v) {
   int b = 1;
@@ -98,44 +97,51 @@ void exclusive_scan_u32(const u32* in, u32* out, size_t n) {
 }
 
 // ------------------------------------------------------------------------------ radix sort
-// Stable LSD radix sort, 8 bits per pass, tiles of 8192 (key, payload) pairs:
+// Stable LSD radix sort, DB = 8 or 10 bits per pass (the width is chosen to minimise passes), tiles of 8192
+// (key, payload) pairs:
 //   k_rs_hist     per-tile digit histogram                      (digit-major table, then one scan)
 //   k_rs_scatter  ranks every pair inside the tile (warp-level match_any rounds + per-digit walk over the
-//                 32 warps), stages the tile in shared memory in sorted order and copies it out so that
+//                 16 warps), stages the tile in shared memory in sorted order and copies it out so that
 //                 every digit run is written with coalesced stores.
 static constexpr int RS_THREADS = 512;
 static constexpr int RS_IPT = 16;
 static constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 8192 pairs per CTA, 512 per warp
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr u32 RS_INVALID = 0xffffffffu;
-static constexpr size_t RS_SMEM = (size_t)RS_WARPS * 256 * 2 + 256 * 4 + 256 * 4 + (size_t)RS_TILE * 8;
+template <int DB> constexpr size_t rs_smem() { return (size_t)RS_WARPS * (1 << DB) * 2 + (size_t)(1 << DB) * 4 * 2 + 64 + (size_t)RS_TILE * 8; }
 
 // per-tile digit histogram, stored digit-major: hist[d * tiles + tile]
+template <int DB>
 __global__ void __launch_bounds__(256) k_rs_hist(const u32* __restrict__ keys, size_t n, int shift, u32* __restrict__ hist, u32 tiles) {
-  __shared__ u32 h[256];
-  h[threadIdx.x] = 0;
+  constexpr int NB = 1 << DB;
+  __shared__ u32 h[NB];
+  for (int d = threadIdx.x; d < NB; d += 256) h[d] = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
   for (int r = 0; r < RS_TILE / 256; ++r) {
     const size_t i = base + (size_t)r * 256 + threadIdx.x;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & (NB - 1)], 1u);
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
+  for (int d = threadIdx.x; d < NB; d += 256) hist[(size_t)d * tiles + blockIdx.x] = h[d];
 }
 
+template <int DB>
 __global__ void __launch_bounds__(RS_THREADS, 2) k_rs_scatter(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
                                                               u32* __restrict__ keys_out, u32* __restrict__ vals_out, size_t n,
                                                               int shift, const u32* __restrict__ offs, u32 tiles, int iota_vals) {
-  extern __shared__ __align__(16) unsigned char rs_smem[];
-  unsigned short* wh = reinterpret_cast<unsigned short*>(rs_smem);            // [RS_WARPS][256] counts, then tile-local bases
-  u32* s_tot = reinterpret_cast<u32*>(rs_smem + (size_t)RS_WARPS * 256 * 2);  // [256] per-digit totals -> tile-local digit base
-  u32* s_gb = s_tot + 256;                                                    // [256] global base - local base
-  u32* s_keys = s_gb + 256;                                                   // [RS_TILE]
-  u32* s_vals = s_keys + RS_TILE;                                             // [RS_TILE]
+  constexpr int NB = 1 << DB;
+  constexpr int DPT = NB / 256;  // digits per thread of the first 256 threads (1 or 4)
+  extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+  unsigned short* wh = reinterpret_cast<unsigned short*>(rs_smem_raw);              // [RS_WARPS][NB] counts, then tile-local bases
+  u32* s_tot = reinterpret_cast<u32*>(rs_smem_raw + (size_t)RS_WARPS * NB * 2);     // [NB] tile-local base of every digit
+  u32* s_gb = s_tot + NB;                                                           // [NB] global base - local base
+  u32* s_wsum = s_gb + NB;                                                          // [8] warp totals of the digit scan
+  u32* s_keys = s_wsum + 16;                                                        // [RS_TILE]
+  u32* s_vals = s_keys + RS_TILE;                                                   // [RS_TILE]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) wh[i] = 0;
+  for (int i = tid; i < RS_WARPS * NB; i += RS_THREADS) wh[i] = 0;
   __syncthreads();
   const size_t tbase = (size_t)blockIdx.x * RS_TILE;
   const size_t base = tbase + (size_t)w * (32 * RS_IPT);
@@ -152,57 +158,70 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_rs_scatter(const u32* __restr
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     const size_t i = base + (size_t)r * 32 + lane;
-    const u32 d = (i < n) ? ((key[r] >> shift) & 255u) : RS_INVALID;
+    const u32 d = (i < n) ? ((key[r] >> shift) & (NB - 1)) : RS_INVALID;
     const unsigned m = __match_any_sync(FULL, d);
     const int leader = __ffs(m) - 1;
     u32 old = 0;
     if (d != RS_INVALID && lane == leader) {
-      old = wh[w * 256 + d];
-      wh[w * 256 + d] = (unsigned short)(old + __popc(m));
+      old = wh[w * NB + d];
+      wh[w * NB + d] = (unsigned short)(old + __popc(m));
     }
     __syncwarp();
     old = __shfl_sync(FULL, old, leader);
     rnk[r] = old + (u32)__popc(m & lt);
   }
   __syncthreads();
-  u32 dtot = 0;
-  if (tid < 256) {  // per digit: exclusive walk over the warps
-    u32 run = 0;
-#pragma unroll 8
-    for (int k = 0; k < RS_WARPS; ++k) {
-      const u32 t = wh[k * 256 + tid];
-      wh[k * 256 + tid] = (unsigned short)run;
-      run += t;
+  // per digit: exclusive walk over the warps (thread t < 256 owns digits t*DPT .. t*DPT+DPT-1), then an
+  // exclusive scan of the digit totals
+  u32 dtot[DPT];
+  u32 tsum = 0;
+  if (tid < 256) {
+#pragma unroll
+    for (int e = 0; e < DPT; ++e) {
+      const int d = tid * DPT + e;
+      u32 run = 0;
+#pragma unroll 4
+      for (int k = 0; k < RS_WARPS; ++k) {
+        const u32 t = wh[k * NB + d];
+        wh[k * NB + d] = (unsigned short)run;
+        run += t;
+      }
+      dtot[e] = run;
+      tsum += run;
     }
-    dtot = run;
   }
-  // exclusive scan of the 256 digit totals (8 warps)
-  u32 inc = dtot;
+  u32 inc = tsum;
   if (tid < 256) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u32 y = __shfl_up_sync(FULL, inc, o);
       if (lane >= o) inc += y;
     }
-    if (lane == 31) s_gb[w] = inc;  // warp totals (temporarily)
+    if (lane == 31) s_wsum[w] = inc;
   }
   __syncthreads();
   if (tid < 256) {
     u32 wb = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      if (k < w) wb += s_gb[k];
-    s_tot[tid] = wb + inc - dtot;  // tile-local base of digit tid
+      if (k < w) wb += s_wsum[k];
+    u32 run = wb + inc - tsum;
+#pragma unroll
+    for (int e = 0; e < DPT; ++e) {
+      const int d = tid * DPT + e;
+      s_tot[d] = run;
+      s_gb[d] = offs[(size_t)d * tiles + blockIdx.x] - run;
+      run += dtot[e];
+    }
   }
   __syncthreads();
-  if (tid < 256) s_gb[tid] = offs[(size_t)tid * tiles + blockIdx.x] - s_tot[tid];
   // stage the tile in sorted order
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     const size_t i = base + (size_t)r * 32 + lane;
     if (i < n) {
-      const u32 d = (key[r] >> shift) & 255u;
-      const u32 p = s_tot[d] + wh[w * 256 + d] + rnk[r];
+      const u32 d = (key[r] >> shift) & (NB - 1);
+      const u32 p = s_tot[d] + wh[w * NB + d] + rnk[r];
       s_keys[p] = key[r];
       s_vals[p] = val[r];
     }
@@ -214,47 +233,57 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_rs_scatter(const u32* __restr
     const u32 p = (u32)r * RS_THREADS + tid;
     if (p < tile_n) {
       const u32 k = s_keys[p];
-      const u32 dst = s_gb[(k >> shift) & 255u] + p;
+      const u32 dst = s_gb[(k >> shift) & (NB - 1)] + p;
       keys_out[dst] = k;
       vals_out[dst] = s_vals[p];
     }
   }
 }
 
-// Stable sort of (key, payload) by the low `bits` bits of key.  vals == nullptr: the payload is the
-// element index (iota), generated on the fly in the first pass.
-int radix_sort_pairs(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
-  if (n == 0) return 0;
+template <int DB>
+static int radix_sort_passes(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int passes, bool iota_payload) {
+  constexpr int NB = 1 << DB;
   static bool attr_set = false;
   if (!attr_set) {
-    CPB_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+    CPB_CUDA(cudaFuncSetAttribute(k_rs_scatter<DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem<DB>()));
     attr_set = true;
   }
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-  DBuf<u32> hist((size_t)256 * tiles);
+  DBuf<u32> hist((size_t)NB * tiles);
   int which = 0;
-  bool first = true;
-  for (int shift = 0; shift < bits; shift += 8) {
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * DB;
     u32* ki = which ? keys_tmp : keys;
     u32* vi = which ? vals_tmp : vals;
     u32* ko = which ? keys : keys_tmp;
     u32* vo = which ? vals : vals_tmp;
-    CPB_LAUNCH(k_rs_hist, tiles, 256, 0, ki, n, shift, hist.get(), tiles);
-    exclusive_scan_u32(hist.get(), hist.get(), (size_t)256 * tiles);
+    CPB_LAUNCH(k_rs_hist<DB>, tiles, 256, 0, ki, n, shift, hist.get(), tiles);
+    exclusive_scan_u32(hist.get(), hist.get(), (size_t)NB * tiles);
     {
       ProfScope pk("k_rs_scatter", (double)n * 16.0);  // read + write one (key, payload) pair per element
-      CPB_LAUNCH(k_rs_scatter, tiles, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, hist.get(), tiles, (first && vals_iota_hint) ? 1 : 0);
+      CPB_LAUNCH(k_rs_scatter<DB>, tiles, RS_THREADS, rs_smem<DB>(), ki, vi, ko, vo, n, shift, hist.get(), tiles, (pass == 0 && iota_payload) ? 1 : 0);
     }
-    first = false;
     which ^= 1;
   }
-  vals_iota_hint = false;
   return which;
 }
 
+// Stable sort of (key, payload) by the low `bits` bits of key.  iota_payload: the payload is the element
+// index, generated on the fly in the first pass (vals need not be initialised).  10-bit digits are used when
+// they save a pass (17..20 and 25..30 key bits).
+static int radix_sort_impl(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits, bool iota_payload) {
+  if (n == 0) return 0;
+  const int p8 = (bits + 7) / 8, p10 = (bits + 9) / 10;
+  if (p10 < p8) return radix_sort_passes<10>(keys, vals, keys_tmp, vals_tmp, n, p10, iota_payload);
+  return radix_sort_passes<8>(keys, vals, keys_tmp, vals_tmp, n, p8, iota_payload);
+}
+
+int radix_sort_pairs(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
+  return radix_sort_impl(keys, vals, keys_tmp, vals_tmp, n, bits, false);
+}
+
 int radix_sort_pairs_iota(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
-  vals_iota_hint = true;
-  return radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, bits);
+  return radix_sort_impl(keys, vals, keys_tmp, vals_tmp, n, bits, true);
 }
 
 // ------------------------------------------------------------------------------ small kernels
