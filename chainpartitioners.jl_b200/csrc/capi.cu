@@ -344,8 +344,8 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
   CPB_REQUIRE(f && spl_out, "NULL argument");
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   switch (method) {
-    case CPB_SPLIT_DYNAMIC_BOTTLENECK: solve_dynamic(*f->O, false, con, K, spl_out); break;
-    case CPB_SPLIT_DYNAMIC_TOTAL: solve_dynamic(*f->O, true, con, K, spl_out); break;
+    case CPB_SPLIT_DYNAMIC_BOTTLENECK: case CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER: solve_dynamic(*f->O, false, con, K, spl_out); break;
+    case CPB_SPLIT_DYNAMIC_TOTAL: case CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER: solve_dynamic(*f->O, true, con, K, spl_out); break;
     case CPB_SPLIT_BISECT_COST: solve_bisect(*f->O, false, eps, K, spl_out); break;
     case CPB_SPLIT_LAZY_BISECT_COST: solve_bisect(*f->O, true, eps, K, spl_out); break;
     case CPB_SPLIT_EQUI: {  // EquiPartitioner.jl:3-9

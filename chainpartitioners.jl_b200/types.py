@@ -483,6 +483,12 @@ class EquiChunker:
     w: int
 
 
+@dataclass
+class DynamicBottleneckChunker:
+    """DynamicChunker.jl:3-5 (only usable through partition_stripe: DynamicSplitter.jl:52-87)."""
+    f: Any
+
+
 class DynamicTotalChunker:
     """DynamicChunker.jl:9-11; the deprecated two-argument form ``DynamicTotalChunker(f, w_max)``
     means ``ConstrainedCost(f, VertexCount(), w_max)`` (ChainPartitioners.jl:221)."""
@@ -564,6 +570,7 @@ class DisjointPacker:
 # method codes shared by the C ABI (include/chainb200.h) and the CPU oracle (oracle/cpo.h)
 SPLIT_DYNAMIC_BOTTLENECK, SPLIT_DYNAMIC_TOTAL, SPLIT_BISECT_COST, SPLIT_LAZY_BISECT_COST = 0, 1, 2, 3
 SPLIT_LAZY_BISECT_GENERIC, SPLIT_EQUI, SPLIT_FLIP_BISECT_COST, SPLIT_LAZY_FLIP_BISECT_COST = 4, 5, 6, 7
+SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, SPLIT_DYNAMIC_TOTAL_CHUNKER = 10, 11
 PACK_DYNAMIC_TOTAL, PACK_CONVEX_TOTAL, PACK_CONCAVE_TOTAL, PACK_OVERLAP, PACK_STRICT, PACK_EQUI = 0, 1, 2, 3, 4, 5
 
 
@@ -583,6 +590,12 @@ def split_method_code(method) -> Tuple[int, Any, float]:
         return SPLIT_LAZY_FLIP_BISECT_COST, method.f, float(method.eps)
     if isinstance(method, EquiSplitter):
         return SPLIT_EQUI, None, 0.0
+    # partition_stripe(A, K, ::AbstractDynamicChunker) (DynamicSplitter.jl:52-87): the K-part DP with the part
+    # index as the inner loop
+    if isinstance(method, DynamicBottleneckChunker):
+        return SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, method.f, 0.0
+    if isinstance(method, DynamicTotalChunker):
+        return SPLIT_DYNAMIC_TOTAL_CHUNKER, method.f, 0.0
     raise TypeError(f"partition_stripe: unsupported method {type(method).__name__}")
 
 

@@ -131,7 +131,11 @@ enum {
   CPB_SPLIT_DYNAMIC_TOTAL = 1,      /* partition_stripe(A, K, DynamicTotalSplitter(f))       DynamicSplitter.jl:15-50 */
   CPB_SPLIT_BISECT_COST = 2,        /* BisectCostBottleneckSplitter(f, eps)      BisectCostBottleneckSplitter.jl:6-63 */
   CPB_SPLIT_LAZY_BISECT_COST = 3,   /* LazyBisectCostBottleneckSplitter(f, eps)  LazyBisectCostBottleneckSplitter.jl:8-70,140-258,260-388 */
-  CPB_SPLIT_EQUI = 5                /* EquiSplitter()                            EquiPartitioner.jl:3-9 */
+  CPB_SPLIT_EQUI = 5,               /* EquiSplitter()                            EquiPartitioner.jl:3-9 */
+  /* partition_stripe(A, K, ::AbstractDynamicChunker) DynamicSplitter.jl:52-87,249-314: the same K-part recurrence
+     and `<=` tie rule as the splitter form with the part index as the inner loop -> identical split vectors */
+  CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* partition_stripe(A, K, DynamicBottleneckChunker(f)) */
+  CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11       /* partition_stripe(A, K, DynamicTotalChunker(f)) */
 };
 /* -> spl_out[K+1] (SplitPartition{Int64}(K, spl), Partitions.jl:3-6); con may be NULL. */
 int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out);

@@ -194,6 +194,14 @@ extern "C" int cpo_partition_stripe(int method, const cpo_model* mdl, const cpo_
             else dynamic_splitter<F, T>(f, n, K, method == CPO_SPLIT_DYNAMIC_TOTAL, spl.data());
           });
           break;
+        case CPO_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER: case CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER:
+          with_oracle<T>(mdl, CPO_HINT_STEP, M, pi_spl, pi_K, [&](auto& f) {
+            t1 = now_s();
+            using F = std::remove_reference_t<decltype(f)>;
+            if (w.enabled) dynamic_chunker_kform_constrained<F, T>(f, w, n, K, method == CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER, spl.data());
+            else dynamic_chunker_kform<F, T>(f, n, K, method == CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER, spl.data());
+          });
+          break;
         case CPO_SPLIT_BISECT_COST: case CPO_SPLIT_FLIP_BISECT_COST:
           with_oracle<T>(mdl, CPO_HINT_SPARSE, M, pi_spl, pi_K, [&](auto& f) {
             using F = std::remove_reference_t<decltype(f)>;

@@ -66,7 +66,9 @@ enum {
   CPO_SPLIT_FLIP_BISECT_COST = 6,     /* BisectCostBottleneckSplitter.jl:70-127 */
   CPO_SPLIT_LAZY_FLIP_BISECT_COST = 7,/* LazyBisectCostBottleneckSplitter.jl:79-138 */
   CPO_SPLIT_CONVEX_TOTAL = 8,         /* ConvexTotalChunker.jl:26-55 (ConvexTotalSplitter) */
-  CPO_SPLIT_CONCAVE_TOTAL = 9         /* ConcaveTotalChunker.jl:26-55 (ConcaveTotalSplitter) */
+  CPO_SPLIT_CONCAVE_TOTAL = 9,        /* ConcaveTotalChunker.jl:26-55 (ConcaveTotalSplitter) */
+  CPO_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* DynamicSplitter.jl:52-87 with DynamicBottleneckChunker */
+  CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11       /* DynamicSplitter.jl:52-87 with DynamicTotalChunker */
 };
 
 /* pack_stripe methods */

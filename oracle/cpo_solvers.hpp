@@ -91,6 +91,34 @@ template <class F, class T> static void dynamic_splitter(F& f, i64 n, i64 K, boo
   unravel_splits(K, n, [&](i64 k, i64 jp) { return P(jp, k); }, spl);
 }
 
+// DynamicSplitter.jl:52-87: partition_stripe(A, K, ::AbstractDynamicChunker) -- the same recurrence with the
+// part index as the inner loop (all layers advance together over j')
+template <class F, class T> static void dynamic_chunker_kform(F& f, i64 n, i64 K, bool total, i64* spl) {
+  auto g = [total](T a, T b) { return total ? a + b : std::max(a, b); };
+  std::vector<i64> ptr((size_t)(K + 1) * (n + 2), 0);
+  std::vector<T> cst((size_t)(K + 1) * (n + 2), tmax<T>());
+  auto P = [&](i64 k, i64 jp) -> i64& { return ptr[(size_t)k + (size_t)(K + 1) * jp]; };
+  auto C = [&](i64 k, i64 jp) -> T& { return cst[(size_t)k + (size_t)(K + 1) * jp]; };
+  for (i64 jp = 1; jp <= n + 1; ++jp) {
+    const i64 K1 = jp == n + 1 ? K : K - 1;
+    T dc = f(1, jp, 1);
+    C(1, jp) = dc;
+    P(1, jp) = 1;
+    for (i64 k = 2; k <= K1; ++k) {
+      T c2 = g(C(k - 1, 1), dc);
+      if (c2 <= C(k, jp)) { C(k, jp) = c2; P(k, jp) = 1; }
+    }
+    for (i64 j = 2; j <= jp; ++j) {
+      dc = f.step_next_same(j, jp, 1);
+      for (i64 k = 2; k <= K1; ++k) {
+        T c2 = g(C(k - 1, j), dc);
+        if (c2 <= C(k, jp)) { C(k, jp) = c2; P(k, jp) = j; }
+      }
+    }
+  }
+  unravel_splits(K, n, [&](i64 k, i64 jp) { return P(k, jp); }, spl);
+}
+
 // DynamicSplitter.jl:144-173 column_constraints
 template <class W> static void column_constraints(i64 n, i64 K, W& w, ivec& lo, ivec& hi) {
   lo.assign(K + 1, 0);
@@ -143,6 +171,67 @@ template <class F, class T> static void dynamic_splitter_constrained(F& f, Weigh
     }
   }
   unravel_splits(K, n, [&](i64 k, i64 jp) { return getP(jp, k); }, spl);
+}
+
+// DynamicSplitter.jl:175-204 part_constraints: for every column boundary the range of part indices that may end there
+template <class W> static void part_constraints(i64 n, i64 K, W& w, ivec& k_lo, ivec& k_hi) {
+  k_hi.assign(n + 2, 0);
+  i64 jp = n + 1;
+  k_hi[n + 1] = K;
+  for (i64 k = K; k >= 1; --k) {
+    i64 j = jp;
+    while (j - 1 >= 1 && !w.over(j - 1, jp)) { j -= 1; k_hi[j] = k - 1; }
+    jp = j;
+  }
+  k_lo.assign(n + 2, 0);
+  i64 j = 1;
+  k_lo[1] = 1;
+  for (i64 k = 1; k <= K; ++k) {
+    jp = j;
+    while (jp + 1 <= n + 1 && !w.over(j, jp + 1)) { jp += 1; k_lo[jp] = k; }
+    j = jp;
+  }
+}
+
+// DynamicSplitter.jl:249-314 (AbstractDynamicChunker{<:ConstrainedCost}): the constrained K-part DP with the part index
+// as the inner loop.  The reference's banded storage holds uninitialised memory inside the window; every in-window
+// entry is written (unconditionally, by the j0 candidate) before it is compared against whenever w is monotone, so
+// the tmax initialisation here is never observed.
+template <class F, class T> static void dynamic_chunker_kform_constrained(F& f, Weight& w, i64 n, i64 K, bool total, i64* spl) {
+  auto g = [total](T a, T b) { return total ? a + b : std::max(a, b); };
+  ivec k_lo, k_hi;
+  part_constraints(n, K, w, k_lo, k_hi);
+  if (k_lo[n + 1] == 0) {  // :259-264 infeasible -> degenerate partition
+    for (i64 k = 1; k <= K; ++k) spl[k] = 1;
+    spl[K + 1] = n + 1;
+    return;
+  }
+  std::vector<i64> ptr((size_t)(K + 2) * (n + 2), 0);
+  std::vector<T> cst((size_t)(K + 2) * (n + 2), tmax<T>());
+  auto inwin = [&](i64 k, i64 jp) { return k_lo[jp] <= k && k <= k_hi[jp]; };
+  auto at = [&](i64 k, i64 jp) { return (size_t)k + (size_t)(K + 2) * jp; };
+  auto getC = [&](i64 k, i64 jp) -> T { return inwin(k, jp) ? cst[at(k, jp)] : tmax<T>(); };
+  auto setC = [&](i64 k, i64 jp, T v) { if (inwin(k, jp)) cst[at(k, jp)] = v; };
+  auto getP = [&](i64 k, i64 jp) -> i64 { return inwin(k, jp) ? ptr[at(k, jp)] : 0; };
+  auto setP = [&](i64 k, i64 jp, i64 v) { if (inwin(k, jp)) ptr[at(k, jp)] = v; };
+  i64 j0 = 1;
+  for (i64 jp = 1; jp <= n + 1; ++jp) {
+    while (w.over(j0, jp)) j0 += 1;
+    T dc = f(j0, jp, 1);
+    if (j0 == 1) { setC(1, jp, dc); setP(1, jp, 1); }
+    for (i64 k = std::max(k_lo[j0] + 1, k_lo[jp]); k <= std::min(k_hi[j0] + 1, k_hi[jp]); ++k) {
+      setC(k, jp, g(getC(k - 1, j0), dc));
+      setP(k, jp, j0);
+    }
+    for (i64 j = j0 + 1; j <= jp; ++j) {
+      dc = f.step_next_same(j, jp, 1);
+      for (i64 k = std::max(k_lo[j] + 1, k_lo[jp]); k <= std::min(k_hi[j] + 1, k_hi[jp]); ++k) {
+        T c2 = g(getC(k - 1, j), dc);
+        if (c2 <= getC(k, jp)) { setC(k, jp, c2); setP(k, jp, j); }
+      }
+    }
+  }
+  unravel_splits(K, n, [&](i64 k, i64 jp) { return getP(k, jp); }, spl);
 }
 
 // BisectCostBottleneckSplitter.jl:6-63 (flip = false) and :70-127 (flip = true)

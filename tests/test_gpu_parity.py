@@ -361,6 +361,18 @@ def test_constrained_dynamic_splitters(ref, fixtures):
                         assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, mk.__name__, g.spl, r.spl)
 
 
+def test_dynamic_chunker_kform(ref, fixtures):
+    """partition_stripe(A, K, DynamicBottleneckChunker(f) / DynamicTotalChunker(f)) (DynamicSplitter.jl:52-87,249-314)."""
+    rng = np.random.default_rng(301)
+    for A in [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 10, 0.3), sprand(rng, 40, 120, 0.1)]:
+        for f in [cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineWorkModel(0, 10, 1)]:
+            for K in [1, 2, 3, 8]:
+                for mk in (cp.DynamicBottleneckChunker, cp.DynamicTotalChunker):
+                    for spec in (f, cp.ConstrainedCost(f, cp.VertexCount(), 8), cp.ConstrainedCost(f, cp.VertexCount(), 2)):
+                        g, r = cp.partition_stripe(A, K, mk(spec)), ref.partition_stripe(A, K, mk(spec))
+                        assert np.array_equal(g.spl, r.spl), (A, f, K, mk.__name__, g.spl, r.spl)
+
+
 def test_degenerate_inputs(ref):
     """Empty matrices, empty columns/rows, K > n, single column -- the ragged cases."""
     z = np.zeros(0, dtype=np.int64)

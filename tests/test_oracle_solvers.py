@@ -161,6 +161,26 @@ def test_dynamic_splitter_constrained(ref):
                     assert objective(Cw, Phi.spl, True) == opt
 
 
+def test_dynamic_chunker_kform(ref):
+    """partition_stripe(A, K, ::AbstractDynamicChunker) (DynamicSplitter.jl:52-87, constrained :249-314): the K-part
+    recurrence with the part index as the inner loop -- optimum, and split vectors identical to the splitter form
+    (same `<=` rule, same candidate sets), which is what lets the device serve both with one DP."""
+    rng = np.random.default_rng(15)
+    for trial in range(60):
+        A = sprand(rng, int(rng.integers(1, 9)), int(rng.integers(1, 13)), float(rng.choice([0.1, 0.3, 0.5])))
+        mdl = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(2, 0, 0, 1)][trial % 3]
+        C = cost_matrix(mdl, A)
+        for K in [1, 2, 3, 4, 8]:
+            for total, S, Ch in [(False, cp.DynamicBottleneckSplitter, cp.DynamicBottleneckChunker), (True, cp.DynamicTotalSplitter, cp.DynamicTotalChunker)]:
+                Phi = ref.partition_stripe(A, K, Ch(mdl))
+                check_split(Phi.spl, A.n, K)
+                assert objective(C, Phi.spl, total) == brute_optimum(C, A.n, K, total)
+                assert Phi.spl.tolist() == ref.partition_stripe(A, K, S(mdl)).spl.tolist() == rightmost_dp(C, A.n, K, total)
+                for w_max in [2, 4]:
+                    f = cp.ConstrainedCost(mdl, cp.VertexCount(), w_max)
+                    assert ref.partition_stripe(A, K, Ch(f)).spl.tolist() == ref.partition_stripe(A, K, S(f)).spl.tolist()
+
+
 def greedy_probe(C, n, K, c):
     """every part as long as feasible at threshold c; None if infeasible"""
     spl = [1]
