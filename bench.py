@@ -289,7 +289,7 @@ def main():
                         "h2d_bytes_per_step": int((A.nnz + A.n + 1) * 8 + 512), "d2h_bytes_per_step": int((K_PARTS + 1) * 8 + 64)},
                 "oracle_queries_per_s": queries_per_s * world, "oracle_query_batch": {"Q": Q, "ms": q_ms / 3, "pattern": "uniform random (j <= j') pairs, device-resident"},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_all_kernels": roofline_all, "cpu_baseline": cpu, "clocks": sampler.summary(),
-                "phases_ms_per_step": phases, "parity": "split vector identical to the CPU oracle" if cpu else "checked at N=1"}
+                "phases_ms_per_step": phases, "bisection": cp.bisect_stats(), "parity": "split vector identical to the CPU oracle" if cpu else "checked at N=1"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

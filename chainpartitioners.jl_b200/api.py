@@ -20,12 +20,12 @@ __all__ = [
     "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
-    "launch_count", "probe_cluster_capacity", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
+    "launch_count", "probe_cluster_capacity", "bisect_stats", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
 ]
 
 I64 = np.int64
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libchainb200.so")
+_LIB_PATH = os.environ.get("CHAINB200_LIB") or os.path.join(_HERE, "libchainb200.so")  # override: instrumented builds only
 _lib = None
 
 ABI_SYMBOLS = [
@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
-    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_probe_cluster_capacity",
+    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_probe_cluster_capacity",
     "cpb_links_partial", "cpb_oracle_set_links",
 ]
 
@@ -519,6 +519,13 @@ def profile_get() -> dict:
         nm = names.raw[32 * t : 32 * t + 32].split(b"\0", 1)[0].decode()
         out[nm] = dict(ms=ms[t], launches=int(launches[t]), bytes=nbytes[t])
     return out
+
+
+def bisect_stats() -> dict:
+    """Diagnostics of the most recent bisection (``cpb_bisect_stats``)."""
+    out = (ctypes.c_double * 6)()
+    _check(load_library().cpb_bisect_stats(out))
+    return {"rounds": int(out[0]), "probes": int(out[1]), "speculated": int(out[2]), "c_lo": out[3], "c_hi": out[4], "plan_upper_bound": out[5]}
 
 
 def probe_cluster_capacity(streaming: bool = True) -> int:

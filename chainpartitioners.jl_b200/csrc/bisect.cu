@@ -19,6 +19,7 @@
 //     back to the full range, so the result never depends on them.
 #include <algorithm>
 #include <cmath>
+#include <queue>
 #include <cooperative_groups.h>
 #include "engine.cuh"
 
@@ -29,7 +30,8 @@ namespace cpb {
 static constexpr int BS_THREADS = 128;
 static constexpr int BS_CLUSTER = 8;
 static constexpr int BS_WIDTH = BS_THREADS * BS_CLUSTER;  // candidates per round
-static constexpr int BS_MAX_DEPTH = 8;      // deepest speculation tree (all ranks together)
+static constexpr int BS_MAX_NODES = 255;    // nodes of one round's speculation tree (all ranks together)
+static constexpr int BS_MAX_DEPTH = 24;     // deepest node of a round's tree (heap index < 2^25)
 static constexpr int BS_LOCAL_DEPTH = 4;    // a single GPU hosts at most 2^4 clusters of 8 CTAs
 
 struct BisectState {
@@ -39,6 +41,25 @@ struct BisectState {
   int rounds;
   int _pad;
 };
+
+// Threshold of the bisection-tree node with heap index `heap` (left child = "the parent's probe was feasible"),
+// produced with the reference's own double expressions from the round's starting state; returns 0 if the
+// sequential loop would have stopped before reaching the node.
+__device__ __forceinline__ int node_threshold(const BisectState* __restrict__ st, double eps1, int heap, double* c_out) {
+  int valid = (st->done || heap < 0) ? 0 : 1;  // heap < 0: unused slot of the round's plan
+  double lo = st->c_lo, hi = st->c_hi;
+  int len = 0;
+  unsigned path = 0;  // bit t = step t (from the node upwards) was a left child
+  for (int i = heap; i > 0; i = (i - 1) >> 1) { path |= (unsigned)(i & 1) << len; ++len; }
+  for (int t = len - 1; t >= 0 && valid; --t) {
+    if (!(lo * eps1 < hi)) { valid = 0; break; }
+    const double c = (lo + hi) / 2;
+    if ((path >> t) & 1u) hi = c; else lo = c;
+  }
+  if (valid && !(lo * eps1 < hi)) valid = 0;
+  *c_out = (lo + hi) / 2;
+  return valid;
+}
 
 // largest x in [a, b] with c(j, x) <= c, or a-1 if c(j, a) > c.  Monotone predicate.  Cluster-wide:
 // every CTA of the cluster calls it with the same arguments and gets the same answer.
@@ -75,29 +96,14 @@ template <class T>
 __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
     k_bisect_round(const __grid_constant__ DevOracle o, int K, double eps1, const BisectState* __restrict__ st,
                    const int* __restrict__ hint_lo, const int* __restrict__ hint_hi, int* __restrict__ node_spl,
-                   int* __restrict__ node_res, double* __restrict__ node_c, int node_base) {
+                   int* __restrict__ node_res, double* __restrict__ node_c, const int* __restrict__ node_ids, int node_base) {
   __shared__ double s_c;
   __shared__ int s_valid;
   __shared__ int s_cnt[2][BS_CLUSTER];
   cg::cluster_group cluster = cg::this_cluster();
-  const int node = node_base + blockIdx.x / BS_CLUSTER;
+  const int node = node_base + blockIdx.x / BS_CLUSTER;  // slot of this round; node_ids[slot] = heap index in the bisection tree
   const bool writer = cluster.block_rank() == 0 && threadIdx.x == 0;
-  if (threadIdx.x == 0) {
-    int valid = st->done ? 0 : 1;
-    double lo = st->c_lo, hi = st->c_hi;
-    // path from the root to this node in heap order: left child = "ancestor was feasible"
-    int path[BS_MAX_DEPTH];
-    int len = 0;
-    for (int i = node; i > 0; i = (i - 1) >> 1) path[len++] = (i & 1);  // 1 = left child
-    for (int t = len - 1; t >= 0 && valid; --t) {
-      if (!(lo * eps1 < hi)) { valid = 0; break; }
-      const double c = (lo + hi) / 2;
-      if (path[t]) hi = c; else lo = c;
-    }
-    if (valid && !(lo * eps1 < hi)) valid = 0;
-    s_valid = valid;
-    s_c = (lo + hi) / 2;
-  }
+  if (threadIdx.x == 0) s_valid = node_threshold(st, eps1, node_ids[node], &s_c);
   __syncthreads();
   if (!s_valid) {  // uniform over the cluster: every CTA derives it from the same state
     if (writer) node_res[node] = 0;
@@ -196,7 +202,8 @@ __device__ unsigned long long g_probe_n;
 template <class T>
 __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS, 1)
     k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
-                   int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c, int node_base) {
+                   int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c,
+                   const int* __restrict__ node_ids, int node_base) {
   __shared__ u32 s_mask[SP_GROUPS * 4 + 4];
   __shared__ u32 s_cum[SP_GROUPS + 1];
   __shared__ double s_c;
@@ -205,26 +212,17 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   __shared__ u32 s_xb[2][4][BS_CLUSTER];  // per-CTA (feasible boundaries, boundaries, P and Wt at the last feasible one)
   __shared__ u32 s_pj[2 * SP_THREADS];    // (P, Wt) of every thread's boundary candidate, pass 1 | pass 2
   __shared__ u32 s_w[2 * SP_THREADS];
+  __shared__ u32 s_wtot[32];              // per-warp `prev < j` totals of the tile
+  __shared__ u32 s_red[2][4];             // single-pass boundary test: (feasible boundaries, max P, max Wt) of the CTA
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int node = node_base + blockIdx.x / BS_CLUSTER;
   const bool writer = crank == 0 && tid == 0;
   if (tid == 0) {
-    int valid = st->done ? 0 : 1;
-    double lo = st->c_lo, hi = st->c_hi;
-    int path[BS_MAX_DEPTH];
-    int len = 0;
-    for (int i = node; i > 0; i = (i - 1) >> 1) path[len++] = (i & 1);
-    for (int t = len - 1; t >= 0 && valid; --t) {
-      if (!(lo * eps1 < hi)) { valid = 0; break; }
-      const double c = (lo + hi) / 2;
-      if (path[t]) hi = c; else lo = c;
-    }
-    if (valid && !(lo * eps1 < hi)) valid = 0;
-    s_valid = valid;
-    s_c = (lo + hi) / 2;
+    s_valid = node_threshold(st, eps1, node_ids[node], &s_c);
     for (int k = 0; k < 4; ++k) s_mask[SP_GROUPS * 4 + k] = 0;
+    for (int k = 0; k < 4; ++k) { s_red[0][k] = 0; s_red[1][k] = 0; }
   }
   __syncthreads();
   if (!s_valid) {
@@ -264,11 +262,13 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
       if (e_c >= Ne && !(first && crank == 0)) jb = 0;
       else jb = ((u64)e_c + CE >= Ne) ? n1 : __ldg(s.colidx + e_c + CE) + 1;
-      // ---- bit masks of `prev < j`: 8 warp-wide 128-bit loads, 4 ballots each ----
+      // ---- bit masks of `prev < j`: each warp owns nv consecutive 128-element groups (one warp-wide 128-bit load and
+      //      4 ballots per group) and keeps the running count of its own groups ----
+      u32 wsum = 0;
 #pragma unroll
       for (int v = 0; v < SP_VEC; ++v) {
         if (v >= (int)nv) break;
-        const u32 g = v * 32 + warp;
+        const u32 g = warp * nv + v;
         const u32 idx = e_c + g * 128 + lane * 4;
         uint4 pv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if ((u64)idx + 4 <= Ne) {
@@ -284,39 +284,27 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         const unsigned m2 = __ballot_sync(0xffffffffu, pv.z < j && !(head && idx + 2 < e0));
         const unsigned m3 = __ballot_sync(0xffffffffu, pv.w < j && !(head && idx + 3 < e0));
         if (lane < 4) s_mask[g * 4 + lane] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
+        if (lane == 4) s_cum[g] = wsum;  // prefix inside the warp's run; the warp's base is added after the barrier
+        wsum += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
       }
+      if (lane == 0) s_wtot[warp] = wsum;
       PT(0);
       __syncthreads();
       PT(1);
-      // ---- exclusive scan of the 256 group popcounts by warp 0 (8 groups per lane); the other warps
-      //      go straight to the cluster barrier below ----
+      // ---- every warp adds the totals of the warps before it to its own groups' prefixes; warp 0 also forms the CTA
+      //      total.  The cluster barrier below orders these writes for the boundary phase. ----
       u32 tot_c = 0;
-      if (warp == 0) {
-        u32 loc[SP_VEC];
-        u32 sum = 0;
-#pragma unroll
-        for (int t = 0; t < SP_VEC; ++t) {
-          loc[t] = sum;
-          if (t < (int)nv) {
-            const uint4 mk = *reinterpret_cast<const uint4*>(&s_mask[(lane * nv + t) * 4]);
-            sum += __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
+      {
+        const u32 t = s_wtot[lane];
+        const u32 wbase = __reduce_add_sync(0xffffffffu, lane < warp ? t : 0u);
+        if (lane < (int)nv) s_cum[warp * nv + lane] += wbase;
+        if (warp == 0) {
+          tot_c = __reduce_add_sync(0xffffffffu, t);
+          if (lane == 0) {
+            s_cum[ngroups] = tot_c;
+            // sentinel masks behind the last group (prefix lookups at x == CE)
+            s_mask[ngroups * 4] = 0; s_mask[ngroups * 4 + 1] = 0; s_mask[ngroups * 4 + 2] = 0; s_mask[ngroups * 4 + 3] = 0;
           }
-        }
-        u32 inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += y;
-        }
-        const u32 excl = inc - sum;
-#pragma unroll
-        for (int t = 0; t < SP_VEC; ++t)
-          if (t < (int)nv) s_cum[lane * nv + t] = excl + loc[t];
-        tot_c = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) {
-          s_cum[ngroups] = tot_c;
-          // sentinel masks behind the last group (prefix lookups at x == CE)
-          s_mask[ngroups * 4] = 0; s_mask[ngroups * 4 + 1] = 0; s_mask[ngroups * 4 + 2] = 0; s_mask[ngroups * 4 + 3] = 0;
         }
       }
       PT(2);
@@ -339,7 +327,49 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       // locate its end (1024 evenly spaced probes, then the boundaries inside the crossing stride); every thread
       // stashes the (P, Wt) of its candidate so the next part can start without reloading them.
       u32 cnt = 0, lastp = 0, lastw = 0;
-      if (nb > 0) {
+      if (tid == 0) { s_red[ph ^ 1][0] = 0; s_red[ph ^ 1][1] = 0; s_red[ph ^ 1][2] = 0; }  // the next super-step's accumulators
+      if (nb > 0 && nb <= 4u * SP_THREADS) {
+        // thread t owns the (at most 4) consecutive boundaries [t * per, (t + 1) * per), all loaded up front (one memory
+        // latency).  Monotone costs: every thread tests its LAST boundary; the first thread whose last boundary fails
+        // holds the crossing and tests its remaining ones from registers.
+        const u32 per = (nb + SP_THREADS - 1) / SP_THREADS;
+        const u32 b0 = (u32)tid * per;
+        const u32 mine = b0 < nb ? min(per, nb - b0) : 0u;
+        u32 pjv[4], wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < (int)mine) {
+            pjv[i] = __ldg(s.P + ja + b0 + i);
+            wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + ja + b0 + i);
+          }
+        bool ok = false;
+        if (mine > 0) {
+          u32 pl = pjv[0], wl = wv[0];
+#pragma unroll
+          for (int i = 1; i < 4; ++i)
+            if (i < (int)mine) { pl = pjv[i]; wl = wv[i]; }
+          s_pj[tid] = pl;
+          s_w[tid] = wl;
+          ok = feasible_pw(ja + b0 + mine - 1, pl, wl);
+        }
+        const int ct = __syncthreads_count(ok);  // threads 0 .. ct-1 are feasible throughout
+        cnt = min((u32)ct * per, nb);
+        if (ct > 0) { lastp = s_pj[ct - 1]; lastw = s_w[ct - 1]; }
+        if (per > 1) {
+          if (tid == ct && mine > 1) {
+            u32 c2 = 0, lp = 0, lw = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (i < (int)mine - 1 && c2 == (u32)i && feasible_pw(ja + b0 + i, pjv[i], wv[i])) { c2 = i + 1; lp = pjv[i]; lw = wv[i]; }
+            s_red[ph][0] = c2;
+            s_red[ph][1] = lp;
+            s_red[ph][2] = lw;
+          }
+          __syncthreads();
+          const u32 c2 = s_red[ph][0];
+          if (c2 > 0) { cnt += c2; lastp = s_red[ph][1]; lastw = s_red[ph][2]; }
+        }
+      } else if (nb > 0) {
         const u32 stride = (nb + SP_THREADS - 1) / SP_THREADS;
         const u32 t0 = (u32)tid * stride;
         bool ok = false;
@@ -431,10 +461,14 @@ __global__ void k_count_zero(const u32* __restrict__ v, size_t n, u32* __restric
 // walks the probed subtree by feasibility (BisectCost...:53-59)
 __global__ void k_bisect_advance(int K, int P, double eps1, BisectState* st, int* __restrict__ hint_lo, int* __restrict__ hint_hi,
                                  int* __restrict__ best, const int* __restrict__ node_spl, const int* __restrict__ node_res,
-                                 const double* __restrict__ node_c) {
+                                 const double* __restrict__ node_c, const int* __restrict__ node_ids) {
   if (st->done) return;
-  int node = 0;
-  while (node < P) {
+  int heap = 0;
+  while (true) {
+    int node = -1;  // slot holding tree node `heap`; the walk leaves the probed set -> the next round continues from here
+    for (int t = 0; t < P; ++t)
+      if (node_ids[t] == heap) { node = t; break; }
+    if (node < 0) break;
     const int res = node_res[node];
     if (res == 0) {
       if (threadIdx.x == 0) st->done = 1;
@@ -444,11 +478,11 @@ __global__ void k_bisect_advance(int K, int P, double eps1, BisectState* st, int
     if (res == 2) {
       for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) { best[t] = spl[t]; hint_hi[t] = spl[t]; }
       if (threadIdx.x == 0) { st->c_hi = node_c[node]; st->probes += 1; }
-      node = 2 * node + 1;
+      heap = 2 * heap + 1;
     } else {
       for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) hint_lo[t] = spl[t];
       if (threadIdx.x == 0) { st->c_lo = node_c[node]; st->probes += 1; }
-      node = 2 * node + 2;
+      heap = 2 * heap + 2;
     }
     __syncthreads();
   }
@@ -487,6 +521,60 @@ i64 count_first_occurrences(const LinkStream& ls) {
   return (i64)h;
 }
 
+// ---- a cheap upper bound on the optimal bottleneck, used ONLY to decide which thresholds of the bisection tree are
+//      worth probing speculatively (plan_round below; the returned split vector never depends on it).  The columns are
+//      cut where U(x) = b_vertex x + b_pin Wt[x] + b_net P[x] (the cost with every pin counted as a new net) crosses
+//      k/K of its total; the bottleneck of that partition, evaluated exactly with one fused pass over the links, bounds
+//      the optimum from above.
+__device__ __forceinline__ double ub_weight(const DevStream& s, const double* cf, u32 x) {
+  return cf[1] * (double)x + cf[2] * (double)__ldg(s.Wt + x) + cf[3] * (double)__ldg(s.P + x);
+}
+__global__ void k_ub_splits(const __grid_constant__ DevStream s, int is_float, int K, int* __restrict__ spl, u32* __restrict__ cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // spl[k], k = 0..K (0-based parts, 1-based columns)
+  if (k > K) return;
+  double cf[4];
+  for (int t = 0; t < 4; ++t) cf[t] = is_float ? s.cf[t] : (double)s.ci[t];
+  if (!(cf[1] + cf[2] + cf[3] > 0)) { cf[1] = 1; cf[2] = 0; cf[3] = 0; }
+  const u32 n1 = s.n + 1;
+  const double u0 = ub_weight(s, cf, 1), u1 = ub_weight(s, cf, n1);
+  const double target = u0 + (u1 - u0) * ((double)k / (double)K);
+  u32 lo = 1, hi = n1;  // smallest x with U(x) >= target
+  while (lo < hi) {
+    const u32 mid = lo + ((hi - lo) >> 1);
+    if (ub_weight(s, cf, mid) >= target) hi = mid; else lo = mid + 1;
+  }
+  spl[k] = (k == 0) ? 1 : (k == K ? (int)n1 : (int)lo);
+  if (k < K) cnt[k] = 0;
+}
+__global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStream s, const int* __restrict__ spl, u32* __restrict__ cnt) {
+  const int k = blockIdx.y;
+  const u32 j = (u32)spl[k];
+  const u32 e0 = __ldg(s.P + j), e1 = __ldg(s.P + (u32)spl[k + 1]);
+  u32 c = 0;
+  for (u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) c += __ldg(s.prev + e) < j;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
+}
+__global__ void k_ub_max(const __grid_constant__ DevStream s, int is_float, int K, const int* __restrict__ spl, const u32* __restrict__ cnt,
+                         double* __restrict__ out) {
+  __shared__ double sm[32];
+  double cf[4];
+  for (int t = 0; t < 4; ++t) cf[t] = is_float ? s.cf[t] : (double)s.ci[t];
+  double best = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const u32 a = (u32)spl[k], b = (u32)spl[k + 1];
+    const double c = cf[0] + (double)(b - a) * cf[1] + ((double)__ldg(s.Wt + b) - (double)__ldg(s.Wt + a)) * cf[2] + (double)cnt[k] * cf[3];
+    best = fmax(best, c);
+  }
+  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmax(best, sm[w]);
+    out[0] = best;
+  }
+}
+
 // ---- one bisection as a sequence of steps, so that the nodes of a round can be probed by different
 //      ranks (chainb200.parallel.partition_stripe_sharded) ----
 struct BisectRun {
@@ -496,7 +584,7 @@ struct BisectRun {
   double eps1 = 1;
   int P = 1;
   DBuf<BisectState> st;
-  DBuf<int> hint_lo, hint_hi, best, own_spl, own_res;
+  DBuf<int> hint_lo, hint_hi, best, own_spl, own_res, ids;
   DBuf<double> own_c;
   int* node_spl = nullptr;
   int* node_res = nullptr;
@@ -504,7 +592,62 @@ struct BisectRun {
   DevStream ds{};
   bool done = false;
   double c_lo0 = 0, c_hi0 = 0, eps = 0;
+  // speculation plan of the current round: slot t probes tree node h_ids[t] (heap index)
+  BisectState h_st{};
+  std::vector<int> h_ids;
+  bool planned = false, adaptive = true;
+  i64 speculated = 0;  // thresholds probed so far (this rank)
+  double ub = 0;  // upper bound on the optimal bottleneck (0 = unknown)
 };
+
+// Prior over the optimal bottleneck c*: log-uniform over the initial bracket, mixed with a log-uniform bump just below
+// the heuristic upper bound when one is known.  A tree node is reached by the walk iff c* lies in its (c_lo, c_hi].
+static double prior_mass(const BisectRun& run, double lo, double hi) {
+  auto lu = [](double lo, double hi, double a, double b) {
+    lo = std::max(lo, a);
+    hi = std::min(hi, b);
+    return (hi > lo && a > 0 && b > a) ? (std::log(hi) - std::log(lo)) / (std::log(b) - std::log(a)) : 0.0;
+  };
+  if (!(run.c_lo0 > 0) || !(run.c_hi0 > run.c_lo0)) return hi - lo;
+  const double wide = lu(lo, hi, run.c_lo0, run.c_hi0);
+  if (!(run.ub > run.c_lo0)) return wide;
+  return 0.2 * wide + 0.8 * lu(lo, hi, std::max(run.ub / 1.5, run.c_lo0), run.ub * (1 + 1e-9));
+}
+
+// Chooses the P tree nodes of the next round: greedily those the sequential loop is most likely to visit (a node's
+// probability is the prior mass of its bracket; a parent's bracket contains its children's, so the set is a subtree
+// containing the root).  With a flat prior this is the complete tree in heap order.  Every rank computes the same plan
+// from the same state.  The plan only decides what is probed speculatively -- the thresholds themselves and the walk
+// are the reference's sequence.
+static void plan_round(BisectRun& run) {
+  const int P = run.P;
+  run.h_ids.clear();
+  if (!run.adaptive) {
+    for (int t = 0; t < P; ++t) run.h_ids.push_back(t);
+  } else {
+    struct Cand { double mass; int depth; int heap; double lo, hi; };
+    auto worse = [](const Cand& a, const Cand& b) {
+      if (a.mass != b.mass) return a.mass < b.mass;
+      if (a.depth != b.depth) return a.depth > b.depth;
+      return a.heap > b.heap;
+    };
+    std::priority_queue<Cand, std::vector<Cand>, decltype(worse)> pq(worse);
+    pq.push({prior_mass(run, run.h_st.c_lo, run.h_st.c_hi), 0, 0, run.h_st.c_lo, run.h_st.c_hi});
+    while (!pq.empty() && (int)run.h_ids.size() < P) {
+      const Cand x = pq.top();
+      pq.pop();
+      if (!(x.lo * run.eps1 < x.hi)) continue;  // the loop stops here: nothing to probe
+      run.h_ids.push_back(x.heap);
+      if (x.depth + 1 > BS_MAX_DEPTH) continue;
+      const double c = (x.lo + x.hi) / 2;
+      pq.push({prior_mass(run, x.lo, c), x.depth + 1, 2 * x.heap + 1, x.lo, c});  // feasible: c_hi = c
+      pq.push({prior_mass(run, c, x.hi), x.depth + 1, 2 * x.heap + 2, c, x.hi});  // infeasible: c_lo = c
+    }
+    while ((int)run.h_ids.size() < P) run.h_ids.push_back(-1);  // unused slots (never matched by the walk)
+  }
+  CPB_CUDA(cudaMemcpyAsync(run.ids.get(), run.h_ids.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, ctx().stream));
+  run.planned = true;
+}
 
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
@@ -542,10 +685,12 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
         CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
       }
   // the round's speculation tree = the first `nodes` nodes of the bisection tree in heap (BFS) order
-  run->P = std::min(std::max(nodes, 1), (1 << BS_MAX_DEPTH) - 1);
+  run->P = std::min(std::max(nodes, 1), BS_MAX_NODES);
+  run->adaptive = env_int("CPB_BISECT_PLAN", 1) != 0;
   run->eps1 = 1 + eps;
   const int P = run->P;
   run->st.alloc(1);
+  run->ids.alloc(P);
   run->hint_lo.alloc(K + 2);
   run->hint_hi.alloc(K + 2);
   run->best.alloc(K + 2);
@@ -564,8 +709,8 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   h.done = !(h.c_lo * run->eps1 < h.c_hi);
   run->done = h.done != 0;
   run->c_lo0 = h.c_lo; run->c_hi0 = h.c_hi; run->eps = eps;
-  CPB_CUDA(cudaMemcpyAsync(run->st.get(), &h, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
-  CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // h is a stack variable
+  run->h_st = h;
+  CPB_CUDA(cudaMemcpyAsync(run->st.get(), &run->h_st, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
   CPB_LAUNCH(k_bisect_init, 1, 256, 0, (int)K, (int)(A.n + 1), run->hint_lo.get(), run->hint_hi.get(), run->best.get());
   if (run->stream) {
     DevStream& ds = run->ds;
@@ -577,6 +722,18 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     ds.n = (u32)A.n;
     ds.same_w = ds.Wt == ds.P;
     for (int t = 0; t < 4; ++t) { ds.cf[t] = f.dev.cf[t]; ds.ci[t] = f.dev.ci[t]; }
+    if (run->adaptive && !run->done && K >= 2 && A.n >= 1) {
+      ProfScope pk("probe_plan_bound");
+      DBuf<int> ub_spl(K + 1);
+      DBuf<u32> ub_cnt(K);
+      DBuf<double> ub_out(1);
+      CPB_LAUNCH(k_ub_splits, (unsigned)((K + 1 + 255) / 256), 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get());
+      const unsigned slices = (unsigned)std::min<i64>(64, std::max<i64>(1, ((i64)ctx().sm_count * 8 + K - 1) / K));
+      CPB_LAUNCH(k_ub_count, dim3(slices, (unsigned)K, 1), 256, 0, ds, ub_spl.get(), ub_cnt.get());
+      CPB_LAUNCH(k_ub_max, 1, 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get(), ub_out.get());
+      CPB_CUDA(cudaMemcpyAsync(&run->ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
   }
   return run.release();
 }
@@ -588,34 +745,42 @@ void bisect_probe(BisectRun& run, int node_lo, int node_hi) {
   if (node_hi <= node_lo) return;
   Oracle& f = *run.f;
   const int K = (int)run.K;
+  if (!run.planned) plan_round(run);
+  for (int t = node_lo; t < node_hi; ++t) run.speculated += run.h_ids[t] >= 0;
   for (int base = node_lo; base < node_hi; base += (1 << BS_LOCAL_DEPTH)) {
     const int cnt = std::min(node_hi - base, 1 << BS_LOCAL_DEPTH);
     if (run.stream) {
       // algorithmic bytes of one fused pass over the links for the thresholds of this launch
       ProfScope pk("k_probe_stream", (double)(f.ls->Ne + f.A->n + 1) * 4.0 + (double)cnt * (K + 1) * 8.0);
       if (f.dev.is_float)
-        CPB_LAUNCH(k_probe_stream<double>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, base);
+        CPB_LAUNCH(k_probe_stream<double>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
       else
-        CPB_LAUNCH(k_probe_stream<i64>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, base);
+        CPB_LAUNCH(k_probe_stream<i64>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
     } else if (f.dev.is_float) {
-      CPB_LAUNCH(k_bisect_round<double>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, base);
+      CPB_LAUNCH(k_bisect_round<double>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
     } else {
-      CPB_LAUNCH(k_bisect_round<i64>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, base);
+      CPB_LAUNCH(k_bisect_round<i64>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
     }
   }
 }
 
 // walks the (complete) tree of the round; `sync` reads back whether the bisection has finished
 bool bisect_advance(BisectRun& run, bool sync) {
+  if (!run.planned) plan_round(run);  // (advance without a probe: the walk stops at the root)
   CPB_LAUNCH(k_bisect_advance, 1, 256, 0, (int)run.K, run.P, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.best.get(),
-             run.node_spl, run.node_res, run.node_c);
+             run.node_spl, run.node_res, run.node_c, run.ids.get());
   if (sync) {
-    BisectState h{};
-    CPB_CUDA(cudaMemcpyAsync(&h, run.st.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaMemcpyAsync(&run.h_st, run.st.get(), sizeof(BisectState), cudaMemcpyDeviceToHost, ctx().stream));
     CPB_CUDA(cudaStreamSynchronize(ctx().stream));
-    run.done = h.done != 0;
+    run.done = run.h_st.done != 0;
+    run.planned = false;  // the next round is planned from the new bracket
   }
   return run.done;
+}
+
+static double g_bisect_stats[6] = {0, 0, 0, 0, 0, 0};
+void bisect_stats(double out[6]) {
+  for (int t = 0; t < 6; ++t) out[t] = g_bisect_stats[t];
 }
 
 void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
@@ -623,6 +788,8 @@ void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
   if (!h_spl_out) return;
   CPB_REQUIRE(run->done, "bisection has not finished");
   const i64 K = run->K;
+  g_bisect_stats[0] = run->h_st.rounds; g_bisect_stats[1] = run->h_st.probes; g_bisect_stats[2] = (double)run->speculated;
+  g_bisect_stats[3] = run->c_lo0; g_bisect_stats[4] = run->c_hi0; g_bisect_stats[5] = run->ub;
   std::vector<int> hb(K + 2);
   CPB_CUDA(cudaMemcpyAsync(hb.data(), run->best.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -667,7 +834,7 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     // The gap c_hi - c_lo halves with every probe and the loop stops once it is <= eps * c_lo, so the number
     // of rounds is bounded from the initial bounds: queue them all without host round trips (rounds past
     // the end find the state `done` and exit immediately), then read the state back once.
-    if (!run->done && run->c_lo0 > 0 && run->eps > 0 && run->c_hi0 > run->c_lo0 && env_int("CPB_BISECT_QUEUE", 0)) {
+    if (!run->done && run->c_lo0 > 0 && run->eps > 0 && run->c_hi0 > run->c_lo0 && !run->adaptive && env_int("CPB_BISECT_QUEUE", 0)) {
       const double iters = std::ceil(std::log2((run->c_hi0 - run->c_lo0) / (run->eps * run->c_lo0))) + 2;
       const int rounds = (int)std::min(64.0, std::ceil(std::max(iters, 1.0) / depth) + 1);
       for (int r = 0; r < rounds; ++r) {

@@ -346,6 +346,7 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
   switch (method) {
     case CPB_SPLIT_DYNAMIC_BOTTLENECK: case CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER: solve_dynamic(*f->O, false, con, K, spl_out); break;
     case CPB_SPLIT_DYNAMIC_TOTAL: case CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER: solve_dynamic(*f->O, true, con, K, spl_out); break;
+    case CPB_SPLIT_CONVEX_TOTAL: solve_convex_splitter(*f->O, con, K, spl_out); break;
     case CPB_SPLIT_BISECT_COST: solve_bisect(*f->O, false, eps, K, spl_out); break;
     case CPB_SPLIT_LAZY_BISECT_COST: solve_bisect(*f->O, true, eps, K, spl_out); break;
     case CPB_SPLIT_EQUI: {  // EquiPartitioner.jl:3-9
@@ -410,6 +411,13 @@ int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out) {
   ensure_context();
   CPB_REQUIRE(b, "NULL argument");
   bisect_finish(reinterpret_cast<BisectRun*>(b), spl_out);
+  CPB_API_END
+}
+
+int cpb_bisect_stats(double out[6]) {
+  CPB_API_BEGIN
+  CPB_REQUIRE(out, "NULL argument");
+  bisect_stats(out);
   CPB_API_END
 }
 

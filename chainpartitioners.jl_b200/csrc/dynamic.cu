@@ -73,9 +73,21 @@ __global__ void __launch_bounds__(256) k_dp_bottleneck(const __grid_constant__ D
   }
 }
 
+// Tie rules of the total-cost layers.  TIE_RIGHT: DynamicTotalSplitter -- the largest j in [1, j'] among the minimisers
+// (`<=` while scanning upwards, DynamicSplitter.jl:40).  TIE_CONVEX: ConvexTotalSplitter (ConvexTotalChunker.jl:26-55) --
+// the row starts from the empty last part (ptr = j', :47-50) and chunk_convex! then overrides it on `<=` with its
+// candidate, which for costs obeying the quadrangle inequality (:121) is the SMALLEST minimiser in [1, j' - 1]
+// (re-verified against the stack algorithm in tests/test_oracle_solvers.py).
+enum { TIE_RIGHT = 0, TIE_CONVEX = 1 };
+template <int TIE, class T> __device__ __forceinline__ bool tie_better(T ob, u32 oa, T best, u32 arg) {
+  if (oa == 0) return false;
+  if (arg == 0 || ob < best) return true;
+  return ob == best && (TIE == TIE_RIGHT ? oa > arg : oa < arg);
+}
+
 // total layer, one warp per j': scan of all j in [1, j'] with a rightmost-argmin reduction.
 // (O(n^2) oracle queries per layer; the monotone divide & conquer version replaces it for large n.)
-template <class T>
+template <int TIE, class T>
 __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
                                                   u32* __restrict__ ptr, u32 jp_first) {
   const u32 n1 = o.n + 1;
@@ -85,16 +97,25 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
     const u32 jp = (u32)t;
     T best = 0;
     u32 arg = 0;
-    for (u32 j = 1 + lane; j <= jp; j += 32) {
+    const u32 j_last = TIE == TIE_RIGHT ? jp : jp - 1;
+    for (u32 j = 1 + lane; j <= j_last; j += 32) {
       const T c = prev[j] + dev_cost<T>(o, j, jp);
-      if (arg == 0 || c <= best) { best = c; arg = j; }  // ascending j within a lane: `<=` keeps the largest
+      // ascending j within a lane: `<=` keeps the largest minimiser, `<` the smallest
+      if (arg == 0 || (TIE == TIE_RIGHT ? c <= best : c < best)) { best = c; arg = j; }
     }
     for (int off = 16; off > 0; off >>= 1) {
       const T ob = __shfl_down_sync(0xffffffffu, best, off);
       const u32 oa = __shfl_down_sync(0xffffffffu, arg, off);
-      if (oa != 0 && (arg == 0 || ob < best || (ob == best && oa > arg))) { best = ob; arg = oa; }
+      if (tie_better<TIE>(ob, oa, best, arg)) { best = ob; arg = oa; }
     }
-    if (lane == 0) { cur[jp] = best; ptr[jp] = arg; }
+    if (lane == 0) {
+      if (TIE == TIE_CONVEX) {  // the empty last part stays only if it is strictly cheaper
+        const T init = prev[jp] + dev_cost<T>(o, jp, jp);
+        if (arg == 0 || init < best) { best = init; arg = jp; }
+      }
+      cur[jp] = best;
+      ptr[jp] = arg;
+    }
   }
 }
 
@@ -103,7 +124,7 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
 // midpoint of a segment are bounded by the argmins of its already solved neighbours.  One launch per
 // level of the implicit balanced tree over t = j' - 1 in [0, n]; one CTA per node scans its candidate
 // range with a rightmost-argmin reduction.  Total work per layer O(n log n) oracle queries.
-template <class T>
+template <int TIE, class T>
 __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
                                                      u32* __restrict__ ptr, u32 step, u32 first_t, u32 t_stride) {
   __shared__ T s_best[8];
@@ -120,14 +141,15 @@ __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ Dev
   }
   T best = 0;
   u32 arg = 0;
-  for (u32 j = lo + threadIdx.x; j <= hi; j += blockDim.x) {
+  const u32 j_last = TIE == TIE_RIGHT ? hi : min(hi, jp - 1);
+  for (u32 j = lo + threadIdx.x; j <= j_last; j += blockDim.x) {
     const T c = prev[j] + dev_cost<T>(o, j, jp);
-    if (arg == 0 || c <= best) { best = c; arg = j; }
+    if (arg == 0 || (TIE == TIE_RIGHT ? c <= best : c < best)) { best = c; arg = j; }
   }
   for (int off = 16; off > 0; off >>= 1) {
     const T ob = __shfl_down_sync(0xffffffffu, best, off);
     const u32 oa = __shfl_down_sync(0xffffffffu, arg, off);
-    if (oa != 0 && (arg == 0 || ob < best || (ob == best && oa > arg))) { best = ob; arg = oa; }
+    if (tie_better<TIE>(ob, oa, best, arg)) { best = ob; arg = oa; }
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) { s_best[w] = best; s_arg[w] = arg; }
@@ -136,7 +158,11 @@ __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ Dev
     for (int k = 1; k < 8; ++k) {
       const T ob = s_best[k];
       const u32 oa = s_arg[k];
-      if (oa != 0 && (arg == 0 || ob < best || (ob == best && oa > arg))) { best = ob; arg = oa; }
+      if (tie_better<TIE>(ob, oa, best, arg)) { best = ob; arg = oa; }
+    }
+    if (TIE == TIE_CONVEX && hi == jp) {  // the empty last part (candidate j') stays only if it is strictly cheaper
+      const T init = prev[jp] + dev_cost<T>(o, jp, jp);
+      if (arg == 0 || init < best) { best = init; arg = jp; }
     }
     cur[jp] = best;
     ptr[jp] = arg;
@@ -178,7 +204,7 @@ __global__ void k_dp_unravel(const u32* __restrict__ ptr, u32 n2, int K, u32 n1,
   }
 }
 
-template <class T> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* h_spl_out) {
+template <class T, int TIE> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* h_spl_out) {
   const Matrix& A = *f.A;
   const u32 n1 = (u32)A.n + 1, n2 = n1 + 1;
   CPB_REQUIRE((double)K * n2 * 4.0 < 64e9, "DP pointer table would not fit");
@@ -202,21 +228,21 @@ template <class T> static void dynamic_T(Oracle& f, bool total, i64 K, int64_t* 
     } else if (monge && A.n > 64) {
       const u32 n = (u32)A.n;
       // j' = n + 1 (t = n): full scan; the only point the last layer needs (DynamicSplitter.jl:34)
-      CPB_LAUNCH(k_dp_total_dc<T>, 1, 256, 0, f.dev, prev, cur, p, 0u, n, 1u);
+      CPB_LAUNCH((k_dp_total_dc<TIE, T>), 1, 256, 0, f.dev, prev, cur, p, 0u, n, 1u);
       if (k < K) {
-        CPB_LAUNCH(k_dp_total_dc<T>, 1, 256, 0, f.dev, prev, cur, p, 0u, 0u, 1u);  // j' = 1 (t = 0)
+        CPB_LAUNCH((k_dp_total_dc<TIE, T>), 1, 256, 0, f.dev, prev, cur, p, 0u, 0u, 1u);  // j' = 1 (t = 0)
         u32 D = 1;
         while (((u64)1 << D) <= n) ++D;  // 2^D > n
         for (u32 step = (u32)1 << (D - 1); step >= 1; step >>= 1) {
           // nodes t = step * (2 i + 1) <= n, t != n (already solved)
           const u64 nodes = ((u64)n / step + 1) / 2;
-          if (nodes > 0) CPB_LAUNCH(k_dp_total_dc<T>, (unsigned)nodes, 256, 0, f.dev, prev, cur, p, step, step, 2 * step);
+          if (nodes > 0) CPB_LAUNCH((k_dp_total_dc<TIE, T>), (unsigned)nodes, 256, 0, f.dev, prev, cur, p, step, step, 2 * step);
         }
       }
     } else {
       const size_t rows = (size_t)n1 - jp_first + 1;
       const unsigned g = (unsigned)std::min<size_t>((rows * 32 + 255) / 256, (size_t)ctx().sm_count * 8);
-      CPB_LAUNCH(k_dp_total<T>, g, 256, 0, f.dev, prev, cur, p, jp_first);
+      CPB_LAUNCH((k_dp_total<TIE, T>), g, 256, 0, f.dev, prev, cur, p, jp_first);
     }
     std::swap(prev, cur);
   }
@@ -281,7 +307,26 @@ void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int6
       throw Error(CPB_ERR_UNSUPPORTED, "bottleneck DP on the device needs a monotone cost model");
   }
   oracle_ensure_ranks(f);
-  if (f.dev.is_float) dynamic_T<double>(f, total, K, h_spl_out); else dynamic_T<i64>(f, total, K, h_spl_out);
+  if (f.dev.is_float) dynamic_T<double, TIE_RIGHT>(f, total, K, h_spl_out); else dynamic_T<i64, TIE_RIGHT>(f, total, K, h_spl_out);
+}
+
+// partition_stripe(A, K, ConvexTotalSplitter(f)) (ConvexTotalChunker.jl:26-55): the total-cost layers with the
+// stack algorithm's tie rule.  Only for cost models that obey the quadrangle inequality the algorithm assumes
+// (:121) -- work, connectivity and monotonized-symmetric models with non-negative coefficients; for anything else
+// the reference's result is an artefact of its candidate stack and is not reproduced here.
+void solve_convex_splitter(Oracle& f, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  if (con && con->enabled) throw Error(CPB_ERR_UNSUPPORTED, "constrained ConvexTotalSplitter (ConvexTotalChunker.jl:167-209) is not built on the device");
+  bool convex = f.mdl.kind == CPB_MODEL_WORK || f.mdl.kind == CPB_MODEL_CONNECTIVITY || f.mdl.kind == CPB_MODEL_MONOSYM;
+  for (int t = 1; t <= 3; ++t) convex = convex && f.mdl.coef[t] >= 0;
+  if (!convex) throw Error(CPB_ERR_UNSUPPORTED, "ConvexTotalSplitter on the device needs a cost model obeying the quadrangle inequality (work / connectivity / monotonized-symmetric, beta >= 0)");
+  if (K == 1) {  // :33-35
+    h_spl_out[0] = 1;
+    h_spl_out[1] = f.A->n + 1;
+    return;
+  }
+  oracle_ensure_ranks(f);
+  if (f.dev.is_float) dynamic_T<double, TIE_CONVEX>(f, true, K, h_spl_out); else dynamic_T<i64, TIE_CONVEX>(f, true, K, h_spl_out);
 }
 
 }  // namespace cpb

@@ -20,11 +20,12 @@ struct TransposeOrder {
 
 static void transpose_order(const u32* row, size_t N, u64 max_row, TransposeOrder& t) {
   t.k0.alloc(N); t.v0.alloc(N); t.k1.alloc(N); t.v1.alloc(N);
-  if (N) CPB_CUDA(cudaMemcpyAsync(t.k0.get(), row, N * sizeof(u32), cudaMemcpyDeviceToDevice, ctx().stream));
-  const int which = radix_sort_pairs_iota(t.k0.get(), t.v0.get(), t.k1.get(), t.v1.get(), N, bits_for(max_row));
+  const int which = radix_sort_pairs_iota(row, t.k0.get(), t.v0.get(), t.k1.get(), t.v1.get(), N, bits_for(max_row));
   t.keys = which ? t.k1.get() : t.k0.get();
   t.q = which ? t.v1.get() : t.v0.get();
 }
+
+static unsigned grid_for(size_t n) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 32)); }
 
 // (row, q) pairs of the nonzeros whose row lies in [lo, hi)
 __global__ void k_row_flags(const u32* __restrict__ row, size_t N, u32 lo, u32 hi, u32* __restrict__ flags) {
@@ -120,9 +121,55 @@ __global__ void k_aug_diag(const u32* __restrict__ pos2, const u32* __restrict__
     if (add[j]) row2[pos2[j + 1] - 1] = (u32)j;  // virtual (j, j) entry appended to its column (:87-91)
 }
 
-static unsigned grid_for(size_t n) { return (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 32)); }
+// ---- link construction by an unordered transpose (rows of bounded degree) --------------------------------------
+// When no row holds more than LT_MAX_DEG nonzeros the stable sort is unnecessary: the nonzeros are dropped into their
+// row's segment in arbitrary order (one atomic cursor per row) and every row, owned by one thread, finds each entry's
+// predecessor -- the largest column below it -- by scanning its own short segment.  The result does not depend on the
+// order inside the segments.  Heavier rows (power-law matrices) take the radix-sort path below.
+static constexpr u32 LT_MAX_DEG = 64;
+__global__ void k_lt_count(const u32* __restrict__ row, size_t N, u32* __restrict__ cnt) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) atomicAdd(&cnt[row[q]], 1u);
+}
+__global__ void k_lt_max(const u32* __restrict__ cnt, size_t m, u32* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 v = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) v = max(v, cnt[i]);
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+__global__ void k_lt_fill(const u32* __restrict__ row, const u32* __restrict__ colidx, size_t N, u32* __restrict__ cursor,
+                          unsigned long long* __restrict__ T) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+    const u32 p = atomicAdd(&cursor[row[q]], 1u);
+    T[p] = ((unsigned long long)colidx[q] << 32) | (unsigned long long)q;
+  }
+}
+// after k_lt_fill, cursor[r] = end of row r's segment = start of row r + 1
+__global__ void k_lt_link(const u32* __restrict__ cursor, u32 m, const unsigned long long* __restrict__ T, u32* __restrict__ prev,
+                          u32* __restrict__ first_count) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 firsts = 0;
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+    const u32 s = r ? cursor[r - 1] : 0u, e = cursor[r];
+    firsts += e > s;
+    for (u32 i = s; i < e; ++i) {
+      const unsigned long long ti = T[i];
+      const u32 ci = (u32)(ti >> 32);
+      u32 best = 0;  // 1-based previous column holding this row, 0 = none
+      for (u32 k = s; k < e; ++k) {
+        const u32 ck = (u32)(T[k] >> 32);
+        if (ck < ci) best = max(best, ck + 1u);
+      }
+      prev[(u32)ti] = best;
+    }
+  }
+  firsts = __reduce_add_sync(0xffffffffu, firsts);
+  if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
+}
 
-static u32 read_u32(const u32* d) {  // (declared above)
+static u32 read_u32(const u32* d) {
   u32 h = 0;
   CPB_CUDA(cudaMemcpyAsync(&h, d, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -130,17 +177,41 @@ static u32 read_u32(const u32* d) {  // (declared above)
 }
 
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
-static u32 read_u32(const u32* d);
-
 // row_lo/row_hi (0-based, half-open) restrict the construction to the nonzeros of a row block: prev[] is
 // written for those nonzeros only and is zero elsewhere (multi-GPU: ranks combine with an element-wise MAX).
 void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
                         i64 row_lo, i64 row_hi) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
-  expand_columns(pos, ncol, colidx, N);
+  {
+    ProfScope pk("k_expand_columns", (double)N * 4.0 + (double)ncol * 4.0);
+    expand_columns(pos, ncol, colidx, N);
+  }
   DBuf<u32> dummy;
   if (!first_count) { dummy.alloc(1); first_count = dummy.get(); }
   CPB_CUDA(cudaMemsetAsync(first_count, 0, sizeof(u32), ctx().stream));
+  const bool no_lt = std::getenv("CPB_NO_ROW_SEGMENTS") != nullptr;  // (tests: force the radix-sort path)
+  if (row_lo <= 0 && row_hi >= (i64)nrow && N && nrow && !no_lt) {
+    DBuf<u32> cur((size_t)nrow + 1);  // per-row counts -> segment starts -> (after the fill) segment ends; [nrow] = max degree
+    CPB_CUDA(cudaMemsetAsync(cur.get(), 0, ((size_t)nrow + 1) * sizeof(u32), ctx().stream));
+    {
+      ProfScope pk("k_lt_count", (double)N * 4.0);
+      CPB_LAUNCH(k_lt_count, grid_for(N), 256, 0, row, N, cur.get());
+    }
+    CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
+    if (read_u32(cur.get() + nrow) <= LT_MAX_DEG) {
+      exclusive_scan_u32(cur.get(), cur.get(), (size_t)nrow);
+      DBuf<unsigned long long> T(N);
+      {
+        ProfScope pk("k_lt_fill", (double)N * 16.0);
+        CPB_LAUNCH(k_lt_fill, grid_for(N), 256, 0, row, colidx, N, cur.get(), T.get());
+      }
+      {
+        ProfScope pk("k_lt_link", (double)N * 12.0);
+        CPB_LAUNCH(k_lt_link, grid_for(nrow), 256, 0, cur.get(), nrow, T.get(), prev, first_count);
+      }
+      return;
+    }
+  }
   if (row_lo <= 0 && row_hi >= (i64)nrow) {
     TransposeOrder t;
     transpose_order(row, N, nrow ? nrow - 1 : 0, t);

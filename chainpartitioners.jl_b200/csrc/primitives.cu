@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_rs_scatter(const u32* __restr
 }
 
 template <int DB>
-static int radix_sort_passes(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int passes, bool iota_payload) {
+static int radix_sort_passes(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int passes, bool iota_payload, const u32* first_keys) {
   constexpr int NB = 1 << DB;
   static bool attr_set = false;
   if (!attr_set) {
@@ -253,7 +253,8 @@ static int radix_sort_passes(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp,
   int which = 0;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * DB;
-    u32* ki = which ? keys_tmp : keys;
+    const u32* ki = which ? keys_tmp : keys;
+    if (pass == 0 && first_keys) ki = first_keys;  // read-only source of the first pass (saves a copy into `keys`)
     u32* vi = which ? vals_tmp : vals;
     u32* ko = which ? keys : keys_tmp;
     u32* vo = which ? vals : vals_tmp;
@@ -271,19 +272,19 @@ static int radix_sort_passes(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp,
 // Stable sort of (key, payload) by the low `bits` bits of key.  iota_payload: the payload is the element
 // index, generated on the fly in the first pass (vals need not be initialised).  10-bit digits are used when
 // they save a pass (17..20 and 25..30 key bits).
-static int radix_sort_impl(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits, bool iota_payload) {
+static int radix_sort_impl(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits, bool iota_payload, const u32* first_keys) {
   if (n == 0) return 0;
   const int p8 = (bits + 7) / 8, p10 = (bits + 9) / 10;
-  if (p10 < p8) return radix_sort_passes<10>(keys, vals, keys_tmp, vals_tmp, n, p10, iota_payload);
-  return radix_sort_passes<8>(keys, vals, keys_tmp, vals_tmp, n, p8, iota_payload);
+  if (p10 < p8) return radix_sort_passes<10>(keys, vals, keys_tmp, vals_tmp, n, p10, iota_payload, first_keys);
+  return radix_sort_passes<8>(keys, vals, keys_tmp, vals_tmp, n, p8, iota_payload, first_keys);
 }
 
 int radix_sort_pairs(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
-  return radix_sort_impl(keys, vals, keys_tmp, vals_tmp, n, bits, false);
+  return radix_sort_impl(keys, vals, keys_tmp, vals_tmp, n, bits, false, nullptr);
 }
 
-int radix_sort_pairs_iota(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
-  return radix_sort_impl(keys, vals, keys_tmp, vals_tmp, n, bits, true);
+int radix_sort_pairs_iota(const u32* keys_src, u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits) {
+  return radix_sort_impl(keys, vals, keys_tmp, vals_tmp, n, bits, true, keys_src);
 }
 
 // ------------------------------------------------------------------------------ small kernels
@@ -325,26 +326,28 @@ void iota_u32(u32* dst, size_t n) {
   CPB_LAUNCH(k_iota, grid, 256, 0, dst, n);
 }
 
-// colidx[q] = largest j with pos[j] <= q.  A CTA owns 2048 consecutive nonzeros: two global binary searches
-// bound its column range, the offsets of that range are staged in shared memory and every nonzero
-// searches there (<= 11 shared-memory steps instead of ~20 dependent L2 reads).
+// colidx[q] = largest j with pos[j] <= q.  A CTA owns 2048 consecutive nonzeros.  k_expand_bounds finds the column of
+// every tile's first nonzero (one global binary search per tile, all tiles in parallel); k_expand_columns stages the
+// offsets of the tile's column range in shared memory and every nonzero searches there (<= 11 shared-memory steps
+// instead of ~20 dependent L2 reads).
 static constexpr int EX_TILE = 2048;
-__global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ pos, u32 ncol, u32* __restrict__ colidx, size_t N) {
+__global__ void k_expand_bounds(const u32* __restrict__ pos, u32 ncol, size_t N, u32 tiles, u32* __restrict__ bounds) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > tiles) return;
+  if (t == tiles) { bounds[t] = ncol - 1; return; }
+  const u32 q = (u32)((size_t)t * EX_TILE);
+  u32 lo = 0, hi = ncol;  // largest j in [0, ncol) with pos[j] <= q   (pos[ncol] == N > q)
+  while (hi - lo > 1) {
+    const u32 mid = lo + ((hi - lo) >> 1);
+    if (__ldg(pos + mid) <= q) lo = mid; else hi = mid;
+  }
+  bounds[t] = lo;
+}
+__global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ pos, const u32* __restrict__ bounds, u32* __restrict__ colidx, size_t N) {
   __shared__ u32 s_pos[EX_TILE + 2];
-  __shared__ u32 s_lo, s_hi;
   const size_t q0 = (size_t)blockIdx.x * EX_TILE;
   const size_t q1 = min(N, q0 + (size_t)EX_TILE);
-  if (threadIdx.x < 2) {
-    const u32 q = (u32)(threadIdx.x == 0 ? q0 : q1 - 1);
-    u32 lo = 0, hi = ncol;  // largest j in [0, ncol) with pos[j] <= q   (pos[ncol] == N > q)
-    while (hi - lo > 1) {
-      const u32 mid = lo + ((hi - lo) >> 1);
-      if (__ldg(pos + mid) <= q) lo = mid; else hi = mid;
-    }
-    if (threadIdx.x == 0) s_lo = lo; else s_hi = lo;
-  }
-  __syncthreads();
-  const u32 c_lo = s_lo, c_hi = s_hi;
+  const u32 c_lo = bounds[blockIdx.x], c_hi = bounds[blockIdx.x + 1];  // columns of the first nonzero of this / the next tile
   const u32 ncols = c_hi - c_lo + 1;
   if (ncols <= (u32)EX_TILE) {
     for (u32 t = threadIdx.x; t <= ncols; t += blockDim.x) s_pos[t] = __ldg(pos + c_lo + t);  // pos[c_lo .. c_hi + 1]
@@ -370,7 +373,10 @@ __global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ 
 }
 void expand_columns(const u32* pos, u32 ncol, u32* colidx, size_t N) {
   if (N == 0) return;
-  CPB_LAUNCH(k_expand_columns, (unsigned)((N + EX_TILE - 1) / EX_TILE), 256, 0, pos, ncol, colidx, N);
+  const u32 tiles = (u32)((N + EX_TILE - 1) / EX_TILE);
+  DBuf<u32> bounds((size_t)tiles + 1);
+  CPB_LAUNCH(k_expand_bounds, (tiles + 1 + 255) / 256, 256, 0, pos, ncol, N, tiles, bounds.get());
+  CPB_LAUNCH(k_expand_columns, tiles, 256, 0, pos, bounds.get(), colidx, N);
 }
 
 __global__ void k_segment_starts(const u32* __restrict__ keys, size_t n, u32* __restrict__ P, u32 domain) {

@@ -8,11 +8,12 @@ namespace cpb {
 // out[i] = sum_{t<i} in[i]  (u32, n entries).  in == out allowed.
 void exclusive_scan_u32(const u32* in, u32* out, size_t n);
 
-// Stable sort of (key, payload) by the low `bits` bits of key, 8 bits per pass.  Buffers are
+// Stable sort of (key, payload) by the low `bits` bits of key, 8 or 10 bits per pass.  Buffers are
 // ping-ponged; returns 0 if the result is in (keys, vals), 1 if in (keys_tmp, vals_tmp).
 int radix_sort_pairs(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits);
-// same with payload = element index, generated on the fly (vals need not be initialised)
-int radix_sort_pairs_iota(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits);
+// same with payload = element index, generated on the fly (vals need not be initialised); the keys are read from the
+// read-only keys_src in the first pass (keys is scratch and need not be initialised either)
+int radix_sort_pairs_iota(const u32* keys_src, u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, size_t n, int bits);
 
 // dst[i] = (u32)(src[i] - 1); flags[0] |= 1 if any src[i] outside [lo, hi]
 void narrow_minus1(const i64* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flags);

@@ -20,7 +20,7 @@ import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_st
     ColumnBlockComponentCostModel, BlockComponentCostModel, block_component,
     ConstrainedCost, VertexCount, FeasibleCost, SplitPartition,
     DynamicBottleneckSplitter, DynamicTotalSplitter, BisectCostBottleneckSplitter, LazyBisectCostBottleneckSplitter,
-    DynamicBottleneckChunker, DynamicTotalChunker, ConvexTotalChunker, OverlapChunker, StrictChunker, EquiChunker, EquiSplitter
+    DynamicBottleneckChunker, DynamicTotalChunker, ConvexTotalChunker, ConvexTotalSplitter, OverlapChunker, StrictChunker, EquiChunker, EquiSplitter
 
 const lib = get(ENV, "CHAINB200_LIB", "libchainb200.so")
 
@@ -143,6 +143,7 @@ split_code(::DynamicBottleneckSplitter) = (0, 0.0)
 split_code(::DynamicTotalSplitter) = (1, 0.0)
 split_code(m::BisectCostBottleneckSplitter) = (2, Float64(m.ϵ))
 split_code(m::LazyBisectCostBottleneckSplitter) = (3, Float64(m.ϵ))
+split_code(::ConvexTotalSplitter) = (8, 0.0)
 split_code(::DynamicBottleneckChunker) = (10, 0.0)   # partition_stripe(A, K, ::AbstractDynamicChunker), DynamicSplitter.jl:52-87
 split_code(::DynamicTotalChunker) = (11, 0.0)
 

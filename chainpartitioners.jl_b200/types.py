@@ -513,6 +513,18 @@ class ConcaveTotalChunker:
 
 
 @dataclass
+class ConvexTotalSplitter:
+    """ConvexTotalChunker.jl:5-7 (partition_stripe, :26-55)."""
+    f: Any
+
+
+@dataclass
+class ConcaveTotalSplitter:
+    """ConcaveTotalChunker.jl:5-7 (partition_stripe, :26-55)."""
+    f: Any
+
+
+@dataclass
 class OverlapChunker:
     """OverlapChunker.jl:1-4."""
     rho: float
@@ -570,6 +582,7 @@ class DisjointPacker:
 # method codes shared by the C ABI (include/chainb200.h) and the CPU oracle (oracle/cpo.h)
 SPLIT_DYNAMIC_BOTTLENECK, SPLIT_DYNAMIC_TOTAL, SPLIT_BISECT_COST, SPLIT_LAZY_BISECT_COST = 0, 1, 2, 3
 SPLIT_LAZY_BISECT_GENERIC, SPLIT_EQUI, SPLIT_FLIP_BISECT_COST, SPLIT_LAZY_FLIP_BISECT_COST = 4, 5, 6, 7
+SPLIT_CONVEX_TOTAL, SPLIT_CONCAVE_TOTAL = 8, 9
 SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, SPLIT_DYNAMIC_TOTAL_CHUNKER = 10, 11
 PACK_DYNAMIC_TOTAL, PACK_CONVEX_TOTAL, PACK_CONCAVE_TOTAL, PACK_OVERLAP, PACK_STRICT, PACK_EQUI = 0, 1, 2, 3, 4, 5
 
@@ -590,6 +603,10 @@ def split_method_code(method) -> Tuple[int, Any, float]:
         return SPLIT_LAZY_FLIP_BISECT_COST, method.f, float(method.eps)
     if isinstance(method, EquiSplitter):
         return SPLIT_EQUI, None, 0.0
+    if isinstance(method, ConvexTotalSplitter):
+        return SPLIT_CONVEX_TOTAL, method.f, 0.0
+    if isinstance(method, ConcaveTotalSplitter):
+        return SPLIT_CONCAVE_TOTAL, method.f, 0.0
     # partition_stripe(A, K, ::AbstractDynamicChunker) (DynamicSplitter.jl:52-87): the K-part DP with the part
     # index as the inner loop
     if isinstance(method, DynamicBottleneckChunker):

@@ -132,6 +132,7 @@ enum {
   CPB_SPLIT_BISECT_COST = 2,        /* BisectCostBottleneckSplitter(f, eps)      BisectCostBottleneckSplitter.jl:6-63 */
   CPB_SPLIT_LAZY_BISECT_COST = 3,   /* LazyBisectCostBottleneckSplitter(f, eps)  LazyBisectCostBottleneckSplitter.jl:8-70,140-258,260-388 */
   CPB_SPLIT_EQUI = 5,               /* EquiSplitter()                            EquiPartitioner.jl:3-9 */
+  CPB_SPLIT_CONVEX_TOTAL = 8,       /* partition_stripe(A, K, ConvexTotalSplitter(f))  ConvexTotalChunker.jl:26-55 (quadrangle-inequality models) */
   /* partition_stripe(A, K, ::AbstractDynamicChunker) DynamicSplitter.jl:52-87,249-314: the same K-part recurrence
      and `<=` tie rule as the splitter form with the part index as the inner loop -> identical split vectors */
   CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* partition_stripe(A, K, DynamicBottleneckChunker(f)) */
@@ -149,8 +150,10 @@ int cpb_links_partial(cpb_oracle* f, int64_t row_lo, int64_t row_hi, uint32_t* d
 int cpb_oracle_set_links(cpb_oracle* f, const uint32_t* d_prev, int64_t ne);
 
 /* The same bisection (BisectCostBottleneckSplitter.jl:41-60 / LazyBisect...:237-255) as explicit steps, so that
- * the speculative thresholds of a round -- the first `nodes` nodes (<= 255) of the bisection tree in heap order --
- * can be probed by different GPUs (one process per GPU):
+ * the speculative thresholds of a round -- `nodes` (<= 255) nodes of the bisection tree, slot t holding the t-th
+ * node of the round's plan (the subtree the sequential loop is most likely to visit; every rank derives the same
+ * plan from the same state; CPB_BISECT_PLAN=0 selects the complete tree in heap order) -- can be probed by
+ * different GPUs (one process per GPU):
  *   begin   builds what the probes need, computes bound_stripe, sets up the round state.  d_node_res (int32
  *           per node: 0 = loop condition already false, 1 = infeasible, 2 = feasible), d_node_c (double per
  *           node), d_node_spl ((K+2) int32 per node, 1-based split points in [1..K+1]) are DEVICE buffers for
@@ -168,6 +171,10 @@ int cpb_bisect_probe(cpb_bisect* b, int node_lo, int node_hi);
 int cpb_probe_cluster_capacity(int streaming, int* out);
 int cpb_bisect_advance(cpb_bisect* b, int* done_out);
 int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out);
+/* Diagnostics of the most recently finished bisection of this process: out[0] = rounds (batches of concurrent
+ * probes), out[1] = probes the sequential loop of the reference would have run, out[2] = thresholds probed
+ * speculatively in total, out[3] = initial c_lo, out[4] = initial c_hi, out[5] = the planner's upper bound (0 = none). */
+int cpb_bisect_stats(double out[6]);
 
 /* ---- pack_stripe ------------------------------------------------------------------------- */
 enum {

@@ -608,6 +608,24 @@ template <class T, class FP> static void chunk_concave(std::vector<T>& cst, ivec
   }
 }
 
+// ConvexTotalChunker.jl:26-55 (ConvexTotalSplitter) and ConcaveTotalChunker.jl:26-55 (ConcaveTotalSplitter): K layers, each
+// initialised with the empty last part (ptr = j') and then relaxed by the stack / queue routine on the previous layer
+template <class F, class T> static void quadrangle_total_splitter(F& f, i64 n, i64 K, bool concave, i64* spl) {
+  if (K == 1) { spl[1] = 1; spl[2] = n + 1; return; }
+  std::vector<std::vector<T>> cst(K + 1, std::vector<T>(n + 2, tmax<T>()));
+  std::vector<ivec> ptr(K + 1, ivec(n + 2, 0));
+  for (i64 jp = 1; jp <= n + 1; ++jp) { cst[1][jp] = f(1, jp, 1); ptr[1][jp] = 1; }
+  std::vector<std::pair<i64, i64>> stack;
+  std::deque<std::pair<i64, i64>> queue;
+  for (i64 k = 2; k <= K; ++k) {
+    auto fp = [&](i64 j, i64 jp) -> T { return cst[k - 1][j] + f(j, jp, k); };
+    for (i64 jp = 1; jp <= n + 1; ++jp) { cst[k][jp] = fp(jp, jp); ptr[k][jp] = jp; }
+    if (concave) chunk_concave<T>(cst[k], ptr[k], fp, 1, n + 1, queue);
+    else chunk_convex<T>(cst[k], ptr[k], fp, 1, n + 1, stack);
+  }
+  unravel_splits(K, n, [&](i64 k, i64 jp) { return ptr[k][jp]; }, spl);
+}
+
 // ConvexTotalChunker.jl:211-265
 template <class T, class FP> static void chunk_convex_constrained(std::vector<T>& cst, ivec& ptr, FP fp, Weight& w, i64 J0, i64 JP1,
                                                                   std::vector<std::pair<i64, i64>>& ftr) {

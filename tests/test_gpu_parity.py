@@ -49,6 +49,30 @@ def test_color_arrays(ref, fixtures):
             assert np.array_equal(cp.selfpincount(A).query(j, jp), ref.selfpincount(A, j, jp))
 
 
+def test_link_construction_paths(ref, monkeypatch):
+    """build_links has two forms -- per-row segments filled through atomic cursors (rows of <= 64 nonzeros) and the
+    stable radix sort (heavier rows): net / dia-net counts and the streaming bisection must not depend on which ran."""
+    rng = np.random.default_rng(102)
+    light = synth.erdos_renyi(20000, 10)
+    dense_row = sprand(rng, 300, 300, 0.1)
+    rows = [np.unique(np.concatenate([dense_row.rowval[dense_row.colptr[j] - 1:dense_row.colptr[j + 1] - 1], [7]])) for j in range(dense_row.n)]
+    heavy = cp.SparseMatrixCSC(300, 300, np.cumsum([1] + [len(r) for r in rows]), np.concatenate(rows))  # row 7 holds 300 nonzeros
+    for A in (light, heavy):
+        j, jp = rand_pairs(rng, A.n, 400)
+        want_net, want_dia = ref.netcount(A, j, jp), ref.dianetcount(A, j, jp)
+        mtd = cp.LazyBisectCostBottleneckSplitter(AFF, 0.01)
+        want_spl = ref.partition_stripe(A, 8, mtd).spl
+        for force_sort in (False, True):
+            if force_sort:
+                monkeypatch.setenv("CPB_NO_ROW_SEGMENTS", "1")
+            else:
+                monkeypatch.delenv("CPB_NO_ROW_SEGMENTS", raising=False)
+            assert np.array_equal(cp.netcount(A).query(j, jp), want_net)
+            assert np.array_equal(cp.dianetcount(A).query(j, jp), want_dia)
+            assert np.array_equal(cp.partition_stripe(A, 8, mtd).spl, want_spl)
+    monkeypatch.delenv("CPB_NO_ROW_SEGMENTS", raising=False)
+
+
 MODELS = [
     cp.AffineWorkModel(0, 10, 1),
     cp.AffineConnectivityModel(0, 10, 1, 100),
@@ -371,6 +395,25 @@ def test_dynamic_chunker_kform(ref, fixtures):
                     for spec in (f, cp.ConstrainedCost(f, cp.VertexCount(), 8), cp.ConstrainedCost(f, cp.VertexCount(), 2)):
                         g, r = cp.partition_stripe(A, K, mk(spec)), ref.partition_stripe(A, K, mk(spec))
                         assert np.array_equal(g.spl, r.spl), (A, f, K, mk.__name__, g.spl, r.spl)
+
+
+def test_convex_total_splitter(ref, fixtures):
+    """partition_stripe(A, K, ConvexTotalSplitter(f)) (ConvexTotalChunker.jl:26-55): warp-scan layers (n <= 64) and
+    monotone divide & conquer layers (larger n) against the reference's stack algorithm."""
+    rng = np.random.default_rng(302)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], fixtures["LPnetlib/lp_blend"], sprand(rng, 6, 10, 0.3), sprand(rng, 40, 200, 0.1),
+            synth.laplacian5(24), synth.erdos_renyi(1500, 6)]
+    for A in mats:
+        fs = [cp.AffineConnectivityModel(0, 3, 1, 3), AFF, cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0)]
+        if A.m == A.n:
+            fs.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
+        for f in fs:
+            for K in [1, 2, 3, 8]:
+                mtd = cp.ConvexTotalSplitter(f)
+                g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                assert np.array_equal(g.spl, r.spl), (A, f, K, g.spl, r.spl)
+    with pytest.raises(cp.CpbError):  # not a quadrangle-inequality model: the reference's result is an artefact of its stack
+        cp.partition_stripe(mats[0], 3, cp.ConvexTotalSplitter(cp.AffineSymmetricEdgeCutModel(1, 1, 1, 1)))
 
 
 def test_degenerate_inputs(ref):

@@ -181,6 +181,48 @@ def test_dynamic_chunker_kform(ref):
                     assert ref.partition_stripe(A, K, Ch(f)).spl.tolist() == ref.partition_stripe(A, K, S(f)).spl.tolist()
 
 
+def convex_splitter_rule(C, n, K):
+    """App. B: each layer keeps the empty last part (ptr = j') only if it is strictly cheaper than the SMALLEST
+    minimiser in [1, j' - 1]."""
+    prev = [None] + [C[1, jp] for jp in range(1, n + 2)]
+    ptrs = [None, [None] + [1] * (n + 1)]
+    for k in range(2, K + 1):
+        cur, pt = [None] * (n + 2), [None] * (n + 2)
+        for jp in range(1, n + 2):
+            best, arg = prev[jp] + C[jp, jp], jp
+            vals = [prev[j] + C[j, jp] for j in range(1, jp)]
+            if vals and min(vals) <= best:
+                best, arg = min(vals), 1 + vals.index(min(vals))
+            cur[jp], pt[jp] = best, arg
+        prev = cur
+        ptrs.append(pt)
+    spl = [0] * (K + 1)
+    spl[K] = n + 1
+    for k in range(K, 0, -1):
+        spl[k - 1] = ptrs[k][spl[k]]
+    return spl
+
+
+def test_quadrangle_total_splitters(ref, fixtures):
+    """ConvexTotalSplitter (ConvexTotalChunker.jl:26-55) on costs obeying the quadrangle inequality: optimal total
+    (test_Partitioners.jl:171-199) and the tie rule the device implements; ConcaveTotalSplitter on the additive work
+    model (the only affine model that is concave): optimal total."""
+    rng = np.random.default_rng(16)
+    mats = [fixtures["LPnetlib/lpi_itest6"]] + [sprand(rng, int(rng.integers(1, 10)), int(rng.integers(1, 14)), float(rng.choice([0.1, 0.3, 0.5]))) for _ in range(40)]
+    for t, A in enumerate(mats):
+        mdl = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(2, 0, 0, 1), cp.AffineConnectivityModel(0, 10, 1, 100)][t % 4]
+        C = cost_matrix(mdl, A)
+        for K in [1, 2, 3, 4, 8]:
+            Phi = ref.partition_stripe(A, K, cp.ConvexTotalSplitter(mdl))
+            check_split(Phi.spl, A.n, K)
+            assert objective(C, Phi.spl, True) == brute_optimum(C, A.n, K, True)
+            assert Phi.spl.tolist() == convex_splitter_rule(C, A.n, K)
+            if t % 4 == 0:
+                Phi = ref.partition_stripe(A, K, cp.ConcaveTotalSplitter(mdl))
+                check_split(Phi.spl, A.n, K)
+                assert objective(C, Phi.spl, True) == brute_optimum(C, A.n, K, True)
+
+
 def greedy_probe(C, n, K, c):
     """every part as long as feasible at threshold c; None if infeasible"""
     spl = [1]
