@@ -63,6 +63,10 @@ def run_config(name, A, gpu_call, cpu_call, cmp, reps, extra=None, skip_cpu=Fals
         line["cpu_phases_s"] = list(ref.last_seconds)
         line["identical"] = bool(cmp(out_e2e, out_cpu) and cmp(out_res, out_cpu))
         line["speedup_e2e"] = line["cpu_oracle_ms"] / line["gpu_e2e_ms"]
+    try:
+        line["bisection"] = cp.bisect_stats()
+    except Exception:
+        pass
     if extra:
         line.update(extra(out_e2e))
     dA.close()

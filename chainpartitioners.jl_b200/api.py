@@ -523,9 +523,10 @@ def profile_get() -> dict:
 
 def bisect_stats() -> dict:
     """Diagnostics of the most recent bisection (``cpb_bisect_stats``)."""
-    out = (ctypes.c_double * 6)()
+    out = (ctypes.c_double * 8)()
     _check(load_library().cpb_bisect_stats(out))
-    return {"rounds": int(out[0]), "probes": int(out[1]), "speculated": int(out[2]), "c_lo": out[3], "c_hi": out[4], "plan_upper_bound": out[5]}
+    return {"rounds": int(out[0]), "probes": int(out[1]), "speculated": int(out[2]), "c_lo": out[3], "c_hi": out[4], "plan_upper_bound": out[5],
+            "c_lo_final": out[6], "c_hi_final": out[7]}
 
 
 def probe_cluster_capacity(streaming: bool = True) -> int:

@@ -194,6 +194,7 @@ template <class T> __device__ __forceinline__ T stream_cost(const DevStream& s, 
 #ifdef CPB_PROBE_TIMING
 __device__ unsigned long long g_probe_t[8];
 __device__ unsigned long long g_probe_n;
+__device__ unsigned long long g_probe_parts[4];  // per slot 0..3: parts started
 #define PT(i) do { if (node == 0 && crank == 0 && tid == 0) { unsigned long long _t = clock64(); g_probe_t[i] += _t - t_last; t_last = _t; } } while (0)
 #else
 #define PT(i) do {} while (0)
@@ -244,6 +245,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     if (!cost_leq(stream_cost<T>(s, 0, 0, 0), c)) { broke = true; break; }  // even the empty part exceeds c
     const u32 e0 = pcur;
     const i64 wj = (i64)wcur;
+#ifdef CPB_PROBE_TIMING
+    if (node < 4 && crank == 0 && tid == 0) g_probe_parts[node] += 1;
+#endif
     u32 jlast = j;
     u32 grun = 0;
     bool first = true, missed = false;
@@ -254,6 +258,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
 #ifdef CPB_PROBE_TIMING
       unsigned long long t_last = clock64();
       if (node == 0 && crank == 0 && tid == 0) g_probe_n += 1;
+      if (node == 1 && crank == 0 && tid == 0) g_probe_parts[3] += 1;  // super-steps of slot 1
 #endif
       const u32 e_c = e_tile + crank * CE;
       // ---- column boundaries whose element offset falls into (e_c, e_c + CE] (loads issued ahead of the tile) ----
@@ -440,6 +445,12 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       nv = nv_est;
     }
     if (k == K) { feasible = (jlast == n1); break; }
+    if (jlast == n1) {  // every column is placed: the remaining parts are empty (their cost was tested at the loop top)
+      if (writer)
+        for (int t = k + 1; t <= K; ++t) spl[t] = (int)n1;
+      feasible = true;
+      break;
+    }
     if (writer) spl[k + 1] = (int)jlast;
     j = jlast;
   }
@@ -609,9 +620,12 @@ static double prior_mass(const BisectRun& run, double lo, double hi) {
     return (hi > lo && a > 0 && b > a) ? (std::log(hi) - std::log(lo)) / (std::log(b) - std::log(a)) : 0.0;
   };
   if (!(run.c_lo0 > 0) || !(run.c_hi0 > run.c_lo0)) return hi - lo;
-  const double wide = lu(lo, hi, run.c_lo0, run.c_hi0);
-  if (!(run.ub > run.c_lo0)) return wide;
-  return 0.2 * wide + 0.8 * lu(lo, hi, std::max(run.ub / 1.5, run.c_lo0), run.ub * (1 + 1e-9));
+  if (!(run.ub > run.c_lo0)) return lu(lo, hi, run.c_lo0, run.c_hi0);
+  // the bound is the bottleneck of an actual partition, so c* <= ub: no mass above it.  Most of the mass sits just
+  // below the bound (on near-uniform matrices the bounding partition is within a percent of the optimum).
+  const double top = std::min(run.ub * (1 + 1e-9), run.c_hi0);
+  return 0.1 * lu(lo, hi, run.c_lo0, top) + 0.3 * lu(lo, hi, std::max(run.ub / 1.5, run.c_lo0), top) +
+         0.6 * lu(lo, hi, std::max(run.ub / 1.03, run.c_lo0), top);
 }
 
 // Chooses the P tree nodes of the next round: greedily those the sequential loop is most likely to visit (a node's
@@ -778,9 +792,9 @@ bool bisect_advance(BisectRun& run, bool sync) {
   return run.done;
 }
 
-static double g_bisect_stats[6] = {0, 0, 0, 0, 0, 0};
-void bisect_stats(double out[6]) {
-  for (int t = 0; t < 6; ++t) out[t] = g_bisect_stats[t];
+static double g_bisect_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+void bisect_stats(double out[8]) {
+  for (int t = 0; t < 8; ++t) out[t] = g_bisect_stats[t];
 }
 
 void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
@@ -790,6 +804,7 @@ void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
   const i64 K = run->K;
   g_bisect_stats[0] = run->h_st.rounds; g_bisect_stats[1] = run->h_st.probes; g_bisect_stats[2] = (double)run->speculated;
   g_bisect_stats[3] = run->c_lo0; g_bisect_stats[4] = run->c_hi0; g_bisect_stats[5] = run->ub;
+  g_bisect_stats[6] = run->h_st.c_lo; g_bisect_stats[7] = run->h_st.c_hi;
   std::vector<int> hb(K + 2);
   CPB_CUDA(cudaMemcpyAsync(hb.data(), run->best.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -804,6 +819,9 @@ void probe_timing_dump() {
   const char* names[6] = {"loads+ballots", "syncthreads", "scan(warp0)", "push+cluster.sync#1", "boundaries", "push+cluster.sync#2"};
   for (int i = 0; i < 6; ++i) std::printf("probe_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / (double)std::max<unsigned long long>(n, 1));
   std::printf("probe_timing super-steps %llu\n", n);
+  unsigned long long parts[4];
+  cudaMemcpyFromSymbol(parts, g_probe_parts, sizeof(parts));
+  std::printf("probe_timing parts slot0 %llu slot1 %llu slot2 %llu ; super-steps slot1 %llu\n", parts[0], parts[1], parts[2], parts[3]);
 }
 #endif
 

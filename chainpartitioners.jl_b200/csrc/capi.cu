@@ -414,7 +414,7 @@ int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out) {
   CPB_API_END
 }
 
-int cpb_bisect_stats(double out[6]) {
+int cpb_bisect_stats(double out[8]) {
   CPB_API_BEGIN
   CPB_REQUIRE(out, "NULL argument");
   bisect_stats(out);

@@ -123,10 +123,10 @@ __global__ void k_aug_diag(const u32* __restrict__ pos2, const u32* __restrict__
 
 // ---- link construction by an unordered transpose (rows of bounded degree) --------------------------------------
 // When no row holds more than LT_MAX_DEG nonzeros the stable sort is unnecessary: the nonzeros are dropped into their
-// row's segment in arbitrary order (one atomic cursor per row) and every row, owned by one thread, finds each entry's
-// predecessor -- the largest column below it -- by scanning its own short segment.  The result does not depend on the
+// row's segment in arbitrary order (one atomic cursor per row) and every entry finds its predecessor -- the largest
+// column below its own -- by scanning its row's short segment.  The result does not depend on the
 // order inside the segments.  Heavier rows (power-law matrices) take the radix-sort path below.
-static constexpr u32 LT_MAX_DEG = 64;
+static constexpr u32 LT_MAX_DEG = 128;
 __global__ void k_lt_count(const u32* __restrict__ row, size_t N, u32* __restrict__ cnt) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) atomicAdd(&cnt[row[q]], 1u);
@@ -146,24 +146,40 @@ __global__ void k_lt_fill(const u32* __restrict__ row, const u32* __restrict__ c
     T[p] = ((unsigned long long)colidx[q] << 32) | (unsigned long long)q;
   }
 }
-// after k_lt_fill, cursor[r] = end of row r's segment = start of row r + 1
-__global__ void k_lt_link(const u32* __restrict__ cursor, u32 m, const unsigned long long* __restrict__ T, u32* __restrict__ prev,
-                          u32* __restrict__ first_count) {
+// after k_lt_fill, cursor[r] = end of row r's segment = start of row r + 1: mark the first slot of every non-empty row
+__global__ void k_lt_heads(const u32* __restrict__ cursor, u32 m, u32* __restrict__ heads) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  u32 firsts = 0;
   for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
     const u32 s = r ? cursor[r - 1] : 0u, e = cursor[r];
-    firsts += e > s;
-    for (u32 i = s; i < e; ++i) {
-      const unsigned long long ti = T[i];
-      const u32 ci = (u32)(ti >> 32);
-      u32 best = 0;  // 1-based previous column holding this row, 0 = none
-      for (u32 k = s; k < e; ++k) {
-        const u32 ck = (u32)(T[k] >> 32);
-        if (ck < ci) best = max(best, ck + 1u);
-      }
-      prev[(u32)ti] = best;
+    if (e > s) atomicOr(&heads[s >> 5], 1u << (s & 31));
+  }
+}
+// One thread per slot: the slot's row segment is delimited by the head bits around it; the predecessor of the slot's
+// entry is the largest column below its own inside the segment.  Neighbouring threads share a segment, so the scan
+// reads are warp-wide broadcasts.
+__global__ void k_lt_link(const unsigned long long* __restrict__ T, const u32* __restrict__ heads, size_t N, u32* __restrict__ prev,
+                          u32* __restrict__ first_count) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const u32 nwords = (u32)((N + 31) >> 5);
+  u32 firsts = 0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
+    u32 w = (u32)(p >> 5);
+    u32 bits = heads[w] & (0xffffffffu >> (31 - (u32)(p & 31)));  // heads at or before p (slot 0 is always one)
+    while (!bits) bits = heads[--w];
+    const u32 s = (w << 5) + (31 - __clz(bits));
+    w = (u32)(p >> 5);
+    bits = (p & 31) == 31 ? 0u : (heads[w] & (0xffffffffu << ((u32)(p & 31) + 1)));
+    while (!bits && ++w < nwords) bits = heads[w];
+    const u32 e = bits ? min((u32)N, (w << 5) + (u32)__ffs(bits) - 1u) : (u32)N;
+    const unsigned long long ti = T[p];
+    const u32 ci = (u32)(ti >> 32);
+    u32 best = 0;  // 1-based previous column holding this row, 0 = none
+    for (u32 k = s; k < e; ++k) {
+      const u32 ck = (u32)(T[k] >> 32);
+      if (ck < ci) best = max(best, ck + 1u);
     }
+    prev[(u32)ti] = best;
+    firsts += best == 0u;
   }
   firsts = __reduce_add_sync(0xffffffffu, firsts);
   if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
@@ -207,7 +223,10 @@ void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
       }
       {
         ProfScope pk("k_lt_link", (double)N * 12.0);
-        CPB_LAUNCH(k_lt_link, grid_for(nrow), 256, 0, cur.get(), nrow, T.get(), prev, first_count);
+        DBuf<u32> heads(N / 32 + 2);
+        heads.zero();
+        CPB_LAUNCH(k_lt_heads, grid_for(nrow), 256, 0, cur.get(), nrow, heads.get());
+        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), N, prev, first_count);
       }
       return;
     }

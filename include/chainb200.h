@@ -173,8 +173,9 @@ int cpb_bisect_advance(cpb_bisect* b, int* done_out);
 int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out);
 /* Diagnostics of the most recently finished bisection of this process: out[0] = rounds (batches of concurrent
  * probes), out[1] = probes the sequential loop of the reference would have run, out[2] = thresholds probed
- * speculatively in total, out[3] = initial c_lo, out[4] = initial c_hi, out[5] = the planner's upper bound (0 = none). */
-int cpb_bisect_stats(double out[6]);
+ * speculatively in total, out[3] = initial c_lo, out[4] = initial c_hi, out[5] = the planner's upper bound (0 = none), out[6] = final c_lo,
+ * out[7] = final c_hi. */
+int cpb_bisect_stats(double out[8]);
 
 /* ---- pack_stripe ------------------------------------------------------------------------- */
 enum {
