@@ -605,7 +605,7 @@ struct BisectRun {
   double c_lo0 = 0, c_hi0 = 0, eps = 0;
   // speculation plan of the current round: slot t probes tree node h_ids[t] (heap index)
   BisectState h_st{};
-  std::vector<int> h_ids;
+  std::vector<int> h_ids, h_best;  // h_best: host copy of `best`, refreshed with every synchronising advance
   bool planned = false, adaptive = true;
   i64 speculated = 0;  // thresholds probed so far (this rank)
   double ub = 0;  // upper bound on the optimal bottleneck (0 = unknown)
@@ -663,6 +663,30 @@ static void plan_round(BisectRun& run) {
   run.planned = true;
 }
 
+// DevStream view of the oracle's link stream
+static void stream_view(Oracle& f, DevStream& ds) {
+  const Matrix& A = *f.A;
+  ds.prev = f.ls->prev.get();
+  ds.colidx = f.ls->colidx.get();
+  ds.P = f.ls->P;
+  ds.Wt = (f.dev.kind == CPB_MODEL_MONOSYM) ? f.overpos.get() - 1 : A.pos.get() - 1;
+  ds.Ne = (u32)f.ls->Ne;
+  ds.n = (u32)A.n;
+  ds.same_w = ds.Wt == ds.P;
+  for (int t = 0; t < 4; ++t) { ds.cf[t] = f.dev.cf[t]; ds.ci[t] = f.dev.ci[t]; }
+}
+
+// planner's upper bound (see k_ub_splits) into d_out[0]; asynchronous
+static void launch_upper_bound(Oracle& f, const DevStream& ds, i64 K, double* d_out) {
+  ProfScope pk("probe_plan_bound");
+  DBuf<int> ub_spl(K + 1);
+  DBuf<u32> ub_cnt(K);
+  CPB_LAUNCH(k_ub_splits, (unsigned)((K + 1 + 255) / 256), 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get());
+  const unsigned slices = (unsigned)std::min<i64>(64, std::max<i64>(1, ((i64)ctx().sm_count * 8 + K - 1) / K));
+  CPB_LAUNCH(k_ub_count, dim3(slices, (unsigned)K, 1), 256, 0, ds, ub_spl.get(), ub_cnt.get());
+  CPB_LAUNCH(k_ub_max, 1, 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get(), d_out);
+}
+
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
@@ -671,13 +695,38 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   auto run = std::make_unique<BisectRun>();
   run->f = &f;
   run->K = K;
+  run->adaptive = env_int("CPB_BISECT_PLAN", 1) != 0;
   // Connectivity-type models stream the link array (no dominance index needed); the others walk the index.
   run->stream = (f.dev.kind == CPB_MODEL_CONNECTIVITY || f.dev.kind == CPB_MODEL_MONOSYM) && env_int("CPB_PROBE_STREAM", 1) != 0;
   if (run->stream) {
+    // Everything the host needs before the first round -- the row-degree check of the link construction, nets(1, n+1)
+    // or the over-pin total for bound_stripe, the planner's upper bound -- is produced without waiting and read back
+    // with ONE synchronisation.
     CPB_REQUIRE(f.ls_complete, "partial links were built but never completed (cpb_oracle_set_links)");
+    const bool dia = f.dev.kind == CPB_MODEL_MONOSYM;
     if (!f.ls) {
       ProfScope prof("oracle_stripe");
-      f.ls = build_link_stream(*f.A, f.dev.kind == CPB_MODEL_MONOSYM);
+      f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/true);
+    }
+    const bool want_ub = run->adaptive && K >= 2 && A.n >= 1;
+    DBuf<double> ub_out(1);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      stream_view(f, run->ds);
+      if (want_ub) launch_upper_bound(f, run->ds, K, ub_out.get());
+      u32 info[2] = {0, 0}, n_over = 0;
+      CPB_CUDA(cudaMemcpyAsync(info, f.ls->first_count.get(), sizeof(info), cudaMemcpyDeviceToHost, ctx().stream));
+      if (dia) CPB_CUDA(cudaMemcpyAsync(&n_over, f.overpos.get() + A.n, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+      if (want_ub) CPB_CUDA(cudaMemcpyAsync(&run->ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      if (f.ls->speculative && info[1] > LT_MAX_DEG) {  // a heavy row: the row-segment kernels did nothing -> stable sort
+        ProfScope prof("oracle_stripe");
+        f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, false, /*force_sort=*/true);
+        continue;
+      }
+      f.ls->speculative = false;
+      f.ls->h_first_count = info[0];
+      if (dia) f.h_n_over = n_over;
+      break;
     }
   } else {
     oracle_ensure_ranks(f);
@@ -698,9 +747,8 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((bytes / 128 + 255) / 256, (size_t)ctx().sm_count * 8));
         CPB_LAUNCH(k_l2_prefetch, grid, 256, 0, (const char*)rs->wm.blocks.get(), bytes);
       }
-  // the round's speculation tree = the first `nodes` nodes of the bisection tree in heap (BFS) order
+  // the round's speculation tree: `nodes` slots, filled by plan_round
   run->P = std::min(std::max(nodes, 1), BS_MAX_NODES);
-  run->adaptive = env_int("CPB_BISECT_PLAN", 1) != 0;
   run->eps1 = 1 + eps;
   const int P = run->P;
   run->st.alloc(1);
@@ -708,6 +756,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   run->hint_lo.alloc(K + 2);
   run->hint_hi.alloc(K + 2);
   run->best.alloc(K + 2);
+  run->h_best.assign(K + 2, 0);
   if (d_node_res && d_node_c && d_node_spl) {
     run->node_res = d_node_res; run->node_c = d_node_c; run->node_spl = d_node_spl;
   } else {
@@ -726,28 +775,9 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   run->h_st = h;
   CPB_CUDA(cudaMemcpyAsync(run->st.get(), &run->h_st, sizeof(h), cudaMemcpyHostToDevice, ctx().stream));
   CPB_LAUNCH(k_bisect_init, 1, 256, 0, (int)K, (int)(A.n + 1), run->hint_lo.get(), run->hint_hi.get(), run->best.get());
-  if (run->stream) {
-    DevStream& ds = run->ds;
-    ds.prev = f.ls->prev.get();
-    ds.colidx = f.ls->colidx.get();
-    ds.P = f.ls->P;
-    ds.Wt = (f.dev.kind == CPB_MODEL_MONOSYM) ? f.overpos.get() - 1 : A.pos.get() - 1;
-    ds.Ne = (u32)f.ls->Ne;
-    ds.n = (u32)A.n;
-    ds.same_w = ds.Wt == ds.P;
-    for (int t = 0; t < 4; ++t) { ds.cf[t] = f.dev.cf[t]; ds.ci[t] = f.dev.ci[t]; }
-    if (run->adaptive && !run->done && K >= 2 && A.n >= 1) {
-      ProfScope pk("probe_plan_bound");
-      DBuf<int> ub_spl(K + 1);
-      DBuf<u32> ub_cnt(K);
-      DBuf<double> ub_out(1);
-      CPB_LAUNCH(k_ub_splits, (unsigned)((K + 1 + 255) / 256), 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get());
-      const unsigned slices = (unsigned)std::min<i64>(64, std::max<i64>(1, ((i64)ctx().sm_count * 8 + K - 1) / K));
-      CPB_LAUNCH(k_ub_count, dim3(slices, (unsigned)K, 1), 256, 0, ds, ub_spl.get(), ub_cnt.get());
-      CPB_LAUNCH(k_ub_max, 1, 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get(), ub_out.get());
-      CPB_CUDA(cudaMemcpyAsync(&run->ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
-      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
-    }
+  if (run->done) {  // no probe will run: the answer is the initial spl_hi = [1, n+1, ..., n+1] (BisectCost...:32-33)
+    CPB_CUDA(cudaMemcpyAsync(run->h_best.data(), run->best.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   }
   return run.release();
 }
@@ -785,6 +815,7 @@ bool bisect_advance(BisectRun& run, bool sync) {
              run.node_spl, run.node_res, run.node_c, run.ids.get());
   if (sync) {
     CPB_CUDA(cudaMemcpyAsync(&run.h_st, run.st.get(), sizeof(BisectState), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaMemcpyAsync(run.h_best.data(), run.best.get(), (run.K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
     CPB_CUDA(cudaStreamSynchronize(ctx().stream));
     run.done = run.h_st.done != 0;
     run.planned = false;  // the next round is planned from the new bracket
@@ -805,10 +836,7 @@ void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
   g_bisect_stats[0] = run->h_st.rounds; g_bisect_stats[1] = run->h_st.probes; g_bisect_stats[2] = (double)run->speculated;
   g_bisect_stats[3] = run->c_lo0; g_bisect_stats[4] = run->c_hi0; g_bisect_stats[5] = run->ub;
   g_bisect_stats[6] = run->h_st.c_lo; g_bisect_stats[7] = run->h_st.c_hi;
-  std::vector<int> hb(K + 2);
-  CPB_CUDA(cudaMemcpyAsync(hb.data(), run->best.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
-  for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = hb[k];
+  for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = run->h_best[k];  // read back by the last advance
 }
 
 #ifdef CPB_PROBE_TIMING

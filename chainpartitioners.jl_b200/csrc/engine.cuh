@@ -27,19 +27,23 @@ struct LinkStream {
   DBuf<u32> prev;    // [Ne] 1-based previous column holding the same row, 0 = none
   DBuf<u32> colidx;  // [Ne] 0-based column of each element
   DBuf<u32> P_own;   // own prefix array (diagonal-augmented variant)
-  DBuf<u32> first_count;  // [1] number of links equal to 0 (= non-empty rows)
+  DBuf<u32> first_count;  // [2] number of links equal to 0 (= non-empty rows); max row degree seen by the row-segment form
+  bool speculative = false;   // the row-segment kernels were launched before that degree was checked (see compute_prev_links)
+  i64 h_first_count = -1;     // host copy of first_count[0] once it has been read
   const u32* P = nullptr;  // P[x] = #{elements in columns < x}, 1 <= x <= n+1
   size_t Ne = 0;
 };
 struct Matrix;
-std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo = 0, i64 row_hi = ((i64)1 << 62));
+static constexpr u32 LT_MAX_DEG = 128;  // largest row degree handled by the row-segment link construction (links.cu)
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false,
+                                              bool force_sort = false);
 
 // SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
-void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
-                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62));
+bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
+                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false);
 // For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
 
 // ---- device-side oracle ------------------------------------------------------------------------
@@ -69,6 +73,7 @@ struct Oracle {
   std::unique_ptr<RankStruct> net, dianet, selfnet, selfpin;
   std::unique_ptr<LinkStream> ls;  // links for the streaming probes (net or dia-net, by model)
   DBuf<u32> overpos;
+  i64 h_n_over = -1;  // host copy of overpos[n] once it has been read
   DBuf<i64> env;
   int envH = 0;
   DBuf<double> tab_f;  // alpha_col | beta_col (double)

@@ -126,7 +126,6 @@ __global__ void k_aug_diag(const u32* __restrict__ pos2, const u32* __restrict__
 // row's segment in arbitrary order (one atomic cursor per row) and every entry finds its predecessor -- the largest
 // column below its own -- by scanning its row's short segment.  The result does not depend on the
 // order inside the segments.  Heavier rows (power-law matrices) take the radix-sort path below.
-static constexpr u32 LT_MAX_DEG = 128;
 __global__ void k_lt_count(const u32* __restrict__ row, size_t N, u32* __restrict__ cnt) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) atomicAdd(&cnt[row[q]], 1u);
@@ -136,10 +135,20 @@ __global__ void k_lt_max(const u32* __restrict__ cnt, size_t m, u32* __restrict_
   u32 v = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) v = max(v, cnt[i]);
   v = __reduce_max_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+  __shared__ u32 sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (threadIdx.x == 0 && v > *(volatile u32*)out) atomicMax(out, v);
+  }
 }
-__global__ void k_lt_fill(const u32* __restrict__ row, const u32* __restrict__ colidx, size_t N, u32* __restrict__ cursor,
+// (the three kernels below return at once when the maximal row degree, left behind the cursors by k_lt_max, exceeds the
+//  limit: the host may launch them before it has seen that value and falls back to the sort afterwards)
+__global__ void k_lt_fill(const u32* __restrict__ row, const u32* __restrict__ colidx, size_t N, u32* __restrict__ cursor, u32 m,
                           unsigned long long* __restrict__ T) {
+  if (cursor[m] > LT_MAX_DEG) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
     const u32 p = atomicAdd(&cursor[row[q]], 1u);
@@ -148,6 +157,7 @@ __global__ void k_lt_fill(const u32* __restrict__ row, const u32* __restrict__ c
 }
 // after k_lt_fill, cursor[r] = end of row r's segment = start of row r + 1: mark the first slot of every non-empty row
 __global__ void k_lt_heads(const u32* __restrict__ cursor, u32 m, u32* __restrict__ heads) {
+  if (cursor[m] > LT_MAX_DEG) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
     const u32 s = r ? cursor[r - 1] : 0u, e = cursor[r];
@@ -158,7 +168,10 @@ __global__ void k_lt_heads(const u32* __restrict__ cursor, u32 m, u32* __restric
 // entry is the largest column below its own inside the segment.  Neighbouring threads share a segment, so the scan
 // reads are warp-wide broadcasts.
 __global__ void k_lt_link(const unsigned long long* __restrict__ T, const u32* __restrict__ heads, size_t N, u32* __restrict__ prev,
-                          u32* __restrict__ first_count) {
+                          u32* __restrict__ info, const u32* __restrict__ maxdeg) {
+  u32* first_count = info;
+  if (blockIdx.x == 0 && threadIdx.x == 0) info[1] = *maxdeg;
+  if (*maxdeg > LT_MAX_DEG) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const u32 nwords = (u32)((N + 31) >> 5);
   u32 firsts = 0;
@@ -195,17 +208,21 @@ static u32 read_u32(const u32* d) {
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
 // row_lo/row_hi (0-based, half-open) restrict the construction to the nonzeros of a row block: prev[] is
 // written for those nonzeros only and is zero elsewhere (multi-GPU: ranks combine with an element-wise MAX).
-void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
-                        i64 row_lo, i64 row_hi) {
+// info[0] receives the number of links equal to 0 (= non-empty rows), info[1] the maximal row degree when the row-segment
+// form was tried (0 otherwise).  defer_check: do not wait for that degree -- launch the row-segment kernels at once (they
+// do nothing if the degree is too large) and return true; the caller inspects info[1] later and calls again with
+// CPB_NO_ROW_SEGMENTS semantics (force_sort) if it exceeds LT_MAX_DEG.
+bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
+                        i64 row_lo, i64 row_hi, bool defer_check, bool force_sort) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
   {
     ProfScope pk("k_expand_columns", (double)N * 4.0 + (double)ncol * 4.0);
     expand_columns(pos, ncol, colidx, N);
   }
   DBuf<u32> dummy;
-  if (!first_count) { dummy.alloc(1); first_count = dummy.get(); }
-  CPB_CUDA(cudaMemsetAsync(first_count, 0, sizeof(u32), ctx().stream));
-  const bool no_lt = std::getenv("CPB_NO_ROW_SEGMENTS") != nullptr;  // (tests: force the radix-sort path)
+  if (!first_count) { dummy.alloc(2); first_count = dummy.get(); }
+  CPB_CUDA(cudaMemsetAsync(first_count, 0, 2 * sizeof(u32), ctx().stream));
+  const bool no_lt = force_sort || std::getenv("CPB_NO_ROW_SEGMENTS") != nullptr;  // (tests: force the radix-sort path)
   if (row_lo <= 0 && row_hi >= (i64)nrow && N && nrow && !no_lt) {
     DBuf<u32> cur((size_t)nrow + 1);  // per-row counts -> segment starts -> (after the fill) segment ends; [nrow] = max degree
     CPB_CUDA(cudaMemsetAsync(cur.get(), 0, ((size_t)nrow + 1) * sizeof(u32), ctx().stream));
@@ -214,44 +231,45 @@ void compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
       CPB_LAUNCH(k_lt_count, grid_for(N), 256, 0, row, N, cur.get());
     }
     CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
-    if (read_u32(cur.get() + nrow) <= LT_MAX_DEG) {
+    if (defer_check || read_u32(cur.get() + nrow) <= LT_MAX_DEG) {
       exclusive_scan_u32(cur.get(), cur.get(), (size_t)nrow);
       DBuf<unsigned long long> T(N);
       {
         ProfScope pk("k_lt_fill", (double)N * 16.0);
-        CPB_LAUNCH(k_lt_fill, grid_for(N), 256, 0, row, colidx, N, cur.get(), T.get());
+        CPB_LAUNCH(k_lt_fill, grid_for(N), 256, 0, row, colidx, N, cur.get(), nrow, T.get());
       }
       {
         ProfScope pk("k_lt_link", (double)N * 12.0);
         DBuf<u32> heads(N / 32 + 2);
         heads.zero();
         CPB_LAUNCH(k_lt_heads, grid_for(nrow), 256, 0, cur.get(), nrow, heads.get());
-        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), N, prev, first_count);
+        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), N, prev, first_count, cur.get() + nrow);
       }
-      return;
+      return defer_check;
     }
   }
   if (row_lo <= 0 && row_hi >= (i64)nrow) {
     TransposeOrder t;
     transpose_order(row, N, nrow ? nrow - 1 : 0, t);
     if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count);
-    return;
+    return false;
   }
   if (N) CPB_CUDA(cudaMemsetAsync(prev, 0, N * sizeof(u32), ctx().stream));
   DBuf<u32> flags(N + 1), scan(N + 1);
   CPB_LAUNCH(k_row_flags, grid_for(N + 1), 256, 0, row, N, (u32)std::max<i64>(row_lo, 0), (u32)std::min<i64>(row_hi, nrow), flags.get());
   exclusive_scan_u32(flags.get(), scan.get(), N + 1);
   const size_t M = read_u32(scan.get() + N);
-  if (M == 0) return;
+  if (M == 0) return false;
   DBuf<u32> k0(M), v0(M), k1(M), v1(M);
   CPB_LAUNCH(k_row_compact, grid_for(N), 256, 0, row, flags.get(), scan.get(), N, k0.get(), v0.get());
   const int which = radix_sort_pairs(k0.get(), v0.get(), k1.get(), v1.get(), M, bits_for(nrow ? nrow - 1 : 0));
   CPB_LAUNCH(k_link_prev, grid_for(M), 256, 0, which ? k1.get() : k0.get(), which ? v1.get() : v0.get(), colidx, prev, M, first_count);
+  return false;
 }
 
 // The link array of A (dia = false) or of A + I (dia = true, SparseColorArrays.jl:72-99) in column order,
 // kept for the streaming probes; P[x] = #{elements in columns < x}.
-std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo, i64 row_hi) {
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo, i64 row_hi, bool defer_check, bool force_sort) {
   auto ls = std::make_unique<LinkStream>();
   const size_t N = (size_t)A.N;
   const u32 n = (u32)A.n, m = (u32)A.m;
@@ -259,8 +277,9 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
     ls->Ne = N;
     ls->prev.alloc(N);
     ls->colidx.alloc(N);
-    ls->first_count.alloc(1);
-    compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi);
+    ls->first_count.alloc(2);
+    ls->speculative = compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi,
+                                         defer_check, force_sort);
     ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
     return ls;
   }
@@ -281,8 +300,9 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
   ls->Ne = N2;
   ls->prev.alloc(N2);
   ls->colidx.alloc(N2);
-  ls->first_count.alloc(1);
-  compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi);
+  ls->first_count.alloc(2);
+  ls->speculative = compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi, defer_check,
+                                       force_sort);
   ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
   return ls;
 }

@@ -234,6 +234,7 @@ void oracle_set_links(Oracle& f, const u32* d_prev, i64 Ne) {
   if (Ne) CPB_CUDA(cudaMemcpyAsync(f.ls->prev.get(), d_prev, (size_t)Ne * sizeof(u32), cudaMemcpyDeviceToDevice, ctx().stream));
   CPB_CUDA(cudaMemsetAsync(f.ls->first_count.get(), 0, sizeof(u32), ctx().stream));
   if (Ne) CPB_LAUNCH(k_count_zero_u32, grid_for((size_t)Ne), 256, 0, f.ls->prev.get(), (size_t)Ne, f.ls->first_count.get());
+  f.ls->h_first_count = -1;
   f.ls_complete = true;
 }
 
@@ -295,7 +296,8 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
         c_hi = (T)query_one(f, 1, A.n + 1);
       } else {  // ocl(1, n+1) from the link array alone: nets(1, n+1) = number of non-empty rows
         if (!f.ls) f.ls = build_link_stream(*f.A, false);
-        const i64 nets_all = count_first_occurrences(*f.ls);
+        if (f.ls->h_first_count < 0) f.ls->h_first_count = count_first_occurrences(*f.ls);
+        const i64 nets_all = f.ls->h_first_count;
         c_hi = c[0] + (T)A.n * c[1] + (T)A.N * c[2] + (T)nets_all * c[3];
       }
       c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
@@ -303,9 +305,13 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
     }
     case CPB_MODEL_MONOSYM: {
       CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0, "negative beta (Monotonized...:98-100)");
-      u32 n_over = 0;
-      CPB_CUDA(cudaMemcpyAsync(&n_over, f.overpos.get() + A.n, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
-      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      if (f.h_n_over < 0) {
+        u32 n_over = 0;
+        CPB_CUDA(cudaMemcpyAsync(&n_over, f.overpos.get() + A.n, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+        CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+        f.h_n_over = n_over;
+      }
+      const u32 n_over = (u32)f.h_n_over;
       c_hi = c[0] + c[1] * (T)A.n + c[2] * (T)n_over + c[3] * (T)A.m;
       c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
       break;
