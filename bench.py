@@ -33,9 +33,9 @@ NNZ_PER_COL = 10
 K_PARTS = 64
 EPS = 0.01
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at this workload
-# (profiles/r01_notes.md: k_probe_stream 44.7 MB read + 0.2 MB write; k_rs_scatter 42-82 MB read + 52-56 MB
-# write over the three passes; k_wm_level 40.05 MB read + 1-3 MB write), bytes
-TRAFFIC = {"k_probe_stream": 44.9e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6}
+# (profiles/r01_ncu_summary.md: k_probe_stream 45.0 MB read + 0.9 MB write; k_lt_fill 163.3 + 169.8 MB; k_lt_link
+# 116.5 + 40.6 MB; k_lt_count 44.0 MB read; k_rs_scatter 42-82 MB read + 52-56 MB write; k_wm_level 40.05 + 1-3 MB), bytes
+TRAFFIC = {"k_probe_stream": 45.9e6, "k_lt_fill": 333.1e6, "k_lt_link": 157.1e6, "k_lt_count": 44.0e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6}
 METRIC = "partition_stripe throughput (BisectCostBottleneckSplitter, Erdos-Renyi 1Mx1M, K=64)"
 UNIT = "partitions/s"
 
@@ -264,9 +264,14 @@ def main():
                     "peak_source": peak_src, "launches_per_step": k["launches"] / max(args.steps, 1), "avg_launch_us": 1e3 * k["ms"] / max(k["launches"], 1),
                     "algorithmic_bytes_per_launch": k["bytes"] / max(k["launches"], 1), "share_of_step": k["ms"] / max(dev_ms, 1e-9), "note": note}
 
-        NOTES = {"k_probe_stream": "greedy feasibility probes of 2^4-1 thresholds, one 8-CTA cluster each; latency-bound (K sequential parts x 2 cluster barriers), "
-                                   "bytes = ONE pass over the link array per launch (SURVEY 8d G4) although every threshold streams it (mostly from L2)",
-                 "k_rs_scatter": "stable 8-bit radix scatter of (row, position) pairs inside build_links",
+        NOTES = {"k_probe_stream": "greedy feasibility probes of the 15 most likely thresholds of the bisection tree, one 8-CTA cluster each; latency-bound "
+                                   "(K sequential parts x 2 cluster barriers), bytes = ONE pass over the link array per launch (SURVEY 8d G4) although every "
+                                   "threshold streams it (mostly from L2)",
+                 "k_lt_fill": "build_links: every nonzero takes a slot of its row's segment through an atomic cursor and stores its position; "
+                              "bytes = read row, write 4 B per nonzero (random 4-byte stores)",
+                 "k_lt_link": "build_links: every slot scans its row segment for the largest column below its own and writes the link (scattered 4-byte stores)",
+                 "k_lt_count": "build_links: row histogram (one atomic per nonzero)",
+                 "k_rs_scatter": "stable radix scatter of (row, position) pairs inside build_links (rows heavier than 128 nonzeros)",
                  "k_wm_level": "one bit level of the wavelet-matrix dominance index"}
         roofline = roof(top, NOTES.get(top, "")) if top else None
         roofline_all = [roof(nm, NOTES.get(nm, "")) for nm in sorted(kernels, key=lambda nm: -kernels[nm]["ms"])]

@@ -124,7 +124,7 @@ __global__ void k_aug_diag(const u32* __restrict__ pos2, const u32* __restrict__
 // ---- link construction by an unordered transpose (rows of bounded degree) --------------------------------------
 // When no row holds more than LT_MAX_DEG nonzeros the stable sort is unnecessary: the nonzeros are dropped into their
 // row's segment in arbitrary order (one atomic cursor per row) and every entry finds its predecessor -- the largest
-// column below its own -- by scanning its row's short segment.  The result does not depend on the
+// CSC position below its own -- by scanning its row's short segment.  The result does not depend on the
 // order inside the segments.  Heavier rows (power-law matrices) take the radix-sort path below.
 __global__ void k_lt_count(const u32* __restrict__ row, size_t N, u32* __restrict__ cnt) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -146,14 +146,10 @@ __global__ void k_lt_max(const u32* __restrict__ cnt, size_t m, u32* __restrict_
 }
 // (the three kernels below return at once when the maximal row degree, left behind the cursors by k_lt_max, exceeds the
 //  limit: the host may launch them before it has seen that value and falls back to the sort afterwards)
-__global__ void k_lt_fill(const u32* __restrict__ row, const u32* __restrict__ colidx, size_t N, u32* __restrict__ cursor, u32 m,
-                          unsigned long long* __restrict__ T) {
+__global__ void k_lt_fill(const u32* __restrict__ row, size_t N, u32* __restrict__ cursor, u32 m, u32* __restrict__ T) {
   if (cursor[m] > LT_MAX_DEG) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
-    const u32 p = atomicAdd(&cursor[row[q]], 1u);
-    T[p] = ((unsigned long long)colidx[q] << 32) | (unsigned long long)q;
-  }
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) T[atomicAdd(&cursor[row[q]], 1u)] = (u32)q;
 }
 // after k_lt_fill, cursor[r] = end of row r's segment = start of row r + 1: mark the first slot of every non-empty row
 __global__ void k_lt_heads(const u32* __restrict__ cursor, u32 m, u32* __restrict__ heads) {
@@ -165,10 +161,10 @@ __global__ void k_lt_heads(const u32* __restrict__ cursor, u32 m, u32* __restric
   }
 }
 // One thread per slot: the slot's row segment is delimited by the head bits around it; the predecessor of the slot's
-// entry is the largest column below its own inside the segment.  Neighbouring threads share a segment, so the scan
-// reads are warp-wide broadcasts.
-__global__ void k_lt_link(const unsigned long long* __restrict__ T, const u32* __restrict__ heads, size_t N, u32* __restrict__ prev,
-                          u32* __restrict__ info, const u32* __restrict__ maxdeg) {
+// entry is the largest CSC position below its own inside the segment (positions ascend with the column), and its
+// column is the link.  Neighbouring threads share a segment, so the scan reads are warp-wide broadcasts.
+__global__ void k_lt_link(const u32* __restrict__ T, const u32* __restrict__ heads, const u32* __restrict__ colidx, size_t N,
+                          u32* __restrict__ prev, u32* __restrict__ info, const u32* __restrict__ maxdeg) {
   u32* first_count = info;
   if (blockIdx.x == 0 && threadIdx.x == 0) info[1] = *maxdeg;
   if (*maxdeg > LT_MAX_DEG) return;
@@ -184,14 +180,13 @@ __global__ void k_lt_link(const unsigned long long* __restrict__ T, const u32* _
     bits = (p & 31) == 31 ? 0u : (heads[w] & (0xffffffffu << ((u32)(p & 31) + 1)));
     while (!bits && ++w < nwords) bits = heads[w];
     const u32 e = bits ? min((u32)N, (w << 5) + (u32)__ffs(bits) - 1u) : (u32)N;
-    const unsigned long long ti = T[p];
-    const u32 ci = (u32)(ti >> 32);
-    u32 best = 0;  // 1-based previous column holding this row, 0 = none
+    const u32 qi = T[p];
+    u32 best = 0;  // 1 + position of the previous nonzero of this row, 0 = none
     for (u32 k = s; k < e; ++k) {
-      const u32 ck = (u32)(T[k] >> 32);
-      if (ck < ci) best = max(best, ck + 1u);
+      const u32 qk = T[k];
+      if (qk < qi) best = max(best, qk + 1u);
     }
-    prev[(u32)ti] = best;
+    prev[qi] = best ? __ldg(colidx + (best - 1u)) + 1u : 0u;  // 1-based previous column holding this row
     firsts += best == 0u;
   }
   firsts = __reduce_add_sync(0xffffffffu, firsts);
@@ -233,17 +228,17 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
     CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
     if (defer_check || read_u32(cur.get() + nrow) <= LT_MAX_DEG) {
       exclusive_scan_u32(cur.get(), cur.get(), (size_t)nrow);
-      DBuf<unsigned long long> T(N);
+      DBuf<u32> T(N);
       {
-        ProfScope pk("k_lt_fill", (double)N * 16.0);
-        CPB_LAUNCH(k_lt_fill, grid_for(N), 256, 0, row, colidx, N, cur.get(), nrow, T.get());
+        ProfScope pk("k_lt_fill", (double)N * 8.0);
+        CPB_LAUNCH(k_lt_fill, grid_for(N), 256, 0, row, N, cur.get(), nrow, T.get());
       }
       {
         ProfScope pk("k_lt_link", (double)N * 12.0);
         DBuf<u32> heads(N / 32 + 2);
         heads.zero();
         CPB_LAUNCH(k_lt_heads, grid_for(nrow), 256, 0, cur.get(), nrow, heads.get());
-        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), N, prev, first_count, cur.get() + nrow);
+        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), colidx, N, prev, first_count, cur.get() + nrow);
       }
       return defer_check;
     }
