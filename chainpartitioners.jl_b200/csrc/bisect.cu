@@ -144,6 +144,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
 // ------------------------------------------------------------------------------------------------
 // Streaming probe (kernel "probe_stream"): the device form of the reference's lazy probes
 // (LazyBisectCostBottleneckSplitter.jl:194-229 connectivity, :323-359 monotonized symmetric).
+// (Here the link array holds 1 + the CSC POSITION of the previous nonzero of the same row, so "previous column < j"
+// is `prev <= first position of the part`; written `prev < j` below.)
 // The reference streams cch[] = previous column of every nonzero and counts `cch[q] < j` for the
 // current part start j; a part ends where the running cost first exceeds c.  Here one 8-CTA cluster
 // per threshold streams the same link array in super-steps of 8 x 16384 elements: ballots turn
@@ -173,7 +175,8 @@ __device__ __forceinline__ u32 stream_prefix(const u32* s_mask, const u32* s_cum
 }
 
 struct DevStream {
-  const u32* prev;    // [Ne]
+  const u32* prev;    // [Ne] 1 + position of the previous nonzero of the same row (0 = none): "its column lies left of the part"
+                      //      is simply prev <= first position of the part
   const u32* colidx;  // [Ne]
   const u32* P;       // element offsets of the column boundaries, 1 <= x <= n+1
   const u32* Wt;      // prefix of the pin-like term, 1 <= x <= n+1
@@ -275,7 +278,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         if (v >= (int)nv) break;
         const u32 g = warp * nv + v;
         const u32 idx = e_c + g * 128 + lane * 4;
-        uint4 pv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        uint4 pv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // (beyond the end: never counted)
         if ((u64)idx + 4 <= Ne) {
           pv = __ldg(reinterpret_cast<const uint4*>(s.prev + idx));
         } else {
@@ -284,10 +287,10 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
           if (idx + 2 < Ne) pv.z = __ldg(s.prev + idx + 2);
         }
         const bool head = idx < e0;  // only the first few elements of the first tile
-        const unsigned m0 = __ballot_sync(0xffffffffu, pv.x < j && !(head && idx + 0 < e0));
-        const unsigned m1 = __ballot_sync(0xffffffffu, pv.y < j && !(head && idx + 1 < e0));
-        const unsigned m2 = __ballot_sync(0xffffffffu, pv.z < j && !(head && idx + 2 < e0));
-        const unsigned m3 = __ballot_sync(0xffffffffu, pv.w < j && !(head && idx + 3 < e0));
+        const unsigned m0 = __ballot_sync(0xffffffffu, pv.x <= e0 && !(head && idx + 0 < e0));
+        const unsigned m1 = __ballot_sync(0xffffffffu, pv.y <= e0 && !(head && idx + 1 < e0));
+        const unsigned m2 = __ballot_sync(0xffffffffu, pv.z <= e0 && !(head && idx + 2 < e0));
+        const unsigned m3 = __ballot_sync(0xffffffffu, pv.w <= e0 && !(head && idx + 3 < e0));
         if (lane < 4) s_mask[g * 4 + lane] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
         if (lane == 4) s_cum[g] = wsum;  // prefix inside the warp's run; the warp's base is added after the barrier
         wsum += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStr
   const u32 j = (u32)spl[k];
   const u32 e0 = __ldg(s.P + j), e1 = __ldg(s.P + (u32)spl[k + 1]);
   u32 c = 0;
-  for (u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) c += __ldg(s.prev + e) < j;
+  for (u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) c += __ldg(s.prev + e) <= e0;
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
 }
@@ -706,7 +709,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     const bool dia = f.dev.kind == CPB_MODEL_MONOSYM;
     if (!f.ls) {
       ProfScope prof("oracle_stripe");
-      f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/true);
+      f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/true, false, /*as_pos=*/true);
     }
     const bool want_ub = run->adaptive && K >= 2 && A.n >= 1;
     DBuf<double> ub_out(1);
@@ -720,7 +723,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
       CPB_CUDA(cudaStreamSynchronize(ctx().stream));
       if (f.ls->speculative && info[1] > LT_MAX_DEG) {  // a heavy row: the row-segment kernels did nothing -> stable sort
         ProfScope prof("oracle_stripe");
-        f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, false, /*force_sort=*/true);
+        f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, false, /*force_sort=*/true, /*as_pos=*/true);
         continue;
       }
       f.ls->speculative = false;

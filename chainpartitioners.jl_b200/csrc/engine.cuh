@@ -24,7 +24,8 @@ struct RankStruct {
 
 // the link array itself, in column order (streaming probes; also the input of the wavelet build)
 struct LinkStream {
-  DBuf<u32> prev;    // [Ne] 1-based previous column holding the same row, 0 = none
+  DBuf<u32> prev;    // [Ne] 1-based previous column holding the same row, 0 = none; pos_links: 1 + position of that nonzero
+  bool pos_links = false;
   DBuf<u32> colidx;  // [Ne] 0-based column of each element
   DBuf<u32> P_own;   // own prefix array (diagonal-augmented variant)
   DBuf<u32> first_count;  // [2] number of links equal to 0 (= non-empty rows); max row degree seen by the row-segment form
@@ -36,14 +37,14 @@ struct LinkStream {
 struct Matrix;
 static constexpr u32 LT_MAX_DEG = 128;  // largest row degree handled by the row-segment link construction (links.cu)
 std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false,
-                                              bool force_sort = false);
+                                              bool force_sort = false, bool as_pos = false);
 
 // SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
-                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false);
+                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false, bool as_pos = false);
 // For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
 
 // ---- device-side oracle ------------------------------------------------------------------------

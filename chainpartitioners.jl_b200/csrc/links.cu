@@ -39,14 +39,15 @@ __global__ void k_row_compact(const u32* __restrict__ row, const u32* __restrict
     if (flags[q]) { keys[scan[q]] = row[q]; vals[scan[q]] = (u32)q; }
 }
 
-// prev[q] = 1-based previous column holding the same row, 0 if none
+// prev[q] = 1-based previous column holding the same row, 0 if none; as_pos: 1 + CSC position of that previous nonzero
+// instead (what the streaming probes compare against the part's first position -- no column lookup at all)
 __global__ void k_link_prev(const u32* __restrict__ sk, const u32* __restrict__ sq, const u32* __restrict__ colidx,
-                            u32* __restrict__ prev, size_t N, u32* __restrict__ first_count) {
+                            u32* __restrict__ prev, size_t N, u32* __restrict__ first_count, int as_pos) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   u32 firsts = 0;  // links equal to 0 = first occurrence of a row = number of non-empty rows
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
     u32 link = 0;
-    if (p > 0 && sk[p - 1] == sk[p]) link = __ldg(colidx + sq[p - 1]) + 1u;
+    if (p > 0 && sk[p - 1] == sk[p]) link = as_pos ? sq[p - 1] + 1u : __ldg(colidx + sq[p - 1]) + 1u;
     prev[sq[p]] = link;
     firsts += link == 0u;
   }
@@ -164,7 +165,7 @@ __global__ void k_lt_heads(const u32* __restrict__ cursor, u32 m, u32* __restric
 // entry is the largest CSC position below its own inside the segment (positions ascend with the column), and its
 // column is the link.  Neighbouring threads share a segment, so the scan reads are warp-wide broadcasts.
 __global__ void k_lt_link(const u32* __restrict__ T, const u32* __restrict__ heads, const u32* __restrict__ colidx, size_t N,
-                          u32* __restrict__ prev, u32* __restrict__ info, const u32* __restrict__ maxdeg) {
+                          u32* __restrict__ prev, u32* __restrict__ info, const u32* __restrict__ maxdeg, int as_pos) {
   u32* first_count = info;
   if (blockIdx.x == 0 && threadIdx.x == 0) info[1] = *maxdeg;
   if (*maxdeg > LT_MAX_DEG) return;
@@ -186,7 +187,7 @@ __global__ void k_lt_link(const u32* __restrict__ T, const u32* __restrict__ hea
       const u32 qk = T[k];
       if (qk < qi) best = max(best, qk + 1u);
     }
-    prev[qi] = best ? __ldg(colidx + (best - 1u)) + 1u : 0u;  // 1-based previous column holding this row
+    prev[qi] = (best && !as_pos) ? __ldg(colidx + (best - 1u)) + 1u : best;  // 1-based previous column (or position) of this row
     firsts += best == 0u;
   }
   firsts = __reduce_add_sync(0xffffffffu, firsts);
@@ -208,7 +209,7 @@ static u32 read_u32(const u32* d) {
 // do nothing if the degree is too large) and return true; the caller inspects info[1] later and calls again with
 // CPB_NO_ROW_SEGMENTS semantics (force_sort) if it exceeds LT_MAX_DEG.
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
-                        i64 row_lo, i64 row_hi, bool defer_check, bool force_sort) {
+                        i64 row_lo, i64 row_hi, bool defer_check, bool force_sort, bool as_pos) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
   {
     ProfScope pk("k_expand_columns", (double)N * 4.0 + (double)ncol * 4.0);
@@ -238,7 +239,7 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
         DBuf<u32> heads(N / 32 + 2);
         heads.zero();
         CPB_LAUNCH(k_lt_heads, grid_for(nrow), 256, 0, cur.get(), nrow, heads.get());
-        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), colidx, N, prev, first_count, cur.get() + nrow);
+        CPB_LAUNCH(k_lt_link, grid_for(N), 256, 0, T.get(), heads.get(), colidx, N, prev, first_count, cur.get() + nrow, as_pos ? 1 : 0);
       }
       return defer_check;
     }
@@ -246,7 +247,7 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   if (row_lo <= 0 && row_hi >= (i64)nrow) {
     TransposeOrder t;
     transpose_order(row, N, nrow ? nrow - 1 : 0, t);
-    if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count);
+    if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count, as_pos ? 1 : 0);
     return false;
   }
   if (N) CPB_CUDA(cudaMemsetAsync(prev, 0, N * sizeof(u32), ctx().stream));
@@ -258,14 +259,15 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   DBuf<u32> k0(M), v0(M), k1(M), v1(M);
   CPB_LAUNCH(k_row_compact, grid_for(N), 256, 0, row, flags.get(), scan.get(), N, k0.get(), v0.get());
   const int which = radix_sort_pairs(k0.get(), v0.get(), k1.get(), v1.get(), M, bits_for(nrow ? nrow - 1 : 0));
-  CPB_LAUNCH(k_link_prev, grid_for(M), 256, 0, which ? k1.get() : k0.get(), which ? v1.get() : v0.get(), colidx, prev, M, first_count);
+  CPB_LAUNCH(k_link_prev, grid_for(M), 256, 0, which ? k1.get() : k0.get(), which ? v1.get() : v0.get(), colidx, prev, M, first_count, as_pos ? 1 : 0);
   return false;
 }
 
 // The link array of A (dia = false) or of A + I (dia = true, SparseColorArrays.jl:72-99) in column order,
 // kept for the streaming probes; P[x] = #{elements in columns < x}.
-std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo, i64 row_hi, bool defer_check, bool force_sort) {
+std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo, i64 row_hi, bool defer_check, bool force_sort, bool as_pos) {
   auto ls = std::make_unique<LinkStream>();
+  ls->pos_links = as_pos;
   const size_t N = (size_t)A.N;
   const u32 n = (u32)A.n, m = (u32)A.m;
   if (!dia) {
@@ -274,7 +276,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
     ls->colidx.alloc(N);
     ls->first_count.alloc(2);
     ls->speculative = compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi,
-                                         defer_check, force_sort);
+                                         defer_check, force_sort, as_pos);
     ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
     return ls;
   }
@@ -297,7 +299,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
   ls->colidx.alloc(N2);
   ls->first_count.alloc(2);
   ls->speculative = compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi, defer_check,
-                                       force_sort);
+                                       force_sort, as_pos);
   ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
   return ls;
 }

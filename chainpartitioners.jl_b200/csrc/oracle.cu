@@ -219,7 +219,7 @@ static bool model_uses_dia(int kind) { return kind == CPB_MODEL_MONOSYM; }
 // the links of the nonzeros whose row is in [row_lo, row_hi) (1-based, half-open); zero elsewhere
 i64 oracle_links_partial(Oracle& f, i64 row_lo, i64 row_hi, u32* d_prev_out) {
   CPB_REQUIRE(f.dev.kind == CPB_MODEL_CONNECTIVITY || f.dev.kind == CPB_MODEL_MONOSYM, "streaming links exist for connectivity-type models only");
-  auto ls = build_link_stream(*f.A, model_uses_dia(f.dev.kind), row_lo - 1, row_hi - 1);
+  auto ls = build_link_stream(*f.A, model_uses_dia(f.dev.kind), row_lo - 1, row_hi - 1, false, false, /*as_pos=*/true);
   if (d_prev_out && ls->Ne) CPB_CUDA(cudaMemcpyAsync(d_prev_out, ls->prev.get(), ls->Ne * sizeof(u32), cudaMemcpyDeviceToDevice, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   const i64 Ne = (i64)ls->Ne;
@@ -295,7 +295,7 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
       if (f.ranks_built) {
         c_hi = (T)query_one(f, 1, A.n + 1);
       } else {  // ocl(1, n+1) from the link array alone: nets(1, n+1) = number of non-empty rows
-        if (!f.ls) f.ls = build_link_stream(*f.A, false);
+        if (!f.ls) f.ls = build_link_stream(*f.A, false, 0, (i64)1 << 62, false, false, /*as_pos=*/true);
         if (f.ls->h_first_count < 0) f.ls->h_first_count = count_first_occurrences(*f.ls);
         const i64 nets_all = f.ls->h_first_count;
         c_hi = c[0] + (T)A.n * c[1] + (T)A.N * c[2] + (T)nets_all * c[3];
