@@ -317,7 +317,22 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       }
       PT(2);
       if (tid < BS_CLUSTER) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
-      cluster.sync();  // also orders s_cum for the boundary phase
+      cluster.barrier_arrive();  // split barrier: the boundary offsets below are fetched while the totals travel
+      const u32 nb = (jb >= ja) ? jb - ja + 1 : 0;
+      // thread t owns the (at most 4) consecutive boundaries [t * per, (t + 1) * per) when the CTA has at most 4096 of
+      // them: all loaded up front (one memory latency), before the barrier completes
+      const bool few = nb > 0 && nb <= 4u * SP_THREADS;
+      const u32 per = (nb + SP_THREADS - 1) / SP_THREADS;
+      const u32 b0 = (u32)tid * per;
+      const u32 mine = (few && b0 < nb) ? min(per, nb - b0) : 0u;
+      u32 pjv[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < (int)mine) {
+          pjv[i] = __ldg(s.P + ja + b0 + i);
+          wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + ja + b0 + i);
+        }
+      cluster.barrier_wait();  // also orders s_cum for the boundary phase
       PT(3);
       u32 base_c = 0, tile_tot = 0;
 #pragma unroll
@@ -326,30 +341,17 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         if (p < (int)crank) base_c += v;
         tile_tot += v;
       }
-      const u32 nb = (jb >= ja) ? jb - ja + 1 : 0;
       auto feasible_pw = [&](u32 jp, u32 pj, u32 w) -> bool {
         const u32 g = grun + base_c + stream_prefix(s_mask, s_cum, pj - e_c);
         return cost_leq(stream_cost<T>(s, (i64)jp - (i64)j, (i64)w - wj, (i64)g), c);
       };
-      // monotone costs: the feasible boundaries of this CTA form a prefix [ja, ja + cnt).  Two strided passes
-      // locate its end (1024 evenly spaced probes, then the boundaries inside the crossing stride); every thread
-      // stashes the (P, Wt) of its candidate so the next part can start without reloading them.
+      // monotone costs: the feasible boundaries of this CTA form a prefix [ja, ja + cnt); every thread stashes the
+      // (P, Wt) of its candidate so the next part can start without reloading them.
       u32 cnt = 0, lastp = 0, lastw = 0;
       if (tid == 0) { s_red[ph ^ 1][0] = 0; s_red[ph ^ 1][1] = 0; s_red[ph ^ 1][2] = 0; }  // the next super-step's accumulators
-      if (nb > 0 && nb <= 4u * SP_THREADS) {
-        // thread t owns the (at most 4) consecutive boundaries [t * per, (t + 1) * per), all loaded up front (one memory
-        // latency).  Monotone costs: every thread tests its LAST boundary; the first thread whose last boundary fails
-        // holds the crossing and tests its remaining ones from registers.
-        const u32 per = (nb + SP_THREADS - 1) / SP_THREADS;
-        const u32 b0 = (u32)tid * per;
-        const u32 mine = b0 < nb ? min(per, nb - b0) : 0u;
-        u32 pjv[4], wv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < (int)mine) {
-            pjv[i] = __ldg(s.P + ja + b0 + i);
-            wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + ja + b0 + i);
-          }
+      if (few) {
+        // every thread tests its LAST boundary; the first thread whose last boundary fails holds the crossing and tests
+        // its remaining ones from registers.
         bool ok = false;
         if (mine > 0) {
           u32 pl = pjv[0], wl = wv[0];
