@@ -47,6 +47,99 @@ __global__ void __launch_bounds__(WM_THREADS, 2048 / WM_THREADS) k_wm_level(cons
   const u32 wbase = w * WM_BLOCK;  // element offset of this warp's rank block inside the tile
   if (tid < 4) s_next[tid] = 0;
 
+  // ---- full tiles (all but the last): the level is issue-bound (ncu: 88 % issue slots busy at 40 % of dram peak), so
+  //      this path keeps the per-element instruction count down -- no bounds predicates, the zero masks are the
+  //      complements of the one masks, and the next level's per-tile zero counts come from warp-uniform popcounts (a
+  //      warp's zeros / ones land in one contiguous destination range; only a warp whose range straddles a
+  //      destination-tile boundary looks at individual lanes).
+  if (tbase + WM_TILE <= (size_t)n) {
+    const u32* src = cur + tbase + wbase + lane;
+    u32 v[WM_ROUNDS], ones[WM_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < WM_ROUNDS; ++r) v[r] = src[r * 32];
+    const u32 Z0 = tile_off[tile];
+    const u32 ztot = tile_off[tiles];
+    u32 wo = 0;
+#pragma unroll
+    for (int r = 0; r < WM_ROUNDS; ++r) {
+      ones[r] = __ballot_sync(FULL, (v[r] >> bit) & 1u);
+      wo += __popc(ones[r]);
+    }
+    const u32 wz = WM_BLOCK - wo;
+    if (lane == 0) s_wz[w] = wz;
+    __syncthreads();
+    const u32 zbefore = __reduce_add_sync(FULL, lane < w ? s_wz[lane] : 0u);  // zeros of the tile before this warp
+    if (tile == 0 && tid == 0) *z_out = ztot;
+    {  // rank block: header (zeros before the block) + 7 bit words, one 32-byte store
+      u32 word = Z0 + zbefore;
+#pragma unroll
+      for (int k = 0; k < WM_ROUNDS; ++k)
+        if (lane == k + 1) word = ones[k];
+      if (lane < 8) blocks[((size_t)tile * WM_TILE_BLOCKS + w) * 8 + lane] = word;
+    }
+    const u32 O0 = ztot + (u32)(tbase - Z0);
+    const unsigned lt = (1u << lane) - 1u;
+    u32 zrun = zbefore;
+    u32* const dz = nxt + Z0;
+    u32* const dones = nxt + O0;
+    const u32 in_tile0 = wbase + lane;
+#pragma unroll
+    for (int r = 0; r < WM_ROUNDS; ++r) {
+      const u32 zm = ~ones[r];
+      const u32 zb = zrun + __popc(zm & lt);  // zeros of the tile before this element
+      if ((v[r] >> bit) & 1u) dones[in_tile0 + r * 32 - zb] = v[r]; else dz[zb] = v[r];  // (ones before me = index - zeros before me)
+      zrun += __popc(zm);
+    }
+    if (next_bit >= 0) {
+      const u32 bndZ = (Z0 / WM_TILE + 1) * WM_TILE;
+      const u32 bndO = (O0 / WM_TILE + 1) * WM_TILE;
+      u32 wz_nz = 0, wo_nz = 0;
+#pragma unroll
+      for (int r = 0; r < WM_ROUNDS; ++r) {
+        const u32 nzr = __ballot_sync(FULL, ((v[r] >> next_bit) & 1u) == 0u);
+        wz_nz += __popc(~ones[r] & nzr);
+        wo_nz += __popc(ones[r] & nzr);
+      }
+      // how many of this warp's zeros (ones) with a 0 next bit land before the destination-tile boundary
+      auto before_boundary = [&](bool zero_class, u32 start, u32 count, u32 bnd, u32 total_nz) -> u32 {
+        if (start + count <= bnd) return total_nz;
+        if (start >= bnd) return 0u;
+        const u32 k = bnd - start;  // elements of the class landing before the boundary
+        u32 run = 0, before = 0;
+#pragma unroll
+        for (int r = 0; r < WM_ROUNDS; ++r) {
+          const u32 cm = zero_class ? ~ones[r] : ones[r];
+          const u32 cr = __popc(cm);
+          if (run < k) {  // (warp-uniform) this round still has elements before the boundary
+            const u32 nzr = __ballot_sync(FULL, ((v[r] >> next_bit) & 1u) == 0u);
+            if (run + cr <= k) {
+              before += __popc(cm & nzr);
+            } else {
+              const bool mine = ((cm >> lane) & 1u) && (u32)__popc(cm & lt) < k - run;
+              before += __popc(__ballot_sync(FULL, mine) & nzr);
+            }
+          }
+          run += cr;
+        }
+        return before;
+      };
+      const u32 a0 = before_boundary(true, Z0 + zbefore, wz, bndZ, wz_nz);
+      const u32 a2 = before_boundary(false, O0 + (wbase - zbefore), wo, bndO, wo_nz);
+      if (lane == 0) {
+        if (a0) atomicAdd(&s_next[0], a0);
+        if (wz_nz - a0) atomicAdd(&s_next[1], wz_nz - a0);
+        if (a2) atomicAdd(&s_next[2], a2);
+        if (wo_nz - a2) atomicAdd(&s_next[3], wo_nz - a2);
+      }
+      __syncthreads();
+      if (tid < 4 && s_next[tid]) {
+        const u32 t = (tid < 2 ? bndZ : bndO) / WM_TILE - 1 + (tid & 1);
+        atomicAdd(&next_tile_zeros[t], s_next[tid]);
+      }
+    }
+    return;
+  }
+
   u32 v[WM_ROUNDS], ones[WM_ROUNDS], zmask[WM_ROUNDS];
   u32 wz = 0;
 #pragma unroll
