@@ -711,7 +711,9 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     const bool dia = f.dev.kind == CPB_MODEL_MONOSYM;
     if (!f.ls) {
       ProfScope prof("oracle_stripe");
-      f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/true, false, /*as_pos=*/true);
+      // (large patterns: check the row degree first -- a wasted gigabyte-sized segment allocation costs far more than
+      //  the ~20 us round trip the deferred check saves)
+      f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/A.N < ((i64)1 << 25), false, /*as_pos=*/true);
     }
     const bool want_ub = run->adaptive && K >= 2 && A.n >= 1;
     DBuf<double> ub_out(1);

@@ -247,7 +247,10 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   if (row_lo <= 0 && row_hi >= (i64)nrow) {
     TransposeOrder t;
     transpose_order(row, N, nrow ? nrow - 1 : 0, t);
-    if (N) CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count, as_pos ? 1 : 0);
+    if (N) {
+      ProfScope pk("k_link_prev", (double)N * 12.0);
+      CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count, as_pos ? 1 : 0);
+    }
     return false;
   }
   if (N) CPB_CUDA(cudaMemsetAsync(prev, 0, N * sizeof(u32), ctx().stream));

@@ -258,8 +258,14 @@ static int radix_sort_passes(u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp,
     u32* vi = which ? vals_tmp : vals;
     u32* ko = which ? keys : keys_tmp;
     u32* vo = which ? vals : vals_tmp;
-    CPB_LAUNCH(k_rs_hist<DB>, tiles, 256, 0, ki, n, shift, hist.get(), tiles);
-    exclusive_scan_u32(hist.get(), hist.get(), (size_t)NB * tiles);
+    {
+      ProfScope pk("k_rs_hist", (double)n * 4.0);
+      CPB_LAUNCH(k_rs_hist<DB>, tiles, 256, 0, ki, n, shift, hist.get(), tiles);
+    }
+    {
+      ProfScope pk("rs_scan", (double)NB * tiles * 8.0);
+      exclusive_scan_u32(hist.get(), hist.get(), (size_t)NB * tiles);
+    }
     {
       ProfScope pk("k_rs_scatter", (double)n * 16.0);  // read + write one (key, payload) pair per element
       CPB_LAUNCH(k_rs_scatter<DB>, tiles, RS_THREADS, rs_smem<DB>(), ki, vi, ko, vo, n, shift, hist.get(), tiles, (pass == 0 && iota_payload) ? 1 : 0);
