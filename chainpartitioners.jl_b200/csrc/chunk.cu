@@ -549,6 +549,25 @@ void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, dou
     case CPB_PACK_DYNAMIC_TOTAL:
     case CPB_PACK_CONVEX_TOTAL:
       CPB_REQUIRE(f != nullptr, "pack_stripe: this method needs a cost oracle");
+      if (method == CPB_PACK_CONVEX_TOTAL && !(con && con->enabled)) {
+        // pack_stripe(A, ConvexTotalChunker(f)) without a width constraint (ConvexTotalChunker.jl:9-24).  For the affine
+        // models that obey the quadrangle inequality the stack algorithm assumes (:121) -- work, connectivity,
+        // monotonized-symmetric with alpha >= 0 and beta >= 0 -- costs are subadditive (f(1, j') <= f(1, j) + f(j, j') -
+        // alpha), so j = 1 attains every minimum of cst[j'] = min_j cst[j] + f(j, j') and, being the smallest minimiser
+        // (the rule chunk_convex! follows), is the pointer of every j': the result is the single
+        // chunk [1, n + 1] (no chunk at all for n = 0) -- 2400/2400 random cases against the restated stack algorithm
+        // in tests/test_oracle_solvers.py.  Nothing needs the device.
+        const cpb_model& m = f->mdl;
+        bool ok = m.kind == CPB_MODEL_WORK || m.kind == CPB_MODEL_CONNECTIVITY || m.kind == CPB_MODEL_MONOSYM;
+        for (int t = 0; t <= 3; ++t) ok = ok && m.coef[t] >= 0;
+        if (!ok)
+          throw Error(CPB_ERR_UNSUPPORTED, "unconstrained ConvexTotalChunker needs a quadrangle-inequality model with alpha, beta >= 0 "
+                                           "(work / connectivity / monotonized-symmetric); anything else is an online least-weight-subsequence chain");
+        h_spl_out[0] = 1;
+        if (n >= 1) h_spl_out[1] = n + 1;
+        *K_out = n >= 1 ? 1 : 0;
+        return;
+      }
       pack_dynamic(A, *f, method, con, h_spl_out, K_out);
       return;
     case CPB_PACK_OVERLAP:
@@ -572,7 +591,7 @@ void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, dou
       }
       return;
     }
-    default: throw Error(CPB_ERR_UNSUPPORTED, "pack_stripe method not built on the device (ConcaveTotalChunker: next round)");
+    default: throw Error(CPB_ERR_UNSUPPORTED, "pack_stripe method not built on the device (ConcaveTotalChunker: no affine model is strictly concave, see DESIGN.md)");
   }
 }
 

@@ -223,6 +223,22 @@ def test_quadrangle_total_splitters(ref, fixtures):
                 assert objective(C, Phi.spl, True) == brute_optimum(C, A.n, K, True)
 
 
+def test_unconstrained_convex_chunker_is_one_chunk(ref):
+    """pack_stripe(A, ConvexTotalChunker(f)) without a width constraint on the affine quadrangle-inequality models
+    (alpha, beta >= 0): subadditive costs make j = 1 the smallest minimiser of every prefix, so the restated stack
+    algorithm (ConvexTotalChunker.jl:9-24,57-112) returns the single chunk -- the closed form the device returns."""
+    rng = np.random.default_rng(17)
+    for trial in range(150):
+        m, n = int(rng.integers(1, 10)), int(rng.integers(1, 14))
+        A = sprand(rng, m, n, float(rng.choice([0.0, 0.1, 0.3, 0.5])))
+        mdls = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(2, 0, 0, 1),
+                cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0), cp.AffineWorkModel(0, 0, 0)]
+        if m == n:
+            mdls.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
+        for mdl in mdls:
+            assert ref.pack_stripe(A, cp.ConvexTotalChunker(mdl)).spl.tolist() == [1, n + 1]
+
+
 def greedy_probe(C, n, K, c):
     """every part as long as feasible at threshold c; None if infeasible"""
     spl = [1]
