@@ -375,12 +375,25 @@ def partition_stripe(A, K, method, Pi=None, **kwargs) -> T.SplitPartition:
     return T.SplitPartition(K, spl)
 
 
+_SCRATCH = {}
+
+
+def _scratch(name: str, count: int) -> np.ndarray:
+    buf = _SCRATCH.get(name)
+    if buf is None or buf.size < count:
+        buf = np.empty(max(count, 1024), dtype=I64)
+        _SCRATCH[name] = buf
+    return buf[:count]
+
+
 def pack_stripe(A, method, Pi=None, n_nets=None, **kwargs) -> T.SplitPartition:
     """``pack_stripe(A, method[, Pi]; kwargs...)`` -> ``SplitPartition(K, spl)`` with a free number of chunks."""
     code, spec, rho, w_max = T.pack_method_code(method)
     with _Scoped(A) as dm:
-        spl = np.empty(dm.n + 1, dtype=I64)
-        nn = np.zeros(max(dm.n, 1), dtype=I64)
+        # the ABI wants room for the worst case (n + 1 boundaries): reuse one scratch array across calls instead of
+        # faulting in tens of megabytes per call
+        spl = _scratch("spl", dm.n + 1)
+        nn = _scratch("nn", max(dm.n, 1)) if n_nets is not None else None
         Kout = ctypes.c_int64()
         ocl = None
         con = T.CConstraint()
@@ -389,7 +402,7 @@ def pack_stripe(A, method, Pi=None, n_nets=None, **kwargs) -> T.SplitPartition:
             con = ocl.constraint
         try:
             _check(load_library().cpb_pack_stripe(dm._h, ocl._h if ocl else None, code, ctypes.byref(con), rho, w_max, _p(spl),
-                                                   ctypes.byref(Kout), _p(nn)))
+                                                   ctypes.byref(Kout), _p(nn) if nn is not None else None))
         finally:
             if ocl:
                 ocl.close()

@@ -35,28 +35,38 @@ static unsigned grid_t(size_t n, int threads) { return (unsigned)std::max<size_t
 // ------------------------------------------------------------------------------------------------
 
 // G[r][(c-1)*W + (s-1)] = sum of weights of the points of column c whose link distance c - prev is >= s
-// (s = 1..W).  One thread per column.  wgt == nullptr: unit weights (plain distinct-row counting).
-__global__ void k_window_hist(const u32* __restrict__ pos, const u32* __restrict__ ids, const u32* __restrict__ prev, u32 n, int W, int R,
-                              const i64* __restrict__ wgt /* [R][nids] or null */, u32 nids, i64* __restrict__ G) {
+// (s = 1..W).  One thread per column; the W suffix sums live in registers (WM = W rounded up to 8/16/32/64).
+// wgt == nullptr: unit weights (plain distinct-row counting).
+template <int WM>
+__global__ void __launch_bounds__(128) k_window_hist(const u32* __restrict__ pos, const u32* __restrict__ ids, const u32* __restrict__ prev, u32 n, int W, int R,
+                                                      const i64* __restrict__ wgt /* [R][nids] or null */, u32 nids, i64* __restrict__ G) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t c0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < n; c0 += stride) {
     const u32 c = (u32)c0 + 1;
+    const u32 q0 = pos[c0], q1 = pos[c0 + 1];
     for (int r = 0; r < R; ++r) {
-      i64 h[CH_MAXW];
-      for (int s = 0; s < W; ++s) h[s] = 0;
-      for (u32 q = pos[c0]; q < pos[c0 + 1]; ++q) {
+      i64 h[WM];
+#pragma unroll
+      for (int s = 0; s < WM; ++s) h[s] = 0;
+      for (u32 q = q0; q < q1; ++q) {
         const u32 d = c - prev[q];
-        const int s = (int)min(d, (u32)W);
-        h[s - 1] += wgt ? wgt[(size_t)r * nids + ids[q]] : 1;
+        const i64 w = wgt ? wgt[(size_t)r * nids + ids[q]] : 1;
+#pragma unroll
+        for (int s = 0; s < WM; ++s) h[s] += (d > (u32)s) ? w : 0;  // distance >= s + 1
       }
-      i64 run = 0;
       i64* out = G + ((size_t)r * n + c0) * W;
-      for (int s = W - 1; s >= 0; --s) {
-        run += h[s];
-        out[s] = run;
-      }
+#pragma unroll
+      for (int s = 0; s < WM; ++s)
+        if (s < W) out[s] = h[s];
     }
   }
+}
+static void window_hist(const u32* pos, const u32* ids, const u32* prev, u32 n, int W, int R, const i64* wgt, u32 nids, i64* G) {
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(((size_t)n + 127) / 128, (size_t)ctx().sm_count * 64));
+  if (W <= 8) CPB_LAUNCH(k_window_hist<8>, grid, 128, 0, pos, ids, prev, n, W, R, wgt, nids, G);
+  else if (W <= 16) CPB_LAUNCH(k_window_hist<16>, grid, 128, 0, pos, ids, prev, n, W, R, wgt, nids, G);
+  else if (W <= 32) CPB_LAUNCH(k_window_hist<32>, grid, 128, 0, pos, ids, prev, n, W, R, wgt, nids, G);
+  else CPB_LAUNCH(k_window_hist<64>, grid, 128, 0, pos, ids, prev, n, W, R, wgt, nids, G);
 }
 
 struct TableModel {
@@ -189,6 +199,139 @@ __global__ void __launch_bounds__(128) k_chunk_final(const i64* __restrict__ C, 
   dp_block_run<WM>(C, W, jb + 1, last, x, cst, ptr);
 }
 
+
+// ---- warp-per-block forms (W <= 32) -------------------------------------------------------------------------------
+// The thread-per-block kernels above wait a full memory latency per DP step (ncu: k_chunk_final 1.5 ms, k_chunk_combine
+// 4.3 ms at n = 4M).  Here a warp owns a block: the cost rows are fetched 256 values at a time with coalesced loads, one
+// batch ahead of the chain, and staged in shared memory; lane i < W runs the chain started from the unit state e_i
+// (transfer) or every lane runs the true state (final, lane 0 writes).
+static constexpr int CW_WARPS = 8;
+template <int WM, bool FINAL>
+__global__ void __launch_bounds__(32 * CW_WARPS) k_chunk_warp(const i64* __restrict__ C, u32 n, int W, u32 nblocks, const i64* __restrict__ S,
+                                                             i64* __restrict__ M, i64* __restrict__ cst, u32* __restrict__ ptr) {
+  __shared__ i64 s_rows[CW_WARPS][2][256];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const u32 b = blockIdx.x * CW_WARPS + wi;
+  if (b >= nblocks) return;  // warp-uniform; only __syncwarp below
+  const int RB = 256 / W;    // rows per batch (>= 8 for W <= 32)
+  const u32 jb = 1 + b * CH_BLOCK;
+  const u32 first = jb + 1, last = min(jb + CH_BLOCK, n + 1);
+  i64 x[WM];
+#pragma unroll
+  for (int t = 0; t < WM; ++t) x[t] = FINAL ? (t < W ? S[(size_t)b * W + t] : CH_INF) : ((t == lane) ? 0 : CH_INF);
+  if (FINAL && b == 0 && lane == 0) { cst[1] = 0; ptr[1] = 0; }
+  i64 pre[8];
+  auto fetch = [&](u32 jp0) {  // rows jp0 .. jp0 + RB - 1 (clipped to the block) -> registers
+    const size_t base = (size_t)(jp0 - 1) * W;
+    const u32 total = (u32)min((u32)RB, last - jp0 + 1) * (u32)W;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const u32 idx = (u32)k * 32 + lane;
+      pre[k] = idx < total ? C[base + idx] : CH_INF;
+    }
+  };
+  auto stash = [&](int slot) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_rows[wi][slot][k * 32 + lane] = pre[k];
+  };
+  if (first <= last) {
+    fetch(first);
+    stash(0);
+  }
+  __syncwarp();
+  int slot = 0;
+  for (u32 jp0 = first; jp0 <= last; jp0 += RB, slot ^= 1) {
+    const bool more = (u64)jp0 + RB <= last;
+    if (more) fetch(jp0 + RB);  // in flight while the chain below runs
+    const u32 cnt = min((u32)RB, last - jp0 + 1);
+#pragma unroll 4
+    for (u32 r = 0; r < cnt; ++r) {
+      const i64* row = &s_rows[wi][slot][r * W];
+      // candidates t = W .. 2 only use states that are at least one step old: their minimum is off the critical path;
+      // the chain itself is  best = (x[0] + row[0] < rest) ? x[0] + row[0] : rest.
+      // descending t = ascending j: strict `<` keeps the smallest j (DynamicChunker.jl:45)
+      i64 rest = CH_INF;
+      int rt = 0;
+#pragma unroll
+      for (int t = WM; t >= 2; --t) {
+        if (t <= W) {
+          const i64 c = x[t - 1] + row[t - 1];
+          if (c < rest) { rest = c; rt = t; }
+        }
+      }
+      const i64 c1 = x[0] + row[0];
+      i64 best = rest;
+      int bt = rt;
+      if (c1 < rest) { best = c1; bt = 1; }
+      if (best >= CH_INF) { best = CH_INF; bt = 0; }
+#pragma unroll
+      for (int t = WM - 1; t >= 1; --t) x[t] = x[t - 1];
+      x[0] = best;
+      if (FINAL && lane == 0) {
+        const u32 jp = jp0 + r;
+        cst[jp] = best;
+        ptr[jp] = bt ? jp - bt : 0;
+      }
+    }
+    __syncwarp();  // everyone is done with s_rows[slot ^ 1]'s previous contents (read one iteration ago)
+    if (more) stash(slot ^ 1);
+    __syncwarp();
+  }
+  if (!FINAL && lane < W) {
+    i64* out = M + ((size_t)b * W + lane) * W;
+#pragma unroll
+    for (int t = 0; t < WM; ++t)
+      if (t < W) out[t] = x[t];
+  }
+}
+
+// One warp walks the blocks with the state in registers (lane t holds x[t]).  The whole CTA stages the transfer
+// matrices of CB_CHUNK blocks at a time in shared memory (coalesced), one chunk ahead of the walking warp, so a step
+// costs a few shuffles instead of a memory latency (a one-block look-ahead in registers still paid ~0.5 us per block).
+static constexpr int CB_THREADS = 256;
+template <int WM>
+__global__ void __launch_bounds__(CB_THREADS) k_chunk_combine_warp(const i64* __restrict__ M, u32 nblocks, int W, i64* __restrict__ S) {
+  constexpr int CHUNK_VALS = 2560;  // i64 values per staged chunk (20 KB), two buffers
+  __shared__ i64 s_m[2][CHUNK_VALS];
+  const int tid = threadIdx.x;
+  const u32 per = (u32)W * (u32)W;
+  const u32 cb = max(1u, (u32)CHUNK_VALS / per);  // blocks per chunk
+  const size_t total = (size_t)nblocks * per;
+  auto stage = [&](u32 chunk, int buf, int first_thread) {  // by threads first_thread .. CB_THREADS - 1
+    const size_t base = (size_t)chunk * cb * per;
+    const u32 cnt = (u32)min((size_t)cb * per, total > base ? total - base : (size_t)0);
+    for (u32 i = tid - first_thread; i < cnt; i += CB_THREADS - first_thread) s_m[buf][i] = M[base + i];
+  };
+  const u32 nchunks = (nblocks + cb - 1) / cb;
+  if (nchunks) stage(0, 0, 0);
+  __syncthreads();
+  i64 x = (tid == 0) ? 0 : CH_INF;  // cst[1] = 0, nothing before column 1   (warp 0, lane t holds x[t])
+  for (u32 ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (tid >= 32) {
+      if (ch + 1 < nchunks) stage(ch + 1, buf ^ 1, 32);  // warps 1.. prefetch the next chunk
+    } else {
+      const u32 b0 = ch * cb, b1 = min(nblocks, b0 + cb);
+      for (u32 b = b0; b < b1; ++b) {
+        const i64* Mb = &s_m[buf][(size_t)(b - b0) * per];
+        if (tid < W) S[(size_t)b * W + tid] = x;
+        i64 cand[WM];
+#pragma unroll
+        for (int i = 0; i < WM; ++i) {
+          const i64 xi = __shfl_sync(0xffffffffu, x, i);
+          cand[i] = (i < W && tid < W) ? xi + Mb[i * W + tid] : CH_INF;
+        }
+#pragma unroll
+        for (int span = WM / 2; span >= 1; span >>= 1)  // tree minimum: depth log2(WM) instead of WM
+#pragma unroll
+          for (int i = 0; i < span; ++i) cand[i] = min(cand[i], cand[i + span]);
+        x = cand[0] >= CH_INF ? CH_INF : cand[0];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Float64 costs: re-association would change roundings, so the chain runs in order on one thread
 __global__ void k_chunk_seq_f64(const double* __restrict__ C, u32 n, int W, double* __restrict__ cst, u32* __restrict__ ptr) {
   if (blockIdx.x || threadIdx.x) return;
@@ -236,7 +379,7 @@ __global__ void k_convex_ptr(const T* __restrict__ C, const T* __restrict__ cst,
 // ------------------------------------------------------------------------------------------------
 // chain unravel: nodes 1..n+1, forward pointers nxt[u] in (u, u + W], the chain runs 1 -> n+1
 // ------------------------------------------------------------------------------------------------
-static constexpr int UN_BLOCK = 2048;
+static constexpr int UN_BLOCK = 512;
 
 // DIR = +1: nxt is used as is.  DIR = -1: the chain is given by backward pointers ptr[j'] < j' and is
 // walked in mirrored coordinates u = n + 2 - j'.
@@ -263,6 +406,39 @@ __global__ void k_chain_entries(const u32* __restrict__ exits, int W, u32 nblock
     entry[b] = e;
     if (e == 0xffffffffu) continue;
     e = exits[(size_t)b * W + e];
+  }
+}
+
+// The whole CTA stages the exit tables of many blocks in shared memory, one chunk ahead; thread 0 then resolves a block
+// with one shared-memory read instead of one dependent global read.
+static constexpr int CE_THREADS = 256;
+__global__ void __launch_bounds__(CE_THREADS) k_chain_entries_staged(const u32* __restrict__ exits, int W, u32 nblocks, u32* __restrict__ entry) {
+  constexpr int CHUNK_VALS = 5120;  // 20 KB per buffer
+  __shared__ u32 s_e[2][CHUNK_VALS];
+  const int tid = threadIdx.x;
+  const u32 cb = max(1u, (u32)CHUNK_VALS / (u32)W);
+  const size_t total = (size_t)nblocks * W;
+  auto stage = [&](u32 chunk, int buf, int first_thread) {  // by threads first_thread .. CE_THREADS - 1
+    const size_t base = (size_t)chunk * cb * W;
+    const u32 cnt = (u32)min((size_t)cb * W, total > base ? total - base : (size_t)0);
+    for (u32 i = tid - first_thread; i < cnt; i += CE_THREADS - first_thread) s_e[buf][i] = exits[base + i];
+  };
+  const u32 nchunks = (nblocks + cb - 1) / cb;
+  if (nchunks) stage(0, 0, 0);
+  __syncthreads();
+  u32 e = 0;
+  for (u32 ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (tid != 0) {
+      if (ch + 1 < nchunks) stage(ch + 1, buf ^ 1, 1);
+    } else {
+      const u32 b0 = ch * cb, b1 = min(nblocks, b0 + cb);
+      for (u32 b = b0; b < b1; ++b) {
+        entry[b] = e;
+        if (e != 0xffffffffu) e = s_e[buf][(size_t)(b - b0) * W + e];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -295,7 +471,7 @@ template <int DIR> static i64 unravel_chain(const u32* p, u32 n, int W, int64_t*
   DBuf<u32> exits((size_t)nblocks * W), entry(nblocks), flags((size_t)n + 3), scan((size_t)n + 3);
   flags.zero();
   CPB_LAUNCH(k_chain_exits<DIR>, grid_t((size_t)nblocks * W, 128), 128, 0, p, n, W, nblocks, exits.get());
-  CPB_LAUNCH(k_chain_entries, 1, 32, 0, exits.get(), W, nblocks, entry.get());
+  CPB_LAUNCH(k_chain_entries_staged, 1, CE_THREADS, 0, exits.get(), W, nblocks, entry.get());
   CPB_LAUNCH(k_chain_mark<DIR>, grid_t(nblocks, 128), 128, 0, p, n, nblocks, entry.get(), flags.get());
   exclusive_scan_u32(flags.get(), scan.get(), (size_t)n + 3);
   u32 total = 0;
@@ -415,6 +591,13 @@ template <int WM> static void run_dp_blocks(const i64* C, u32 n, int W, i64* cst
   const u32 nblocks = (u32)(((size_t)n + CH_BLOCK - 1) / CH_BLOCK);
   if (nblocks == 0) return;
   DBuf<i64> M((size_t)nblocks * W * W), S((size_t)nblocks * W);
+  if (WM <= 32 && !std::getenv("CPB_CHUNK_THREAD_BLOCKS")) {
+    const unsigned g = (nblocks + CW_WARPS - 1) / CW_WARPS;
+    CPB_LAUNCH((k_chunk_warp<WM, false>), g, 32 * CW_WARPS, 0, C, n, W, nblocks, (const i64*)nullptr, M.get(), (i64*)nullptr, (u32*)nullptr);
+    CPB_LAUNCH(k_chunk_combine_warp<WM>, 1, CB_THREADS, 0, M.get(), nblocks, W, S.get());
+    CPB_LAUNCH((k_chunk_warp<WM, true>), g, 32 * CW_WARPS, 0, C, n, W, nblocks, S.get(), (i64*)nullptr, cst, ptr);
+    return;
+  }
   CPB_LAUNCH(k_chunk_transfer<WM>, grid_t((size_t)nblocks * W, 128), 128, 0, C, n, W, nblocks, M.get());
   CPB_LAUNCH(k_chunk_combine, 1, CH_MAXW, 0, M.get(), nblocks, W, S.get());
   CPB_LAUNCH(k_chunk_final<WM>, grid_t(nblocks, 128), 128, 0, C, n, W, nblocks, S.get(), cst, ptr);
@@ -452,7 +635,7 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
       DBuf<u32> prev(N), colidx(N);
       compute_prev_links(A.pos.get(), A.row.get(), (u32)A.m, n, N, prev.get(), colidx.get());
       G.alloc((size_t)n * W);
-      CPB_LAUNCH(k_window_hist, grid_for(n), 256, 0, A.pos.get(), A.row.get(), prev.get(), n, W, 1, (const i64*)nullptr, 0u, G.get());
+      window_hist(A.pos.get(), A.row.get(), prev.get(), n, W, 1, (const i64*)nullptr, 0u, G.get());
     } else if (mdl.kind == CPB_MODEL_BLOCK) {
       const int R = mdl.R;
       tm.R = R;
@@ -477,7 +660,7 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
       wgt.alloc((size_t)R * Kp);
       if (Kp) CPB_LAUNCH(k_part_weights, grid_for(Kp), 256, 0, f.pi_size.get(), Kp, R, dbr.get(), U, wgt.get());
       G.alloc((size_t)R * n * W);
-      CPB_LAUNCH(k_window_hist, grid_for(n), 256, 0, pos2.get(), ids.get(), prev.get(), n, W, R, wgt.get(), Kp, G.get());
+      window_hist(pos2.get(), ids.get(), prev.get(), n, W, R, wgt.get(), Kp, G.get());
       CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // hbr goes out of scope
     }
     if (mdl.kind == CPB_MODEL_COLBLOCK || mdl.kind == CPB_MODEL_BLOCK) {

@@ -348,6 +348,17 @@ def test_config4_downscaled(ref):
     assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl)
 
 
+def test_chunk_dp_many_blocks(ref):
+    """n = 2^19 columns: several staged chunks in the blocked (min,+) combine and in the chain unravel (the kernels
+    stage 40 DP blocks / 640 chain blocks at a time in shared memory)."""
+    A = synth.banded(1 << 19, 6)
+    for mtd in [cp.DynamicTotalChunker(cp.AffineConnectivityModel(0, 3, 1, 3), 8),
+                cp.ConvexTotalChunker(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.VertexCount(), 5)),
+                cp.StrictChunker(4)]:
+        g, r = cp.pack_stripe(A, mtd), ref.pack_stripe(A, mtd)
+        assert g.K == r.K and np.array_equal(g.spl, r.spl), type(mtd).__name__
+
+
 def test_torch_generators_match_numpy():
     from chainb200 import synth_torch
 
