@@ -20,7 +20,7 @@ __all__ = [
     "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
-    "launch_count", "probe_cluster_capacity", "bisect_stats", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
+    "launch_count", "probe_cluster_capacity", "bisect_stats", "bisect_plan", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
 ]
 
 I64 = np.int64
@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
-    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_probe_cluster_capacity",
+    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_bisect_plan", "cpb_probe_cluster_capacity",
     "cpb_links_partial", "cpb_oracle_set_links",
 ]
 
@@ -532,6 +532,15 @@ def profile_get() -> dict:
         nm = names.raw[32 * t : 32 * t + 32].split(b"\0", 1)[0].decode()
         out[nm] = dict(ms=ms[t], launches=int(launches[t]), bytes=nbytes[t])
     return out
+
+
+def bisect_plan(c_lo: float, c_hi: float, eps: float, nodes: int, c_lo0: float = None, c_hi0: float = None, upper_bound: float = 0.0):
+    """Heap indices of the bisection-tree nodes one round probes concurrently (``cpb_bisect_plan``; host-only)."""
+    ids = (ctypes.c_int32 * nodes)()
+    lib = load_library()
+    lib.cpb_bisect_plan.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    _check(lib.cpb_bisect_plan(c_lo, c_hi, eps, nodes, c_lo if c_lo0 is None else c_lo0, c_hi if c_hi0 is None else c_hi0, upper_bound, ids))
+    return [int(x) for x in ids]
 
 
 def bisect_stats() -> dict:

@@ -618,52 +618,62 @@ struct BisectRun {
 
 // Prior over the optimal bottleneck c*: log-uniform over the initial bracket, mixed with a log-uniform bump just below
 // the heuristic upper bound when one is known.  A tree node is reached by the walk iff c* lies in its (c_lo, c_hi].
-static double prior_mass(const BisectRun& run, double lo, double hi) {
+struct PlanPrior {
+  double c_lo0, c_hi0, ub;  // initial bracket, planner's upper bound (0 = none)
+};
+static double prior_mass(const PlanPrior& pr, double lo, double hi) {
   auto lu = [](double lo, double hi, double a, double b) {
     lo = std::max(lo, a);
     hi = std::min(hi, b);
     return (hi > lo && a > 0 && b > a) ? (std::log(hi) - std::log(lo)) / (std::log(b) - std::log(a)) : 0.0;
   };
-  if (!(run.c_lo0 > 0) || !(run.c_hi0 > run.c_lo0)) return hi - lo;
-  if (!(run.ub > run.c_lo0)) return lu(lo, hi, run.c_lo0, run.c_hi0);
+  if (!(pr.c_lo0 > 0) || !(pr.c_hi0 > pr.c_lo0)) return hi - lo;
+  if (!(pr.ub > pr.c_lo0)) return lu(lo, hi, pr.c_lo0, pr.c_hi0);
   // the bound is the bottleneck of an actual partition, so c* <= ub: no mass above it.  Most of the mass sits just
   // below the bound (on near-uniform matrices the bounding partition is within a percent of the optimum).
-  const double top = std::min(run.ub * (1 + 1e-9), run.c_hi0);
-  return 0.1 * lu(lo, hi, run.c_lo0, top) + 0.3 * lu(lo, hi, std::max(run.ub / 1.5, run.c_lo0), top) +
-         0.6 * lu(lo, hi, std::max(run.ub / 1.03, run.c_lo0), top);
+  const double top = std::min(pr.ub * (1 + 1e-9), pr.c_hi0);
+  return 0.1 * lu(lo, hi, pr.c_lo0, top) + 0.3 * lu(lo, hi, std::max(pr.ub / 1.5, pr.c_lo0), top) +
+         0.6 * lu(lo, hi, std::max(pr.ub / 1.03, pr.c_lo0), top);
 }
 
-// Chooses the P tree nodes of the next round: greedily those the sequential loop is most likely to visit (a node's
-// probability is the prior mass of its bracket; a parent's bracket contains its children's, so the set is a subtree
-// containing the root).  With a flat prior this is the complete tree in heap order.  Every rank computes the same plan
-// from the same state.  The plan only decides what is probed speculatively -- the thresholds themselves and the walk
-// are the reference's sequence.
+// Chooses the P tree nodes of the next round (heap indices, -1 = unused slot): greedily those the sequential loop is
+// most likely to visit (a node's probability is the prior mass of its bracket; a parent's bracket contains its
+// children's, so the set is a subtree containing the root).  With a flat prior this is the complete tree in heap order.
+// Pure host arithmetic: every rank computes the same plan from the same state.  The plan only decides what is probed
+// speculatively -- the thresholds themselves and the walk are the reference's sequence.
+void bisect_plan_nodes(double c_lo, double c_hi, double eps, int P, double c_lo0, double c_hi0, double ub, bool adaptive, int* ids_out) {
+  int count = 0;
+  if (!adaptive) {
+    for (int t = 0; t < P; ++t) ids_out[count++] = t;
+    return;
+  }
+  const double eps1 = 1 + eps;
+  const PlanPrior pr{c_lo0, c_hi0, ub};
+  struct Cand { double mass; int depth; int heap; double lo, hi; };
+  auto worse = [](const Cand& a, const Cand& b) {
+    if (a.mass != b.mass) return a.mass < b.mass;
+    if (a.depth != b.depth) return a.depth > b.depth;
+    return a.heap > b.heap;
+  };
+  std::priority_queue<Cand, std::vector<Cand>, decltype(worse)> pq(worse);
+  pq.push({prior_mass(pr, c_lo, c_hi), 0, 0, c_lo, c_hi});
+  while (!pq.empty() && count < P) {
+    const Cand x = pq.top();
+    pq.pop();
+    if (!(x.lo * eps1 < x.hi)) continue;  // the loop stops here: nothing to probe
+    ids_out[count++] = x.heap;
+    if (x.depth + 1 > BS_MAX_DEPTH) continue;
+    const double c = (x.lo + x.hi) / 2;
+    pq.push({prior_mass(pr, x.lo, c), x.depth + 1, 2 * x.heap + 1, x.lo, c});  // feasible: c_hi = c
+    pq.push({prior_mass(pr, c, x.hi), x.depth + 1, 2 * x.heap + 2, c, x.hi});  // infeasible: c_lo = c
+  }
+  while (count < P) ids_out[count++] = -1;  // unused slots (never matched by the walk)
+}
+
 static void plan_round(BisectRun& run) {
   const int P = run.P;
-  run.h_ids.clear();
-  if (!run.adaptive) {
-    for (int t = 0; t < P; ++t) run.h_ids.push_back(t);
-  } else {
-    struct Cand { double mass; int depth; int heap; double lo, hi; };
-    auto worse = [](const Cand& a, const Cand& b) {
-      if (a.mass != b.mass) return a.mass < b.mass;
-      if (a.depth != b.depth) return a.depth > b.depth;
-      return a.heap > b.heap;
-    };
-    std::priority_queue<Cand, std::vector<Cand>, decltype(worse)> pq(worse);
-    pq.push({prior_mass(run, run.h_st.c_lo, run.h_st.c_hi), 0, 0, run.h_st.c_lo, run.h_st.c_hi});
-    while (!pq.empty() && (int)run.h_ids.size() < P) {
-      const Cand x = pq.top();
-      pq.pop();
-      if (!(x.lo * run.eps1 < x.hi)) continue;  // the loop stops here: nothing to probe
-      run.h_ids.push_back(x.heap);
-      if (x.depth + 1 > BS_MAX_DEPTH) continue;
-      const double c = (x.lo + x.hi) / 2;
-      pq.push({prior_mass(run, x.lo, c), x.depth + 1, 2 * x.heap + 1, x.lo, c});  // feasible: c_hi = c
-      pq.push({prior_mass(run, c, x.hi), x.depth + 1, 2 * x.heap + 2, c, x.hi});  // infeasible: c_lo = c
-    }
-    while ((int)run.h_ids.size() < P) run.h_ids.push_back(-1);  // unused slots (never matched by the walk)
-  }
+  run.h_ids.assign(P, -1);
+  bisect_plan_nodes(run.h_st.c_lo, run.h_st.c_hi, run.eps, P, run.c_lo0, run.c_hi0, run.ub, run.adaptive, run.h_ids.data());
   CPB_CUDA(cudaMemcpyAsync(run.ids.get(), run.h_ids.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, ctx().stream));
   run.planned = true;
 }

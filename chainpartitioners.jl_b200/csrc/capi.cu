@@ -414,6 +414,13 @@ int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out) {
   CPB_API_END
 }
 
+int cpb_bisect_plan(double c_lo, double c_hi, double eps, int nodes, double c_lo0, double c_hi0, double upper_bound, int32_t* ids_out) {
+  CPB_API_BEGIN
+  CPB_REQUIRE(ids_out && nodes >= 1 && nodes <= 255, "bad plan request");
+  bisect_plan_nodes(c_lo, c_hi, eps, nodes, c_lo0, c_hi0, upper_bound, true, ids_out);
+  CPB_API_END
+}
+
 int cpb_bisect_stats(double out[8]) {
   CPB_API_BEGIN
   CPB_REQUIRE(out, "NULL argument");

@@ -171,6 +171,12 @@ int cpb_bisect_probe(cpb_bisect* b, int node_lo, int node_hi);
 int cpb_probe_cluster_capacity(int streaming, int* out);
 int cpb_bisect_advance(cpb_bisect* b, int* done_out);
 int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out);
+/* The speculation plan of one round, as a pure host computation (no device needed): the `nodes` nodes (heap indices in
+ * the bisection tree, root = 0, left child 2i+1 = "probe i was feasible"; -1 = unused slot) that are probed concurrently
+ * when the bracket is (c_lo, c_hi], the initial bracket was (c_lo0, c_hi0] and `upper_bound` (0 = unknown) bounds the
+ * optimum from above.  The set always contains the root and is closed under taking parents; which nodes are in it never
+ * changes the result, only how many rounds the bisection needs. */
+int cpb_bisect_plan(double c_lo, double c_hi, double eps, int nodes, double c_lo0, double c_hi0, double upper_bound, int32_t* ids_out);
 /* Diagnostics of the most recently finished bisection of this process: out[0] = rounds (batches of concurrent
  * probes), out[1] = probes the sequential loop of the reference would have run, out[2] = thresholds probed
  * speculatively in total, out[3] = initial c_lo, out[4] = initial c_hi, out[5] = the planner's upper bound (0 = none), out[6] = final c_lo,
