@@ -208,7 +208,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
                    int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c,
                    const int* __restrict__ node_ids, int node_base) {
-  __shared__ u32 s_mask[SP_GROUPS * 4 + 4];
+  __shared__ __align__(16) u32 s_mask[SP_GROUPS * 4 + 4];
   __shared__ u32 s_cum[SP_GROUPS + 1];
   __shared__ double s_c;
   __shared__ int s_valid;
@@ -273,26 +273,47 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       // ---- bit masks of `prev < j`: each warp owns nv consecutive 128-element groups (one warp-wide 128-bit load and
       //      4 ballots per group) and keeps the running count of its own groups ----
       u32 wsum = 0;
+      // (the ballot phase is issue-bound -- an experiment with the loads removed still spent 4.9 k of its 7.9 k cycles
+      //  here -- so groups that lie entirely inside [e0, Ne) take a path without the head / tail predicates, and one
+      //  lane stores the four masks with a single 128-bit store)
+      // all loads of the super-step are issued before the first ballot (one exposed memory latency instead of nv)
+      uint4 pv[SP_VEC];
+#pragma unroll
+      for (int v = 0; v < SP_VEC; ++v) {
+        pv[v] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // (beyond the end: never counted)
+        if (v < (int)nv) {
+          const u32 idx = e_c + (warp * nv + v) * 128 + lane * 4;
+          if ((u64)idx + 4 <= Ne) {
+            pv[v] = __ldg(reinterpret_cast<const uint4*>(s.prev + idx));
+          } else {
+            if (idx < Ne) pv[v].x = __ldg(s.prev + idx);
+            if (idx + 1 < Ne) pv[v].y = __ldg(s.prev + idx + 1);
+            if (idx + 2 < Ne) pv[v].z = __ldg(s.prev + idx + 2);
+          }
+        }
+      }
 #pragma unroll
       for (int v = 0; v < SP_VEC; ++v) {
         if (v >= (int)nv) break;
         const u32 g = warp * nv + v;
-        const u32 idx = e_c + g * 128 + lane * 4;
-        uint4 pv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // (beyond the end: never counted)
-        if ((u64)idx + 4 <= Ne) {
-          pv = __ldg(reinterpret_cast<const uint4*>(s.prev + idx));
-        } else {
-          if (idx < Ne) pv.x = __ldg(s.prev + idx);
-          if (idx + 1 < Ne) pv.y = __ldg(s.prev + idx + 1);
-          if (idx + 2 < Ne) pv.z = __ldg(s.prev + idx + 2);
+        const u32 gbase = e_c + g * 128;  // first element of the group (warp-uniform)
+        unsigned m0, m1, m2, m3;
+        if (gbase >= e0) {
+          m0 = __ballot_sync(0xffffffffu, pv[v].x <= e0);
+          m1 = __ballot_sync(0xffffffffu, pv[v].y <= e0);
+          m2 = __ballot_sync(0xffffffffu, pv[v].z <= e0);
+          m3 = __ballot_sync(0xffffffffu, pv[v].w <= e0);
+        } else {  // the group holding the part's first element: mask what lies in front of it
+          const u32 idx = gbase + lane * 4;
+          m0 = __ballot_sync(0xffffffffu, pv[v].x <= e0 && idx + 0 >= e0);
+          m1 = __ballot_sync(0xffffffffu, pv[v].y <= e0 && idx + 1 >= e0);
+          m2 = __ballot_sync(0xffffffffu, pv[v].z <= e0 && idx + 2 >= e0);
+          m3 = __ballot_sync(0xffffffffu, pv[v].w <= e0 && idx + 3 >= e0);
         }
-        const bool head = idx < e0;  // only the first few elements of the first tile
-        const unsigned m0 = __ballot_sync(0xffffffffu, pv.x <= e0 && !(head && idx + 0 < e0));
-        const unsigned m1 = __ballot_sync(0xffffffffu, pv.y <= e0 && !(head && idx + 1 < e0));
-        const unsigned m2 = __ballot_sync(0xffffffffu, pv.z <= e0 && !(head && idx + 2 < e0));
-        const unsigned m3 = __ballot_sync(0xffffffffu, pv.w <= e0 && !(head && idx + 3 < e0));
-        if (lane < 4) s_mask[g * 4 + lane] = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
-        if (lane == 4) s_cum[g] = wsum;  // prefix inside the warp's run; the warp's base is added after the barrier
+        if (lane == 0) {
+          *reinterpret_cast<uint4*>(&s_mask[g * 4]) = make_uint4(m0, m1, m2, m3);
+          s_cum[g] = wsum;  // prefix inside the warp's run; the warp's base is added after the barrier
+        }
         wsum += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
       }
       if (lane == 0) s_wtot[warp] = wsum;
