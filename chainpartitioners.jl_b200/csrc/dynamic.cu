@@ -169,11 +169,20 @@ __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ Dev
   }
 }
 
-// weight-constrained layer (DynamicSplitter.jl:206-247) for weights w = a + b_v (j' - j): the feasible
-// predecessors of j' are the window [max(lo_prev, j' - W), min(j', hi_prev)]; rightmost argmin (`<=`).
+// weight-constrained layer (DynamicSplitter.jl:206-247) for weights w(j, j') = a + b_v (j' - j) + b_p (pos[j'] - pos[j])
+// with b_v, b_p >= 0: the feasible predecessors of j' are the window [max(lo_prev, j0(j')), min(j', hi_prev)], j0(j') the
+// smallest j with w(j, j') <= w_max (the reference advances j0 monotonically, :231-233; here a binary search, or
+// j' - W when there is no pin term); rightmost argmin (`<=`).
+struct DevWeight {
+  i64 a, bv, bp, w_max;
+};
+__device__ __forceinline__ bool weight_ok(const DevOracle& o, const DevWeight& w, u32 j, u32 jp) {
+  return w.a + (i64)(jp - j) * w.bv + ((i64)__ldg(o.pos + (jp - 1)) - (i64)__ldg(o.pos + (j - 1))) * w.bp <= w.w_max;
+}
 template <class T>
 __global__ void __launch_bounds__(256) k_dp_constrained(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
-                                                        u32* __restrict__ ptr, int total, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, u32 W, int first) {
+                                                        u32* __restrict__ ptr, int total, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, u32 W, int first,
+                                                        DevWeight wt) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + lo_k; t <= hi_k; t += stride) {
     const u32 jp = (u32)t;
@@ -182,8 +191,16 @@ __global__ void __launch_bounds__(256) k_dp_constrained(const __grid_constant__ 
       ptr[jp] = 1;
       continue;
     }
-    const u32 j0 = max(lo_p, jp > W ? jp - W : 1u);
+    u32 j0 = max(lo_p, jp > W ? jp - W : 1u);
     const u32 j1 = min(jp, hi_p);
+    if (wt.bp != 0) {  // smallest j in [j0, jp] with w(j, j') <= w_max (w shrinks as j grows)
+      u32 a = j0, b = jp;
+      while (a < b) {
+        const u32 mid = a + ((b - a) >> 1);
+        if (weight_ok(o, wt, mid, jp)) b = mid; else a = mid + 1;
+      }
+      j0 = a;
+    }
     T best = 0;
     u32 arg = 0;
     for (u32 j = j0; j <= j1; ++j) {
@@ -254,14 +271,44 @@ template <class T, int TIE> static void dynamic_T(Oracle& f, bool total, i64 K, 
 template <class T> static void dynamic_constrained_T(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
   const Matrix& A = *f.A;
   const i64 n = A.n;
-  CPB_REQUIRE(con->w_coef[2] == 0 && con->w_coef[1] >= 1 && con->w_coef[0] >= 0,
-              "constrained dynamic splitters on the device need a vertex-count weight (VertexCount or AffineWorkModel(a, b_v >= 1, 0))");
-  const i64 W = (con->w_max - con->w_coef[0]) / con->w_coef[1];  // widest feasible part (may be <= 0)
-  // column_constraints (DynamicSplitter.jl:144-173) in closed form for this weight
+  CPB_REQUIRE(con->w_coef[1] >= 0 && con->w_coef[2] >= 0 && con->w_coef[1] + con->w_coef[2] >= 1 && con->w_coef[0] >= 0,
+              "constrained dynamic splitters on the device need a weight that grows with the part (VertexCount or AffineWorkModel(a >= 0, b_v >= 0, b_p >= 0))");
+  const i64 wa = con->w_coef[0], wbv = con->w_coef[1], wbp = con->w_coef[2], w_max = con->w_max;
+  // widest part the vertex term alone allows (no pin term: exactly the window; with a pin term: an upper bound)
+  const i64 W = wbv > 0 ? (w_max - wa) / wbv : n;
+  // column_constraints (DynamicSplitter.jl:144-173): greedy chains from both ends.  The `while` loops of the reference
+  // are binary searches here because w is monotone in both arguments.
+  std::vector<u32> hpos;
+  if (wbp != 0) {
+    hpos.resize((size_t)n + 1);
+    CPB_CUDA(cudaMemcpyAsync(hpos.data(), A.pos.get(), ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  }
+  auto fits = [&](i64 j, i64 jp) {  // w(j, j') <= w_max, 1-based
+    i64 w = wa + (jp - j) * wbv;
+    if (wbp != 0) w += ((i64)hpos[jp - 1] - (i64)hpos[j - 1]) * wbp;
+    return w <= w_max;
+  };
   std::vector<i64> lo(K + 1), hi(K + 1);
-  for (i64 k = K, jp = n + 1; k >= 1; --k) { lo[k] = jp; jp = std::max<i64>(1, jp - std::max<i64>(W, 0)); }
-  for (i64 k = 1, j = 1; k <= K; ++k) { hi[k] = std::min<i64>(n + 1, j + std::max<i64>(W, 0)); j = hi[k]; }
-  if (con->w_coef[0] > con->w_max) { for (i64 k = 1; k <= K; ++k) hi[k] = 1; }  // not even the empty part is feasible
+  for (i64 k = K, jp = n + 1; k >= 1; --k) {
+    lo[k] = jp;
+    i64 a = 1, b = jp;  // smallest j in [1, jp] that fits (j = jp always "fits" in the reference's loop: it never tests it)
+    while (a < b) {
+      const i64 mid = a + (b - a) / 2;
+      if (fits(mid, jp)) b = mid; else a = mid + 1;
+    }
+    jp = a;
+  }
+  for (i64 k = 1, j = 1; k <= K; ++k) {
+    i64 a = j, b = n + 1;  // largest jp in [j, n + 1] that fits (jp = j is never tested by the reference either)
+    while (a < b) {
+      const i64 mid = a + (b - a + 1) / 2;
+      if (fits(j, mid)) a = mid; else b = mid - 1;
+    }
+    hi[k] = a;
+    j = a;
+  }
+  if (wa > w_max) { for (i64 k = 1; k <= K; ++k) hi[k] = 1; }  // not even the empty part is feasible
   if (hi[K] < n + 1) {  // :217-222 infeasible -> degenerate partition
     for (i64 k = 0; k < K; ++k) h_spl_out[k] = 1;
     h_spl_out[K] = n + 1;
@@ -279,7 +326,8 @@ template <class T> static void dynamic_constrained_T(Oracle& f, bool total, cons
     const size_t cnt = (size_t)(hi[k] - lo[k] + 1);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt + 255) / 256, (size_t)ctx().sm_count * 8));
     CPB_LAUNCH(k_dp_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, total ? 1 : 0, (u32)lo[k], (u32)hi[k],
-               (u32)(k > 1 ? lo[k - 1] : 1), (u32)(k > 1 ? hi[k - 1] : 1), (u32)std::max<i64>(W, 0), k == 1 ? 1 : 0);
+               (u32)(k > 1 ? lo[k - 1] : 1), (u32)(k > 1 ? hi[k - 1] : 1), (u32)std::min<i64>(std::max<i64>(W, 0), n + 1), k == 1 ? 1 : 0,
+               DevWeight{wa, wbv, wbp, w_max});
     std::swap(prev, cur);
   }
   CPB_LAUNCH(k_dp_unravel, 1, 32, 0, ptr.get(), n2, (int)K, n1, spl.get());

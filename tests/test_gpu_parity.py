@@ -388,7 +388,10 @@ def test_constrained_dynamic_splitters(ref, fixtures):
     for A in mats:
         for f in [cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0)]:
             for w, w_max in [(cp.AffineWorkModel(0, 1, 0), 2), (cp.AffineWorkModel(0, 1, 0), 4), (cp.VertexCount(), 8), (cp.AffineWorkModel(1, 2, 0), 9),
-                             (cp.AffineWorkModel(5, 1, 0), 3)]:
+                             (cp.AffineWorkModel(5, 1, 0), 3),
+                             # weights with a pin term: windows follow the column lengths (binary searches on pos)
+                             (cp.AffineWorkModel(0, 1, 1), 12), (cp.AffineWorkModel(0, 0, 1), 9), (cp.AffineWorkModel(2, 1, 2), 40),
+                             (cp.AffineWorkModel(0, 0, 1), 2)]:
                 for K in [1, 2, 3, 4, 8, 60]:
                     for mk in (cp.DynamicTotalSplitter, cp.DynamicBottleneckSplitter):
                         mtd = mk(cp.ConstrainedCost(f, w, w_max))

@@ -239,6 +239,31 @@ def test_unconstrained_convex_chunker_is_one_chunk(ref):
             assert ref.pack_stripe(A, cp.ConvexTotalChunker(mdl)).spl.tolist() == [1, n + 1]
 
 
+def test_dynamic_splitter_constrained_pin_weights(ref):
+    """DynamicSplitter.jl:206-247 with a weight that counts pins (AffineWorkModel(a, b_v, b_p) as the weight oracle):
+    optimum among weight-feasible partitions, or the degenerate partition."""
+    rng = np.random.default_rng(18)
+    for n in [1, 4, 7, 11]:
+        A = sprand(rng, 6, n, 0.4)
+        mdl = cp.AffineConnectivityModel(0, 1, 0, 2)
+        C = cost_matrix(mdl, A)
+        for (a, bv, bp), w_max in [((0, 1, 1), 6), ((0, 0, 1), 4), ((1, 1, 2), 12)]:
+            Cw = C.copy()
+            for j in range(1, n + 2):
+                for jp in range(j, n + 2):
+                    if a + bv * (jp - j) + bp * int(A.colptr[jp - 1] - A.colptr[j - 1]) > w_max:
+                        Cw[j, jp] = np.inf
+            for K in [1, 2, 3, 5]:
+                for total, S in [(True, cp.DynamicTotalSplitter), (False, cp.DynamicBottleneckSplitter)]:
+                    Phi = ref.partition_stripe(A, K, S(cp.ConstrainedCost(mdl, cp.AffineWorkModel(a, bv, bp), w_max)))
+                    opt = brute_optimum(Cw, n, K, total)
+                    if np.isinf(opt):
+                        assert Phi.spl.tolist() == [1] * K + [n + 1]
+                    else:
+                        check_split(Phi.spl, n, K)
+                        assert objective(Cw, Phi.spl, total) == opt
+
+
 def greedy_probe(C, n, K, c):
     """every part as long as feasible at threshold c; None if infeasible"""
     spl = [1]
