@@ -607,7 +607,7 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
   const u32 n = (u32)A.n;
   const size_t N = (size_t)A.N;
   const cpb_model& mdl = f.mdl;
-  CPB_REQUIRE(con && con->enabled, "the device chunk DP needs a width constraint ConstrainedCost(f, w, w_max) (unconstrained: not built yet)");
+  CPB_REQUIRE(con && con->enabled, "the device chunk DP needs a width constraint ConstrainedCost(f, w, w_max) (unconstrained block-cost chunking is an O(n^2) chain: not built)");
   CPB_REQUIRE(con->w_coef[1] >= 1 && con->w_coef[2] >= 0 && con->w_coef[0] >= 0, "weight must grow with the vertex count (VertexCount or AffineWorkModel(0, b_v >= 1, b_p >= 0))");
   if (n == 0) { h_spl_out[0] = 1; *K_out = 0; return; }
   const i64 Wl = std::min<i64>(n, (con->w_max - con->w_coef[0]) / con->w_coef[1]);
@@ -732,19 +732,20 @@ void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, dou
     case CPB_PACK_DYNAMIC_TOTAL:
     case CPB_PACK_CONVEX_TOTAL:
       CPB_REQUIRE(f != nullptr, "pack_stripe: this method needs a cost oracle");
-      if (method == CPB_PACK_CONVEX_TOTAL && !(con && con->enabled)) {
-        // pack_stripe(A, ConvexTotalChunker(f)) without a width constraint (ConvexTotalChunker.jl:9-24).  For the affine
+      if (!(con && con->enabled) && f->mdl.kind != CPB_MODEL_BLOCK && f->mdl.kind != CPB_MODEL_COLBLOCK) {
+        // pack_stripe(A, ConvexTotalChunker(f)) (ConvexTotalChunker.jl:9-24) and pack_stripe(A, DynamicTotalChunker(f))
+        // (DynamicChunker.jl:15-56 with the FeasibleCost sentinel) without a width constraint.  For the affine
         // models that obey the quadrangle inequality the stack algorithm assumes (:121) -- work, connectivity,
         // monotonized-symmetric with alpha >= 0 and beta >= 0 -- costs are subadditive (f(1, j') <= f(1, j) + f(j, j') -
         // alpha), so j = 1 attains every minimum of cst[j'] = min_j cst[j] + f(j, j') and, being the smallest minimiser
-        // (the rule chunk_convex! follows), is the pointer of every j': the result is the single
-        // chunk [1, n + 1] (no chunk at all for n = 0) -- 2400/2400 random cases against the restated stack algorithm
-        // in tests/test_oracle_solvers.py.  Nothing needs the device.
+        // (the rule chunk_convex! follows, SURVEY.md App. B, and the `<` of DynamicChunker.jl:45), is the pointer of every
+        // j': the result is the single chunk [1, n + 1] (no chunk at all for n = 0) -- 2400/2400 and 1500/1500 random
+        // cases against the restated algorithms in tests/test_oracle_solvers.py.  Nothing needs the device.
         const cpb_model& m = f->mdl;
         bool ok = m.kind == CPB_MODEL_WORK || m.kind == CPB_MODEL_CONNECTIVITY || m.kind == CPB_MODEL_MONOSYM;
         for (int t = 0; t <= 3; ++t) ok = ok && m.coef[t] >= 0;
         if (!ok)
-          throw Error(CPB_ERR_UNSUPPORTED, "unconstrained ConvexTotalChunker needs a quadrangle-inequality model with alpha, beta >= 0 "
+          throw Error(CPB_ERR_UNSUPPORTED, "unconstrained Convex/DynamicTotalChunker needs a subadditive affine model with alpha, beta >= 0 "
                                            "(work / connectivity / monotonized-symmetric); anything else is an online least-weight-subsequence chain");
         h_spl_out[0] = 1;
         if (n >= 1) h_spl_out[1] = n + 1;

@@ -435,8 +435,9 @@ def test_unconstrained_convex_chunker(ref, fixtures):
     rng = np.random.default_rng(303)
     for A in [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 10, 0.3), sprand(rng, 5, 1, 0.5), synth.erdos_renyi(2000, 5)]:
         for f in [cp.AffineConnectivityModel(0, 3, 1, 3), AFF, cp.AffineWorkModel(2, 10, 1), cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0)]:
-            g, r = cp.pack_stripe(A, cp.ConvexTotalChunker(f)), ref.pack_stripe(A, cp.ConvexTotalChunker(f))
-            assert g.K == r.K and np.array_equal(g.spl, r.spl), (A, f, g.spl, r.spl)
+            for mk in (cp.ConvexTotalChunker, cp.DynamicTotalChunker):
+                g, r = cp.pack_stripe(A, mk(f)), ref.pack_stripe(A, mk(f))
+                assert g.K == r.K and np.array_equal(g.spl, r.spl), (A, f, mk.__name__, g.spl, r.spl)
     with pytest.raises(cp.CpbError):
         cp.pack_stripe(sprand(rng, 6, 10, 0.3), cp.ConvexTotalChunker(cp.AffineConnectivityModel(-1, 3, 1, 3)))
 

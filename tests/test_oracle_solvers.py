@@ -237,6 +237,7 @@ def test_unconstrained_convex_chunker_is_one_chunk(ref):
             mdls.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
         for mdl in mdls:
             assert ref.pack_stripe(A, cp.ConvexTotalChunker(mdl)).spl.tolist() == [1, n + 1]
+            assert ref.pack_stripe(A, cp.DynamicTotalChunker(mdl)).spl.tolist() == [1, n + 1]  # `<` keeps the smallest j too
 
 
 def test_dynamic_splitter_constrained_pin_weights(ref):
