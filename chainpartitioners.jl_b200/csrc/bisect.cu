@@ -142,6 +142,84 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// BisectIndexBottleneckSplitter (BisectIndexBottleneckSplitter.jl:5-81): the EXACT bottleneck splitter.  Candidate
+// thresholds are costs c(spl[k], j') of actual parts; for every part k a binary search over j' keeps the candidates
+// inside [c_lo, c_hi) and tests each with a greedy probe of the remaining parts, searched inside the windows
+// spl_lo / spl_hi left by earlier probes.  The whole control flow runs inside ONE kernel on one 8-CTA cluster (every
+// thread follows the same deterministic sequence; the part searches are the 1024-way cluster searches of
+// k_bisect_round), the windows are hard limits exactly as in the reference, so the split vector is the reference's.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
+    k_bisect_index(const __grid_constant__ DevOracle o, int K, double c_lo, double c_hi, int* __restrict__ spl, int* __restrict__ spl_lo,
+                   int* __restrict__ spl_hi, int* __restrict__ probes_out) {
+  __shared__ int s_cnt[2][BS_CLUSTER];
+  cg::cluster_group cluster = cg::this_cluster();
+  const bool cta0 = cluster.block_rank() == 0;
+  const bool writer = cta0 && threadIdx.x == 0;
+  const i64 n1 = (i64)o.n + 1;
+  if (cta0)
+    for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) {  // :29-37
+      spl_lo[t] = (t == K + 1) ? (int)n1 : 1;
+      spl_hi[t] = (t == 1) ? 1 : (int)n1;
+      spl[t] = (t == 1) ? 1 : (t == K + 1 ? (int)n1 : 0);
+    }
+  __threadfence();
+  cluster.sync();
+  int phase = 0, probes = 0;
+  i64 sk = 1;  // spl[k]
+  for (int k = 1; k <= K; ++k) {
+    i64 jp_hi = __ldcg(spl_hi + k + 1);
+    i64 jp_lo = max(sk, (i64)__ldcg(spl_lo + k + 1));
+    while (jp_lo <= jp_hi) {
+      const i64 jp = (jp_lo + jp_hi) >> 1;
+      const T c = dev_cost<T>(o, (u32)sk, (u32)jp);
+      const double cd = (double)c;
+      if (c_lo <= cd && cd < c_hi) {
+        ++probes;
+        bool chk = true;
+        if (writer) spl[k + 1] = (int)jp;
+        i64 j = jp;
+        for (int kk = k + 1; kk <= K - 1; ++kk) {
+          const i64 a = max(j, (i64)__ldcg(spl_lo + kk + 1));
+          const i64 b = __ldcg(spl_hi + kk + 1);
+          // search (:14-27): the largest j' in [a, b] with c(j, j') <= c; b if the window is empty, a - 1 if none fits
+          const i64 r = a > b ? b : wide_search<T>(o, cluster, s_cnt, phase, (u32)j, a, b, cd);
+          if (writer) spl[kk + 1] = (int)r;
+          if (r < j) {
+            chk = false;
+            if (cta0)
+              for (int t = kk + 1 + threadIdx.x; t <= K; t += blockDim.x) spl[t] = (int)j;
+            break;
+          }
+          j = r;
+        }
+        // the last part: [spl[K], spl[K+1])
+        const i64 ls = (k == K) ? sk : j, le = (k == K) ? jp : n1;
+        const bool feas = chk && cost_leq(dev_cost<T>(o, (u32)ls, (u32)le), cd);
+        __syncthreads();  // CTA 0: the writer's spl entries are visible to the copying threads
+        if (feas) { c_hi = cd; jp_hi = jp - 1; } else { c_lo = cd; jp_lo = jp + 1; }
+        if (cta0) {
+          int* dst = feas ? spl_hi : spl_lo;
+          for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) dst[t] = spl[t];
+          __threadfence();
+        }
+        cluster.sync();  // the new window is visible to every CTA before the next search reads it
+      } else if (cd >= c_hi) {
+        jp_hi = jp - 1;
+      } else {
+        jp_lo = jp + 1;
+      }
+    }
+    if (jp_hi < sk) break;
+    if (writer) spl[k + 1] = (int)jp_hi;
+    sk = jp_hi;
+  }
+  if (writer) *probes_out = probes;
+  cluster.sync();  // no CTA may exit while peers can still write into its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------
 // Streaming probe (kernel "probe_stream"): the device form of the reference's lazy probes
 // (LazyBisectCostBottleneckSplitter.jl:194-229 connectivity, :323-359 monotonized symmetric).
 // (Here the link array holds 1 + the CSC POSITION of the previous nonzero of the same row, so "previous column < j"
@@ -908,6 +986,30 @@ int probe_cluster_capacity(bool stream) {
   if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_stream<i64>, &cfg));
   else CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_bisect_round<i64>, &cfg));
   return n;
+}
+
+void solve_bisect_index(Oracle& f, i64 K, int64_t* h_spl_out) {
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
+  const Matrix& A = *f.A;
+  CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
+  oracle_ensure_ranks(f);
+  double bnd[2];
+  oracle_bound(f, K, bnd);  // (c_lo, c_hi) ./ 1 -- also checks beta >= 0, which the monotone part searches need
+  ProfScope prof("probe");
+  DBuf<int> spl(K + 2), spl_lo(K + 2), spl_hi(K + 2), probes(1);
+  if (f.dev.is_float)
+    CPB_LAUNCH(k_bisect_index<double>, BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, bnd[0], bnd[1], spl.get(), spl_lo.get(), spl_hi.get(), probes.get());
+  else
+    CPB_LAUNCH(k_bisect_index<i64>, BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, bnd[0], bnd[1], spl.get(), spl_lo.get(), spl_hi.get(), probes.get());
+  std::vector<int> h(K + 2);
+  int hp = 0;
+  CPB_CUDA(cudaMemcpyAsync(h.data(), spl_hi.get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(&hp, probes.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = h[k];
+  g_bisect_stats[0] = 1; g_bisect_stats[1] = hp; g_bisect_stats[2] = hp;
+  g_bisect_stats[3] = bnd[0]; g_bisect_stats[4] = bnd[1]; g_bisect_stats[5] = 0; g_bisect_stats[6] = 0; g_bisect_stats[7] = 0;
 }
 
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {

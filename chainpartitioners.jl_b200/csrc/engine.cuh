@@ -101,6 +101,7 @@ void count_query(Matrix& A, int which, i64 Q, const i64* d_j, const i64* d_jp, i
 
 // solvers (bisect.cu / dynamic.cu / chunk.cu)
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out);
+void solve_bisect_index(Oracle& f, i64 K, int64_t* h_spl_out);
 int probe_cluster_capacity(bool stream);
 struct BisectRun;
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl);

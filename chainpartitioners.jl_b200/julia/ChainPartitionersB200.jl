@@ -19,7 +19,7 @@ import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_st
     AffineSymmetricConnectivityModel, AffineHyperedgeCutModel, AffineSymmetricEdgeCutModel, AffineEnvelopeModel,
     ColumnBlockComponentCostModel, BlockComponentCostModel, block_component,
     ConstrainedCost, VertexCount, FeasibleCost, SplitPartition,
-    DynamicBottleneckSplitter, DynamicTotalSplitter, BisectCostBottleneckSplitter, LazyBisectCostBottleneckSplitter,
+    DynamicBottleneckSplitter, DynamicTotalSplitter, BisectCostBottleneckSplitter, BisectIndexBottleneckSplitter, LazyBisectCostBottleneckSplitter,
     DynamicBottleneckChunker, DynamicTotalChunker, ConvexTotalChunker, ConvexTotalSplitter, OverlapChunker, StrictChunker, EquiChunker, EquiSplitter
 
 const lib = get(ENV, "CHAINB200_LIB", "libchainb200.so")
@@ -144,6 +144,7 @@ split_code(::DynamicTotalSplitter) = (1, 0.0)
 split_code(m::BisectCostBottleneckSplitter) = (2, Float64(m.ϵ))
 split_code(m::LazyBisectCostBottleneckSplitter) = (3, Float64(m.ϵ))
 split_code(::ConvexTotalSplitter) = (8, 0.0)
+split_code(::BisectIndexBottleneckSplitter) = (12, 0.0)
 split_code(::DynamicBottleneckChunker) = (10, 0.0)   # partition_stripe(A, K, ::AbstractDynamicChunker), DynamicSplitter.jl:52-87
 split_code(::DynamicTotalChunker) = (11, 0.0)
 

@@ -460,6 +460,12 @@ class FlipBisectCostBottleneckSplitter:
 
 
 @dataclass
+class BisectIndexBottleneckSplitter:
+    """BisectIndexBottleneckSplitter.jl:1-3 (exact bottleneck, :5-81)."""
+    f: Any
+
+
+@dataclass
 class LazyBisectCostBottleneckSplitter:
     """LazyBisectCostBottleneckSplitter.jl:1-4."""
     f: Any
@@ -583,7 +589,7 @@ class DisjointPacker:
 SPLIT_DYNAMIC_BOTTLENECK, SPLIT_DYNAMIC_TOTAL, SPLIT_BISECT_COST, SPLIT_LAZY_BISECT_COST = 0, 1, 2, 3
 SPLIT_LAZY_BISECT_GENERIC, SPLIT_EQUI, SPLIT_FLIP_BISECT_COST, SPLIT_LAZY_FLIP_BISECT_COST = 4, 5, 6, 7
 SPLIT_CONVEX_TOTAL, SPLIT_CONCAVE_TOTAL = 8, 9
-SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, SPLIT_DYNAMIC_TOTAL_CHUNKER = 10, 11
+SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, SPLIT_DYNAMIC_TOTAL_CHUNKER, SPLIT_BISECT_INDEX = 10, 11, 12
 PACK_DYNAMIC_TOTAL, PACK_CONVEX_TOTAL, PACK_CONCAVE_TOTAL, PACK_OVERLAP, PACK_STRICT, PACK_EQUI = 0, 1, 2, 3, 4, 5
 
 
@@ -595,6 +601,8 @@ def split_method_code(method) -> Tuple[int, Any, float]:
         return SPLIT_DYNAMIC_TOTAL, method.f, 0.0
     if isinstance(method, BisectCostBottleneckSplitter):
         return SPLIT_BISECT_COST, method.f, float(method.eps)
+    if isinstance(method, BisectIndexBottleneckSplitter):
+        return SPLIT_BISECT_INDEX, method.f, 0.0
     if isinstance(method, FlipBisectCostBottleneckSplitter):
         return SPLIT_FLIP_BISECT_COST, method.f, float(method.eps)
     if isinstance(method, LazyBisectCostBottleneckSplitter):

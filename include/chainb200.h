@@ -136,7 +136,8 @@ enum {
   /* partition_stripe(A, K, ::AbstractDynamicChunker) DynamicSplitter.jl:52-87,249-314: the same K-part recurrence
      and `<=` tie rule as the splitter form with the part index as the inner loop -> identical split vectors */
   CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* partition_stripe(A, K, DynamicBottleneckChunker(f)) */
-  CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11       /* partition_stripe(A, K, DynamicTotalChunker(f)) */
+  CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11,      /* partition_stripe(A, K, DynamicTotalChunker(f)) */
+  CPB_SPLIT_BISECT_INDEX = 12                /* BisectIndexBottleneckSplitter(f): exact bottleneck   BisectIndexBottleneckSplitter.jl:5-81 */
 };
 /* -> spl_out[K+1] (SplitPartition{Int64}(K, spl), Partitions.jl:3-6); con may be NULL. */
 int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out);

@@ -210,6 +210,15 @@ extern "C" int cpo_partition_stripe(int method, const cpo_model* mdl, const cpo_
             quadrangle_total_splitter<F, T>(f, n, K, method == CPO_SPLIT_CONCAVE_TOTAL, spl.data());
           });
           break;
+        case CPO_SPLIT_BISECT_INDEX:
+          with_oracle<T>(mdl, CPO_HINT_SPARSE, M, pi_spl, pi_K, [&](auto& f) {
+            using F = std::remove_reference_t<decltype(f)>;
+            Model<T> m(mdl);
+            bound_stripe<T>(M, K, m, &f, bnd);
+            t1 = now_s();
+            bisect_index<F, T>(f, n, K, bnd, spl.data());
+          });
+          break;
         case CPO_SPLIT_BISECT_COST: case CPO_SPLIT_FLIP_BISECT_COST:
           with_oracle<T>(mdl, CPO_HINT_SPARSE, M, pi_spl, pi_K, [&](auto& f) {
             using F = std::remove_reference_t<decltype(f)>;

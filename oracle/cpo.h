@@ -68,7 +68,8 @@ enum {
   CPO_SPLIT_CONVEX_TOTAL = 8,         /* ConvexTotalChunker.jl:26-55 (ConvexTotalSplitter) */
   CPO_SPLIT_CONCAVE_TOTAL = 9,        /* ConcaveTotalChunker.jl:26-55 (ConcaveTotalSplitter) */
   CPO_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* DynamicSplitter.jl:52-87 with DynamicBottleneckChunker */
-  CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11       /* DynamicSplitter.jl:52-87 with DynamicTotalChunker */
+  CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11,      /* DynamicSplitter.jl:52-87 with DynamicTotalChunker */
+  CPO_SPLIT_BISECT_INDEX = 12                /* BisectIndexBottleneckSplitter.jl:5-81 */
 };
 
 /* pack_stripe methods */

@@ -281,6 +281,67 @@ template <class F, class T> static void bisect_cost(F& f, i64 n, i64 K, double e
   if (n_queries) *n_queries = nq;
 }
 
+// BisectIndexBottleneckSplitter.jl:5-81: the exact bottleneck splitter.  Candidate thresholds are the costs c(spl[k], j')
+// of actual parts; for every part k a binary search over j' keeps the candidates inside (c_lo, c_hi) and tests each with
+// a greedy probe of the remaining parts inside the windows left by earlier probes.
+template <class F, class T> static void bisect_index(F& f, i64 n, i64 K, const double bnd[2], i64* out, i64* n_probes = nullptr) {
+  i64 np = 0;
+  auto search = [&](i64 j, i64 lo, i64 hi, i64 k, T c) -> i64 {  // :14-27
+    lo = std::max(j, lo);
+    while (lo <= hi) {
+      i64 jp = fld2(lo + hi);
+      if (f(j, jp, k) <= c) lo = jp + 1; else hi = jp - 1;
+    }
+    return hi;
+  };
+  ivec spl_lo(K + 2, 1), spl_hi(K + 2, n + 1), spl(K + 2, 0);
+  spl_lo[K + 1] = n + 1;
+  spl_hi[1] = 1;
+  spl[1] = 1;
+  spl[K + 1] = n + 1;
+  // c_lo, c_hi start as Float64 bounds and are then overwritten by costs of type T (Julia re-binds the variables);
+  // mixed comparisons are exact for |c| < 2^53
+  double c_lo = bnd[0], c_hi = bnd[1];
+  for (i64 k = 1; k <= K; ++k) {
+    i64 jp_hi = spl_hi[k + 1];
+    i64 jp_lo = std::max(spl[k], spl_lo[k + 1]);
+    while (jp_lo <= jp_hi) {
+      const i64 jp = fld2(jp_lo + jp_hi);
+      const T c = f(spl[k], jp, k);
+      if (c_lo <= (double)c && (double)c < c_hi) {
+        ++np;
+        bool chk = true;
+        spl[k + 1] = jp;
+        for (i64 kk = k + 1; kk <= K - 1; ++kk) {
+          spl[kk + 1] = search(spl[kk], spl_lo[kk + 1], spl_hi[kk + 1], kk, c);
+          if (spl[kk + 1] < spl[kk]) {
+            chk = false;
+            for (i64 t = kk + 1; t <= K; ++t) spl[t] = spl[kk];
+            break;
+          }
+        }
+        if (chk && f(spl[K], spl[K + 1], K) <= c) {
+          c_hi = (double)c;
+          jp_hi = jp - 1;
+          spl_hi = spl;
+        } else {
+          c_lo = (double)c;
+          jp_lo = jp + 1;
+          spl_lo = spl;
+        }
+      } else if ((double)c >= c_hi) {
+        jp_hi = jp - 1;
+      } else {
+        jp_lo = jp + 1;
+      }
+    }
+    if (jp_hi < spl[k]) break;
+    spl[k + 1] = jp_hi;
+  }
+  for (i64 k = 1; k <= K + 1; ++k) out[k] = spl_hi[k];
+  if (n_probes) *n_probes = np;
+}
+
 // LazyBisectCostBottleneckSplitter.jl:8-70 (generic step-oracle probe)
 template <class F, class T> static void lazy_bisect_generic(F& f, i64 n, i64 K, double eps, const double bnd[2], i64* out) {
   ivec spl(K + 2, 0), spl_hi(K + 2, n + 1);

@@ -442,6 +442,27 @@ def test_unconstrained_convex_chunker(ref, fixtures):
         cp.pack_stripe(sprand(rng, 6, 10, 0.3), cp.ConvexTotalChunker(cp.AffineConnectivityModel(-1, 3, 1, 3)))
 
 
+def test_bisect_index_splitter(ref, fixtures):
+    """partition_stripe(A, K, BisectIndexBottleneckSplitter(f)) (BisectIndexBottleneckSplitter.jl:5-81): the exact
+    bottleneck splitter, one cluster kernel following the reference's control flow; identical split vectors, and the
+    bottleneck equals the DynamicBottleneckSplitter optimum."""
+    rng = np.random.default_rng(304)
+    mats = small_matrices(fixtures)[:10] + [sprand(rng, 40, 200, 0.1), synth.laplacian5(20), synth.erdos_renyi(3000, 6)]
+    for A in mats:
+        fs = [cp.AffineConnectivityModel(0, 3, 1, 3), AFF, cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0.0, 3.0, 1.0, 3.5)]
+        if A.m == A.n:
+            fs.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
+        for f in fs:
+            for K in [1, 2, 3, 8, 33]:
+                mtd = cp.BisectIndexBottleneckSplitter(f)
+                g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                assert np.array_equal(g.spl, r.spl), (A, f, K, g.spl, r.spl)
+    A = synth.erdos_renyi(3000, 6)
+    g = cp.partition_stripe(A, 8, cp.BisectIndexBottleneckSplitter(AFF))
+    d = cp.partition_stripe(A, 8, cp.DynamicBottleneckSplitter(AFF))
+    assert cp.bottleneck_value(A, g, AFF) == cp.bottleneck_value(A, d, AFF)
+
+
 def test_degenerate_inputs(ref):
     """Empty matrices, empty columns/rows, K > n, single column -- the ragged cases."""
     z = np.zeros(0, dtype=np.int64)

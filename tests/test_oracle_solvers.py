@@ -324,6 +324,23 @@ def test_bisect_and_lazy(ref, fixtures, eps):
                     assert got["bisect"] == got["lazy"], (mdl, K, A)
 
 
+def test_bisect_index_is_exact(ref, fixtures):
+    """BisectIndexBottleneckSplitter (BisectIndexBottleneckSplitter.jl:5-81): the reference tests it with tolerance 0
+    against the brute-force optimum (test_Partitioners.jl:101,109-111)."""
+    rng = np.random.default_rng(19)
+    mats = [fixtures["LPnetlib/lpi_itest6"]] + [sprand(rng, int(rng.integers(1, 10)), int(rng.integers(1, 14)), float(rng.choice([0.1, 0.3, 0.5]))) for _ in range(60)]
+    for A in mats:
+        mdls = [cp.AffineWorkModel(0, 10, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(2, 0, 0, 1), cp.AffineConnectivityModel(0.0, 0.5, 1.0, 3.0)]
+        if A.m == A.n:
+            mdls.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
+        for mdl in mdls:
+            C = cost_matrix(mdl, A)
+            for K in [1, 2, 3, 4, 8]:
+                Phi = ref.partition_stripe(A, K, cp.BisectIndexBottleneckSplitter(mdl))
+                check_split(Phi.spl, A.n, K)
+                assert objective(C, Phi.spl, False) == brute_optimum(C, A.n, K, False)
+
+
 def leftmost_chunk_dp(C, n, w_max):
     cst = np.full(n + 2, np.inf)
     cst[1] = 0
