@@ -690,6 +690,37 @@ __global__ void k_ub_max(const __grid_constant__ DevStream s, int is_float, int 
   }
 }
 
+// The same bound for the models probed through the dominance index: parts cut at equal shares of (columns + pins),
+// their costs evaluated with K oracle queries.
+template <class T>
+__global__ void k_ub_index(const __grid_constant__ DevOracle o, int K, double* __restrict__ out) {
+  __shared__ double sm[32];
+  const u32 n1 = o.n + 1;
+  const double N = (double)__ldg(o.pos + o.n), n = (double)o.n;
+  auto weight = [&](u32 x) { return (double)(x - 1) * (N + 1) + (double)__ldg(o.pos + (x - 1)) * (n + 1); };  // x = 1..n+1
+  const double total = weight(n1);
+  auto cut = [&](int k) -> u32 {  // smallest x with weight(x) >= k / K of the total
+    if (k <= 0) return 1u;
+    if (k >= K) return n1;
+    const double target = total * ((double)k / (double)K);
+    u32 lo = 1, hi = n1;
+    while (lo < hi) {
+      const u32 mid = lo + ((hi - lo) >> 1);
+      if (weight(mid) >= target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  double best = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) best = fmax(best, (double)dev_cost<T>(o, cut(k), cut(k + 1)));
+  for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmax(best, sm[w]);
+    out[0] = best;
+  }
+}
+
 // ---- one bisection as a sequence of steps, so that the nodes of a round can be probed by different
 //      ranks (chainb200.parallel.partition_stripe_sharded) ----
 struct BisectRun {
@@ -846,6 +877,16 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     }
   } else {
     oracle_ensure_ranks(f);
+    bool monotone = true;  // the bound is only meaningful for costs that grow with the part (beta >= 0)
+    for (int t = 1; t <= 4; ++t) monotone = monotone && (f.mdl.coef[t] >= 0 || (f.mdl.kind == CPB_MODEL_MONOSYM && t == 4));
+    if (run->adaptive && K >= 2 && A.n >= 1 && monotone && f.dev.kind != CPB_MODEL_COLBLOCK) {
+      ProfScope pk("probe_plan_bound");
+      DBuf<double> ub_out(1);
+      if (f.dev.is_float) CPB_LAUNCH(k_ub_index<double>, 1, 256, 0, f.dev, (int)K, ub_out.get());
+      else CPB_LAUNCH(k_ub_index<i64>, 1, 256, 0, f.dev, (int)K, ub_out.get());
+      CPB_CUDA(cudaMemcpyAsync(&run->ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
   }
   double bnd[2];
   oracle_bound(f, K, bnd);  // (c_lo, c_hi) ./ 1
