@@ -33,9 +33,9 @@ NNZ_PER_COL = 10
 K_PARTS = 64
 EPS = 0.01
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at this workload
-# (profiles/r01_ncu_summary.md: k_probe_stream 45.0 MB read + 0.9 MB write; k_lt_fill 163.3 + 169.8 MB; k_lt_link
-# 116.5 + 40.6 MB; k_lt_count 44.0 MB read; k_rs_scatter 42-82 MB read + 52-56 MB write; k_wm_level 40.05 + 1-3 MB), bytes
-TRAFFIC = {"k_probe_stream": 45.9e6, "k_lt_fill": 333.1e6, "k_lt_link": 157.1e6, "k_lt_count": 44.0e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6}
+# (profiles/r01_ncu_summary.md: k_probe_stream 45.0 MB read + 0.2 MB write; k_lt_fill 79.6 + 37.9 MB; k_lt_link
+# 76.3 + 36.2 MB; k_lt_count 44.0 MB read; k_rs_scatter 42-82 MB read + 52-56 MB write; k_wm_level 40.05 + 1-3 MB), bytes
+TRAFFIC = {"k_probe_stream": 45.2e6, "k_lt_fill": 117.5e6, "k_lt_link": 112.5e6, "k_lt_count": 44.0e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6}
 METRIC = "partition_stripe throughput (BisectCostBottleneckSplitter, Erdos-Renyi 1Mx1M, K=64)"
 UNIT = "partitions/s"
 

@@ -855,7 +855,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
       //  the ~20 us round trip the deferred check saves)
       f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/A.N < ((i64)1 << 25), false, /*as_pos=*/true);
     }
-    const bool want_ub = run->adaptive && K >= 2 && A.n >= 1;
+    const bool want_ub = run->adaptive && K >= 2 && K <= 65535 && A.n >= 1;  // (K is the y extent of the counting grid)
     DBuf<double> ub_out(1);
     for (int attempt = 0; attempt < 2; ++attempt) {
       stream_view(f, run->ds);
