@@ -247,6 +247,38 @@ def test_full_size_properties_config2():
     dA.close()
 
 
+def test_large_inputs_independent_engines_agree(monkeypatch):
+    """Sizes the CPU oracle does not finish in seconds: the streaming probes (link array, k_probe_stream), the
+    dominance-index probes (k_bisect_round) and the exact splitter (k_bisect_index) are three separate device
+    implementations -- the first two must return the same split vector, and the eps-bisection's bottleneck must lie
+    within (1 + eps) of the exact optimum.  R-MAT takes the radix-sort link construction (heavy rows), the others the
+    row-segment form."""
+    from chainb200 import synth_torch
+
+    sym = cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 4)
+    cases = [(synth_torch.rmat(20, 16 << 20), AFF, 256, 0.01), (synth_torch.erdos_renyi(1_000_000, 10), AFF, 64, 0.01),
+             (synth_torch.random_geometric(1 << 20), sym, 128, 0.01), (synth.laplacian5(512), AFF, 100, 0.001)]
+    for A, f, K, eps in cases:
+        dA = cp.device_matrix(A)
+        mtd = cp.LazyBisectCostBottleneckSplitter(f, eps)
+        monkeypatch.delenv("CPB_PROBE_STREAM", raising=False)
+        a = cp.partition_stripe(dA, K, mtd)
+        st = cp.bisect_stats()
+        monkeypatch.setenv("CPB_PROBE_STREAM", "0")
+        b = cp.partition_stripe(dA, K, mtd)
+        monkeypatch.delenv("CPB_PROBE_STREAM", raising=False)
+        assert np.array_equal(a.spl, b.spl), (A.n, K)
+        monkeypatch.setenv("CPB_BISECT_PLAN", "0")  # the complete speculation tree instead of the planned one
+        c = cp.partition_stripe(dA, K, mtd)
+        monkeypatch.delenv("CPB_BISECT_PLAN", raising=False)
+        assert np.array_equal(a.spl, c.spl), (A.n, K)
+        exact = cp.partition_stripe(dA, K, cp.BisectIndexBottleneckSplitter(f))
+        v, v0 = cp.bottleneck_value(dA, a, f), cp.bottleneck_value(dA, exact, f)
+        assert v0 <= v <= v0 * (1 + eps), (A.n, K, v0, v)
+        assert st["c_lo_final"] < v0 <= st["c_hi_final"] or v0 <= st["c_lo"]  # the final bracket holds the optimum
+        dA.close()
+
+
 # ------------------------------------------------------------------------------------------ pack_stripe
 def chunk_matrices(fixtures):
     rng = np.random.default_rng(200)
