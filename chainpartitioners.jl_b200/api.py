@@ -216,7 +216,10 @@ class StripeOracle:
     def query(self, j, jp, k=None) -> np.ndarray:
         j, jp = _arr(np.atleast_1d(j)), _arr(np.atleast_1d(jp))
         out = np.empty(len(j), dtype=np.float64)
-        _check(load_library().cpb_oracle_query(self._h, len(j), _p(j), _p(jp), None, ctypes.c_void_p(out.ctypes.data)))
+        kk = None
+        if k is not None:  # the part index: only the row-partition-aware (primary) models read it
+            kk = _arr(np.broadcast_to(np.atleast_1d(k), j.shape))
+        _check(load_library().cpb_oracle_query(self._h, len(j), _p(j), _p(jp), _p(kk) if kk is not None else None, ctypes.c_void_p(out.ctypes.data)))
         if self.constraint.enabled:  # ConstrainedCostOracle (Costs.jl:141-147)
             w = self.constraint.w_coef
             dm_pos = None

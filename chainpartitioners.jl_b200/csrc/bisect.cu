@@ -65,7 +65,7 @@ __device__ __forceinline__ int node_threshold(const BisectState* __restrict__ st
 // every CTA of the cluster calls it with the same arguments and gets the same answer.
 template <class T>
 __device__ __forceinline__ i64 wide_search(const DevOracle& o, cg::cluster_group& cluster, int (*s_cnt)[BS_CLUSTER], int& phase,
-                                           u32 j, i64 a, i64 b, double c) {
+                                           u32 j, i64 a, i64 b, double c, u32 k) {
   const unsigned crank = cluster.block_rank();
   while (true) {
     const i64 S = b - a + 1;
@@ -73,7 +73,7 @@ __device__ __forceinline__ i64 wide_search(const DevOracle& o, cg::cluster_group
     const i64 stride = (S + BS_WIDTH - 1) / BS_WIDTH;
     const i64 x = a + (i64)(crank * BS_THREADS + threadIdx.x) * stride;
     bool ok = false;
-    if (x <= b) ok = cost_leq(dev_cost<T>(o, j, (u32)x), c);
+    if (x <= b) ok = cost_leq(dev_cost<T>(o, j, (u32)x, k), c);
     const int mine = __syncthreads_count(ok);
     if (threadIdx.x < BS_CLUSTER) {  // push my count into slot [crank] of every CTA of the cluster
       int* remote = cluster.map_shared_rank(&s_cnt[phase][crank], threadIdx.x);
@@ -120,9 +120,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
     i64 a = max(j, (i64)hint_lo[k + 1]);
     i64 b = min((i64)hint_hi[k + 1], n1);
     if (b < a) { a = j; b = n1; }
-    i64 r = wide_search<T>(o, cluster, s_cnt, phase, (u32)j, a, b, c);
-    if (r == a - 1 && a > j) r = wide_search<T>(o, cluster, s_cnt, phase, (u32)j, j, a - 1, c);
-    else if (r == b && b < n1) r = wide_search<T>(o, cluster, s_cnt, phase, (u32)j, b + 1, n1, c);
+    i64 r = wide_search<T>(o, cluster, s_cnt, phase, (u32)j, a, b, c, (u32)k);
+    if (r == a - 1 && a > j) r = wide_search<T>(o, cluster, s_cnt, phase, (u32)j, j, a - 1, c, (u32)k);
+    else if (r == b && b < n1) r = wide_search<T>(o, cluster, s_cnt, phase, (u32)j, b + 1, n1, c, (u32)k);
     if (r < j) {  // even the empty part exceeds c (BisectCost...:47-51)
       broke = true;
       if (writer)
@@ -134,7 +134,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
   }
   if (writer) {
     bool feas = false;
-    if (!broke) feas = cost_leq(dev_cost<T>(o, (u32)j, (u32)n1), c);
+    if (!broke) feas = cost_leq(dev_cost<T>(o, (u32)j, (u32)n1, (u32)K), c);
     node_c[node] = c;
     node_res[node] = feas ? 2 : 1;
   }
@@ -173,7 +173,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
     i64 jp_lo = max(sk, (i64)__ldcg(spl_lo + k + 1));
     while (jp_lo <= jp_hi) {
       const i64 jp = (jp_lo + jp_hi) >> 1;
-      const T c = dev_cost<T>(o, (u32)sk, (u32)jp);
+      const T c = dev_cost<T>(o, (u32)sk, (u32)jp, (u32)k);
       const double cd = (double)c;
       if (c_lo <= cd && cd < c_hi) {
         ++probes;
@@ -184,7 +184,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
           const i64 a = max(j, (i64)__ldcg(spl_lo + kk + 1));
           const i64 b = __ldcg(spl_hi + kk + 1);
           // search (:14-27): the largest j' in [a, b] with c(j, j') <= c; b if the window is empty, a - 1 if none fits
-          const i64 r = a > b ? b : wide_search<T>(o, cluster, s_cnt, phase, (u32)j, a, b, cd);
+          const i64 r = a > b ? b : wide_search<T>(o, cluster, s_cnt, phase, (u32)j, a, b, cd, (u32)kk);
           if (writer) spl[kk + 1] = (int)r;
           if (r < j) {
             chk = false;
@@ -196,7 +196,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
         }
         // the last part: [spl[K], spl[K+1])
         const i64 ls = (k == K) ? sk : j, le = (k == K) ? jp : n1;
-        const bool feas = chk && cost_leq(dev_cost<T>(o, (u32)ls, (u32)le), cd);
+        const bool feas = chk && cost_leq(dev_cost<T>(o, (u32)ls, (u32)le, (u32)K), cd);
         __syncthreads();  // CTA 0: the writer's spl entries are visible to the copying threads
         if (feas) { c_hi = cd; jp_hi = jp - 1; } else { c_lo = cd; jp_lo = jp + 1; }
         if (cta0) {
@@ -711,7 +711,7 @@ __global__ void k_ub_index(const __grid_constant__ DevOracle o, int K, double* _
     return lo;
   };
   double best = 0;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) best = fmax(best, (double)dev_cost<T>(o, cut(k), cut(k + 1)));
+  for (int k = threadIdx.x; k < K; k += blockDim.x) best = fmax(best, (double)dev_cost<T>(o, cut(k), cut(k + 1), (u32)k + 1u));
   for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
   __syncthreads();

@@ -287,18 +287,19 @@ int cpb_oracle_query_device(cpb_oracle* f, int64_t Q, const int64_t* d_j, const 
   CPB_API_END
 }
 
-int cpb_oracle_query(cpb_oracle* f, int64_t Q, const int64_t* j, const int64_t* jp, const int64_t* /*k*/, double* cost_out) {
+int cpb_oracle_query(cpb_oracle* f, int64_t Q, const int64_t* j, const int64_t* jp, const int64_t* k, double* cost_out) {
   CPB_API_BEGIN
   ensure_context();
   CPB_REQUIRE(f && Q >= 0 && (Q == 0 || (j && jp && cost_out)), "NULL argument");
   if (Q > 0) {
     const i64 n1 = f->O->A->n + 1;
     for (i64 t = 0; t < Q; ++t) CPB_REQUIRE(j[t] >= 1 && jp[t] >= j[t] && jp[t] <= n1, "query out of range (need 1 <= j <= j' <= n+1)");
-    DBuf<i64> dj(Q), djp(Q);
+    DBuf<i64> dj(Q), djp(Q), dk(k ? Q : 0);
     DBuf<double> dc(Q);
     CPB_CUDA(cudaMemcpyAsync(dj.get(), j, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
     CPB_CUDA(cudaMemcpyAsync(djp.get(), jp, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
-    oracle_query(*f->O, Q, dj.get(), djp.get(), dc.get());
+    if (k) CPB_CUDA(cudaMemcpyAsync(dk.get(), k, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));  // part index (1-based): only the row-partition-aware models use it
+    oracle_query(*f->O, Q, dj.get(), djp.get(), dc.get(), k ? dk.get() : nullptr);
     CPB_CUDA(cudaMemcpyAsync(cost_out, dc.get(), Q * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
     CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   }

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_dp_first(const __grid_constant__ DevOra
 // bottleneck layer: a(j) = prev[j] (non-decreasing), b(j) = c(j, j') (non-increasing)
 template <class T>
 __global__ void __launch_bounds__(256) k_dp_bottleneck(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
-                                                       u32* __restrict__ ptr, u32 jp_first) {
+                                                       u32* __restrict__ ptr, u32 jp_first, u32 k) {
   const u32 n1 = o.n + 1;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + jp_first; t <= n1; t += stride) {
@@ -38,20 +38,20 @@ __global__ void __launch_bounds__(256) k_dp_bottleneck(const __grid_constant__ D
     u32 lo = 1, hi = jp + 1;
     while (lo < hi) {
       const u32 mid = lo + ((hi - lo) >> 1);
-      if (prev[mid] >= dev_cost<T>(o, mid, jp)) hi = mid; else lo = mid + 1;
+      if (prev[mid] >= dev_cost<T>(o, mid, jp, k)) hi = mid; else lo = mid + 1;
     }
     const u32 js = lo;
     T v;
     u32 arg;
     if (js > jp) {  // a < b everywhere: h = b is minimised at the right end
       arg = jp;
-      v = dev_cost<T>(o, jp, jp);
+      v = dev_cost<T>(o, jp, jp, k);
     } else {
       const T va = prev[js];
       bool right = true;
       T vb = va;
       if (js > 1) {
-        vb = dev_cost<T>(o, js - 1, jp);
+        vb = dev_cost<T>(o, js - 1, jp, k);
         right = va <= vb;
       }
       if (right) {
@@ -89,7 +89,7 @@ template <int TIE, class T> __device__ __forceinline__ bool tie_better(T ob, u32
 // (O(n^2) oracle queries per layer; the monotone divide & conquer version replaces it for large n.)
 template <int TIE, class T>
 __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
-                                                  u32* __restrict__ ptr, u32 jp_first) {
+                                                  u32* __restrict__ ptr, u32 jp_first, u32 k) {
   const u32 n1 = o.n + 1;
   const int lane = threadIdx.x & 31;
   const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
     u32 arg = 0;
     const u32 j_last = TIE == TIE_RIGHT ? jp : jp - 1;
     for (u32 j = 1 + lane; j <= j_last; j += 32) {
-      const T c = prev[j] + dev_cost<T>(o, j, jp);
+      const T c = prev[j] + dev_cost<T>(o, j, jp, k);
       // ascending j within a lane: `<=` keeps the largest minimiser, `<` the smallest
       if (arg == 0 || (TIE == TIE_RIGHT ? c <= best : c < best)) { best = c; arg = j; }
     }
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
     }
     if (lane == 0) {
       if (TIE == TIE_CONVEX) {  // the empty last part stays only if it is strictly cheaper
-        const T init = prev[jp] + dev_cost<T>(o, jp, jp);
+        const T init = prev[jp] + dev_cost<T>(o, jp, jp, k);
         if (arg == 0 || init < best) { best = init; arg = jp; }
       }
       cur[jp] = best;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
 // range with a rightmost-argmin reduction.  Total work per layer O(n log n) oracle queries.
 template <int TIE, class T>
 __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
-                                                     u32* __restrict__ ptr, u32 step, u32 first_t, u32 t_stride) {
+                                                     u32* __restrict__ ptr, u32 step, u32 first_t, u32 t_stride, u32 k) {
   __shared__ T s_best[8];
   __shared__ u32 s_arg[8];
   const u32 n = o.n;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ Dev
   u32 arg = 0;
   const u32 j_last = TIE == TIE_RIGHT ? hi : min(hi, jp - 1);
   for (u32 j = lo + threadIdx.x; j <= j_last; j += blockDim.x) {
-    const T c = prev[j] + dev_cost<T>(o, j, jp);
+    const T c = prev[j] + dev_cost<T>(o, j, jp, k);
     if (arg == 0 || (TIE == TIE_RIGHT ? c <= best : c < best)) { best = c; arg = j; }
   }
   for (int off = 16; off > 0; off >>= 1) {
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_dp_total_dc(const __grid_constant__ Dev
       if (tie_better<TIE>(ob, oa, best, arg)) { best = ob; arg = oa; }
     }
     if (TIE == TIE_CONVEX && hi == jp) {  // the empty last part (candidate j') stays only if it is strictly cheaper
-      const T init = prev[jp] + dev_cost<T>(o, jp, jp);
+      const T init = prev[jp] + dev_cost<T>(o, jp, jp, k);
       if (arg == 0 || init < best) { best = init; arg = jp; }
     }
     cur[jp] = best;
@@ -182,7 +182,7 @@ __device__ __forceinline__ bool weight_ok(const DevOracle& o, const DevWeight& w
 template <class T>
 __global__ void __launch_bounds__(256) k_dp_constrained(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
                                                         u32* __restrict__ ptr, int total, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, u32 W, int first,
-                                                        DevWeight wt) {
+                                                        DevWeight wt, u32 k) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + lo_k; t <= hi_k; t += stride) {
     const u32 jp = (u32)t;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) k_dp_constrained(const __grid_constant__ 
     T best = 0;
     u32 arg = 0;
     for (u32 j = j0; j <= j1; ++j) {
-      const T c = dev_cost<T>(o, j, jp);
+      const T c = dev_cost<T>(o, j, jp, k);
       const T v = total ? prev[j] + c : max(prev[j], c);
       if (arg == 0 || v <= best) { best = v; arg = j; }
     }
@@ -241,25 +241,25 @@ template <class T, int TIE> static void dynamic_T(Oracle& f, bool total, i64 K, 
     u32* p = ptr.get() + (size_t)(k - 1) * n2;
     if (!total) {
       const unsigned g = (k == K) ? 1 : grid;
-      CPB_LAUNCH(k_dp_bottleneck<T>, g, 256, 0, f.dev, prev, cur, p, jp_first);
+      CPB_LAUNCH(k_dp_bottleneck<T>, g, 256, 0, f.dev, prev, cur, p, jp_first, (u32)k);
     } else if (monge && A.n > 64) {
       const u32 n = (u32)A.n;
       // j' = n + 1 (t = n): full scan; the only point the last layer needs (DynamicSplitter.jl:34)
-      CPB_LAUNCH((k_dp_total_dc<TIE, T>), 1, 256, 0, f.dev, prev, cur, p, 0u, n, 1u);
+      CPB_LAUNCH((k_dp_total_dc<TIE, T>), 1, 256, 0, f.dev, prev, cur, p, 0u, n, 1u, (u32)k);
       if (k < K) {
-        CPB_LAUNCH((k_dp_total_dc<TIE, T>), 1, 256, 0, f.dev, prev, cur, p, 0u, 0u, 1u);  // j' = 1 (t = 0)
+        CPB_LAUNCH((k_dp_total_dc<TIE, T>), 1, 256, 0, f.dev, prev, cur, p, 0u, 0u, 1u, (u32)k);  // j' = 1 (t = 0)
         u32 D = 1;
         while (((u64)1 << D) <= n) ++D;  // 2^D > n
         for (u32 step = (u32)1 << (D - 1); step >= 1; step >>= 1) {
           // nodes t = step * (2 i + 1) <= n, t != n (already solved)
           const u64 nodes = ((u64)n / step + 1) / 2;
-          if (nodes > 0) CPB_LAUNCH((k_dp_total_dc<TIE, T>), (unsigned)nodes, 256, 0, f.dev, prev, cur, p, step, step, 2 * step);
+          if (nodes > 0) CPB_LAUNCH((k_dp_total_dc<TIE, T>), (unsigned)nodes, 256, 0, f.dev, prev, cur, p, step, step, 2 * step, (u32)k);
         }
       }
     } else {
       const size_t rows = (size_t)n1 - jp_first + 1;
       const unsigned g = (unsigned)std::min<size_t>((rows * 32 + 255) / 256, (size_t)ctx().sm_count * 8);
-      CPB_LAUNCH((k_dp_total<TIE, T>), g, 256, 0, f.dev, prev, cur, p, jp_first);
+      CPB_LAUNCH((k_dp_total<TIE, T>), g, 256, 0, f.dev, prev, cur, p, jp_first, (u32)k);
     }
     std::swap(prev, cur);
   }
@@ -327,7 +327,7 @@ template <class T> static void dynamic_constrained_T(Oracle& f, bool total, cons
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt + 255) / 256, (size_t)ctx().sm_count * 8));
     CPB_LAUNCH(k_dp_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, total ? 1 : 0, (u32)lo[k], (u32)hi[k],
                (u32)(k > 1 ? lo[k - 1] : 1), (u32)(k > 1 ? hi[k - 1] : 1), (u32)std::min<i64>(std::max<i64>(W, 0), n + 1), k == 1 ? 1 : 0,
-               DevWeight{wa, wbv, wbp, w_max});
+               DevWeight{wa, wbv, wbp, w_max}, (u32)k);
     std::swap(prev, cur);
   }
   CPB_LAUNCH(k_dp_unravel, 1, 32, 0, ptr.get(), n2, (int)K, n1, spl.get());

@@ -42,6 +42,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
 // SparseColorArrays.jl: NetCount :103-118, dianetcount! :72-99, SelfNetCount :177-229, SelfPinCount :281-318
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
+std::unique_ptr<RankStruct> build_partwise_rank(const Matrix& A, const u32* asg, u32 K, DBuf<u32>& part_col, DBuf<u32>& part_start);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
                         i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false, bool as_pos = false);
@@ -55,6 +56,13 @@ struct DevOracle {
   const u32* pos;      // [n+1] 0-based
   const u32* overpos;  // [n+1] prefix of max(deg - delta_pins, 0)   (MONOSYM)
   DevRank net, dianet, selfnet, selfpin;
+  // PRIMCONN: the nonzeros regrouped by the row part that owns their row (parts outermost, columns ascending inside a
+  // part -- the reference's "stacked" matrix of PartwiseCounts.jl:1-67): lcn.wm = wavelet matrix over their column-valued
+  // links, part_col[p] = 0-based column of stacked element p, part_start[k] = first element of part k (0-based k, K+1 entries)
+  DevRank lcn;
+  const u32* part_col;
+  const u32* part_start;
+  u32 n_parts;
   const i64* env;      // segment tree of packed (lo, hi) (ENVELOPE); envH = height
   int envH;
   double cf[5];
@@ -71,7 +79,8 @@ struct Oracle {
   Matrix* A = nullptr;
   cpb_model mdl{};
   std::vector<double> h_alpha_col, h_beta_col, h_beta_row;  // host copies of tables
-  std::unique_ptr<RankStruct> net, dianet, selfnet, selfpin;
+  std::unique_ptr<RankStruct> net, dianet, selfnet, selfpin, lcn;
+  DBuf<u32> part_col, part_start;  // PRIMCONN (see DevOracle)
   std::unique_ptr<LinkStream> ls;  // links for the streaming probes (net or dia-net, by model)
   DBuf<u32> overpos;
   i64 h_n_over = -1;  // host copy of overpos[n] once it has been read
@@ -94,7 +103,7 @@ void oracle_set_links(Oracle& f, const u32* d_prev, i64 Ne);
 i64 count_first_occurrences(const LinkStream& ls);
 
 std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int64_t* pi_spl, i64 pi_K);
-void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost);
+void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost, const i64* d_k = nullptr);
 void oracle_bound(Oracle& f, i64 K, double out[2]);
 double oracle_objective(Oracle& f, bool total, i64 K, const int64_t* h_spl);
 void count_query(Matrix& A, int which, i64 Q, const i64* d_j, const i64* d_jp, i64* d_out);
@@ -152,7 +161,25 @@ __device__ __forceinline__ void dev_envelope(const DevOracle& o, u32 j, u32 jp, 
   }
 }
 
-template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32 j, u32 jp) {
+// local nets of part k (1-based) in columns [j, j'): first occurrences (link < j) among the part's elements of those columns
+__device__ __forceinline__ u32 dev_localnets(const DevOracle& o, u32 j, u32 jp, u32 k) {
+  if (k < 1 || k > o.n_parts) return 0;
+  const u32 s = __ldg(o.part_start + (k - 1)), e = __ldg(o.part_start + k);
+  auto lower = [&](u32 c0) {  // first stacked element of the part whose 0-based column is >= c0
+    u32 lo = s, hi = e;
+    while (lo < hi) {
+      const u32 mid = lo + ((hi - lo) >> 1);
+      if (__ldg(o.part_col + mid) < c0) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const u32 a = lower(j - 1), b = lower(jp - 1);
+  if (a >= b) return 0;
+  if (o.lcn.wm.L < 32 && (j >> o.lcn.wm.L) != 0) return b - a;  // j beyond the link range: every link is smaller
+  return wm_descend(o.lcn.wm, b, j) - wm_descend(o.lcn.wm, a, j);
+}
+
+template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32 j, u32 jp, u32 k = 1) {
   using C = CoefOf<T>;
   const i64 nv = (i64)jp - (i64)j;
   const i64 np = (i64)__ldg(o.pos + (jp - 1)) - (i64)__ldg(o.pos + (j - 1));
@@ -186,6 +213,11 @@ template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32
     case CPB_MODEL_SYMEDGECUT: {  // SymmetricEdgeCutCosts.jl:18,37-43
       const i64 l = rank_count_ge(o.selfpin, j, jp);
       return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)l * C::get(o, 2) + (T)(np - l) * C::get(o, 3);
+    }
+    case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:19,66-73
+      const i64 d = dev_netcount(o.net, j, jp);
+      const i64 l = dev_localnets(o, j, jp, k);
+      return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)l * C::get(o, 3) + (T)(d - l) * C::get(o, 4);
     }
     case CPB_MODEL_ENVELOPE: {  // EnvelopeCosts.jl:20,66-73
       i64 lo, hi;

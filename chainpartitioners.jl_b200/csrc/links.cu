@@ -360,6 +360,40 @@ std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which) {
   return rs;
 }
 
+// PRIMCONN: elements regrouped by the row part of their row (stable: columns stay ascending inside a part), wavelet matrix
+// over their column-valued links (PartwiseCounts.jl:1-67 builds the same "stacked" matrix and a net count on it)
+__global__ void k_part_ids(const u32* __restrict__ row, const u32* __restrict__ asg, size_t N, u32* __restrict__ pid) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) pid[q] = asg[row[q]];
+}
+__global__ void k_part_gather(const u32* __restrict__ sq, const u32* __restrict__ colidx, const u32* __restrict__ prev, size_t N,
+                              u32* __restrict__ col_s, u32* __restrict__ prev_s) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
+    const u32 q = sq[p];
+    col_s[p] = colidx[q];
+    prev_s[p] = prev[q];
+  }
+}
+std::unique_ptr<RankStruct> build_partwise_rank(const Matrix& A, const u32* asg, u32 K, DBuf<u32>& part_col, DBuf<u32>& part_start) {
+  auto rs = std::make_unique<RankStruct>();
+  const size_t N = (size_t)A.N;
+  const u32 n = (u32)A.n, m = (u32)A.m;
+  DBuf<u32> prev(N), colidx(N), pid(N), k0(N), v0(N), k1(N), v1(N), prev_s(N);
+  compute_prev_links(A.pos.get(), A.row.get(), m, n, N, prev.get(), colidx.get());
+  if (N) CPB_LAUNCH(k_part_ids, grid_for(N), 256, 0, A.row.get(), asg, N, pid.get());
+  const int which = radix_sort_pairs_iota(pid.get(), k0.get(), v0.get(), k1.get(), v1.get(), N, bits_for(K ? K - 1 : 0));
+  const u32* keys = which ? k1.get() : k0.get();
+  const u32* sq = which ? v1.get() : v0.get();
+  part_col.alloc(N + 1);
+  if (N) CPB_LAUNCH(k_part_gather, grid_for(N), 256, 0, sq, colidx.get(), prev.get(), N, part_col.get(), prev_s.get());
+  part_start.alloc((size_t)K + 2);
+  segment_starts(keys, N, part_start.get(), K);  // part_start[k] = first stacked element with part id >= k, k = 0..K
+  rs->wm.build(prev_s.get(), prev.get(), N, n);
+  rs->P = nullptr;
+  return rs;
+}
+
 // adjointpattern(A) (util.jl:67-95): stable sort by row = CSC of the transpose
 __global__ void k_gather_cols(const u32* __restrict__ sq, const u32* __restrict__ colidx, size_t N, u32* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;

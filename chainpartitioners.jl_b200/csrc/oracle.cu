@@ -153,6 +153,24 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
       d.envH = H;
       break;
     }
+    case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:56-67: needs the row partition Pi
+      CPB_REQUIRE(pi_spl != nullptr && pi_K >= 1, "primary connectivity model needs a row partition (SplitPartition)");
+      CPB_REQUIRE(pi_spl[0] == 1 && pi_spl[pi_K] == A.m + 1, "row partition must cover rows 1..m");
+      f->pi_K = pi_K;
+      f->h_pi_spl.assign(pi_spl, pi_spl + pi_K + 1);
+      std::vector<u32> spl0(pi_K + 1);
+      for (i64 k = 0; k <= pi_K; ++k) {
+        CPB_REQUIRE(k == 0 || pi_spl[k] >= pi_spl[k - 1], "row partition must be sorted");
+        spl0[k] = (u32)(pi_spl[k] - 1);
+      }
+      DBuf<u32> dspl(pi_K + 1);
+      CPB_CUDA(cudaMemcpyAsync(dspl.get(), spl0.data(), spl0.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx().stream));
+      f->pi_asg.alloc((size_t)A.m);
+      f->pi_size.alloc((size_t)pi_K);
+      CPB_LAUNCH(k_pi_assign, grid_for((size_t)pi_K), 256, 0, dspl.get(), (u32)pi_K, f->pi_asg.get(), f->pi_size.get());
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      break;
+    }
     case CPB_MODEL_BLOCK: {
       CPB_REQUIRE(pi_spl != nullptr && pi_K >= 0, "block cost model needs a row partition (SplitPartition)");
       CPB_REQUIRE(mdl->R >= 0 && mdl->R <= 4, "block model supports up to 4 components");
@@ -196,6 +214,14 @@ void oracle_ensure_ranks(Oracle& f) {
     case CPB_MODEL_SYMCONN: f.net = build_rank(A, RANK_NET); f.dianet = build_rank(A, RANK_DIANET); break;
     case CPB_MODEL_HYPEREDGE: f.net = build_rank(A, RANK_NET); f.selfnet = build_rank(A, RANK_SELFNET); break;
     case CPB_MODEL_SYMEDGECUT: f.selfpin = build_rank(A, RANK_SELFPIN); break;
+    case CPB_MODEL_PRIMCONN:
+      f.net = build_rank(A, RANK_NET);
+      f.lcn = build_partwise_rank(A, f.pi_asg.get(), (u32)f.pi_K, f.part_col, f.part_start);
+      d.lcn = f.lcn->dev();
+      d.part_col = f.part_col.get();
+      d.part_start = f.part_start.get();
+      d.n_parts = (u32)f.pi_K;
+      break;
     default: break;
   }
   if (f.net) d.net = f.net->dev();
@@ -241,26 +267,26 @@ void oracle_set_links(Oracle& f, const u32* d_prev, i64 Ne) {
 // ---- oracle_query_batch ---------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(256) k_oracle_query(const __grid_constant__ DevOracle o, i64 Q, const i64* __restrict__ qj,
-                                                      const i64* __restrict__ qjp, double* __restrict__ out) {
+                                                      const i64* __restrict__ qjp, const i64* __restrict__ qk, double* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)Q; t += stride) {
     const i64 j = qj[t], jp = qjp[t];
     double r;
     if (j < 1 || jp < j || jp > (i64)o.n + 1) r = __longlong_as_double(0x7ff8000000000000ll);  // invalid query -> NaN
-    else r = (double)dev_cost<T>(o, (u32)j, (u32)jp);
+    else r = (double)dev_cost<T>(o, (u32)j, (u32)jp, qk ? (u32)qk[t] : 1u);
     out[t] = r;
   }
 }
 
-void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost) {
+void oracle_query(Oracle& f, i64 Q, const i64* d_j, const i64* d_jp, double* d_cost, const i64* d_k) {
   if (Q <= 0) return;
   if (f.dev.kind == CPB_MODEL_BLOCK) throw Error(CPB_ERR_UNSUPPORTED, "random-access queries of the 2-D block model are served through pack_stripe only");
   oracle_ensure_ranks(f);
   const double L = f.net ? f.net->wm.L : f.dianet ? f.dianet->wm.L : f.selfpin ? f.selfpin->wm.L : 0;
   ProfScope prof("oracle_query_batch", (double)Q * (24.0 + L * 2.0 * 32.0));
   const unsigned grid = (unsigned)std::min<size_t>(((size_t)Q + 255) / 256, (size_t)ctx().sm_count * 16);
-  if (f.dev.is_float) CPB_LAUNCH(k_oracle_query<double>, grid, 256, 0, f.dev, Q, d_j, d_jp, d_cost);
-  else CPB_LAUNCH(k_oracle_query<i64>, grid, 256, 0, f.dev, Q, d_j, d_jp, d_cost);
+  if (f.dev.is_float) CPB_LAUNCH(k_oracle_query<double>, grid, 256, 0, f.dev, Q, d_j, d_jp, d_k, d_cost);
+  else CPB_LAUNCH(k_oracle_query<i64>, grid, 256, 0, f.dev, Q, d_j, d_jp, d_k, d_cost);
 }
 
 static double query_one(Oracle& f, i64 j, i64 jp) {
@@ -301,6 +327,21 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
         c_hi = c[0] + (T)A.n * c[1] + (T)A.N * c[2] + (T)nets_all * c[3];
       }
       c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
+      break;
+    }
+    case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:31-42 (oracle form)
+      CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0 && c[4] >= 0, "negative beta (PrimaryConnectivityCosts.jl:35-38)");
+      oracle_ensure_ranks(f);
+      cpb_model conn = f.mdl;  // nets(1, n+1) through a plain connectivity query: (0, 0, 0, 1)
+      const DevOracle saved = f.dev;
+      f.dev.kind = CPB_MODEL_CONNECTIVITY;
+      f.dev.cf[0] = f.dev.cf[1] = f.dev.cf[2] = 0; f.dev.cf[3] = 1;
+      f.dev.ci[0] = f.dev.ci[1] = f.dev.ci[2] = 0; f.dev.ci[3] = 1;
+      const double nets_all = query_one(f, 1, A.n + 1);
+      f.dev = saved;
+      (void)conn;
+      c_hi = c[0] + c[1] * (T)A.n + c[2] * (T)A.N + std::max(c[3], c[4]) * (T)nets_all;
+      c_lo = c[0] + jl_fld(c[1] * (T)A.n + c[2] * (T)A.N, (T)K);
       break;
     }
     case CPB_MODEL_MONOSYM: {
@@ -345,11 +386,14 @@ void oracle_bound(Oracle& f, i64 K, double out[2]) {
 double oracle_objective(Oracle& f, bool total, i64 K, const int64_t* h_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   std::vector<i64> hj(h_spl, h_spl + K), hjp(h_spl + 1, h_spl + K + 1);
-  DBuf<i64> dj(K), djp(K);
+  std::vector<i64> hk(K);
+  for (i64 k = 0; k < K; ++k) hk[k] = k + 1;  // part k is charged with the part-k cost (Costs.jl:44-52)
+  DBuf<i64> dj(K), djp(K), dk(K);
   DBuf<double> dc(K);
   CPB_CUDA(cudaMemcpyAsync(dj.get(), hj.data(), K * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
   CPB_CUDA(cudaMemcpyAsync(djp.get(), hjp.data(), K * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
-  oracle_query(f, K, dj.get(), djp.get(), dc.get());
+  CPB_CUDA(cudaMemcpyAsync(dk.get(), hk.data(), K * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+  oracle_query(f, K, dj.get(), djp.get(), dc.get(), dk.get());
   std::vector<double> hc(K);
   CPB_CUDA(cudaMemcpyAsync(hc.data(), dc.get(), K * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));

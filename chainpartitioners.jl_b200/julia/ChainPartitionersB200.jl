@@ -17,6 +17,7 @@ using ChainPartitioners
 import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_stripe,
     AffineWorkModel, AffineConnectivityModel, AffineMonotonizedSymmetricConnectivityModel,
     AffineSymmetricConnectivityModel, AffineHyperedgeCutModel, AffineSymmetricEdgeCutModel, AffineEnvelopeModel,
+    AffinePrimaryConnectivityModel,
     ColumnBlockComponentCostModel, BlockComponentCostModel, block_component,
     ConstrainedCost, VertexCount, FeasibleCost, SplitPartition,
     DynamicBottleneckSplitter, DynamicTotalSplitter, BisectCostBottleneckSplitter, BisectIndexBottleneckSplitter, LazyBisectCostBottleneckSplitter,
@@ -64,6 +65,7 @@ cmodel(m::AffineSymmetricConnectivityModel{Tv}, args...) where {Tv} = affine(3, 
 cmodel(m::AffineHyperedgeCutModel{Tv}, args...) where {Tv} = affine(4, Tv, m.α, m.β_vertex, m.β_pin, m.β_self_net, m.β_cut_net)
 cmodel(m::AffineSymmetricEdgeCutModel{Tv}, args...) where {Tv} = affine(5, Tv, m.α, m.β_vertex, m.β_self_pin, m.β_cut_pin)
 cmodel(m::AffineEnvelopeModel{Tv}, args...) where {Tv} = affine(6, Tv, m.α, m.β_vertex, m.β_pin, m.β_net)
+cmodel(m::AffinePrimaryConnectivityModel{Tv}, args...) where {Tv} = affine(9, Tv, m.α, m.β_vertex, m.β_pin, m.β_local_net, m.β_remote_net)  # needs Π
 
 # Functors cannot cross the ABI: tabulate block_component(f, w) (src/BlockCosts.jl:41-44) for w = 0..w_tab
 tab(f, hi) = Float64[w == 0 && !(f isa Function || f isa Number) ? 0.0 : block_component(f, w) for w in 0:hi]

@@ -195,7 +195,7 @@ class StepHint(AbstractHint):
 # --------------------------------------------------------------------------- cost models
 
 MODEL_WORK, MODEL_CONNECTIVITY, MODEL_MONOSYM, MODEL_SYMCONN = 0, 1, 2, 3
-MODEL_HYPEREDGE, MODEL_SYMEDGECUT, MODEL_ENVELOPE, MODEL_COLBLOCK, MODEL_BLOCK = 4, 5, 6, 7, 8
+MODEL_HYPEREDGE, MODEL_SYMEDGECUT, MODEL_ENVELOPE, MODEL_COLBLOCK, MODEL_BLOCK, MODEL_PRIMCONN = 4, 5, 6, 7, 8, 9
 
 
 def _is_int(x) -> bool:
@@ -302,6 +302,15 @@ class AffineSymmetricEdgeCutModel(_AffineModel):
 
     kind = MODEL_SYMEDGECUT
     names = ("alpha", "beta_vertex", "beta_self_pin", "beta_cut_pin")
+
+
+class AffinePrimaryConnectivityModel(_AffineModel):
+    """PrimaryConnectivityCosts.jl:5-19: ``alpha + n_vertices*beta_vertex + n_pins*beta_pin + n_local_nets*beta_local_net +
+    n_remote_nets*beta_remote_net`` where a net of part k's columns is local if row part k of Pi owns it; always used
+    with a row partition (``oracle_stripe(mdl, A, Pi)``, ``partition_stripe(A, K, method, Pi)``)."""
+
+    kind = MODEL_PRIMCONN
+    names = ("alpha", "beta_vertex", "beta_pin", "beta_local_net", "beta_remote_net")
 
 
 class AffineEnvelopeModel(_AffineModel):

@@ -42,7 +42,9 @@ enum {
   CPB_MODEL_SYMEDGECUT = 5,   /* AffineSymmetricEdgeCutModel              SymmetricEdgeCutCosts.jl:5-18 */
   CPB_MODEL_ENVELOPE = 6,     /* AffineEnvelopeModel                      EnvelopeCosts.jl:5-20 */
   CPB_MODEL_COLBLOCK = 7,     /* ColumnBlockComponentCostModel            BlockCosts.jl:1-17 */
-  CPB_MODEL_BLOCK = 8         /* BlockComponentCostModel                  BlockCosts.jl:19-44 */
+  CPB_MODEL_BLOCK = 8,        /* BlockComponentCostModel                  BlockCosts.jl:19-44 */
+  CPB_MODEL_PRIMCONN = 9            /* AffinePrimaryConnectivityModel(a, b_v, b_p, b_local, b_remote) with a row partition Pi: a net of part k's
+                                       columns is local if row part k owns it   PrimaryConnectivityCosts.jl:5-86, PartwiseCounts.jl:1-101 */
 };
 
 /* coef[] by kind, evaluated left to right without FMA contraction (e.g. ConnectivityCosts.jl:20):

@@ -125,6 +125,15 @@ template <class T, class Fn> static void with_oracle(const cpo_model* mdl, int h
     fn(f);
     return;
   }
+  if (mdl->kind == CPO_MODEL_PRIMCONN) {
+    if (!pi_spl) throw std::invalid_argument("primary connectivity model needs a row partition");
+    with_dom(hint, [&](auto* tag) {
+      using Dom = std::remove_pointer_t<decltype(tag)>;
+      PrimaryOracle<Dom, T> f(M, mdl, pi_spl, pi_K);
+      fn(f);
+    });
+    return;
+  }
   with_dom(hint, [&](auto* tag) {
     using Dom = std::remove_pointer_t<decltype(tag)>;
     Oracle<Dom, T> f(M, mdl);

@@ -46,7 +46,8 @@ enum {
   CPO_MODEL_SYMEDGECUT = 5,        /* AffineSymmetricEdgeCutModel         (SymmetricEdgeCutCosts.jl:5-18) */
   CPO_MODEL_ENVELOPE = 6,          /* AffineEnvelopeModel                 (EnvelopeCosts.jl:5-20) */
   CPO_MODEL_COLBLOCK = 7,          /* ColumnBlockComponentCostModel       (BlockCosts.jl:1-17) */
-  CPO_MODEL_BLOCK = 8              /* BlockComponentCostModel             (BlockCosts.jl:19-44) */
+  CPO_MODEL_BLOCK = 8,             /* BlockComponentCostModel             (BlockCosts.jl:19-44) */
+  CPO_MODEL_PRIMCONN = 9           /* AffinePrimaryConnectivityModel + row partition (PrimaryConnectivityCosts.jl:5-19) */
 };
 
 /* hints -> dominance structure (SparsePrefixMatrices.jl:450-458) */

@@ -593,6 +593,80 @@ template <class Dom, class T> struct Oracle {
   inline T step_next_same(i64 j, i64 jp, i64 = 1) { return eval<2>(j, jp); }
 };
 
+// PartwiseCounts.jl:1-67 partwise(A, Π) + :69-101 PartwiseCount, and PrimaryConnectivityCosts.jl:21-86
+// PrimaryConnectivityOracle: c(j, j', k) = α + n_v β_v + n_p β_p + l β_local + (d - l) β_remote with d = nets(j, j') and
+// l = lcn(j, j', k) = the nets of columns [j, j') that row part k of Π owns.  lcn is a net count on the "stacked" matrix A'
+// whose columns are the non-empty (part, column) pairs, parts outermost; (j, j', k) maps to a column range of A' by two
+// binary searches in the part's column list prm.
+template <class Dom, class T> struct PrimaryOracle {
+  const Mat& A;
+  Model<T> mdl;
+  i64 n, K;
+  ivec asg, pios, prm;  // Π as a map; πos[1..K+1]: first stacked column of each part; prm[j']: original column
+  Mat Ap;
+  NetCount<Dom> net, lcn;
+
+  PrimaryOracle(const Mat& A_, const cpo_model* s, const i64* pi_spl, i64 pi_K) : A(A_), mdl(s), n(A_.n), K(pi_K) {
+    if (pi_spl[0] != 1 || pi_spl[K] != A.m + 1) throw std::invalid_argument("row partition must cover rows 1..m");
+    asg.assign(A.m + 1, 0);  // Partitions.jl:60-68
+    for (i64 k = 1; k <= K; ++k)
+      for (i64 i = pi_spl[k - 1]; i < pi_spl[k]; ++i) asg[i] = k;
+    // partwise (PartwiseCounts.jl:1-67)
+    ivec Pios(K + 2, 0), hst(K + 1, 0);
+    pios.assign(K + 2, 0);
+    for (i64 j = 1; j <= A.n; ++j)
+      for (i64 q = A.pos[j]; q < A.pos[j + 1]; ++q) {
+        const i64 k = asg[A.idx[q]];
+        pios[k + 1] += hst[k] != j;
+        hst[k] = j;
+        Pios[k + 1] += 1;
+      }
+    i64 q = 1, jp = 1;
+    for (i64 k = 1; k <= K + 1; ++k) {
+      const i64 a = Pios[k], b = pios[k];
+      Pios[k] = q; q += a;
+      pios[k] = jp; jp += b;
+    }
+    const i64 np = jp - 1;
+    Ap.m = A.m; Ap.n = np; Ap.N = A.N;
+    Ap.pos.assign(np + 2, 0);
+    Ap.idx.assign(A.N + 1, 0);
+    prm.assign(np + 1, 0);
+    std::fill(hst.begin(), hst.end(), 0);
+    // after the shift above Pios[k + 1] / pios[k + 1] are the running cursors of part k (they end at the next part's start)
+    for (i64 j = 1; j <= A.n; ++j)
+      for (i64 qq = A.pos[j]; qq < A.pos[j + 1]; ++qq) {
+        const i64 i = A.idx[qq], k = asg[i];
+        const i64 q2 = Pios[k + 1];
+        Ap.idx[q2] = i;
+        Pios[k + 1] = q2 + 1;
+        if (hst[k] != j) {
+          const i64 j2 = pios[k + 1];
+          Ap.pos[j2] = q2;
+          prm[j2] = j;
+          pios[k + 1] = j2 + 1;
+        }
+        hst[k] = j;
+      }
+    Ap.pos[np + 1] = A.N + 1;
+    // the cursors have advanced by one part, so now πos[k] = first stacked column of part k, πos[K + 1] = n' + 1 -- the
+    // layout PartwiseCount indexes (:84-85)
+    net.build(A, false);
+    lcn.build(Ap, false);
+  }
+  inline i64 rank_of(i64 k, i64 j) const {  // πos[k] + searchsortedfirst(prm[πos[k] : πos[k+1]-1], j) - 1
+    return std::lower_bound(prm.begin() + pios[k], prm.begin() + pios[k + 1], j) - prm.begin();
+  }
+  inline T operator()(i64 j, i64 jp, i64 k = 1) {
+    const i64 w = A.pos[jp] - A.pos[j];
+    const i64 d = net.at(j, jp);
+    const i64 l = lcn.at(rank_of(k, j), rank_of(k, jp));
+    return mdl.eval4(jp - j, w, l, d - l);
+  }
+  inline T step_same_next(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
+  inline T step_next_same(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
+};
+
 // BlockCosts.jl:46-142 BlockComponentCostStepOracle (stateful)
 template <class T> struct BlockOracle {
   const Mat& A;

@@ -9,6 +9,10 @@
 
 namespace cpo {
 
+// nets(1, n + 1) of an oracle that owns a net count (SFINAE: the block oracle has none)
+template <class F> static auto nets_all(F& f, i64 n, int) -> decltype(f.net.at((i64)1, n)) { return f.net.at(1, n + 1); }
+template <class F> static i64 nets_all(F&, i64, long) { throw std::logic_error("this oracle has no net count"); }
+
 // ---- bound_stripe -----------------------------------------------------------
 // WorkCosts.jl:37-51; ConnectivityCosts.jl:22-35; MonotonizedSymmetricConnectivityCosts.jl:50-66,94-105;
 // EnvelopeCosts.jl:44-54.  Returned "./ 1" (BisectCostBottleneckSplitter.jl:39).
@@ -37,6 +41,13 @@ template <class T, class F> static void bound_stripe(const Mat& A, i64 K, const 
       for (i64 j = 1; j <= n; ++j) n_over += std::max<T>((T)(A.pos[j + 1] - A.pos[j]) - mdl.c[4], (T)0);
       c_hi = mdl.c[0] + mdl.c[1] * (T)n + mdl.c[2] * n_over + mdl.c[3] * (T)m;
       c_lo = mdl.c[0] + jl_fld(c_hi - mdl.c[0], (T)K);
+      break;
+    }
+    case CPO_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:31-42 (oracle form)
+      if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0 && mdl.c[4] >= 0)) throw std::invalid_argument("negative beta");
+      if (!ocl) throw std::logic_error("primary connectivity bound needs an oracle");
+      c_hi = mdl.c[0] + mdl.c[1] * (T)n + mdl.c[2] * (T)N + std::max(mdl.c[3], mdl.c[4]) * (T)nets_all(*ocl, n, 0);
+      c_lo = mdl.c[0] + jl_fld(mdl.c[1] * (T)n + mdl.c[2] * (T)N, (T)K);
       break;
     }
     case CPO_MODEL_ENVELOPE: {

@@ -495,6 +495,36 @@ def test_bisect_index_splitter(ref, fixtures):
     assert cp.bottleneck_value(A, g, AFF) == cp.bottleneck_value(A, d, AFF)
 
 
+def prim_partitions(ref, A, K):
+    """Pi = partition_stripe(A', K, EquiSplitter()) as in test_Partitioners.jl:95."""
+    return ref.partition_stripe(ref.adjointpattern(A), K, cp.EquiSplitter())
+
+
+def test_primary_connectivity_model(ref, fixtures):
+    """AffinePrimaryConnectivityModel with a row partition (PrimaryConnectivityCosts.jl:5-86, PartwiseCounts.jl:1-101):
+    oracle queries with the part index, bound_stripe, and every splitter of test_Partitioners.jl:86-113 on it."""
+    rng = np.random.default_rng(305)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 10, 0.3), sprand(rng, 8, 3, 0.5), sprand(rng, 40, 120, 0.1),
+            synth.erdos_renyi(2000, 5)]
+    for A in mats:
+        for K in [1, 2, 3, 8]:
+            Pi = prim_partitions(ref, A, K)
+            for f in [cp.AffinePrimaryConnectivityModel(0, 2, 1, 3, 6), cp.AffinePrimaryConnectivityModel(1, 1, 1, 1, 1),
+                      cp.AffinePrimaryConnectivityModel(0.0, 0.5, 1.0, 3.0, 6.5)]:
+                j, jp = rand_pairs(rng, A.n, 300)
+                k = rng.integers(1, K + 1, 300)
+                ocl = cp.oracle_stripe(f, A, Pi)
+                assert np.array_equal(ocl.query(j, jp, k), ref.oracle_query(f, A, j, jp, k, Pi=Pi))
+                ocl.close()
+                if A.n > 500 and K > 3:
+                    continue
+                for mtd in [cp.DynamicBottleneckSplitter(f), cp.DynamicTotalSplitter(f), cp.BisectIndexBottleneckSplitter(f),
+                            cp.BisectCostBottleneckSplitter(f, 0.1), cp.BisectCostBottleneckSplitter(f, 0.01), cp.LazyBisectCostBottleneckSplitter(f, 0.01)]:
+                    g, r = cp.partition_stripe(A, K, mtd, Pi), ref.partition_stripe(A, K, mtd, Pi)
+                    assert np.array_equal(g.spl, r.spl), (A, f, K, type(mtd).__name__, g.spl, r.spl)
+                    assert cp.bottleneck_value(A, g, f, Pi) == ref.bottleneck_value(A, g, f, Pi)
+
+
 def test_degenerate_inputs(ref):
     """Empty matrices, empty columns/rows, K > n, single column -- the ragged cases."""
     z = np.zeros(0, dtype=np.int64)

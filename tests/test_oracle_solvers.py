@@ -341,6 +341,54 @@ def test_bisect_index_is_exact(ref, fixtures):
                 assert objective(C, Phi.spl, False) == brute_optimum(C, A.n, K, False)
 
 
+def primary_cost(mdl, A, Pi, j, jp, k):
+    """PrimaryConnectivityCosts.jl:19,66-73 from the set definition: nets of columns [j, j') owned by row part k are local."""
+    c = mdl.coef
+    rows = set()
+    for col in range(j, jp):
+        rows |= set(col_rows(A, col).tolist())
+    l = sum(1 for r in rows if Pi.spl[k - 1] <= r < Pi.spl[k])
+    return c[0] + (jp - j) * c[1] + int(A.colptr[jp - 1] - A.colptr[j - 1]) * c[2] + l * c[3] + (len(rows) - l) * c[4]
+
+
+def test_primary_connectivity_oracle_and_solvers(ref, fixtures):
+    """AffinePrimaryConnectivityModel with Pi = partition_stripe(A', K, EquiSplitter()) (test_Partitioners.jl:86-113;
+    test_Costs.jl:51-79): the oracle equals the set definition for every (j, j', k) and every hint (the partwise
+    "stacked" matrix of PartwiseCounts.jl restated), bound sandwich, Dynamic / BisectIndex optimal, Bisect within eps."""
+    rng = np.random.default_rng(20)
+    for trial in range(40):
+        m, n = int(rng.integers(1, 9)), int(rng.integers(1, 10))
+        A = sprand(rng, m, n, float(rng.choice([0.1, 0.3, 0.6])))
+        for K in [1, 2, 3, 4]:
+            Pi = ref.partition_stripe(ref.adjointpattern(A), K, cp.EquiSplitter())
+            mdl = [cp.AffinePrimaryConnectivityModel(0, 2, 1, 3, 6), cp.AffinePrimaryConnectivityModel(1, 1, 1, 1, 1),
+                   cp.AffinePrimaryConnectivityModel(0.0, 0.5, 1.0, 3.0, 6.5)][trial % 3]
+            Ck = {(k, j, jp): primary_cost(mdl, A, Pi, j, jp, k) for k in range(1, K + 1) for j in range(1, n + 2) for jp in range(j, n + 2)}
+            keys = list(Ck)
+            for hint in HINTS:
+                got = ref.oracle_query(mdl, A, [t[1] for t in keys], [t[2] for t in keys], [t[0] for t in keys], hint=hint, Pi=Pi)
+                assert got.tolist() == [float(Ck[t]) for t in keys]
+
+            def dp(total):
+                prev = {jp: Ck[(1, 1, jp)] for jp in range(1, n + 2)}
+                for k in range(2, K + 1):
+                    prev = {jp: min((prev[j] + Ck[(k, j, jp)]) if total else max(prev[j], Ck[(k, j, jp)]) for j in range(1, jp + 1)) for jp in range(1, n + 2)}
+                return prev[n + 1]
+
+            def value(spl, total):
+                v = [Ck[(k + 1, int(spl[k]), int(spl[k + 1]))] for k in range(K)]
+                return sum(v) if total else max(v)
+
+            for mtd, total, eps in [(cp.DynamicBottleneckSplitter(mdl), False, 0), (cp.DynamicTotalSplitter(mdl), True, 0),
+                                    (cp.BisectIndexBottleneckSplitter(mdl), False, 0), (cp.BisectCostBottleneckSplitter(mdl, 0.1), False, 0.1),
+                                    (cp.LazyBisectCostBottleneckSplitter(mdl, 0.01), False, 0.01)]:
+                Phi = ref.partition_stripe(A, K, mtd, Pi)
+                check_split(Phi.spl, n, K)
+                opt = dp(total)
+                assert opt <= value(Phi.spl, total) <= opt * (1 + eps), type(mtd).__name__
+                assert ref.bottleneck_value(A, Phi, mdl, Pi) == value(Phi.spl, False)
+
+
 def leftmost_chunk_dp(C, n, w_max):
     cst = np.full(n + 2, np.inf)
     cst[1] = 0
