@@ -525,6 +525,19 @@ def test_primary_connectivity_model(ref, fixtures):
                     assert cp.bottleneck_value(A, g, f, Pi) == ref.bottleneck_value(A, g, f, Pi)
 
 
+def test_plaid_with_primary_models(ref):
+    """A genuinely 2-D alternation (bin/test_table_bottleneck.jl:47-55 style): columns by connectivity, then rows and
+    columns in turn by the primary connectivity cost given the other side's partition."""
+    A = synth.erdos_renyi(1500, 5)
+    net = cp.AffineConnectivityModel(0, 10, 1, 100)
+    comm = cp.AffinePrimaryConnectivityModel(0, 10, 1, 0, 100)
+    for K in (4, 7):
+        meth = cp.AlternatingPartitioner(cp.LazyBisectCostBottleneckSplitter(net, 0.01), cp.BisectCostBottleneckSplitter(comm, 0.01),
+                                         cp.DynamicBottleneckSplitter(comm), cp.BisectIndexBottleneckSplitter(comm))
+        (Pg, Fg), (Pr, Fr) = cp.partition_plaid(A, K, meth), ref.partition_plaid(A, K, meth)
+        assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl), K
+
+
 def test_degenerate_inputs(ref):
     """Empty matrices, empty columns/rows, K > n, single column -- the ragged cases."""
     z = np.zeros(0, dtype=np.int64)
