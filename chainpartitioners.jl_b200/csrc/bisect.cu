@@ -220,6 +220,183 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The Flip family (costs that DEcrease as the part grows -- the secondary models): FlipBisectCostBottleneckSplitter
+// (BisectCostBottleneckSplitter.jl:70-127), LazyFlipBisectCostBottleneckSplitter (LazyBisect...:79-138) and
+// FlipBisectIndexBottleneckSplitter (BisectIndex...:87-166).  Each part is made as SHORT as the threshold allows.  These
+// run as one kernel on one cluster that follows the reference's sequential control flow (hard windows included), with
+// the 1024-way cluster search for "the smallest j' whose cost is <= c".
+// ------------------------------------------------------------------------------------------------
+// smallest x in [a, b] with c(j, x, k) <= c, b + 1 if none; a if the window is empty (the reference returns j'_lo).
+// The predicate is monotone (false ... false true ... true).
+template <class T>
+__device__ __forceinline__ i64 wide_search_flip(const DevOracle& o, cg::cluster_group& cluster, int (*s_cnt)[BS_CLUSTER], int& phase,
+                                                u32 j, i64 a, i64 b, double c, u32 k) {
+  const unsigned crank = cluster.block_rank();
+  if (a > b) return a;
+  while (true) {
+    const i64 S = b - a + 1;
+    const i64 stride = (S + BS_WIDTH - 1) / BS_WIDTH;
+    const i64 x = a + (i64)(crank * BS_THREADS + threadIdx.x) * stride;
+    bool bad = false;  // a candidate inside the window whose cost still exceeds c
+    if (x <= b) bad = !cost_leq(dev_cost<T>(o, j, (u32)x, k), c);
+    const int mine = __syncthreads_count(bad);
+    if (threadIdx.x < BS_CLUSTER) *cluster.map_shared_rank(&s_cnt[phase][crank], threadIdx.x) = mine;
+    cluster.sync();
+    int cf = 0;
+#pragma unroll
+    for (int p = 0; p < BS_CLUSTER; ++p) cf += s_cnt[phase][p];
+    phase ^= 1;
+    if (cf == 0) return a;                 // the first candidate already fits
+    const i64 xf = a + (i64)(cf - 1) * stride;  // last candidate that does not fit
+    if (stride == 1) return xf + 1;        // (= b + 1 if none fits)
+    a = xf + 1;
+    b = min(b, xf + stride);
+    if (a > b) return b + 1;
+  }
+}
+
+struct FlipResult {
+  int probes, rounds;
+};
+
+// mode 0: FlipBisectCost (windows spl_lo / spl_hi, answer spl_lo); mode 1: LazyFlipBisectCost (no windows, answer spl_hi)
+template <class T>
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
+    k_flip_bisect(const __grid_constant__ DevOracle o, int K, double eps1, double c_lo, double c_hi, int lazy, int* __restrict__ spl,
+                  int* __restrict__ spl_lo, int* __restrict__ spl_hi, int* __restrict__ probes_out) {
+  __shared__ int s_cnt[2][BS_CLUSTER];
+  cg::cluster_group cluster = cg::this_cluster();
+  const bool cta0 = cluster.block_rank() == 0;
+  const bool writer = cta0 && threadIdx.x == 0;
+  const i64 n1 = (i64)o.n + 1;
+  if (cta0)
+    for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) {
+      spl_lo[t] = (t == K + 1) ? (int)n1 : 1;
+      spl_hi[t] = (t == 1) ? 1 : (int)n1;
+      spl[t] = (t == 1) ? 1 : (t == K + 1 ? (int)n1 : 0);
+    }
+  __threadfence();
+  cluster.sync();
+  int phase = 0, probes = 0;
+  while (c_lo * eps1 < c_hi) {
+    const double c = (c_lo + c_hi) / 2;
+    ++probes;
+    bool feas;
+    if (!lazy) {  // BisectCost...:101-117
+      bool chk = true;
+      i64 j = 1;
+      for (int k = 1; k <= K - 1; ++k) {
+        const i64 a = max(j, (i64)__ldcg(spl_lo + k + 1));
+        const i64 b = __ldcg(spl_hi + k + 1);
+        const i64 r = wide_search_flip<T>(o, cluster, s_cnt, phase, (u32)j, a, b, c, (u32)k);
+        if (writer) spl[k + 1] = (int)r;
+        if (r > n1) {
+          chk = false;
+          if (cta0)
+            for (int t = k + 1 + threadIdx.x; t <= K; t += blockDim.x) spl[t] = (int)n1;
+          break;
+        }
+        j = r;
+      }
+      feas = chk && cost_leq(dev_cost<T>(o, (u32)j, (u32)n1, (u32)K), c);
+    } else {  // LazyBisect...:96-124: every part ends at the first position (not before the previous end) where it fits
+      feas = false;
+      i64 j = 1;
+      for (int k = 1; k <= K; ++k) {
+        const i64 r = wide_search_flip<T>(o, cluster, s_cnt, phase, (u32)j, j, n1, c, (u32)k);
+        if (r > n1) break;
+        if (k == K) { feas = true; break; }
+        if (writer) spl[k + 1] = (int)r;
+        j = r;
+      }
+    }
+    __syncthreads();
+    if (feas) c_hi = c; else c_lo = c;
+    if (cta0) {
+      int* dst = nullptr;
+      if (!lazy) dst = feas ? spl_lo : spl_hi;
+      else if (feas) dst = spl_hi;
+      if (dst) {
+        for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) dst[t] = (t == K + 1) ? (int)n1 : spl[t];
+        __threadfence();
+      }
+    }
+    cluster.sync();
+  }
+  if (writer) *probes_out = probes;
+  cluster.sync();
+}
+
+// FlipBisectIndexBottleneckSplitter (BisectIndex...:87-166)
+template <class T>
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
+    k_flip_bisect_index(const __grid_constant__ DevOracle o, int K, double c_lo, double c_hi, int* __restrict__ spl, int* __restrict__ spl_lo,
+                        int* __restrict__ spl_hi, int* __restrict__ probes_out) {
+  __shared__ int s_cnt[2][BS_CLUSTER];
+  cg::cluster_group cluster = cg::this_cluster();
+  const bool cta0 = cluster.block_rank() == 0;
+  const bool writer = cta0 && threadIdx.x == 0;
+  const i64 n1 = (i64)o.n + 1;
+  if (cta0)
+    for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) {
+      spl_lo[t] = (t == K + 1) ? (int)n1 : 1;
+      spl_hi[t] = (t == 1) ? 1 : (int)n1;
+      spl[t] = (t == 1) ? 1 : (t == K + 1 ? (int)n1 : 0);
+    }
+  __threadfence();
+  cluster.sync();
+  int phase = 0, probes = 0;
+  i64 sk = 1;
+  for (int k = 1; k <= K; ++k) {
+    i64 jp_hi = __ldcg(spl_hi + k + 1);
+    i64 jp_lo = max(sk, (i64)__ldcg(spl_lo + k + 1));
+    while (jp_lo <= jp_hi) {
+      const i64 jp = (jp_lo + jp_hi) >> 1;
+      const T c = dev_cost<T>(o, (u32)sk, (u32)jp, (u32)k);
+      const double cd = (double)c;
+      if (c_lo <= cd && cd < c_hi) {
+        ++probes;
+        bool chk = true;
+        if (writer) spl[k + 1] = (int)jp;
+        i64 j = jp;
+        for (int kk = k + 1; kk <= K - 1; ++kk) {
+          const i64 a = max(j, (i64)__ldcg(spl_lo + kk + 1));
+          const i64 b = __ldcg(spl_hi + kk + 1);
+          const i64 r = wide_search_flip<T>(o, cluster, s_cnt, phase, (u32)j, a, b, cd, (u32)kk);
+          if (writer) spl[kk + 1] = (int)r;
+          if (r > n1) {
+            chk = false;
+            if (cta0)
+              for (int t = kk + 1 + threadIdx.x; t <= K; t += blockDim.x) spl[t] = (int)n1;
+            break;
+          }
+          j = r;
+        }
+        const i64 ls = (k == K) ? sk : j, le = (k == K) ? jp : n1;
+        const bool feas = chk && cost_leq(dev_cost<T>(o, (u32)ls, (u32)le, (u32)K), cd);
+        __syncthreads();
+        if (feas) { c_hi = cd; jp_lo = jp + 1; } else { c_lo = cd; jp_hi = jp - 1; }
+        if (cta0) {
+          int* dst = feas ? spl_lo : spl_hi;
+          for (int t = 1 + threadIdx.x; t <= K + 1; t += blockDim.x) dst[t] = spl[t];
+          __threadfence();
+        }
+        cluster.sync();
+      } else if (cd >= c_hi) {
+        jp_lo = jp + 1;
+      } else {
+        jp_hi = jp - 1;
+      }
+    }
+    if (jp_lo > n1) break;
+    if (writer) spl[k + 1] = (int)jp_lo;
+    sk = jp_lo;
+  }
+  if (writer) *probes_out = probes;
+  cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Streaming probe (kernel "probe_stream"): the device form of the reference's lazy probes
 // (LazyBisectCostBottleneckSplitter.jl:194-229 connectivity, :323-359 monotonized symmetric).
 // (Here the link array holds 1 + the CSC POSITION of the previous nonzero of the same row, so "previous column < j"
@@ -1051,6 +1228,33 @@ void solve_bisect_index(Oracle& f, i64 K, int64_t* h_spl_out) {
   for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = h[k];
   g_bisect_stats[0] = 1; g_bisect_stats[1] = hp; g_bisect_stats[2] = hp;
   g_bisect_stats[3] = bnd[0]; g_bisect_stats[4] = bnd[1]; g_bisect_stats[5] = 0; g_bisect_stats[6] = 0; g_bisect_stats[7] = 0;
+}
+
+// method: CPB_SPLIT_FLIP_BISECT_COST, CPB_SPLIT_LAZY_FLIP_BISECT_COST or CPB_SPLIT_FLIP_BISECT_INDEX
+void solve_flip(Oracle& f, int method, double eps, i64 K, int64_t* h_spl_out) {
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  CPB_REQUIRE(f.dev.kind == CPB_MODEL_SECCONN, "the Flip splitters on the device serve the (decreasing) secondary connectivity model");
+  CPB_REQUIRE(f.mdl.coef[3] <= f.mdl.coef[4], "Flip splitters need a cost that does not grow with the part (beta_local_net <= beta_remote_net)");
+  const Matrix& A = *f.A;
+  CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
+  CPB_REQUIRE(K == f.pi_K, "the secondary model's row partition must have K parts");
+  oracle_ensure_ranks(f);
+  double bnd[2];
+  oracle_bound(f, K, bnd);
+  ProfScope prof("probe");
+  DBuf<int> spl(K + 2), spl_lo(K + 2), spl_hi(K + 2), probes(1);
+  const bool lazy = method == CPB_SPLIT_LAZY_FLIP_BISECT_COST;
+  if (method == CPB_SPLIT_FLIP_BISECT_INDEX) {
+    if (f.dev.is_float) CPB_LAUNCH(k_flip_bisect_index<double>, BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, bnd[0], bnd[1], spl.get(), spl_lo.get(), spl_hi.get(), probes.get());
+    else CPB_LAUNCH(k_flip_bisect_index<i64>, BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, bnd[0], bnd[1], spl.get(), spl_lo.get(), spl_hi.get(), probes.get());
+  } else {
+    if (f.dev.is_float) CPB_LAUNCH(k_flip_bisect<double>, BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, 1 + eps, bnd[0], bnd[1], lazy ? 1 : 0, spl.get(), spl_lo.get(), spl_hi.get(), probes.get());
+    else CPB_LAUNCH(k_flip_bisect<i64>, BS_CLUSTER, BS_THREADS, 0, f.dev, (int)K, 1 + eps, bnd[0], bnd[1], lazy ? 1 : 0, spl.get(), spl_lo.get(), spl_hi.get(), probes.get());
+  }
+  std::vector<int> h(K + 2);
+  CPB_CUDA(cudaMemcpyAsync(h.data(), (lazy ? spl_hi : spl_lo).get(), (K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (i64 k = 1; k <= K + 1; ++k) h_spl_out[k - 1] = h[k];
 }
 
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {

@@ -351,6 +351,9 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
     case CPB_SPLIT_BISECT_COST: solve_bisect(*f->O, false, eps, K, spl_out); break;
     case CPB_SPLIT_LAZY_BISECT_COST: solve_bisect(*f->O, true, eps, K, spl_out); break;
     case CPB_SPLIT_BISECT_INDEX: solve_bisect_index(*f->O, K, spl_out); break;
+    case CPB_SPLIT_FLIP_BISECT_COST: case CPB_SPLIT_LAZY_FLIP_BISECT_COST: case CPB_SPLIT_FLIP_BISECT_INDEX:
+      solve_flip(*f->O, method, eps, K, spl_out);
+      break;
     case CPB_SPLIT_EQUI: {  // EquiPartitioner.jl:3-9
       const i64 n = f->O->A->n;
       for (i64 k = 1; k <= K + 1; ++k) spl_out[k - 1] = (k - 1) * (n / K) + std::min(n % K, k - 1) + 1;

@@ -87,7 +87,9 @@ template <int TIE, class T> __device__ __forceinline__ bool tie_better(T ob, u32
 
 // total layer, one warp per j': scan of all j in [1, j'] with a rightmost-argmin reduction.
 // (O(n^2) oracle queries per layer; the monotone divide & conquer version replaces it for large n.)
-template <int TIE, class T>
+// MAXOP: the bottleneck recurrence (g = max) for costs the crossing search of k_dp_bottleneck cannot take (decreasing
+// secondary costs): the same exhaustive scan, O(n^2) queries per layer.
+template <int TIE, class T, bool MAXOP = false>
 __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
                                                   u32* __restrict__ ptr, u32 jp_first, u32 k) {
   const u32 n1 = o.n + 1;
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(256) k_dp_total(const __grid_constant__ DevOra
     u32 arg = 0;
     const u32 j_last = TIE == TIE_RIGHT ? jp : jp - 1;
     for (u32 j = 1 + lane; j <= j_last; j += 32) {
-      const T c = prev[j] + dev_cost<T>(o, j, jp, k);
+      const T cj = dev_cost<T>(o, j, jp, k);
+      const T c = MAXOP ? max(prev[j], cj) : prev[j] + cj;
       // ascending j within a lane: `<=` keeps the largest minimiser, `<` the smallest
       if (arg == 0 || (TIE == TIE_RIGHT ? c <= best : c < best)) { best = c; arg = j; }
     }
@@ -239,7 +242,11 @@ template <class T, int TIE> static void dynamic_T(Oracle& f, bool total, i64 K, 
   for (i64 k = 2; k <= K; ++k) {
     const u32 jp_first = (k == K) ? n1 : 1;  // DynamicSplitter.jl:34
     u32* p = ptr.get() + (size_t)(k - 1) * n2;
-    if (!total) {
+    if (!total && f.mdl.kind == CPB_MODEL_SECCONN) {  // decreasing costs: exhaustive scan with g = max
+      const size_t rows = (size_t)n1 - jp_first + 1;
+      const unsigned g = (unsigned)std::min<size_t>((rows * 32 + 255) / 256, (size_t)ctx().sm_count * 8);
+      CPB_LAUNCH((k_dp_total<TIE_RIGHT, T, true>), g, 256, 0, f.dev, prev, cur, p, jp_first, (u32)k);
+    } else if (!total) {
       const unsigned g = (k == K) ? 1 : grid;
       CPB_LAUNCH(k_dp_bottleneck<T>, g, 256, 0, f.dev, prev, cur, p, jp_first, (u32)k);
     } else if (monge && A.n > 64) {
@@ -346,7 +353,7 @@ void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int6
   }
   if (f.dev.kind == CPB_MODEL_BLOCK || f.dev.kind == CPB_MODEL_COLBLOCK)
     throw Error(CPB_ERR_UNSUPPORTED, "dynamic splitters need an affine random-access oracle");
-  if (!total) {
+  if (!total && f.mdl.kind != CPB_MODEL_SECCONN) {
     // the crossing search needs monotone costs: the same beta >= 0 the reference asserts in bound_stripe
     for (int t = 1; t <= 4; ++t)
       if (f.mdl.coef[t] < 0 && !(f.mdl.kind == CPB_MODEL_MONOSYM && t == 4))

@@ -43,6 +43,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
 enum { RANK_NET = 1, RANK_DIANET = 2, RANK_SELFNET = 3, RANK_SELFPIN = 4 };
 std::unique_ptr<RankStruct> build_rank(const Matrix& A, int which);
 std::unique_ptr<RankStruct> build_partwise_rank(const Matrix& A, const u32* asg, u32 K, DBuf<u32>& part_col, DBuf<u32>& part_start);
+void build_partwise_columns(const Matrix& A, const u32* asg, u32 K, DBuf<u32>& part_col, DBuf<u32>& part_start, DBuf<u32>& part_head);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
                         i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false, bool as_pos = false);
@@ -63,6 +64,9 @@ struct DevOracle {
   const u32* part_col;
   const u32* part_start;
   u32 n_parts;
+  // SECCONN: part_head[p] = number of distinct (part, column) pairs among the stacked elements before p; part_size[k] = rows of part k
+  const u32* part_head;
+  const u32* part_size;
   const i64* env;      // segment tree of packed (lo, hi) (ENVELOPE); envH = height
   int envH;
   double cf[5];
@@ -80,7 +84,7 @@ struct Oracle {
   cpb_model mdl{};
   std::vector<double> h_alpha_col, h_beta_col, h_beta_row;  // host copies of tables
   std::unique_ptr<RankStruct> net, dianet, selfnet, selfpin, lcn;
-  DBuf<u32> part_col, part_start;  // PRIMCONN (see DevOracle)
+  DBuf<u32> part_col, part_start, part_head;  // PRIMCONN / SECCONN (see DevOracle)
   std::unique_ptr<LinkStream> ls;  // links for the streaming probes (net or dia-net, by model)
   DBuf<u32> overpos;
   i64 h_n_over = -1;  // host copy of overpos[n] once it has been read
@@ -111,6 +115,7 @@ void count_query(Matrix& A, int which, i64 Q, const i64* d_j, const i64* d_jp, i
 // solvers (bisect.cu / dynamic.cu / chunk.cu)
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out);
 void solve_bisect_index(Oracle& f, i64 K, int64_t* h_spl_out);
+void solve_flip(Oracle& f, int method, double eps, i64 K, int64_t* h_spl_out);
 int probe_cluster_capacity(bool stream);
 struct BisectRun;
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl);
@@ -218,6 +223,22 @@ template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32
       const i64 d = dev_netcount(o.net, j, jp);
       const i64 l = dev_localnets(o, j, jp, k);
       return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)l * C::get(o, 3) + (T)(d - l) * C::get(o, 4);
+    }
+    case CPB_MODEL_SECCONN: {  // SecondaryConnectivityCosts.jl:19,83-90: everything but the local count is fixed by the row part
+      if (k < 1 || k > o.n_parts) return T(0);
+      const u32 s = __ldg(o.part_start + (k - 1)), e = __ldg(o.part_start + k);
+      auto lower = [&](u32 c0) {
+        u32 lo = s, hi = e;
+        while (lo < hi) {
+          const u32 mid = lo + ((hi - lo) >> 1);
+          if (__ldg(o.part_col + mid) < c0) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const u32 hs = __ldg(o.part_head + s);
+      const i64 d = (i64)__ldg(o.part_head + e) - (i64)hs;
+      const i64 l = (i64)__ldg(o.part_head + lower(jp - 1)) - (i64)__ldg(o.part_head + lower(j - 1));
+      return C::get(o, 0) + (T)(i64)__ldg(o.part_size + (k - 1)) * C::get(o, 1) + (T)(i64)(e - s) * C::get(o, 2) + (T)l * C::get(o, 3) + (T)(d - l) * C::get(o, 4);
     }
     case CPB_MODEL_ENVELOPE: {  // EnvelopeCosts.jl:20,66-73
       i64 lo, hi;

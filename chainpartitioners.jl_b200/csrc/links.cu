@@ -394,6 +394,33 @@ std::unique_ptr<RankStruct> build_partwise_rank(const Matrix& A, const u32* asg,
   return rs;
 }
 
+// SECCONN: the same regrouping without links; part_head = exclusive scan of "first element of its (part, column) pair"
+__global__ void k_part_heads(const u32* __restrict__ keys, const u32* __restrict__ col_s, size_t N, u32* __restrict__ flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p <= N; p += stride)
+    flags[p] = (p < N && (p == 0 || keys[p] != keys[p - 1] || col_s[p] != col_s[p - 1])) ? 1u : 0u;
+}
+__global__ void k_gather_u32(const u32* __restrict__ idx, const u32* __restrict__ src, size_t N, u32* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) out[p] = src[idx[p]];
+}
+void build_partwise_columns(const Matrix& A, const u32* asg, u32 K, DBuf<u32>& part_col, DBuf<u32>& part_start, DBuf<u32>& part_head) {
+  const size_t N = (size_t)A.N;
+  DBuf<u32> colidx(N), pid(N), k0(N), v0(N), k1(N), v1(N), flags(N + 1);
+  expand_columns(A.pos.get(), (u32)A.n, colidx.get(), N);
+  if (N) CPB_LAUNCH(k_part_ids, grid_for(N), 256, 0, A.row.get(), asg, N, pid.get());
+  const int which = radix_sort_pairs_iota(pid.get(), k0.get(), v0.get(), k1.get(), v1.get(), N, bits_for(K ? K - 1 : 0));
+  const u32* keys = which ? k1.get() : k0.get();
+  const u32* sq = which ? v1.get() : v0.get();
+  part_col.alloc(N + 1);
+  if (N) CPB_LAUNCH(k_gather_u32, grid_for(N), 256, 0, sq, colidx.get(), N, part_col.get());
+  part_start.alloc((size_t)K + 2);
+  segment_starts(keys, N, part_start.get(), K);
+  CPB_LAUNCH(k_part_heads, grid_for(N + 1), 256, 0, keys, part_col.get(), N, flags.get());
+  part_head.alloc(N + 1);
+  exclusive_scan_u32(flags.get(), part_head.get(), N + 1);
+}
+
 // adjointpattern(A) (util.jl:67-95): stable sort by row = CSC of the transpose
 __global__ void k_gather_cols(const u32* __restrict__ sq, const u32* __restrict__ colidx, size_t N, u32* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;

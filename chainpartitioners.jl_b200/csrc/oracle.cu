@@ -153,8 +153,9 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
       d.envH = H;
       break;
     }
-    case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:56-67: needs the row partition Pi
-      CPB_REQUIRE(pi_spl != nullptr && pi_K >= 1, "primary connectivity model needs a row partition (SplitPartition)");
+    case CPB_MODEL_SECCONN:
+    case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:56-67 / SecondaryConnectivityCosts.jl:67-81: need the row partition Pi
+      CPB_REQUIRE(pi_spl != nullptr && pi_K >= 1, "primary / secondary connectivity models need a row partition (SplitPartition)");
       CPB_REQUIRE(pi_spl[0] == 1 && pi_spl[pi_K] == A.m + 1, "row partition must cover rows 1..m");
       f->pi_K = pi_K;
       f->h_pi_spl.assign(pi_spl, pi_spl + pi_K + 1);
@@ -214,6 +215,14 @@ void oracle_ensure_ranks(Oracle& f) {
     case CPB_MODEL_SYMCONN: f.net = build_rank(A, RANK_NET); f.dianet = build_rank(A, RANK_DIANET); break;
     case CPB_MODEL_HYPEREDGE: f.net = build_rank(A, RANK_NET); f.selfnet = build_rank(A, RANK_SELFNET); break;
     case CPB_MODEL_SYMEDGECUT: f.selfpin = build_rank(A, RANK_SELFPIN); break;
+    case CPB_MODEL_SECCONN:
+      build_partwise_columns(A, f.pi_asg.get(), (u32)f.pi_K, f.part_col, f.part_start, f.part_head);
+      d.part_col = f.part_col.get();
+      d.part_start = f.part_start.get();
+      d.part_head = f.part_head.get();
+      d.part_size = f.pi_size.get();
+      d.n_parts = (u32)f.pi_K;
+      break;
     case CPB_MODEL_PRIMCONN:
       f.net = build_rank(A, RANK_NET);
       f.lcn = build_partwise_rank(A, f.pi_asg.get(), (u32)f.pi_K, f.part_col, f.part_start);
@@ -327,6 +336,24 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
         c_hi = c[0] + (T)A.n * c[1] + (T)A.N * c[2] + (T)nets_all * c[3];
       }
       c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
+      break;
+    }
+    case CPB_MODEL_SECCONN: {  // SecondaryConnectivityCosts.jl:44-65 (oracle form): maxima over the row parts
+      CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0 && c[4] >= 0, "negative beta (SecondaryConnectivityCosts.jl:50-53)");
+      oracle_ensure_ranks(f);
+      const i64 Kp = f.pi_K;
+      std::vector<u32> hs(Kp + 1), hh(Kp + 1), hz(Kp);
+      CPB_CUDA(cudaMemcpyAsync(hs.data(), f.part_start.get(), (Kp + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaMemcpyAsync(hz.data(), f.pi_size.get(), Kp * sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      for (i64 k = 0; k <= Kp; ++k) CPB_CUDA(cudaMemcpyAsync(&hh[k], f.part_head.get() + hs[k], sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      c_lo = 0; c_hi = 0;
+      for (i64 k = 0; k < std::min<i64>(K, Kp); ++k) {
+        const T base = c[0] + (T)(i64)hz[k] * c[1] + (T)(i64)(hs[k + 1] - hs[k]) * c[2];
+        c_lo = std::max(c_lo, base);
+        c_hi = std::max(c_hi, c[0] + (T)(i64)hz[k] * c[1] + (T)(i64)(hs[k + 1] - hs[k]) * c[2] + (T)(i64)(hh[k + 1] - hh[k]) * c[4]);
+      }
       break;
     }
     case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:31-42 (oracle form)

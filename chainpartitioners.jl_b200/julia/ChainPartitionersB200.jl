@@ -17,10 +17,11 @@ using ChainPartitioners
 import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_stripe,
     AffineWorkModel, AffineConnectivityModel, AffineMonotonizedSymmetricConnectivityModel,
     AffineSymmetricConnectivityModel, AffineHyperedgeCutModel, AffineSymmetricEdgeCutModel, AffineEnvelopeModel,
-    AffinePrimaryConnectivityModel,
+    AffinePrimaryConnectivityModel, AffineSecondaryConnectivityModel,
     ColumnBlockComponentCostModel, BlockComponentCostModel, block_component,
     ConstrainedCost, VertexCount, FeasibleCost, SplitPartition,
     DynamicBottleneckSplitter, DynamicTotalSplitter, BisectCostBottleneckSplitter, BisectIndexBottleneckSplitter, LazyBisectCostBottleneckSplitter,
+    FlipBisectCostBottleneckSplitter, LazyFlipBisectCostBottleneckSplitter, FlipBisectIndexBottleneckSplitter,
     DynamicBottleneckChunker, DynamicTotalChunker, ConvexTotalChunker, ConvexTotalSplitter, OverlapChunker, StrictChunker, EquiChunker, EquiSplitter
 
 const lib = get(ENV, "CHAINB200_LIB", "libchainb200.so")
@@ -66,6 +67,7 @@ cmodel(m::AffineHyperedgeCutModel{Tv}, args...) where {Tv} = affine(4, Tv, m.α,
 cmodel(m::AffineSymmetricEdgeCutModel{Tv}, args...) where {Tv} = affine(5, Tv, m.α, m.β_vertex, m.β_self_pin, m.β_cut_pin)
 cmodel(m::AffineEnvelopeModel{Tv}, args...) where {Tv} = affine(6, Tv, m.α, m.β_vertex, m.β_pin, m.β_net)
 cmodel(m::AffinePrimaryConnectivityModel{Tv}, args...) where {Tv} = affine(9, Tv, m.α, m.β_vertex, m.β_pin, m.β_local_net, m.β_remote_net)  # needs Π
+cmodel(m::AffineSecondaryConnectivityModel{Tv}, args...) where {Tv} = affine(10, Tv, m.α, m.β_vertex, m.β_pin, m.β_local_net, m.β_remote_net)  # needs Π
 
 # Functors cannot cross the ABI: tabulate block_component(f, w) (src/BlockCosts.jl:41-44) for w = 0..w_tab
 tab(f, hi) = Float64[w == 0 && !(f isa Function || f isa Number) ? 0.0 : block_component(f, w) for w in 0:hi]
@@ -147,6 +149,9 @@ split_code(m::BisectCostBottleneckSplitter) = (2, Float64(m.ϵ))
 split_code(m::LazyBisectCostBottleneckSplitter) = (3, Float64(m.ϵ))
 split_code(::ConvexTotalSplitter) = (8, 0.0)
 split_code(::BisectIndexBottleneckSplitter) = (12, 0.0)
+split_code(m::FlipBisectCostBottleneckSplitter) = (6, Float64(m.ϵ))          # Flip family: the secondary (decreasing) models
+split_code(m::LazyFlipBisectCostBottleneckSplitter) = (7, Float64(m.ϵ))
+split_code(::FlipBisectIndexBottleneckSplitter) = (13, 0.0)
 split_code(::DynamicBottleneckChunker) = (10, 0.0)   # partition_stripe(A, K, ::AbstractDynamicChunker), DynamicSplitter.jl:52-87
 split_code(::DynamicTotalChunker) = (11, 0.0)
 

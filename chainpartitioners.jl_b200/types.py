@@ -195,7 +195,7 @@ class StepHint(AbstractHint):
 # --------------------------------------------------------------------------- cost models
 
 MODEL_WORK, MODEL_CONNECTIVITY, MODEL_MONOSYM, MODEL_SYMCONN = 0, 1, 2, 3
-MODEL_HYPEREDGE, MODEL_SYMEDGECUT, MODEL_ENVELOPE, MODEL_COLBLOCK, MODEL_BLOCK, MODEL_PRIMCONN = 4, 5, 6, 7, 8, 9
+MODEL_HYPEREDGE, MODEL_SYMEDGECUT, MODEL_ENVELOPE, MODEL_COLBLOCK, MODEL_BLOCK, MODEL_PRIMCONN, MODEL_SECCONN = 4, 5, 6, 7, 8, 9, 10
 
 
 def _is_int(x) -> bool:
@@ -310,6 +310,15 @@ class AffinePrimaryConnectivityModel(_AffineModel):
     with a row partition (``oracle_stripe(mdl, A, Pi)``, ``partition_stripe(A, K, method, Pi)``)."""
 
     kind = MODEL_PRIMCONN
+    names = ("alpha", "beta_vertex", "beta_pin", "beta_local_net", "beta_remote_net")
+
+
+class AffineSecondaryConnectivityModel(_AffineModel):
+    """SecondaryConnectivityCosts.jl:5-19: the cost of part k seen from the other side -- vertex, pin and net totals of
+    row part k of Pi are fixed, only the number of its nets (columns) that fall inside the column range [i, i') -- the
+    local ones -- depends on the split; used as ``partition_stripe(adj_A, K, method, Phi)``."""
+
+    kind = MODEL_SECCONN
     names = ("alpha", "beta_vertex", "beta_pin", "beta_local_net", "beta_remote_net")
 
 
@@ -475,6 +484,12 @@ class BisectIndexBottleneckSplitter:
 
 
 @dataclass
+class FlipBisectIndexBottleneckSplitter:
+    """BisectIndexBottleneckSplitter.jl:83-85 (exact bottleneck for decreasing costs, :87-166)."""
+    f: Any
+
+
+@dataclass
 class LazyBisectCostBottleneckSplitter:
     """LazyBisectCostBottleneckSplitter.jl:1-4."""
     f: Any
@@ -598,7 +613,7 @@ class DisjointPacker:
 SPLIT_DYNAMIC_BOTTLENECK, SPLIT_DYNAMIC_TOTAL, SPLIT_BISECT_COST, SPLIT_LAZY_BISECT_COST = 0, 1, 2, 3
 SPLIT_LAZY_BISECT_GENERIC, SPLIT_EQUI, SPLIT_FLIP_BISECT_COST, SPLIT_LAZY_FLIP_BISECT_COST = 4, 5, 6, 7
 SPLIT_CONVEX_TOTAL, SPLIT_CONCAVE_TOTAL = 8, 9
-SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, SPLIT_DYNAMIC_TOTAL_CHUNKER, SPLIT_BISECT_INDEX = 10, 11, 12
+SPLIT_DYNAMIC_BOTTLENECK_CHUNKER, SPLIT_DYNAMIC_TOTAL_CHUNKER, SPLIT_BISECT_INDEX, SPLIT_FLIP_BISECT_INDEX = 10, 11, 12, 13
 PACK_DYNAMIC_TOTAL, PACK_CONVEX_TOTAL, PACK_CONCAVE_TOTAL, PACK_OVERLAP, PACK_STRICT, PACK_EQUI = 0, 1, 2, 3, 4, 5
 
 
@@ -612,6 +627,8 @@ def split_method_code(method) -> Tuple[int, Any, float]:
         return SPLIT_BISECT_COST, method.f, float(method.eps)
     if isinstance(method, BisectIndexBottleneckSplitter):
         return SPLIT_BISECT_INDEX, method.f, 0.0
+    if isinstance(method, FlipBisectIndexBottleneckSplitter):
+        return SPLIT_FLIP_BISECT_INDEX, method.f, 0.0
     if isinstance(method, FlipBisectCostBottleneckSplitter):
         return SPLIT_FLIP_BISECT_COST, method.f, float(method.eps)
     if isinstance(method, LazyBisectCostBottleneckSplitter):

@@ -43,6 +43,8 @@ enum {
   CPB_MODEL_ENVELOPE = 6,     /* AffineEnvelopeModel                      EnvelopeCosts.jl:5-20 */
   CPB_MODEL_COLBLOCK = 7,     /* ColumnBlockComponentCostModel            BlockCosts.jl:1-17 */
   CPB_MODEL_BLOCK = 8,        /* BlockComponentCostModel                  BlockCosts.jl:19-44 */
+  CPB_MODEL_SECCONN = 10,           /* AffineSecondaryConnectivityModel with a row partition Pi: the cost of row part k as a function of the column
+                                       range [i, i') that is local to it (decreasing)   SecondaryConnectivityCosts.jl:5-102 */
   CPB_MODEL_PRIMCONN = 9            /* AffinePrimaryConnectivityModel(a, b_v, b_p, b_local, b_remote) with a row partition Pi: a net of part k's
                                        columns is local if row part k owns it   PrimaryConnectivityCosts.jl:5-86, PartwiseCounts.jl:1-101 */
 };
@@ -139,7 +141,11 @@ enum {
      and `<=` tie rule as the splitter form with the part index as the inner loop -> identical split vectors */
   CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* partition_stripe(A, K, DynamicBottleneckChunker(f)) */
   CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11,      /* partition_stripe(A, K, DynamicTotalChunker(f)) */
-  CPB_SPLIT_BISECT_INDEX = 12                /* BisectIndexBottleneckSplitter(f): exact bottleneck   BisectIndexBottleneckSplitter.jl:5-81 */
+  CPB_SPLIT_BISECT_INDEX = 12,               /* BisectIndexBottleneckSplitter(f): exact bottleneck   BisectIndexBottleneckSplitter.jl:5-81 */
+  /* the Flip family: costs that DEcrease as the part grows (the secondary models) */
+  CPB_SPLIT_FLIP_BISECT_COST = 6,            /* FlipBisectCostBottleneckSplitter(f, eps)       BisectCostBottleneckSplitter.jl:70-127 */
+  CPB_SPLIT_LAZY_FLIP_BISECT_COST = 7,       /* LazyFlipBisectCostBottleneckSplitter(f, eps)   LazyBisectCostBottleneckSplitter.jl:79-138 */
+  CPB_SPLIT_FLIP_BISECT_INDEX = 13           /* FlipBisectIndexBottleneckSplitter(f)           BisectIndexBottleneckSplitter.jl:87-166 */
 };
 /* -> spl_out[K+1] (SplitPartition{Int64}(K, spl), Partitions.jl:3-6); con may be NULL. */
 int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, double eps, int64_t K, int64_t* spl_out);

@@ -125,6 +125,12 @@ template <class T, class Fn> static void with_oracle(const cpo_model* mdl, int h
     fn(f);
     return;
   }
+  if (mdl->kind == CPO_MODEL_SECCONN) {
+    if (!pi_spl) throw std::invalid_argument("secondary connectivity model needs a row partition");
+    SecondaryOracle<T> f(M, mdl, pi_spl, pi_K);
+    fn(f);
+    return;
+  }
   if (mdl->kind == CPO_MODEL_PRIMCONN) {
     if (!pi_spl) throw std::invalid_argument("primary connectivity model needs a row partition");
     with_dom(hint, [&](auto* tag) {
@@ -219,13 +225,14 @@ extern "C" int cpo_partition_stripe(int method, const cpo_model* mdl, const cpo_
             quadrangle_total_splitter<F, T>(f, n, K, method == CPO_SPLIT_CONCAVE_TOTAL, spl.data());
           });
           break;
-        case CPO_SPLIT_BISECT_INDEX:
+        case CPO_SPLIT_BISECT_INDEX: case CPO_SPLIT_FLIP_BISECT_INDEX:
           with_oracle<T>(mdl, CPO_HINT_SPARSE, M, pi_spl, pi_K, [&](auto& f) {
             using F = std::remove_reference_t<decltype(f)>;
             Model<T> m(mdl);
             bound_stripe<T>(M, K, m, &f, bnd);
             t1 = now_s();
-            bisect_index<F, T>(f, n, K, bnd, spl.data());
+            if (method == CPO_SPLIT_FLIP_BISECT_INDEX) flip_bisect_index<F, T>(f, n, K, bnd, spl.data());
+            else bisect_index<F, T>(f, n, K, bnd, spl.data());
           });
           break;
         case CPO_SPLIT_BISECT_COST: case CPO_SPLIT_FLIP_BISECT_COST:

@@ -47,7 +47,8 @@ enum {
   CPO_MODEL_ENVELOPE = 6,          /* AffineEnvelopeModel                 (EnvelopeCosts.jl:5-20) */
   CPO_MODEL_COLBLOCK = 7,          /* ColumnBlockComponentCostModel       (BlockCosts.jl:1-17) */
   CPO_MODEL_BLOCK = 8,             /* BlockComponentCostModel             (BlockCosts.jl:19-44) */
-  CPO_MODEL_PRIMCONN = 9           /* AffinePrimaryConnectivityModel + row partition (PrimaryConnectivityCosts.jl:5-19) */
+  CPO_MODEL_PRIMCONN = 9,          /* AffinePrimaryConnectivityModel + row partition (PrimaryConnectivityCosts.jl:5-19) */
+  CPO_MODEL_SECCONN = 10           /* AffineSecondaryConnectivityModel + row partition (SecondaryConnectivityCosts.jl:5-19) */
 };
 
 /* hints -> dominance structure (SparsePrefixMatrices.jl:450-458) */
@@ -70,7 +71,8 @@ enum {
   CPO_SPLIT_CONCAVE_TOTAL = 9,        /* ConcaveTotalChunker.jl:26-55 (ConcaveTotalSplitter) */
   CPO_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* DynamicSplitter.jl:52-87 with DynamicBottleneckChunker */
   CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER = 11,      /* DynamicSplitter.jl:52-87 with DynamicTotalChunker */
-  CPO_SPLIT_BISECT_INDEX = 12                /* BisectIndexBottleneckSplitter.jl:5-81 */
+  CPO_SPLIT_BISECT_INDEX = 12,               /* BisectIndexBottleneckSplitter.jl:5-81 */
+  CPO_SPLIT_FLIP_BISECT_INDEX = 13           /* BisectIndexBottleneckSplitter.jl:87-166 (FlipBisectIndexBottleneckSplitter) */
 };
 
 /* pack_stripe methods */

@@ -667,6 +667,64 @@ template <class Dom, class T> struct PrimaryOracle {
   inline T step_next_same(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
 };
 
+// SecondaryConnectivityCosts.jl:33-102 SecondaryConnectivityOracle: the cost of part k seen from the OTHER side.  The
+// matrix handed in is the one whose columns are being split (i, i'); its rows carry the partition Π.  For part k the
+// vertex, pin and net totals are fixed by Π (rows of the part, their nonzeros, the distinct columns they touch); only
+// the number of those columns that fall inside [i, i') -- the local ones -- depends on the split:
+//   c(i, i', k) = α + n_v(k) β_v + n_p(k) β_p + l β_local + (d(k) - l) β_remote,  l = #{columns of part k in [i, i')}.
+// With β_local < β_remote the cost DEcreases as the part grows (hence the Flip splitters).
+template <class T> struct SecondaryOracle {
+  const Mat& A;
+  Model<T> mdl;
+  i64 n, K;
+  ivec spl, pins, pios, prm;  // Π; nonzeros per row part; partwise column lists (PartwiseCounts.jl:1-67 with VertexCount)
+
+  SecondaryOracle(const Mat& A_, const cpo_model* s, const i64* pi_spl, i64 pi_K) : A(A_), mdl(s), n(A_.n), K(pi_K) {
+    if (pi_spl[0] != 1 || pi_spl[K] != A.m + 1) throw std::invalid_argument("row partition must cover rows 1..m");
+    spl.assign(K + 2, 0);
+    for (i64 k = 1; k <= K + 1; ++k) spl[k] = pi_spl[k - 1];
+    ivec asg(A.m + 1, 0);
+    for (i64 k = 1; k <= K; ++k)
+      for (i64 i = spl[k]; i < spl[k + 1]; ++i) asg[i] = k;
+    pins.assign(K + 2, 0);
+    std::vector<ivec> cols(K + 1);
+    ivec hst(K + 1, 0);
+    for (i64 j = 1; j <= A.n; ++j)
+      for (i64 q = A.pos[j]; q < A.pos[j + 1]; ++q) {
+        const i64 k = asg[A.idx[q]];
+        pins[k] += 1;  // = adj_pos[Π.spl[k+1]] - adj_pos[Π.spl[k]] (:85)
+        if (hst[k] != j) { cols[k].push_back(j); hst[k] = j; }
+      }
+    pios.assign(K + 2, 0);
+    prm.assign(1, 0);
+    for (i64 k = 1; k <= K; ++k) {
+      pios[k] = (i64)prm.size();
+      prm.insert(prm.end(), cols[k].begin(), cols[k].end());
+    }
+    pios[K + 1] = (i64)prm.size();
+  }
+  inline i64 rank_of(i64 k, i64 j) const { return std::lower_bound(prm.begin() + pios[k], prm.begin() + pios[k + 1], j) - prm.begin(); }
+  inline T operator()(i64 i, i64 ip, i64 k = 1) {  // :83-90
+    const i64 w = pins[k];
+    const i64 d = pios[k + 1] - pios[k];
+    const i64 l = rank_of(k, ip) - rank_of(k, i);  // lcc = VertexCount on the stacked columns
+    return mdl.eval4(spl[k + 1] - spl[k], w, l, d - l);
+  }
+  inline T step_same_next(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
+  inline T step_next_same(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
+  // bound_stripe(A, K, Π, ocl) :44-65
+  void bounds(double out[2]) const {
+    T c_lo = 0, c_hi = 0;
+    for (i64 k = 1; k <= K; ++k) {
+      const T base = mdl.c[0] + (T)(spl[k + 1] - spl[k]) * mdl.c[1] + (T)pins[k] * mdl.c[2];
+      c_lo = std::max(c_lo, base);
+      c_hi = std::max(c_hi, mdl.c[0] + (T)(spl[k + 1] - spl[k]) * mdl.c[1] + (T)pins[k] * mdl.c[2] + (T)(pios[k + 1] - pios[k]) * mdl.c[4]);
+    }
+    out[0] = (double)c_lo;
+    out[1] = (double)c_hi;
+  }
+};
+
 // BlockCosts.jl:46-142 BlockComponentCostStepOracle (stateful)
 template <class T> struct BlockOracle {
   const Mat& A;

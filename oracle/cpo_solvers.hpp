@@ -13,6 +13,9 @@ namespace cpo {
 template <class F> static auto nets_all(F& f, i64 n, int) -> decltype(f.net.at((i64)1, n)) { return f.net.at(1, n + 1); }
 template <class F> static i64 nets_all(F&, i64, long) { throw std::logic_error("this oracle has no net count"); }
 
+template <class F> static auto secondary_bounds(F& f, double out[2], int) -> decltype(f.bounds(out)) { f.bounds(out); }
+template <class F> static void secondary_bounds(F&, double*, long) { throw std::logic_error("not a secondary oracle"); }
+
 // ---- bound_stripe -----------------------------------------------------------
 // WorkCosts.jl:37-51; ConnectivityCosts.jl:22-35; MonotonizedSymmetricConnectivityCosts.jl:50-66,94-105;
 // EnvelopeCosts.jl:44-54.  Returned "./ 1" (BisectCostBottleneckSplitter.jl:39).
@@ -42,6 +45,12 @@ template <class T, class F> static void bound_stripe(const Mat& A, i64 K, const 
       c_hi = mdl.c[0] + mdl.c[1] * (T)n + mdl.c[2] * n_over + mdl.c[3] * (T)m;
       c_lo = mdl.c[0] + jl_fld(c_hi - mdl.c[0], (T)K);
       break;
+    }
+    case CPO_MODEL_SECCONN: {  // SecondaryConnectivityCosts.jl:44-65 (oracle form)
+      if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0 && mdl.c[4] >= 0)) throw std::invalid_argument("negative beta");
+      if (!ocl) throw std::logic_error("secondary connectivity bound needs an oracle");
+      secondary_bounds(*ocl, out, 0);
+      return;
     }
     case CPO_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:31-42 (oracle form)
       if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0 && mdl.c[4] >= 0)) throw std::invalid_argument("negative beta");
@@ -351,6 +360,61 @@ template <class F, class T> static void bisect_index(F& f, i64 n, i64 K, const d
   }
   for (i64 k = 1; k <= K + 1; ++k) out[k] = spl_hi[k];
   if (n_probes) *n_probes = np;
+}
+
+// BisectIndexBottleneckSplitter.jl:87-166 FlipBisectIndexBottleneckSplitter: the same search for costs that DEcrease as
+// the part grows (every part as short as the threshold allows)
+template <class F, class T> static void flip_bisect_index(F& f, i64 n, i64 K, const double bnd[2], i64* out) {
+  auto search = [&](i64 j, i64 lo, i64 hi, i64 k, T c) -> i64 {  // :96-109: smallest j' with f <= c, hi + 1 if none
+    lo = std::max(j, lo);
+    while (lo <= hi) {
+      i64 jp = fld2(lo + hi);
+      if (f(j, jp, k) <= c) hi = jp - 1; else lo = jp + 1;
+    }
+    return lo;
+  };
+  ivec spl_lo(K + 2, 1), spl_hi(K + 2, n + 1), spl(K + 2, 0);
+  spl_lo[K + 1] = n + 1;
+  spl_hi[1] = 1;
+  spl[1] = 1;
+  spl[K + 1] = n + 1;
+  double c_lo = bnd[0], c_hi = bnd[1];
+  for (i64 k = 1; k <= K; ++k) {
+    i64 jp_hi = spl_hi[k + 1];
+    i64 jp_lo = std::max(spl[k], spl_lo[k + 1]);
+    while (jp_lo <= jp_hi) {
+      const i64 jp = fld2(jp_lo + jp_hi);
+      const T c = f(spl[k], jp, k);
+      if (c_lo <= (double)c && (double)c < c_hi) {
+        bool chk = true;
+        spl[k + 1] = jp;
+        for (i64 kk = k + 1; kk <= K - 1; ++kk) {
+          spl[kk + 1] = search(spl[kk], spl_lo[kk + 1], spl_hi[kk + 1], kk, c);
+          if (spl[kk + 1] > n + 1) {
+            chk = false;
+            for (i64 t = kk + 1; t <= K; ++t) spl[t] = n + 1;
+            break;
+          }
+        }
+        if (chk && f(spl[K], spl[K + 1], K) <= c) {
+          c_hi = (double)c;
+          jp_lo = jp + 1;
+          spl_lo = spl;
+        } else {
+          c_lo = (double)c;
+          jp_hi = jp - 1;
+          spl_hi = spl;
+        }
+      } else if ((double)c >= c_hi) {
+        jp_lo = jp + 1;
+      } else {
+        jp_hi = jp - 1;
+      }
+    }
+    if (jp_lo > n + 1) break;
+    spl[k + 1] = jp_lo;
+  }
+  for (i64 k = 1; k <= K + 1; ++k) out[k] = spl_lo[k];
 }
 
 // LazyBisectCostBottleneckSplitter.jl:8-70 (generic step-oracle probe)

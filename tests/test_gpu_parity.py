@@ -525,6 +525,32 @@ def test_primary_connectivity_model(ref, fixtures):
                     assert cp.bottleneck_value(A, g, f, Pi) == ref.bottleneck_value(A, g, f, Pi)
 
 
+def test_secondary_connectivity_model_and_flip_splitters(ref, fixtures):
+    """AffineSecondaryConnectivityModel with a row partition (SecondaryConnectivityCosts.jl:5-102) and the Flip family
+    (BisectCost...:70-127, LazyBisect...:79-138, BisectIndex...:87-166): queries with the part index, bound_stripe, and
+    identical split vectors for every splitter of test_Partitioners.jl:131-148."""
+    rng = np.random.default_rng(306)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 10, 0.3), sprand(rng, 8, 3, 0.5), sprand(rng, 40, 120, 0.1),
+            synth.erdos_renyi(2000, 5)]
+    for A in mats:
+        for K in [1, 2, 3, 8]:
+            Pi = prim_partitions(ref, A, K)
+            for f in [cp.AffineSecondaryConnectivityModel(0, 2, 1, 3, 6), cp.AffineSecondaryConnectivityModel(1, 1, 1, 1, 1),
+                      cp.AffineSecondaryConnectivityModel(0.0, 0.5, 1.0, 3.0, 6.5)]:
+                j, jp = rand_pairs(rng, A.n, 300)
+                k = rng.integers(1, K + 1, 300)
+                ocl = cp.oracle_stripe(f, A, Pi)
+                assert np.array_equal(ocl.query(j, jp, k), ref.oracle_query(f, A, j, jp, k, Pi=Pi))
+                ocl.close()
+                mtds = [cp.FlipBisectIndexBottleneckSplitter(f), cp.FlipBisectCostBottleneckSplitter(f, 0.1), cp.FlipBisectCostBottleneckSplitter(f, 0.001),
+                        cp.LazyFlipBisectCostBottleneckSplitter(f, 0.1), cp.LazyFlipBisectCostBottleneckSplitter(f, 0.001)]
+                if A.n <= 500:
+                    mtds.append(cp.DynamicBottleneckSplitter(f))
+                for mtd in mtds:
+                    g, r = cp.partition_stripe(A, K, mtd, Pi), ref.partition_stripe(A, K, mtd, Pi)
+                    assert np.array_equal(g.spl, r.spl), (A, f, K, type(mtd).__name__, g.spl, r.spl)
+
+
 def test_plaid_with_primary_models(ref):
     """A genuinely 2-D alternation (bin/test_table_bottleneck.jl:47-55 style): columns by connectivity, then rows and
     columns in turn by the primary connectivity cost given the other side's partition."""

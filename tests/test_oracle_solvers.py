@@ -389,6 +389,49 @@ def test_primary_connectivity_oracle_and_solvers(ref, fixtures):
                 assert ref.bottleneck_value(A, Phi, mdl, Pi) == value(Phi.spl, False)
 
 
+def secondary_cost(mdl, M, Pi, i, ip, k):
+    """SecondaryConnectivityCosts.jl:19,83-90 from the set definition: rows, pins and touched columns of row part k are
+    fixed; the touched columns inside [i, i') are local."""
+    c = mdl.coef
+    cols, pins = set(), 0
+    for j in range(1, M.n + 1):
+        hit = [r for r in col_rows(M, j) if Pi.spl[k - 1] <= r < Pi.spl[k]]
+        pins += len(hit)
+        if hit:
+            cols.add(j)
+    l = sum(1 for j in cols if i <= j < ip)
+    return c[0] + int(Pi.spl[k] - Pi.spl[k - 1]) * c[1] + pins * c[2] + l * c[3] + (len(cols) - l) * c[4]
+
+
+def test_secondary_connectivity_oracle_and_flip_solvers(ref):
+    """AffineSecondaryConnectivityModel + the Flip family (test_Partitioners.jl:115-148, test_Costs.jl:51-79): oracle equals
+    the set definition, bounds bracket the optimum, DynamicBottleneck / FlipBisectIndex optimal, FlipBisectCost and
+    LazyFlipBisectCost within eps."""
+    rng = np.random.default_rng(22)
+    for trial in range(40):
+        m, n = int(rng.integers(1, 9)), int(rng.integers(1, 10))
+        A = sprand(rng, m, n, float(rng.choice([0.1, 0.3, 0.6])))
+        for K in [1, 2, 3, 4]:
+            Pi = ref.partition_stripe(ref.adjointpattern(A), K, cp.EquiSplitter())
+            mdl = [cp.AffineSecondaryConnectivityModel(0, 2, 1, 3, 6), cp.AffineSecondaryConnectivityModel(1, 1, 1, 1, 1),
+                   cp.AffineSecondaryConnectivityModel(0.0, 0.5, 1.0, 3.0, 6.5)][trial % 3]
+            Ck = {(k, i, ip): secondary_cost(mdl, A, Pi, i, ip, k) for k in range(1, K + 1) for i in range(1, n + 2) for ip in range(i, n + 2)}
+            keys = list(Ck)
+            got = ref.oracle_query(mdl, A, [t[1] for t in keys], [t[2] for t in keys], [t[0] for t in keys], Pi=Pi)
+            assert got.tolist() == [float(Ck[t]) for t in keys]
+            prev = {jp: Ck[(1, 1, jp)] for jp in range(1, n + 2)}
+            for k in range(2, K + 1):
+                prev = {jp: min(max(prev[j], Ck[(k, j, jp)]) for j in range(1, jp + 1)) for jp in range(1, n + 2)}
+            opt = prev[n + 1]
+            for mtd, eps in [(cp.DynamicBottleneckSplitter(mdl), 0), (cp.FlipBisectIndexBottleneckSplitter(mdl), 0),
+                             (cp.FlipBisectCostBottleneckSplitter(mdl, 0.01), 0.01), (cp.LazyFlipBisectCostBottleneckSplitter(mdl, 0.01), 0.01),
+                             (cp.FlipBisectCostBottleneckSplitter(mdl, 0.1), 0.1), (cp.LazyFlipBisectCostBottleneckSplitter(mdl, 0.1), 0.1)]:
+                Phi = ref.partition_stripe(A, K, mtd, Pi)
+                check_split(Phi.spl, n, K)
+                v = max(Ck[(k + 1, int(Phi.spl[k]), int(Phi.spl[k + 1]))] for k in range(K))
+                assert opt <= v <= opt * (1 + eps), type(mtd).__name__
+
+
 def leftmost_chunk_dp(C, n, w_max):
     cst = np.full(n + 2, np.inf)
     cst[1] = 0
