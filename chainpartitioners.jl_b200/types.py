@@ -574,6 +574,16 @@ class AlternatingPartitioner:
         self.mtds = mtds
 
 
+class AlternatingNetPartitioner(AlternatingPartitioner):
+    """AlternatingPartitioner.jl:34-57: AlternatingPartitioner that shares one net count of ``A`` between the solves
+    (``net=`` keyword).  The hint only chooses a CPU data structure in the reference; the result is the alternation's."""
+
+    def __init__(self, *mtds):
+        if mtds and isinstance(mtds[0], (NoHint, SparseHint, StepHint, RandomHint)):
+            mtds = mtds[1:]
+        super().__init__(*mtds)
+
+
 class SymmetricPartitioner:
     """AlternatingPartitioner.jl:59-69."""
 

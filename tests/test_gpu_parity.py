@@ -564,6 +564,20 @@ def test_plaid_with_primary_models(ref):
         assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl), K
 
 
+def test_two_dimensional_pipeline(ref):
+    """bin/test_table_bottleneck.jl:36-37: columns by nets, then rows / columns in turn by the primary (communication) and
+    secondary (locality) costs given the other side's partition, with the exact index splitters."""
+    A = synth.erdos_renyi(1200, 5)
+    net = cp.AffineConnectivityModel(0, 10, 1, 100)
+    comm = cp.AffinePrimaryConnectivityModel(0, 10, 1, 0, 100)
+    loc = cp.AffineSecondaryConnectivityModel(0, 10, 1, 0, 100)
+    for K in (3, 6):
+        meth = cp.AlternatingNetPartitioner(cp.SparseHint(), cp.BisectIndexBottleneckSplitter(net), cp.FlipBisectIndexBottleneckSplitter(loc),
+                                            cp.BisectIndexBottleneckSplitter(comm), cp.FlipBisectIndexBottleneckSplitter(loc))
+        (Pg, Fg), (Pr, Fr) = cp.partition_plaid(A, K, meth), ref.partition_plaid(A, K, meth)
+        assert np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl), K
+
+
 def test_degenerate_inputs(ref):
     """Empty matrices, empty columns/rows, K > n, single column -- the ragged cases."""
     z = np.zeros(0, dtype=np.int64)
