@@ -1233,8 +1233,11 @@ void solve_bisect_index(Oracle& f, i64 K, int64_t* h_spl_out) {
 // method: CPB_SPLIT_FLIP_BISECT_COST, CPB_SPLIT_LAZY_FLIP_BISECT_COST or CPB_SPLIT_FLIP_BISECT_INDEX
 void solve_flip(Oracle& f, int method, double eps, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
-  CPB_REQUIRE(f.dev.kind == CPB_MODEL_SECCONN, "the Flip splitters on the device serve the (decreasing) secondary connectivity model");
-  CPB_REQUIRE(f.mdl.coef[3] <= f.mdl.coef[4], "Flip splitters need a cost that does not grow with the part (beta_local_net <= beta_remote_net)");
+  CPB_REQUIRE(f.dev.kind == CPB_MODEL_SECCONN || f.dev.kind == CPB_MODEL_SECEDGE, "the Flip splitters on the device serve the (decreasing) secondary models");
+  if (f.dev.kind == CPB_MODEL_SECCONN)
+    CPB_REQUIRE(f.mdl.coef[3] <= f.mdl.coef[4], "Flip splitters need a cost that does not grow with the part (beta_local_net <= beta_remote_net)");
+  else
+    CPB_REQUIRE(f.mdl.coef[2] <= f.mdl.coef[3], "Flip splitters need a cost that does not grow with the part (beta_self_pin <= beta_cut_pin)");
   const Matrix& A = *f.A;
   CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
   CPB_REQUIRE(K == f.pi_K, "the secondary model's row partition must have K parts");

@@ -242,7 +242,7 @@ template <class T, int TIE> static void dynamic_T(Oracle& f, bool total, i64 K, 
   for (i64 k = 2; k <= K; ++k) {
     const u32 jp_first = (k == K) ? n1 : 1;  // DynamicSplitter.jl:34
     u32* p = ptr.get() + (size_t)(k - 1) * n2;
-    if (!total && f.mdl.kind == CPB_MODEL_SECCONN) {  // decreasing costs: exhaustive scan with g = max
+    if (!total && (f.mdl.kind == CPB_MODEL_SECCONN || f.mdl.kind == CPB_MODEL_SECEDGE)) {  // decreasing costs: exhaustive scan with g = max
       const size_t rows = (size_t)n1 - jp_first + 1;
       const unsigned g = (unsigned)std::min<size_t>((rows * 32 + 255) / 256, (size_t)ctx().sm_count * 8);
       CPB_LAUNCH((k_dp_total<TIE_RIGHT, T, true>), g, 256, 0, f.dev, prev, cur, p, jp_first, (u32)k);
@@ -353,7 +353,7 @@ void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int6
   }
   if (f.dev.kind == CPB_MODEL_BLOCK || f.dev.kind == CPB_MODEL_COLBLOCK)
     throw Error(CPB_ERR_UNSUPPORTED, "dynamic splitters need an affine random-access oracle");
-  if (!total && f.mdl.kind != CPB_MODEL_SECCONN) {
+  if (!total && f.mdl.kind != CPB_MODEL_SECCONN && f.mdl.kind != CPB_MODEL_SECEDGE) {
     // the crossing search needs monotone costs: the same beta >= 0 the reference asserts in bound_stripe
     for (int t = 1; t <= 4; ++t)
       if (f.mdl.coef[t] < 0 && !(f.mdl.kind == CPB_MODEL_MONOSYM && t == 4))

@@ -240,6 +240,22 @@ template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32
       const i64 l = (i64)__ldg(o.part_head + lower(jp - 1)) - (i64)__ldg(o.part_head + lower(j - 1));
       return C::get(o, 0) + (T)(i64)__ldg(o.part_size + (k - 1)) * C::get(o, 1) + (T)(i64)(e - s) * C::get(o, 2) + (T)l * C::get(o, 3) + (T)(d - l) * C::get(o, 4);
     }
+    case CPB_MODEL_PRIMEDGE:    // PrimaryEdgeCutCosts.jl:18,50-56: self pins = part k's nonzeros inside the column range
+    case CPB_MODEL_SECEDGE: {   // SecondaryEdgeCutCosts.jl:18,78-85: vertices and pins of row part k are fixed
+      if (k < 1 || k > o.n_parts) return T(0);
+      const u32 s = __ldg(o.part_start + (k - 1)), e = __ldg(o.part_start + k);
+      auto lower = [&](u32 c0) {
+        u32 lo = s, hi = e;
+        while (lo < hi) {
+          const u32 mid = lo + ((hi - lo) >> 1);
+          if (__ldg(o.part_col + mid) < c0) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const i64 l = (i64)lower(jp - 1) - (i64)lower(j - 1);
+      if (o.kind == CPB_MODEL_PRIMEDGE) return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)l * C::get(o, 2) + (T)(np - l) * C::get(o, 3);
+      return C::get(o, 0) + (T)(i64)__ldg(o.part_size + (k - 1)) * C::get(o, 1) + (T)l * C::get(o, 2) + (T)((i64)(e - s) - l) * C::get(o, 3);
+    }
     case CPB_MODEL_ENVELOPE: {  // EnvelopeCosts.jl:20,66-73
       i64 lo, hi;
       dev_envelope(o, j, jp, lo, hi);

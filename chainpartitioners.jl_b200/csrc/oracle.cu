@@ -153,6 +153,8 @@ std::unique_ptr<Oracle> oracle_create(Matrix& A, const cpb_model* mdl, const int
       d.envH = H;
       break;
     }
+    case CPB_MODEL_PRIMEDGE:
+    case CPB_MODEL_SECEDGE:
     case CPB_MODEL_SECCONN:
     case CPB_MODEL_PRIMCONN: {  // PrimaryConnectivityCosts.jl:56-67 / SecondaryConnectivityCosts.jl:67-81: need the row partition Pi
       CPB_REQUIRE(pi_spl != nullptr && pi_K >= 1, "primary / secondary connectivity models need a row partition (SplitPartition)");
@@ -215,6 +217,8 @@ void oracle_ensure_ranks(Oracle& f) {
     case CPB_MODEL_SYMCONN: f.net = build_rank(A, RANK_NET); f.dianet = build_rank(A, RANK_DIANET); break;
     case CPB_MODEL_HYPEREDGE: f.net = build_rank(A, RANK_NET); f.selfnet = build_rank(A, RANK_SELFNET); break;
     case CPB_MODEL_SYMEDGECUT: f.selfpin = build_rank(A, RANK_SELFPIN); break;
+    case CPB_MODEL_PRIMEDGE:
+    case CPB_MODEL_SECEDGE:
     case CPB_MODEL_SECCONN:
       build_partwise_columns(A, f.pi_asg.get(), (u32)f.pi_K, f.part_col, f.part_start, f.part_head);
       d.part_col = f.part_col.get();
@@ -336,6 +340,27 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
         c_hi = c[0] + (T)A.n * c[1] + (T)A.N * c[2] + (T)nets_all * c[3];
       }
       c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
+      break;
+    }
+    case CPB_MODEL_PRIMEDGE: {  // PrimaryEdgeCutCosts.jl:29-40
+      CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0, "negative beta (PrimaryEdgeCutCosts.jl:33-35)");
+      c_hi = c[0] + c[1] * (T)A.n + std::max(c[2], c[3]) * (T)A.N;
+      c_lo = c[0] + jl_fld(c[1] * (T)A.n + std::min(c[2], c[3]) * (T)A.N, (T)K);
+      break;
+    }
+    case CPB_MODEL_SECEDGE: {  // SecondaryEdgeCutCosts.jl:43-60 (oracle form)
+      CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0, "negative beta (SecondaryEdgeCutCosts.jl:49-51)");
+      oracle_ensure_ranks(f);
+      const i64 Kp = f.pi_K;
+      std::vector<u32> hs(Kp + 1), hz(Kp);
+      CPB_CUDA(cudaMemcpyAsync(hs.data(), f.part_start.get(), (Kp + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaMemcpyAsync(hz.data(), f.pi_size.get(), Kp * sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      c_lo = 0; c_hi = 0;
+      for (i64 k = 0; k < std::min<i64>(K, Kp); ++k) {
+        c_lo = std::max(c_lo, c[0] + (T)(i64)hz[k] * c[1] + (T)(i64)(hs[k + 1] - hs[k]) * std::min(c[2], c[3]));
+        c_hi = std::max(c_hi, c[0] + (T)(i64)hz[k] * c[1] + (T)(i64)(hs[k + 1] - hs[k]) * std::max(c[2], c[3]));
+      }
       break;
     }
     case CPB_MODEL_SECCONN: {  // SecondaryConnectivityCosts.jl:44-65 (oracle form): maxima over the row parts

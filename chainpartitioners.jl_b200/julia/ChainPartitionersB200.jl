@@ -17,7 +17,7 @@ using ChainPartitioners
 import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_stripe,
     AffineWorkModel, AffineConnectivityModel, AffineMonotonizedSymmetricConnectivityModel,
     AffineSymmetricConnectivityModel, AffineHyperedgeCutModel, AffineSymmetricEdgeCutModel, AffineEnvelopeModel,
-    AffinePrimaryConnectivityModel, AffineSecondaryConnectivityModel,
+    AffinePrimaryConnectivityModel, AffineSecondaryConnectivityModel, AffinePrimaryEdgeCutModel, AffineSecondaryEdgeCutModel,
     ColumnBlockComponentCostModel, BlockComponentCostModel, block_component,
     ConstrainedCost, VertexCount, FeasibleCost, SplitPartition,
     DynamicBottleneckSplitter, DynamicTotalSplitter, BisectCostBottleneckSplitter, BisectIndexBottleneckSplitter, LazyBisectCostBottleneckSplitter,
@@ -68,6 +68,8 @@ cmodel(m::AffineSymmetricEdgeCutModel{Tv}, args...) where {Tv} = affine(5, Tv, m
 cmodel(m::AffineEnvelopeModel{Tv}, args...) where {Tv} = affine(6, Tv, m.α, m.β_vertex, m.β_pin, m.β_net)
 cmodel(m::AffinePrimaryConnectivityModel{Tv}, args...) where {Tv} = affine(9, Tv, m.α, m.β_vertex, m.β_pin, m.β_local_net, m.β_remote_net)  # needs Π
 cmodel(m::AffineSecondaryConnectivityModel{Tv}, args...) where {Tv} = affine(10, Tv, m.α, m.β_vertex, m.β_pin, m.β_local_net, m.β_remote_net)  # needs Π
+cmodel(m::AffinePrimaryEdgeCutModel{Tv}, args...) where {Tv} = affine(11, Tv, m.α, m.β_vertex, m.β_self_pin, m.β_cut_pin)  # needs Π
+cmodel(m::AffineSecondaryEdgeCutModel{Tv}, args...) where {Tv} = affine(12, Tv, m.α, m.β_vertex, m.β_self_pin, m.β_cut_pin)  # needs Π
 
 # Functors cannot cross the ABI: tabulate block_component(f, w) (src/BlockCosts.jl:41-44) for w = 0..w_tab
 tab(f, hi) = Float64[w == 0 && !(f isa Function || f isa Number) ? 0.0 : block_component(f, w) for w in 0:hi]

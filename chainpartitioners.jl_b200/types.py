@@ -196,6 +196,7 @@ class StepHint(AbstractHint):
 
 MODEL_WORK, MODEL_CONNECTIVITY, MODEL_MONOSYM, MODEL_SYMCONN = 0, 1, 2, 3
 MODEL_HYPEREDGE, MODEL_SYMEDGECUT, MODEL_ENVELOPE, MODEL_COLBLOCK, MODEL_BLOCK, MODEL_PRIMCONN, MODEL_SECCONN = 4, 5, 6, 7, 8, 9, 10
+MODEL_PRIMEDGE, MODEL_SECEDGE = 11, 12
 
 
 def _is_int(x) -> bool:
@@ -320,6 +321,22 @@ class AffineSecondaryConnectivityModel(_AffineModel):
 
     kind = MODEL_SECCONN
     names = ("alpha", "beta_vertex", "beta_pin", "beta_local_net", "beta_remote_net")
+
+
+class AffinePrimaryEdgeCutModel(_AffineModel):
+    """PrimaryEdgeCutCosts.jl:5-18: ``alpha + n_vertices*beta_vertex + n_self_pins*beta_self_pin + n_cut_pins*beta_cut_pin``;
+    a pin of part k's columns is a self pin if row part k of Pi owns its row."""
+
+    kind = MODEL_PRIMEDGE
+    names = ("alpha", "beta_vertex", "beta_self_pin", "beta_cut_pin")
+
+
+class AffineSecondaryEdgeCutModel(_AffineModel):
+    """SecondaryEdgeCutCosts.jl:5-18: the same seen from the other side (vertices and pins of row part k fixed, its pins
+    inside the column range [i, i') are the self pins)."""
+
+    kind = MODEL_SECEDGE
+    names = ("alpha", "beta_vertex", "beta_self_pin", "beta_cut_pin")
 
 
 class AffineEnvelopeModel(_AffineModel):

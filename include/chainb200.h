@@ -45,6 +45,8 @@ enum {
   CPB_MODEL_BLOCK = 8,        /* BlockComponentCostModel                  BlockCosts.jl:19-44 */
   CPB_MODEL_SECCONN = 10,           /* AffineSecondaryConnectivityModel with a row partition Pi: the cost of row part k as a function of the column
                                        range [i, i') that is local to it (decreasing)   SecondaryConnectivityCosts.jl:5-102 */
+  CPB_MODEL_PRIMEDGE = 11,          /* AffinePrimaryEdgeCutModel(a, b_v, b_self_pin, b_cut_pin) with Pi      PrimaryEdgeCutCosts.jl:5-66 */
+  CPB_MODEL_SECEDGE = 12,           /* AffineSecondaryEdgeCutModel(a, b_v, b_self_pin, b_cut_pin) with Pi    SecondaryEdgeCutCosts.jl:5-97 */
   CPB_MODEL_PRIMCONN = 9            /* AffinePrimaryConnectivityModel(a, b_v, b_p, b_local, b_remote) with a row partition Pi: a net of part k's
                                        columns is local if row part k owns it   PrimaryConnectivityCosts.jl:5-86, PartwiseCounts.jl:1-101 */
 };

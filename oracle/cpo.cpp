@@ -125,6 +125,12 @@ template <class T, class Fn> static void with_oracle(const cpo_model* mdl, int h
     fn(f);
     return;
   }
+  if (mdl->kind == CPO_MODEL_PRIMEDGE || mdl->kind == CPO_MODEL_SECEDGE) {
+    if (!pi_spl) throw std::invalid_argument("primary / secondary edge-cut models need a row partition");
+    EdgeCutPartOracle<T> f(M, mdl, pi_spl, pi_K, mdl->kind == CPO_MODEL_SECEDGE);
+    fn(f);
+    return;
+  }
   if (mdl->kind == CPO_MODEL_SECCONN) {
     if (!pi_spl) throw std::invalid_argument("secondary connectivity model needs a row partition");
     SecondaryOracle<T> f(M, mdl, pi_spl, pi_K);

@@ -48,7 +48,9 @@ enum {
   CPO_MODEL_COLBLOCK = 7,          /* ColumnBlockComponentCostModel       (BlockCosts.jl:1-17) */
   CPO_MODEL_BLOCK = 8,             /* BlockComponentCostModel             (BlockCosts.jl:19-44) */
   CPO_MODEL_PRIMCONN = 9,          /* AffinePrimaryConnectivityModel + row partition (PrimaryConnectivityCosts.jl:5-19) */
-  CPO_MODEL_SECCONN = 10           /* AffineSecondaryConnectivityModel + row partition (SecondaryConnectivityCosts.jl:5-19) */
+  CPO_MODEL_SECCONN = 10,          /* AffineSecondaryConnectivityModel + row partition (SecondaryConnectivityCosts.jl:5-19) */
+  CPO_MODEL_PRIMEDGE = 11,         /* AffinePrimaryEdgeCutModel + row partition   (PrimaryEdgeCutCosts.jl:5-18) */
+  CPO_MODEL_SECEDGE = 12           /* AffineSecondaryEdgeCutModel + row partition (SecondaryEdgeCutCosts.jl:5-18) */
 };
 
 /* hints -> dominance structure (SparsePrefixMatrices.jl:450-458) */

@@ -725,6 +725,51 @@ template <class T> struct SecondaryOracle {
   }
 };
 
+// PrimaryEdgeCutCosts.jl:20-66 and SecondaryEdgeCutCosts.jl:33-97: the pin-level analogues.  Both need, for row part k,
+// the number of its nonzeros inside a column range (lcp / lcv = a pin count on the stacked matrix, PartwiseCounts.jl).
+template <class T> struct EdgeCutPartOracle {
+  const Mat& A;
+  Model<T> mdl;
+  i64 n, K;
+  bool secondary;
+  ivec spl, pins;
+  std::vector<ivec> cum;  // cum[k][j] = nonzeros of row part k in columns < j
+  EdgeCutPartOracle(const Mat& A_, const cpo_model* s, const i64* pi_spl, i64 pi_K, bool secondary_) : A(A_), mdl(s), n(A_.n), K(pi_K), secondary(secondary_) {
+    if (pi_spl[0] != 1 || pi_spl[K] != A.m + 1) throw std::invalid_argument("row partition must cover rows 1..m");
+    spl.assign(K + 2, 0);
+    for (i64 k = 1; k <= K + 1; ++k) spl[k] = pi_spl[k - 1];
+    ivec asg(A.m + 1, 0);
+    for (i64 k = 1; k <= K; ++k)
+      for (i64 i = spl[k]; i < spl[k + 1]; ++i) asg[i] = k;
+    cum.assign(K + 1, ivec(n + 2, 0));
+    pins.assign(K + 2, 0);
+    for (i64 j = 1; j <= n; ++j) {
+      for (i64 k = 1; k <= K; ++k) cum[k][j + 1] = cum[k][j];
+      for (i64 q = A.pos[j]; q < A.pos[j + 1]; ++q) { const i64 k = asg[A.idx[q]]; cum[k][j + 1] += 1; pins[k] += 1; }
+    }
+  }
+  inline T operator()(i64 j, i64 jp, i64 k = 1) {
+    const i64 l = cum[k][jp] - cum[k][j];
+    if (!secondary) {  // PrimaryEdgeCutCosts.jl:50-56
+      const i64 w = A.pos[jp] - A.pos[j];
+      return mdl.eval3(jp - j, l, w - l);
+    }
+    return mdl.eval3(spl[k + 1] - spl[k], l, pins[k] - l);  // SecondaryEdgeCutCosts.jl:78-85
+  }
+  inline T step_same_next(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
+  inline T step_next_same(i64 j, i64 jp, i64 k = 1) { return (*this)(j, jp, k); }
+  void bounds(double out[2]) const {  // SecondaryEdgeCutCosts.jl:43-60
+    T c_lo = 0, c_hi = 0;
+    for (i64 k = 1; k <= K; ++k) {
+      const T nv = (T)(spl[k + 1] - spl[k]);
+      c_lo = std::max(c_lo, mdl.c[0] + nv * mdl.c[1] + (T)pins[k] * std::min(mdl.c[2], mdl.c[3]));
+      c_hi = std::max(c_hi, mdl.c[0] + nv * mdl.c[1] + (T)pins[k] * std::max(mdl.c[2], mdl.c[3]));
+    }
+    out[0] = (double)c_lo;
+    out[1] = (double)c_hi;
+  }
+};
+
 // BlockCosts.jl:46-142 BlockComponentCostStepOracle (stateful)
 template <class T> struct BlockOracle {
   const Mat& A;

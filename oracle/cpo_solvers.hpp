@@ -46,6 +46,18 @@ template <class T, class F> static void bound_stripe(const Mat& A, i64 K, const 
       c_lo = mdl.c[0] + jl_fld(c_hi - mdl.c[0], (T)K);
       break;
     }
+    case CPO_MODEL_PRIMEDGE: {  // PrimaryEdgeCutCosts.jl:29-40 (reached through the fallbacks Costs.jl:9-19)
+      if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0)) throw std::invalid_argument("negative beta");
+      c_hi = mdl.c[0] + mdl.c[1] * (T)n + std::max(mdl.c[2], mdl.c[3]) * (T)N;
+      c_lo = mdl.c[0] + jl_fld(mdl.c[1] * (T)n + std::min(mdl.c[2], mdl.c[3]) * (T)N, (T)K);
+      break;
+    }
+    case CPO_MODEL_SECEDGE: {  // SecondaryEdgeCutCosts.jl:43-60 (oracle form)
+      if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0)) throw std::invalid_argument("negative beta");
+      if (!ocl) throw std::logic_error("secondary edge-cut bound needs an oracle");
+      secondary_bounds(*ocl, out, 0);
+      return;
+    }
     case CPO_MODEL_SECCONN: {  // SecondaryConnectivityCosts.jl:44-65 (oracle form)
       if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0 && mdl.c[4] >= 0)) throw std::invalid_argument("negative beta");
       if (!ocl) throw std::logic_error("secondary connectivity bound needs an oracle");

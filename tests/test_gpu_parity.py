@@ -551,6 +551,39 @@ def test_secondary_connectivity_model_and_flip_splitters(ref, fixtures):
                     assert np.array_equal(g.spl, r.spl), (A, f, K, type(mtd).__name__, g.spl, r.spl)
 
 
+def test_edgecut_part_models(ref, fixtures):
+    """AffinePrimaryEdgeCutModel / AffineSecondaryEdgeCutModel with a row partition (PrimaryEdgeCutCosts.jl:5-66,
+    SecondaryEdgeCutCosts.jl:5-97): queries with the part index, and identical split vectors for the increasing-cost
+    splitters (primary) and the Flip family (secondary)."""
+    rng = np.random.default_rng(307)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 10, 0.3), sprand(rng, 8, 3, 0.5), sprand(rng, 40, 120, 0.1),
+            synth.erdos_renyi(2000, 5)]
+    for A in mats:
+        for K in [1, 2, 3, 8]:
+            Pi = prim_partitions(ref, A, K)
+            for co in [(0, 2, 1, 5), (1, 1, 1, 1), (0.0, 0.5, 1.0, 3.5)]:
+                for f in (cp.AffinePrimaryEdgeCutModel(*co), cp.AffineSecondaryEdgeCutModel(*co)):
+                    j, jp = rand_pairs(rng, A.n, 300)
+                    k = rng.integers(1, K + 1, 300)
+                    ocl = cp.oracle_stripe(f, A, Pi)
+                    assert np.array_equal(ocl.query(j, jp, k), ref.oracle_query(f, A, j, jp, k, Pi=Pi))
+                    ocl.close()
+                    if isinstance(f, cp.AffinePrimaryEdgeCutModel):
+                        mtds = [cp.BisectIndexBottleneckSplitter(f), cp.BisectCostBottleneckSplitter(f, 0.1), cp.BisectCostBottleneckSplitter(f, 0.01),
+                                cp.LazyBisectCostBottleneckSplitter(f, 0.01)]
+                        if A.n <= 500:
+                            mtds += [cp.DynamicBottleneckSplitter(f), cp.DynamicTotalSplitter(f)]
+                    else:
+                        mtds = [cp.FlipBisectIndexBottleneckSplitter(f), cp.FlipBisectCostBottleneckSplitter(f, 0.1), cp.FlipBisectCostBottleneckSplitter(f, 0.001),
+                                cp.LazyFlipBisectCostBottleneckSplitter(f, 0.01)]
+                        if A.n <= 500:
+                            mtds.append(cp.DynamicBottleneckSplitter(f))
+                    for mtd in mtds:
+                        g, r = cp.partition_stripe(A, K, mtd, Pi), ref.partition_stripe(A, K, mtd, Pi)
+                        assert np.array_equal(g.spl, r.spl), (A, f, K, type(mtd).__name__, g.spl, r.spl)
+                        assert cp.bottleneck_value(A, g, f, Pi) == ref.bottleneck_value(A, g, f, Pi)
+
+
 def test_plaid_with_primary_models(ref):
     """A genuinely 2-D alternation (bin/test_table_bottleneck.jl:47-55 style): columns by connectivity, then rows and
     columns in turn by the primary connectivity cost given the other side's partition."""

@@ -432,6 +432,54 @@ def test_secondary_connectivity_oracle_and_flip_solvers(ref):
                 assert opt <= v <= opt * (1 + eps), type(mtd).__name__
 
 
+def edgecut_part_cost(mdl, M, Pi, j, jp, k):
+    """PrimaryEdgeCutCosts.jl:18,50-56 / SecondaryEdgeCutCosts.jl:18,78-85 from the set definition: a pin (r, c) is a
+    self pin of part k when row part k of Pi owns r and c lies in [j, j')."""
+    c = mdl.coef
+    own = lambda r: Pi.spl[k - 1] <= r < Pi.spl[k]
+    self_pins = sum(1 for q in range(j, jp) for r in col_rows(M, q) if own(r))
+    if mdl.kind == cp.types.MODEL_PRIMEDGE:
+        pins = sum(len(col_rows(M, q)) for q in range(j, jp))
+        return c[0] + (jp - j) * c[1] + self_pins * c[2] + (pins - self_pins) * c[3]
+    pins = sum(1 for q in range(1, M.n + 1) for r in col_rows(M, q) if own(r))
+    return c[0] + int(Pi.spl[k] - Pi.spl[k - 1]) * c[1] + self_pins * c[2] + (pins - self_pins) * c[3]
+
+
+def test_edgecut_part_oracles_and_solvers(ref):
+    """AffinePrimaryEdgeCutModel / AffineSecondaryEdgeCutModel with a row partition (PrimaryEdgeCutCosts.jl:5-66,
+    SecondaryEdgeCutCosts.jl:5-97): the oracle equals the set definition for every (j, j', k); the primary cost grows with
+    the part (Dynamic, BisectIndex, BisectCost, LazyBisectCost), the secondary one shrinks when beta_self <= beta_cut
+    (Dynamic, the Flip family); exact solvers optimal, bisections within eps."""
+    rng = np.random.default_rng(23)
+    for trial in range(40):
+        m, n = int(rng.integers(1, 9)), int(rng.integers(1, 10))
+        A = sprand(rng, m, n, float(rng.choice([0.1, 0.3, 0.6])))
+        for K in [1, 2, 3, 4]:
+            Pi = ref.partition_stripe(ref.adjointpattern(A), K, cp.EquiSplitter())
+            co = [(0, 2, 1, 5), (1, 1, 1, 1), (0.0, 0.5, 1.0, 3.5)][trial % 3]
+            for mdl in (cp.AffinePrimaryEdgeCutModel(*co), cp.AffineSecondaryEdgeCutModel(*co)):
+                prim = mdl.kind == cp.types.MODEL_PRIMEDGE
+                Ck = {(k, j, jp): edgecut_part_cost(mdl, A, Pi, j, jp, k) for k in range(1, K + 1) for j in range(1, n + 2) for jp in range(j, n + 2)}
+                keys = list(Ck)
+                got = ref.oracle_query(mdl, A, [t[1] for t in keys], [t[2] for t in keys], [t[0] for t in keys], Pi=Pi)
+                assert got.tolist() == [float(Ck[t]) for t in keys]
+                prev = {jp: Ck[(1, 1, jp)] for jp in range(1, n + 2)}
+                for k in range(2, K + 1):
+                    prev = {jp: min(max(prev[j], Ck[(k, j, jp)]) for j in range(1, jp + 1)) for jp in range(1, n + 2)}
+                opt = prev[n + 1]
+                if prim:
+                    mtds = [(cp.DynamicBottleneckSplitter(mdl), 0), (cp.BisectIndexBottleneckSplitter(mdl), 0),
+                            (cp.BisectCostBottleneckSplitter(mdl, 0.1), 0.1), (cp.LazyBisectCostBottleneckSplitter(mdl, 0.01), 0.01)]
+                else:
+                    mtds = [(cp.DynamicBottleneckSplitter(mdl), 0), (cp.FlipBisectIndexBottleneckSplitter(mdl), 0),
+                            (cp.FlipBisectCostBottleneckSplitter(mdl, 0.01), 0.01), (cp.LazyFlipBisectCostBottleneckSplitter(mdl, 0.1), 0.1)]
+                for mtd, eps in mtds:
+                    Phi = ref.partition_stripe(A, K, mtd, Pi)
+                    check_split(Phi.spl, n, K)
+                    v = max(Ck[(k + 1, int(Phi.spl[k]), int(Phi.spl[k + 1]))] for k in range(K))
+                    assert opt <= v <= opt * (1 + eps), type(mtd).__name__
+
+
 def leftmost_chunk_dp(C, n, w_max):
     cst = np.full(n + 2, np.inf)
     cst[1] = 0
