@@ -19,7 +19,7 @@ from . import types as T
 __all__ = [
     "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
-    "dianetcount", "selfnetcount", "selfpincount", "profile_enable", "profile_reset", "profile_get",
+    "dianetcount", "selfnetcount", "selfpincount", "PrefixMatrix", "dominancecount", "dominancesum", "rookcount", "rooksum", "profile_enable", "profile_reset", "profile_get",
     "launch_count", "probe_cluster_capacity", "bisect_stats", "bisect_plan", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
 ]
 
@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
     "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_bisect_plan", "cpb_probe_cluster_capacity",
-    "cpb_links_partial", "cpb_oracle_set_links",
+    "cpb_links_partial", "cpb_oracle_set_links", "cpb_prefix_create", "cpb_prefix_query", "cpb_prefix_destroy",
 ]
 
 
@@ -155,6 +155,92 @@ def device_matrix(A) -> DeviceMatrix:
     h = ctypes.c_void_p()
     _check(load_library().cpb_matrix_create(A.m, A.n, A.nnz, _p(A.colptr), _p(A.rowval), ctypes.byref(h)))
     return DeviceMatrix(h, A.m, A.n, A.nnz)
+
+
+# ------------------------------------------------------------------------------- 2-D prefix structures
+
+
+def _as_i64_values(val):
+    """Integer values as the 64-bit words the device sums (Julia's Int64 / UInt64 wrap-around arithmetic)."""
+    val = np.asarray(val)
+    if val.dtype.kind not in "iub":
+        raise TypeError("dominance / rook sums on the device take integer values (Float64 sums depend on the summation order)")
+    dtype = np.uint64 if val.dtype == np.uint64 else I64
+    return np.ascontiguousarray(val.astype(dtype, copy=False)).view(I64), dtype
+
+
+class PrefixMatrix:
+    """``C = dominancecount(A)`` / ``S = dominancesum(A, val)`` / ``rookcount!(N, idx)`` / ``rooksum!(N, idx, val)``
+    (SparsePrefixMatrices.jl:1-1273) resident in HBM: an ``(m+1) x (n+1)`` matrix, ``P[i, j]`` = number (or sum of the values)
+    of the points ``(r, c)`` with ``r <= i-1`` and ``c <= j-1``.  ``P[i, j]`` answers one entry, ``P.query(i, j)`` a batch."""
+
+    def __init__(self, handle, m, n, summed, dtype):
+        self._h, self.m, self.n, self.summed, self.dtype = handle, int(m), int(n), bool(summed), dtype
+
+    @property
+    def shape(self):
+        return (self.m + 1, self.n + 1)
+
+    def query(self, i, j) -> np.ndarray:
+        i, j = np.ascontiguousarray(i, dtype=I64), np.ascontiguousarray(j, dtype=I64)
+        if i.shape != j.shape or i.ndim != 1:
+            raise ValueError("i and j must be 1-d arrays of equal length")
+        out = np.empty(len(i), dtype=I64)
+        none = ctypes.c_void_p(0)
+        _check(load_library().cpb_prefix_query(self._h, ctypes.c_longlong(len(i)), _p(i), _p(j), none if self.summed else _p(out), _p(out) if self.summed else none))
+        return out.view(self.dtype)
+
+    def __getitem__(self, ij):
+        i, j = ij
+        return self.query([int(i)], [int(j)])[0]
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.cpb_prefix_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _prefix_create(m, n, N, pos, idx, val):
+    idx = np.ascontiguousarray(idx, dtype=I64)
+    pos = None if pos is None else np.ascontiguousarray(pos, dtype=I64)
+    dtype = I64
+    if val is not None:
+        val, dtype = _as_i64_values(val)
+        if val.shape != (N,):
+            raise ValueError("one value per point expected")
+    if idx.shape != (N,):
+        raise ValueError("one row index per point expected")
+    h = ctypes.c_void_p()
+    _check(load_library().cpb_prefix_create(ctypes.c_longlong(m), ctypes.c_longlong(n), ctypes.c_longlong(N), _p(pos), _p(idx), _p(val), ctypes.byref(h)))
+    return PrefixMatrix(h, m, n, val is not None, dtype)
+
+
+def dominancecount(A, hint=None, **layout) -> PrefixMatrix:
+    """``dominancecount([hint,] A; b, H, b')`` (SparsePrefixMatrices.jl:440-460).  The hint and the layout keywords select
+    among the reference's CPU structures; the device has one index, so they are accepted and ignored."""
+    return _prefix_create(A.m, A.n, A.nnz, A.colptr, A.rowval, None)
+
+
+def dominancesum(A, val, hint=None, **layout) -> PrefixMatrix:
+    """``dominancesum([hint,] A; ...)`` (SparsePrefixMatrices.jl:31-58); ``val`` = ``A.nzval`` (the host matrix type here
+    holds the pattern only)."""
+    return _prefix_create(A.m, A.n, A.nnz, A.colptr, A.rowval, val)
+
+
+def rookcount(N, idx, hint=None, **layout) -> PrefixMatrix:
+    """``rookcount!([hint,] N, idx)`` (SparsePrefixMatrices.jl:1056-1063): the points ``(idx[q], q)``."""
+    return _prefix_create(N, N, N, None, idx, None)
+
+
+def rooksum(N, idx, val, hint=None, **layout) -> PrefixMatrix:
+    """``rooksum!([hint,] N, idx, val)`` (SparsePrefixMatrices.jl:840-851)."""
+    return _prefix_create(N, N, N, None, idx, val)
 
 
 class _Scoped:

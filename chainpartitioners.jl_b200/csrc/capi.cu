@@ -10,6 +10,7 @@ using namespace cpb;
 
 struct cpb_matrix { Matrix M; };
 struct cpb_oracle { std::unique_ptr<Oracle> O; };
+struct cpb_prefix { std::unique_ptr<PrefixMatrix> P; };
 
 namespace cpb {
 
@@ -321,6 +322,46 @@ int cpb_count_query(cpb_matrix* A, int which, int64_t Q, const int64_t* j, const
   if (Q) CPB_CUDA(cudaMemcpyAsync(out, dout.get(), Q * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   CPB_API_END
+}
+
+int cpb_prefix_create(int64_t m, int64_t n, int64_t N, const int64_t* pos, const int64_t* idx, const int64_t* val, cpb_prefix** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(out && (idx || N == 0), "NULL argument");
+  CPB_REQUIRE(m >= 0 && n >= 0 && N >= 0, "negative dimension");
+  DBuf<i64> dpos(pos ? (size_t)n + 1 : 0), didx((size_t)std::max<int64_t>(N, 1)), dval(val ? (size_t)std::max<int64_t>(N, 1) : 0);
+  if (pos) h2d_copy(dpos.get(), pos, ((size_t)n + 1) * sizeof(i64));
+  h2d_copy(didx.get(), idx, (size_t)N * sizeof(i64));
+  if (val) h2d_copy(dval.get(), val, (size_t)N * sizeof(i64));
+  auto h = std::make_unique<cpb_prefix>();
+  h->P = prefix_build(m, n, N, pos ? dpos.get() : nullptr, didx.get(), val ? dval.get() : nullptr);
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *out = h.release();
+  CPB_API_END
+}
+
+int cpb_prefix_query(cpb_prefix* P, int64_t Q, const int64_t* i, const int64_t* j, int64_t* count_out, int64_t* sum_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(P && Q >= 0 && (Q == 0 || (i && j)), "NULL argument");
+  const PrefixMatrix& M = *P->P;
+  for (i64 t = 0; t < Q; ++t) CPB_REQUIRE(i[t] >= 1 && i[t] <= M.m + 1 && j[t] >= 1 && j[t] <= M.n + 1, "index out of range (need 1 <= i <= m+1, 1 <= j <= n+1)");
+  DBuf<i64> di(Q), dj(Q), dc(count_out ? Q : 0), ds(sum_out ? Q : 0);
+  if (Q) {
+    CPB_CUDA(cudaMemcpyAsync(di.get(), i, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+    CPB_CUDA(cudaMemcpyAsync(dj.get(), j, Q * sizeof(i64), cudaMemcpyHostToDevice, ctx().stream));
+  }
+  prefix_query(M, Q, di.get(), dj.get(), count_out ? dc.get() : nullptr, sum_out ? ds.get() : nullptr);
+  if (Q && count_out) CPB_CUDA(cudaMemcpyAsync(count_out, dc.get(), Q * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  if (Q && sum_out) CPB_CUDA(cudaMemcpyAsync(sum_out, ds.get(), Q * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_API_END
+}
+
+void cpb_prefix_destroy(cpb_prefix* P) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  if (cpb::g_ctx.ready) cudaSetDevice(cpb::g_ctx.device);
+  delete P;
 }
 
 int cpb_bound_stripe(cpb_oracle* f, int64_t K, double out[2]) {

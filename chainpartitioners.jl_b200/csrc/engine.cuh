@@ -22,6 +22,17 @@ struct RankStruct {
   DevRank dev() const { return DevRank{wm.dev(), P}; }
 };
 
+// SparsePrefixMatrices.jl as a user-facing structure (prefix.cu): dominance counts / sums of a sparse matrix, rook counts /
+// sums of a permutation
+struct PrefixMatrix {
+  i64 m = 0, n = 0, N = 0;
+  DBuf<u32> pos;    // [n+1] offsets (empty: rook form, one point per column)
+  WaveletMatrix wm; // over the 0-based row of every point, points in column order
+  DBuf<i64> wsum;   // [(L+1)][N+1] exclusive prefix sums of the values in the element order of each level (empty: counts only)
+};
+std::unique_ptr<PrefixMatrix> prefix_build(i64 m, i64 n, i64 N, const i64* d_pos, const i64* d_idx, const i64* d_val);
+void prefix_query(const PrefixMatrix& P, i64 Q, const i64* d_i, const i64* d_j, i64* d_count, i64* d_sum);
+
 // the link array itself, in column order (streaming probes; also the input of the wavelet build)
 struct LinkStream {
   DBuf<u32> prev;    // [Ne] 1-based previous column holding the same row, 0 = none; pos_links: 1 + position of that nonzero

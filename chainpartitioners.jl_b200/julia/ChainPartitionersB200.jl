@@ -14,7 +14,7 @@ module ChainPartitionersB200
 
 using SparseArrays
 using ChainPartitioners
-import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_stripe,
+import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_stripe, dominancecount, dominancesum, rookcount!, rooksum!,
     AffineWorkModel, AffineConnectivityModel, AffineMonotonizedSymmetricConnectivityModel,
     AffineSymmetricConnectivityModel, AffineHyperedgeCutModel, AffineSymmetricEdgeCutModel, AffineEnvelopeModel,
     AffinePrimaryConnectivityModel, AffineSecondaryConnectivityModel, AffinePrimaryEdgeCutModel, AffineSecondaryEdgeCutModel,
@@ -190,6 +190,37 @@ function pack_stripe(A::SparseMatrixCSC{Tv, Int64}, method::OnB200, args...; n_n
     end
     return SplitPartition{Int64}(K[], resize!(spl, K[] + 1))
 end
+
+# ---- SparsePrefixMatrices.jl on the device: dominancecount / dominancesum / rookcount! / rooksum! --------------------
+# (src/SparsePrefixMatrices.jl:31-58, 440-460, 840-851, 1056-1063).  One handle type; `C[i, j]` as in the reference.
+# The device takes the place of the hint argument: `dominancecount(OnB200(nothing), A)`.
+mutable struct DevicePrefixMatrix{Tv} <: AbstractMatrix{Tv}
+    h::Ptr{Cvoid}
+    m::Int
+    n::Int
+    summed::Bool
+    function DevicePrefixMatrix{Tv}(m, n, N, pos, idx::Vector{Int64}, val) where {Tv}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve pos idx val check(ccall((:cpb_prefix_create, lib), Cint,
+            (Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}), m, n, N,
+            pos === nothing ? C_NULL : pointer(pos), idx, val === nothing ? C_NULL : Ptr{Int64}(pointer(val)), h))
+        finalizer(x -> ccall((:cpb_prefix_destroy, lib), Cvoid, (Ptr{Cvoid},), x.h), new{Tv}(h[], m, n, val !== nothing))
+    end
+end
+Base.size(P::DevicePrefixMatrix) = (P.m + 1, P.n + 1)
+function Base.getindex(P::DevicePrefixMatrix{Tv}, i::Integer, j::Integer) where {Tv}
+    out = Ref{Int64}(0)
+    check(ccall((:cpb_prefix_query, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}),
+                P.h, 1, Int64(i), Int64(j), P.summed ? C_NULL : out, P.summed ? out : C_NULL))
+    return reinterpret(Tv, out[])
+end
+dominancecount(::OnB200, A::SparseMatrixCSC{Tv, Int64}; kwargs...) where {Tv} =
+    DevicePrefixMatrix{Int64}(size(A)..., nnz(A), A.colptr, A.rowval, nothing)
+dominancesum(::OnB200, A::SparseMatrixCSC{Tv, Int64}; kwargs...) where {Tv <: Union{Int64, UInt64}} =
+    DevicePrefixMatrix{Tv}(size(A)..., nnz(A), A.colptr, A.rowval, A.nzval)
+rookcount!(::OnB200, N, idx::Vector{Int64}; kwargs...) = DevicePrefixMatrix{Int64}(N, N, N, nothing, idx, nothing)
+rooksum!(::OnB200, N, idx::Vector{Int64}, val::Vector{Tv}; kwargs...) where {Tv <: Union{Int64, UInt64}} =
+    DevicePrefixMatrix{Tv}(N, N, N, nothing, idx, val)
 
 # partition_plaid / pack_plaid need no glue: AlternatingPartitioner(OnB200(mtd1), OnB200(mtd2)) already
 # alternates partition_stripe calls on A and adjointpattern(A) (src/AlternatingPartitioner.jl:18-32).

@@ -109,6 +109,19 @@ void cpb_matrix_destroy(cpb_matrix* A);
 /* adjointpattern(A) (util.jl:67-95): CSC pattern of the transpose, built on the device. */
 int cpb_adjointpattern(cpb_matrix* A, cpb_matrix** out);
 
+/* ---- 2-D prefix structures (SparsePrefixMatrices.jl) ---------------------------------------- */
+typedef struct cpb_prefix cpb_prefix;
+/* dominancecount!(hint, m, n, N, pos, idx) / dominancesum!(hint, m, n, N, pos, idx, val) (SparsePrefixMatrices.jl:33-58,
+ * 440-460) and rookcount!(hint, N, idx) / rooksum!(hint, N, idx, val) (:840-851, 1056-1063).  pos (n+1) and idx (N) are the
+ * 1-based Int64 arrays Julia holds; pos == NULL selects the rook form (point q sits in column q, n == N, m == N);
+ * val == NULL builds counts only.  Values are 64-bit integers, sums wrap like Julia's Int64 / UInt64.  The hint and the
+ * b / H / b' layout arguments of the reference have no device counterpart: one wavelet-matrix index serves all of them. */
+int cpb_prefix_create(int64_t m, int64_t n, int64_t N, const int64_t* pos, const int64_t* idx, const int64_t* val, cpb_prefix** out);
+/* C[i, j] = #{points (r, c): r <= i-1, c <= j-1} and S[i, j] = the sum of their values, 1 <= i <= m+1, 1 <= j <= n+1
+ * (getindex, SparsePrefixMatrices.jl:187-254, 537-604, 660-689, 957-1021, 1137-1206, 1246-1273).  Either output may be NULL. */
+int cpb_prefix_query(cpb_prefix* P, int64_t Q, const int64_t* i, const int64_t* j, int64_t* count_out, int64_t* sum_out);
+void cpb_prefix_destroy(cpb_prefix* P);
+
 /* ---- cost oracles ------------------------------------------------------------------------ */
 typedef struct cpb_oracle cpb_oracle;
 /* oracle_stripe(hint, mdl, A[, Pi]) (Costs.jl:3-7, ConnectivityCosts.jl:47-56, Monotonized...:77-92,

@@ -55,6 +55,32 @@ extern "C" int cpo_dominancecount(int hint, const cpo_csc* A, int b, int H, int 
   CPO_CATCH
 }
 
+extern "C" int cpo_prefix_query(cpo_i64 m, cpo_i64 n, cpo_i64 N, const cpo_i64* pos, const cpo_i64* idx, const cpo_i64* val, cpo_i64 Q,
+                                const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out) {
+  CPO_TRY
+  if (!pos && n != N) throw std::runtime_error("rook form needs n == N");
+  std::vector<i64> order(Q);
+  for (i64 t = 0; t < Q; ++t) {
+    if (qi[t] < 1 || qi[t] > m + 1 || qj[t] < 1 || qj[t] > n + 1) throw std::runtime_error("prefix query out of range");
+    order[t] = t;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](i64 a, i64 b) { return qj[a] < qj[b]; });
+  std::vector<unsigned long long> fen(m + 1, 0);  // Fenwick tree over rows 1..m, wrap-around sums
+  i64 q = 0;                                      // points [0, q) are inserted
+  for (i64 t : order) {
+    const i64 upto = pos ? pos[qj[t] - 1] - 1 : qj[t] - 1;  // points in columns < qj
+    for (; q < upto; ++q) {
+      if (idx[q] < 1 || idx[q] > m) throw std::runtime_error("row index out of range");
+      const unsigned long long w = val ? (unsigned long long)val[q] : 1ull;
+      for (i64 r = idx[q]; r <= m; r += r & -r) fen[r] += w;
+    }
+    unsigned long long s = 0;
+    for (i64 r = qi[t] - 1; r > 0; r -= r & -r) s += fen[r];
+    out[t] = (i64)s;
+  }
+  CPO_CATCH
+}
+
 extern "C" int cpo_dominancecount_walk(const cpo_csc* A, cpo_i64 T, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out) {
   // Walks (i,j) through the stepwise counter using Next/Prev/Same steps when the move is a unit
   // step in one coordinate and a jump otherwise (test_SparsePrefixMatrices.jl:74-92).

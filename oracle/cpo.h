@@ -143,6 +143,14 @@ int cpo_dominancecount(int hint, const cpo_csc* A, int b, int H, int bp,
  * {0 Same,1 Next,2 Prev,3 Jump} for i and j  (test_SparsePrefixMatrices.jl:74-92) */
 int cpo_dominancecount_walk(const cpo_csc* A, cpo_i64 T, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out);
 
+/* dominancesum / rookcount / rooksum (SparsePrefixMatrices.jl:1-392, 825-1273) by their DEFINITION
+ * (test_SparsePrefixMatrices.jl:14-15): out[t] = number (val == NULL) or wrap-around sum of the values of the points
+ * (idx[q], column of q) with row <= qi-1 and column <= qj-1.  pos == NULL: rook form, point q sits in column q.
+ * Restated as an offline sweep with a Fenwick tree over the rows -- not the reference's b-ary layout, whose only
+ * observable is this number. */
+int cpo_prefix_query(cpo_i64 m, cpo_i64 n, cpo_i64 N, const cpo_i64* pos, const cpo_i64* idx, const cpo_i64* val,
+                     cpo_i64 Q, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out);
+
 /* netcount / dianetcount / selfnetcount / selfpincount / pincount [j,j'] (SparseColorArrays.jl) */
 int cpo_colorcount(int which, int hint, const cpo_csc* A,
                    cpo_i64 Q, const cpo_i64* qj, const cpo_i64* qjp, cpo_i64* out);

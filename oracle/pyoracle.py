@@ -100,6 +100,21 @@ def dominancecount(A, i, j, hint=T.NoHint(), b=0, H=0, bp=0) -> np.ndarray:
     return out
 
 
+def prefix_query(m, n, N, pos, idx, val, i, j) -> np.ndarray:
+    """dominancesum / rookcount / rooksum entries by the offline sweep of cpo_prefix_query (pos None: rook form; val None: counts)."""
+    i, j, idx = _arr(i), _arr(j), _arr(idx)
+    pos = None if pos is None else _arr(pos)
+    dtype = I64
+    if val is not None:
+        val = np.asarray(val)
+        dtype = np.uint64 if val.dtype == np.uint64 else I64
+        val = np.ascontiguousarray(val.astype(dtype, copy=False)).view(I64)
+    out = np.empty(len(i), dtype=I64)
+    L = ctypes.c_longlong
+    _check(lib().cpo_prefix_query(L(m), L(n), L(N), _ptr(pos), _ptr(idx), _ptr(val), L(len(i)), _ptr(i), _ptr(j), _ptr(out)))
+    return out.view(dtype)
+
+
 def dominancecount_walk(A, i, j) -> np.ndarray:
     i, j = _arr(i), _arr(j)
     out = np.empty(len(i), dtype=I64)

@@ -584,6 +584,42 @@ def test_edgecut_part_models(ref, fixtures):
                         assert cp.bottleneck_value(A, g, f, Pi) == ref.bottleneck_value(A, g, f, Pi)
 
 
+def test_prefix_structures(ref):
+    """dominancecount / dominancesum / rookcount! / rooksum! on the device (SparsePrefixMatrices.jl:1-1273; the reference's
+    test_SparsePrefixMatrices.jl:26-71 dims and value types, plus sizes that span many rank blocks and scan tiles): every
+    entry equals the CPU sweep, single entries through getindex, corners included."""
+    rng = np.random.default_rng(308)
+    dims = [1, 2, 3, 7, 8, 9, 31, 32, 33, 63, 64, 65]
+    cases = [(m, n, 0.5) for m in dims for n in (1, 3, 8, 33)] + [(300, 500, 0.02), (1000, 1000, 0.01), (5000, 40000, 0.002), (70000, 3000, 0.001), (5, 6, 0.0)]
+    for m, n, p in cases:
+        A = sprand(rng, m, n, p)
+        Q = 400 if A.nnz > 1000 else 40
+        i = np.concatenate([rng.integers(1, m + 2, Q), [1, 1, m + 1, m + 1]])
+        j = np.concatenate([rng.integers(1, n + 2, Q), [1, n + 1, 1, n + 1]])
+        for val in (rng.integers(0, 2**64, A.nnz, dtype=np.uint64), rng.integers(-5, 6, A.nnz)):
+            C, S = cp.dominancecount(A), cp.dominancesum(A, val)
+            assert C.shape == (m + 1, n + 1)
+            assert np.array_equal(C.query(i, j), ref.dominancecount(A, i, j))
+            got, exp = S.query(i, j), ref.prefix_query(m, n, A.nnz, A.colptr, A.rowval, val, i, j)
+            assert got.dtype == exp.dtype and np.array_equal(got, exp), (m, n)
+            assert S[m + 1, n + 1] == val.sum(dtype=val.dtype) and C[int(i[0]), int(j[0])] == C.query(i[:1], j[:1])[0]
+            C.close(); S.close()
+    for N in dims + [1000, 100000]:
+        idx = rng.permutation(N) + 1
+        val = (rng.integers(0, 2**63, N, dtype=np.uint64) << np.uint64(1)) + np.uint64(1)
+        i = np.concatenate([rng.integers(1, N + 2, 200), [1, 1, N + 1, N + 1]])
+        j = np.concatenate([rng.integers(1, N + 2, 200), [1, N + 1, 1, N + 1]])
+        RC, RS = cp.rookcount(N, idx), cp.rooksum(N, idx, val)
+        assert np.array_equal(RC.query(i, j), ref.prefix_query(N, N, N, None, idx, None, i, j))
+        assert np.array_equal(RS.query(i, j), ref.prefix_query(N, N, N, None, idx, val, i, j))
+        assert RC[N + 1, N + 1] == N
+    with pytest.raises(TypeError):
+        cp.dominancesum(A, np.ones(A.nnz))
+    with pytest.raises(cp.CpbError):
+        C = cp.dominancecount(A)
+        C.query([A.m + 2], [1])
+
+
 def test_plaid_with_primary_models(ref):
     """A genuinely 2-D alternation (bin/test_table_bottleneck.jl:47-55 style): columns by connectivity, then rows and
     columns in turn by the primary connectivity cost given the other side's partition."""

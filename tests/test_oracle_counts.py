@@ -48,6 +48,37 @@ def test_dominancecount_jump(ref, kw):
                 assert got.tolist() == exp, (hint, m, n, kw)
 
 
+def ref_prefix(rows, cols, vals, i, j):
+    """test_SparsePrefixMatrices.jl:14-15 on coordinate lists: count and (wrap-around) sum of the points below (i, j)."""
+    sel = (rows <= i - 1) & (cols <= j - 1)
+    return int(sel.sum()), int(vals[sel].sum(dtype=np.uint64))
+
+
+def test_dominancesum_and_rook_structures(ref):
+    """dominancesum, rookcount!, rooksum! (test_SparsePrefixMatrices.jl:43-69): UInt values with wrap-around, a random
+    permutation with odd values; every entry equals the definition.  The sweep also reproduces dominancecount."""
+    rng = np.random.default_rng(31)
+    for m in DIMS + [31, 32, 33]:
+        for n in DIMS:
+            A = sprand(rng, m, n, 0.5)
+            val = rng.integers(0, 2**64, A.nnz, dtype=np.uint64)
+            cols = np.repeat(np.arange(1, n + 1), np.diff(A.colptr))
+            pts = probes(rng, 10, (1, m + 1), (1, n + 1))
+            i, j = [p[0] for p in pts], [p[1] for p in pts]
+            exp = [ref_prefix(A.rowval, cols, val, a, b) for a, b in pts]
+            assert ref.prefix_query(m, n, A.nnz, A.colptr, A.rowval, None, i, j).tolist() == [e[0] for e in exp]
+            assert ref.prefix_query(m, n, A.nnz, A.colptr, A.rowval, None, i, j).tolist() == ref.dominancecount(A, i, j).tolist()
+            assert ref.prefix_query(m, n, A.nnz, A.colptr, A.rowval, val, i, j).tolist() == [e[1] for e in exp]
+        N = m
+        idx = rng.permutation(N) + 1
+        val = (rng.integers(0, 2**63, N, dtype=np.uint64) << np.uint64(1)) + np.uint64(1)
+        pts = probes(rng, 100, (1, N + 1), (1, N + 1))
+        i, j = [p[0] for p in pts], [p[1] for p in pts]
+        exp = [ref_prefix(idx, np.arange(1, N + 1), val, a, b) for a, b in pts]
+        assert ref.prefix_query(N, N, N, None, idx, None, i, j).tolist() == [e[0] for e in exp]
+        assert ref.prefix_query(N, N, N, None, idx, val, i, j).tolist() == [e[1] for e in exp]
+
+
 def test_dominancecount_larger(ref):
     rng = np.random.default_rng(3)
     for (m, n, p) in [(100, 80, 0.1), (300, 500, 0.02), (1000, 1000, 0.005)]:
