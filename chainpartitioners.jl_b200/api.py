@@ -17,7 +17,7 @@ import numpy as np
 from . import types as T
 
 __all__ = [
-    "DeviceMatrix", "device_matrix", "adjointpattern", "oracle_stripe", "bound_stripe", "partition_stripe",
+    "DeviceMatrix", "device_matrix", "adjointpattern", "permute", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "PrefixMatrix", "dominancecount", "dominancesum", "rookcount", "rooksum", "profile_enable", "profile_reset", "profile_get",
     "launch_count", "probe_cluster_capacity", "bisect_stats", "bisect_plan", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "library_path", "load_library", "CpbError",
@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
     "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_bisect_plan", "cpb_probe_cluster_capacity",
-    "cpb_links_partial", "cpb_oracle_set_links", "cpb_prefix_create", "cpb_prefix_query", "cpb_prefix_destroy",
+    "cpb_links_partial", "cpb_oracle_set_links", "cpb_prefix_create", "cpb_prefix_query", "cpb_prefix_destroy", "cpb_matrix_permute",
 ]
 
 
@@ -243,6 +243,29 @@ def rooksum(N, idx, val, hint=None, **layout) -> PrefixMatrix:
     return _prefix_create(N, N, N, None, idx, val)
 
 
+def permute(A, col_prm=None, row_new=None) -> DeviceMatrix:
+    """``A[:, col_prm]`` with row ``r`` renamed ``row_new[r]`` (1-based permutations, ``None`` = identity), built on the
+    device -- the first step of ``compute_objective`` for non-contiguous partitions (Costs.jl:34-39, 52-57)."""
+    with _Scoped(A) as dm:
+        c = None if col_prm is None else _arr(col_prm)
+        r = None if row_new is None else _arr(row_new)
+        if (c is not None and c.shape != (dm.n,)) or (r is not None and r.shape != (dm.m,)):
+            raise ValueError("col_prm needs n entries, row_new needs m entries")
+        h = ctypes.c_void_p()
+        _check(load_library().cpb_matrix_permute(dm._h, _p(c), _p(r), ctypes.byref(h)))
+        return DeviceMatrix(h, dm.m, dm.n, dm.nnz)
+
+
+def _rows_by_part(Pi, m):
+    """A Map/DomainPartition of the rows as (row_new, SplitPartition): rows renumbered part by part (stable)."""
+    dom = T.convert(T.DomainPartition, Pi)
+    if dom.prm.shape != (m,):
+        raise ValueError("row partition must cover the m rows")
+    row_new = np.empty(m, dtype=I64)
+    row_new[dom.prm - 1] = np.arange(1, m + 1, dtype=I64)
+    return row_new, T.SplitPartition(dom.K, dom.spl)
+
+
 class _Scoped:
     """device view of a matrix argument; frees the upload on exit if we made it"""
 
@@ -288,7 +311,15 @@ class StripeOracle:
     def __init__(self, mdl, A, Pi=None, hint=None, w_tab=None):
         f, con = T.split_constrained(mdl)
         self.model, self.constraint = f, con
-        self._own = _Scoped(A)
+        if Pi is not None and not isinstance(Pi, T.SplitPartition):
+            # oracle_stripe converts any row partition to a MapPartition (PrimaryConnectivityCosts.jl:56-67); the device
+            # structures want contiguous row parts, and the counts depend on a row only through its part: rename the rows
+            row_new, Pi = _rows_by_part(Pi, A.m)
+            A = permute(A, None, row_new)
+            self._own = _Scoped(A)
+            self._own.owned = True
+        else:
+            self._own = _Scoped(A)
         self.dm = self._own.dm
         self.Pi = Pi
         tabs = T.model_tables(f, self.dm, con, Pi) if hasattr(f, "to_c") else {}
@@ -382,6 +413,17 @@ def bound_stripe(A, K, mdl_or_ocl, Pi=None):
 
 
 def _objective(total, A, Phi, mdl_or_ocl, Pi):
+    tmp = None
+    if not isinstance(Phi, T.SplitPartition):
+        # compute_objective for Map / DomainPartitions (Costs.jl:34-39, 52-57; WorkCosts.jl:63-81; PrimaryConnectivityCosts.jl:
+        # 127-163; EnvelopeCosts.jl:100-129): gather the columns part by part, then evaluate the contiguous parts
+        if isinstance(mdl_or_ocl, StripeOracle):
+            raise TypeError("a non-contiguous partition needs the model, not an oracle of the unpermuted matrix")
+        dom = T.convert(T.DomainPartition, Phi)
+        if dom.prm.shape != (A.n,):
+            raise ValueError("the partition must cover the n columns")
+        tmp = A = permute(A, dom.prm, None)
+        Phi = T.SplitPartition(dom.K, dom.spl)
     ocl, own = _as_oracle(A, mdl_or_ocl, Pi)
     try:
         out = ctypes.c_double()
@@ -391,15 +433,18 @@ def _objective(total, A, Phi, mdl_or_ocl, Pi):
     finally:
         if own:
             ocl.close()
+        if tmp is not None:
+            tmp.close()
 
 
 def bottleneck_value(A, Phi, mdl, Pi=None):
-    """Costs.jl:26-27 for a SplitPartition ``Phi``."""
+    """Costs.jl:26-27: ``Phi`` a Split-, Domain- or MapPartition of the columns, ``Pi`` (for the partition-aware models) any
+    partition of the rows."""
     return _objective(False, A, Phi, mdl, Pi)
 
 
 def total_value(A, Phi, mdl, Pi=None):
-    """Costs.jl:28-29 for a SplitPartition ``Phi``."""
+    """Costs.jl:28-29 (same argument forms as ``bottleneck_value``)."""
     return _objective(True, A, Phi, mdl, Pi)
 
 

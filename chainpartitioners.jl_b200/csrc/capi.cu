@@ -264,6 +264,33 @@ int cpb_adjointpattern(cpb_matrix* A, cpb_matrix** out) {
   CPB_API_END
 }
 
+int cpb_matrix_permute(cpb_matrix* A, const int64_t* col_prm, const int64_t* row_new, cpb_matrix** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && out, "NULL argument");
+  const Matrix& M = A->M;
+  DBuf<u32> dc, dr, flags(1);
+  flags.zero();
+  auto upload = [&](const int64_t* h, i64 len, DBuf<u32>& d) {
+    if (!h) return;
+    DBuf<i64> wide((size_t)std::max<i64>(len, 1));
+    h2d_copy(wide.get(), h, (size_t)len * sizeof(i64));
+    d.alloc((size_t)std::max<i64>(len, 1));
+    narrow_minus1(wide.get(), d.get(), (size_t)len, 1, len, flags.get());
+  };
+  upload(col_prm, M.n, dc);
+  upload(row_new, M.m, dr);
+  u32 hf = 0;
+  CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_REQUIRE(hf == 0, "permutation entry out of range (expected 1-based indices)");
+  auto B = permute_pattern(M, col_prm ? dc.get() : nullptr, row_new ? dr.get() : nullptr);
+  auto h = std::make_unique<cpb_matrix>();
+  h->M = std::move(*B);
+  *out = h.release();
+  CPB_API_END
+}
+
 int cpb_oracle_create(cpb_matrix* A, const cpb_model* mdl, const int64_t* pi_spl, int64_t pi_K, cpb_oracle** out) {
   CPB_API_BEGIN
   ensure_context();

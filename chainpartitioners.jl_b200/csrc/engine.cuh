@@ -140,6 +140,8 @@ void solve_convex_splitter(Oracle& f, const cpb_constraint* con, i64 K, int64_t*
 void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, double rho, i64 w_max, int64_t* h_spl_out,
                 int64_t* K_out, int64_t* n_nets_out);
 std::unique_ptr<Matrix> adjoint_pattern(const Matrix& A);
+// A[:, col_prm] with row r renamed row_new[r] (0-based device arrays; nullptr = identity)
+std::unique_ptr<Matrix> permute_pattern(const Matrix& A, const u32* col_prm, const u32* row_new);
 
 #ifdef __CUDACC__
 // --- cost evaluation on the device: left-to-right sums, no FMA (compiled with -fmad=false) -----

@@ -444,4 +444,70 @@ std::unique_ptr<Matrix> adjoint_pattern(const Matrix& A) {
   return B;
 }
 
+// ---- A[:, prm] with relabelled rows: the first step of the objective evaluators for non-contiguous partitions
+// (Costs.jl:34-39, 52-57: "A_prm = A[:, Phi_dom.prm]"; a MapPartition of the rows becomes a SplitPartition by renumbering
+// the rows part by part -- every partition-aware count depends on a row only through the part that owns it).
+__global__ void k_perm_degrees(const u32* __restrict__ pos, const u32* __restrict__ prm, u32 n, u32* __restrict__ deg) {
+  const u32 c = blockIdx.x * 256u + threadIdx.x;
+  if (c > n) return;
+  u32 d = 0;
+  if (c < n) {
+    const u32 p = prm ? __ldg(prm + c) : c;
+    d = __ldg(pos + p + 1) - __ldg(pos + p);
+  }
+  deg[c] = d;  // entry n = 0, so the exclusive scan over n + 1 entries ends with the total
+}
+
+__global__ void k_perm_rows(const u32* __restrict__ pos, const u32* __restrict__ row, const u32* __restrict__ prm, const u32* __restrict__ row_new,
+                            const u32* __restrict__ new_pos, const u32* __restrict__ new_col, size_t N, u32* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+    const u32 c = __ldg(new_col + q);
+    const u32 p = prm ? __ldg(prm + c) : c;
+    const u32 r = __ldg(row + __ldg(pos + p) + ((u32)q - __ldg(new_pos + c)));
+    out[q] = row_new ? __ldg(row_new + r) : r;
+  }
+}
+
+// flags |= 1 unless v[0..n) is a permutation of 0..n-1 (seen: n zero-initialised words)
+__global__ void k_check_permutation(const u32* __restrict__ v, u32 n, u32* __restrict__ seen, u32* __restrict__ flags) {
+  const u32 i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  const u32 x = v[i];
+  if (x >= n || atomicExch(seen + x, 1u) != 0u) atomicOr(flags, 1u);
+}
+
+std::unique_ptr<Matrix> permute_pattern(const Matrix& A, const u32* col_prm, const u32* row_new) {
+  auto B = std::make_unique<Matrix>();
+  B->m = A.m; B->n = A.n; B->N = A.N;
+  const size_t N = (size_t)A.N;
+  const u32 n = (u32)A.n;
+  ProfScope prof("permute_pattern", (double)(3 * N + 3 * (size_t)n) * 4.0);
+  DBuf<u32> flags(1);
+  flags.zero();
+  for (int side = 0; side < 2; ++side) {
+    const u32* v = side ? row_new : col_prm;
+    const u32 len = side ? (u32)A.m : n;
+    if (!v || len == 0) continue;
+    DBuf<u32> seen(len);
+    seen.zero();
+    CPB_LAUNCH(k_check_permutation, (len + 255) / 256, 256, 0, v, len, seen.get(), flags.get());
+  }
+  B->pos.alloc((size_t)n + 1);
+  B->row.alloc(N);
+  DBuf<u32> deg((size_t)n + 1);
+  CPB_LAUNCH(k_perm_degrees, n / 256 + 1, 256, 0, A.pos.get(), col_prm, n, deg.get());
+  exclusive_scan_u32(deg.get(), B->pos.get(), (size_t)n + 1);
+  if (N) {
+    DBuf<u32> new_col(N);
+    expand_columns(B->pos.get(), n, new_col.get(), N);
+    CPB_LAUNCH(k_perm_rows, grid_for(N), 256, 0, A.pos.get(), A.row.get(), col_prm, row_new, B->pos.get(), new_col.get(), N, B->row.get());
+  }
+  u32 hf = 0;
+  CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_REQUIRE(hf == 0, "not a permutation (expected every index 1..len exactly once)");
+  return B;
+}
+
 }  // namespace cpb

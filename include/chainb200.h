@@ -109,6 +109,12 @@ void cpb_matrix_destroy(cpb_matrix* A);
 /* adjointpattern(A) (util.jl:67-95): CSC pattern of the transpose, built on the device. */
 int cpb_adjointpattern(cpb_matrix* A, cpb_matrix** out);
 
+/* A[:, col_prm] with row r renamed row_new[r] -- the first step of compute_objective for non-contiguous partitions
+ * (Costs.jl:34-39, 52-57: A_prm = A[:, Phi_dom.prm]; PrimaryConnectivityCosts.jl:88-163, WorkCosts.jl:63-81,
+ * EnvelopeCosts.jl:100-129).  col_prm: n entries, row_new: m entries, both 1-based permutations; NULL = identity.
+ * A MapPartition of the rows becomes a SplitPartition by renaming the rows part by part. */
+int cpb_matrix_permute(cpb_matrix* A, const int64_t* col_prm, const int64_t* row_new, cpb_matrix** out);
+
 /* ---- 2-D prefix structures (SparsePrefixMatrices.jl) ---------------------------------------- */
 typedef struct cpb_prefix cpb_prefix;
 /* dominancecount!(hint, m, n, N, pos, idx) / dominancesum!(hint, m, n, N, pos, idx, val) (SparsePrefixMatrices.jl:33-58,

@@ -185,7 +185,33 @@ def bound_stripe(A, K, mdl):
     return (out[0], out[1])
 
 
+def permute(A, col_prm=None, row_new=None) -> T.SparseMatrixCSC:
+    """A[:, col_prm] with row r renamed row_new[r] (numpy; Costs.jl:34-39, 52-57 "A_prm = A[:, Phi_dom.prm]")."""
+    deg = np.diff(A.colptr)
+    prm = np.arange(A.n) if col_prm is None else _arr(col_prm) - 1
+    pos = np.concatenate(([1], 1 + np.cumsum(deg[prm]))).astype(I64)
+    src = np.concatenate([np.arange(A.colptr[c] - 1, A.colptr[c + 1] - 1) for c in prm]).astype(I64) if A.nnz else np.zeros(0, dtype=I64)
+    rows = A.rowval[src]
+    if row_new is not None:
+        rows = _arr(row_new)[rows - 1]
+    return T.SparseMatrixCSC(A.m, A.n, pos, rows)
+
+
+def _contiguous(A, Phi, Pi):
+    """compute_objective's reduction of Map / DomainPartitions to SplitPartitions of a permuted matrix."""
+    if Pi is not None and not isinstance(Pi, T.SplitPartition):
+        dom = T.convert(T.DomainPartition, Pi)
+        row_new = np.empty(A.m, dtype=I64)
+        row_new[dom.prm - 1] = np.arange(1, A.m + 1, dtype=I64)
+        A, Pi = permute(A, None, row_new), T.SplitPartition(dom.K, dom.spl)
+    if not isinstance(Phi, T.SplitPartition):
+        dom = T.convert(T.DomainPartition, Phi)
+        A, Phi = permute(A, dom.prm, None), T.SplitPartition(dom.K, dom.spl)
+    return A, Phi, Pi
+
+
 def _objective(total, A, Phi, mdl, Pi=None, hint=T.StepHint()):
+    A, Phi, Pi = _contiguous(A, Phi, Pi)
     f, _ = T.split_constrained(mdl)
     spl, pK = _pi(Pi)
     cm, keep = _model(f, A, T.CConstraint(), Pi)

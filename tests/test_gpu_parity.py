@@ -584,6 +584,43 @@ def test_edgecut_part_models(ref, fixtures):
                         assert cp.bottleneck_value(A, g, f, Pi) == ref.bottleneck_value(A, g, f, Pi)
 
 
+def test_objective_of_noncontiguous_partitions(ref, fixtures):
+    """bottleneck_value / total_value of Map- and DomainPartitions (Costs.jl:26-66, WorkCosts.jl:53-81,
+    PrimaryConnectivityCosts.jl:88-163, EnvelopeCosts.jl:75-129): the device gathers the columns part by part
+    (cpb_matrix_permute), renames the rows of a non-contiguous row partition, and evaluates contiguous parts.  Also:
+    partition_stripe with a MapPartition of the rows, and a SplitPartition seen as a MapPartition has the same value."""
+    rng = np.random.default_rng(309)
+    models = [cp.AffineWorkModel(1, 2, 3), cp.AffineConnectivityModel(0, 10, 1, 100), cp.AffineConnectivityModel(0.5, 1.0, 0.25, 3.0),
+              cp.AffinePrimaryConnectivityModel(0, 2, 1, 3, 6), cp.AffinePrimaryEdgeCutModel(0, 2, 1, 5), cp.AffineEnvelopeModel(0, 1, 1, 2),
+              cp.AffineSecondaryConnectivityModel(0, 2, 1, 3, 6)]
+    mats = [fixtures["LPnetlib/lpi_itest6"], sprand(rng, 6, 10, 0.3), sprand(rng, 8, 3, 0.5), sprand(rng, 40, 120, 0.1), sprand(rng, 5, 7, 0.0),
+            synth.erdos_renyi(3000, 6)]
+    for A in mats:
+        for K in (1, 3, 7):
+            Phi = cp.MapPartition(K, rng.integers(1, K + 1, A.n))
+            Pi = cp.MapPartition(K, rng.integers(1, K + 1, A.m))
+            dom = cp.convert(cp.DomainPartition, Phi)
+            for mdl in models:
+                pi = Pi if "Primary" in type(mdl).__name__ or "Secondary" in type(mdl).__name__ else None
+                for P in (Phi, dom):
+                    assert cp.bottleneck_value(A, P, mdl, pi) == ref.bottleneck_value(A, P, mdl, pi), (A, K, mdl)
+                    assert cp.total_value(A, P, mdl, pi) == ref.total_value(A, P, mdl, pi), (A, K, mdl)
+            f = cp.AffinePrimaryConnectivityModel(0, 2, 1, 3, 6)
+            for mtd in (cp.DynamicBottleneckSplitter(f), cp.BisectCostBottleneckSplitter(f, 0.01)):
+                if A.n > 500 and isinstance(mtd, cp.DynamicBottleneckSplitter):
+                    continue
+                g = cp.partition_stripe(A, K, mtd, Pi)
+                Amap, _, Pis = ref._contiguous(A, g, Pi)
+                assert np.array_equal(g.spl, ref.partition_stripe(Amap, K, mtd, Pis).spl)
+            S = cp.partition_stripe(A, K, cp.EquiSplitter())
+            net = cp.AffineConnectivityModel(0, 10, 1, 100)
+            assert cp.bottleneck_value(A, cp.convert(cp.MapPartition, S), net) == cp.bottleneck_value(A, S, net)
+    B = cp.permute(mats[0], rng.permutation(mats[0].n) + 1, None).to_host()
+    assert sorted(np.diff(B.colptr).tolist()) == sorted(np.diff(mats[0].colptr).tolist())
+    with pytest.raises(cp.CpbError):
+        cp.permute(mats[0], np.ones(mats[0].n, dtype=np.int64), None)
+
+
 def test_prefix_structures(ref):
     """dominancecount / dominancesum / rookcount! / rooksum! on the device (SparsePrefixMatrices.jl:1-1273; the reference's
     test_SparsePrefixMatrices.jl:26-71 dims and value types, plus sizes that span many rank blocks and scan tiles): every

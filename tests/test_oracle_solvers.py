@@ -480,6 +480,56 @@ def test_edgecut_part_oracles_and_solvers(ref):
                     assert opt <= v <= opt * (1 + eps), type(mtd).__name__
 
 
+def part_cost_by_definition(mdl, A, cols, row_asg, k):
+    """compute_objective's per-part numbers from the set definition (WorkCosts.jl:63-77, Costs.jl:52-66 on A[:, prm],
+    PrimaryConnectivityCosts.jl:127-159, EnvelopeCosts.jl:100-125): ``cols`` = the columns of part k in domain order."""
+    c = mdl.coef
+    rows = [r for j in cols for r in col_rows(A, j).tolist()]
+    nv, pins, nets = len(cols), len(rows), len(set(rows))
+    kind = mdl.kind
+    if kind == cp.types.MODEL_WORK:
+        return c[0] + nv * c[1] + pins * c[2]
+    if kind == cp.types.MODEL_CONNECTIVITY:
+        return c[0] + nv * c[1] + pins * c[2] + nets * c[3]
+    if kind == cp.types.MODEL_PRIMCONN:
+        l = sum(1 for r in set(rows) if row_asg[r - 1] == k)
+        return c[0] + nv * c[1] + pins * c[2] + l * c[3] + (nets - l) * c[4]
+    if kind == cp.types.MODEL_PRIMEDGE:
+        l = sum(1 for r in rows if row_asg[r - 1] == k)
+        return c[0] + nv * c[1] + l * c[2] + (pins - l) * c[3]
+    if kind == cp.types.MODEL_ENVELOPE:
+        lo, hi = A.m + 1, 0
+        for j in cols:
+            r = col_rows(A, j)
+            if len(r):
+                lo, hi = min(lo, int(r[0])), max(hi, int(r[-1]))
+        return c[0] + nv * c[1] + pins * c[2] + max(hi - lo, 0) * c[3]
+    raise AssertionError(kind)
+
+
+OBJECTIVE_MODELS = [cp.AffineWorkModel(1, 2, 3), cp.AffineConnectivityModel(0, 10, 1, 100), cp.AffineConnectivityModel(0.5, 1.0, 0.25, 3.0),
+                    cp.AffinePrimaryConnectivityModel(0, 2, 1, 3, 6), cp.AffinePrimaryEdgeCutModel(0, 2, 1, 5), cp.AffineEnvelopeModel(0, 1, 1, 2)]
+
+
+def test_objective_of_noncontiguous_partitions(ref):
+    """bottleneck_value / total_value for Map- and DomainPartitions of the columns and MapPartitions of the rows
+    (Costs.jl:26-66, WorkCosts.jl:53-81, PrimaryConnectivityCosts.jl:88-163, EnvelopeCosts.jl:75-129) equal the set definition."""
+    rng = np.random.default_rng(24)
+    for trial in range(60):
+        m, n = int(rng.integers(1, 10)), int(rng.integers(1, 12))
+        A = sprand(rng, m, n, float(rng.choice([0.1, 0.3, 0.6])))
+        K = int(rng.integers(1, 5))
+        Phi = cp.MapPartition(K, rng.integers(1, K + 1, n))
+        Pi = cp.MapPartition(K, rng.integers(1, K + 1, m))
+        dom = cp.convert(cp.DomainPartition, Phi)
+        for mdl in OBJECTIVE_MODELS:
+            needs_pi = mdl.kind in (cp.types.MODEL_PRIMCONN, cp.types.MODEL_PRIMEDGE)
+            costs = [part_cost_by_definition(mdl, A, dom.prm[dom.spl[k] - 1 : dom.spl[k + 1] - 1].tolist(), Pi.asg, k + 1) for k in range(K)]
+            for P in (Phi, dom):
+                assert ref.bottleneck_value(A, P, mdl, Pi if needs_pi else None) == max(costs)
+                assert ref.total_value(A, P, mdl, Pi if needs_pi else None) == sum(costs)
+
+
 def leftmost_chunk_dp(C, n, w_max):
     cst = np.full(n + 2, np.inf)
     cst[1] = 0
