@@ -412,6 +412,11 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
   ensure_context();
   CPB_REQUIRE(f && spl_out, "NULL argument");
   CPB_REQUIRE(K >= 1, "K must be >= 1");
+  if ((method == CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER || method == CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER) && f->O->mdl.kind >= CPB_MODEL_PRIMCONN &&
+      f->O->mdl.kind <= CPB_MODEL_SECEDGE)
+    // the chunker-form K-DP calls f(j, j') without a part index (DynamicSplitter.jl:62-71, 290-301): a MethodError for the
+    // partition-aware oracles, whose only method is (j, j', k) (PrimaryConnectivityCosts.jl:66, SecondaryConnectivityCosts.jl:82, ...)
+    throw Error(CPB_ERR_UNSUPPORTED, "the chunker-form K-DP has no method for the row-partition-aware cost models (the reference calls f(j, j') without k)");
   switch (method) {
     case CPB_SPLIT_DYNAMIC_BOTTLENECK: case CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER: solve_dynamic(*f->O, false, con, K, spl_out); break;
     case CPB_SPLIT_DYNAMIC_TOTAL: case CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER: solve_dynamic(*f->O, true, con, K, spl_out); break;

@@ -278,8 +278,9 @@ template <class T, int TIE> static void dynamic_T(Oracle& f, bool total, i64 K, 
 template <class T> static void dynamic_constrained_T(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
   const Matrix& A = *f.A;
   const i64 n = A.n;
-  CPB_REQUIRE(con->w_coef[1] >= 0 && con->w_coef[2] >= 0 && con->w_coef[1] + con->w_coef[2] >= 1 && con->w_coef[0] >= 0,
-              "constrained dynamic splitters on the device need a weight that grows with the part (VertexCount or AffineWorkModel(a >= 0, b_v >= 0, b_p >= 0))");
+  if (!(con->w_coef[1] >= 0 && con->w_coef[2] >= 0 && con->w_coef[1] + con->w_coef[2] >= 1 && con->w_coef[0] >= 0))
+    throw Error(CPB_ERR_UNSUPPORTED, "constrained dynamic splitters on the device need a weight that grows with the part (VertexCount or "
+                                     "AffineWorkModel(a >= 0, b_v >= 0, b_p >= 0) with b_v + b_p >= 1)");
   const i64 wa = con->w_coef[0], wbv = con->w_coef[1], wbp = con->w_coef[2], w_max = con->w_max;
   // widest part the vertex term alone allows (no pin term: exactly the window; with a pin term: an upper bound)
   const i64 W = wbv > 0 ? (w_max - wa) / wbv : n;

@@ -242,6 +242,10 @@ extern "C" int cpo_partition_stripe(int method, const cpo_model* mdl, const cpo_
           });
           break;
         case CPO_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER: case CPO_SPLIT_DYNAMIC_TOTAL_CHUNKER:
+          // DynamicSplitter.jl:62-71, 290-301 call f(1, j') and Step(f)(Next(j), Same(j')) WITHOUT a part index; the
+          // partition-aware oracles only have the method (j, j', k) (PrimaryConnectivityCosts.jl:66, ...)
+          if (mdl->kind >= CPO_MODEL_PRIMCONN && mdl->kind <= CPO_MODEL_SECEDGE)
+            throw std::invalid_argument("chunker-form K-DP on a row-partition-aware model (MethodError in the reference: no method f(j, j') without k)");
           with_oracle<T>(mdl, CPO_HINT_STEP, M, pi_spl, pi_K, [&](auto& f) {
             t1 = now_s();
             using F = std::remove_reference_t<decltype(f)>;

@@ -657,6 +657,25 @@ def test_prefix_structures(ref):
         C.query([A.m + 2], [1])
 
 
+def test_declined_combinations_match_the_reference(ref):
+    """Combinations the reference has no method for are declined on both sides (found by tests/fuzz_parity.py): the
+    chunker-form K-DP calls f(j, j') without a part index (DynamicSplitter.jl:62-71) -- a MethodError for the
+    partition-aware oracles; a weight that does not grow with the part is CPB_ERR_UNSUPPORTED, not an argument error."""
+    rng = np.random.default_rng(310)
+    A = sprand(rng, 12, 15, 0.3)
+    Pi = ref.partition_stripe(ref.adjointpattern(A), 3, cp.EquiSplitter())
+    for f in (cp.AffinePrimaryConnectivityModel(0, 2, 1, 3, 6), cp.AffinePrimaryEdgeCutModel(0, 2, 1, 5)):
+        for mtd in (cp.DynamicBottleneckChunker(f), cp.DynamicTotalChunker(f)):
+            with pytest.raises(RuntimeError):
+                ref.partition_stripe(A, 3, mtd, Pi)
+            with pytest.raises(cp.CpbError) as e:
+                cp.partition_stripe(A, 3, mtd, Pi)
+            assert e.value.code == -2
+    with pytest.raises(cp.CpbError) as e:
+        cp.partition_stripe(A, 3, cp.DynamicTotalSplitter(cp.ConstrainedCost(AFF, cp.AffineWorkModel(1, 0, 0), 5)))
+    assert e.value.code == -2
+
+
 def test_plaid_with_primary_models(ref):
     """A genuinely 2-D alternation (bin/test_table_bottleneck.jl:47-55 style): columns by connectivity, then rows and
     columns in turn by the primary connectivity cost given the other side's partition."""
