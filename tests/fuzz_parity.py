@@ -26,6 +26,19 @@ import pyoracle as ref  # noqa: E402
 from helpers import sprand  # noqa: E402
 
 
+def rand_large_matrix(rng):
+    """mid-size inputs: several probe tiles, rows beyond the row-segment limit (radix-sort link path), many rank blocks"""
+    fam = rng.integers(0, 4)
+    if fam == 0:
+        scale = int(rng.integers(12, 17))
+        return synth.rmat(scale, int((1 << scale) * rng.integers(4, 24)))
+    if fam == 1:
+        return synth.erdos_renyi(int(rng.integers(20000, 150000)), int(rng.integers(2, 12)))
+    if fam == 2:
+        return synth.banded(int(rng.integers(5000, 60000)), int(rng.integers(1, 40)), int(rng.integers(2, 6)))
+    return synth.random_geometric(int(rng.integers(10000, 80000)), float(rng.integers(3, 12)))
+
+
 def rand_matrix(rng):
     fam = rng.integers(0, 8)
     if fam == 0:
@@ -103,8 +116,13 @@ def rand_model(rng, A):
     return cp.AffineSecondaryEdgeCutModel(*c), True, True
 
 
-def rand_splitter(rng, f, decreasing, constrained_ok):
+def rand_splitter(rng, f, decreasing, constrained_ok, large=False):
     eps = float(rng.choice([0.3, 0.1, 0.01, 0.001]))
+    if large:  # the O(n^2) reference DPs would take minutes here
+        if decreasing:
+            return rng.choice([cp.FlipBisectIndexBottleneckSplitter(f), cp.FlipBisectCostBottleneckSplitter(f, eps), cp.LazyFlipBisectCostBottleneckSplitter(f, eps)])
+        return rng.choice([cp.BisectCostBottleneckSplitter(f, eps), cp.LazyBisectCostBottleneckSplitter(f, eps), cp.LazyBisectCostBottleneckSplitter(f, eps),
+                           cp.BisectIndexBottleneckSplitter(f), cp.EquiSplitter()])
     spec = f
     if constrained_ok and rng.random() < 0.25:
         w = cp.VertexCount() if rng.random() < 0.6 else cp.AffineWorkModel(*[int(x) for x in rng.choice([0, 1, 2], 3)])
@@ -137,6 +155,53 @@ def rand_packer(rng, A):
     return cp.DynamicTotalChunker(cp.ConstrainedCost(f, cp.VertexCount(), w_max)), True
 
 
+def misc_case(rng, A, stats):
+    """structures and drivers around the solvers: prefix matrices, colour counts, adjointpattern, objectives of
+    non-contiguous partitions, the plaid driver.  Returns a description of the first difference, or None."""
+    r = int(rng.integers(0, 5))
+    if r == 0:
+        val = rng.integers(0, 2**64, A.nnz, dtype=np.uint64) if rng.random() < 0.5 else rng.integers(-9, 10, A.nnz)
+        i, j = rng.integers(1, A.m + 2, 24), rng.integers(1, A.n + 2, 24)
+        C, S = cp.dominancecount(A), cp.dominancesum(A, val)
+        gc, gs = C.query(i, j), S.query(i, j)
+        C.close(); S.close()
+        if not np.array_equal(gc, ref.dominancecount(A, i, j)) or not np.array_equal(gs, ref.prefix_query(A.m, A.n, A.nnz, A.colptr, A.rowval, val, i, j)):
+            return "prefix structures"
+    elif r == 1:
+        j = rng.integers(1, A.n + 2, 24)
+        jp = rng.integers(1, A.n + 2, 24)
+        j, jp = np.minimum(j, jp), np.maximum(j, jp)
+        names = ["pincount", "netcount", "selfnetcount"] + (["dianetcount", "selfpincount"] if A.m == A.n else [])
+        for nm in names:
+            if not np.array_equal(getattr(cp, nm)(A).query(j, jp), getattr(ref, nm)(A, j, jp)):
+                return nm
+    elif r == 2:
+        g, e = cp.adjointpattern(A), ref.adjointpattern(A)
+        if not (np.array_equal(g.colptr, e.colptr) and np.array_equal(g.rowval, e.rowval)):
+            return "adjointpattern"
+    elif r == 3:
+        K = int(rng.integers(1, 6))
+        Phi = cp.MapPartition(K, rng.integers(1, K + 1, A.n))
+        Pi = cp.MapPartition(K, rng.integers(1, K + 1, A.m))
+        f, needs_pi, _ = rand_model(rng, A)
+        if isinstance(f, (cp.AffineSymmetricConnectivityModel, cp.AffineSymmetricEdgeCutModel, cp.AffineMonotonizedSymmetricConnectivityModel)):
+            return None  # diagonal-aware models have no meaning after a column permutation alone
+        pi = Pi if needs_pi else None
+        for fn in ("bottleneck_value", "total_value"):
+            if getattr(cp, fn)(A, Phi, f, pi) != getattr(ref, fn)(A, Phi, f, pi):
+                return fn + " of a MapPartition, " + type(f).__name__
+    else:
+        K = int(rng.integers(1, 6))
+        eps = float(rng.choice([0.1, 0.01]))
+        f1, f2 = cp.AffineConnectivityModel(*coefs(rng, 4)), cp.AffineConnectivityModel(*coefs(rng, 4))
+        meth = cp.AlternatingPartitioner(cp.LazyBisectCostBottleneckSplitter(f1, eps), cp.BisectCostBottleneckSplitter(f2, eps))
+        (Pg, Fg), (Pr, Fr) = cp.partition_plaid(A, K, meth), ref.partition_plaid(A, K, meth)
+        if not (np.array_equal(Pg.spl, Pr.spl) and np.array_equal(Fg.spl, Fr.spl)):
+            return "partition_plaid"
+    stats["misc"] += 1
+    return None
+
+
 def describe(A):
     return dict(m=A.m, n=A.n, colptr=A.colptr.tolist(), rowval=A.rowval.tolist()) if A.nnz <= 400 else dict(m=A.m, n=A.n, nnz=A.nnz)
 
@@ -146,17 +211,29 @@ def main():
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-cases", type=int, default=10**9)
+    ap.add_argument("--large", type=float, default=0.0, help="fraction of mid-size inputs (10^4..10^5 columns, up to ~10^6 nonzeros)")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     cp.init(0)
     t0 = time.time()
-    stats = dict(cases=0, compared=0, queries=0, unsupported=0, oracle_rejected=0, mismatches=0)
+    stats = dict(cases=0, compared=0, queries=0, misc=0, unsupported=0, oracle_rejected=0, mismatches=0)
     by_method = {}
     while time.time() - t0 < args.seconds and stats["cases"] < args.max_cases:
         stats["cases"] += 1
-        A = rand_matrix(rng)
+        large = rng.random() < args.large
+        A = rand_large_matrix(rng) if large else rand_matrix(rng)
         packing = rng.random() < 0.25
         Pi = None
+        if rng.random() < 0.12:
+            mtd = None
+            try:
+                what = misc_case(rng, A, stats)
+            except Exception as e:
+                what = "ERROR " + type(e).__name__ + " " + str(e)[:200]
+            if what:
+                stats["mismatches"] += 1
+                print("MISC MISMATCH", what, "A =", describe(A), flush=True)
+            continue
         try:
             if packing:
                 mtd, needs_pi = rand_packer(rng, A)
@@ -166,10 +243,10 @@ def main():
                 K = None
             else:
                 f, needs_pi, decreasing = rand_model(rng, A)
-                K = int(rng.integers(1, min(A.n + 3, 14)))
+                K = int(rng.integers(1, min(A.n + 3, 14))) if not large else int(rng.choice([2, 7, 64, 300, 1500]))
                 if needs_pi:
                     Pi = ref.partition_stripe(ref.adjointpattern(A), K, cp.EquiSplitter())
-                mtd = rand_splitter(rng, f, decreasing, constrained_ok=not needs_pi)
+                mtd = rand_splitter(rng, f, decreasing, constrained_ok=not needs_pi, large=large)
                 if rng.random() < 0.3:  # the oracle itself: c(j, j', k) on random ranges, and bound_stripe where the reference has one
                     j = rng.integers(1, A.n + 2, 24)
                     jp = rng.integers(1, A.n + 2, 24)
@@ -209,6 +286,7 @@ def main():
             name = type(mtd).__name__ + ("/" + type(getattr(mtd, "f", None)).__name__ if hasattr(mtd, "f") else "")
             by_method[name] = by_method.get(name, 0) + 1
             stats["compared"] += 1
+            stats["large"] = stats.get("large", 0) + int(large)
             if g.K != r.K or not np.array_equal(g.spl, r.spl):
                 stats["mismatches"] += 1
                 print("MISMATCH", name, "K =", K, "model =", getattr(getattr(mtd, "f", None), "__dict__", None), "Pi =", None if Pi is None else Pi.spl.tolist(),
