@@ -1032,6 +1032,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
       //  the ~20 us round trip the deferred check saves)
       f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, /*defer_check=*/A.N < ((i64)1 << 25), false, /*as_pos=*/true);
     }
+    trace_mark("links");
     const bool want_ub = run->adaptive && K >= 2 && K <= 65535 && A.n >= 1;  // (K is the y extent of the counting grid)
     DBuf<double> ub_out(1);
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1047,6 +1048,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
         f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, false, /*force_sort=*/true, /*as_pos=*/true);
         continue;
       }
+      trace_mark("plan_bound");
       f.ls->speculative = false;
       f.ls->h_first_count = info[0];
       if (dia) f.h_n_over = n_over;
@@ -1263,6 +1265,7 @@ void solve_flip(Oracle& f, int method, double eps, i64 K, int64_t* h_spl_out) {
 void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
   const int depth = std::min(std::max(env_int("CPB_BISECT_DEPTH", BS_LOCAL_DEPTH), 1), BS_LOCAL_DEPTH);
   BisectRun* run = bisect_begin(f, lazy, eps, K, (1 << depth) - 1, nullptr, nullptr, nullptr);
+  trace_mark("begin");
   try {
     ProfScope prof("probe");
     // The gap c_hi - c_lo halves with every probe and the loop stops once it is <= eps * c_lo, so the number
@@ -1278,7 +1281,9 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     }
     for (int guard = 0; guard < 4096 && !run->done; ++guard) {
       bisect_probe(*run, 0, run->P);
+      trace_mark("probe");
       bisect_advance(*run, true);
+      trace_mark("advance");
     }
     CPB_REQUIRE(run->done, "bisection did not terminate (eps too small for Float64?)");
   } catch (...) {
@@ -1286,6 +1291,7 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     throw;
   }
   bisect_finish(run, h_spl_out);
+  trace_mark("finish");
 #ifdef CPB_PROBE_TIMING
   if (env_int("CPB_PROBE_TIMING_DUMP", 0)) probe_timing_dump();
 #endif

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libchainb200.so (include/chainb200.h): argument checking, handle
 // ownership, error translation.  Nothing throws across this boundary.
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include "engine.cuh"
@@ -46,6 +47,76 @@ static void init_context(int device) {
   unsigned long long thr = ~0ull;  // keep freed blocks cached in the pool
   CPB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   g_ctx.ready = true;
+}
+
+// ---- CPB_TRACE ------------------------------------------------------------------------------------------------------
+static std::vector<std::pair<const char*, double>> g_trace;
+static int trace_on() {
+  static const int on = std::getenv("CPB_TRACE") ? std::atoi(std::getenv("CPB_TRACE")) : 0;
+  return on;
+}
+void trace_mark(const char* label) {
+  if (!trace_on()) return;
+  if (g_ctx.stream) cudaStreamSynchronize(g_ctx.stream);
+  g_trace.push_back({label, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count()});
+}
+void trace_flush(const char* what) {
+  if (!trace_on() || g_trace.empty()) return;
+  std::string line = std::string("[cpb trace] ") + what + ":";
+  for (size_t i = 1; i < g_trace.size(); ++i) {
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), " %s=%.2f", g_trace[i].first, g_trace[i].second - g_trace[i - 1].second);
+    line += buf;
+  }
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), " | total=%.2f ms", g_trace.back().second - g_trace.front().second);
+  std::fprintf(stderr, "%s%s\n", line.c_str(), buf);
+  g_trace.clear();
+}
+
+// ---- free list of large device blocks (see common.cuh) --------------------------------------------------------------
+static std::multimap<size_t, void*> g_big_free;
+static size_t g_big_cached = 0;
+void big_trim() {
+  if (g_big_free.empty()) return;
+  cudaStreamSynchronize(g_ctx.stream);
+  for (auto& kv : g_big_free) cudaFree(kv.second);
+  g_big_free.clear();
+  g_big_cached = 0;
+}
+void* big_alloc(size_t bytes) {
+  auto it = g_big_free.find(bytes);
+  if (it != g_big_free.end()) {
+    void* p = it->second;
+    g_big_free.erase(it);
+    g_big_cached -= bytes;
+    return p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {  // give the cached blocks (and the driver pool's) back and try once more
+    cudaGetLastError();
+    big_trim();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(CPB_ERR_CUDA, std::string("out of device memory (") + std::to_string(bytes >> 20) + " MiB requested): " + cudaGetErrorString(e));
+  }
+  return p;
+}
+void big_free(void* p, size_t bytes) {
+  // everything is returned to the driver once the cache holds more than a quarter of the device
+  static size_t limit = 0;
+  if (limit == 0) {
+    size_t free_b = 0, total_b = 0;
+    limit = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) ? total_b / 4 : ((size_t)16 << 30);
+  }
+  if (g_big_cached + bytes > limit) big_trim();
+  g_big_free.emplace(bytes, p);
+  g_big_cached += bytes;
 }
 
 void ensure_context() {
@@ -119,6 +190,17 @@ int cpb_device_count(void) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
   return count;
+}
+
+int cpb_trim_memory(void) {
+  CPB_API_BEGIN
+  ensure_context();
+  big_trim();
+  cudaMemPool_t pool;
+  CPB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx().device));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_CUDA(cudaMemPoolTrimTo(pool, 0));
+  CPB_API_END
 }
 
 int cpb_synchronize(void) {
@@ -412,6 +494,8 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
   ensure_context();
   CPB_REQUIRE(f && spl_out, "NULL argument");
   CPB_REQUIRE(K >= 1, "K must be >= 1");
+  trace_mark("enter");
+  struct TraceEnd { ~TraceEnd() { trace_mark("exit"); trace_flush("partition_stripe"); } } trace_end;
   if ((method == CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER || method == CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER) && f->O->mdl.kind >= CPB_MODEL_PRIMCONN &&
       f->O->mdl.kind <= CPB_MODEL_SECEDGE)
     // the chunker-form K-DP calls f(j, j') without a part index (DynamicSplitter.jl:62-71, 290-301): a MethodError for the

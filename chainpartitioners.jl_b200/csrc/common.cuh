@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -68,7 +69,16 @@ void ensure_context();   // throws Error(-3) when no usable device
     CPB_CUDA(cudaPeekAtLastError());                                               \
   } while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync on the library stream).
+// Large buffers (>= 64 MiB) bypass the driver's stream-ordered pool: at the GB sizes of the big configurations the pool
+// occasionally re-stitches its virtual ranges inside cudaMallocAsync, which showed up as 50-700 ms stalls on the device
+// timeline of a 37 ms solve.  The library keeps its own free list of exact-size blocks instead (every solve asks for the
+// same sizes again); all work runs on the one library stream, so handing a freed block to the next request is ordered.
+static constexpr size_t CPB_BIG_BYTES = (size_t)64 << 20;
+void* big_alloc(size_t bytes);           // capi.cu
+void big_free(void* p, size_t bytes);    // capi.cu
+void big_trim();                         // returns every cached block to the driver
+
+// Stream-ordered device buffer (cudaMallocAsync on the library stream; large blocks from the library's own free list).
 template <class T> struct DBuf {
   T* p = nullptr;
   size_t n = 0;
@@ -85,12 +95,18 @@ template <class T> struct DBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    size_t bytes = (count ? count : 1) * sizeof(T);
-    CPB_CUDA(cudaMallocAsync((void**)&p, bytes, ctx().stream));
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    if (bytes >= CPB_BIG_BYTES) p = (T*)big_alloc(bytes);
+    else CPB_CUDA(cudaMallocAsync((void**)&p, bytes, ctx().stream));
   }
   void zero() { if (p) CPB_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx().stream)); }
   void release() {
-    if (p) { cudaFreeAsync(p, ctx().stream); p = nullptr; n = 0; }
+    if (p) {
+      const size_t bytes = (n ? n : 1) * sizeof(T);
+      if (bytes >= CPB_BIG_BYTES) big_free(p, bytes); else cudaFreeAsync(p, ctx().stream);
+      p = nullptr;
+      n = 0;
+    }
   }
   T* get() const { return p; }
   operator T*() const { return p; }
@@ -106,6 +122,11 @@ struct ProfScope {
   ProfScope(const char* nm, double algorithmic_bytes = 0);
   ~ProfScope();
 };
+
+// CPB_TRACE=1: host wall-clock marks (each after a stream synchronise) printed to stderr by the next cpb_* entry point that
+// flushes them -- for attributing time that no kernel scope accounts for.  Off: one predictable branch.
+void trace_mark(const char* label);  // capi.cu
+void trace_flush(const char* what);
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -55,6 +55,26 @@ __global__ void k_link_prev(const u32* __restrict__ sk, const u32* __restrict__ 
   if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
 }
 
+// The same links as values in sorted order (no scatter yet): lv[p] = link of the nonzero sq[p]
+__global__ void k_link_values(const u32* __restrict__ sk, const u32* __restrict__ sq, const u32* __restrict__ colidx, u32* __restrict__ lv, size_t N,
+                              u32* __restrict__ first_count, int as_pos) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 firsts = 0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) {
+    u32 link = 0;
+    if (p > 0 && sk[p - 1] == sk[p]) link = as_pos ? sq[p - 1] + 1u : __ldg(colidx + sq[p - 1]) + 1u;
+    lv[p] = link;
+    firsts += link == 0u;
+  }
+  firsts = __reduce_add_sync(0xffffffffu, firsts);
+  if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
+}
+// prev[q[p]] = v[p], pairs grouped by destination window: consecutive CTAs write into the same few megabytes
+__global__ void k_scatter_pairs(const u32* __restrict__ q, const u32* __restrict__ v, u32* __restrict__ prev, size_t N) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < N) prev[q[p]] = v[p];
+}
+
 __global__ void k_head_flags(const u32* __restrict__ sk, size_t N, u32* __restrict__ flags) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p <= N; p += stride)
@@ -245,9 +265,24 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
     }
   }
   if (row_lo <= 0 && row_hi >= (i64)nrow) {
+    trace_mark("degree_check");
     TransposeOrder t;
     transpose_order(row, N, nrow ? nrow - 1 : 0, t);
-    if (N) {
+    trace_mark("sort");
+    const char* wmin_env = std::getenv("CPB_WINDOWED_SCATTER_MIN");  // (tests force the windowed form on small inputs; 0 = never)
+    const size_t wmin = wmin_env ? (size_t)std::atoll(wmin_env) : ((size_t)1 << 25);
+    if (wmin > 0 && N >= wmin) {
+      // the link array no longer fits L2: a scatter in row order touches one HBM sector per 4-byte link (measured 10.9 ms
+      // at N = 2.6e8).  One more partition pass groups the (position, link) pairs by 2^20-position windows (4 MB of `prev`
+      // each), and the scatter of each window stays in L2.
+      ProfScope pk("k_link_prev", (double)N * 12.0);
+      u32* const other_k = (t.keys == t.k0.get()) ? t.k1.get() : t.k0.get();  // the sort's scratch pair
+      u32* const other_v = (t.q == t.v0.get()) ? t.v1.get() : t.v0.get();
+      CPB_LAUNCH(k_link_values, grid_for(N), 256, 0, t.keys, t.q, colidx, other_k, N, first_count, as_pos ? 1 : 0);
+      const int shift = std::max(0, bits_for(N - 1) - 8);
+      radix_partition_pass(t.q, other_k, t.keys, other_v, N, shift);  // t.keys is free once the links are formed
+      CPB_LAUNCH(k_scatter_pairs, (unsigned)((N + 255) / 256), 256, 0, t.keys, other_v, prev, N);
+    } else if (N) {
       ProfScope pk("k_link_prev", (double)N * 12.0);
       CPB_LAUNCH(k_link_prev, grid_for(N), 256, 0, t.keys, t.q, colidx, prev, N, first_count, as_pos ? 1 : 0);
     }

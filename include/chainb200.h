@@ -95,6 +95,9 @@ int cpb_init(int device);
 int cpb_device_count(void);
 /* Blocks until all queued work of the library stream has finished. */
 int cpb_synchronize(void);
+/* Returns the device memory the library keeps cached between calls (its free list of large blocks and the stream-ordered
+ * pool) to the driver.  Handles stay valid. */
+int cpb_trim_memory(void);
 
 /* ---- matrices ---------------------------------------------------------------------------- */
 typedef struct cpb_matrix cpb_matrix;

@@ -62,15 +62,18 @@ def test_link_construction_paths(ref, monkeypatch):
         want_net, want_dia = ref.netcount(A, j, jp), ref.dianetcount(A, j, jp)
         mtd = cp.LazyBisectCostBottleneckSplitter(AFF, 0.01)
         want_spl = ref.partition_stripe(A, 8, mtd).spl
-        for force_sort in (False, True):
+        for force_sort, windowed in ((False, False), (True, False), (True, True)):
             if force_sort:
                 monkeypatch.setenv("CPB_NO_ROW_SEGMENTS", "1")
             else:
                 monkeypatch.delenv("CPB_NO_ROW_SEGMENTS", raising=False)
+            # the sort form scatters the links either directly or (large inputs) after grouping them by destination window
+            monkeypatch.setenv("CPB_WINDOWED_SCATTER_MIN", "1" if windowed else "0")
             assert np.array_equal(cp.netcount(A).query(j, jp), want_net)
             assert np.array_equal(cp.dianetcount(A).query(j, jp), want_dia)
             assert np.array_equal(cp.partition_stripe(A, 8, mtd).spl, want_spl)
     monkeypatch.delenv("CPB_NO_ROW_SEGMENTS", raising=False)
+    monkeypatch.delenv("CPB_WINDOWED_SCATTER_MIN", raising=False)
 
 
 MODELS = [
