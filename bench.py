@@ -206,16 +206,42 @@ def main():
     # ---- e2e: host buffers through the public call ----
     barrier()
     e2e_ms = 0.0
+    e2e_samples = []
     for _ in range(args.steps):
         flush_l2()
         t0 = time.perf_counter()
         Phi2 = step_e2e()
         cp.synchronize()
-        e2e_ms += (time.perf_counter() - t0) * 1e3
+        e2e_samples.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms += e2e_samples[-1]
     barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     assert np.array_equal(Phi.spl, Phi2.spl)
+
+    # ---- the same end-to-end call for a SparseMatrixCSC{Tv, Int32} (half the upload; informative, not the headline) ----
+    colptr32_pin = torch.from_numpy(A.colptr.astype(np.int32)).pin_memory()
+    rowval32_pin = torch.from_numpy(A.rowval.astype(np.int32)).pin_memory()
+
+    def step_e2e_i32():
+        d32 = cp.device_matrix_i32(A.m, A.n, colptr32_pin.numpy(), rowval32_pin.numpy())
+        try:
+            return cp.partition_stripe(d32, K_PARTS, mtd)
+        finally:
+            d32.close()
+
+    for _ in range(3):
+        step_e2e_i32()
+    n32 = max(3, min(args.steps, 50))
+    e2e32_samples = []
+    for _ in range(n32):
+        flush_l2()
+        t0 = time.perf_counter()
+        Phi3 = step_e2e_i32()
+        cp.synchronize()
+        e2e32_samples.append((time.perf_counter() - t0) * 1e3)
+    e2e32_ms = float(np.mean(e2e32_samples))
+    assert np.array_equal(Phi.spl, Phi3.spl)
 
     # ---- cost-oracle query throughput (the other half of BASELINE.json's metric) ----
     Q = 1 << 22
@@ -290,8 +316,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
                 "data": "synthetic", "config": config,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps,
-                        "h2d_bytes_per_step": int((A.nnz + A.n + 1) * 8 + 512), "d2h_bytes_per_step": int((K_PARTS + 1) * 8 + 64)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps, "median_ms_per_step": float(np.median(e2e_samples)),
+                        "max_ms": float(np.max(e2e_samples)), "h2d_bytes_per_step": int((A.nnz + A.n + 1) * 8 + 512), "d2h_bytes_per_step": int((K_PARTS + 1) * 8 + 64)},
+                "e2e_int32_index": {"ms_per_step": e2e32_ms, "median_ms_per_step": float(np.median(e2e32_samples)), "max_ms": float(np.max(e2e32_samples)), "h2d_bytes_per_step": int(colptr32_pin.numel() * 4 + rowval32_pin.numel() * 4),
+                                    "note": "same public call for a SparseMatrixCSC{Tv,Int32} (cpb_matrix_create_i32), rank 0; the headline e2e is the Int64 form"},
                 "oracle_queries_per_s": queries_per_s * world, "oracle_query_batch": {"Q": Q, "ms": q_ms / 3, "pattern": "uniform random (j <= j') pairs, device-resident"},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_all_kernels": roofline_all, "cpu_baseline": cpu, "clocks": sampler.summary(),
                 "phases_ms_per_step": phases, "bisection": cp.bisect_stats(), "parity": "split vector identical to the CPU oracle" if cpu else "checked at N=1"}

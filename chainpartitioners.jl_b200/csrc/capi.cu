@@ -259,7 +259,8 @@ static void h2d_copy(void* d_dst, const void* h_src, size_t bytes) {
   }
 }
 
-static void matrix_from_device(Matrix& M, i64 m, i64 n, i64 nnz, const i64* d_colptr, const i64* d_rowval) {
+extern "C++" {
+template <class Ti> static void matrix_from_device(Matrix& M, i64 m, i64 n, i64 nnz, const Ti* d_colptr, const Ti* d_rowval) {
   CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
   CPB_REQUIRE(nnz + n + 1 < ((i64)1 << 31) && m < ((i64)1 << 31) - 2 && n < ((i64)1 << 31) - 2, "matrix too large for the 32-bit device index");
   M.m = m; M.n = n; M.N = nnz;
@@ -267,19 +268,25 @@ static void matrix_from_device(Matrix& M, i64 m, i64 n, i64 nnz, const i64* d_co
   M.row.alloc((size_t)nnz);
   DBuf<u32> flags(1);
   flags.zero();
-  narrow_minus1(d_colptr, M.pos.get(), (size_t)n + 1, 1, nnz + 1, flags.get());
-  narrow_minus1(d_rowval, M.row.get(), (size_t)nnz, 1, m, flags.get());
+  if constexpr (sizeof(Ti) == 8) {
+    narrow_minus1((const i64*)d_colptr, M.pos.get(), (size_t)n + 1, 1, nnz + 1, flags.get());
+    narrow_minus1((const i64*)d_rowval, M.row.get(), (size_t)nnz, 1, m, flags.get());
+  } else {
+    narrow32_minus1((const int*)d_colptr, M.pos.get(), (size_t)n + 1, 1, nnz + 1, flags.get());
+    narrow32_minus1((const int*)d_rowval, M.row.get(), (size_t)nnz, 1, m, flags.get());
+  }
   check_monotone(M.pos.get(), (size_t)n + 1, flags.get());
   u32 hf = 0;
-  i64 ends[2] = {0, 0};
+  Ti ends[2] = {0, 0};
   CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
-  CPB_CUDA(cudaMemcpyAsync(&ends[0], d_colptr, sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
-  CPB_CUDA(cudaMemcpyAsync(&ends[1], d_colptr + n, sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(&ends[0], d_colptr, sizeof(Ti), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaMemcpyAsync(&ends[1], d_colptr + n, sizeof(Ti), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
   CPB_REQUIRE((hf & 1u) == 0, "colptr/rowval entry out of range (expected 1-based indices)");
   CPB_REQUIRE((hf & 2u) == 0, "colptr is not non-decreasing");
-  CPB_REQUIRE(ends[0] == 1 && ends[1] == nnz + 1, "colptr[1] must be 1 and colptr[n+1] must be nnz+1");
+  CPB_REQUIRE((i64)ends[0] == 1 && (i64)ends[1] == nnz + 1, "colptr[1] must be 1 and colptr[n+1] must be nnz+1");
 }
+}  // extern "C++"
 
 int cpb_matrix_create_device(int64_t m, int64_t n, int64_t nnz, const int64_t* d_colptr, const int64_t* d_rowval, cpb_matrix** out) {
   CPB_API_BEGIN
@@ -302,6 +309,21 @@ int cpb_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, 
   h2d_copy(dr.get(), rowval, (size_t)nnz * sizeof(i64));
   auto h = std::make_unique<cpb_matrix>();
   matrix_from_device(h->M, m, n, nnz, dc.get(), dr.get());
+  *out = h.release();
+  CPB_API_END
+}
+
+int cpb_matrix_create_i32(int64_t m, int64_t n, int64_t nnz, const int32_t* colptr, const int32_t* rowval, cpb_matrix** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(out && colptr && (rowval || nnz == 0), "NULL argument");
+  CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
+  ProfScope prof("h2d_matrix", (double)(nnz + n + 1) * 4.0);
+  DBuf<int> dc((size_t)n + 1), dr((size_t)nnz);
+  h2d_copy(dc.get(), colptr, ((size_t)n + 1) * sizeof(int));
+  h2d_copy(dr.get(), rowval, (size_t)nnz * sizeof(int));
+  auto h = std::make_unique<cpb_matrix>();
+  matrix_from_device<int>(h->M, m, n, nnz, dc.get(), dr.get());
   *out = h.release();
   CPB_API_END
 }

@@ -321,6 +321,21 @@ __global__ void k_narrow_minus1(const i64* __restrict__ src, u32* __restrict__ d
   }
   if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
 }
+__global__ void k_narrow32_minus1(const int* __restrict__ src, u32* __restrict__ dst, size_t n, i64 lo, i64 hi, u32* flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const i64 v = src[i];
+    bad |= (v < lo) | (v > hi);
+    dst[i] = (u32)(v - 1);
+  }
+  if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+}
+void narrow32_minus1(const int* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flags) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_narrow32_minus1, grid, 256, 0, src, dst, n, lo, hi, flags);
+}
 void narrow_minus1(const i64* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flags) {
   if (n == 0) return;
   const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);

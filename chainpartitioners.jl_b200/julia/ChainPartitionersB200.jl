@@ -103,6 +103,13 @@ mutable struct DeviceMatrix
             (Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}), m, n, nnz(A), A.colptr, A.rowval, h))
         finalizer(x -> ccall((:cpb_matrix_destroy, lib), Cvoid, (Ptr{Cvoid},), x.h), new(h[], m, n))
     end
+    function DeviceMatrix(A::SparseMatrixCSC{Tv, Int32}) where {Tv}  # half the upload
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        (m, n) = size(A)
+        GC.@preserve A check(ccall((:cpb_matrix_create_i32, lib), Cint,
+            (Int64, Int64, Int64, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}), m, n, nnz(A), A.colptr, A.rowval, h))
+        finalizer(x -> ccall((:cpb_matrix_destroy, lib), Cvoid, (Ptr{Cvoid},), x.h), new(h[], m, n))
+    end
 end
 
 mutable struct DeviceOracle

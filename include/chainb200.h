@@ -103,6 +103,8 @@ int cpb_trim_memory(void);
 typedef struct cpb_matrix cpb_matrix;
 /* Copies a SparseMatrixCSC pattern (A.colptr, A.rowval) to the device (32-bit, 0-based there). */
 int cpb_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, cpb_matrix** out);
+/* The same for a SparseMatrixCSC{Tv, Int32} (the reference is generic in the index type Ti; half the upload). */
+int cpb_matrix_create_i32(int64_t m, int64_t n, int64_t nnz, const int32_t* colptr, const int32_t* rowval, cpb_matrix** out);
 /* Same from device-resident Int64 arrays (inputs already in HBM). */
 int cpb_matrix_create_device(int64_t m, int64_t n, int64_t nnz, const int64_t* d_colptr, const int64_t* d_rowval, cpb_matrix** out);
 int cpb_matrix_dims(const cpb_matrix* A, int64_t* m, int64_t* n, int64_t* nnz);

@@ -35,6 +35,21 @@ def test_adjointpattern(ref, fixtures):
         assert (g.m, g.n) == (A.n, A.m)
 
 
+def test_int32_indexed_matrix(ref, fixtures):
+    """cpb_matrix_create_i32 (SparseMatrixCSC{Tv, Int32}): the same device matrix as the Int64 form, and the same errors."""
+    for A in small_matrices(fixtures) + [synth.erdos_renyi(20000, 10)]:
+        d = cp.device_matrix_i32(A.m, A.n, A.colptr.astype(np.int32), A.rowval.astype(np.int32))
+        B = d.to_host()
+        assert (B.m, B.n) == (A.m, A.n) and np.array_equal(B.colptr, A.colptr) and np.array_equal(B.rowval, A.rowval)
+        mtd = cp.LazyBisectCostBottleneckSplitter(AFF, 0.01)
+        assert np.array_equal(cp.partition_stripe(d, 4, mtd).spl, ref.partition_stripe(A, 4, mtd).spl)
+        d.close()
+    with pytest.raises(cp.CpbError):
+        cp.device_matrix_i32(2, 2, np.array([1, 2, 3], dtype=np.int32), np.array([1, 3], dtype=np.int32))  # row 3 of 2
+    with pytest.raises(cp.CpbError):
+        cp.device_matrix_i32(2, 2, np.array([1, 3, 2], dtype=np.int32), np.array([1, 2], dtype=np.int32))  # colptr not monotone
+
+
 def test_color_arrays(ref, fixtures):
     rng = np.random.default_rng(101)
     for A in small_matrices(fixtures) + [synth.laplacian5(40), synth.erdos_renyi(5000, 10)]:
