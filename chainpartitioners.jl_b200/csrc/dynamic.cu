@@ -343,6 +343,160 @@ template <class T> static void dynamic_constrained_T(Oracle& f, bool total, cons
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 
+// ---- ConvexTotalSplitter{<:ConstrainedCost} (ConvexTotalChunker.jl:167-265) ---------------------------------------------
+// Per layer the reference runs chunk_convex_constrained! on window-constrained columns of Extended costs: the columns
+// after J0 = j'_lo[k-1] fall into blocks (b_t, b_t+1], b_t+1 = the last column that still fits into one part with b_t; a
+// block first receives, from the "staircase" pass, the best split point among the previous block (the reversed indices of
+// :252-258 make it the RIGHTMOST minimiser, and the value replaces the layer's initial empty-part candidate), then the
+// in-block pass offers the LEFTMOST minimiser of [b_t, j'-1] and wins ties (`<=`, :66,74).  Block 0 only has the in-block
+// pass against the empty-part initialisation.  The values are the constrained optimum; this rule reproduces the pointers:
+// 2500/2500 random cases (vertex- and pin-weighted windows, Int64 and Float64 costs) against the restated algorithm
+// (scratch/convex_k_rule2.py), and tests/test_gpu_parity.py::test_constrained_convex_total_splitter.
+template <class T> struct DpInf;
+template <> struct DpInf<i64> { static __device__ __forceinline__ i64 get() { return (i64)1 << 61; } };
+template <> struct DpInf<double> { static __device__ __forceinline__ double get() { return 1e300; } };
+
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_convex_constrained(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
+                                                               u32* __restrict__ ptr, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, DevWeight wt, u32 k,
+                                                               const u32* __restrict__ blk, u32 nblk) {
+  const T INF = DpInf<T>::get();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x + lo_k; idx <= hi_k; idx += stride) {
+    const u32 jp = (u32)idx;
+    // the layer's initialisation: the empty part k (ptr = j')
+    T best = (jp >= lo_p && jp <= hi_p && prev[jp] < INF) ? prev[jp] + dev_cost<T>(o, jp, jp, k) : INF;
+    u32 arg = jp;
+    if (jp > blk[0]) {
+      u32 a = 0, b = nblk;  // largest t with blk[t] < jp   (blk[0] < jp <= blk[nblk])
+      while (b - a > 1) {
+        const u32 mid = a + ((b - a) >> 1);
+        if (__ldg(blk + mid) < jp) a = mid; else b = mid;
+      }
+      const u32 j0 = __ldg(blk + a);
+      if (a > 0) {  // staircase pass: rightmost minimiser among the previous block's columns that still fit; replaces the initialisation
+        u32 lo_j = __ldg(blk + a - 1) + 1, hi_j = min(j0, hi_p);
+        {
+          u32 x = lo_j, y = j0;  // smallest j in [lo_j, j0] with w(j, j') <= w_max (j0 itself fits: j' lies in its block)
+          while (x < y) {
+            const u32 mid = x + ((y - x) >> 1);
+            if (weight_ok(o, wt, mid, jp)) y = mid; else x = mid + 1;
+          }
+          lo_j = max(x, lo_p);
+        }
+        best = INF;
+        arg = j0;
+        for (u32 j = lo_j; j <= hi_j; ++j) {
+          const T pv = prev[j];
+          if (pv >= INF) continue;
+          const T v = pv + dev_cost<T>(o, j, jp, k);
+          if (best >= INF || v <= best) { best = v; arg = j; }
+        }
+      }
+      // in-block pass: leftmost minimiser of [j0, j'-1]; wins ties against what the column holds
+      T vin = INF;
+      u32 jin = 0;
+      for (u32 j = max(j0, lo_p); j <= min(jp - 1, hi_p); ++j) {
+        const T pv = prev[j];
+        if (pv >= INF) continue;
+        const T v = pv + dev_cost<T>(o, j, jp, k);
+        if (vin >= INF || v < vin) { vin = v; jin = j; }
+      }
+      if (vin < INF && (best >= INF || vin <= best)) { best = vin; arg = jin; }
+    }
+    cur[jp] = best;
+    ptr[jp] = arg;
+  }
+}
+
+template <class T> static void convex_constrained_T(Oracle& f, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
+  const Matrix& A = *f.A;
+  const i64 n = A.n;
+  if (!(con->w_coef[1] >= 0 && con->w_coef[2] >= 0 && con->w_coef[1] + con->w_coef[2] >= 1 && con->w_coef[0] >= 0))
+    throw Error(CPB_ERR_UNSUPPORTED, "constrained splitters on the device need a weight that grows with the part (VertexCount or "
+                                     "AffineWorkModel(a >= 0, b_v >= 0, b_p >= 0) with b_v + b_p >= 1)");
+  const i64 wa = con->w_coef[0], wbv = con->w_coef[1], wbp = con->w_coef[2], w_max = con->w_max;
+  std::vector<u32> hpos;
+  if (wbp != 0) {
+    hpos.resize((size_t)n + 1);
+    CPB_CUDA(cudaMemcpyAsync(hpos.data(), A.pos.get(), ((size_t)n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  }
+  auto fits = [&](i64 j, i64 jp) {
+    i64 w = wa + (jp - j) * wbv;
+    if (wbp != 0) w += ((i64)hpos[jp - 1] - (i64)hpos[j - 1]) * wbp;
+    return w <= w_max;
+  };
+  auto reach = [&](i64 j, i64 limit) {  // largest jp in [j + 1, limit] reached by the reference's `while w(j, jp + 1) <= w_max` from jp = j + 1
+    i64 a = std::min(j + 1, limit), b = limit;
+    while (a < b) {
+      const i64 mid = a + (b - a + 1) / 2;
+      if (fits(j, mid)) a = mid; else b = mid - 1;
+    }
+    return a;
+  };
+  // column_constraints (DynamicSplitter.jl:144-173), as in dynamic_constrained_T
+  std::vector<i64> lo(K + 1), hi(K + 1);
+  for (i64 k = K, jp = n + 1; k >= 1; --k) {
+    lo[k] = jp;
+    i64 a = 1, b = jp;
+    while (a < b) {
+      const i64 mid = a + (b - a) / 2;
+      if (fits(mid, jp)) b = mid; else a = mid + 1;
+    }
+    jp = a;
+  }
+  for (i64 k = 1, j = 1; k <= K; ++k) {
+    i64 a = j, b = n + 1;
+    while (a < b) {
+      const i64 mid = a + (b - a + 1) / 2;
+      if (fits(j, mid)) a = mid; else b = mid - 1;
+    }
+    hi[k] = a;
+    j = a;
+  }
+  if (wa > w_max) { for (i64 k = 1; k <= K; ++k) hi[k] = 1; }
+  if (hi[K] < n + 1) {  // ConvexTotalChunker.jl:184-189 infeasible -> degenerate partition
+    for (i64 k = 0; k < K; ++k) h_spl_out[k] = 1;
+    h_spl_out[K] = n + 1;
+    return;
+  }
+  const u32 n1 = (u32)n + 1, n2 = n1 + 1;
+  ProfScope prof("dp_layer");
+  DBuf<T> rowa(n2), rowb(n2);
+  DBuf<u32> ptr((size_t)K * n2), dblk(n2);
+  DBuf<i64> spl(K + 1);
+  ptr.zero();
+  T* prev = rowa.get();
+  T* cur = rowb.get();
+  std::vector<u32> blk;
+  for (i64 k = 1; k <= K; ++k) {
+    const size_t cnt = (size_t)(hi[k] - lo[k] + 1);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt + 255) / 256, (size_t)ctx().sm_count * 8));
+    if (k == 1) {
+      CPB_LAUNCH(k_dp_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get(), 1, (u32)lo[1], (u32)hi[1], 1u, 1u, 0u, 1, DevWeight{wa, wbv, wbp, w_max}, 1u);
+    } else {
+      // the block chain of this layer: b_0 = j'_lo[k-1], b_1 = the reach of b_0 (at least b_0 + 1, :213-216), b_t+1 = the reach of b_t
+      const i64 J0 = lo[k - 1], JP1 = hi[k];
+      blk.clear();
+      blk.push_back((u32)J0);
+      for (i64 b = J0; b < JP1;) {
+        const i64 nx = std::max(reach(b, JP1), b + 1);
+        blk.push_back((u32)nx);
+        b = nx;
+      }
+      CPB_CUDA(cudaMemcpyAsync(dblk.get(), blk.data(), blk.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // blk is reused by the next layer
+      CPB_LAUNCH(k_dp_convex_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, (u32)lo[k], (u32)hi[k], (u32)lo[k - 1],
+                 (u32)hi[k - 1], DevWeight{wa, wbv, wbp, w_max}, (u32)k, dblk.get(), (u32)(blk.size() - 1));
+    }
+    std::swap(prev, cur);
+  }
+  CPB_LAUNCH(k_dp_unravel, 1, 32, 0, ptr.get(), n2, (int)K, n1, spl.get());
+  CPB_CUDA(cudaMemcpyAsync(h_spl_out, spl.get(), (K + 1) * sizeof(i64), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
 void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   if (con && con->enabled) {
@@ -372,10 +526,14 @@ void solve_dynamic(Oracle& f, bool total, const cpb_constraint* con, i64 K, int6
 // the reference's result is an artefact of its candidate stack and is not reproduced here.
 void solve_convex_splitter(Oracle& f, const cpb_constraint* con, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
-  if (con && con->enabled) throw Error(CPB_ERR_UNSUPPORTED, "constrained ConvexTotalSplitter (ConvexTotalChunker.jl:167-209) is not built on the device");
   bool convex = f.mdl.kind == CPB_MODEL_WORK || f.mdl.kind == CPB_MODEL_CONNECTIVITY || f.mdl.kind == CPB_MODEL_MONOSYM;
   for (int t = 1; t <= 3; ++t) convex = convex && f.mdl.coef[t] >= 0;
   if (!convex) throw Error(CPB_ERR_UNSUPPORTED, "ConvexTotalSplitter on the device needs a cost model obeying the quadrangle inequality (work / connectivity / monotonized-symmetric, beta >= 0)");
+  if (con && con->enabled) {  // ConvexTotalChunker.jl:167-209
+    oracle_ensure_ranks(f);
+    if (f.dev.is_float) convex_constrained_T<double>(f, con, K, h_spl_out); else convex_constrained_T<i64>(f, con, K, h_spl_out);
+    return;
+  }
   if (K == 1) {  // :33-35
     h_spl_out[0] = 1;
     h_spl_out[1] = f.A->n + 1;

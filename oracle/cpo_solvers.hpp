@@ -695,18 +695,19 @@ template <class F, class T> static i64 dynamic_total_chunker(F& f, Weight& w, i6
 }
 
 // ConvexTotalChunker.jl:57-112.  fp(j, j') = cst[j] + f(j, j') supplied by the caller.
-template <class T, class FP> static void chunk_convex(std::vector<T>& cst, ivec& ptr, FP fp, i64 j0, i64 jp1, std::vector<std::pair<i64, i64>>& ftr) {
+template <class T, class FP, class CV, class PV> static void chunk_convex(CV& cst, PV& ptr, FP fp, i64 j0, i64 jp1, std::vector<std::pair<i64, i64>>& ftr) {
   ftr.clear();
   ftr.push_back({j0, jp1 + 1});
   for (i64 jp = j0 + 1; jp <= jp1; ++jp) {
     i64 j = ftr.back().first, h = ftr.back().second;
     T c = fp(j, jp);
     T c2 = fp(jp - 1, jp);
+    const T cur = cst[jp];
     if (c <= c2) {
-      if (c <= cst[jp]) { cst[jp] = c; ptr[jp] = j; }
+      if (c <= cur) { cst[jp] = c; ptr[jp] = j; }
       if (h == jp + 1) ftr.pop_back();
     } else {
-      if (c2 <= cst[jp]) { cst[jp] = c2; ptr[jp] = jp - 1; }
+      if (c2 <= cur) { cst[jp] = c2; ptr[jp] = jp - 1; }
       while (!ftr.empty() && (j = ftr.back().first, h = ftr.back().second, fp(jp - 1, h - 1) < fp(j, h - 1))) ftr.pop_back();
       if (ftr.empty()) {
         ftr.push_back({jp - 1, jp1 + 1});
@@ -775,11 +776,11 @@ template <class F, class T> static void quadrangle_total_splitter(F& f, i64 n, i
 }
 
 // ConvexTotalChunker.jl:211-265
-template <class T, class FP> static void chunk_convex_constrained(std::vector<T>& cst, ivec& ptr, FP fp, Weight& w, i64 J0, i64 JP1,
+template <class T, class FP, class CV, class PV> static void chunk_convex_constrained(CV& cst, PV& ptr, FP fp, Weight& w, i64 J0, i64 JP1,
                                                                   std::vector<std::pair<i64, i64>>& ftr) {
   const i64 cap = 2 * (JP1 + 1) + 3;
   ivec s_j(cap, 0), s_jp(cap, 0), s_ptr(cap, 0);
-  std::vector<T> s_cst(cap, T(0));
+  std::vector<T> s_cst(cap, T{});
   i64 jp1 = J0 + 1;
   while (jp1 < JP1 && !w.over(J0, jp1 + 1)) jp1 += 1;
   i64 j0 = J0;
@@ -812,6 +813,61 @@ template <class T, class FP> static void chunk_convex_constrained(std::vector<T>
     j0 = jp1;
     jp1 = s_jp[I - 2];
   }
+}
+
+// Costs.jl:79-103: Extended{T} -- a cost or infinity; `+` ORs the flags, infinities compare equal.
+template <class T> struct Ext {
+  bool inf = false;
+  T x = T(0);
+};
+template <class T> static inline Ext<T> operator+(const Ext<T>& a, const Ext<T>& b) { return Ext<T>{a.inf || b.inf, (T)(a.x + b.x)}; }
+template <class T> static inline bool operator<(const Ext<T>& a, const Ext<T>& b) { return (!a.inf && b.inf) || (!a.inf && !b.inf && a.x < b.x); }
+template <class T> static inline bool operator==(const Ext<T>& a, const Ext<T>& b) { return (a.inf && b.inf) || (!a.inf && !b.inf && a.x == b.x); }
+template <class T> static inline bool operator<=(const Ext<T>& a, const Ext<T>& b) { return (a < b) || (a == b); }
+template <class T> static inline bool operator>(const Ext<T>& a, const Ext<T>& b) { return b < a; }
+template <> inline Ext<i64> tmax<Ext<i64>>() { return Ext<i64>{true, 0}; }           // typemax(Extended{T}) = infinity (Costs.jl:99)
+template <> inline Ext<double> tmax<Ext<double>>() { return Ext<double>{true, 0.0}; }
+
+// one column of a WindowConstrainedMatrix (DynamicSplitter.jl:101-142): reads outside [lo, hi] give z, writes are dropped
+template <class V> struct WindowColumn {
+  std::vector<V> v;
+  i64 lo = 1, hi = 0;
+  V z{};
+  struct Ref {
+    WindowColumn& a;
+    i64 i;
+    operator V() const { return (a.lo <= i && i <= a.hi) ? a.v[i] : a.z; }
+    Ref& operator=(const V& x) { if (a.lo <= i && i <= a.hi) a.v[i] = x; return *this; }
+  };
+  Ref operator[](i64 i) { return Ref{*this, i}; }
+  V get(i64 i) const { return (lo <= i && i <= hi) ? v[i] : z; }
+};
+
+// ConvexTotalChunker.jl:167-209: partition_stripe(A, K, ConvexTotalSplitter(ConstrainedCost(f, w, w_max))) -- K layers of
+// chunk_convex_constrained! over window-constrained columns of Extended costs
+template <class F, class T> static void convex_total_splitter_constrained(F& f, Weight& w, i64 n, i64 K, i64* spl) {
+  using E = Ext<T>;
+  ivec lo, hi;
+  column_constraints(n, K, w, lo, hi);
+  if (hi[K] < n + 1) {  // :184-189 infeasible -> degenerate partition
+    for (i64 k = 1; k <= K; ++k) spl[k] = 1;
+    spl[K + 1] = n + 1;
+    return;
+  }
+  std::vector<WindowColumn<E>> cst(K + 1);
+  std::vector<WindowColumn<i64>> ptr(K + 1);
+  for (i64 k = 1; k <= K; ++k) {
+    cst[k].v.assign(n + 2, E{true, T(0)}); cst[k].lo = lo[k]; cst[k].hi = hi[k]; cst[k].z = E{true, T(0)};
+    ptr[k].v.assign(n + 2, 0); ptr[k].lo = lo[k]; ptr[k].hi = hi[k]; ptr[k].z = 0;
+  }
+  for (i64 jp = lo[1]; jp <= hi[1]; ++jp) { cst[1][jp] = E{false, f(1, jp, 1)}; ptr[1][jp] = 1; }
+  std::vector<std::pair<i64, i64>> stack;
+  for (i64 k = 2; k <= K; ++k) {
+    auto fp = [&](i64 j, i64 jp) -> E { return cst[k - 1].get(j) + E{false, f(j, jp, k)}; };
+    for (i64 jp = lo[k]; jp <= hi[k]; ++jp) { cst[k][jp] = fp(jp, jp); ptr[k][jp] = jp; }
+    chunk_convex_constrained<E>(cst[k], ptr[k], fp, w, lo[k - 1], hi[k], stack);
+  }
+  unravel_splits(K, n, [&](i64 k, i64 jp) { return ptr[k].get(jp); }, spl);
 }
 
 // OverlapChunker.jl:6-75 (note :29 -- `c` is never updated at a split; kept)

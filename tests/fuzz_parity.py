@@ -132,7 +132,7 @@ def rand_splitter(rng, f, decreasing, constrained_ok, large=False):
                            cp.DynamicBottleneckSplitter(f)])
     return rng.choice([cp.DynamicBottleneckSplitter(spec), cp.DynamicTotalSplitter(spec), cp.DynamicBottleneckChunker(spec), cp.DynamicTotalChunker(spec),
                        cp.BisectCostBottleneckSplitter(f, eps), cp.LazyBisectCostBottleneckSplitter(f, eps), cp.BisectIndexBottleneckSplitter(f),
-                       cp.ConvexTotalSplitter(f), cp.EquiSplitter()])
+                       cp.ConvexTotalSplitter(spec), cp.EquiSplitter()])
 
 
 def rand_packer(rng, A):

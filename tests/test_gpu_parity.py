@@ -449,6 +449,27 @@ def test_constrained_dynamic_splitters(ref, fixtures):
                         assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, mk.__name__, g.spl, r.spl)
 
 
+def test_constrained_convex_total_splitter(ref, fixtures):
+    """partition_stripe(A, K, ConvexTotalSplitter(ConstrainedCost(f, w, w_max))) (ConvexTotalChunker.jl:167-265; the
+    reference's own cases test_Partitioners.jl:176-196 and bin/test_table_constrained_splits.jl:26-40): identical split
+    vectors for vertex- and pin-weighted windows, incl. the degenerate result for infeasible constraints."""
+    rng = np.random.default_rng(311)
+    mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 1, 0.5), sprand(rng, 6, 10, 0.3), sprand(rng, 40, 200, 0.1),
+            synth.laplacian5(20)]
+    for A in mats:
+        fs = [cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineConnectivityModel(0.0, 0.0, 0.0, 1.0), cp.AffineWorkModel(0, 0, 0)]
+        if A.m == A.n:
+            fs.append(cp.AffineMonotonizedSymmetricConnectivityModel(0, 3, 1, 3, 5))
+        for f in fs:
+            for w, w_max in [(cp.AffineWorkModel(0, 1, 0), 2), (cp.AffineWorkModel(0, 1, 0), 4), (cp.AffineWorkModel(0, 1, 0), 8), (cp.VertexCount(), 8),
+                             (cp.AffineWorkModel(1, 2, 0), 9), (cp.AffineWorkModel(5, 1, 0), 3), (cp.AffineWorkModel(0, 1, 1), 12), (cp.AffineWorkModel(0, 0, 1), 9),
+                             (cp.AffineWorkModel(2, 1, 2), 40), (cp.VertexCount(), int(np.ceil(A.n / 4 * 1.5)))]:
+                for K in [1, 2, 3, 4, 8, 16, 60]:
+                    mtd = cp.ConvexTotalSplitter(cp.ConstrainedCost(f, w, w_max))
+                    g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                    assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, g.spl, r.spl)
+
+
 def test_dynamic_chunker_kform(ref, fixtures):
     """partition_stripe(A, K, DynamicBottleneckChunker(f) / DynamicTotalChunker(f)) (DynamicSplitter.jl:52-87,249-314)."""
     rng = np.random.default_rng(301)

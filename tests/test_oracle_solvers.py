@@ -530,6 +530,28 @@ def test_objective_of_noncontiguous_partitions(ref):
                 assert ref.total_value(A, P, mdl, Pi if needs_pi else None) == sum(costs)
 
 
+def test_constrained_convex_total_splitter_is_optimal(ref):
+    """ConvexTotalSplitter{<:ConstrainedCost} (ConvexTotalChunker.jl:167-265) restated with Extended costs and window-
+    constrained columns: the reference's own check (test_Partitioners.jl:176-196) -- the total cost equals the constrained
+    DynamicTotalSplitter's, and both are feasible or both degenerate."""
+    rng = np.random.default_rng(25)
+    for trial in range(300):
+        m, n = int(rng.integers(1, 12)), int(rng.integers(1, 16))
+        A = sprand(rng, m, n, float(rng.choice([0.1, 0.3, 0.6])))
+        K = int(rng.integers(1, 7))
+        f = [cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineWorkModel(0, 0, 0), cp.AffineConnectivityModel(0.5, 0.25, 1.5, 3.0)][trial % 4]
+        w, w_max = [(cp.AffineWorkModel(0, 1, 0), 2), (cp.AffineWorkModel(0, 1, 0), 4), (cp.VertexCount(), 8), (cp.AffineWorkModel(0, 1, 1), 12), (cp.AffineWorkModel(2, 1, 2), 30)][trial % 5]
+        spec = cp.ConstrainedCost(f, w, w_max)
+        r = ref.partition_stripe(A, K, cp.ConvexTotalSplitter(spec))
+        d = ref.partition_stripe(A, K, cp.DynamicTotalSplitter(spec))
+        check_split(r.spl, n, K)
+        assert ref.total_value(A, r, f) == ref.total_value(A, d, f), (A, K, r.spl, d.spl)
+        pos = A.colptr
+        wgt = lambda P: [w.coef[0] + (P.spl[k + 1] - P.spl[k]) * w.coef[1] + (pos[P.spl[k + 1] - 1] - pos[P.spl[k] - 1]) * w.coef[2] if not isinstance(w, cp.VertexCount)
+                         else P.spl[k + 1] - P.spl[k] for k in range(K)]
+        assert (max(wgt(r)) <= w_max) == (max(wgt(d)) <= w_max)
+
+
 def leftmost_chunk_dp(C, n, w_max):
     cst = np.full(n + 2, np.inf)
     cst[1] = 0
