@@ -352,6 +352,10 @@ template <class T> static void dynamic_constrained_T(Oracle& f, bool total, cons
 // pass against the empty-part initialisation.  The values are the constrained optimum; this rule reproduces the pointers:
 // 2500/2500 random cases (vertex- and pin-weighted windows, Int64 and Float64 costs) against the restated algorithm
 // (scratch/convex_k_rule2.py), and tests/test_gpu_parity.py::test_constrained_convex_total_splitter.
+// Every split point of the window is evaluated (O(n W) queries).  A per-block divide & conquer over "monotone" minimisers was
+// tried (3-7 ms instead of 80-118 ms at n = 2^14, W = 1.5 n / K) and is WRONG: these costs obey the INVERSE quadrangle
+// inequality -- the reason the reference uses a stack -- and inside a constrained block the minimisers are not monotone
+// (3 of ~230 random cases differed, one with a worse total).  Dropped; see profiles/r01_next.md.
 template <class T> struct DpInf;
 template <> struct DpInf<i64> { static __device__ __forceinline__ i64 get() { return (i64)1 << 61; } };
 template <> struct DpInf<double> { static __device__ __forceinline__ double get() { return 1e300; } };

@@ -211,6 +211,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-cases", type=int, default=10**9)
+    ap.add_argument("--focus", default="", help="'total': only the unconstrained total-cost splitters on 65..600 columns -- the layers the device "
+                                                  "solves by monotone divide & conquer (an empirical property of these costs, DESIGN.md 4)")
     ap.add_argument("--large", type=float, default=0.0, help="fraction of mid-size inputs (10^4..10^5 columns, up to ~10^6 nonzeros)")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
@@ -222,6 +224,43 @@ def main():
         stats["cases"] += 1
         large = rng.random() < args.large
         A = rand_large_matrix(rng) if large else rand_matrix(rng)
+        if args.focus == "total":
+            n = int(rng.integers(65, 600))
+            fam = int(rng.integers(0, 4))
+            if fam == 0:
+                A = sprand(rng, int(rng.integers(1, 400)), n, float(rng.choice([0.005, 0.02, 0.1, 0.3])))
+            elif fam == 1:
+                A = sprand(rng, n, n, float(rng.choice([0.005, 0.02, 0.1])))
+            elif fam == 2:
+                hb = int(rng.integers(0, 6))
+                I, J = np.nonzero(np.abs(np.subtract.outer(np.arange(n), np.arange(n))) <= hb)
+                keep = rng.random(len(I)) < float(rng.choice([0.3, 0.8, 1.0]))
+                A = cp.SparseMatrixCSC.from_coo(n, n, I[keep] + 1, J[keep] + 1)
+            else:  # a few dense rows / columns over a sparse pattern
+                mask = rng.random((n, n)) < 0.01
+                for _ in range(int(rng.integers(1, 4))):
+                    mask[int(rng.integers(0, n)), :] |= rng.random(n) < 0.7
+                    mask[:, int(rng.integers(0, n))] |= rng.random(n) < 0.5
+                I, J = np.nonzero(mask)
+                A = cp.SparseMatrixCSC.from_coo(n, n, I + 1, J + 1)
+            try:
+                fs = [cp.AffineConnectivityModel(*coefs(rng, 4)), cp.AffineWorkModel(*coefs(rng, 3))]
+                if A.m == A.n:
+                    c = coefs(rng, 4)
+                    fs.append(cp.AffineMonotonizedSymmetricConnectivityModel(*c, type(c[0])(rng.integers(0, 6))))
+                f = fs[int(rng.integers(0, len(fs)))]
+                K = int(rng.integers(2, 12))
+                mtd = cp.DynamicTotalSplitter(f) if rng.random() < 0.6 else cp.ConvexTotalSplitter(f)
+                r = ref.partition_stripe(A, K, mtd)
+                g = cp.partition_stripe(A, K, mtd)
+                stats["compared"] += 1
+                if not np.array_equal(g.spl, r.spl):
+                    stats["mismatches"] += 1
+                    print("MISMATCH", type(mtd).__name__, f.__dict__, "K =", K, "A =", describe(A), "\n  device:", g.spl.tolist(), "\n  oracle:", r.spl.tolist(),
+                          "totals", cp.total_value(A, g, f), ref.total_value(A, r, f), flush=True)
+            except cp.CpbError as e:
+                stats["unsupported"] += 1
+            continue
         packing = rng.random() < 0.25
         Pi = None
         if rng.random() < 0.12:

@@ -452,7 +452,7 @@ def test_constrained_dynamic_splitters(ref, fixtures):
 def test_constrained_convex_total_splitter(ref, fixtures):
     """partition_stripe(A, K, ConvexTotalSplitter(ConstrainedCost(f, w, w_max))) (ConvexTotalChunker.jl:167-265; the
     reference's own cases test_Partitioners.jl:176-196 and bin/test_table_constrained_splits.jl:26-40): identical split
-    vectors for vertex- and pin-weighted windows, incl. the degenerate result for infeasible constraints."""
+    vectors for vertex- and pin-weighted windows, incl. the degenerate result for infeasible constraints and wide windows."""
     rng = np.random.default_rng(311)
     mats = [fixtures["LPnetlib/lpi_itest6"], fixtures["Pajek/GD99_c"], sprand(rng, 6, 1, 0.5), sprand(rng, 6, 10, 0.3), sprand(rng, 40, 200, 0.1),
             synth.laplacian5(20)]
@@ -468,6 +468,10 @@ def test_constrained_convex_total_splitter(ref, fixtures):
                     mtd = cp.ConvexTotalSplitter(cp.ConstrainedCost(f, w, w_max))
                     g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
                     assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, g.spl, r.spl)
+    B = synth.banded(3000, 6, 3)  # wide windows (bin/test_table_constrained_splits.jl: w_max = 1.5 n / K)
+    for K in (3, 8):
+        mtd = cp.ConvexTotalSplitter(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.VertexCount(), int(np.ceil(B.n / K * 1.5))))
+        assert np.array_equal(cp.partition_stripe(B, K, mtd).spl, ref.partition_stripe(B, K, mtd).spl)
 
 
 def test_dynamic_chunker_kform(ref, fixtures):
