@@ -364,9 +364,12 @@ template <class T>
 __global__ void __launch_bounds__(256) k_dp_convex_constrained(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
                                                                u32* __restrict__ ptr, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, DevWeight wt, u32 k,
                                                                const u32* __restrict__ blk, u32 nblk) {
+  // one warp per j': the lanes share the window (wide windows -- w_max = 1.5 n / K in the reference's table -- would leave a
+  // thread-per-j' layer with a few thousand dependent query chains per thread and most of the machine idle)
   const T INF = DpInf<T>::get();
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x + lo_k; idx <= hi_k; idx += stride) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t idx = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + lo_k; idx <= hi_k; idx += warps) {
     const u32 jp = (u32)idx;
     // the layer's initialisation: the empty part k (ptr = j')
     T best = (jp >= lo_p && jp <= hi_p && prev[jp] < INF) ? prev[jp] + dev_cost<T>(o, jp, jp, k) : INF;
@@ -379,7 +382,8 @@ __global__ void __launch_bounds__(256) k_dp_convex_constrained(const __grid_cons
       }
       const u32 j0 = __ldg(blk + a);
       if (a > 0) {  // staircase pass: rightmost minimiser among the previous block's columns that still fit; replaces the initialisation
-        u32 lo_j = __ldg(blk + a - 1) + 1, hi_j = min(j0, hi_p);
+        u32 lo_j = __ldg(blk + a - 1) + 1;
+        const u32 hi_j = min(j0, hi_p);
         {
           u32 x = lo_j, y = j0;  // smallest j in [lo_j, j0] with w(j, j') <= w_max (j0 itself fits: j' lies in its block)
           while (x < y) {
@@ -388,28 +392,44 @@ __global__ void __launch_bounds__(256) k_dp_convex_constrained(const __grid_cons
           }
           lo_j = max(x, lo_p);
         }
-        best = INF;
-        arg = j0;
-        for (u32 j = lo_j; j <= hi_j; ++j) {
+        T vb = INF;
+        u32 ab = 0;
+        for (u64 j64 = (u64)lo_j + lane; j64 <= hi_j; j64 += 32) {
+          const u32 j = (u32)j64;
           const T pv = prev[j];
           if (pv >= INF) continue;
           const T v = pv + dev_cost<T>(o, j, jp, k);
-          if (best >= INF || v <= best) { best = v; arg = j; }
+          if (ab == 0 || v <= vb) { vb = v; ab = j; }
         }
+        for (int d = 16; d > 0; d >>= 1) {  // smallest value, then the largest column
+          const T ov = __shfl_xor_sync(0xffffffffu, vb, d);
+          const u32 oa = __shfl_xor_sync(0xffffffffu, ab, d);
+          if (oa != 0 && (ab == 0 || ov < vb || (ov == vb && oa > ab))) { vb = ov; ab = oa; }
+        }
+        best = ab ? vb : INF;
+        arg = ab ? ab : j0;
       }
       // in-block pass: leftmost minimiser of [j0, j'-1]; wins ties against what the column holds
       T vin = INF;
       u32 jin = 0;
-      for (u32 j = max(j0, lo_p); j <= min(jp - 1, hi_p); ++j) {
+      for (u64 j64 = (u64)max(j0, lo_p) + lane; j64 <= min(jp - 1, hi_p); j64 += 32) {
+        const u32 j = (u32)j64;
         const T pv = prev[j];
         if (pv >= INF) continue;
         const T v = pv + dev_cost<T>(o, j, jp, k);
-        if (vin >= INF || v < vin) { vin = v; jin = j; }
+        if (jin == 0 || v < vin) { vin = v; jin = j; }
       }
-      if (vin < INF && (best >= INF || vin <= best)) { best = vin; arg = jin; }
+      for (int d = 16; d > 0; d >>= 1) {  // smallest value, then the smallest column
+        const T ov = __shfl_xor_sync(0xffffffffu, vin, d);
+        const u32 oa = __shfl_xor_sync(0xffffffffu, jin, d);
+        if (oa != 0 && (jin == 0 || ov < vin || (ov == vin && oa < jin))) { vin = ov; jin = oa; }
+      }
+      if (jin != 0 && (best >= INF || vin <= best)) { best = vin; arg = jin; }
     }
-    cur[jp] = best;
-    ptr[jp] = arg;
+    if (lane == 0) {
+      cur[jp] = best;
+      ptr[jp] = arg;
+    }
   }
 }
 
@@ -491,7 +511,8 @@ template <class T> static void convex_constrained_T(Oracle& f, const cpb_constra
       }
       CPB_CUDA(cudaMemcpyAsync(dblk.get(), blk.data(), blk.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx().stream));
       CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // blk is reused by the next layer
-      CPB_LAUNCH(k_dp_convex_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, (u32)lo[k], (u32)hi[k], (u32)lo[k - 1],
+      const unsigned wgrid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt * 32 + 255) / 256, (size_t)ctx().sm_count * 16));
+      CPB_LAUNCH(k_dp_convex_constrained<T>, wgrid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, (u32)lo[k], (u32)hi[k], (u32)lo[k - 1],
                  (u32)hi[k - 1], DevWeight{wa, wbv, wbp, w_max}, (u32)k, dblk.get(), (u32)(blk.size() - 1));
     }
     std::swap(prev, cur);
