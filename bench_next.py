@@ -98,6 +98,9 @@ def main():
             mdl = cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.VertexCount(), int(np.ceil(B.n / k * 1.5)))
             split_case("convex_constrained: ConvexTotalSplitter(ConstrainedCost(nets, VertexCount, ceil(1.5 n / K))), banded n = 2^14",
                        cp.ConvexTotalSplitter(mdl), None, matrix=B, dmatrix=dB, k=k)
+            if k == 8:  # the "dynamic" row of the same table
+                split_case("dynamic_constrained: DynamicTotalSplitter(ConstrainedCost(nets, VertexCount, ceil(1.5 n / K))), banded n = 2^14",
+                           cp.DynamicTotalSplitter(mdl), None, matrix=B, dmatrix=dB, k=k)
         dB.close()
     if "map_objective" in cases:
         rng = np.random.default_rng(1)

@@ -216,6 +216,46 @@ __global__ void __launch_bounds__(256) k_dp_constrained(const __grid_constant__ 
   }
 }
 
+// the same layer with one warp per j' for wide windows (a thread-per-j' scan of thousands of split points is one dependent
+// chain of oracle queries per thread and leaves most of the machine idle): lanes share the window, butterfly reduction to the
+// smallest value and, among ties, the largest column (the `<=` rule)
+template <class T>
+__global__ void __launch_bounds__(256) k_dp_constrained_warp(const __grid_constant__ DevOracle o, const T* __restrict__ prev, T* __restrict__ cur,
+                                                             u32* __restrict__ ptr, int total, u32 lo_k, u32 hi_k, u32 lo_p, u32 hi_p, u32 W, DevWeight wt, u32 k) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t t = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + lo_k; t <= hi_k; t += warps) {
+    const u32 jp = (u32)t;
+    u32 j0 = max(lo_p, jp > W ? jp - W : 1u);
+    const u32 j1 = min(jp, hi_p);
+    if (wt.bp != 0) {
+      u32 a = j0, b = jp;
+      while (a < b) {
+        const u32 mid = a + ((b - a) >> 1);
+        if (weight_ok(o, wt, mid, jp)) b = mid; else a = mid + 1;
+      }
+      j0 = a;
+    }
+    T best = 0;
+    u32 arg = 0;
+    for (u64 j64 = (u64)j0 + lane; j64 <= j1; j64 += 32) {
+      const u32 j = (u32)j64;
+      const T c = dev_cost<T>(o, j, jp, k);
+      const T v = total ? prev[j] + c : max(prev[j], c);
+      if (arg == 0 || v <= best) { best = v; arg = j; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, best, d);
+      const u32 oa = __shfl_xor_sync(0xffffffffu, arg, d);
+      if (oa != 0 && (arg == 0 || ov < best || (ov == best && oa > arg))) { best = ov; arg = oa; }
+    }
+    if (lane == 0) {
+      cur[jp] = best;
+      ptr[jp] = arg;
+    }
+  }
+}
+
 __global__ void k_dp_unravel(const u32* __restrict__ ptr, u32 n2, int K, u32 n1, i64* __restrict__ spl) {
   // DynamicSplitter.jl:89-99
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -333,9 +373,16 @@ template <class T> static void dynamic_constrained_T(Oracle& f, bool total, cons
   for (i64 k = 1; k <= K; ++k) {
     const size_t cnt = (size_t)(hi[k] - lo[k] + 1);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt + 255) / 256, (size_t)ctx().sm_count * 8));
-    CPB_LAUNCH(k_dp_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, total ? 1 : 0, (u32)lo[k], (u32)hi[k],
-               (u32)(k > 1 ? lo[k - 1] : 1), (u32)(k > 1 ? hi[k - 1] : 1), (u32)std::min<i64>(std::max<i64>(W, 0), n + 1), k == 1 ? 1 : 0,
-               DevWeight{wa, wbv, wbp, w_max}, (u32)k);
+    const bool wide = k > 1 && std::min<i64>(W, hi[k - 1] - lo[k - 1] + 1) > 64 && std::getenv("CPB_DP_THREAD_WINDOWS") == nullptr;
+    if (wide) {
+      const unsigned wgrid = (unsigned)std::max<size_t>(1, std::min<size_t>((cnt * 32 + 255) / 256, (size_t)ctx().sm_count * 16));
+      CPB_LAUNCH(k_dp_constrained_warp<T>, wgrid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, total ? 1 : 0, (u32)lo[k], (u32)hi[k],
+                 (u32)lo[k - 1], (u32)hi[k - 1], (u32)std::min<i64>(std::max<i64>(W, 0), n + 1), DevWeight{wa, wbv, wbp, w_max}, (u32)k);
+    } else {
+      CPB_LAUNCH(k_dp_constrained<T>, grid, 256, 0, f.dev, prev, cur, ptr.get() + (size_t)(k - 1) * n2, total ? 1 : 0, (u32)lo[k], (u32)hi[k],
+                 (u32)(k > 1 ? lo[k - 1] : 1), (u32)(k > 1 ? hi[k - 1] : 1), (u32)std::min<i64>(std::max<i64>(W, 0), n + 1), k == 1 ? 1 : 0,
+                 DevWeight{wa, wbv, wbp, w_max}, (u32)k);
+    }
     std::swap(prev, cur);
   }
   CPB_LAUNCH(k_dp_unravel, 1, 32, 0, ptr.get(), n2, (int)K, n1, spl.get());

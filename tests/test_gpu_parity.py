@@ -468,10 +468,14 @@ def test_constrained_convex_total_splitter(ref, fixtures):
                     mtd = cp.ConvexTotalSplitter(cp.ConstrainedCost(f, w, w_max))
                     g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
                     assert np.array_equal(g.spl, r.spl), (A, f, w_max, K, g.spl, r.spl)
-    B = synth.banded(3000, 6, 3)  # wide windows (bin/test_table_constrained_splits.jl: w_max = 1.5 n / K)
+    B = synth.banded(3000, 6, 3)  # wide windows (bin/test_table_constrained_splits.jl: w_max = 1.5 n / K): warp-per-column layers
     for K in (3, 8):
-        mtd = cp.ConvexTotalSplitter(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.VertexCount(), int(np.ceil(B.n / K * 1.5))))
-        assert np.array_equal(cp.partition_stripe(B, K, mtd).spl, ref.partition_stripe(B, K, mtd).spl)
+        spec = cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.VertexCount(), int(np.ceil(B.n / K * 1.5)))
+        for mk in (cp.ConvexTotalSplitter, cp.DynamicTotalSplitter, cp.DynamicBottleneckSplitter):
+            assert np.array_equal(cp.partition_stripe(B, K, mk(spec)).spl, ref.partition_stripe(B, K, mk(spec)).spl), (K, mk.__name__)
+        spec = cp.ConstrainedCost(cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineWorkModel(0, 1, 1), int(np.ceil((B.n + B.nnz) / K * 1.5)))
+        for mk in (cp.ConvexTotalSplitter, cp.DynamicTotalSplitter):
+            assert np.array_equal(cp.partition_stripe(B, K, mk(spec)).spl, ref.partition_stripe(B, K, mk(spec)).spl), (K, mk.__name__, "pin-weighted")
 
 
 def test_dynamic_chunker_kform(ref, fixtures):
