@@ -398,7 +398,7 @@ template <class T> static void dynamic_constrained_T(Oracle& f, bool total, cons
 // in-block pass offers the LEFTMOST minimiser of [b_t, j'-1] and wins ties (`<=`, :66,74).  Block 0 only has the in-block
 // pass against the empty-part initialisation.  The values are the constrained optimum; this rule reproduces the pointers:
 // 2500/2500 random cases (vertex- and pin-weighted windows, Int64 and Float64 costs) against the restated algorithm
-// (scratch/convex_k_rule2.py), and tests/test_gpu_parity.py::test_constrained_convex_total_splitter.
+// (tools/convex_k_rule.py), and tests/test_gpu_parity.py::test_constrained_convex_total_splitter.
 // Every split point of the window is evaluated (O(n W) queries).  A per-block divide & conquer over "monotone" minimisers was
 // tried (3-7 ms instead of 80-118 ms at n = 2^14, W = 1.5 n / K) and is WRONG: these costs obey the INVERSE quadrangle
 // inequality -- the reason the reference uses a stack -- and inside a constrained block the minimisers are not monotone
