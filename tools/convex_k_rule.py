@@ -2,7 +2,9 @@
 restated reference algorithm (oracle: chunk_convex_constrained! per layer, ConvexTotalChunker.jl:167-265) on random small cases.
 CPU only:  python tools/convex_k_rule.py   ->  "<cases> [<cases matching>, 0]"."""
 import sys
-sys.path[:0]=['/root/repo','/root/repo/oracle','/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')]
 import numpy as np
 import chainb200 as cp, pyoracle as ref
 from helpers import sprand
