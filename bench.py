@@ -35,7 +35,9 @@ EPS = 0.01
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` at this workload
 # (profiles/r01_ncu_summary.md: k_probe_stream 45.0 MB read + 0.2 MB write; k_lt_fill 79.6 + 37.9 MB; k_lt_link
 # 76.3 + 36.2 MB; k_lt_count 44.0 MB read; k_rs_scatter 42-82 MB read + 52-56 MB write; k_wm_level 40.05 + 1-3 MB), bytes
-TRAFFIC = {"k_probe_stream": 45.2e6, "k_lt_fill": 117.5e6, "k_lt_link": 112.5e6, "k_lt_count": 44.0e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6}
+# dram read + write per launch from the ncu --set full captures (profiles/r01_ncu_summary.md sections 2 and 6)
+TRAFFIC = {"k_probe_stream": 46.8e6, "k_lt_fill": 118.7e6, "k_lt_link": 113.9e6, "k_lt_count": 44.0e6, "k_rs_scatter": 122e6, "k_wm_level": 42e6,
+           "k_expand_columns": 4.1e6}
 METRIC = "partition_stripe throughput (BisectCostBottleneckSplitter, Erdos-Renyi 1Mx1M, K=64)"
 UNIT = "partitions/s"
 
@@ -298,7 +300,9 @@ def main():
                  "k_lt_link": "build_links: every slot scans its row segment for the largest column below its own and writes the link (scattered 4-byte stores)",
                  "k_lt_count": "build_links: row histogram (one atomic per nonzero)",
                  "k_rs_scatter": "stable radix scatter of (row, position) pairs inside build_links (rows heavier than 128 nonzeros)",
-                 "k_wm_level": "one bit level of the wavelet-matrix dominance index"}
+                 "k_wm_level": "one bit level of the wavelet-matrix dominance index",
+                 "k_expand_columns": "column of every nonzero from the offsets (marks + running maximum per tile); two launches per scope (tile bounds, expansion); "
+                                     "the 40 MB it writes are consumed from L2 by the next kernels (dram traffic under ncu: 4 MB read, ~0 written)"}
         roofline = roof(top, NOTES.get(top, "")) if top else None
         roofline_all = [roof(nm, NOTES.get(nm, "")) for nm in sorted(kernels, key=lambda nm: -kernels[nm]["ms"])]
         phases = {nm: round(v["ms"] / args.steps, 4) for nm, v in prof.items()}
