@@ -843,7 +843,16 @@ __global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStr
   const u32 j = (u32)spl[k];
   const u32 e0 = __ldg(s.P + j), e1 = __ldg(s.P + (u32)spl[k + 1]);
   u32 c = 0;
-  for (u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) c += __ldg(s.prev + e) <= e0;
+  const u32 stride = gridDim.x * blockDim.x;
+  u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+  for (; (u64)e + 7ull * stride < e1; e += 8 * stride) {  // eight independent loads in flight per thread (the scalar loop ran at 1.1 TB/s, 8 % SM busy)
+    u32 v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = __ldg(s.prev + e + (u32)t * stride);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) c += v[t] <= e0;
+  }
+  for (; e < e1; e += stride) c += __ldg(s.prev + e) <= e0;
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
 }
