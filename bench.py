@@ -301,7 +301,7 @@ def main():
                  "k_lt_count": "build_links: row histogram (one atomic per nonzero)",
                  "k_rs_scatter": "stable radix scatter of (row, position) pairs inside build_links (rows heavier than 128 nonzeros)",
                  "k_wm_level": "one bit level of the wavelet-matrix dominance index",
-                 "k_expand_columns": "column of every nonzero from the offsets (marks + running maximum per tile); two launches per scope (tile bounds, expansion); "
+                 "k_expand_columns": "column of every nonzero from the offsets (marks + running maximum per tile); "
                                      "the 40 MB it writes are consumed from L2 by the next kernels (dram traffic under ncu: 4 MB read, ~0 written)"}
         roofline = roof(top, NOTES.get(top, "")) if top else None
         roofline_all = [roof(nm, NOTES.get(nm, "")) for nm in sorted(kernels, key=lambda nm: -kernels[nm]["ms"])]

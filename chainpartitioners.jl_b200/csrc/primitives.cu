@@ -364,39 +364,37 @@ void iota_u32(u32* dst, size_t n) {
   CPB_LAUNCH(k_iota, grid, 256, 0, dst, n);
 }
 
-// colidx[q] = largest j with pos[j] <= q.  A CTA owns 2048 consecutive nonzeros.  k_expand_bounds finds the column of
-// every tile's first nonzero (one global binary search per tile, all tiles in parallel); k_expand_columns marks the first
-// nonzero of every column that starts inside the tile with the column's number (a run of empty columns shares one offset:
-// the largest number wins) and a running maximum over the tile turns the marks into the column of every nonzero --
-// ~20 instructions per nonzero instead of an 11-step binary search each.
+// colidx[q] = largest j with pos[j] <= q.  A CTA owns 2048 consecutive nonzeros: a cooperative 256-ary search (three rounds
+// for a million columns) finds the column of its first nonzero, every column that starts inside the tile marks its first
+// nonzero with its number (a run of empty columns shares one offset: the largest number wins), and a running maximum over
+// the tile turns the marks into the column of every nonzero -- ~20 instructions per nonzero instead of a binary search each.
 static constexpr int EX_TILE = 2048;
 static constexpr int EX_PER = EX_TILE / 256;  // consecutive nonzeros per thread
-__global__ void k_expand_bounds(const u32* __restrict__ pos, u32 ncol, size_t N, u32 tiles, u32* __restrict__ bounds) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t > tiles) return;
-  if (t == tiles) { bounds[t] = ncol - 1; return; }
-  const u32 q = (u32)((size_t)t * EX_TILE);
-  u32 lo = 0, hi = ncol;  // largest j in [0, ncol) with pos[j] <= q   (pos[ncol] == N > q)
-  while (hi - lo > 1) {
-    const u32 mid = lo + ((hi - lo) >> 1);
-    if (__ldg(pos + mid) <= q) lo = mid; else hi = mid;
-  }
-  bounds[t] = lo;
-}
-__global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ pos, const u32* __restrict__ bounds, u32* __restrict__ colidx, size_t N) {
+__global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ pos, u32 ncol, u32* __restrict__ colidx, size_t N) {
   __shared__ __align__(16) u32 s_head[EX_TILE];
   __shared__ u32 s_wmax[8];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const size_t q0 = (size_t)blockIdx.x * EX_TILE;
-  const u32 c_lo = bounds[blockIdx.x], c_hi = bounds[blockIdx.x + 1];  // columns of the first nonzero of this / the next tile
 #pragma unroll
   for (int k = 0; k < EX_PER; ++k) s_head[tid * EX_PER + k] = 0;
+  // c_lo = largest j in [0, ncol) with pos[j] <= q0   (pos[0] = 0 <= q0 < N = pos[ncol])
+  u32 lo = 0, hi = ncol;
+  while (hi - lo > 1) {
+    const u32 step = (hi - lo + 255) / 256;
+    const u64 idx = (u64)lo + (u64)(tid + 1) * step;
+    const bool ok = idx < hi && __ldg(pos + idx) <= q0;
+    const u32 cnt = (u32)__syncthreads_count(ok);  // pos is monotone: the probes that hold form a prefix
+    const u32 nlo = lo + cnt * step;
+    hi = min(hi, nlo + step);
+    lo = nlo;
+  }
+  const u32 c_lo = lo;
   __syncthreads();
-  // columns c_lo + 1 .. c_hi start at or after q0 (c_lo is the column of nonzero q0 itself) and no later than the next
-  // tile's first nonzero
-  for (u32 c = c_lo + 1 + tid; c <= c_hi; c += 256) {
+  // columns after c_lo start behind q0; those that start inside the tile leave their mark
+  for (u64 c = (u64)c_lo + 1 + tid; c < ncol; c += 256) {
     const size_t p = __ldg(pos + c);
-    if (p >= q0 && p < q0 + EX_TILE) atomicMax(&s_head[p - q0], c);
+    if (p >= q0 + EX_TILE) break;
+    atomicMax(&s_head[p - q0], (u32)c);
   }
   __syncthreads();
   u32 v[EX_PER];
@@ -434,9 +432,7 @@ __global__ void __launch_bounds__(256) k_expand_columns(const u32* __restrict__ 
 void expand_columns(const u32* pos, u32 ncol, u32* colidx, size_t N) {
   if (N == 0) return;
   const u32 tiles = (u32)((N + EX_TILE - 1) / EX_TILE);
-  DBuf<u32> bounds((size_t)tiles + 1);
-  CPB_LAUNCH(k_expand_bounds, (tiles + 1 + 255) / 256, 256, 0, pos, ncol, N, tiles, bounds.get());
-  CPB_LAUNCH(k_expand_columns, tiles, 256, 0, pos, bounds.get(), colidx, N);
+  CPB_LAUNCH(k_expand_columns, tiles, 256, 0, pos, ncol, colidx, N);
 }
 
 __global__ void k_segment_starts(const u32* __restrict__ keys, size_t n, u32* __restrict__ P, u32 domain) {
