@@ -254,11 +254,10 @@ extern "C" int cpo_partition_stripe(int method, const cpo_model* mdl, const cpo_
           });
           break;
         case CPO_SPLIT_CONVEX_TOTAL: case CPO_SPLIT_CONCAVE_TOTAL:
-          if (w.enabled && method == CPO_SPLIT_CONCAVE_TOTAL) throw std::invalid_argument("constrained ConcaveTotalSplitter (ConcaveTotalChunker.jl:143-181) not restated");
           with_oracle<T>(mdl, CPO_HINT_RANDOM, M, pi_spl, pi_K, [&](auto& f) {
             t1 = now_s();
             using F = std::remove_reference_t<decltype(f)>;
-            if (w.enabled) convex_total_splitter_constrained<F, T>(f, w, n, K, spl.data());
+            if (w.enabled) convex_total_splitter_constrained<F, T>(f, w, n, K, spl.data(), method == CPO_SPLIT_CONCAVE_TOTAL);
             else quadrangle_total_splitter<F, T>(f, n, K, method == CPO_SPLIT_CONCAVE_TOTAL, spl.data());
           });
           break;

@@ -727,19 +727,20 @@ template <class T, class FP, class CV, class PV> static void chunk_convex(CV& cs
 }
 
 // ConcaveTotalChunker.jl:57-114
-template <class T, class FP> static void chunk_concave(std::vector<T>& cst, ivec& ptr, FP fp, i64 j0, i64 jp1, std::deque<std::pair<i64, i64>>& ftr) {
+template <class T, class FP, class CV, class PV> static void chunk_concave(CV& cst, PV& ptr, FP fp, i64 j0, i64 jp1, std::deque<std::pair<i64, i64>>& ftr) {
   ftr.clear();
   ftr.push_back({j0, j0 + 1});
   for (i64 jp = j0 + 1; jp <= jp1; ++jp) {
     i64 j = ftr.front().first, h = ftr.front().second;
     T c = fp(j, jp);
     T c2 = fp(jp - 1, jp);
+    const T cur = cst[jp];
     if (c2 <= c) {
-      if (c2 <= cst[jp]) { cst[jp] = c2; ptr[jp] = jp - 1; }
+      if (c2 <= cur) { cst[jp] = c2; ptr[jp] = jp - 1; }
       ftr.clear();
       ftr.push_back({jp - 1, jp + 1});
     } else {
-      if (c <= cst[jp]) { cst[jp] = c; ptr[jp] = j; }
+      if (c <= cur) { cst[jp] = c; ptr[jp] = j; }
       while ((j = ftr.back().first, h = ftr.back().second, fp(jp - 1, h) <= fp(j, h))) ftr.pop_back();
       j = ftr.back().first;
       h = ftr.back().second;
@@ -843,9 +844,9 @@ template <class V> struct WindowColumn {
   V get(i64 i) const { return (lo <= i && i <= hi) ? v[i] : z; }
 };
 
-// ConvexTotalChunker.jl:167-209: partition_stripe(A, K, ConvexTotalSplitter(ConstrainedCost(f, w, w_max))) -- K layers of
+// ConvexTotalChunker.jl:167-209 / ConcaveTotalChunker.jl:143-181: partition_stripe(A, K, Convex/ConcaveTotalSplitter(ConstrainedCost(f, w, w_max))) -- K layers of
 // chunk_convex_constrained! over window-constrained columns of Extended costs
-template <class F, class T> static void convex_total_splitter_constrained(F& f, Weight& w, i64 n, i64 K, i64* spl) {
+template <class F, class T> static void convex_total_splitter_constrained(F& f, Weight& w, i64 n, i64 K, i64* spl, bool concave = false) {
   using E = Ext<T>;
   ivec lo, hi;
   column_constraints(n, K, w, lo, hi);
@@ -862,10 +863,14 @@ template <class F, class T> static void convex_total_splitter_constrained(F& f, 
   }
   for (i64 jp = lo[1]; jp <= hi[1]; ++jp) { cst[1][jp] = E{false, f(1, jp, 1)}; ptr[1][jp] = 1; }
   std::vector<std::pair<i64, i64>> stack;
+  std::deque<std::pair<i64, i64>> queue;
   for (i64 k = 2; k <= K; ++k) {
     auto fp = [&](i64 j, i64 jp) -> E { return cst[k - 1].get(j) + E{false, f(j, jp, k)}; };
     for (i64 jp = lo[k]; jp <= hi[k]; ++jp) { cst[k][jp] = fp(jp, jp); ptr[k][jp] = jp; }
-    chunk_convex_constrained<E>(cst[k], ptr[k], fp, w, lo[k - 1], hi[k], stack);
+    // ConcaveTotalChunker.jl:143-181: the concave K-form runs the plain queue routine over the window-constrained columns
+    // (the weight only shapes the windows); the convex one alternates in-window and staircase passes (:211-265)
+    if (concave) chunk_concave<E>(cst[k], ptr[k], fp, lo[k - 1], hi[k], queue);
+    else chunk_convex_constrained<E>(cst[k], ptr[k], fp, w, lo[k - 1], hi[k], stack);
   }
   unravel_splits(K, n, [&](i64 k, i64 jp) { return ptr[k].get(jp); }, spl);
 }

@@ -550,6 +550,11 @@ def test_constrained_convex_total_splitter_is_optimal(ref):
         wgt = lambda P: [w.coef[0] + (P.spl[k + 1] - P.spl[k]) * w.coef[1] + (pos[P.spl[k + 1] - 1] - pos[P.spl[k] - 1]) * w.coef[2] if not isinstance(w, cp.VertexCount)
                          else P.spl[k + 1] - P.spl[k] for k in range(K)]
         assert (max(wgt(r)) <= w_max) == (max(wgt(d)) <= w_max)
+        if trial % 4 == 2:  # the additive work model is also (weakly) concave: ConcaveTotalSplitter{<:ConstrainedCost} (ConcaveTotalChunker.jl:143-181)
+            c = ref.partition_stripe(A, K, cp.ConcaveTotalSplitter(spec))
+            check_split(c.spl, n, K)
+            assert (max(wgt(c)) <= w_max) == (max(wgt(d)) <= w_max)
+            assert ref.total_value(A, c, f) == ref.total_value(A, d, f)
 
 
 def leftmost_chunk_dp(C, n, w_max):
