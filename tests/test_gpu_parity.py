@@ -65,7 +65,7 @@ def test_color_arrays(ref, fixtures):
 
 
 def test_link_construction_paths(ref, monkeypatch):
-    """build_links has two forms -- per-row segments filled through atomic cursors (rows of <= 64 nonzeros) and the
+    """build_links has two forms -- per-row segments filled through atomic cursors (rows of <= 128 nonzeros) and the
     stable radix sort (heavier rows): net / dia-net counts and the streaming bisection must not depend on which ran."""
     rng = np.random.default_rng(102)
     light = synth.erdos_renyi(20000, 10)
