@@ -55,6 +55,18 @@ extern "C" int cpo_dominancecount(int hint, const cpo_csc* A, int b, int H, int 
   CPO_CATCH
 }
 
+extern "C" int cpo_dominancesum(const cpo_csc* A, const cpo_i64* val, int b, int H, int bp, cpo_i64 Q, const cpo_i64* qi, const cpo_i64* qj,
+                                cpo_i64* out) {
+  CPO_TRY
+  Mat M(A);
+  BarySum dom(M.m, M.n, M.N, &M.pos, M.idx, (const BarySum::W64*)val, b, H, bp);  // dominancesum copies colptr/rowval (:36-37)
+  for (i64 t = 0; t < Q; ++t) {
+    if (qi[t] < 1 || qi[t] > M.m + 1 || qj[t] < 1 || qj[t] > M.n + 1) throw std::runtime_error("dominancesum query out of range");
+    out[t] = (i64)dom.at(qi[t], qj[t]);
+  }
+  CPO_CATCH
+}
+
 extern "C" int cpo_prefix_query(cpo_i64 m, cpo_i64 n, cpo_i64 N, const cpo_i64* pos, const cpo_i64* idx, const cpo_i64* val, cpo_i64 Q,
                                 const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out) {
   CPO_TRY

@@ -143,6 +143,11 @@ int cpo_dominancecount(int hint, const cpo_csc* A, int b, int H, int bp,
  * {0 Same,1 Next,2 Prev,3 Jump} for i and j  (test_SparsePrefixMatrices.jl:74-92) */
 int cpo_dominancecount_walk(const cpo_csc* A, cpo_i64 T, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out);
 
+/* dominancesum(hint, A; b, H, b')[i, j] with the reference's own structure (DominanceSum, SparsePrefixMatrices.jl:1-254);
+ * val: nnz 64-bit words (wrap-around sums); b/H/bp <= 0 -> the reference's defaults */
+int cpo_dominancesum(const cpo_csc* A, const cpo_i64* val, int b, int H, int bp,
+                     cpo_i64 Q, const cpo_i64* qi, const cpo_i64* qj, cpo_i64* out);
+
 /* dominancesum / rookcount / rooksum (SparsePrefixMatrices.jl:1-392, 825-1273) by their DEFINITION
  * (test_SparsePrefixMatrices.jl:14-15): out[t] = number (val == NULL) or wrap-around sum of the values of the points
  * (idx[q], column of q) with row <= qi-1 and column <= qj-1.  pos == NULL: rook form, point q sits in column q.

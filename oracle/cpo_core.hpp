@@ -202,6 +202,147 @@ struct BaryDom {
   i64 step_prev_same(i64 i, i64 j) { return at(i, j); }
 };
 
+// SparsePrefixMatrices.jl:1-14 (struct), :60-185 (build), :188-254 (query): DominanceSum, the b-ary tree of DominanceCount with a
+// permuted copy of the values per level (wgt), cached per-digit counts (cnt, levels 2..H) and cached cumulative per-digit sums
+// (scn).  Values are 64-bit words with wrap-around (Julia's Int64 / UInt64 arithmetic).
+struct BarySum {
+  typedef unsigned long long W64;
+  i64 m, N;
+  int b, bp, H;
+  const ivec* pos;
+  ivec qos, byt;
+  std::vector<i64> cnt;  // cnt[d, Q, h], dims (2^b, (N>>bp)+1, H-1)
+  std::vector<W64> wgt;  // wgt[q, h],   dims (N, H)
+  std::vector<W64> scn;  // scn[d, Q, h], dims (2^b+1, (N>>bp)+1, H)
+  i64 B, D2;
+  inline i64& C(i64 d, i64 Q, i64 h) { return cnt[(size_t)(d - 1) + (size_t)B * ((Q - 1) + (size_t)D2 * (h - 1))]; }
+  inline i64 Cc(i64 d, i64 Q, i64 h) const { return cnt[(size_t)(d - 1) + (size_t)B * ((Q - 1) + (size_t)D2 * (h - 1))]; }
+  inline W64& S(i64 d, i64 Q, i64 h) { return scn[(size_t)(d - 1) + (size_t)(B + 1) * ((Q - 1) + (size_t)D2 * (h - 1))]; }
+  inline W64 Sc(i64 d, i64 Q, i64 h) const { return scn[(size_t)(d - 1) + (size_t)(B + 1) * ((Q - 1) + (size_t)D2 * (h - 1))]; }
+  inline W64& Wt(i64 q, i64 h) { return wgt[(size_t)(q - 1) + (size_t)N * (h - 1)]; }
+  inline W64 Wc(i64 q, i64 h) const { return wgt[(size_t)(q - 1) + (size_t)N * (h - 1)]; }
+
+  BarySum(i64 m_, i64 /*n*/, i64 N_, const ivec* pos_, ivec idx, const W64* val /* 0-based, N entries */, int b_ = 0, int H_ = 0, int bp_ = 0)
+      : m(m_), N(N_), pos(pos_) {
+    if (b_ <= 0) b_ = (int)cld(cllog2(m + 1), H_ <= 0 ? 3 : H_);  // :62-68
+    if (b_ <= 0) b_ = 1;
+    if (H_ <= 0) H_ = (int)cld(cllog2(m + 1), b_);                // :70-72
+    if (H_ <= 0) H_ = 1;
+    if (bp_ <= 0) bp_ = b_ + (int)cllog2(H_);                     // :74-76
+    b = b_; H = H_; bp = bp_;
+    B = (i64)1 << b;
+    D2 = (N >> bp) + 1;
+    qos.assign(m + 3, 0);
+    qos[1] = 1;
+    qos[m + 2] = N + 1;
+    ivec bkt(B + 2, 0);
+    std::vector<W64> pre(B + 2, 0);
+    cnt.assign((size_t)B * D2 * std::max(H - 1, 1), 0);
+    wgt.assign((size_t)std::max<i64>(N, 1) * H, 0);
+    scn.assign((size_t)(B + 1) * D2 * H, 0);
+    for (i64 q = 1; q <= N; ++q) Wt(q, H) = val[q - 1];
+    byt.assign(N + 1, 0);
+    const i64 bpmask = ((i64)1 << bp) - 1;
+    for (int h = H; h >= 2; --h) {  // :88-139
+      const i64 span = (i64)1 << (h * b);
+      const int sh = (h - 1) * b;
+      const i64 lowmask = ((i64)1 << sh) - 1;
+      for (i64 ip = 1; ip <= m + 1; ip += span) {
+        std::fill(bkt.begin(), bkt.end(), 0);
+        const i64 qend = qos[std::min(ip + span, m + 2)] - 1;
+        for (i64 q = qos[ip]; q <= qend; ++q) bkt[((idx[q] >> sh) & (B - 1)) + 2] += 1;
+        bkt[1] = qos[ip];
+        for (i64 d = 1; d <= B; ++d) bkt[d + 1] = bkt[d] + bkt[d + 1];
+        for (i64 q = qos[ip]; q <= qend; ++q) {
+          const i64 i = idx[q];
+          const i64 d = ((i >> sh) & (B - 1)) + 1;
+          const i64 qq = bkt[d];
+          byt[qq] = (idx[qq] & ~lowmask) | (i & lowmask);
+          Wt(qq, h - 1) = Wc(q, h);
+          bkt[d] = qq + 1;
+        }
+        for (i64 d = 1; d <= B; ++d) qos[std::min(ip + (d << sh), m + 2)] = bkt[d];
+      }
+      for (i64 d = 1; d <= B; ++d) C(d, 1, h - 1) = 0;
+      for (i64 d = 0; d <= B; ++d) S(d + 1, 1, h) = 0;
+      std::fill(bkt.begin(), bkt.end(), 0);
+      std::fill(pre.begin(), pre.end(), 0);
+      for (i64 q = 1; q <= N; ++q) {
+        const i64 d = ((idx[q] >> sh) & (B - 1)) + 1;
+        bkt[d] += 1;
+        pre[d] += Wc(q, h);
+        if ((q & bpmask) == 0) {  // cache at the end of each 2^b' block
+          const i64 Q = (q >> bp) + 1;
+          S(1, Q, h) = 0;
+          for (i64 dd = 1; dd <= B; ++dd) {
+            C(dd, Q, h - 1) = bkt[dd];
+            S(dd + 1, Q, h) = pre[dd] + Sc(dd, Q, h);
+          }
+        }
+      }
+      std::swap(idx, byt);
+    }
+    for (i64 ip = 1; ip <= m + 1; ip += B) {  // :141-160 (the last level only advances qos)
+      std::fill(bkt.begin(), bkt.end(), 0);
+      const i64 qend = qos[std::min(ip + B, m + 2)] - 1;
+      for (i64 q = qos[ip]; q <= qend; ++q) bkt[(idx[q] & (B - 1)) + 2] += 1;
+      bkt[1] = qos[ip];
+      for (i64 d = 1; d <= B; ++d) bkt[d + 1] = bkt[d] + bkt[d + 1];
+      for (i64 q = qos[ip]; q <= qend; ++q) bkt[(idx[q] & (B - 1)) + 1] += 1;
+      for (i64 d = 1; d <= B; ++d) qos[std::min(ip + d, m + 2)] = bkt[d];
+    }
+    for (i64 d = 0; d <= B; ++d) S(d + 1, 1, 1) = 0;  // :161-177
+    std::fill(pre.begin(), pre.end(), 0);
+    for (i64 q = 1; q <= N; ++q) {
+      const i64 d = (idx[q] & (B - 1)) + 1;
+      pre[d] += Wc(q, 1);
+      if ((q & bpmask) == 0) {
+        const i64 Q = (q >> bp) + 1;
+        S(1, Q, 1) = 0;
+        for (i64 dd = 1; dd <= B; ++dd) S(dd + 1, Q, 1) = pre[dd] + Sc(dd, Q, 1);
+      }
+    }
+    byt = std::move(idx);
+  }
+
+  W64 at(i64 i, i64 j) const {  // :188-254
+    i64 dq = (*pos)[j] - 1;
+    i = i - 1;
+    W64 s = 0;
+    for (int h = H; h >= 2; --h) {
+      const int sh = (h - 1) * b;
+      const i64 ip = (i & ~(((i64)1 << (h * b)) - 1)) + 1;
+      const i64 q1 = qos[ip] - 1;
+      const i64 q2 = q1 + dq;
+      const i64 d = ((i >> sh) & (B - 1)) + 1;
+      const i64 Q1 = (q1 >> bp) + 1, Q2 = (q2 >> bp) + 1;
+      s += Sc(d, Q2, h) - Sc(d, Q1, h);
+      dq = Cc(d, Q2, h - 1) - Cc(d, Q1, h - 1);
+      for (i64 q = ((Q1 - 1) << bp) + 1; q <= q1; ++q) {
+        const i64 dd = ((byt[q] >> sh) & (B - 1)) + 1;
+        if (dd < d) s -= Wc(q, h);
+        dq -= dd == d;
+      }
+      for (i64 q = ((Q2 - 1) << bp) + 1; q <= q2; ++q) {
+        const i64 dd = ((byt[q] >> sh) & (B - 1)) + 1;
+        if (dd < d) s += Wc(q, h);
+        dq += dd == d;
+      }
+    }
+    const i64 ip = (i & ~(B - 1)) + 1;
+    const i64 q1 = qos[ip] - 1;
+    const i64 q2 = q1 + dq;
+    const i64 d = (i & (B - 1)) + 1;
+    const i64 Q1 = (q1 >> bp) + 1, Q2 = (q2 >> bp) + 1;
+    s += Sc(d + 1, Q2, 1) - Sc(d + 1, Q1, 1);
+    for (i64 q = ((Q1 - 1) << bp) + 1; q <= q1; ++q)
+      if ((byt[q] & (B - 1)) + 1 <= d) s -= Wc(q, 1);
+    for (i64 q = ((Q2 - 1) << bp) + 1; q <= q2; ++q)
+      if ((byt[q] & (B - 1)) + 1 <= d) s += Wc(q, 1);
+    return s;
+  }
+};
+
 // SparsePrefixMatrices.jl:411-420 (struct), :610-655 (build), :660-689 (query)
 struct BinDom {
   i64 m, N;

@@ -100,6 +100,17 @@ def dominancecount(A, i, j, hint=T.NoHint(), b=0, H=0, bp=0) -> np.ndarray:
     return out
 
 
+def dominancesum(A, val, i, j, b=0, H=0, bp=0) -> np.ndarray:
+    """``dominancesum(hint, A; b, H, b')[i, j]`` through the restated DominanceSum structure (SparsePrefixMatrices.jl:1-254)."""
+    i, j = _arr(i), _arr(j)
+    val = np.asarray(val)
+    dtype = np.uint64 if val.dtype == np.uint64 else I64
+    v = np.ascontiguousarray(val.astype(dtype, copy=False)).view(I64)
+    out = np.empty(len(i), dtype=I64)
+    _check(lib().cpo_dominancesum(ctypes.byref(_csc(A)), _ptr(v), int(b), int(H), int(bp), ctypes.c_longlong(len(i)), _ptr(i), _ptr(j), _ptr(out)))
+    return out.view(dtype)
+
+
 def prefix_query(m, n, N, pos, idx, val, i, j) -> np.ndarray:
     """dominancesum / rookcount / rooksum entries by the offline sweep of cpo_prefix_query (pos None: rook form; val None: counts)."""
     i, j, idx = _arr(i), _arr(j), _arr(idx)

@@ -686,6 +686,7 @@ def test_prefix_structures(ref):
             assert np.array_equal(C.query(i, j), ref.dominancecount(A, i, j))
             got, exp = S.query(i, j), ref.prefix_query(m, n, A.nnz, A.colptr, A.rowval, val, i, j)
             assert got.dtype == exp.dtype and np.array_equal(got, exp), (m, n)
+            assert np.array_equal(got, ref.dominancesum(A, val, i, j)), (m, n)  # the restated DominanceSum structure of the reference
             assert S[m + 1, n + 1] == val.sum(dtype=val.dtype) and C[int(i[0]), int(j[0])] == C.query(i[:1], j[:1])[0]
             C.close(); S.close()
     for N in dims + [1000, 100000]:

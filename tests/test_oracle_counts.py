@@ -54,6 +54,24 @@ def ref_prefix(rows, cols, vals, i, j):
     return int(sel.sum()), int(vals[sel].sum(dtype=np.uint64))
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(H=1), dict(H=2), dict(H=3), dict(H=4), dict(b=1), dict(b=2), dict(b=3), dict(b=4)])
+def test_dominancesum_reference_structure(ref, kw):
+    """The restated DominanceSum (SparsePrefixMatrices.jl:1-254: b-ary tree, permuted value copies, cached digit counts and
+    cumulative sums) for the reference's own parameter grid (test_SparsePrefixMatrices.jl:27-41) with UInt values: every probed
+    entry equals sum(A[1:i-1, 1:j-1]) with wrap-around, and the independent offline sweep."""
+    rng = np.random.default_rng(32)
+    for m in DIMS + [15, 16, 17, 31, 32, 33, 63, 64, 65]:
+        for n in DIMS:
+            A = sprand(rng, m, n, 0.5)
+            val = rng.integers(0, 2**64, A.nnz, dtype=np.uint64)
+            cols = np.repeat(np.arange(1, n + 1), np.diff(A.colptr))
+            pts = probes(rng, 10, (1, m + 1), (1, n + 1))
+            i, j = [p[0] for p in pts], [p[1] for p in pts]
+            got = ref.dominancesum(A, val, i, j, **kw)
+            assert got.tolist() == [ref_prefix(A.rowval, cols, val, a, b)[1] for a, b in pts], (m, n, kw)
+            assert np.array_equal(got, ref.prefix_query(m, n, A.nnz, A.colptr, A.rowval, val, i, j))
+
+
 def test_dominancesum_and_rook_structures(ref):
     """dominancesum, rookcount!, rooksum! (test_SparsePrefixMatrices.jl:43-69): UInt values with wrap-around, a random
     permutation with odd values; every entry equals the definition.  The sweep also reproduces dominancecount."""
