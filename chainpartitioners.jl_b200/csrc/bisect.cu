@@ -1052,6 +1052,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
       if (dia) CPB_CUDA(cudaMemcpyAsync(&n_over, f.overpos.get() + A.n, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
       if (want_ub) CPB_CUDA(cudaMemcpyAsync(&run->ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
       CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      if (f.ls->speculative && !dia) A.max_row_deg = (i64)info[1];
       if (f.ls->speculative && info[1] > LT_MAX_DEG) {  // a heavy row: the row-segment kernels did nothing -> stable sort
         ProfScope prof("oracle_stripe");
         f.ls = build_link_stream(A, dia, 0, (i64)1 << 62, false, /*force_sort=*/true, /*as_pos=*/true);

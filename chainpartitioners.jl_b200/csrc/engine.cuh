@@ -12,6 +12,9 @@ struct Matrix {
   i64 m = 0, n = 0, N = 0;
   DBuf<u32> pos;  // [n+1] offsets, pos[n] == N
   DBuf<u32> row;  // [N] row indices
+  // largest number of nonzeros in one row, learned by the first link construction on this handle (-1 = not known yet):
+  // later solves on a resident matrix skip the row histogram when it only serves to pick the construction path
+  mutable i64 max_row_deg = -1;
 };
 
 // ---- a dominance ("rank") structure: points sorted by x + wavelet matrix over their link value
@@ -57,7 +60,8 @@ std::unique_ptr<RankStruct> build_partwise_rank(const Matrix& A, const u32* asg,
 void build_partwise_columns(const Matrix& A, const u32* asg, u32 K, DBuf<u32>& part_col, DBuf<u32>& part_start, DBuf<u32>& part_head);
 // prev[q] = 1-based previous column holding the same row (0 if none); colidx[q] = 0-based column of q
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count = nullptr,
-                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false, bool as_pos = false);
+                        i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false, bool force_sort = false, bool as_pos = false,
+                        i64* max_deg_cache = nullptr);
 // For the diagonal-augmented structure the pin prefix (pos') differs from A.pos; it is RankStruct::P.
 
 // ---- device-side oracle ------------------------------------------------------------------------
@@ -150,11 +154,13 @@ template <> struct CoefOf<i64> {
   static __device__ __forceinline__ i64 get(const DevOracle& o, int t) { return o.ci[t]; }
   static __device__ __forceinline__ i64 alpha_col(const DevOracle& o, u32 w) { return o.tab_alpha_i[w]; }
   static __device__ __forceinline__ i64 beta_col(const DevOracle& o, u32 w) { return o.tab_beta_i[w]; }
+  static __device__ __forceinline__ i64 infinite() { return (i64)1 << 60; }
 };
 template <> struct CoefOf<double> {
   static __device__ __forceinline__ double get(const DevOracle& o, int t) { return o.cf[t]; }
   static __device__ __forceinline__ double alpha_col(const DevOracle& o, u32 w) { return o.tab_alpha_f[w]; }
   static __device__ __forceinline__ double beta_col(const DevOracle& o, u32 w) { return o.tab_beta_f[w]; }
+  static __device__ __forceinline__ double infinite() { return __longlong_as_double(0x7ff0000000000000ll); }
 };
 
 // nets(j,j') = #distinct rows in columns [j,j')  = #{q < pos[j'] : prev_q < j} - pos[j]   (1-based j, j')
@@ -209,6 +215,9 @@ template <class T> __device__ __forceinline__ T dev_cost(const DevOracle& o, u32
       return C::get(o, 0) + (T)nv * C::get(o, 1) + (T)np * C::get(o, 2) + (T)d * C::get(o, 3);
     }
     case CPB_MODEL_COLBLOCK: {  // BlockCosts.jl:17
+      // the tables hold w = 0..w_tab only (a ConstrainedCost shrinks them to the widest feasible part): a wider part has no
+      // tabulated cost -- it is infeasible under the constraint that shrank the table -- and evaluates to "infinite"
+      if (nv > (i64)o.w_tab) return CoefOf<T>::infinite();
       const i64 d = dev_netcount(o.net, j, jp);
       return C::alpha_col(o, (u32)nv) + (T)d * C::beta_col(o, (u32)nv);
     }

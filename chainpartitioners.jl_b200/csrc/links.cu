@@ -229,7 +229,7 @@ static u32 read_u32(const u32* d) {
 // do nothing if the degree is too large) and return true; the caller inspects info[1] later and calls again with
 // CPB_NO_ROW_SEGMENTS semantics (force_sort) if it exceeds LT_MAX_DEG.
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
-                        i64 row_lo, i64 row_hi, bool defer_check, bool force_sort, bool as_pos) {
+                        i64 row_lo, i64 row_hi, bool defer_check, bool force_sort, bool as_pos, i64* max_deg_cache) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
   {
     ProfScope pk("k_expand_columns", (double)N * 4.0 + (double)ncol * 4.0);
@@ -238,7 +238,9 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   DBuf<u32> dummy;
   if (!first_count) { dummy.alloc(2); first_count = dummy.get(); }
   CPB_CUDA(cudaMemsetAsync(first_count, 0, 2 * sizeof(u32), ctx().stream));
-  const bool no_lt = force_sort || std::getenv("CPB_NO_ROW_SEGMENTS") != nullptr;  // (tests: force the radix-sort path)
+  // a row known to be too heavy (an earlier construction on the same resident matrix saw it): straight to the sort
+  const bool known_heavy = max_deg_cache && *max_deg_cache > (i64)LT_MAX_DEG;
+  const bool no_lt = force_sort || known_heavy || std::getenv("CPB_NO_ROW_SEGMENTS") != nullptr;  // (tests: force the radix-sort path)
   if (row_lo <= 0 && row_hi >= (i64)nrow && N && nrow && !no_lt) {
     DBuf<u32> cur((size_t)nrow + 1);  // per-row counts -> segment starts -> (after the fill) segment ends; [nrow] = max degree
     CPB_CUDA(cudaMemsetAsync(cur.get(), 0, ((size_t)nrow + 1) * sizeof(u32), ctx().stream));
@@ -247,7 +249,12 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
       CPB_LAUNCH(k_lt_count, grid_for(N), 256, 0, row, N, cur.get());
     }
     CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
-    if (defer_check || read_u32(cur.get() + nrow) <= LT_MAX_DEG) {
+    u32 seen_deg = 0;
+    if (!defer_check) {
+      seen_deg = read_u32(cur.get() + nrow);
+      if (max_deg_cache) *max_deg_cache = (i64)seen_deg;
+    }
+    if (defer_check || seen_deg <= LT_MAX_DEG) {
       exclusive_scan_u32(cur.get(), cur.get(), (size_t)nrow);
       DBuf<u32> T(N);
       {
@@ -314,7 +321,7 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
     ls->colidx.alloc(N);
     ls->first_count.alloc(2);
     ls->speculative = compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi,
-                                         defer_check, force_sort, as_pos);
+                                         defer_check, force_sort, as_pos, &A.max_row_deg);
     ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
     return ls;
   }
@@ -332,12 +339,13 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
   expand_columns(A.pos.get(), n, colidx.get(), N);
   if (N) CPB_LAUNCH(k_aug_rows, grid_for(N), 256, 0, A.row.get(), colidx.get(), addscan.get(), N, row2.get());
   if (n) CPB_LAUNCH(k_aug_diag, grid_for(n), 256, 0, pos2, add.get(), n, row2.get());
+  i64 heavy_hint = A.max_row_deg > (i64)LT_MAX_DEG ? A.max_row_deg : -1;  // A + I only adds entries: a heavy row of A stays heavy
   ls->Ne = N2;
   ls->prev.alloc(N2);
   ls->colidx.alloc(N2);
   ls->first_count.alloc(2);
   ls->speculative = compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi, defer_check,
-                                       force_sort, as_pos);
+                                       force_sort, as_pos, &heavy_hint);
   ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
   return ls;
 }

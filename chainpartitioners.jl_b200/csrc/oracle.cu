@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(256) k_oracle_query(const __grid_constant__ De
     const i64 j = qj[t], jp = qjp[t];
     double r;
     if (j < 1 || jp < j || jp > (i64)o.n + 1) r = __longlong_as_double(0x7ff8000000000000ll);  // invalid query -> NaN
+    else if (o.kind == CPB_MODEL_COLBLOCK && jp - j > (i64)o.w_tab) r = __longlong_as_double(0x7ff0000000000000ll);  // wider than the tables: +Inf
     else r = (double)dev_cost<T>(o, (u32)j, (u32)jp, qk ? (u32)qk[t] : 1u);
     out[t] = r;
   }

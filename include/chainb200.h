@@ -63,7 +63,10 @@ enum {
  * COLBLOCK / BLOCK: block_component(f, w) (BlockCosts.jl:41-44) tabulated by the caller, because
  * Julia functors cannot cross the ABI:
  *   alpha_col[w], w = 0..w_tab;  beta_col[r*(w_tab+1) + w], r = 0..R-1 (COLBLOCK: R = 1);
- *   beta_row[r*(u_tab+1) + u], u = 0..u_tab (BLOCK only; u = size of a row part). */
+ *   beta_row[r*(u_tab+1) + u], u = 0..u_tab (BLOCK only; u = size of a row part).
+ * COLBLOCK parts wider than w_tab columns have no tabulated cost: cpb_oracle_query returns +Inf for
+ * them (the table is normally shrunk to the widest part a ConstrainedCost allows, so such a part is
+ * infeasible anyway); the solvers never evaluate them. */
 typedef struct cpb_model {
   int32_t kind;
   int32_t is_float;

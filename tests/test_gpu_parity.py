@@ -138,6 +138,27 @@ def test_column_block_oracle(ref, fixtures):
         assert np.array_equal(got, ref.oracle_query(mdl, A, j, jp))
 
 
+def test_column_block_oracle_wider_than_table(ref, fixtures):
+    """a ConstrainedCost shrinks the tabulated widths to w_tab < n; queries wider than the table must not read
+    past it -- they are infeasible under the constraint and come back as +Inf, the others equal the CPU oracle."""
+    rng = np.random.default_rng(1031)
+    A = fixtures["LPnetlib/lp_blend"]
+    mdl = cp.ColumnBlockComponentCostModel(int, 3, lambda w: 1 + w)
+    con = cp.ConstrainedCost(mdl, cp.VertexCount(), 5)
+    j = rng.integers(1, A.n + 1, 2000)
+    jp = np.minimum(j + rng.integers(0, A.n, 2000), A.n + 1)  # most of them far wider than the 5-column window
+    ocl = cp.oracle_stripe(con, A)
+    got = ocl.query(j, jp)
+    ocl.close()
+    wide = (jp - j) > 5
+    assert np.all(np.isinf(got[wide])) and wide.sum() > 1000
+    assert np.array_equal(got[~wide], ref.oracle_query(mdl, A, j[~wide], jp[~wide]))
+    raw = cp.oracle_stripe(mdl, A, w_tab=4)  # an explicit short table, no constraint: still no out-of-bounds read
+    got = raw.query(j, jp)
+    raw.close()
+    assert np.all(np.isinf(got[(jp - j) > 4]))
+
+
 def test_bound_and_objective(ref, fixtures):
     rng = np.random.default_rng(104)
     for A in small_matrices(fixtures):
