@@ -17,7 +17,9 @@ def run_sharded(cp, dist, W, M, extra, args, rank, world, local_rank, barrier, f
     from chainb200 import parallel
 
     K = min(1024, max(2, M.n // 64))
-    mtd = cp.LazyBisectCostBottleneckSplitter(cp.workloads.AFF, 0.01)
+    from chainb200.workloads import AFF
+
+    mtd = cp.LazyBisectCostBottleneckSplitter(AFF, 0.01)
     comm = parallel.library_communicator(cp, dist, rank, world)
     warm = max(args.warmup, 3)
     # ---- resident: the pattern already in HBM on every rank (each rank holds its column block + the offsets) ----

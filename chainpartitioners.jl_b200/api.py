@@ -20,6 +20,7 @@ __all__ = [
     "DeviceMatrix", "device_matrix", "device_matrix_i32", "adjointpattern", "permute", "oracle_stripe", "bound_stripe", "partition_stripe",
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "PrefixMatrix", "dominancecount", "dominancesum", "rookcount", "rooksum", "profile_enable", "profile_reset", "profile_get",
+    "Communicator", "ShardedMatrix", "partition_stripe_sharded", "partition_stripe_sharded_emulated", "sharded_stats", "shard_range",
     "launch_count", "probe_cluster_capacity", "bisect_stats", "bisect_plan", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "trim_memory", "library_path", "load_library", "CpbError",
 ]
 
@@ -35,6 +36,8 @@ ABI_SYMBOLS = [
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
     "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_bisect_plan", "cpb_probe_cluster_capacity",
+    "cpb_comm_unique_id", "cpb_comm_init", "cpb_comm_destroy", "cpb_comm_info", "cpb_shard_range", "cpb_sharded_matrix_create", "cpb_sharded_matrix_destroy",
+    "cpb_partition_stripe_sharded", "cpb_partition_stripe_sharded_emulated", "cpb_sharded_stats",
     "cpb_links_partial", "cpb_oracle_set_links", "cpb_prefix_create", "cpb_prefix_query", "cpb_prefix_destroy", "cpb_matrix_permute", "cpb_trim_memory", "cpb_matrix_create_i32",
 ]
 
@@ -86,6 +89,16 @@ def load_library():
         lib.cpb_bisect_finish.argtypes = [vp, vp]
         lib.cpb_links_partial.argtypes = [vp, i64, i64, vp, ctypes.POINTER(i64)]
         lib.cpb_oracle_set_links.argtypes = [vp, vp, i64]
+        lib.cpb_comm_unique_id.argtypes = [vp]
+        lib.cpb_comm_init.argtypes = [vp, i32, i32]
+        lib.cpb_comm_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        lib.cpb_shard_range.argtypes = [i64, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        lib.cpb_sharded_matrix_create.argtypes = [i64, i64, i64, vp, vp, i32, ctypes.POINTER(vp)]
+        lib.cpb_sharded_matrix_destroy.argtypes = [vp]
+        lib.cpb_sharded_matrix_destroy.restype = None
+        lib.cpb_partition_stripe_sharded.argtypes = [vp, ctypes.POINTER(T.CModel), i32, dbl, i64, vp]
+        lib.cpb_partition_stripe_sharded_emulated.argtypes = [vp, ctypes.POINTER(T.CModel), i32, dbl, i64, i32, vp]
+        lib.cpb_sharded_stats.argtypes = [vp]
         _lib = lib
     return _lib
 
@@ -620,6 +633,114 @@ def pack_plaid(A, method, adj_A=None, **kwargs):
         finally:
             if own_adj or not isinstance(adj_A, DeviceMatrix):
                 dT.close()
+
+
+# ------------------------------------------------------------------------------- one solve over several GPUs
+
+
+class Communicator:
+    """The library-owned NCCL communicator (``cpb_comm_*``): one process per GPU.  Rank 0 makes the 128-byte id with
+    ``Communicator.unique_id()``, the host ships it to the other ranks (MPI bcast, a file, torch.distributed -- see
+    ``parallel.library_communicator``), every rank constructs ``Communicator(id, rank, world)`` after ``init(device)``."""
+
+    def __init__(self, uid: bytes, rank: int, world: int):
+        if len(uid) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        self.rank, self.world = int(rank), int(world)
+        buf = ctypes.create_string_buffer(bytes(uid), 128)
+        _check(load_library().cpb_comm_init(buf, self.rank, self.world))
+        self._open = True
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _check(load_library().cpb_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_open", False) and _lib is not None:
+            _lib.cpb_comm_destroy()
+        self._open = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_range(nnz: int, rank: int, world: int):
+    """0-based half-open block of CSC positions owned by ``rank`` (``cpb_shard_range``; host arithmetic only)."""
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    _check(load_library().cpb_shard_range(int(nnz), int(rank), int(world), ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+class ShardedMatrix:
+    """A pattern spread over the ranks of the communicator (``cpb_sharded``): every rank holds the column offsets and its own
+    block of ``rowval``.  Collective: every rank constructs it from the same host matrix."""
+
+    def __init__(self, A, comm: Optional[Communicator] = None):
+        self.m, self.n, self.nnz = int(A.m), int(A.n), int(A.nnz)
+        self.comm = comm
+        self._h = ctypes.c_void_p()
+        _check(load_library().cpb_sharded_matrix_create(self.m, self.n, self.nnz, _p(A.colptr), _p(A.rowval), 0, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.cpb_sharded_matrix_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _sharded_args(method):
+    code, spec, eps = T.split_method_code(method)
+    f, con = T.split_constrained(spec)
+    if con.enabled:
+        raise TypeError("sharded solves take an unconstrained AffineConnectivityModel")
+    cm, keep = f.to_c()
+    return code, cm, keep, eps
+
+
+def partition_stripe_sharded(A, K, method, comm: Optional[Communicator] = None) -> T.SplitPartition:
+    """``partition_stripe(A, K, BisectCost/LazyBisectCost(AffineConnectivityModel, eps))`` as ONE solve over all ranks of the
+    communicator (collective; every rank gets the same ``SplitPartition``).  ``A``: a ``ShardedMatrix`` (resident) or a host
+    matrix (every rank uploads its block inside the call)."""
+    K = int(K)
+    code, cm, keep, eps = _sharded_args(method)
+    own = not isinstance(A, ShardedMatrix)
+    sh = ShardedMatrix(A, comm) if own else A
+    try:
+        spl = np.empty(K + 1, dtype=I64)
+        _check(load_library().cpb_partition_stripe_sharded(sh._h, ctypes.byref(cm), code, eps, K, _p(spl)))
+    finally:
+        if own:
+            sh.close()
+    return T.SplitPartition(K, spl)
+
+
+def partition_stripe_sharded_emulated(A, K, method, world: int) -> T.SplitPartition:
+    """The sharded solve with ``world`` ranks played one after the other on this GPU (tests: block construction + carry
+    rule + world x 15 thresholds per round, no NCCL)."""
+    K = int(K)
+    code, cm, keep, eps = _sharded_args(method)
+    spl = np.empty(K + 1, dtype=I64)
+    with _Scoped(A) as dm:
+        _check(load_library().cpb_partition_stripe_sharded_emulated(dm._h, ctypes.byref(cm), code, eps, K, int(world), _p(spl)))
+    return T.SplitPartition(K, spl)
+
+
+def sharded_stats() -> dict:
+    out = (ctypes.c_double * 16)()
+    _check(load_library().cpb_sharded_stats(out))
+    return {"world": int(out[0]), "host_ms_until_links_queued": out[1], "bisection_ms_incl_links_wait": out[2], "rounds": int(out[3]),
+            "link_allgather_bytes": out[4], "carry_bytes_per_hop": out[5], "threshold_allgather_bytes": out[6], "thresholds_per_round": int(out[7]),
+            "limiting_collective": "in-place ncclAllGather of the link array (nnz x 4 bytes on every rank)"}
 
 
 class StepwiseBisection:

@@ -435,6 +435,7 @@ struct DevStream {
   const u32* colidx;  // [Ne]
   const u32* P;       // element offsets of the column boundaries, 1 <= x <= n+1
   const u32* Wt;      // prefix of the pin-like term, 1 <= x <= n+1
+  const u32* chunk_col;  // [ceil(Ne / 4096) + 1] column of the first element of every 4096-element chunk (ring probes)
   u32 Ne, n;
   int same_w;         // Wt == P
   double cf[4];
@@ -742,6 +743,399 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   cluster.sync();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming probe, ring form (kernel "probe_ring").  Same algorithm and results as k_probe_stream; what changes is how
+// the latency chain of a part is built:
+//   * the link array is consumed strictly left to right by every threshold, so it is staged AHEAD of the search: the
+//     cluster's 8 CTAs own the 16 KB chunks of the array round-robin (chunk g belongs to CTA g mod 8) and each keeps its
+//     next PR_S chunks in a shared-memory ring filled by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx).  Only the
+//     compare `prev <= first position of the part` depends on the part start, so a part's tile is already on chip when
+//     its start becomes known -- no global-memory latency on the chain;
+//   * the two exchanges of a super-step (per-chunk `prev < j` totals; per-CTA feasible-boundary counts) are remote
+//     st.async stores that carry their payload into every peer's shared memory and complete a transaction count on the
+//     peer's mbarrier -- no barrier.cluster, no fence in front of it, no L1 invalidation;
+//   * chunk boundaries (first / last column of a chunk) come from a per-chunk table built once with the links.
+// A super-step covers the chunks [g_win, g_win + 8 W) (W <= PR_WMAX per CTA, sized from the previous part); warp w owns
+// the 128-element group w of every chunk of its CTA.
+// ------------------------------------------------------------------------------------------------
+static constexpr int PR_THREADS = 1024;
+static constexpr u32 PR_C = 4096;      // elements per chunk (16 KB)
+static constexpr int PR_S = 12;        // ring slots per CTA (192 KB)
+static constexpr int PR_WMAX = 6;      // chunks per CTA per super-step
+static constexpr int PR_G = 32;        // 128-element groups per chunk = warps per CTA
+static constexpr size_t PR_RING_BYTES = (size_t)PR_S * PR_C * sizeof(u32);
+
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 map_peer(u32 addr, u32 rank) {
+  u32 r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// (a wait that never completes -- a protocol bug -- traps after ~2^22 polls instead of hanging the GPU)
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {  // data written by this CTA's bulk copies
+  u32 ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {  // data written by peers' st.async
+  u32 ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(u32 remote_addr, u32 a, u32 b, u32 c, u32 d, u32 remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr), "r"(a), "r"(b),
+               "r"(c), "r"(d), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct PrShared {
+  alignas(16) u32 mask[PR_WMAX][PR_G + 1][4];  // `prev < j` bit masks of every group; [.][32] = zero sentinel (offset == chunk size)
+  u32 cnt[PR_WMAX][PR_G];                      // set bits per group
+  u32 cum[PR_WMAX][PR_G + 1];                  // exclusive prefix of cnt inside the chunk; [.][32] = chunk total
+  u32 cb[PR_WMAX][2];                          // (first boundary, number of boundaries) of this CTA's chunks in the window
+  alignas(16) u32 x1[2][8 * PR_WMAX];          // exchange 1: chunk totals of the whole window, window order
+  alignas(16) u32 x2[2][8][4];                 // exchange 2: per CTA (feasible boundaries, boundaries, P and Wt at its last feasible one)
+  u32 pj[2 * PR_THREADS];                      // (P, Wt) of the boundary candidates of the current search round
+  u32 w[2 * PR_THREADS];
+  u32 red[2][4];                               // refinement result of the crossing thread (per super-step parity)
+  alignas(8) unsigned long long mb_full[PR_S];
+  alignas(8) unsigned long long mb_x1[2];
+  alignas(8) unsigned long long mb_x2[2];
+  double c;
+  int valid;
+};
+
+template <class T>
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS, 1)
+    k_probe_ring(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st, int* __restrict__ node_spl,
+                 int* __restrict__ node_res, double* __restrict__ node_c, const int* __restrict__ node_ids, int node_base) {
+  extern __shared__ __align__(128) unsigned char pr_ring_raw[];
+  u32* const ring = reinterpret_cast<u32*>(pr_ring_raw);  // [PR_S][PR_C]
+  __shared__ PrShared sh;
+  cg::cluster_group cluster = cg::this_cluster();
+  const u32 crank = cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int node = node_base + blockIdx.x / BS_CLUSTER;
+  const bool writer = crank == 0 && tid == 0;
+  if (tid == 0) {
+    sh.valid = node_threshold(st, eps1, node_ids[node], &sh.c);
+    for (int t = 0; t < PR_S; ++t) mbar_init(smem_addr(&sh.mb_full[t]), 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(smem_addr(&sh.mb_x1[t]), 1); mbar_init(smem_addr(&sh.mb_x2[t]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < PR_WMAX * 4) sh.mask[tid >> 2][PR_G][tid & 3] = 0;
+  __syncthreads();
+  if (!sh.valid) {  // uniform over the cluster: every CTA derives it from the same state
+    if (writer) node_res[node] = 0;
+    return;
+  }
+  cluster.sync();  // every CTA's mbarriers are initialised before a peer's st.async can reach them
+  const double c = sh.c;
+  const u32 n1 = s.n + 1;
+  const u32 Ne = s.Ne;
+  int* spl = node_spl + (size_t)node * (K + 2);
+  if (writer) { spl[1] = 1; spl[K + 1] = (int)n1; }
+  u32 W = PR_WMAX, w_est = PR_WMAX;
+  u32 sstep = 0;      // super-steps so far (selects the exchange buffers / mbarrier parities)
+  u32 fill_hi = 0;    // this CTA's chunks [0, fill_hi) have been requested (local chunk l = global chunk 8 l + crank)
+  u32 j = 1;
+  bool broke = false, feasible = false;
+  u32 pcur = __ldg(s.P + 1), wcur = __ldg(s.Wt + 1);
+  const u32 x1_base = smem_addr(&sh.x1[0][0]), x2_base = smem_addr(&sh.x2[0][0][0]);
+  const u32 bar_x1 = smem_addr(&sh.mb_x1[0]), bar_x2 = smem_addr(&sh.mb_x2[0]);
+  for (int k = 1; k <= K; ++k) {
+    if (!cost_leq(stream_cost<T>(s, 0, 0, 0), c)) { broke = true; break; }  // even the empty part exceeds c
+    const u32 e0 = pcur;
+    const i64 wj = (i64)wcur;
+    u32 jlast = j, grun = 0;
+    bool first = true, missed = false;
+    for (u32 g_win = e0 / PR_C;;) {
+      const u32 ph = sstep & 1u, xpar = (sstep >> 1) & 1u;
+      const u32 l0 = (g_win + 7u - crank) >> 3;              // first local chunk of this CTA inside the window
+      const u32 p0 = (crank - g_win) & 7u;                   // its position in window order; the others follow at +8
+      // ---- arm this super-step's exchange barriers, keep the ring full ----
+      if (tid == 0) {
+        sh.red[ph][0] = 0;
+        mbar_expect_tx(bar_x1 + 8u * ph, 32u * W);
+        mbar_expect_tx(bar_x2 + 8u * ph, 128u);
+        const u32 want_hi = l0 + PR_S;
+        if (fill_hi < want_hi) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slots' last readers were generic-proxy loads
+          for (u32 l = fill_hi; l < want_hi; ++l) {
+            const u64 x0 = ((u64)l * 8u + crank) * PR_C;
+            if (x0 >= Ne) break;
+            const u32 slot = l % PR_S;
+            const u32 bar = smem_addr(&sh.mb_full[slot]);
+            mbar_expect_tx(bar, PR_C * 4u);
+            bulk_load(smem_addr(ring + (size_t)slot * PR_C), s.prev + x0, PR_C * 4u, bar);
+          }
+        }
+      }
+      fill_hi = max(fill_hi, l0 + PR_S);
+      // ---- boundaries of this CTA's chunks: chunk [x0, x0 + C) owns the columns boundaries r with x0 < P[r] <= x0 + C ----
+      if (tid < (int)W) {
+        const u32 g = (l0 + tid) * 8u + crank;
+        const u64 x0 = (u64)g * PR_C;
+        const bool head = first && g == g_win;  // the chunk holding the part's first element: candidates start right after j
+        u32 ja, jb;
+        if (head) ja = j + 1;
+        else ja = (x0 < Ne) ? __ldg(s.chunk_col + g) + 2 : n1 + 1;
+        if (x0 >= Ne && !head) jb = 0;
+        else jb = (x0 + PR_C >= Ne) ? n1 : __ldg(s.chunk_col + g + 1) + 1;
+        sh.cb[tid][0] = ja;
+        sh.cb[tid][1] = (jb >= ja) ? jb - ja + 1 : 0;
+      }
+      // ---- bit masks of `prev < j`: warp w owns group w of each of the W chunks ----
+#pragma unroll
+      for (int v = 0; v < PR_WMAX; ++v) {
+        if (v >= (int)W) break;
+        const u32 l = l0 + v;
+        const u64 x0 = ((u64)l * 8u + crank) * PR_C;
+        const u64 gbase = x0 + (u32)warp * 128u;
+        unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (gbase < Ne && gbase + 128u > e0) {  // (warp-uniform) the group holds elements of [e0, Ne)
+          const u32 slot = l % PR_S;
+          mbar_wait(smem_addr(&sh.mb_full[slot]), (l / PR_S) & 1u);
+          const uint4 pv = *reinterpret_cast<const uint4*>(ring + (size_t)slot * PR_C + warp * 128 + lane * 4);
+          if (gbase >= e0 && gbase + 128u <= Ne) {
+            m0 = __ballot_sync(0xffffffffu, pv.x <= e0);
+            m1 = __ballot_sync(0xffffffffu, pv.y <= e0);
+            m2 = __ballot_sync(0xffffffffu, pv.z <= e0);
+            m3 = __ballot_sync(0xffffffffu, pv.w <= e0);
+          } else {  // the part's first group / the array's last group: mask what lies outside [e0, Ne)
+            const u64 idx = gbase + (u32)lane * 4u;
+            m0 = __ballot_sync(0xffffffffu, pv.x <= e0 && idx + 0 >= e0 && idx + 0 < Ne);
+            m1 = __ballot_sync(0xffffffffu, pv.y <= e0 && idx + 1 >= e0 && idx + 1 < Ne);
+            m2 = __ballot_sync(0xffffffffu, pv.z <= e0 && idx + 2 >= e0 && idx + 2 < Ne);
+            m3 = __ballot_sync(0xffffffffu, pv.w <= e0 && idx + 3 >= e0 && idx + 3 < Ne);
+          }
+        }
+        if (lane == 0) {
+          *reinterpret_cast<uint4*>(&sh.mask[v][warp][0]) = make_uint4(m0, m1, m2, m3);
+          sh.cnt[v][warp] = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        }
+      }
+      __syncthreads();
+      // ---- warp v scans chunk v and pushes the chunk total into every CTA's window table ----
+      if (warp < (int)W) {
+        const u32 t = sh.cnt[warp][lane];
+        u32 inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += y;
+        }
+        sh.cum[warp][lane] = inc - t;
+        if (lane == 31) sh.cum[warp][PR_G] = inc;
+        const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane < BS_CLUSTER) {
+          const u32 dst = x1_base + 4u * (ph * 8u * PR_WMAX + (u32)warp * 8u + p0);
+          st_async_u32(map_peer(dst, lane), tot, map_peer(bar_x1 + 8u * ph, lane));
+        }
+      }
+      __syncthreads();
+      // ---- this CTA's boundary candidates, flat over its W chunks; the offsets of a thread's (at most 4) candidates are
+      //      fetched while the totals travel ----
+      u32 cn[PR_WMAX + 1], cja[PR_WMAX];
+      cn[0] = 0;
+#pragma unroll
+      for (int v = 0; v < PR_WMAX; ++v) {
+        const bool on = v < (int)W;
+        cja[v] = on ? sh.cb[v][0] : 0u;
+        cn[v + 1] = cn[v] + (on ? sh.cb[v][1] : 0u);
+      }
+      const u32 nb = cn[PR_WMAX];
+      auto locate = [&](u32 b, u32& r, u32& v) {  // flat candidate index -> (boundary, local chunk)
+        v = 0;
+#pragma unroll
+        for (int t = 1; t < PR_WMAX; ++t) v += (b >= cn[t]) ? 1u : 0u;
+        u32 cv = cn[0], jv = cja[0];
+#pragma unroll
+        for (int t = 1; t < PR_WMAX; ++t)
+          if (v == (u32)t) { cv = cn[t]; jv = cja[t]; }
+        r = jv + (b - cv);
+      };
+      const bool few = nb > 0 && nb <= 4u * PR_THREADS;
+      const u32 per = (nb + PR_THREADS - 1) / PR_THREADS;
+      const u32 b0 = (u32)tid * per;
+      const u32 mine = (few && b0 < nb) ? min(per, nb - b0) : 0u;
+      u32 pjv[4], wv[4], rv[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < (int)mine) {
+          locate(b0 + i, rv[i], vv[i]);
+          pjv[i] = __ldg(s.P + rv[i]);
+          wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + rv[i]);
+        }
+      mbar_wait_cluster(bar_x1 + 8u * ph, xpar);
+      // ---- exclusive prefix of the window's chunk totals (window order), redundantly per warp: lane p and lane p + 32 ----
+      u32 excl0, excl1, tile_tot;
+      {
+        const u32 nwin = 8u * W;
+        const u32 q0 = (u32)lane, q1 = (u32)lane + 32u;
+        const u32 t0 = q0 < nwin ? sh.x1[ph][(q0 >> 3) * 8u + (q0 & 7u)] : 0u;  // x1[ph][i * 8 + position mod 8], i = q / 8
+        const u32 t1 = q1 < nwin ? sh.x1[ph][(q1 >> 3) * 8u + (q1 & 7u)] : 0u;
+        u32 i0 = t0, i1 = t1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 y0 = __shfl_up_sync(0xffffffffu, i0, o), y1 = __shfl_up_sync(0xffffffffu, i1, o);
+          if (lane >= o) { i0 += y0; i1 += y1; }
+        }
+        const u32 tot0 = __shfl_sync(0xffffffffu, i0, 31);
+        excl0 = i0 - t0;
+        excl1 = tot0 + i1 - t1;
+        tile_tot = tot0 + __shfl_sync(0xffffffffu, i1, 31);
+      }
+      // count of `prev < j` among the part's elements left of offset pj, pj inside (or at the end of) local chunk v
+      auto count_at = [&](u32 pj, u32 v) -> u32 {
+        const u32 q = v * 8u + p0;  // window position of the chunk
+        const u32 b_lo = __shfl_sync(0xffffffffu, excl0, q & 31u), b_hi = __shfl_sync(0xffffffffu, excl1, q & 31u);
+        const u32 x = pj - (u32)((((u64)(l0 + v)) * 8u + crank) * PR_C);  // 0 <= x <= C
+        const u32 g = x >> 7, r = x & 127u;
+        u32 cnt = grun + (q < 32u ? b_lo : b_hi) + sh.cum[v][g];
+        const uint4 mk = *reinterpret_cast<const uint4*>(&sh.mask[v][g][0]);
+        const u32 mm[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int nl = ((int)r - t + 3) >> 2;  // lanes l with 4 l + t < r
+          const u32 msk = nl >= 32 ? 0xffffffffu : (nl <= 0 ? 0u : ((1u << nl) - 1u));
+          cnt += __popc(mm[t] & msk);
+        }
+        return cnt;
+      };
+      // (count_at shuffles: every lane of a warp must call it the same number of times -- callers pass dummies)
+      auto feasible_at = [&](bool live, u32 r, u32 pj, u32 w, u32 v) -> bool {
+        const u32 g = count_at(live ? pj : (u32)((((u64)l0) * 8u + crank) * PR_C), live ? v : 0u);
+        return live && cost_leq(stream_cost<T>(s, (i64)r - (i64)j, (i64)w - wj, (i64)g), c);
+      };
+      u32 cnt = 0, lastp = 0, lastw = 0;
+      if (few) {
+        // every thread tests its LAST candidate; the first thread whose last one fails holds the crossing and tests its
+        // remaining ones from registers
+        u32 pl = 0, wl = 0, rl = 0, vl = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < (int)mine) { pl = pjv[i]; wl = wv[i]; rl = rv[i]; vl = vv[i]; }
+        if (mine > 0) { sh.pj[tid] = pl; sh.w[tid] = wl; }
+        const bool ok = feasible_at(mine > 0, rl, pl, wl, vl);
+        const int ct = __syncthreads_count(ok);  // threads 0 .. ct-1 are feasible throughout
+        cnt = min((u32)ct * per, nb);
+        if (ct > 0) { lastp = sh.pj[ct - 1]; lastw = sh.w[ct - 1]; }
+        if (per > 1) {
+          // (warp-uniform trip count: the whole warp of the crossing thread evaluates, only that thread's result counts)
+          const bool crossing_warp = (ct >> 5) == warp && ct < PR_THREADS;
+          if (crossing_warp) {
+            const bool me = tid == ct && mine > 1;
+            u32 c2 = 0, lp = 0, lw = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const bool live = me && i < (int)mine - 1 && c2 == (u32)i;
+              if (feasible_at(live, rv[i], pjv[i], wv[i], vv[i])) { c2 = i + 1; lp = pjv[i]; lw = wv[i]; }
+            }
+            if (me) { sh.red[ph][0] = c2; sh.red[ph][1] = lp; sh.red[ph][2] = lw; }
+          }
+          __syncthreads();
+          const u32 c2 = sh.red[ph][0];
+          if (c2 > 0) { cnt += c2; lastp = sh.red[ph][1]; lastw = sh.red[ph][2]; }
+        }
+      } else if (nb > 0) {
+        // many candidates (runs of empty columns): 1024-way search, repeated until the crossing is pinned down
+        u32 lo = 0, hi = nb;  // candidates [0, lo) feasible, [hi, nb) not
+        while (lo < hi) {
+          const u32 span = hi - lo;
+          const u32 stride = (span + PR_THREADS - 1) / PR_THREADS;
+          const u64 tb = (u64)lo + (u64)(tid + 1) * stride - 1;  // the last candidate of this thread's block
+          const bool live = (u64)lo + (u64)tid * stride < hi;
+          const u32 b = (u32)min(tb, (u64)hi - 1);
+          u32 r = 0, v = 0, pj = 0, w = 0;
+          if (live) {
+            locate(b, r, v);
+            pj = __ldg(s.P + r);
+            w = s.same_w ? pj : __ldg(s.Wt + r);
+            sh.pj[tid] = pj;
+            sh.w[tid] = w;
+          }
+          const bool ok = feasible_at(live, r, pj, w, v);
+          const int ct = __syncthreads_count(ok);
+          if (ct > 0) { lastp = sh.pj[ct - 1]; lastw = sh.w[ct - 1]; }
+          const u32 nlo = (u32)min((u64)lo + (u64)ct * stride, (u64)hi);
+          const u32 nhi = (u32)min((u64)hi, (u64)lo + (u64)(ct + 1) * stride - 1);  // thread ct's last candidate failed
+          __syncthreads();  // sh.pj / sh.w are rewritten by the next round
+          lo = nlo;
+          hi = max(nhi, nlo);
+          if (stride == 1) break;
+        }
+        cnt = lo;
+      }
+      // ---- exchange 2: (feasible boundaries, boundaries, P and Wt at the last feasible one) of every CTA ----
+      if (tid < BS_CLUSTER) {
+        const u32 dst = x2_base + 16u * (ph * 8u + crank);
+        st_async_v4(map_peer(dst, tid), cnt, nb, lastp, lastw, map_peer(bar_x2 + 8u * ph, tid));
+      }
+      mbar_wait_cluster(bar_x2 + 8u * ph, xpar);
+      u32 feas = 0, nbs = 0, bestp = 0;
+      bool any = false;
+#pragma unroll
+      for (int p = 0; p < BS_CLUSTER; ++p) {
+        const uint4 q = *reinterpret_cast<const uint4*>(&sh.x2[ph][p][0]);
+        feas += q.x;
+        nbs += q.y;
+        if (q.x > 0 && (!any || q.z >= bestp)) { any = true; bestp = q.z; pcur = q.z; wcur = q.w; }  // the furthest feasible boundary wins
+      }
+      ++sstep;
+      first = false;
+      jlast += feas;
+      if (feas < nbs) break;                                     // the cost crossed c inside this window
+      if (((u64)g_win + 8u * W) * PR_C >= Ne) break;             // streamed to the end: jlast == n + 1
+      grun += tile_tot;
+      g_win += 8u * W;
+      W = PR_WMAX;                                               // the part is longer than estimated
+      missed = true;
+    }
+    {  // size the next part's window from this part (+1/8 slack, +1 chunk row for the misaligned start)
+      const u32 elems = pcur - e0;
+      const u32 want = (elems + (elems >> 3) + 9u * PR_C - 1u) / (PR_C * BS_CLUSTER);
+      w_est = missed ? (u32)PR_WMAX : max(min(want, (u32)PR_WMAX), w_est > 1u ? w_est - 1u : 1u);
+      W = w_est;
+    }
+    if (k == K) { feasible = (jlast == n1); break; }
+    if (jlast == n1) {
+      if (writer)
+        for (int t = k + 1; t <= K; ++t) spl[t] = (int)n1;
+      feasible = true;
+      break;
+    }
+    if (writer) spl[k + 1] = (int)jlast;
+    j = jlast;
+  }
+  if (writer) {
+    node_c[node] = c;
+    node_res[node] = (!broke && feasible) ? 2 : 1;
+  }
+  if (tid == 0)  // the ring runs ahead of the search: wait for the bulk copies still in flight into this CTA's shared memory
+    for (u32 l = fill_hi > (u32)PR_S ? fill_hi - PR_S : 0u; l < fill_hi; ++l) {
+      if (((u64)l * 8u + crank) * PR_C >= Ne) break;
+      mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (l / PR_S) & 1u);
+    }
+  cluster.sync();  // no CTA may exit while peers can still write into its shared memory
+}
+
 __global__ void k_count_zero(const u32* __restrict__ v, size_t n, u32* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   u32 c = 0;
@@ -999,6 +1393,7 @@ static void stream_view(Oracle& f, DevStream& ds) {
   const Matrix& A = *f.A;
   ds.prev = f.ls->prev.get();
   ds.colidx = f.ls->colidx.get();
+  ds.chunk_col = f.ls->chunk_col.get();
   ds.P = f.ls->P;
   ds.Wt = (f.dev.kind == CPB_MODEL_MONOSYM) ? f.overpos.get() - 1 : A.pos.get() - 1;
   ds.Ne = (u32)f.ls->Ne;
@@ -1128,6 +1523,18 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   return run.release();
 }
 
+// CPB_PROBE_RING=0 selects the register-tile probes (k_probe_stream) instead of the shared-memory ring form
+static bool probe_ring_enabled() {
+  static bool attr_set = false;
+  if (env_int("CPB_PROBE_RING", 1) == 0) return false;
+  if (!attr_set) {
+    CPB_CUDA(cudaFuncSetAttribute(k_probe_ring<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_RING_BYTES));
+    CPB_CUDA(cudaFuncSetAttribute(k_probe_ring<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_RING_BYTES));
+    attr_set = true;
+  }
+  return true;
+}
+
 // probes the nodes [node_lo, node_hi) of the current round's speculation tree
 void bisect_probe(BisectRun& run, int node_lo, int node_hi) {
   node_lo = std::max(node_lo, 0);
@@ -1139,7 +1546,14 @@ void bisect_probe(BisectRun& run, int node_lo, int node_hi) {
   for (int t = node_lo; t < node_hi; ++t) run.speculated += run.h_ids[t] >= 0;
   for (int base = node_lo; base < node_hi; base += (1 << BS_LOCAL_DEPTH)) {
     const int cnt = std::min(node_hi - base, 1 << BS_LOCAL_DEPTH);
-    if (run.stream) {
+    if (run.stream && probe_ring_enabled()) {
+      // algorithmic bytes of one fused pass over the links for the thresholds of this launch
+      ProfScope pk("k_probe_ring", (double)(f.ls->Ne + f.A->n + 1) * 4.0 + (double)cnt * (K + 1) * 8.0);
+      if (f.dev.is_float)
+        CPB_LAUNCH(k_probe_ring<double>, cnt * BS_CLUSTER, PR_THREADS, PR_RING_BYTES, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+      else
+        CPB_LAUNCH(k_probe_ring<i64>, cnt * BS_CLUSTER, PR_THREADS, PR_RING_BYTES, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+    } else if (run.stream) {
       // algorithmic bytes of one fused pass over the links for the thresholds of this launch
       ProfScope pk("k_probe_stream", (double)(f.ls->Ne + f.A->n + 1) * 4.0 + (double)cnt * (K + 1) * 8.0);
       if (f.dev.is_float)
@@ -1168,6 +1582,11 @@ bool bisect_advance(BisectRun& run, bool sync) {
   }
   return run.done;
 }
+
+void bisect_node_buffers(BisectRun& run, int** res, double** c, int** spl, int* P) {
+  *res = run.node_res; *c = run.node_c; *spl = run.node_spl; *P = run.P;
+}
+bool bisect_is_done(BisectRun& run) { return run.done; }
 
 static double g_bisect_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 void bisect_stats(double out[8]) {
@@ -1213,7 +1632,11 @@ int probe_cluster_capacity(bool stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_stream<i64>, &cfg));
+  if (stream && probe_ring_enabled()) {
+    cfg.blockDim = dim3(PR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = PR_RING_BYTES;
+    CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_ring<i64>, &cfg));
+  } else if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_stream<i64>, &cfg));
   else CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_bisect_round<i64>, &cfg));
   return n;
 }

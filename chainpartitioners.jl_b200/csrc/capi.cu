@@ -612,6 +612,93 @@ int cpb_bisect_stats(double out[8]) {
   CPB_API_END
 }
 
+// ---- multi-GPU: library-owned communicator, one solve over all ranks (sharded.cu) ----
+extern "C++" {
+namespace cpb {
+struct ShardedMatrix;
+void comm_unique_id(char out[128]);
+void comm_init(const char id[128], int rank, int world);
+void comm_destroy();
+void comm_info(int* rank, int* world);
+void shard_range(i64 N, int rank, int world, i64* cnt_out, i64* lo_out, i64* hi_out);
+ShardedMatrix* sharded_create(i64 m, i64 n, i64 nnz, const i64* h_colptr, const i64* h_rowval, bool rows_are_block,
+                              void (*h2d)(void*, const void*, size_t));
+void sharded_destroy(ShardedMatrix* S);
+void solve_sharded(ShardedMatrix& S, const cpb_model* mdl, int method, double eps, i64 K, int64_t* h_spl_out);
+void solve_sharded_emulated(Matrix& A, const cpb_model* mdl, int method, double eps, i64 K, int world, int64_t* h_spl_out);
+void sharded_stats(double out[16]);
+}  // namespace cpb
+}  // extern "C++"
+
+int cpb_comm_unique_id(char id_out[128]) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(id_out, "NULL argument");
+  comm_unique_id(id_out);
+  CPB_API_END
+}
+int cpb_comm_init(const char id[128], int rank, int world) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(id, "NULL argument");
+  comm_init(id, rank, world);
+  CPB_API_END
+}
+int cpb_comm_destroy(void) {
+  CPB_API_BEGIN
+  if (cpb::g_ctx.ready) { CPB_CUDA(cudaSetDevice(cpb::g_ctx.device)); comm_destroy(); }
+  CPB_API_END
+}
+int cpb_comm_info(int* rank, int* world) {
+  CPB_API_BEGIN
+  comm_info(rank, world);
+  CPB_API_END
+}
+int cpb_shard_range(int64_t nnz, int rank, int world, int64_t* q_lo, int64_t* q_hi) {
+  CPB_API_BEGIN
+  CPB_REQUIRE(world >= 1 && rank >= 0 && rank < world && nnz >= 0, "bad shard request");
+  i64 lo = 0, hi = 0;
+  shard_range(nnz, rank, world, nullptr, &lo, &hi);
+  if (q_lo) *q_lo = lo;
+  if (q_hi) *q_hi = hi;
+  CPB_API_END
+}
+int cpb_sharded_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, int rowval_is_block, cpb_sharded** out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(out && colptr && (rowval || nnz == 0), "NULL argument");
+  ProfScope prof("h2d_matrix");
+  *out = reinterpret_cast<cpb_sharded*>(sharded_create(m, n, nnz, (const i64*)colptr, (const i64*)rowval, rowval_is_block != 0, h2d_copy));
+  CPB_API_END
+}
+void cpb_sharded_matrix_destroy(cpb_sharded* A) {
+  std::lock_guard<std::mutex> lk(cpb::g_mu);
+  if (cpb::g_ctx.ready) cudaSetDevice(cpb::g_ctx.device);
+  sharded_destroy(reinterpret_cast<ShardedMatrix*>(A));
+}
+int cpb_partition_stripe_sharded(cpb_sharded* A, const cpb_model* mdl, int method, double eps, int64_t K, int64_t* spl_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && mdl && spl_out, "NULL argument");
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  solve_sharded(*reinterpret_cast<ShardedMatrix*>(A), mdl, method, eps, K, spl_out);
+  CPB_API_END
+}
+int cpb_partition_stripe_sharded_emulated(cpb_matrix* A, const cpb_model* mdl, int method, double eps, int64_t K, int world, int64_t* spl_out) {
+  CPB_API_BEGIN
+  ensure_context();
+  CPB_REQUIRE(A && mdl && spl_out, "NULL argument");
+  CPB_REQUIRE(K >= 1, "K must be >= 1");
+  solve_sharded_emulated(A->M, mdl, method, eps, K, world, spl_out);
+  CPB_API_END
+}
+int cpb_sharded_stats(double out[16]) {
+  CPB_API_BEGIN
+  CPB_REQUIRE(out, "NULL argument");
+  sharded_stats(out);
+  CPB_API_END
+}
+
 int cpb_pack_stripe(cpb_matrix* A, cpb_oracle* f, int method, const cpb_constraint* con, double rho, int64_t w_max,
                     int64_t* spl_out, int64_t* K_out, int64_t* n_nets_out) {
   CPB_API_BEGIN

@@ -134,3 +134,12 @@ def partition_stripe_sharded(A, K, method, rank: int = 0, world: int = 1, emulat
         return run.finish()
     finally:
         ocl.close()
+
+
+def library_communicator(cp, dist_mod, rank: int, world: int):
+    """Creates the library-owned NCCL communicator (``cp.Communicator``) on every rank: rank 0 makes the 128-byte id, the
+    ranks receive it through the host framework's own process group (any transport would do -- the id is just bytes)."""
+    uid = [cp.Communicator.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist_mod.broadcast_object_list(uid, src=0)
+    return cp.Communicator(uid[0], rank, world)

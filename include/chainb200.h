@@ -221,6 +221,40 @@ int cpb_bisect_plan(double c_lo, double c_hi, double eps, int nodes, double c_lo
  * out[7] = final c_hi. */
 int cpb_bisect_stats(double out[8]);
 
+/* ---- one stripe solve over several GPUs (one process per GPU) ----------------------------------
+ * The reference has no counterpart (it is single-threaded); these entry points stand where a maintainer would put a
+ * `Distributed`/MPI.jl driver around partition_stripe(A, K, LazyBisectCostBottleneckSplitter(...)) (LazyBisectCost...:140-258).
+ * The communicator is owned by the library (NCCL, loaded at run time): rank 0 obtains the 128-byte id with
+ * cpb_comm_unique_id, ships it to the other ranks by any means (MPI.jl bcast, a file, torch.distributed), and every rank
+ * calls cpb_comm_init after cpb_init(its device).  All sharded calls are COLLECTIVE: every rank makes the same call with
+ * the same matrix, model, K and eps.
+ *
+ * cpb_sharded_matrix_create: every rank passes the complete colptr; of rowval only the rank's block of CSC positions
+ * [q_lo, q_hi) (cpb_shard_range) is read and uploaded -- pass the whole array (rowval_is_block = 0) or just the block
+ * (rowval_is_block = 1, rowval[0] = entry q_lo).
+ * cpb_partition_stripe_sharded: BisectCost / LazyBisectCost with the AffineConnectivityModel.  Link construction by
+ * blocks of CSC positions: local stable sort by row, the per-row "last position" array (m x 4 bytes) carried down the ranks
+ * once (ncclSend/Recv), one in-place all-gather of the link shards (nnz x 4 bytes); bisection rounds of world x 15
+ * thresholds, rank r probing its 15, one all-gather of the per-threshold results per round.  Every rank returns the same
+ * split vector -- the single-GPU (and the reference's) one.
+ * cpb_partition_stripe_sharded_emulated plays `world` ranks one after the other on this GPU (tests; no NCCL).
+ * cpb_sharded_stats: out[0] = world, [1] = host ms until the construction was queued, [2] = ms of the bisection (incl.
+ * waiting for the construction), [3] = bisection rounds, [4] = link all-gather bytes, [5] = carry bytes per hop,
+ * [6] = threshold all-gather bytes, [7] = thresholds per round. */
+typedef struct cpb_sharded cpb_sharded;
+int cpb_comm_unique_id(char id_out[128]);
+int cpb_comm_init(const char id[128], int rank, int world);
+int cpb_comm_destroy(void);
+int cpb_comm_info(int* rank, int* world);
+int cpb_shard_range(int64_t nnz, int rank, int world, int64_t* q_lo, int64_t* q_hi);
+int cpb_sharded_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, int rowval_is_block,
+                              cpb_sharded** out);
+void cpb_sharded_matrix_destroy(cpb_sharded* A);
+int cpb_partition_stripe_sharded(cpb_sharded* A, const cpb_model* mdl, int method, double eps, int64_t K, int64_t* spl_out);
+int cpb_partition_stripe_sharded_emulated(cpb_matrix* A, const cpb_model* mdl, int method, double eps, int64_t K, int world,
+                                          int64_t* spl_out);
+int cpb_sharded_stats(double out[16]);
+
 /* ---- pack_stripe ------------------------------------------------------------------------- */
 enum {
   CPB_PACK_DYNAMIC_TOTAL = 0, /* pack_stripe(A, DynamicTotalChunker(ConstrainedCost(f, w, w_max))[, Pi])  DynamicChunker.jl:20-56 */

@@ -240,6 +240,37 @@ def test_speculation_depth_does_not_change_result(ref, monkeypatch):
         assert np.array_equal(cp.partition_stripe(A, 16, mtd).spl, exp), depth
 
 
+def test_probe_ring_and_register_tile_forms(ref, monkeypatch):
+    """The two streaming-probe kernels (k_probe_ring: shared-memory ring + st.async exchanges, the default; k_probe_stream:
+    register tiles + cluster barriers, CPB_PROBE_RING=0) against the CPU oracle on inputs that span many 4096-element chunks
+    per part, many parts per chunk, long runs of empty columns (more than 4096 boundary candidates per window), the
+    diagonal-augmented stream and Float64 costs."""
+    rng = np.random.default_rng(77)
+    n_sparse = 300_000
+    cols = np.sort(rng.choice(n_sparse, 4000, replace=False))
+    deg = np.zeros(n_sparse, dtype=np.int64)
+    deg[cols] = rng.integers(1, 12, len(cols))
+    colptr = np.concatenate(([1], 1 + np.cumsum(deg)))
+    rowval = np.concatenate([np.sort(rng.choice(5000, d, replace=False)) + 1 for d in deg[cols]])
+    sparse_cols = cp.SparseMatrixCSC(5000, n_sparse, colptr, rowval)
+    sym = cp.AffineMonotonizedSymmetricConnectivityModel(0, 0, 1, 100, 4)
+    cases = [(synth.erdos_renyi(50000, 10), AFF, [7, 64], 0.01), (synth.erdos_renyi(50000, 10), cp.AffineConnectivityModel(0.5, 10.0, 1.0, 100.0), [64], 0.01),
+             (synth.rmat(15, 16 << 15), AFF, [128, 1000], 0.01), (sparse_cols, AFF, [3, 16, 200], 0.05),
+             (sparse_cols, cp.AffineConnectivityModel(0, 1, 0, 0), [16], 0.01), (synth.random_geometric(30000), sym, [32], 0.1),
+             (synth.banded(40000, 40), AFF, [50], 0.01), (synth.laplacian5(150), cp.AffineConnectivityModel(3, 0, 0, 1), [5, 31], 0.001)]
+    for A, f, Ks, eps in cases:
+        dA = cp.device_matrix(A)
+        for K in Ks:
+            for mtd in (cp.LazyBisectCostBottleneckSplitter(f, eps), cp.BisectCostBottleneckSplitter(f, eps)):
+                exp = ref.partition_stripe(A, K, mtd).spl
+                for ring in ("1", "0"):
+                    monkeypatch.setenv("CPB_PROBE_RING", ring)
+                    got = cp.partition_stripe(dA, K, mtd).spl
+                    assert np.array_equal(got, exp), (A.n, K, type(mtd).__name__, "ring=" + ring)
+        monkeypatch.delenv("CPB_PROBE_RING", raising=False)
+        dA.close()
+
+
 def test_device_resident_matrix_and_errors():
     A = synth.laplacian5(16)
     dA = cp.device_matrix(A)
@@ -822,6 +853,23 @@ def test_sharded_bisection_emulated_ranks(ref):
         for world in (1, 2, 4, 8):
             got = parallel.partition_stripe_sharded(M, K, mtd, world=world, emulate_ranks=True)
             assert np.array_equal(got.spl, exp), (type(mtd).__name__, K, world)
+
+
+def test_sharded_solve_emulated_ranks_and_single_rank(ref):
+    """csrc/sharded.cu on one GPU: the block-wise link construction with the carried "last position" array and rounds of
+    world x 15 thresholds, the ranks played one after the other (cpb_partition_stripe_sharded_emulated), and the real entry
+    point with a world of one (no communicator)."""
+    cases = [(synth.erdos_renyi(30000, 10), 16, 0.01), (synth.rmat(14, 16 << 14), 128, 0.01), (synth.laplacian5(40), 7, 0.001),
+             (synth.banded(3000, 20), 5, 0.05), (cp.SparseMatrixCSC(4, 3, [1, 1, 1, 1], np.zeros(0, dtype=np.int64)), 2, 0.1)]
+    for A, K, eps in cases:
+        for mtd in (cp.LazyBisectCostBottleneckSplitter(AFF, eps), cp.BisectCostBottleneckSplitter(cp.AffineConnectivityModel(0.0, 3.0, 1.0, 7.0), eps)):
+            exp = ref.partition_stripe(A, K, mtd).spl
+            for world in (1, 2, 3, 8):
+                got = cp.partition_stripe_sharded_emulated(A, K, mtd, world).spl
+                assert np.array_equal(got, exp), (A.n, K, world)
+            assert np.array_equal(cp.partition_stripe_sharded(A, K, mtd).spl, exp), (A.n, K, "world of one")
+    with pytest.raises(cp.CpbError):
+        cp.partition_stripe_sharded(cases[0][0], 4, cp.LazyBisectCostBottleneckSplitter(cp.AffineWorkModel(0, 1, 1), 0.1))
 
 
 def test_node_slots():
