@@ -775,21 +775,27 @@ __device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mb
 __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// (a wait that never completes -- a protocol bug -- traps after ~2^22 polls instead of hanging the GPU)
+// (a wait that never completes -- a protocol bug -- traps after ~2 s instead of hanging the GPU)
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {  // data written by this CTA's bulk copies
-  u32 ok = 0, spins = 0;
+  u32 ok = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) break;
-    if (++spins > (1u << 22)) __trap();
+    const long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {  // data written by peers' st.async
-  u32 ok = 0, spins = 0;
+  u32 ok = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) break;
-    if (++spins > (1u << 22)) __trap();
+    const long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_bar) {
