@@ -775,8 +775,20 @@ __device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mb
 __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// (a wait that never completes -- a protocol bug -- traps after ~2 s instead of hanging the GPU)
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {  // data written by this CTA's bulk copies
+// A wait that never completes -- a protocol bug -- traps after ~2 s instead of hanging the GPU, after leaving a record
+// (which wait, where) in a host-mapped buffer that bisect_advance appends to the error message.
+__device__ unsigned long long* g_ring_dbg = nullptr;
+__device__ __noinline__ void ring_wait_failed(u32 tag, u32 a, u32 b, u32 c, u32 d) {
+  unsigned long long* g = g_ring_dbg;
+  if (g && atomicCAS(g, 0ull, 1ull) == 0ull) {
+    unsigned cr;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
+    g[1] = tag; g[2] = blockIdx.x; g[3] = cr; g[4] = threadIdx.x; g[5] = a; g[6] = b; g[7] = c; g[8] = d;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, u32 tag = 0, u32 a = 0, u32 b = 0, u32 c = 0, u32 d = 0) {  // this CTA's bulk copies
   u32 ok = 0;
   long long t0 = 0;
   while (true) {
@@ -784,10 +796,10 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {  // data writte
     if (ok) break;
     const long long t = clock64();
     if (t0 == 0) t0 = t;
-    else if (t - t0 > 4000000000ll) __trap();
+    else if (t - t0 > 4000000000ll) ring_wait_failed(tag, a, b, c, d);
   }
 }
-__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {  // data written by peers' st.async
+__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity, u32 tag = 0, u32 a = 0, u32 b = 0, u32 c = 0, u32 d = 0) {  // peers' st.async
   u32 ok = 0;
   long long t0 = 0;
   while (true) {
@@ -795,7 +807,7 @@ __device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {  // dat
     if (ok) break;
     const long long t = clock64();
     if (t0 == 0) t0 = t;
-    else if (t - t0 > 4000000000ll) __trap();
+    else if (t - t0 > 4000000000ll) ring_wait_failed(tag, a, b, c, d);
   }
 }
 __device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_bar) {
@@ -809,6 +821,16 @@ __device__ __forceinline__ void bulk_load(u32 dst, const void* src, u32 bytes, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+
+#ifdef CPB_PROBE_TIMING
+__device__ unsigned long long g_ring_t[16];
+__device__ unsigned long long g_ring_n[8];  // super-steps, parts, few-path steps, many-path steps, empty steps, sum of W
+#define RT(i) do { if (node == 0 && crank == 0 && tid == 0) { unsigned long long _t = clock64(); g_ring_t[i] += _t - rt_last; rt_last = _t; } } while (0)
+#define RN(i, v) do { if (node == 0 && crank == 0 && tid == 0) g_ring_n[i] += (v); } while (0)
+#else
+#define RT(i) do {} while (0)
+#define RN(i, v) do {} while (0)
+#endif
 
 struct PrShared {
   alignas(16) u32 mask[PR_WMAX][PR_G + 1][4];  // `prev < j` bit masks of every group; [.][32] = zero sentinel (offset == chunk size)
@@ -871,7 +893,13 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
     const i64 wj = (i64)wcur;
     u32 jlast = j, grun = 0;
     bool first = true, missed = false;
+    RN(1, 1);
     for (u32 g_win = e0 / PR_C;;) {
+#ifdef CPB_PROBE_TIMING
+      unsigned long long rt_last = clock64();
+#endif
+      RN(0, 1);
+      RN(5, W);
       const u32 ph = sstep & 1u, xpar = (sstep >> 1) & 1u;
       const u32 l0 = (g_win + 7u - crank) >> 3;              // first local chunk of this CTA inside the window
       const u32 p0 = (crank - g_win) & 7u;                   // its position in window order; the others follow at +8
@@ -894,6 +922,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
         }
       }
       fill_hi = max(fill_hi, l0 + PR_S);
+      RT(0);
       // ---- boundaries of this CTA's chunks: chunk [x0, x0 + C) owns the columns boundaries r with x0 < P[r] <= x0 + C ----
       if (tid < (int)W) {
         const u32 g = (l0 + tid) * 8u + crank;
@@ -917,7 +946,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
         unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
         if (gbase < Ne && gbase + 128u > e0) {  // (warp-uniform) the group holds elements of [e0, Ne)
           const u32 slot = l % PR_S;
-          mbar_wait(smem_addr(&sh.mb_full[slot]), (l / PR_S) & 1u);
+          mbar_wait(smem_addr(&sh.mb_full[slot]), (l / PR_S) & 1u, 1u, l, sstep, e0, W);
           const uint4 pv = *reinterpret_cast<const uint4*>(ring + (size_t)slot * PR_C + warp * 128 + lane * 4);
           if (gbase >= e0 && gbase + 128u <= Ne) {
             m0 = __ballot_sync(0xffffffffu, pv.x <= e0);
@@ -937,7 +966,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
           sh.cnt[v][warp] = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
         }
       }
+      RT(1);
       __syncthreads();
+      RT(2);
       // ---- warp v scans chunk v and pushes the chunk total into every CTA's window table ----
       if (warp < (int)W) {
         const u32 t = sh.cnt[warp][lane];
@@ -955,7 +986,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
           st_async_u32(map_peer(dst, lane), tot, map_peer(bar_x1 + 8u * ph, lane));
         }
       }
+      RT(3);
       __syncthreads();
+      RT(4);
       // ---- this CTA's boundary candidates, flat over its W chunks; the offsets of a thread's (at most 4) candidates are
       //      fetched while the totals travel ----
       u32 cn[PR_WMAX + 1], cja[PR_WMAX];
@@ -989,7 +1022,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
           pjv[i] = __ldg(s.P + rv[i]);
           wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + rv[i]);
         }
-      mbar_wait_cluster(bar_x1 + 8u * ph, xpar);
+      RT(5);
+      mbar_wait_cluster(bar_x1 + 8u * ph, xpar, 2u, sstep, W, e0, g_win);
+      RT(6);
       // ---- exclusive prefix of the window's chunk totals (window order), redundantly per warp: lane p and lane p + 32 ----
       u32 excl0, excl1, tile_tot;
       {
@@ -1031,6 +1066,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
         return live && cost_leq(stream_cost<T>(s, (i64)r - (i64)j, (i64)w - wj, (i64)g), c);
       };
       u32 cnt = 0, lastp = 0, lastw = 0;
+      RT(7);
+      RN(few ? 2 : (nb > 0 ? 3 : 4), 1);
       if (few) {
         // every thread tests its LAST candidate; the first thread whose last one fails holds the crossing and tests its
         // remaining ones from registers
@@ -1089,12 +1126,15 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
         }
         cnt = lo;
       }
+      RT(8);
       // ---- exchange 2: (feasible boundaries, boundaries, P and Wt at the last feasible one) of every CTA ----
       if (tid < BS_CLUSTER) {
         const u32 dst = x2_base + 16u * (ph * 8u + crank);
         st_async_v4(map_peer(dst, tid), cnt, nb, lastp, lastw, map_peer(bar_x2 + 8u * ph, tid));
       }
-      mbar_wait_cluster(bar_x2 + 8u * ph, xpar);
+      RT(9);
+      mbar_wait_cluster(bar_x2 + 8u * ph, xpar, 3u, sstep, W, e0, g_win);
+      RT(10);
       u32 feas = 0, nbs = 0, bestp = 0;
       bool any = false;
 #pragma unroll
@@ -1137,7 +1177,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
   if (tid == 0)  // the ring runs ahead of the search: wait for the bulk copies still in flight into this CTA's shared memory
     for (u32 l = fill_hi > (u32)PR_S ? fill_hi - PR_S : 0u; l < fill_hi; ++l) {
       if (((u64)l * 8u + crank) * PR_C >= Ne) break;
-      mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (l / PR_S) & 1u);
+      mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (l / PR_S) & 1u, 4u, l, sstep, fill_hi, 0u);
     }
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
@@ -1244,15 +1284,25 @@ __global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStr
   const u32 e0 = __ldg(s.P + j), e1 = __ldg(s.P + (u32)spl[k + 1]);
   u32 c = 0;
   const u32 stride = gridDim.x * blockDim.x;
-  u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
-  for (; (u64)e + 7ull * stride < e1; e += 8 * stride) {  // eight independent loads in flight per thread (the scalar loop ran at 1.1 TB/s, 8 % SM busy)
-    u32 v[8];
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  // 128-bit loads over the 16-byte aligned middle of [e0, e1), four in flight per thread; scalar head and tail
+  const u32 a0 = min((e0 + 3u) & ~3u, e1), a1 = max(e1 & ~3u, a0);
+  if (t < a0 - e0) c += __ldg(s.prev + e0 + t) <= e0;
+  if (t < e1 - a1) c += __ldg(s.prev + a1 + t) <= e0;
+  const uint4* v4 = reinterpret_cast<const uint4*>(s.prev + a0);
+  const u32 nvec = (a1 - a0) >> 2;
+  u32 i = t;
+  for (; (u64)i + 3ull * stride < nvec; i += 4 * stride) {
+    uint4 v[4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = __ldg(s.prev + e + (u32)t * stride);
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(v4 + i + (u32)u * stride);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) c += v[t] <= e0;
+    for (int u = 0; u < 4; ++u) c += (v[u].x <= e0) + (v[u].y <= e0) + (v[u].z <= e0) + (v[u].w <= e0);
   }
-  for (; e < e1; e += stride) c += __ldg(s.prev + e) <= e0;
+  for (; i < nvec; i += stride) {
+    const uint4 v = __ldg(v4 + i);
+    c += (v.x <= e0) + (v.y <= e0) + (v.z <= e0) + (v.w <= e0);
+  }
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
 }
@@ -1530,10 +1580,23 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
 }
 
 // CPB_PROBE_RING=0 selects the register-tile probes (k_probe_stream) instead of the shared-memory ring form
+static unsigned long long* g_ring_dbg_host = nullptr;
+static std::string ring_debug_string() {
+  if (!g_ring_dbg_host || g_ring_dbg_host[0] == 0) return "";
+  char buf[256];
+  std::snprintf(buf, sizeof(buf), " [ring probe wait timed out: tag=%llu block=%llu crank=%llu tid=%llu a=%llu b=%llu c=%llu d=%llu]", g_ring_dbg_host[1], g_ring_dbg_host[2],
+                g_ring_dbg_host[3], g_ring_dbg_host[4], g_ring_dbg_host[5], g_ring_dbg_host[6], g_ring_dbg_host[7], g_ring_dbg_host[8]);
+  return buf;
+}
 static bool probe_ring_enabled() {
   static bool attr_set = false;
   if (env_int("CPB_PROBE_RING", 1) == 0) return false;
   if (!attr_set) {
+    unsigned long long* d = nullptr;
+    CPB_CUDA(cudaHostAlloc((void**)&g_ring_dbg_host, 128, cudaHostAllocMapped));
+    std::memset(g_ring_dbg_host, 0, 128);
+    CPB_CUDA(cudaHostGetDevicePointer((void**)&d, g_ring_dbg_host, 0));
+    CPB_CUDA(cudaMemcpyToSymbol(g_ring_dbg, &d, sizeof(d)));
     CPB_CUDA(cudaFuncSetAttribute(k_probe_ring<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_RING_BYTES));
     CPB_CUDA(cudaFuncSetAttribute(k_probe_ring<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_RING_BYTES));
     attr_set = true;
@@ -1582,7 +1645,10 @@ bool bisect_advance(BisectRun& run, bool sync) {
   if (sync) {
     CPB_CUDA(cudaMemcpyAsync(&run.h_st, run.st.get(), sizeof(BisectState), cudaMemcpyDeviceToHost, ctx().stream));
     CPB_CUDA(cudaMemcpyAsync(run.h_best.data(), run.best.get(), (run.K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-    CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    {
+      const cudaError_t e = cudaStreamSynchronize(ctx().stream);
+      if (e != cudaSuccess) throw Error(CPB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in the bisection probes" + ring_debug_string());
+    }
     run.done = run.h_st.done != 0;
     run.planned = false;  // the next round is planned from the new bracket
   }
@@ -1611,6 +1677,22 @@ void bisect_finish(BisectRun* run_ptr, int64_t* h_spl_out) {
 }
 
 #ifdef CPB_PROBE_TIMING
+void ring_timing_dump() {
+  unsigned long long t[16], n[8];
+  cudaMemcpyFromSymbol(t, g_ring_t, sizeof(t));
+  cudaMemcpyFromSymbol(n, g_ring_n, sizeof(n));
+  const char* names[11] = {"arm+fill", "chunk ranges+ballots", "sync B1", "chunk scan+push x1", "sync B2", "candidates+P loads", "wait x1", "window scan",
+                           "boundary search", "push x2", "wait x2"};
+  const double ss = (double)std::max<unsigned long long>(n[0], 1);
+  double tot = 0;
+  for (int i = 0; i < 11; ++i) tot += (double)t[i];
+  for (int i = 0; i < 11; ++i) std::printf("ring_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / ss);
+  std::printf("ring_timing total %.1f cycles/super-step; super-steps %llu parts %llu few %llu many %llu empty %llu mean W %.2f\n", tot / ss, n[0], n[1], n[2], n[3], n[4],
+              (double)n[5] / ss);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_ring_t, z, sizeof(t));
+  cudaMemcpyToSymbol(g_ring_n, z, sizeof(n));
+}
 void probe_timing_dump() {
   unsigned long long t[8], n;
   cudaMemcpyFromSymbol(t, g_probe_t, sizeof(t));
@@ -1729,10 +1811,13 @@ void solve_bisect(Oracle& f, bool lazy, double eps, i64 K, int64_t* h_spl_out) {
     delete run;
     throw;
   }
+#ifdef CPB_PROBE_TIMING
+  const bool run_was_ring = run->stream && probe_ring_enabled();
+#endif
   bisect_finish(run, h_spl_out);
   trace_mark("finish");
 #ifdef CPB_PROBE_TIMING
-  if (env_int("CPB_PROBE_TIMING_DUMP", 0)) probe_timing_dump();
+  if (env_int("CPB_PROBE_TIMING_DUMP", 0)) { if (run_was_ring) ring_timing_dump(); else probe_timing_dump(); }
 #endif
 }
 

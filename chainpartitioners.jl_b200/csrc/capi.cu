@@ -212,51 +212,87 @@ int cpb_synchronize(void) {
 
 // Host -> device copy of a caller's array.  Pinned (registered) memory goes straight to cudaMemcpyAsync.
 // Pageable memory -- what a Julia Array is -- would be staged by the driver through one internal buffer by
-// one thread (~10 GB/s measured); instead several host threads copy 32 MiB chunks into three pinned staging
-// buffers while the previous chunks are in flight over PCIe.
+// one thread (~10 GB/s measured); instead a pool of host threads (hostpack.cpp) copies chunks into pinned staging
+// buffers while the previous chunks are in flight over PCIe.  Int64 index arrays are NARROWED while they are staged
+// (upload_index_array below): half the PCIe bytes.
 static constexpr size_t H2D_CHUNK = (size_t)32 << 20;
-static constexpr int H2D_BUFS = 3;
-static void* g_stage[H2D_BUFS] = {nullptr, nullptr, nullptr};
-static cudaEvent_t g_stage_ev[H2D_BUFS] = {nullptr, nullptr, nullptr};
-static bool g_stage_busy[H2D_BUFS] = {false, false, false};
+static constexpr size_t PACK_CHUNK_ELEMS = (size_t)2 << 20;  // 8 MB staged / 16 MB of Int64 source per chunk
+static constexpr int H2D_BUFS = 4;
+static void* g_stage[H2D_BUFS] = {nullptr, nullptr, nullptr, nullptr};
+static cudaEvent_t g_stage_ev[H2D_BUFS] = {nullptr, nullptr, nullptr, nullptr};
+static bool g_stage_busy[H2D_BUFS] = {false, false, false, false};
+static int g_stage_next = 0;
 
-static void h2d_copy(void* d_dst, const void* h_src, size_t bytes) {
-  if (bytes == 0) return;
+extern "C++" {
+namespace cpb {
+void host_copy(void* dst, const void* src, size_t bytes);            // hostpack.cpp
+uint64_t host_pack(uint32_t* dst, const int64_t* src, size_t n);     // hostpack.cpp
+}
+}
+
+static bool host_pinned(const void* p) {
   cudaPointerAttributes attr{};
-  const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();  // unregistered memory may set a sticky-free error on old drivers
+  return pinned;
+}
+static bool staging_disabled() {
   static const bool disabled = std::getenv("CPB_NO_STAGED_H2D") != nullptr;
-  if (pinned || bytes < 2 * H2D_CHUNK || disabled) {
-    CPB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx().stream));
-    return;
-  }
+  return disabled;
+}
+// next staging buffer, free to be overwritten by the host
+static int stage_acquire() {
   for (int b = 0; b < H2D_BUFS; ++b)
     if (!g_stage[b]) {
       CPB_CUDA(cudaHostAlloc(&g_stage[b], H2D_CHUNK, cudaHostAllocDefault));
       CPB_CUDA(cudaEventCreateWithFlags(&g_stage_ev[b], cudaEventDisableTiming));
     }
-  const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
-  const int T = (int)std::min<unsigned>(8, std::max(1u, hc / 2));
-  size_t off = 0;
-  for (int i = 0; off < bytes; ++i) {
-    const int b = i % H2D_BUFS;
-    const size_t sz = std::min(H2D_CHUNK, bytes - off);
-    if (g_stage_busy[b]) CPB_CUDA(cudaEventSynchronize(g_stage_ev[b]));  // the copy that last used this buffer (maybe in an earlier call) has finished
-    const char* src = (const char*)h_src + off;
-    char* dst = (char*)g_stage[b];
-    std::vector<std::thread> th;
-    const size_t slice = ((sz + T - 1) / T + 63) & ~(size_t)63;
-    for (int t = 1; t < T; ++t) {
-      const size_t o = (size_t)t * slice;
-      if (o < sz) th.emplace_back([=] { std::memcpy(dst + o, src + o, std::min(slice, sz - o)); });
-    }
-    std::memcpy(dst, src, std::min(slice, sz));
-    for (auto& x : th) x.join();
-    CPB_CUDA(cudaMemcpyAsync((char*)d_dst + off, g_stage[b], sz, cudaMemcpyHostToDevice, ctx().stream));
-    CPB_CUDA(cudaEventRecord(g_stage_ev[b], ctx().stream));
-    g_stage_busy[b] = true;
-    off += sz;
+  const int b = g_stage_next;
+  g_stage_next = (g_stage_next + 1) % H2D_BUFS;
+  if (g_stage_busy[b]) CPB_CUDA(cudaEventSynchronize(g_stage_ev[b]));  // the copy that last used this buffer (maybe in an earlier call) has finished
+  return b;
+}
+static void stage_release(int b) {
+  CPB_CUDA(cudaEventRecord(g_stage_ev[b], ctx().stream));
+  g_stage_busy[b] = true;
+}
+
+static void h2d_copy(void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return;
+  if (host_pinned(h_src) || bytes < 2 * H2D_CHUNK || staging_disabled()) {
+    CPB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx().stream));
+    return;
   }
+  for (size_t off = 0; off < bytes; off += H2D_CHUNK) {
+    const int b = stage_acquire();
+    const size_t sz = std::min(H2D_CHUNK, bytes - off);
+    host_copy(g_stage[b], (const char*)h_src + off, sz);
+    CPB_CUDA(cudaMemcpyAsync((char*)d_dst + off, g_stage[b], sz, cudaMemcpyHostToDevice, ctx().stream));
+    stage_release(b);
+  }
+}
+
+// 1-based Int64 host index array -> 0-based u32 device array, range-checked ([lo, hi], flags |= 1 on the device).
+// Pageable sources are narrowed to 32 bits by the host pool while they are staged, the decrement + check runs per chunk
+// on the device behind its copy; pinned sources go over the bus as they are and are narrowed on the device.
+static void upload_index_array(const i64* h_src, size_t n, u32* d_dst, i64 lo, i64 hi, u32* d_flags) {
+  if (n == 0) return;
+  if (host_pinned(h_src) || n < PACK_CHUNK_ELEMS || staging_disabled() || std::getenv("CPB_NO_HOST_PACK")) {
+    DBuf<i64> wide(n);
+    h2d_copy(wide.get(), h_src, n * sizeof(i64));
+    narrow_minus1(wide.get(), d_dst, n, lo, hi, d_flags);
+    return;
+  }
+  uint64_t acc = 0;
+  for (size_t off = 0; off < n; off += PACK_CHUNK_ELEMS) {
+    const int b = stage_acquire();
+    const size_t cnt = std::min(PACK_CHUNK_ELEMS, n - off);
+    acc |= host_pack((uint32_t*)g_stage[b], reinterpret_cast<const int64_t*>(h_src + off), cnt);
+    CPB_CUDA(cudaMemcpyAsync(d_dst + off, g_stage[b], cnt * sizeof(u32), cudaMemcpyHostToDevice, ctx().stream));
+    stage_release(b);
+    dec_check_u32(d_dst + off, cnt, lo, hi, d_flags);
+  }
+  CPB_REQUIRE((acc >> 31) == 0, "colptr/rowval entry out of range (expected 1-based indices below 2^31)");
 }
 
 extern "C++" {
@@ -303,12 +339,24 @@ int cpb_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* colptr, 
   ensure_context();
   CPB_REQUIRE(out && colptr && (rowval || nnz == 0), "NULL argument");
   CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
+  CPB_REQUIRE(nnz + n + 1 < ((i64)1 << 31) && m < ((i64)1 << 31) - 2 && n < ((i64)1 << 31) - 2, "matrix too large for the 32-bit device index");
   ProfScope prof("h2d_matrix", (double)(nnz + n + 1) * 8.0);
-  DBuf<i64> dc((size_t)n + 1), dr((size_t)nnz);
-  h2d_copy(dc.get(), colptr, ((size_t)n + 1) * sizeof(i64));
-  h2d_copy(dr.get(), rowval, (size_t)nnz * sizeof(i64));
   auto h = std::make_unique<cpb_matrix>();
-  matrix_from_device(h->M, m, n, nnz, dc.get(), dr.get());
+  Matrix& M = h->M;
+  M.m = m; M.n = n; M.N = nnz;
+  M.pos.alloc((size_t)n + 1);
+  M.row.alloc((size_t)nnz);
+  DBuf<u32> flags(1);
+  flags.zero();
+  upload_index_array((const i64*)colptr, (size_t)n + 1, M.pos.get(), 1, nnz + 1, flags.get());
+  upload_index_array((const i64*)rowval, (size_t)nnz, M.row.get(), 1, m, flags.get());
+  check_monotone(M.pos.get(), (size_t)n + 1, flags.get());
+  u32 hf = 0;
+  CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
+  CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  CPB_REQUIRE((hf & 1u) == 0, "colptr/rowval entry out of range (expected 1-based indices)");
+  CPB_REQUIRE((hf & 2u) == 0, "colptr is not non-decreasing");
+  CPB_REQUIRE(colptr[0] == 1 && colptr[n] == nnz + 1, "colptr[1] must be 1 and colptr[n+1] must be nnz+1");
   *out = h.release();
   CPB_API_END
 }
@@ -622,7 +670,7 @@ void comm_destroy();
 void comm_info(int* rank, int* world);
 void shard_range(i64 N, int rank, int world, i64* cnt_out, i64* lo_out, i64* hi_out);
 ShardedMatrix* sharded_create(i64 m, i64 n, i64 nnz, const i64* h_colptr, const i64* h_rowval, bool rows_are_block,
-                              void (*h2d)(void*, const void*, size_t));
+                              void (*upload)(const i64*, size_t, u32*, i64, i64, u32*));
 void sharded_destroy(ShardedMatrix* S);
 void solve_sharded(ShardedMatrix& S, const cpb_model* mdl, int method, double eps, i64 K, int64_t* h_spl_out);
 void solve_sharded_emulated(Matrix& A, const cpb_model* mdl, int method, double eps, i64 K, int world, int64_t* h_spl_out);
@@ -668,7 +716,7 @@ int cpb_sharded_matrix_create(int64_t m, int64_t n, int64_t nnz, const int64_t* 
   ensure_context();
   CPB_REQUIRE(out && colptr && (rowval || nnz == 0), "NULL argument");
   ProfScope prof("h2d_matrix");
-  *out = reinterpret_cast<cpb_sharded*>(sharded_create(m, n, nnz, (const i64*)colptr, (const i64*)rowval, rowval_is_block != 0, h2d_copy));
+  *out = reinterpret_cast<cpb_sharded*>(sharded_create(m, n, nnz, (const i64*)colptr, (const i64*)rowval, rowval_is_block != 0, upload_index_array));
   CPB_API_END
 }
 void cpb_sharded_matrix_destroy(cpb_sharded* A) {

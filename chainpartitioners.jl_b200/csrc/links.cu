@@ -259,16 +259,26 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   if (row_lo <= 0 && row_hi >= (i64)nrow && N && nrow && !no_lt) {
     DBuf<u32> cur((size_t)nrow + 1);  // per-row counts -> segment starts -> (after the fill) segment ends; [nrow] = max degree
     CPB_CUDA(cudaMemsetAsync(cur.get(), 0, ((size_t)nrow + 1) * sizeof(u32), ctx().stream));
-    {
-      ProfScope pk("k_lt_count", (double)N * 4.0);
-      CPB_LAUNCH(k_lt_count, grid_for(N), 256, 0, row, N, cur.get());
-    }
-    CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
     u32 seen_deg = 0;
-    if (!defer_check) {
+    size_t counted = 0;
+    if (!defer_check && N >= ((size_t)1 << 25)) {
+      // large pattern, degree not known: count a 1/16 prefix first -- a power-law matrix shows its heavy rows at once and
+      // goes to the sort without paying for the whole histogram (2.9 ms at 2.6e8 nonzeros)
+      counted = N / 16;
+      ProfScope pk("k_lt_count", (double)counted * 4.0);
+      CPB_LAUNCH(k_lt_count, grid_for(counted), 256, 0, row, counted, cur.get());
+      CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
       seen_deg = read_u32(cur.get() + nrow);
-      if (max_deg_cache) *max_deg_cache = (i64)seen_deg;
     }
+    if (seen_deg <= LT_MAX_DEG) {
+      {
+        ProfScope pk("k_lt_count", (double)(N - counted) * 4.0);
+        CPB_LAUNCH(k_lt_count, grid_for(N - counted), 256, 0, row + counted, N - counted, cur.get());
+      }
+      CPB_LAUNCH(k_lt_max, grid_for(nrow), 256, 0, cur.get(), (size_t)nrow, cur.get() + nrow);
+      if (!defer_check) seen_deg = read_u32(cur.get() + nrow);
+    }
+    if (!defer_check && max_deg_cache) *max_deg_cache = (i64)seen_deg;  // (a lower bound when the prefix already exceeded the limit)
     if (defer_check || seen_deg <= LT_MAX_DEG) {
       exclusive_scan_u32(cur.get(), cur.get(), (size_t)nrow);
       DBuf<u32> T(N);

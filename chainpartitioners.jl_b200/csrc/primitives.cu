@@ -342,6 +342,22 @@ void narrow_minus1(const i64* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flag
   CPB_LAUNCH(k_narrow_minus1, grid, 256, 0, src, dst, n, lo, hi, flags);
 }
 
+__global__ void k_dec_check_u32(u32* v, size_t n, i64 lo, i64 hi, u32* flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const i64 x = (i64)v[i];
+    bad |= (x < lo) | (x > hi);
+    v[i] = (u32)(x - 1);
+  }
+  if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+}
+void dec_check_u32(u32* v, size_t n, i64 lo, i64 hi, u32* flags) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx().sm_count * 16);
+  CPB_LAUNCH(k_dec_check_u32, grid, 256, 0, v, n, lo, hi, flags);
+}
+
 __global__ void k_check_monotone(const u32* __restrict__ pos, size_t n, u32* flags) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   bool bad = false;

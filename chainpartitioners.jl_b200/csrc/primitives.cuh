@@ -21,6 +21,8 @@ void radix_partition_pass(const u32* keys_in, const u32* vals_in, u32* keys_out,
 // dst[i] = (u32)(src[i] - 1); flags[0] |= 1 if any src[i] outside [lo, hi]
 void narrow_minus1(const i64* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flags);
 void narrow32_minus1(const int* src, u32* dst, size_t n, i64 lo, i64 hi, u32* flags);  // the same from Int32 indices
+// in place: v[i] -= 1; flags[0] |= 1 if any v[i] (before the decrement) outside [lo, hi]
+void dec_check_u32(u32* v, size_t n, i64 lo, i64 hi, u32* flags);
 // flags[0] |= 2 if pos is not non-decreasing
 void check_monotone(const u32* pos, size_t n, u32* flags);
 void iota_u32(u32* dst, size_t n);

@@ -281,7 +281,7 @@ std::unique_ptr<LinkStream> emulated_sharded_link_stream(const Matrix& A, int wo
 }
 
 ShardedMatrix* sharded_create(i64 m, i64 n, i64 nnz, const i64* h_colptr, const i64* h_rowval, bool rows_are_block,
-                              void (*h2d)(void*, const void*, size_t)) {
+                              void (*upload)(const i64*, size_t, u32*, i64, i64, u32*)) {
   CPB_REQUIRE(g_comm != nullptr || g_world == 1, "call cpb_comm_init first");
   CPB_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative dimension");
   CPB_REQUIRE(nnz + n + 1 < ((i64)1 << 31) && m < ((i64)1 << 31) - 2 && n < ((i64)1 << 31) - 2, "matrix too large for the 32-bit device index");
@@ -291,15 +291,12 @@ ShardedMatrix* sharded_create(i64 m, i64 n, i64 nnz, const i64* h_colptr, const 
   S->M.m = m; S->M.n = n; S->M.N = nnz;
   shard_range(nnz, g_rank, g_world, &S->cnt, &S->q_lo, &S->q_hi);
   const size_t cntL = (size_t)(S->q_hi - S->q_lo);
-  DBuf<i64> dc((size_t)n + 1), dr(std::max<size_t>(cntL, 1));
-  h2d(dc.get(), h_colptr, ((size_t)n + 1) * sizeof(i64));
-  if (cntL) h2d(dr.get(), rows_are_block ? h_rowval : h_rowval + S->q_lo, cntL * sizeof(i64));
   S->M.pos.alloc((size_t)n + 1);
   S->row_blk.alloc(std::max<size_t>(cntL, 1));
   DBuf<u32> flags(1);
   flags.zero();
-  narrow_minus1(dc.get(), S->M.pos.get(), (size_t)n + 1, 1, nnz + 1, flags.get());
-  narrow_minus1(dr.get(), S->row_blk.get(), cntL, 1, m, flags.get());
+  upload(h_colptr, (size_t)n + 1, S->M.pos.get(), 1, nnz + 1, flags.get());
+  if (cntL) upload(rows_are_block ? h_rowval : h_rowval + S->q_lo, cntL, S->row_blk.get(), 1, m, flags.get());
   check_monotone(S->M.pos.get(), (size_t)n + 1, flags.get());
   u32 hf = 0;
   CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));

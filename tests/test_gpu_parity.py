@@ -901,3 +901,25 @@ def test_c_abi_example_binary(ref):
     assert list(map(int, lines["spl"].split())) == exp.spl.tolist()
     assert tuple(map(float, lines["bound"].split())) == ref.bound_stripe(A, K, AFF)
     assert float(lines["value"]) == ref.bottleneck_value(A, exp, AFF)
+    # the other ABI families, each called from plain C
+    assert list(map(int, lines["spl_exact"].split())) == ref.partition_stripe(A, K, cp.BisectIndexBottleneckSplitter(AFF)).spl.tolist()
+    Q, n = 6, A.n
+    qj = np.array([1 + (n * t) // (2 * Q) for t in range(Q)])
+    qjp = np.array([n + 1 - (n * t) // (3 * Q) for t in range(Q)])
+    assert list(map(float, lines["queries"].split())) == ref.oracle_query(AFF, A, qj, qjp).tolist()
+    assert list(map(int, lines["nets"].split())) == ref.netcount(A, qj, qjp).tolist()
+    chunker = cp.DynamicTotalChunker(cp.ConstrainedCost(AFF, cp.VertexCount(), 8))
+    Pc = ref.pack_stripe(A, chunker)
+    tok = lines["chunks"].split()
+    assert int(tok[0]) == Pc.K and float(tok[2]) == ref.total_value(A, Pc, AFF) and list(map(int, tok[4:])) == Pc.spl[: min(Pc.K, 8) + 1].tolist()
+    nn = []
+    Po = ref.pack_stripe(A, cp.OverlapChunker(0.9, 8), n_nets=nn)
+    tok = lines["overlap"].split()
+    assert int(tok[0]) == Po.K and int(tok[2]) == int(np.sum(nn[0]))
+    At = ref.adjointpattern(A)
+    tok = lines["adjoint"].split()
+    assert (int(tok[0]), int(tok[1]), int(tok[2])) == (At.m, At.n, At.nnz + 1)
+    assert int(tok[4]) == int(np.sum((np.arange(At.nnz) % 7 + 1) * At.rowval))
+    dom = ref.dominancecount(A, [A.m // 2 + 1, A.m + 1], [A.n // 3 + 1, A.n + 1])
+    assert list(map(int, lines["dominance"].split())) == dom.tolist()
+    assert list(map(int, lines["spl_sharded"].split())) == ref.partition_stripe(A, K, cp.LazyBisectCostBottleneckSplitter(AFF, eps)).spl.tolist()
