@@ -450,6 +450,64 @@ template <class T> __device__ __forceinline__ T stream_cost(const DevStream& s, 
   return C::get(s, 0) + (T)nv * C::get(s, 1) + (T)w * C::get(s, 2) + (T)g * C::get(s, 3);
 }
 
+// ---- cluster exchange / bulk copy primitives (PTX) ----
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 map_peer(u32 addr, u32 rank) {
+  u32 r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// A wait that never completes -- a protocol bug -- traps after ~2 s instead of hanging the GPU, after leaving a record
+// (which wait, where) in a host-mapped buffer that bisect_advance appends to the error message.
+__device__ unsigned long long* g_ring_dbg = nullptr;
+__device__ __noinline__ void ring_wait_failed(u32 tag, u32 a, u32 b, u32 c, u32 d) {
+  unsigned long long* g = g_ring_dbg;
+  if (g && atomicCAS(g, 0ull, 1ull) == 0ull) {
+    unsigned cr;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
+    g[1] = tag; g[2] = blockIdx.x; g[3] = cr; g[4] = threadIdx.x; g[5] = a; g[6] = b; g[7] = c; g[8] = d;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, u32 tag = 0, u32 a = 0, u32 b = 0, u32 c = 0, u32 d = 0) {  // this CTA's bulk copies
+  u32 ok = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    const long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000ll) ring_wait_failed(tag, a, b, c, d);
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity, u32 tag = 0, u32 a = 0, u32 b = 0, u32 c = 0, u32 d = 0) {  // peers' st.async
+  u32 ok = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    const long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000ll) ring_wait_failed(tag, a, b, c, d);
+  }
+}
+__device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(u32 remote_addr, u32 a, u32 b, u32 c, u32 d, u32 remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr), "r"(a), "r"(b),
+               "r"(c), "r"(d), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 #ifdef CPB_PROBE_TIMING
 __device__ unsigned long long g_probe_t[8];
 __device__ unsigned long long g_probe_n;
@@ -459,7 +517,9 @@ __device__ unsigned long long g_probe_parts[4];  // per slot 0..3: parts started
 #define PT(i) do {} while (0)
 #endif
 
-template <class T>
+// AX: the two exchanges of a super-step as remote st.async stores that complete a transaction count on every peer's
+// mbarrier (no barrier.cluster, no fence in front of it, no L1 invalidation); !AX: DSMEM stores + cluster barriers.
+template <class T, bool AX>
 __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS, 1)
     k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
                    int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c,
@@ -470,6 +530,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   __shared__ int s_valid;
   __shared__ u32 s_xa[2][BS_CLUSTER];     // per-CTA `prev < j` totals of the tile
   __shared__ u32 s_xb[2][4][BS_CLUSTER];  // per-CTA (feasible boundaries, boundaries, P and Wt at the last feasible one)
+  __shared__ __align__(16) u32 s_xv[2][BS_CLUSTER][4];  // the same, one 16-byte record per CTA (AX)
+  __shared__ __align__(8) unsigned long long s_mb[2][2];  // [exchange][super-step parity] (AX)
   __shared__ u32 s_pj[2 * SP_THREADS];    // (P, Wt) of every thread's boundary candidate, pass 1 | pass 2
   __shared__ u32 s_w[2 * SP_THREADS];
   __shared__ u32 s_wtot[32];              // per-warp `prev < j` totals of the tile
@@ -483,12 +545,19 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     s_valid = node_threshold(st, eps1, node_ids[node], &s_c);
     for (int k = 0; k < 4; ++k) s_mask[SP_GROUPS * 4 + k] = 0;
     for (int k = 0; k < 4; ++k) { s_red[0][k] = 0; s_red[1][k] = 0; }
+    if (AX) {
+      for (int x = 0; x < 2; ++x)
+        for (int p = 0; p < 2; ++p) mbar_init(smem_addr(&s_mb[x][p]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
   }
   __syncthreads();
   if (!s_valid) {
     if (writer) node_res[node] = 0;
     return;
   }
+  if (AX) cluster.sync();  // every CTA's mbarriers exist before a peer's st.async can reach them
+  u32 sstep = 0;
   const double c = s_c;
   const u32 n1 = s.n + 1;
   const u32 Ne = s.Ne;
@@ -593,8 +662,14 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         }
       }
       PT(2);
-      if (tid < BS_CLUSTER) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
-      cluster.barrier_arrive();  // split barrier: the boundary offsets below are fetched while the totals travel
+      const u32 xpar = (sstep >> 1) & 1u;
+      if (AX) {
+        if (tid == 0) { mbar_expect_tx(smem_addr(&s_mb[0][ph]), 4u * BS_CLUSTER); mbar_expect_tx(smem_addr(&s_mb[1][ph]), 16u * BS_CLUSTER); }
+        if (tid < BS_CLUSTER) st_async_u32(map_peer(smem_addr(&s_xa[ph][crank]), tid), tot_c, map_peer(smem_addr(&s_mb[0][ph]), tid));
+      } else {
+        if (tid < BS_CLUSTER) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
+        cluster.barrier_arrive();  // split barrier: the boundary offsets below are fetched while the totals travel
+      }
       const u32 nb = (jb >= ja) ? jb - ja + 1 : 0;
       // thread t owns the (at most 4) consecutive boundaries [t * per, (t + 1) * per) when the CTA has at most 4096 of
       // them: all loaded up front (one memory latency), before the barrier completes
@@ -609,7 +684,12 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
           pjv[i] = __ldg(s.P + ja + b0 + i);
           wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + ja + b0 + i);
         }
-      cluster.barrier_wait();  // also orders s_cum for the boundary phase
+      if (AX) {
+        __syncthreads();  // s_cum (every warp added its base) is complete for the boundary phase
+        mbar_wait_cluster(smem_addr(&s_mb[0][ph]), xpar, 5u, sstep, nv, e0, e_tile);
+      } else {
+        cluster.barrier_wait();  // also orders s_cum for the boundary phase
+      }
       PT(3);
       u32 base_c = 0, tile_tot = 0;
 #pragma unroll
@@ -693,22 +773,36 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         }
       }
       PT(4);
-      if (tid < BS_CLUSTER) {
-        *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
-        *cluster.map_shared_rank(&s_xb[ph][1][crank], tid) = nb;
-        *cluster.map_shared_rank(&s_xb[ph][2][crank], tid) = lastp;
-        *cluster.map_shared_rank(&s_xb[ph][3][crank], tid) = lastw;
-      }
-      cluster.sync();
-      PT(5);
       u32 feas = 0, nbs = 0;
+      if (AX) {
+        if (tid < BS_CLUSTER) st_async_v4(map_peer(smem_addr(&s_xv[ph][crank][0]), tid), cnt, nb, lastp, lastw, map_peer(smem_addr(&s_mb[1][ph]), tid));
+        mbar_wait_cluster(smem_addr(&s_mb[1][ph]), xpar, 6u, sstep, nv, e0, e_tile);
+        PT(5);
 #pragma unroll
-      for (int p = 0; p < BS_CLUSTER; ++p) {
-        const u32 cp = s_xb[ph][0][p];
-        feas += cp;
-        nbs += s_xb[ph][1][p];
-        if (cp > 0) { pcur = s_xb[ph][2][p]; wcur = s_xb[ph][3][p]; }  // the last CTA with a feasible boundary wins
+        for (int p = 0; p < BS_CLUSTER; ++p) {
+          const uint4 q = *reinterpret_cast<const uint4*>(&s_xv[ph][p][0]);
+          feas += q.x;
+          nbs += q.y;
+          if (q.x > 0) { pcur = q.z; wcur = q.w; }  // the last CTA with a feasible boundary wins
+        }
+      } else {
+        if (tid < BS_CLUSTER) {
+          *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
+          *cluster.map_shared_rank(&s_xb[ph][1][crank], tid) = nb;
+          *cluster.map_shared_rank(&s_xb[ph][2][crank], tid) = lastp;
+          *cluster.map_shared_rank(&s_xb[ph][3][crank], tid) = lastw;
+        }
+        cluster.sync();
+        PT(5);
+#pragma unroll
+        for (int p = 0; p < BS_CLUSTER; ++p) {
+          const u32 cp = s_xb[ph][0][p];
+          feas += cp;
+          nbs += s_xb[ph][1][p];
+          if (cp > 0) { pcur = s_xb[ph][2][p]; wcur = s_xb[ph][3][p]; }  // the last CTA with a feasible boundary wins
+        }
       }
+      ++sstep;
       ph ^= 1;
       first = false;
       jlast += feas;
@@ -764,63 +858,6 @@ static constexpr int PR_S = 12;        // ring slots per CTA (192 KB)
 static constexpr int PR_WMAX = 6;      // chunks per CTA per super-step
 static constexpr int PR_G = 32;        // 128-element groups per chunk = warps per CTA
 static constexpr size_t PR_RING_BYTES = (size_t)PR_S * PR_C * sizeof(u32);
-
-__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ u32 map_peer(u32 addr, u32 rank) {
-  u32 r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// A wait that never completes -- a protocol bug -- traps after ~2 s instead of hanging the GPU, after leaving a record
-// (which wait, where) in a host-mapped buffer that bisect_advance appends to the error message.
-__device__ unsigned long long* g_ring_dbg = nullptr;
-__device__ __noinline__ void ring_wait_failed(u32 tag, u32 a, u32 b, u32 c, u32 d) {
-  unsigned long long* g = g_ring_dbg;
-  if (g && atomicCAS(g, 0ull, 1ull) == 0ull) {
-    unsigned cr;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
-    g[1] = tag; g[2] = blockIdx.x; g[3] = cr; g[4] = threadIdx.x; g[5] = a; g[6] = b; g[7] = c; g[8] = d;
-    __threadfence_system();
-  }
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, u32 tag = 0, u32 a = 0, u32 b = 0, u32 c = 0, u32 d = 0) {  // this CTA's bulk copies
-  u32 ok = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    const long long t = clock64();
-    if (t0 == 0) t0 = t;
-    else if (t - t0 > 4000000000ll) ring_wait_failed(tag, a, b, c, d);
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity, u32 tag = 0, u32 a = 0, u32 b = 0, u32 c = 0, u32 d = 0) {  // peers' st.async
-  u32 ok = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    const long long t = clock64();
-    if (t0 == 0) t0 = t;
-    else if (t - t0 > 4000000000ll) ring_wait_failed(tag, a, b, c, d);
-  }
-}
-__device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void st_async_v4(u32 remote_addr, u32 a, u32 b, u32 c, u32 d, u32 remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr), "r"(a), "r"(b),
-               "r"(c), "r"(d), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void bulk_load(u32 dst, const void* src, u32 bytes, u32 bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
 
 #ifdef CPB_PROBE_TIMING
 __device__ unsigned long long g_ring_t[16];
@@ -1588,15 +1625,23 @@ static std::string ring_debug_string() {
                 g_ring_dbg_host[3], g_ring_dbg_host[4], g_ring_dbg_host[5], g_ring_dbg_host[6], g_ring_dbg_host[7], g_ring_dbg_host[8]);
   return buf;
 }
+// the host-mapped record a timed-out wait leaves (see ring_wait_failed)
+static void ring_debug_arm() {
+  if (g_ring_dbg_host) return;
+  unsigned long long* d = nullptr;
+  CPB_CUDA(cudaHostAlloc((void**)&g_ring_dbg_host, 128, cudaHostAllocMapped));
+  std::memset(g_ring_dbg_host, 0, 128);
+  CPB_CUDA(cudaHostGetDevicePointer((void**)&d, g_ring_dbg_host, 0));
+  CPB_CUDA(cudaMemcpyToSymbol(g_ring_dbg, &d, sizeof(d)));
+}
+static void check_probes(cudaError_t e) {
+  if (e != cudaSuccess) throw Error(CPB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in the bisection probes" + ring_debug_string());
+}
 static bool probe_ring_enabled() {
   static bool attr_set = false;
-  if (env_int("CPB_PROBE_RING", 1) == 0) return false;
+  if (env_int("CPB_PROBE_RING", 0) == 0) return false;
   if (!attr_set) {
-    unsigned long long* d = nullptr;
-    CPB_CUDA(cudaHostAlloc((void**)&g_ring_dbg_host, 128, cudaHostAllocMapped));
-    std::memset(g_ring_dbg_host, 0, 128);
-    CPB_CUDA(cudaHostGetDevicePointer((void**)&d, g_ring_dbg_host, 0));
-    CPB_CUDA(cudaMemcpyToSymbol(g_ring_dbg, &d, sizeof(d)));
+    ring_debug_arm();
     CPB_CUDA(cudaFuncSetAttribute(k_probe_ring<i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_RING_BYTES));
     CPB_CUDA(cudaFuncSetAttribute(k_probe_ring<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PR_RING_BYTES));
     attr_set = true;
@@ -1625,10 +1670,15 @@ void bisect_probe(BisectRun& run, int node_lo, int node_hi) {
     } else if (run.stream) {
       // algorithmic bytes of one fused pass over the links for the thresholds of this launch
       ProfScope pk("k_probe_stream", (double)(f.ls->Ne + f.A->n + 1) * 4.0 + (double)cnt * (K + 1) * 8.0);
+      const bool ax = env_int("CPB_PROBE_ASYNC", 1) != 0;  // exchanges by st.async + mbarrier (0: DSMEM stores + cluster barriers)
+      ring_debug_arm();
       if (f.dev.is_float)
-        CPB_LAUNCH(k_probe_stream<double>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+        if (ax) CPB_LAUNCH((k_probe_stream<double, true>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+        else CPB_LAUNCH((k_probe_stream<double, false>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+      else if (ax)
+        CPB_LAUNCH((k_probe_stream<i64, true>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
       else
-        CPB_LAUNCH(k_probe_stream<i64>, cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+        CPB_LAUNCH((k_probe_stream<i64, false>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
     } else if (f.dev.is_float) {
       CPB_LAUNCH(k_bisect_round<double>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
     } else {
@@ -1643,12 +1693,9 @@ bool bisect_advance(BisectRun& run, bool sync) {
   CPB_LAUNCH(k_bisect_advance, 1, 256, 0, (int)run.K, run.P, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.best.get(),
              run.node_spl, run.node_res, run.node_c, run.ids.get());
   if (sync) {
-    CPB_CUDA(cudaMemcpyAsync(&run.h_st, run.st.get(), sizeof(BisectState), cudaMemcpyDeviceToHost, ctx().stream));
-    CPB_CUDA(cudaMemcpyAsync(run.h_best.data(), run.best.get(), (run.K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-    {
-      const cudaError_t e = cudaStreamSynchronize(ctx().stream);
-      if (e != cudaSuccess) throw Error(CPB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in the bisection probes" + ring_debug_string());
-    }
+    check_probes(cudaMemcpyAsync(&run.h_st, run.st.get(), sizeof(BisectState), cudaMemcpyDeviceToHost, ctx().stream));
+    check_probes(cudaMemcpyAsync(run.h_best.data(), run.best.get(), (run.K + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    check_probes(cudaStreamSynchronize(ctx().stream));
     run.done = run.h_st.done != 0;
     run.planned = false;  // the next round is planned from the new bracket
   }
@@ -1724,7 +1771,7 @@ int probe_cluster_capacity(bool stream) {
     cfg.blockDim = dim3(PR_THREADS, 1, 1);
     cfg.dynamicSmemBytes = PR_RING_BYTES;
     CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_ring<i64>, &cfg));
-  } else if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_stream<i64>, &cfg));
+  } else if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, (k_probe_stream<i64, true>), &cfg));
   else CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_bisect_round<i64>, &cfg));
   return n;
 }

@@ -14,7 +14,10 @@ module ChainPartitionersB200
 
 using SparseArrays
 using ChainPartitioners
-import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_stripe, dominancecount, dominancesum, rookcount!, rooksum!,
+import ChainPartitioners: partition_stripe, pack_stripe, partition_plaid, oracle_stripe, bound_stripe, bottleneck_value, total_value, adjointpattern,
+    netcount, dianetcount, selfnetcount, selfpincount, pincount, dominancecount, dominancesum, rookcount!, rooksum!,
+    AlternatingPartitioner, SymmetricPartitioner, DisjointPartitioner, MapPartition, DomainPartition,
+    ConcaveTotalChunker, ConcaveTotalSplitter,
     AffineWorkModel, AffineConnectivityModel, AffineMonotonizedSymmetricConnectivityModel,
     AffineSymmetricConnectivityModel, AffineHyperedgeCutModel, AffineSymmetricEdgeCutModel, AffineEnvelopeModel,
     AffinePrimaryConnectivityModel, AffineSecondaryConnectivityModel, AffinePrimaryEdgeCutModel, AffineSecondaryEdgeCutModel,
@@ -25,6 +28,12 @@ import ChainPartitioners: partition_stripe, pack_stripe, oracle_stripe, bound_st
     DynamicBottleneckChunker, DynamicTotalChunker, ConvexTotalChunker, ConvexTotalSplitter, OverlapChunker, StrictChunker, EquiChunker, EquiSplitter
 
 const lib = get(ENV, "CHAINB200_LIB", "libchainb200.so")
+
+# The dispatch tag: wraps a method (partition_stripe(A, K, OnB200(DynamicBottleneckSplitter(f)))), a model
+# (bottleneck_value(A, Φ, OnB200(f))) or a hint (oracle_stripe(OnB200(SparseHint()), f, A), netcount(OnB200(nothing), A)).
+struct OnB200{Mtd}
+    mtd::Mtd
+end
 
 # ---- C structs (binary layout of cpb_model / cpb_constraint) ---------------------------------
 struct CModel
@@ -110,6 +119,32 @@ mutable struct DeviceMatrix
             (Int64, Int64, Int64, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}), m, n, nnz(A), A.colptr, A.rowval, h))
         finalizer(x -> ccall((:cpb_matrix_destroy, lib), Cvoid, (Ptr{Cvoid},), x.h), new(h[], m, n))
     end
+    DeviceMatrix(h::Ptr{Cvoid}, m::Int, n::Int) = finalizer(x -> ccall((:cpb_matrix_destroy, lib), Cvoid, (Ptr{Cvoid},), x.h), new(h, m, n))
+end
+
+# a handle the library made (cpb_adjointpattern, cpb_matrix_permute): same finalizer
+function DeviceMatrix(h::Ptr{Cvoid})
+    m, n, nz = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:cpb_matrix_dims, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), h, m, n, nz))
+    return DeviceMatrix(h, Int(m[]), Int(n[]))
+end
+Base.size(dA::DeviceMatrix) = (dA.m, dA.n)
+device_matrix(A::DeviceMatrix) = A
+device_matrix(A::SparseMatrixCSC) = DeviceMatrix(A)
+
+# adjointpattern(A) on the device (src/util.jl:67-95): the transpose pattern stays in HBM
+function adjointpattern(dA::DeviceMatrix)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cpb_adjointpattern, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), dA.h, h))
+    return DeviceMatrix(h[])
+end
+# back to the host as a pattern matrix (cpb_matrix_get)
+function SparseArrays.SparseMatrixCSC(dA::DeviceMatrix)
+    m, n, nz = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:cpb_matrix_dims, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), dA.h, m, n, nz))
+    colptr, rowval = Vector{Int64}(undef, n[] + 1), Vector{Int64}(undef, nz[])
+    check(ccall((:cpb_matrix_get, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), dA.h, colptr, rowval))
+    return SparseMatrixCSC(Int(m[]), Int(n[]), colptr, rowval, ones(Bool, nz[]))
 end
 
 mutable struct DeviceOracle
@@ -141,6 +176,60 @@ function query(ocl::DeviceOracle, j::Vector{Int64}, j′::Vector{Int64})
     return out
 end
 
+# ocl(j, j′, k) for the row-partition-aware models (PrimaryConnectivityCosts.jl:66-73, ...): k = part index
+function (ocl::DeviceOracle)(j::Integer, j′::Integer, k::Integer)
+    out = Ref{Float64}(0.0)
+    check(ccall((:cpb_oracle_query, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
+                ocl.h, 1, Int64(j), Int64(j′), Int64(k), out))
+    return out[]
+end
+
+# oracle_stripe(OnB200(hint), mdl, A[, Π]) (src/Costs.jl:3-7): the wrapper takes the place of the hint; A may be a
+# SparseMatrixCSC (uploaded once, kept alive by the oracle) or a DeviceMatrix
+oracle_stripe(::OnB200, mdl, A, args...; kwargs...) = DeviceOracle(device_matrix(A), mdl, args...)
+
+# bottleneck_value / total_value (src/Costs.jl:26-66) of a SplitPartition; Map- and DomainPartitions are first made
+# contiguous by gathering the columns part by part on the device (cpb_matrix_permute), as compute_objective does with
+# A[:, Φ_dom.prm]
+function objective(total::Bool, A, Φ::SplitPartition, f::OnB200, Π...)
+    ocl = DeviceOracle(device_matrix(A), f.mtd, Π...)
+    out = Ref{Float64}(0.0)
+    spl = Vector{Int64}(Φ.spl)
+    check(ccall((:cpb_objective, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ref{Float64}), ocl.h, total ? 1 : 0, Φ.K, spl, out))
+    return out[]
+end
+function objective(total::Bool, A, Φ::Union{MapPartition, DomainPartition}, f::OnB200, Π...)
+    Φ_dom = convert(DomainPartition, Φ)
+    dA = device_matrix(A)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    prm = Vector{Int64}(Φ_dom.prm)
+    check(ccall((:cpb_matrix_permute, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}), dA.h, prm, C_NULL, h))
+    return objective(total, DeviceMatrix(h[]), SplitPartition{Int64}(Φ_dom.K, Vector{Int64}(Φ_dom.spl)), f, Π...)
+end
+bottleneck_value(A, Φ, f::OnB200, Π...) = objective(false, A, Φ, f, Π...)
+total_value(A, Φ, f::OnB200, Π...) = objective(true, A, Φ, f, Π...)
+
+# colour arrays (src/SparseColorArrays.jl): netcount(OnB200(hint), A)[j, j′] etc. through cpb_count_query
+struct DeviceColorArray
+    which::Cint
+    A::DeviceMatrix
+end
+function Base.getindex(c::DeviceColorArray, j::Integer, j′::Integer)
+    out = Ref{Int64}(0)
+    check(ccall((:cpb_count_query, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}), c.A.h, c.which, 1, Int64(j), Int64(j′), out))
+    return out[]
+end
+function query(c::DeviceColorArray, j::Vector{Int64}, j′::Vector{Int64})
+    out = Vector{Int64}(undef, length(j))
+    check(ccall((:cpb_count_query, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), c.A.h, c.which, length(j), j, j′, out))
+    return out
+end
+pincount(::OnB200, A; kwargs...) = DeviceColorArray(0, device_matrix(A))
+netcount(::OnB200, A; kwargs...) = DeviceColorArray(1, device_matrix(A))
+dianetcount(::OnB200, A; kwargs...) = DeviceColorArray(2, device_matrix(A))
+selfnetcount(::OnB200, A; kwargs...) = DeviceColorArray(3, device_matrix(A))
+selfpincount(::OnB200, A; kwargs...) = DeviceColorArray(4, device_matrix(A))
+
 function bound_stripe(ocl::DeviceOracle, K)
     out = Vector{Float64}(undef, 2)
     check(ccall((:cpb_bound_stripe, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), ocl.h, K, out))
@@ -148,9 +237,6 @@ function bound_stripe(ocl::DeviceOracle, K)
 end
 
 # ---- partition_stripe / pack_stripe -----------------------------------------------------------
-struct OnB200{Mtd}   # partition_stripe(A, K, OnB200(DynamicBottleneckSplitter(f))) etc.
-    mtd::Mtd
-end
 
 split_code(::DynamicBottleneckSplitter) = (0, 0.0)
 split_code(::DynamicTotalSplitter) = (1, 0.0)
@@ -164,6 +250,74 @@ split_code(::FlipBisectIndexBottleneckSplitter) = (13, 0.0)
 split_code(::DynamicBottleneckChunker) = (10, 0.0)   # partition_stripe(A, K, ::AbstractDynamicChunker), DynamicSplitter.jl:52-87
 split_code(::DynamicTotalChunker) = (11, 0.0)
 
+split_code(::ConcaveTotalSplitter) = (9, 0.0)
+
+# The stripe solve on a pattern that is already resident (what partition_plaid below and repeated solves use: no upload)
+function partition_stripe(dA::DeviceMatrix, K, method::OnB200, args...; kwargs...)
+    (code, ϵ) = split_code(method.mtd)
+    ocl = DeviceOracle(dA, method.mtd.f, args...)
+    spl = Vector{Int64}(undef, K + 1)
+    check(ccall((:cpb_partition_stripe, lib), Cint, (Ptr{Cvoid}, Cint, Ref{CConstraint}, Float64, Int64, Ptr{Int64}),
+                ocl.h, code, constraint(method.mtd.f), ϵ, K, spl))
+    return SplitPartition{Int64}(K, spl)
+end
+
+# partition_plaid(A, K, AlternatingPartitioner(OnB200(m1), OnB200(m2), ...)) (src/AlternatingPartitioner.jl:18-32): A is
+# uploaded ONCE, adjointpattern runs on the device, every stripe solve takes the resident handles -- the reference's
+# `adj_A = adjointpattern(A)` reuse seam, kept on the device.  A caller-supplied adj_A (host or device) is honoured.
+function partition_plaid(A::Union{SparseMatrixCSC, DeviceMatrix}, K, method::AlternatingPartitioner{<:Tuple{Vararg{OnB200}}}; adj_A = nothing, kwargs...)
+    dA = device_matrix(A)
+    dT = adj_A === nothing ? adjointpattern(dA) : device_matrix(adj_A)
+    Φ = partition_stripe(dA, K, method.mtds[1])
+    Π = partition_stripe(dT, K, method.mtds[2], Φ)
+    for (i, mtd) in enumerate(method.mtds[3:end])
+        if isodd(i)
+            Φ = partition_stripe(dA, K, mtd, Π)
+        else
+            Π = partition_stripe(dT, K, mtd, Φ)
+        end
+    end
+    return (Π, Φ)
+end
+function partition_plaid(A::Union{SparseMatrixCSC, DeviceMatrix}, K, method::SymmetricPartitioner{<:Tuple{Vararg{OnB200}}}; adj_A = nothing, kwargs...)
+    dA = device_matrix(A)
+    Π = partition_stripe(dA, K, method.mtds[1])
+    if length(method.mtds) > 1
+        dT = adj_A === nothing ? adjointpattern(dA) : device_matrix(adj_A)
+        for (i, mtd) in enumerate(method.mtds[2:end])
+            Π = partition_stripe(isodd(i) ? dA : dT, K, mtd, Π)
+        end
+    end
+    return (Π, Π)
+end
+
+# ---- one solve over several GPUs (one Julia process per GPU; cpb_comm_*, cpb_partition_stripe_sharded) ------------
+# rank 0: id = comm_unique_id(); ship the 128 bytes to the other ranks (MPI.bcast, a file, ...); every rank: comm_init
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:cpb_comm_unique_id, lib), Cint, (Ptr{UInt8},), id))
+    return id
+end
+init(device::Integer) = check(ccall((:cpb_init, lib), Cint, (Cint,), device))
+comm_init(id::Vector{UInt8}, rank::Integer, world::Integer) = check(ccall((:cpb_comm_init, lib), Cint, (Ptr{UInt8}, Cint, Cint), id, rank, world))
+comm_destroy() = check(ccall((:cpb_comm_destroy, lib), Cint, ()))
+# collective: every rank calls it with the same A; each uploads only its block of rowval
+function partition_stripe_sharded(A::SparseMatrixCSC{Tv, Int64}, K, method::OnB200{<:Union{BisectCostBottleneckSplitter, LazyBisectCostBottleneckSplitter}}) where {Tv}
+    (m, n) = size(A)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve A check(ccall((:cpb_sharded_matrix_create, lib), Cint, (Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Ref{Ptr{Cvoid}}),
+                               m, n, nnz(A), A.colptr, A.rowval, 0, h))
+    (code, ϵ) = split_code(method.mtd)
+    (cm, keep) = cmodel(method.mtd.f, 0, 0)
+    spl = Vector{Int64}(undef, K + 1)
+    try
+        GC.@preserve keep check(ccall((:cpb_partition_stripe_sharded, lib), Cint, (Ptr{Cvoid}, Ref{CModel}, Cint, Float64, Int64, Ptr{Int64}), h[], cm, code, ϵ, K, spl))
+    finally
+        ccall((:cpb_sharded_matrix_destroy, lib), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    return SplitPartition{Int64}(K, spl)
+end
+
 function partition_stripe(A::SparseMatrixCSC{Tv, Int64}, K, method::OnB200, args...; kwargs...) where {Tv}
     dA = DeviceMatrix(A)
     (code, ϵ) = split_code(method.mtd)
@@ -176,6 +330,7 @@ end
 
 pack_code(m::DynamicTotalChunker) = (0, m.f, 0.0, 0)
 pack_code(m::ConvexTotalChunker) = (1, m.f, 0.0, 0)
+pack_code(m::ConcaveTotalChunker) = (2, m.f, 0.0, 0)
 pack_code(m::OverlapChunker) = (3, nothing, m.ρ, m.w_max)
 pack_code(m::StrictChunker) = (4, nothing, 0.0, m.w_max)
 pack_code(m::EquiChunker) = (5, nothing, 0.0, m.w)
@@ -229,7 +384,7 @@ rookcount!(::OnB200, N, idx::Vector{Int64}; kwargs...) = DevicePrefixMatrix{Int6
 rooksum!(::OnB200, N, idx::Vector{Int64}, val::Vector{Tv}; kwargs...) where {Tv <: Union{Int64, UInt64}} =
     DevicePrefixMatrix{Tv}(N, N, N, nothing, idx, val)
 
-# partition_plaid / pack_plaid need no glue: AlternatingPartitioner(OnB200(mtd1), OnB200(mtd2)) already
-# alternates partition_stripe calls on A and adjointpattern(A) (src/AlternatingPartitioner.jl:18-32).
+# pack_plaid needs no glue: AlternatingPacker(OnB200(mtd1), OnB200(mtd2)) alternates pack_stripe calls on A and
+# adjointpattern(A) (src/AlternatingPacker.jl:6-53); partition_plaid has the resident-handle methods above.
 
 end # module

@@ -41,10 +41,15 @@ def short_name(full):
 
 
 def read_report(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
-    if out.returncode != 0:
-        raise SystemExit(f"ncu -i {path} failed: {out.stderr[:400]}")
-    rows = list(csv.reader(io.StringIO(out.stdout)))
+    """`path`: a .ncu-rep, or the text of `ncu -i <rep> --page raw --csv` saved on the GPU box (large reports stay there)"""
+    if path.endswith(".csv"):
+        text = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
+        if out.returncode != 0:
+            raise SystemExit(f"ncu -i {path} failed: {out.stderr[:400]}")
+        text = out.stdout
+    rows = list(csv.reader(io.StringIO(text)))
     hdr = None
     for i, r in enumerate(rows):
         if "Kernel Name" in r:

@@ -32,7 +32,7 @@ else:
 dA = cp.device_matrix(A)
 mtd = cp.LazyBisectCostBottleneckSplitter(f, eps)
 out = {}
-for ring in ("0", "1"):
+for ring in (("1",) if os.environ.get("CPB_RINGDBG_ONLY") else ("0", "1")):
     os.environ["CPB_PROBE_RING"] = ring
     try:
         cp.partition_stripe(dA, K, mtd)
@@ -45,4 +45,5 @@ for ring in ("0", "1"):
     except Exception as e:
         print(case, "ring", ring, "FAILED:", e, flush=True)
         sys.exit(3)
-print(case, "identical", bool(np.array_equal(out["0"], out["1"])))
+if "0" in out:
+    print(case, "identical", bool(np.array_equal(out["0"], out["1"])))
