@@ -466,11 +466,21 @@ __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
 __device__ unsigned long long* g_ring_dbg = nullptr;
 __device__ __noinline__ void ring_wait_failed(u32 tag, u32 a, u32 b, u32 c, u32 d) {
   unsigned long long* g = g_ring_dbg;
-  if (g && atomicCAS(g, 0ull, 1ull) == 0ull) {
+  if (g) {
     unsigned cr;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
-    g[1] = tag; g[2] = blockIdx.x; g[3] = cr; g[4] = threadIdx.x; g[5] = a; g[6] = b; g[7] = c; g[8] = d;
-    __threadfence_system();
+    // the first record wins; every field travels in one 64-bit system-scope atomic (plain stores may not leave the SM
+    // before the trap): word 0 = 1 | tag << 4 | crank << 8 | block << 12 | tid << 28, words 1..2 = (a, b), (c, d)
+    const unsigned long long w0 = 1ull | ((unsigned long long)(tag & 15u) << 4) | ((unsigned long long)(cr & 15u) << 8) |
+                                  ((unsigned long long)(blockIdx.x & 0xffffu) << 12) | ((unsigned long long)(threadIdx.x & 0xfffu) << 28);
+    if (atomicCAS_system(g, 0ull, w0) == 0ull) {
+      atomicExch_system(g + 1, ((unsigned long long)a << 32) | b);
+      atomicExch_system(g + 2, ((unsigned long long)c << 32) | d);
+      __threadfence_system();
+    }
+    // give the record time to reach the host before the context dies
+    const long long t0 = clock64();
+    while (clock64() - t0 < 2000000) {}
   }
   __trap();
 }
@@ -1620,9 +1630,10 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
 static unsigned long long* g_ring_dbg_host = nullptr;
 static std::string ring_debug_string() {
   if (!g_ring_dbg_host || g_ring_dbg_host[0] == 0) return "";
+  const unsigned long long w0 = g_ring_dbg_host[0], w1 = g_ring_dbg_host[1], w2 = g_ring_dbg_host[2];
   char buf[256];
-  std::snprintf(buf, sizeof(buf), " [ring probe wait timed out: tag=%llu block=%llu crank=%llu tid=%llu a=%llu b=%llu c=%llu d=%llu]", g_ring_dbg_host[1], g_ring_dbg_host[2],
-                g_ring_dbg_host[3], g_ring_dbg_host[4], g_ring_dbg_host[5], g_ring_dbg_host[6], g_ring_dbg_host[7], g_ring_dbg_host[8]);
+  std::snprintf(buf, sizeof(buf), " [probe wait timed out: tag=%llu crank=%llu block=%llu tid=%llu a=%llu b=%llu c=%llu d=%llu]", (w0 >> 4) & 15, (w0 >> 8) & 15,
+                (w0 >> 12) & 0xffff, (w0 >> 28) & 0xfff, w1 >> 32, w1 & 0xffffffffull, w2 >> 32, w2 & 0xffffffffull);
   return buf;
 }
 // the host-mapped record a timed-out wait leaves (see ring_wait_failed)

@@ -273,11 +273,13 @@ static void h2d_copy(void* d_dst, const void* h_src, size_t bytes) {
 }
 
 // 1-based Int64 host index array -> 0-based u32 device array, range-checked ([lo, hi], flags |= 1 on the device).
-// Pageable sources are narrowed to 32 bits by the host pool while they are staged, the decrement + check runs per chunk
-// on the device behind its copy; pinned sources go over the bus as they are and are narrowed on the device.
+// The source is narrowed to 32 bits by the host pool while it is staged, the decrement + check runs per chunk on the
+// device behind its copy; short arrays go over the bus as they are and are narrowed on the device.
 static void upload_index_array(const i64* h_src, size_t n, u32* d_dst, i64 lo, i64 hi, u32* d_flags) {
   if (n == 0) return;
-  if (host_pinned(h_src) || n < PACK_CHUNK_ELEMS || staging_disabled() || std::getenv("CPB_NO_HOST_PACK")) {
+  // (pinned sources take the same path: narrowing halves the bus bytes, and measured on C3 -- 2.2 GB of Int64 indices --
+  //  the packed upload of PAGEABLE arrays, 31 ms, beats the plain DMA of pinned ones, 41 ms)
+  if (n < PACK_CHUNK_ELEMS || staging_disabled() || std::getenv("CPB_NO_HOST_PACK")) {
     DBuf<i64> wide(n);
     h2d_copy(wide.get(), h_src, n * sizeof(i64));
     narrow_minus1(wide.get(), d_dst, n, lo, hi, d_flags);
