@@ -883,7 +883,8 @@ struct PrShared {
   alignas(16) u32 mask[PR_WMAX][PR_G + 1][4];  // `prev < j` bit masks of every group; [.][32] = zero sentinel (offset == chunk size)
   u32 cnt[PR_WMAX][PR_G];                      // set bits per group
   u32 cum[PR_WMAX][PR_G + 1];                  // exclusive prefix of cnt inside the chunk; [.][32] = chunk total
-  u32 cb[PR_WMAX][2];                          // (first boundary, number of boundaries) of this CTA's chunks in the window
+  u32 cb[2][PR_WMAX][2];                       // (first boundary, number of boundaries) of this CTA's chunks in the window, per super-step
+                                               // parity: a window without boundaries has no block barrier between its readers and the next writers
   alignas(16) u32 x1[2][8 * PR_WMAX];          // exchange 1: chunk totals of the whole window, window order
   alignas(16) u32 x2[2][8][4];                 // exchange 2: per CTA (feasible boundaries, boundaries, P and Wt at its last feasible one)
   u32 pj[2 * PR_THREADS];                      // (P, Wt) of the boundary candidates of the current search round
@@ -980,8 +981,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
         else ja = (x0 < Ne) ? __ldg(s.chunk_col + g) + 2 : n1 + 1;
         if (x0 >= Ne && !head) jb = 0;
         else jb = (x0 + PR_C >= Ne) ? n1 : __ldg(s.chunk_col + g + 1) + 1;
-        sh.cb[tid][0] = ja;
-        sh.cb[tid][1] = (jb >= ja) ? jb - ja + 1 : 0;
+        sh.cb[ph][tid][0] = ja;
+        sh.cb[ph][tid][1] = (jb >= ja) ? jb - ja + 1 : 0;
       }
       // ---- bit masks of `prev < j`: warp w owns group w of each of the W chunks ----
 #pragma unroll
@@ -1043,8 +1044,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
 #pragma unroll
       for (int v = 0; v < PR_WMAX; ++v) {
         const bool on = v < (int)W;
-        cja[v] = on ? sh.cb[v][0] : 0u;
-        cn[v + 1] = cn[v] + (on ? sh.cb[v][1] : 0u);
+        cja[v] = on ? sh.cb[ph][v][0] : 0u;
+        cn[v + 1] = cn[v] + (on ? sh.cb[ph][v][1] : 0u);
       }
       const u32 nb = cn[PR_WMAX];
       auto locate = [&](u32 b, u32& r, u32& v) {  // flat candidate index -> (boundary, local chunk)
