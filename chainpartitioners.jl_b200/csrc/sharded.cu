@@ -169,6 +169,16 @@ __global__ void k_carry_merge(const u32* __restrict__ last_local, const u32* __r
   }
 }
 
+// carry[i] = the last position (+1) of row i in the blocks of the ranks below `rank`: the nearest non-empty entry
+__global__ void k_carry_pick(const u32* __restrict__ all, size_t m, int rank, u32* __restrict__ carry) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    u32 c = 0;
+    for (int r = rank - 1; r >= 0 && c == 0; --r) c = all[(size_t)r * m + i];
+    carry[i] = c;
+  }
+}
+
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void fill_chunk_cols_public(LinkStream& ls);  // links.cu
@@ -236,10 +246,20 @@ static std::unique_ptr<LinkStream> sharded_link_stream(const ShardedMatrix& S) {
   BlockWork w;
   block_local_links(S.row_blk.get(), (size_t)(S.q_hi - S.q_lo), (u32)S.q_lo, m, ls->prev.get(), w);
   DBuf<u32> carry(std::max<size_t>(m, 1));
-  {
-    // the "last seen" array travels down the ranks once: m * 4 bytes per hop
+  const bool has_in = S.rank > 0 && S.world > 1;
+  if (S.world > 2 && std::getenv("CPB_SHARD_CHAIN") == nullptr) {
+    // every rank needs the last position of each row in the blocks LEFT of its own.  More than two ranks: one all-gather
+    // of the per-block "last position" arrays (world x m x 4 bytes in, m x 4 bytes out per rank) and a local pick of the
+    // nearest non-empty entry -- all ranks finish together instead of waiting for a chain of world - 1 hops.
+    ProfScope pk("shard_carry", (double)m * 4.0 * S.world);
+    DBuf<u32> all(std::max<size_t>(m, 1) * S.world);
+    CPB_NCCL(g_nccl.AllGather(w.last_local.get(), all.get(), m, ncclUint32, g_comm, ctx().stream));
+    if (has_in) CPB_LAUNCH(k_carry_pick, grid_for(m), 256, 0, all.get(), m, S.rank, carry.get());
+    block_heads(w, has_in ? carry.get() : nullptr, (u32)S.q_lo, ls->prev.get(), ls->first_count.get());
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // `all` is released at the end of this scope
+  } else {
+    // two ranks (or CPB_SHARD_CHAIN=1): the "last seen" array travels down the ranks once, m * 4 bytes per hop
     ProfScope pk("shard_carry", (double)m * 4.0);
-    const bool has_in = S.rank > 0 && S.world > 1;
     if (has_in) CPB_NCCL(g_nccl.Recv(carry.get(), m, ncclUint32, S.rank - 1, g_comm, ctx().stream));
     if (S.rank + 1 < S.world) {
       DBuf<u32> out(std::max<size_t>(m, 1));
