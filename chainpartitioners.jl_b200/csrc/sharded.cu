@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <chrono>
+#include <vector>
 #include "engine.cuh"
 #include "primitives.cuh"
 
@@ -287,6 +288,26 @@ std::unique_ptr<LinkStream> emulated_sharded_link_stream(const Matrix& A, int wo
   shard_range(A.N, 0, world, &cnt, nullptr, nullptr);
   auto ls = new_link_stream(A, (size_t)cnt * world);
   DBuf<u32> carry(std::max<size_t>(m, 1)), next(std::max<size_t>(m, 1));
+  const bool pick = world > 2 && std::getenv("CPB_SHARD_CHAIN") == nullptr;  // the same two carry forms as the real ranks
+  if (pick) {
+    // pass 1: every block's local links and last positions; pass 2: heads from the nearest non-empty entry below
+    DBuf<u32> all(std::max<size_t>(m, 1) * world);
+    std::vector<BlockWork> ws(world);
+    for (int r = 0; r < world; ++r) {
+      i64 lo = 0, hi = 0;
+      shard_range(A.N, r, world, nullptr, &lo, &hi);
+      block_local_links(A.row.get() + lo, (size_t)(hi - lo), (u32)lo, m, ls->prev.get(), ws[r]);
+      if (m) CPB_CUDA(cudaMemcpyAsync(all.get() + (size_t)r * m, ws[r].last_local.get(), m * sizeof(u32), cudaMemcpyDeviceToDevice, ctx().stream));
+    }
+    for (int r = 0; r < world; ++r) {
+      i64 lo = 0;
+      shard_range(A.N, r, world, nullptr, &lo, nullptr);
+      if (r > 0) CPB_LAUNCH(k_carry_pick, grid_for(m), 256, 0, all.get(), m, r, carry.get());
+      block_heads(ws[r], r > 0 ? carry.get() : nullptr, (u32)lo, ls->prev.get(), ls->first_count.get());
+    }
+    CPB_CUDA(cudaStreamSynchronize(ctx().stream));  // the blocks' buffers are released here
+    return ls;
+  }
   for (int r = 0; r < world; ++r) {
     i64 lo = 0, hi = 0;
     shard_range(A.N, r, world, nullptr, &lo, &hi);
