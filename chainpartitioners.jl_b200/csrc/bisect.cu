@@ -435,7 +435,7 @@ struct DevStream {
   const u32* colidx;  // [Ne]
   const u32* P;       // element offsets of the column boundaries, 1 <= x <= n+1
   const u32* Wt;      // prefix of the pin-like term, 1 <= x <= n+1
-  const u32* chunk_col;  // [ceil(Ne / 4096) + 1] column of the first element of every 4096-element chunk (ring probes)
+  const u32* chunk_col;  // [ceil(Ne / LS_CHUNK) + 1] column of the first element of every LS_CHUNK-element chunk (ring probes)
   u32 Ne, n;
   int same_w;         // Wt == P
   double cf[4];
@@ -850,28 +850,36 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
 // ------------------------------------------------------------------------------------------------
 // Streaming probe, ring form (kernel "probe_ring").  Same algorithm and results as k_probe_stream; what changes is how
 // the latency chain of a part is built:
-//   * the link array is consumed strictly left to right by every threshold, so it is staged AHEAD of the search: the
-//     cluster's 8 CTAs own the 16 KB chunks of the array round-robin (chunk g belongs to CTA g mod 8) and each keeps its
-//     next PR_S chunks in a shared-memory ring filled by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx).  Only the
-//     compare `prev <= first position of the part` depends on the part start, so a part's tile is already on chip when
-//     its start becomes known -- no global-memory latency on the chain;
+//   * the link array is consumed (almost always) left to right by every threshold, so it is staged AHEAD of the search:
+//     the cluster's 8 CTAs own the 32 KB chunks of the array round-robin (chunk g belongs to CTA g mod 8) and each keeps
+//     its next PR_S chunks in a shared-memory ring filled by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx).
+//     Only the compare `prev <= first position of the part` depends on the part start, so a part's tile is already on
+//     chip when its start becomes known.  (A part can end far behind the window that detected its end -- a giant column
+//     in between -- and the next part then starts behind the ring: the ring is drained and refilled from there.)
+//   * warp specialisation: warps 0..30 turn chunks into bit masks; warp 31 owns everything asynchronous -- it arms the
+//     exchange barriers, keeps the ring full, resolves the chunks' column ranges, waits for the peers' chunk totals and
+//     turns them into per-chunk bases -- off the consumers' instruction stream (an mbarrier / bulk-copy instruction
+//     costs ~150 cycles on the issuing thread: measured, profiles/r02_ring.md);
 //   * the two exchanges of a super-step (per-chunk `prev < j` totals; per-CTA feasible-boundary counts) are remote
 //     st.async stores that carry their payload into every peer's shared memory and complete a transaction count on the
-//     peer's mbarrier -- no barrier.cluster, no fence in front of it, no L1 invalidation;
-//   * chunk boundaries (first / last column of a chunk) come from a per-chunk table built once with the links.
-// A super-step covers the chunks [g_win, g_win + 8 W) (W <= PR_WMAX per CTA, sized from the previous part); warp w owns
-// the 128-element group w of every chunk of its CTA.
+//     peer's mbarrier -- no barrier.cluster, no fence in front of it, no L1 invalidation; each store is issued by a
+//     different warp (the per-lane cost of remote stores is serial inside one instruction);
+//   * chunk boundaries (first / last column of a chunk) come from a per-chunk table built once with the links; the
+//     crossing is found by 1024-way search rounds over the CTA's boundary candidates.
+// A super-step covers the chunks [g_win, g_win + 8 W) (W <= PR_WMAX per CTA, sized from the previous part).
 // ------------------------------------------------------------------------------------------------
 static constexpr int PR_THREADS = 1024;
-static constexpr u32 PR_C = 4096;      // elements per chunk (16 KB)
-static constexpr int PR_S = 12;        // ring slots per CTA (192 KB)
-static constexpr int PR_WMAX = 6;      // chunks per CTA per super-step
-static constexpr int PR_G = 32;        // 128-element groups per chunk = warps per CTA
+static constexpr u32 PR_C = LS_CHUNK;  // elements per chunk (32 KB)
+static constexpr int PR_S = 6;         // ring slots per CTA (192 KB)
+static constexpr int PR_WMAX = 3;      // chunks per CTA per super-step
+static constexpr int PR_G = 64;        // 128-element groups per chunk
+static constexpr int PR_CW = 31;       // consumer warps; warp 31 is the producer / coordinator
 static constexpr size_t PR_RING_BYTES = (size_t)PR_S * PR_C * sizeof(u32);
+static_assert(PR_C == 8192, "PR_G groups of 128 elements per chunk");
 
 #ifdef CPB_PROBE_TIMING
 __device__ unsigned long long g_ring_t[16];
-__device__ unsigned long long g_ring_n[8];  // super-steps, parts, few-path steps, many-path steps, empty steps, sum of W
+__device__ unsigned long long g_ring_n[8];  // super-steps, parts, search rounds, rewinds, empty steps, sum of W
 #define RT(i) do { if (node == 0 && crank == 0 && tid == 0) { unsigned long long _t = clock64(); g_ring_t[i] += _t - rt_last; rt_last = _t; } } while (0)
 #define RN(i, v) do { if (node == 0 && crank == 0 && tid == 0) g_ring_n[i] += (v); } while (0)
 #else
@@ -880,16 +888,15 @@ __device__ unsigned long long g_ring_n[8];  // super-steps, parts, few-path step
 #endif
 
 struct PrShared {
-  alignas(16) u32 mask[PR_WMAX][PR_G + 1][4];  // `prev < j` bit masks of every group; [.][32] = zero sentinel (offset == chunk size)
+  alignas(16) u32 mask[PR_WMAX][PR_G + 1][4];  // `prev < j` bit masks of every group; [.][64] = zero sentinel (offset == chunk size)
   u32 cnt[PR_WMAX][PR_G];                      // set bits per group
-  u32 cum[PR_WMAX][PR_G + 1];                  // exclusive prefix of cnt inside the chunk; [.][32] = chunk total
-  u32 cb[2][PR_WMAX][2];                       // (first boundary, number of boundaries) of this CTA's chunks in the window, per super-step
-                                               // parity: a window without boundaries has no block barrier between its readers and the next writers
+  u32 cum[PR_WMAX][PR_G + 1];                  // exclusive prefix of cnt inside the chunk; [.][64] = chunk total
+  u32 cb[2][PR_WMAX][2];                       // (first boundary, number of boundaries) of this CTA's chunks, per super-step parity
+  u32 base[2][PR_WMAX + 1];                    // `prev < j` elements of the window in front of each of this CTA's chunks; [.][WMAX] = window total
   alignas(16) u32 x1[2][8 * PR_WMAX];          // exchange 1: chunk totals of the whole window, window order
   alignas(16) u32 x2[2][8][4];                 // exchange 2: per CTA (feasible boundaries, boundaries, P and Wt at its last feasible one)
-  u32 pj[2 * PR_THREADS];                      // (P, Wt) of the boundary candidates of the current search round
-  u32 w[2 * PR_THREADS];
-  u32 red[2][4];                               // refinement result of the crossing thread (per super-step parity)
+  u32 pj[PR_THREADS];                          // (P, Wt) of the boundary candidates of the current search round
+  u32 w[PR_THREADS];
   alignas(8) unsigned long long mb_full[PR_S];
   alignas(8) unsigned long long mb_x1[2];
   alignas(8) unsigned long long mb_x2[2];
@@ -907,6 +914,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
   cg::cluster_group cluster = cg::this_cluster();
   const u32 crank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == PR_CW;
   const int node = node_base + blockIdx.x / BS_CLUSTER;
   const bool writer = crank == 0 && tid == 0;
   if (tid == 0) {
@@ -927,14 +935,25 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
   const u32 Ne = s.Ne;
   int* spl = node_spl + (size_t)node * (K + 2);
   if (writer) { spl[1] = 1; spl[K + 1] = (int)n1; }
+  // this CTA's local chunk l is the global chunk 8 l + crank; l_end = its first chunk that starts at or behind Ne
+  const u32 nchunks = (Ne + PR_C - 1) / PR_C;
+  const u32 l_end = nchunks > crank ? (nchunks - crank + 7u) >> 3 : 0u;
   u32 W = PR_WMAX, w_est = PR_WMAX;
-  u32 sstep = 0;      // super-steps so far (selects the exchange buffers / mbarrier parities)
-  u32 fill_hi = 0;    // this CTA's chunks [0, fill_hi) have been requested (local chunk l = global chunk 8 l + crank)
+  u32 sstep = 0;        // super-steps so far (selects the exchange buffers / mbarrier parities)
+  u32 fill_hi = 0;      // the ring holds (or has requested) the local chunks [fill_hi - PR_S, fill_hi), chunk l in slot l mod PR_S
+  u32 pmask = (1u << PR_S) - 1u;  // bit t: parity of the most recent bulk copy into slot t (first copy: phase 0)
+  u32 ver_hi = 0;       // (consumer warps) chunks below ver_hi are known to have landed
   u32 j = 1;
   bool broke = false, feasible = false;
   u32 pcur = __ldg(s.P + 1), wcur = __ldg(s.Wt + 1);
   const u32 x1_base = smem_addr(&sh.x1[0][0]), x2_base = smem_addr(&sh.x2[0][0][0]);
   const u32 bar_x1 = smem_addr(&sh.mb_x1[0]), bar_x2 = smem_addr(&sh.mb_x2[0]);
+  // slots [a, b) of the ring as a PR_S-bit mask (b - a <= PR_S)
+  auto slot_bits = [](u32 a, u32 b) -> u32 {
+    const u32 len = b - a;
+    u32 m = ((1u << len) - 1u) << (a % PR_S);
+    return (m | (m >> PR_S)) & ((1u << PR_S) - 1u);
+  };
   for (int k = 1; k <= K; ++k) {
     if (!cost_leq(stream_cost<T>(s, 0, 0, 0), c)) { broke = true; break; }  // even the empty part exceeds c
     const u32 e0 = pcur;
@@ -951,94 +970,96 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
       const u32 ph = sstep & 1u, xpar = (sstep >> 1) & 1u;
       const u32 l0 = (g_win + 7u - crank) >> 3;              // first local chunk of this CTA inside the window
       const u32 p0 = (crank - g_win) & 7u;                   // its position in window order; the others follow at +8
-      // ---- arm this super-step's exchange barriers, keep the ring full ----
-      if (tid == 0) {
-        sh.red[ph][0] = 0;
-        mbar_expect_tx(bar_x1 + 8u * ph, 32u * W);
-        mbar_expect_tx(bar_x2 + 8u * ph, 128u);
-        const u32 want_hi = l0 + PR_S;
-        if (fill_hi < want_hi) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slots' last readers were generic-proxy loads
-          for (u32 l = fill_hi; l < want_hi; ++l) {
-            const u64 x0 = ((u64)l * 8u + crank) * PR_C;
-            if (x0 >= Ne) break;
-            const u32 slot = l % PR_S;
-            const u32 bar = smem_addr(&sh.mb_full[slot]);
-            mbar_expect_tx(bar, PR_C * 4u);
-            bulk_load(smem_addr(ring + (size_t)slot * PR_C), s.prev + x0, PR_C * 4u, bar);
-          }
-        }
-      }
-      fill_hi = max(fill_hi, l0 + PR_S);
-      RT(0);
-      // ---- boundaries of this CTA's chunks: chunk [x0, x0 + C) owns the columns boundaries r with x0 < P[r] <= x0 + C ----
-      if (tid < (int)W) {
-        const u32 g = (l0 + tid) * 8u + crank;
-        const u64 x0 = (u64)g * PR_C;
-        const bool head = first && g == g_win;  // the chunk holding the part's first element: candidates start right after j
-        u32 ja, jb;
-        if (head) ja = j + 1;
-        else ja = (x0 < Ne) ? __ldg(s.chunk_col + g) + 2 : n1 + 1;
-        if (x0 >= Ne && !head) jb = 0;
-        else jb = (x0 + PR_C >= Ne) ? n1 : __ldg(s.chunk_col + g + 1) + 1;
-        sh.cb[ph][tid][0] = ja;
-        sh.cb[ph][tid][1] = (jb >= ja) ? jb - ja + 1 : 0;
-      }
-      // ---- bit masks of `prev < j`: warp w owns group w of each of the W chunks ----
-#pragma unroll
-      for (int v = 0; v < PR_WMAX; ++v) {
-        if (v >= (int)W) break;
-        const u32 l = l0 + v;
-        const u64 x0 = ((u64)l * 8u + crank) * PR_C;
-        const u64 gbase = x0 + (u32)warp * 128u;
-        unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        if (gbase < Ne && gbase + 128u > e0) {  // (warp-uniform) the group holds elements of [e0, Ne)
-          const u32 slot = l % PR_S;
-          mbar_wait(smem_addr(&sh.mb_full[slot]), (l / PR_S) & 1u, 1u, l, sstep, e0, W);
-          const uint4 pv = *reinterpret_cast<const uint4*>(ring + (size_t)slot * PR_C + warp * 128 + lane * 4);
-          if (gbase >= e0 && gbase + 128u <= Ne) {
-            m0 = __ballot_sync(0xffffffffu, pv.x <= e0);
-            m1 = __ballot_sync(0xffffffffu, pv.y <= e0);
-            m2 = __ballot_sync(0xffffffffu, pv.z <= e0);
-            m3 = __ballot_sync(0xffffffffu, pv.w <= e0);
-          } else {  // the part's first group / the array's last group: mask what lies outside [e0, Ne)
-            const u64 idx = gbase + (u32)lane * 4u;
-            m0 = __ballot_sync(0xffffffffu, pv.x <= e0 && idx + 0 >= e0 && idx + 0 < Ne);
-            m1 = __ballot_sync(0xffffffffu, pv.y <= e0 && idx + 1 >= e0 && idx + 1 < Ne);
-            m2 = __ballot_sync(0xffffffffu, pv.z <= e0 && idx + 2 >= e0 && idx + 2 < Ne);
-            m3 = __ballot_sync(0xffffffffu, pv.w <= e0 && idx + 3 >= e0 && idx + 3 < Ne);
-          }
-        }
+      // ---- ring bookkeeping, replicated in every thread: which chunks get requested now, the slots' new parities ----
+      const bool rewind = l0 + PR_S < fill_hi;               // the part starts behind the ring
+      const u32 req_lo = rewind ? l0 : max(fill_hi, l0);
+      const u32 req_hi = l0 + PR_S;
+      const u32 iss_lo = min(req_lo, l_end), iss_hi = min(req_hi, l_end);  // chunks that exist (start in front of Ne)
+      const u32 old_lo = fill_hi > (u32)PR_S ? fill_hi - PR_S : 0u;       // (rewind) what was in flight before
+      const u32 old_hi = min(fill_hi, l_end), old_pmask = pmask;
+      if (iss_hi > iss_lo) pmask ^= slot_bits(iss_lo, iss_hi);
+      if (rewind) { ver_hi = l0; RN(3, 1); }
+      fill_hi = req_hi;
+      if (producer) {
+        // ---- warp 31: arm this super-step's exchange barriers, keep the ring full, resolve the chunks' column ranges ----
         if (lane == 0) {
-          *reinterpret_cast<uint4*>(&sh.mask[v][warp][0]) = make_uint4(m0, m1, m2, m3);
-          sh.cnt[v][warp] = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+          mbar_expect_tx(bar_x1 + 8u * ph, 32u * W);
+          mbar_expect_tx(bar_x2 + 8u * ph, 128u);
+          if (rewind)  // every copy still in flight lands before its slot is armed again
+            for (u32 l = old_lo; l < old_hi; ++l) mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (old_pmask >> (l % PR_S)) & 1u, 4u, l, sstep, fill_hi, 1u);
+          if (iss_hi > iss_lo) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slots' last readers were generic-proxy loads
+            for (u32 l = iss_lo; l < iss_hi; ++l) {
+              const u64 x0 = ((u64)l * 8u + crank) * PR_C;
+              const u32 slot = l % PR_S;
+              const u32 bar = smem_addr(&sh.mb_full[slot]);
+              mbar_expect_tx(bar, PR_C * 4u);
+              bulk_load(smem_addr(ring + (size_t)slot * PR_C), s.prev + x0, PR_C * 4u, bar);
+            }
+          }
+        }
+        // chunk [x0, x0 + C) owns the column boundaries r with x0 < P[r] <= x0 + C
+        if (lane < (int)W) {
+          const u32 g = (l0 + lane) * 8u + crank;
+          const u64 x0 = (u64)g * PR_C;
+          const bool head = first && g == g_win;  // the chunk holding the part's first element: candidates start right after j
+          u32 ja, jb;
+          if (head) ja = j + 1;
+          else ja = (x0 < Ne) ? __ldg(s.chunk_col + g) + 2 : n1 + 1;
+          if (x0 >= Ne && !head) jb = 0;
+          else jb = (x0 + PR_C >= Ne) ? n1 : __ldg(s.chunk_col + g + 1) + 1;
+          sh.cb[ph][lane][0] = ja;
+          sh.cb[ph][lane][1] = (jb >= ja) ? jb - ja + 1 : 0;
+        }
+      } else {
+        // ---- warps 0..30: bit masks of `prev < j`; the 64 W groups of the window are dealt round-robin to the warps ----
+        for (u32 l = max(ver_hi, l0); l < min(l0 + W, l_end); ++l)  // chunks of the window this warp has not seen land yet
+          mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (pmask >> (l % PR_S)) & 1u, 1u, l, sstep, e0, W);
+        ver_hi = max(ver_hi, l0 + W);
+        for (u32 G = (u32)warp; G < (u32)PR_G * W; G += PR_CW) {
+          const u32 v = G >> 6, gi = G & 63u;
+          const u32 l = l0 + v;
+          const u64 gbase = ((u64)l * 8u + crank) * PR_C + gi * 128u;
+          unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          if (gbase < Ne && gbase + 128u > e0) {  // (warp-uniform) the group holds elements of [e0, Ne)
+            const uint4 pv = *reinterpret_cast<const uint4*>(ring + (size_t)(l % PR_S) * PR_C + gi * 128u + lane * 4);
+            if (gbase >= e0 && gbase + 128u <= Ne) {
+              m0 = __ballot_sync(0xffffffffu, pv.x <= e0);
+              m1 = __ballot_sync(0xffffffffu, pv.y <= e0);
+              m2 = __ballot_sync(0xffffffffu, pv.z <= e0);
+              m3 = __ballot_sync(0xffffffffu, pv.w <= e0);
+            } else {  // the part's first group / the array's last group: mask what lies outside [e0, Ne)
+              const u64 idx = gbase + (u32)lane * 4u;
+              m0 = __ballot_sync(0xffffffffu, pv.x <= e0 && idx + 0 >= e0 && idx + 0 < Ne);
+              m1 = __ballot_sync(0xffffffffu, pv.y <= e0 && idx + 1 >= e0 && idx + 1 < Ne);
+              m2 = __ballot_sync(0xffffffffu, pv.z <= e0 && idx + 2 >= e0 && idx + 2 < Ne);
+              m3 = __ballot_sync(0xffffffffu, pv.w <= e0 && idx + 3 >= e0 && idx + 3 < Ne);
+            }
+          }
+          if (lane == 0) {
+            *reinterpret_cast<uint4*>(&sh.mask[v][gi][0]) = make_uint4(m0, m1, m2, m3);
+            sh.cnt[v][gi] = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+          }
         }
       }
+      RT(0);
+      __syncthreads();  // B1: masks, counts, column ranges
       RT(1);
-      __syncthreads();
-      RT(2);
-      // ---- warp v scans chunk v and pushes the chunk total into every CTA's window table ----
+      // ---- warp v < W scans chunk v (two groups per lane) ----
       if (warp < (int)W) {
-        const u32 t = sh.cnt[warp][lane];
-        u32 inc = t;
+        const u32 t0 = sh.cnt[warp][2 * lane], t1 = sh.cnt[warp][2 * lane + 1];
+        u32 inc = t0 + t1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += y;
         }
-        sh.cum[warp][lane] = inc - t;
+        const u32 ex = inc - t0 - t1;
+        sh.cum[warp][2 * lane] = ex;
+        sh.cum[warp][2 * lane + 1] = ex + t0;
         if (lane == 31) sh.cum[warp][PR_G] = inc;
-        const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane < BS_CLUSTER) {
-          const u32 dst = x1_base + 4u * (ph * 8u * PR_WMAX + (u32)warp * 8u + p0);
-          st_async_u32(map_peer(dst, lane), tot, map_peer(bar_x1 + 8u * ph, lane));
-        }
       }
-      RT(3);
-      __syncthreads();
-      RT(4);
-      // ---- this CTA's boundary candidates, flat over its W chunks; the offsets of a thread's (at most 4) candidates are
-      //      fetched while the totals travel ----
+      // ---- this CTA's boundary candidates, flat over its W chunks ----
       u32 cn[PR_WMAX + 1], cja[PR_WMAX];
       cn[0] = 0;
 #pragma unroll
@@ -1049,140 +1070,101 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
       }
       const u32 nb = cn[PR_WMAX];
       auto locate = [&](u32 b, u32& r, u32& v) {  // flat candidate index -> (boundary, local chunk)
-        v = 0;
-#pragma unroll
-        for (int t = 1; t < PR_WMAX; ++t) v += (b >= cn[t]) ? 1u : 0u;
-        u32 cv = cn[0], jv = cja[0];
-#pragma unroll
-        for (int t = 1; t < PR_WMAX; ++t)
-          if (v == (u32)t) { cv = cn[t]; jv = cja[t]; }
+        v = (b >= cn[1] ? 1u : 0u) + (b >= cn[2] ? 1u : 0u);
+        const u32 cv = v == 0 ? cn[0] : (v == 1 ? cn[1] : cn[2]);
+        const u32 jv = v == 0 ? cja[0] : (v == 1 ? cja[1] : cja[2]);
         r = jv + (b - cv);
       };
-      const bool few = nb > 0 && nb <= 4u * PR_THREADS;
-      const u32 per = (nb + PR_THREADS - 1) / PR_THREADS;
-      const u32 b0 = (u32)tid * per;
-      const u32 mine = (few && b0 < nb) ? min(per, nb - b0) : 0u;
-      u32 pjv[4], wv[4], rv[4], vv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < (int)mine) {
-          locate(b0 + i, rv[i], vv[i]);
-          pjv[i] = __ldg(s.P + rv[i]);
-          wv[i] = s.same_w ? pjv[i] : __ldg(s.Wt + rv[i]);
-        }
-      RT(5);
-      mbar_wait_cluster(bar_x1 + 8u * ph, xpar, 2u, sstep, W, e0, g_win);
-      RT(6);
-      // ---- exclusive prefix of the window's chunk totals (window order), redundantly per warp: lane p and lane p + 32 ----
-      u32 excl0, excl1, tile_tot;
-      {
-        const u32 nwin = 8u * W;
-        const u32 q0 = (u32)lane, q1 = (u32)lane + 32u;
-        const u32 t0 = q0 < nwin ? sh.x1[ph][(q0 >> 3) * 8u + (q0 & 7u)] : 0u;  // x1[ph][i * 8 + position mod 8], i = q / 8
-        const u32 t1 = q1 < nwin ? sh.x1[ph][(q1 >> 3) * 8u + (q1 & 7u)] : 0u;
-        u32 i0 = t0, i1 = t1;
+      // round 1 of the search: thread t owns the candidates [t stride, (t + 1) stride) and tests the LAST one; its
+      // offsets are fetched while the chunk totals travel
+      u32 lo = 0, hi = nb;  // candidates [0, lo) feasible, [hi, nb) not
+      u32 stride = (nb + PR_THREADS - 1) / PR_THREADS;
+      bool live = nb > 0 && (u64)tid * stride < nb;
+      u32 r = 0, v = 0, pj = 0, w = 0;
+      if (live) {
+        locate((u32)min((u64)(tid + 1) * stride - 1, (u64)nb - 1), r, v);
+        pj = __ldg(s.P + r);
+        w = s.same_w ? pj : __ldg(s.Wt + r);
+      }
+      __syncthreads();  // B2: chunk prefixes and totals
+      RT(2);
+      // ---- exchange 1: warp 8 v + p pushes the total of chunk v to CTA p (one remote store per warp) ----
+      if (warp < 8 * (int)W && lane == 0) {
+        const u32 cv = (u32)warp >> 3, peer = (u32)warp & 7u;
+        const u32 dst = x1_base + 4u * (ph * 8u * PR_WMAX + cv * 8u + p0);
+        st_async_u32(map_peer(dst, peer), sh.cum[cv][PR_G], map_peer(bar_x1 + 8u * ph, peer));
+      }
+      if (producer) {
+        // warp 31 turns the window's chunk totals (window order: position q belongs to CTA (g_win + q) mod 8) into the
+        // base of each of this CTA's chunks
+        mbar_wait_cluster(bar_x1 + 8u * ph, xpar, 2u, sstep, W, e0, g_win);
+        const u32 nwin = 8u * W;  // <= 24
+        const u32 t = (u32)lane < nwin ? sh.x1[ph][lane] : 0u;
+        u32 inc = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const u32 y0 = __shfl_up_sync(0xffffffffu, i0, o), y1 = __shfl_up_sync(0xffffffffu, i1, o);
-          if (lane >= o) { i0 += y0; i1 += y1; }
+          const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += y;
         }
-        const u32 tot0 = __shfl_sync(0xffffffffu, i0, 31);
-        excl0 = i0 - t0;
-        excl1 = tot0 + i1 - t1;
-        tile_tot = tot0 + __shfl_sync(0xffffffffu, i1, 31);
+        if ((u32)lane < nwin && ((u32)lane & 7u) == p0) sh.base[ph][lane >> 3] = inc - t;
+        if (lane == 31) sh.base[ph][PR_WMAX] = inc;
       }
+      RT(3);
+      __syncthreads();  // B3: bases
+      RT(4);
+      const u32 tile_tot = sh.base[ph][PR_WMAX];
       // count of `prev < j` among the part's elements left of offset pj, pj inside (or at the end of) local chunk v
-      auto count_at = [&](u32 pj, u32 v) -> u32 {
-        const u32 q = v * 8u + p0;  // window position of the chunk
-        const u32 b_lo = __shfl_sync(0xffffffffu, excl0, q & 31u), b_hi = __shfl_sync(0xffffffffu, excl1, q & 31u);
-        const u32 x = pj - (u32)((((u64)(l0 + v)) * 8u + crank) * PR_C);  // 0 <= x <= C
-        const u32 g = x >> 7, r = x & 127u;
-        u32 cnt = grun + (q < 32u ? b_lo : b_hi) + sh.cum[v][g];
-        const uint4 mk = *reinterpret_cast<const uint4*>(&sh.mask[v][g][0]);
+      auto count_at = [&](u32 pj_, u32 v_) -> u32 {
+        const u32 x = pj_ - (u32)((((u64)(l0 + v_)) * 8u + crank) * PR_C);  // 0 <= x <= C
+        const u32 g = x >> 7, rr = x & 127u;
+        u32 cnt = grun + sh.base[ph][v_] + sh.cum[v_][g];
+        const uint4 mk = *reinterpret_cast<const uint4*>(&sh.mask[v_][g][0]);
         const u32 mm[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int nl = ((int)r - t + 3) >> 2;  // lanes l with 4 l + t < r
+          const int nl = ((int)rr - t + 3) >> 2;  // lanes l with 4 l + t < rr
           const u32 msk = nl >= 32 ? 0xffffffffu : (nl <= 0 ? 0u : ((1u << nl) - 1u));
           cnt += __popc(mm[t] & msk);
         }
         return cnt;
       };
-      // (count_at shuffles: every lane of a warp must call it the same number of times -- callers pass dummies)
-      auto feasible_at = [&](bool live, u32 r, u32 pj, u32 w, u32 v) -> bool {
-        const u32 g = count_at(live ? pj : (u32)((((u64)l0) * 8u + crank) * PR_C), live ? v : 0u);
-        return live && cost_leq(stream_cost<T>(s, (i64)r - (i64)j, (i64)w - wj, (i64)g), c);
-      };
       u32 cnt = 0, lastp = 0, lastw = 0;
-      RT(7);
-      RN(few ? 2 : (nb > 0 ? 3 : 4), 1);
-      if (few) {
-        // every thread tests its LAST candidate; the first thread whose last one fails holds the crossing and tests its
-        // remaining ones from registers
-        u32 pl = 0, wl = 0, rl = 0, vl = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < (int)mine) { pl = pjv[i]; wl = wv[i]; rl = rv[i]; vl = vv[i]; }
-        if (mine > 0) { sh.pj[tid] = pl; sh.w[tid] = wl; }
-        const bool ok = feasible_at(mine > 0, rl, pl, wl, vl);
-        const int ct = __syncthreads_count(ok);  // threads 0 .. ct-1 are feasible throughout
-        cnt = min((u32)ct * per, nb);
+      if (nb == 0) RN(4, 1);
+      while (lo < hi) {  // (uniform over the CTA)
+        RN(2, 1);
+        bool ok = false;
+        if (live) {
+          sh.pj[tid] = pj;
+          sh.w[tid] = w;
+          ok = cost_leq(stream_cost<T>(s, (i64)r - (i64)j, (i64)w - wj, (i64)count_at(pj, v)), c);
+        }
+        const int ct = __syncthreads_count(ok);  // monotone costs: threads 0 .. ct-1 hold feasible candidates
         if (ct > 0) { lastp = sh.pj[ct - 1]; lastw = sh.w[ct - 1]; }
-        if (per > 1) {
-          // (warp-uniform trip count: the whole warp of the crossing thread evaluates, only that thread's result counts)
-          const bool crossing_warp = (ct >> 5) == warp && ct < PR_THREADS;
-          if (crossing_warp) {
-            const bool me = tid == ct && mine > 1;
-            u32 c2 = 0, lp = 0, lw = 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const bool live = me && i < (int)mine - 1 && c2 == (u32)i;
-              if (feasible_at(live, rv[i], pjv[i], wv[i], vv[i])) { c2 = i + 1; lp = pjv[i]; lw = wv[i]; }
-            }
-            if (me) { sh.red[ph][0] = c2; sh.red[ph][1] = lp; sh.red[ph][2] = lw; }
-          }
-          __syncthreads();
-          const u32 c2 = sh.red[ph][0];
-          if (c2 > 0) { cnt += c2; lastp = sh.red[ph][1]; lastw = sh.red[ph][2]; }
+        const u32 nlo = (u32)min((u64)lo + (u64)ct * stride, (u64)hi);
+        const u32 nhi = (u32)min((u64)hi, (u64)lo + (u64)(ct + 1) * stride - 1);  // thread ct's last candidate failed
+        lo = nlo;
+        hi = max(nhi, nlo);
+        if (stride == 1 || lo >= hi) break;
+        __syncthreads();  // sh.pj / sh.w are rewritten by the next round
+        const u32 span = hi - lo;
+        stride = (span + PR_THREADS - 1) / PR_THREADS;
+        live = (u64)lo + (u64)tid * stride < hi;
+        if (live) {
+          locate((u32)min((u64)lo + (u64)(tid + 1) * stride - 1, (u64)hi - 1), r, v);
+          pj = __ldg(s.P + r);
+          w = s.same_w ? pj : __ldg(s.Wt + r);
         }
-      } else if (nb > 0) {
-        // many candidates (runs of empty columns): 1024-way search, repeated until the crossing is pinned down
-        u32 lo = 0, hi = nb;  // candidates [0, lo) feasible, [hi, nb) not
-        while (lo < hi) {
-          const u32 span = hi - lo;
-          const u32 stride = (span + PR_THREADS - 1) / PR_THREADS;
-          const u64 tb = (u64)lo + (u64)(tid + 1) * stride - 1;  // the last candidate of this thread's block
-          const bool live = (u64)lo + (u64)tid * stride < hi;
-          const u32 b = (u32)min(tb, (u64)hi - 1);
-          u32 r = 0, v = 0, pj = 0, w = 0;
-          if (live) {
-            locate(b, r, v);
-            pj = __ldg(s.P + r);
-            w = s.same_w ? pj : __ldg(s.Wt + r);
-            sh.pj[tid] = pj;
-            sh.w[tid] = w;
-          }
-          const bool ok = feasible_at(live, r, pj, w, v);
-          const int ct = __syncthreads_count(ok);
-          if (ct > 0) { lastp = sh.pj[ct - 1]; lastw = sh.w[ct - 1]; }
-          const u32 nlo = (u32)min((u64)lo + (u64)ct * stride, (u64)hi);
-          const u32 nhi = (u32)min((u64)hi, (u64)lo + (u64)(ct + 1) * stride - 1);  // thread ct's last candidate failed
-          __syncthreads();  // sh.pj / sh.w are rewritten by the next round
-          lo = nlo;
-          hi = max(nhi, nlo);
-          if (stride == 1) break;
-        }
-        cnt = lo;
       }
-      RT(8);
-      // ---- exchange 2: (feasible boundaries, boundaries, P and Wt at the last feasible one) of every CTA ----
-      if (tid < BS_CLUSTER) {
+      cnt = lo;
+      RT(5);
+      // ---- exchange 2: (feasible boundaries, boundaries, P and Wt at the last feasible one), warp p pushes to CTA p ----
+      if (warp < BS_CLUSTER && lane == 0) {
         const u32 dst = x2_base + 16u * (ph * 8u + crank);
-        st_async_v4(map_peer(dst, tid), cnt, nb, lastp, lastw, map_peer(bar_x2 + 8u * ph, tid));
+        st_async_v4(map_peer(dst, (u32)warp), cnt, nb, lastp, lastw, map_peer(bar_x2 + 8u * ph, (u32)warp));
       }
-      RT(9);
+      RT(6);
       mbar_wait_cluster(bar_x2 + 8u * ph, xpar, 3u, sstep, W, e0, g_win);
-      RT(10);
+      RT(7);
       u32 feas = 0, nbs = 0, bestp = 0;
       bool any = false;
 #pragma unroll
@@ -1202,7 +1184,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
       W = PR_WMAX;                                               // the part is longer than estimated
       missed = true;
     }
-    {  // size the next part's window from this part (+1/8 slack, +1 chunk row for the misaligned start)
+    {  // size the next part's window from this part (+1/8 slack, + the misaligned start)
       const u32 elems = pcur - e0;
       const u32 want = (elems + (elems >> 3) + 9u * PR_C - 1u) / (PR_C * BS_CLUSTER);
       w_est = missed ? (u32)PR_WMAX : max(min(want, (u32)PR_WMAX), w_est > 1u ? w_est - 1u : 1u);
@@ -1222,11 +1204,10 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(PR_THREADS,
     node_c[node] = c;
     node_res[node] = (!broke && feasible) ? 2 : 1;
   }
-  if (tid == 0)  // the ring runs ahead of the search: wait for the bulk copies still in flight into this CTA's shared memory
-    for (u32 l = fill_hi > (u32)PR_S ? fill_hi - PR_S : 0u; l < fill_hi; ++l) {
-      if (((u64)l * 8u + crank) * PR_C >= Ne) break;
-      mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (l / PR_S) & 1u, 4u, l, sstep, fill_hi, 0u);
-    }
+  if (producer && lane == 0) {  // the ring runs ahead of the search: wait for the bulk copies still in flight into this CTA's shared memory
+    const u32 a = fill_hi > (u32)PR_S ? fill_hi - PR_S : 0u;
+    for (u32 l = a; l < min(fill_hi, l_end); ++l) mbar_wait(smem_addr(&sh.mb_full[l % PR_S]), (pmask >> (l % PR_S)) & 1u, 4u, l, sstep, fill_hi, 0u);
+  }
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
 
@@ -1740,13 +1721,13 @@ void ring_timing_dump() {
   unsigned long long t[16], n[8];
   cudaMemcpyFromSymbol(t, g_ring_t, sizeof(t));
   cudaMemcpyFromSymbol(n, g_ring_n, sizeof(n));
-  const char* names[11] = {"arm+fill", "chunk ranges+ballots", "sync B1", "chunk scan+push x1", "sync B2", "candidates+P loads", "wait x1", "window scan",
-                           "boundary search", "push x2", "wait x2"};
+  const char* names[11] = {"fill|ballots (to B1)", "sync B1", "scan+candidates (to B2)", "push x1|wait x1+bases", "sync B3", "search rounds", "push x2", "wait x2",
+                           "-", "-", "-"};
   const double ss = (double)std::max<unsigned long long>(n[0], 1);
   double tot = 0;
   for (int i = 0; i < 11; ++i) tot += (double)t[i];
   for (int i = 0; i < 11; ++i) std::printf("ring_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / ss);
-  std::printf("ring_timing total %.1f cycles/super-step; super-steps %llu parts %llu few %llu many %llu empty %llu mean W %.2f\n", tot / ss, n[0], n[1], n[2], n[3], n[4],
+  std::printf("ring_timing total %.1f cycles/super-step; super-steps %llu parts %llu search rounds %llu rewinds %llu empty %llu mean W %.2f\n", tot / ss, n[0], n[1], n[2], n[3], n[4],
               (double)n[5] / ss);
   unsigned long long z[16] = {0};
   cudaMemcpyToSymbol(g_ring_t, z, sizeof(t));

@@ -50,7 +50,7 @@ struct LinkStream {
   size_t Ne = 0;
 };
 struct Matrix;
-static constexpr u32 LS_CHUNK = 4096;   // chunk of the link array the ring probes stage at a time; `prev` is allocated in whole chunks
+static constexpr u32 LS_CHUNK = 8192;   // chunk of the link array the ring probes stage at a time; `prev` is allocated in whole chunks
 static constexpr u32 LT_MAX_DEG = 128;  // largest row degree handled by the row-segment link construction (links.cu)
 std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row_lo = 0, i64 row_hi = ((i64)1 << 62), bool defer_check = false,
                                               bool force_sort = false, bool as_pos = false);
