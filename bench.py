@@ -385,7 +385,7 @@ def main():
                      "C++ restatement of the Julia reference, single thread (the reference has no threads)"}
     sizes = W.sizes(M)
     h2d = int((M.nnz + M.n + 1) * 8)
-    K = int(t["res"].K)
+    K = int(W.describe(t["res"]).get("K", W.describe(t["res"]).get("chunks", 0)))
     del M
     release_memory()
 

@@ -97,7 +97,7 @@ def main():
     for key, rep in args.workload:
         per = read_report(rep)
         sources.append(f"{key}:{os.path.basename(rep)}")
-        traffic[key] = {k: (mean(d["rd"]) or 0) + (mean(d["wr"]) or 0) for k, d in per.items() if d["rd"] or d["wr"]}
+        traffic.setdefault(key, {}).update({k: (mean(d["rd"]) or 0) + (mean(d["wr"]) or 0) for k, d in per.items() if d["rd"] or d["wr"]})
         md.append(f"### {key} -- `{os.path.basename(rep)}` (ncu --set full, per launch, means over the captured launches)\n")
         md.append("| kernel | launches | us | dram read MB | dram write MB | dram % | issue slots % | SM % | warps active % | regs | warp instr | L2 hit % |")
         md.append("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
