@@ -88,16 +88,25 @@ class HostPool {
   bool stop_ = false;
 };
 
-static HostPool& pool() {
-  static HostPool* p = [] {
-    const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
-    const char* env = std::getenv("CPB_H2D_THREADS");
-    int T = env ? std::atoi(env) : (int)std::min(12u, std::max(1u, (hc * 3) / 4));
-    if (T < 1) T = 1;
-    return new HostPool(T - 1);  // lives for the process (worker threads are detached from static destruction order)
-  }();
-  return *p;
+static int g_pool_share = 1;   // processes of this library sharing the host (set by cpb_comm_init before the first upload)
+static HostPool* g_pool = nullptr;
+static int g_pool_threads = 0;
+static int wanted_threads() {
+  const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+  const char* env = std::getenv("CPB_H2D_THREADS");
+  int T = env ? std::atoi(env) : (int)std::min(12u, std::max(2u, ((hc * 3) / 4) / (unsigned)std::max(g_pool_share, 1)));
+  return T < 1 ? 1 : T;
 }
+static HostPool& pool() {
+  const int T = wanted_threads();
+  if (!g_pool || g_pool_threads != T) {  // (re)built between uploads only: run() is never in flight here
+    delete g_pool;
+    g_pool = new HostPool(T - 1);  // lives for the process
+    g_pool_threads = T;
+  }
+  return *g_pool;
+}
+void host_pool_share(int ranks) { g_pool_share = ranks < 1 ? 1 : ranks; }
 
 // parallel memcpy of `bytes` bytes
 void host_copy(void* dst, const void* src, size_t bytes) {

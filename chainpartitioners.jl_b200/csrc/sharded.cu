@@ -37,6 +37,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
+void host_pool_share(int ranks);  // hostpack.cpp
 static NcclApi g_nccl;
 static ncclComm_t g_comm = nullptr;
 static int g_rank = 0, g_world = 1;
@@ -93,6 +94,7 @@ void comm_init(const char id_bytes[128], int rank, int world) {
   CPB_NCCL(g_nccl.CommInitRank(&g_comm, world, id, rank));
   g_rank = rank;
   g_world = world;
+  host_pool_share(world);  // the ranks of one box share its cores: each upload pool takes its share
 }
 
 void comm_destroy() {
@@ -332,13 +334,23 @@ ShardedMatrix* sharded_create(i64 m, i64 n, i64 nnz, const i64* h_colptr, const 
   S->M.m = m; S->M.n = n; S->M.N = nnz;
   shard_range(nnz, g_rank, g_world, &S->cnt, &S->q_lo, &S->q_hi);
   const size_t cntL = (size_t)(S->q_hi - S->q_lo);
-  S->M.pos.alloc((size_t)n + 1);
+  // the column offsets are needed whole on every rank: each rank uploads one slice, one in-place all-gather completes them
+  // (the ranks share the host's memory bandwidth -- n + 1 Int64 values read once instead of `world` times)
+  i64 ccnt = 0, clo = 0, chi = 0;
+  shard_range(n + 1, g_rank, g_world, &ccnt, &clo, &chi);
+  S->M.pos.alloc(std::max<size_t>((size_t)n + 1, (size_t)ccnt * g_world));
   S->row_blk.alloc(std::max<size_t>(cntL, 1));
   DBuf<u32> flags(1);
   flags.zero();
-  upload(h_colptr, (size_t)n + 1, S->M.pos.get(), 1, nnz + 1, flags.get());
+  if (g_world > 1 && g_comm) {
+    if (chi > clo) upload(h_colptr + clo, (size_t)(chi - clo), S->M.pos.get() + clo, 1, nnz + 1, flags.get());
+    CPB_NCCL(g_nccl.AllGather(S->M.pos.get() + (size_t)g_rank * ccnt, S->M.pos.get(), (size_t)ccnt, ncclUint32, g_comm, ctx().stream));
+  } else {
+    upload(h_colptr, (size_t)n + 1, S->M.pos.get(), 1, nnz + 1, flags.get());
+  }
   if (cntL) upload(rows_are_block ? h_rowval : h_rowval + S->q_lo, cntL, S->row_blk.get(), 1, m, flags.get());
   check_monotone(S->M.pos.get(), (size_t)n + 1, flags.get());
+  if (g_world > 1 && g_comm) CPB_NCCL(g_nccl.AllReduce(flags.get(), flags.get(), 1, ncclUint32, ncclMax, g_comm, ctx().stream));  // every rank fails together
   u32 hf = 0;
   CPB_CUDA(cudaMemcpyAsync(&hf, flags.get(), sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
   CPB_CUDA(cudaStreamSynchronize(ctx().stream));
