@@ -411,18 +411,11 @@ template <class T> static void bound_T(Oracle& f, i64 K, double out[2]) {
       break;
     }
     case CPB_MODEL_ENVELOPE: {
-      CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0, "negative beta (EnvelopeCosts.jl:47-49)");
-      CPB_REQUIRE(A.N > 0, "extrema of an empty collection");
-      DBuf<u32> ext(2);
-      const u32 init[2] = {0xffffffffu, 0u};
-      CPB_CUDA(cudaMemcpyAsync(ext.get(), init, sizeof(init), cudaMemcpyHostToDevice, ctx().stream));
-      CPB_LAUNCH(k_row_extrema, grid_for((size_t)A.N), 256, 0, A.row.get(), (size_t)A.N, ext.get());
-      u32 h[2];
-      CPB_CUDA(cudaMemcpyAsync(h, ext.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
-      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
-      const T body = c[1] * (T)A.n + c[2] * (T)A.N + c[3] * (T)((i64)h[1] - (i64)h[0]);
-      c_hi = c[0] + body;
-      c_lo = c[0] + jl_fld(body, (T)K);
+      // the oracle form (EnvelopeCosts.jl:30-42), the one partition_stripe(Bisect*) reaches: c_hi = ocl(1, n + 1) with the
+      // oracle's own left-to-right sum, c_lo = alpha + fld(c_hi - alpha, K); an empty pattern is fine (envelope width 0)
+      CPB_REQUIRE(c[1] >= 0 && c[2] >= 0 && c[3] >= 0, "negative beta (EnvelopeCosts.jl:34-36)");
+      c_hi = (T)query_one(f, 1, A.n + 1);
+      c_lo = c[0] + jl_fld(c_hi - c[0], (T)K);
       break;
     }
     default: throw Error(CPB_ERR_UNSUPPORTED, "bound_stripe has no method for this model in the reference");

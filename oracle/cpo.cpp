@@ -217,12 +217,19 @@ template <class T> static void bound_any(const cpo_model* mdl, const Mat& M, i64
   }
 }
 
-extern "C" int cpo_bound_stripe(const cpo_model* mdl, const cpo_csc* A, cpo_i64 K, int /*via_oracle*/, double out[2]) {
+// via_oracle != 0: the oracle form bound_stripe(A, K, ocl) -- what the Bisect splitters call; it differs from the model
+// form only for the envelope model (EnvelopeCosts.jl:30-42 vs :44-54: association of the sum, empty patterns)
+extern "C" int cpo_bound_stripe(const cpo_model* mdl, const cpo_csc* A, cpo_i64 K, int via_oracle, double out[2]) {
   CPO_TRY
   Mat M(A);
   with_type(mdl, [&](auto* tt) {
     using T = std::remove_pointer_t<decltype(tt)>;
-    bound_any<T>(mdl, M, K, out);
+    if (via_oracle && mdl->kind == CPO_MODEL_ENVELOPE) {
+      Model<T> m(mdl);
+      with_oracle<T>(mdl, 0, M, nullptr, 0, [&](auto& f) { bound_stripe<T>(M, K, m, &f, out); });
+    } else {
+      bound_any<T>(mdl, M, K, out);
+    }
   });
   CPO_CATCH
 }

@@ -73,12 +73,17 @@ template <class T, class F> static void bound_stripe(const Mat& A, i64 K, const 
     }
     case CPO_MODEL_ENVELOPE: {
       if (!(mdl.c[1] >= 0 && mdl.c[2] >= 0 && mdl.c[3] >= 0)) throw std::invalid_argument("negative beta");
-      i64 lo = std::numeric_limits<i64>::max(), hi = std::numeric_limits<i64>::min();
-      for (i64 q = 1; q <= N; ++q) { lo = std::min(lo, A.idx[q]); hi = std::max(hi, A.idx[q]); }
-      if (N == 0) throw std::invalid_argument("extrema of an empty collection");
-      T body = mdl.c[1] * (T)n + mdl.c[2] * (T)N + mdl.c[3] * (T)(hi - lo);
-      c_hi = mdl.c[0] + body;
-      c_lo = mdl.c[0] + jl_fld(body, (T)K);
+      if (ocl) {  // the ORACLE form (EnvelopeCosts.jl:30-42) -- what partition_stripe(Bisect*) calls: c_hi = ocl(1, n + 1)
+        c_hi = (*ocl)(1, n + 1, 1);
+        c_lo = mdl.c[0] + jl_fld(c_hi - mdl.c[0], (T)K);
+      } else {    // the model form (EnvelopeCosts.jl:44-54): extrema(A.rowval), body summed first
+        i64 lo = std::numeric_limits<i64>::max(), hi = std::numeric_limits<i64>::min();
+        for (i64 q = 1; q <= N; ++q) { lo = std::min(lo, A.idx[q]); hi = std::max(hi, A.idx[q]); }
+        if (N == 0) throw std::invalid_argument("extrema of an empty collection");
+        T body = mdl.c[1] * (T)n + mdl.c[2] * (T)N + mdl.c[3] * (T)(hi - lo);
+        c_hi = mdl.c[0] + body;
+        c_lo = mdl.c[0] + jl_fld(body, (T)K);
+      }
       break;
     }
     default: throw std::invalid_argument("bound_stripe is not defined for this model (MethodError in the reference)");

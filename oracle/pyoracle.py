@@ -189,10 +189,12 @@ def oracle_query(mdl, A, j, jp, k=None, hint=T.NoHint(), Pi=None) -> np.ndarray:
     return out
 
 
-def bound_stripe(A, K, mdl):
+def bound_stripe(A, K, mdl, via_oracle=True):
+    """``bound_stripe(A, K, ocl)`` (the oracle form every Bisect splitter calls; default) or, with ``via_oracle=False``,
+    ``bound_stripe(A, K, mdl)`` -- the two differ only for the envelope model (EnvelopeCosts.jl:30-42 vs :44-54)."""
     cm, keep = _model(mdl, A, T.CConstraint(), None)
     out = (ctypes.c_double * 2)()
-    _check(lib().cpo_bound_stripe(ctypes.byref(cm), ctypes.byref(_csc(A)), ctypes.c_longlong(K), 0, out))
+    _check(lib().cpo_bound_stripe(ctypes.byref(cm), ctypes.byref(_csc(A)), ctypes.c_longlong(K), int(bool(via_oracle)), out))
     return (out[0], out[1])
 
 

@@ -159,6 +159,19 @@ def test_column_block_oracle_wider_than_table(ref, fixtures):
     assert np.all(np.isinf(got[(jp - j) > 4]))
 
 
+def test_envelope_bound_is_the_oracle_form(ref, fixtures):
+    """partition_stripe(Bisect*) reaches bound_stripe(A, K, ocl) (EnvelopeCosts.jl:30-42): c_hi = ocl(1, n + 1) summed
+    left to right, c_lo = alpha + fld(c_hi - alpha, K) -- for Float64 models with alpha != 0 that differs from the model form
+    by roundings, and an empty pattern has a bound (no `extrema of an empty collection`)."""
+    f = cp.AffineEnvelopeModel(0.1, 0.7, 0.3, 1.9)
+    for A in [fixtures["LPnetlib/lp_blend"], fixtures["Pajek/GD99_c"], cp.SparseMatrixCSC(5, 4, [1, 1, 1, 1, 1], np.zeros(0, dtype=np.int64))]:
+        for K in (1, 3, 7):
+            assert cp.bound_stripe(A, K, f) == ref.bound_stripe(A, K, f, via_oracle=True), (A.n, K)
+        if A.nnz:
+            for mtd in (cp.BisectCostBottleneckSplitter(f, 0.01), cp.LazyBisectCostBottleneckSplitter(f, 0.01)):
+                assert np.array_equal(cp.partition_stripe(A, 5, mtd).spl, ref.partition_stripe(A, 5, mtd).spl)
+
+
 def test_bound_and_objective(ref, fixtures):
     rng = np.random.default_rng(104)
     for A in small_matrices(fixtures):

@@ -718,3 +718,21 @@ def test_plaid(ref, fixtures):
     check_split(Pi.spl, A.m, 8)
     check_split(Phi.spl, A.n, 8)
     assert Pi == Phi  # symmetric pattern: both stripe solves see the same matrix
+
+
+def test_envelope_bound_forms(ref, fixtures):
+    """bound_stripe(A, K, ocl) vs bound_stripe(A, K, mdl) for the envelope model (EnvelopeCosts.jl:30-42, 44-54): equal for Int64
+    coefficients, equal up to roundings for Float64 ones; only the oracle form accepts an empty pattern."""
+    import chainb200 as cp
+
+    A = fixtures["LPnetlib/lp_blend"]
+    fi = cp.AffineEnvelopeModel(2, 3, 1, 5)
+    ff = cp.AffineEnvelopeModel(0.1, 0.7, 0.3, 1.9)
+    for K in (1, 4, 9):
+        assert ref.bound_stripe(A, K, fi, via_oracle=True) == ref.bound_stripe(A, K, fi, via_oracle=False)
+        a, b = ref.bound_stripe(A, K, ff, via_oracle=True), ref.bound_stripe(A, K, ff, via_oracle=False)
+        assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]) + 1.0 and abs(a[1] - b[1]) <= 1e-9 * abs(b[1])
+    E = cp.SparseMatrixCSC(5, 4, [1, 1, 1, 1, 1], np.zeros(0, dtype=np.int64))
+    assert ref.bound_stripe(E, 2, fi, via_oracle=True) == (2 + (3 * 4) // 2, 2 + 3 * 4)
+    with pytest.raises(RuntimeError):
+        ref.bound_stripe(E, 2, fi, via_oracle=False)
