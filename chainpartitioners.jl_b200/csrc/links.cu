@@ -8,6 +8,7 @@
 // same row is simply the left neighbour inside the row run, and first/last columns are the run ends.
 #include "engine.cuh"
 #include "primitives.cuh"
+#include "onesweep.cuh"
 
 namespace cpb {
 
@@ -298,6 +299,15 @@ bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size
   }
   if (row_lo <= 0 && row_hi >= (i64)nrow) {
     trace_mark("degree_check");
+    const char* wmin_env0 = std::getenv("CPB_WINDOWED_SCATTER_MIN");  // (tests force the windowed form on small inputs; 0 = never)
+    const size_t wmin0 = wmin_env0 ? (size_t)std::atoll(wmin_env0) : ((size_t)1 << 25);
+    const char* os_env = std::getenv("CPB_ONESWEEP");  // 0: the tile-histogram sort of round 1 (kept for comparison)
+    if (onesweep_supported(N) && !(os_env && os_env[0] == '0')) {
+      // one-read-one-write radix passes on packed (row, position) pairs; the window pass forms the links while loading
+      DBuf<u64> a(N), b(N);
+      onesweep_links(row, N, bits_for(nrow ? nrow - 1 : 0), colidx, as_pos, 0u, prev, first_count, nullptr, wmin0, a.get(), b.get());
+      return false;
+    }
     TransposeOrder t;
     transpose_order(row, N, nrow ? nrow - 1 : 0, t);
     trace_mark("sort");
