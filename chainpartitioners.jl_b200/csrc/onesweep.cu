@@ -81,7 +81,7 @@ struct OsLinkArgs {
 // One tile of one pass.  FULLT: the tile holds OS_TILE pairs (no bounds checks).
 template <int MODE, bool FULLT>
 __device__ __forceinline__ void os_tile_body(const u32* __restrict__ keys32, const u64* __restrict__ in, u64* __restrict__ out, size_t n, int dshift,
-                                             u32 dstart, u32* __restrict__ state, const OsLinkArgs& la, u32 tile, u64* s_pair, u32 (*s_wh)[256],
+                                             u32 dstart, u32* __restrict__ state, const OsLinkArgs& la, u32 tile, u32 hot, u64* s_pair, u32 (*s_mask)[256], u32 (*s_cur)[256],
                                              u32* s_gbase, u32* s_scan) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const size_t tbase = (size_t)tile * OS_TILE;
@@ -130,34 +130,55 @@ __device__ __forceinline__ void os_tile_body(const u32* __restrict__ keys32, con
     if (lane == 0 && firsts && la.first_count) atomicAdd(la.first_count, firsts);
   }
 
-  // rank inside the warp: lanes holding the same digit in a round form a group (match); the group reads the warp's count of
-  // that digit so far, its first lane adds the group's size.  The matches do not depend on each other: all issued first.
+  // rank inside the warp: the lanes holding the same digit in a round form a group; the group reads the warp's count of the
+  // digit so far, its first lane adds the group's size.  Two ways to find the group (measured on B200, tools/ in
+  // profiles/r03_onesweep.md): MATCH.ANY costs ~2 cycles per DISTINCT value on the SM's one address-divergence unit (61
+  // cycles for random 8-bit digits, 1.7 ms per pass at 2.6e8 pairs; cheaper for skewed digits); through shared memory
+  // -- every lane ORs its bit into the (warp, digit) mask word and reads it back, the first lane clears it -- costs
+  // ~10 wavefronts per round for random digits (0.5 ms per pass) but lanes on the same word serialise (skewed digits).
+  // `hot` != 0 (the pass's most frequent digit holds more than 1/16 of the pairs): MATCH.ANY; else shared memory.
   // (ranks inside the warp fit 10 bits: two per register)
-  u32 mk[OS_IPT];
-#pragma unroll
-  for (int r = 0; r < OS_IPT; ++r) {
-    const u32 d = (u32)(pr[r] >> dshift) & 255u;
-    mk[r] = __match_any_sync(FULL, OS_OK(r) ? d : 0xffffffffu);
-  }
   const unsigned lt = (1u << lane) - 1u;
   u32 rk2[OS_IPT / 2];
+  if (hot) {
 #pragma unroll
-  for (int r = 0; r < OS_IPT; ++r) {
-    const u32 d = (u32)(pr[r] >> dshift) & 255u;
-    const unsigned m = mk[r];
-    u32 old = 0;
-    if (OS_OK(r)) old = s_wh[w][d];
-    __syncwarp();
-    if (OS_OK(r) && (m & lt) == 0u) s_wh[w][d] = old + (u32)__popc(m);
-    __syncwarp();
-    const u32 rank = old + (u32)__popc(m & lt);
-    if (r & 1) rk2[r >> 1] |= rank << 16; else rk2[r >> 1] = rank;
+    for (int r = 0; r < OS_IPT; ++r) {
+      const u32 d = (u32)(pr[r] >> dshift) & 255u;
+      const unsigned m = __match_any_sync(FULL, OS_OK(r) ? d : 0xffffffffu);
+      u32 cur = 0;
+      if (OS_OK(r)) cur = s_cur[w][d];
+      __syncwarp();
+      if (OS_OK(r) && (m & lt) == 0u) s_cur[w][d] = cur + (u32)__popc(m);
+      __syncwarp();
+      const u32 rank = cur + (u32)__popc(m & lt);
+      if (r & 1) rk2[r >> 1] |= rank << 16; else rk2[r >> 1] = rank;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+      const u32 d = (u32)(pr[r] >> dshift) & 255u;
+      if (OS_OK(r)) atomicOr(&s_mask[w][d], 1u << lane);
+      __syncwarp();
+      u32 m = 0, cur = 0;
+      if (OS_OK(r)) {
+        m = s_mask[w][d];
+        cur = s_cur[w][d];
+      }
+      __syncwarp();
+      if (OS_OK(r) && (m & lt) == 0u) {
+        s_mask[w][d] = 0u;
+        s_cur[w][d] = cur + (u32)__popc(m);
+      }
+      __syncwarp();
+      const u32 rank = cur + (u32)__popc(m & lt);
+      if (r & 1) rk2[r >> 1] |= rank << 16; else rk2[r >> 1] = rank;
+    }
   }
   __syncthreads();
   // digit `tid`: counts of the warps -> tile total, published at once
   u32 total = 0;
 #pragma unroll
-  for (int k = 0; k < OS_WARPS; ++k) total += s_wh[k][tid];
+  for (int k = 0; k < OS_WARPS; ++k) total += s_cur[k][tid];
   u32* const my_state = state + (size_t)tile * 256 + tid;
   st_state(my_state, (tile == 0 ? OS_INC : OS_AGG) | total);
   const u32 lbase = os_block_scan(total, s_scan);  // first staged slot of the digit
@@ -165,8 +186,8 @@ __device__ __forceinline__ void os_tile_body(const u32* __restrict__ keys32, con
     u32 run = lbase;
 #pragma unroll
     for (int k = 0; k < OS_WARPS; ++k) {
-      const u32 c = s_wh[k][tid];
-      s_wh[k][tid] = run;  // first slot of warp k's share of the digit
+      const u32 c = s_cur[k][tid];
+      s_cur[k][tid] = run;  // first slot of warp k's share of the digit
       run += c;
     }
   }
@@ -200,7 +221,7 @@ __device__ __forceinline__ void os_tile_body(const u32* __restrict__ keys32, con
 #pragma unroll
   for (int r = 0; r < OS_IPT; ++r) {
     const u32 d = (u32)(pr[r] >> dshift) & 255u;
-    if (OS_OK(r)) s_pair[s_wh[w][d] + ((r & 1) ? (rk2[r >> 1] >> 16) : (rk2[r >> 1] & 0xffffu))] = pr[r];
+    if (OS_OK(r)) s_pair[s_cur[w][d] + ((r & 1) ? (rk2[r >> 1] >> 16) : (rk2[r >> 1] & 0xffffu))] = pr[r];
   }
   __syncthreads();
   // copy-out: consecutive slots of one digit go to consecutive addresses
@@ -220,25 +241,39 @@ __global__ void __launch_bounds__(OS_THREADS, 3)
 k_os_pass(const u32* __restrict__ keys32, const u64* __restrict__ in, u64* __restrict__ out, size_t n, int dshift, const u32* __restrict__ ghist,
           u32* __restrict__ state, u32* __restrict__ counter, OsLinkArgs la) {
   extern __shared__ __align__(16) u64 s_pair[];  // OS_TILE staged pairs
-  __shared__ u32 s_wh[OS_WARPS][256];             // per-warp digit counts -> first slot of the warp's share of every digit
+  __shared__ u32 s_mask[OS_WARPS][256];           // per warp and digit: lanes holding the digit in the current round
+  __shared__ u32 s_cur[OS_WARPS][256];            // per warp and digit: count so far -> first slot of the warp's share of the digit
+  __shared__ u32 s_hot;
   __shared__ u32 s_gbase[256];                    // global index of a digit's first slot minus the slot
   __shared__ u32 s_scan[OS_WARPS];
   __shared__ u32 s_tile;
   const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(counter, 1u);
 #pragma unroll
-  for (int k = 0; k < OS_WARPS; ++k) s_wh[k][tid] = 0;
+  for (int k = 0; k < OS_WARPS; ++k) { s_mask[k][tid] = 0u; s_cur[k][tid] = 0u; }
   // where the digit `tid` starts in the output
   u32 dstart;
   if (MODE == 2) {
     dstart = (u32)min((unsigned long long)n, (unsigned long long)tid << dshift);
   } else {
-    dstart = os_block_scan(ghist[tid], s_scan);
+    const u32 g = ghist[tid];
+    dstart = os_block_scan(g, s_scan);
+    // is the pass's most frequent digit heavy (more than 1/16 of the pairs)?
+    const u32 best = __reduce_max_sync(FULL, g);
+    if ((tid & 31) == 0) s_scan[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+      u32 b = 0;
+      for (int k = 0; k < OS_WARPS; ++k) b = max(b, s_scan[k]);
+      s_hot = ((unsigned long long)b * 16ull > (unsigned long long)n) ? 1u : 0u;
+    }
   }
+  if (MODE == 2 && tid == 0) s_hot = 0u;  // (windows of the position: near-uniform digits)
   __syncthreads();
   const u32 tile = s_tile;
-  if ((size_t)(tile + 1) * OS_TILE <= n) os_tile_body<MODE, true>(keys32, in, out, n, dshift, dstart, state, la, tile, s_pair, s_wh, s_gbase, s_scan);
-  else os_tile_body<MODE, false>(keys32, in, out, n, dshift, dstart, state, la, tile, s_pair, s_wh, s_gbase, s_scan);
+  const u32 hot = s_hot;
+  if ((size_t)(tile + 1) * OS_TILE <= n) os_tile_body<MODE, true>(keys32, in, out, n, dshift, dstart, state, la, tile, hot, s_pair, s_mask, s_cur, s_gbase, s_scan);
+  else os_tile_body<MODE, false>(keys32, in, out, n, dshift, dstart, state, la, tile, hot, s_pair, s_mask, s_cur, s_gbase, s_scan);
 }
 
 static size_t os_tiles(size_t n) { return (n + OS_TILE - 1) / OS_TILE; }

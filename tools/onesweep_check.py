@@ -83,4 +83,20 @@ if "--c3" in sys.argv:
         print("onesweep", os_on, "resident ms", ["%.1f" % (t * 1e3) for t in ts], {k: round(v["ms"], 2) for k, v in prof.items() if k in keys}, flush=True)
     assert (spl["0"] == spl["1"]).all()
     print("identical split vectors")
+if "--er" in sys.argv:
+    # uniform digits, forced through the sort path
+    A = synth_torch.erdos_renyi(8_000_000, 16)
+    dA = check("er 8M x 16 (sort path forced)", A, with_numpy=False)
+    os.environ["CPB_NO_ROW_SEGMENTS"] = "1"
+    ocl = cp.oracle_stripe(AFF, dA)
+    buf = torch.zeros(A.nnz + A.n + 8, dtype=torch.int32, device="cuda")
+    for os_on in ("0", "1", "0", "1"):
+        os.environ["CPB_ONESWEEP"] = os_on
+        ocl.links_partial(1, A.m + 1, buf.data_ptr()); cp.synchronize()
+        cp.profile_enable(True); cp.profile_reset()
+        ocl.links_partial(1, A.m + 1, buf.data_ptr()); cp.synchronize()
+        prof = cp.profile_get(); cp.profile_enable(False)
+        keys = ("k_expand_columns", "k_os_hist", "k_os_pass", "k_link_prev", "k_rs_scatter", "k_rs_hist", "build_links")
+        print("er onesweep", os_on, "nnz", A.nnz, {k: round(v["ms"], 2) for k, v in prof.items() if k in keys}, flush=True)
+    os.environ.pop("CPB_NO_ROW_SEGMENTS"); os.environ.pop("CPB_ONESWEEP")
 print("onesweep check ok")
