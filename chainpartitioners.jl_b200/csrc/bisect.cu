@@ -429,6 +429,22 @@ __device__ __forceinline__ u32 stream_prefix(const u32* s_mask, const u32* s_cum
   return cnt;
 }
 
+// The same count when a group's flags are stored as one byte per lane (bit k of byte l = element 4 l + k of the group; 8 words
+// per group): what k_probe_stream writes since round 2 -- every thread stores the nibble of its own four compares, no
+// warp vote (VOTE runs on the SM's one address-divergence unit: 1024 votes per super-step were the tile phase's limiter).
+__device__ __forceinline__ u32 stream_prefix_nib(const u32* s_mask, const u32* s_cum, u32 x) {
+  const u32 g = x >> 7, r = x & 127u;
+  u32 cnt = s_cum[g];
+  const uint4 a = *reinterpret_cast<const uint4*>(&s_mask[g * 8]);
+  const uint4 b = *reinterpret_cast<const uint4*>(&s_mask[g * 8 + 4]);
+  const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const u32 full = r >> 4, q8 = ((r & 15u) >> 2) * 8u, t = r & 3u;
+  const u32 msk = ((1u << q8) - 1u) | (((1u << t) - 1u) << q8);
+#pragma unroll
+  for (u32 i = 0; i < 8; ++i) cnt += __popc(i < full ? w[i] : (i == full ? (w[i] & msk) : 0u));
+  return cnt;
+}
+
 struct DevStream {
   const u32* prev;    // [Ne] 1 + position of the previous nonzero of the same row (0 = none): "its column lies left of the part"
                       //      is simply prev <= first position of the part
@@ -522,7 +538,9 @@ __device__ __forceinline__ void bulk_load(u32 dst, const void* src, u32 bytes, u
 __device__ unsigned long long g_probe_t[8];
 __device__ unsigned long long g_probe_n;
 __device__ unsigned long long g_probe_parts[4];  // per slot 0..3: parts started
-#define PT(i) do { if (node == 0 && crank == 0 && tid == 0) { unsigned long long _t = clock64(); g_probe_t[i] += _t - t_last; t_last = _t; } } while (0)
+__device__ unsigned long long g_probe_node[16][4];  // per slot: cycles of its cluster, super-steps, parts, launches
+// (accumulated in shared memory by one thread and flushed at the end: a global read-modify-write per mark costs an L2 round trip)
+#define PT(i) do { if (node == node_base && crank == 0 && tid == 0) { unsigned long long _t = clock64(); s_pt[i] += _t - t_last; t_last = _t; } } while (0)
 #else
 #define PT(i) do {} while (0)
 #endif
@@ -534,7 +552,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
                    int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c,
                    const int* __restrict__ node_ids, int node_base) {
-  __shared__ __align__(16) u32 s_mask[SP_GROUPS * 4 + 4];
+  __shared__ __align__(16) u32 s_mask[SP_GROUPS * 8 + 8];  // one byte per lane and group: the lane's four `prev <= e0` flags
   __shared__ u32 s_cum[SP_GROUPS + 1];
   __shared__ double s_c;
   __shared__ int s_valid;
@@ -553,7 +571,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   const bool writer = crank == 0 && tid == 0;
   if (tid == 0) {
     s_valid = node_threshold(st, eps1, node_ids[node], &s_c);
-    for (int k = 0; k < 4; ++k) s_mask[SP_GROUPS * 4 + k] = 0;
+    for (int k = 0; k < 8; ++k) s_mask[SP_GROUPS * 8 + k] = 0;
     for (int k = 0; k < 4; ++k) { s_red[0][k] = 0; s_red[1][k] = 0; }
     if (AX) {
       for (int x = 0; x < 2; ++x)
@@ -568,6 +586,13 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   }
   if (AX) cluster.sync();  // every CTA's mbarriers exist before a peer's st.async can reach them
   u32 sstep = 0;
+#ifdef CPB_PROBE_TIMING
+  __shared__ unsigned long long s_pt[8];
+  if (tid == 0) for (int i = 0; i < 8; ++i) s_pt[i] = 0;
+  const long long t_node0 = clock64();
+  unsigned long long t_last = clock64();
+  u32 parts_run = 0;
+#endif
   const double c = s_c;
   const u32 n1 = s.n + 1;
   const u32 Ne = s.Ne;
@@ -584,7 +609,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     const u32 e0 = pcur;
     const i64 wj = (i64)wcur;
 #ifdef CPB_PROBE_TIMING
-    if (node < 4 && crank == 0 && tid == 0) g_probe_parts[node] += 1;
+    parts_run += 1;
 #endif
     u32 jlast = j;
     u32 grun = 0;
@@ -594,9 +619,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       const u32 TE = CE * BS_CLUSTER;
       const u32 ngroups = nv * 32u;
 #ifdef CPB_PROBE_TIMING
-      unsigned long long t_last = clock64();
-      if (node == 0 && crank == 0 && tid == 0) g_probe_n += 1;
-      if (node == 1 && crank == 0 && tid == 0) g_probe_parts[3] += 1;  // super-steps of slot 1
+      PT(6);  // between the super-steps (part bookkeeping)
 #endif
       const u32 e_c = e_tile + crank * CE;
       // ---- column boundaries whose element offset falls into (e_c, e_c + CE] (loads issued ahead of the tile) ----
@@ -605,13 +628,12 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
       if (e_c >= Ne && !(first && crank == 0)) jb = 0;
       else jb = ((u64)e_c + CE >= Ne) ? n1 : __ldg(s.colidx + e_c + CE) + 1;
-      // ---- bit masks of `prev < j`: each warp owns nv consecutive 128-element groups (one warp-wide 128-bit load and
-      //      4 ballots per group) and keeps the running count of its own groups ----
+      // ---- flags of `prev <= e0`: each warp owns nv consecutive 128-element groups (one warp-wide 128-bit load per group);
+      //      every lane stores the nibble of its four compares as one byte, the group totals come from two packed warp
+      //      reductions.  (Round 1 formed the masks with 4 ballots per group: 1024 VOTEs per CTA and super-step on the SM's one
+      //      address-divergence unit -- ~3 cycles each, measured with scratch/ubench -- were what bounded this phase.) ----
       u32 wsum = 0;
-      // (the ballot phase is issue-bound -- an experiment with the loads removed still spent 4.9 k of its 7.9 k cycles
-      //  here -- so groups that lie entirely inside [e0, Ne) take a path without the head / tail predicates, and one
-      //  lane stores the four masks with a single 128-bit store)
-      // all loads of the super-step are issued before the first ballot (one exposed memory latency instead of nv)
+      // all loads of the super-step are issued before the first compare (one exposed memory latency instead of nv)
       uint4 pv[SP_VEC];
 #pragma unroll
       for (int v = 0; v < SP_VEC; ++v) {
@@ -627,29 +649,33 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
           }
         }
       }
+      unsigned char* const s_nib = reinterpret_cast<unsigned char*>(s_mask);
+      u32 pkA = 0, pkB = 0;  // flag counts of the warp's groups, one byte per group (<= 128 each)
 #pragma unroll
       for (int v = 0; v < SP_VEC; ++v) {
         if (v >= (int)nv) break;
         const u32 g = warp * nv + v;
         const u32 gbase = e_c + g * 128;  // first element of the group (warp-uniform)
-        unsigned m0, m1, m2, m3;
+        u32 nib;
         if (gbase >= e0) {
-          m0 = __ballot_sync(0xffffffffu, pv[v].x <= e0);
-          m1 = __ballot_sync(0xffffffffu, pv[v].y <= e0);
-          m2 = __ballot_sync(0xffffffffu, pv[v].z <= e0);
-          m3 = __ballot_sync(0xffffffffu, pv[v].w <= e0);
+          nib = (u32)(pv[v].x <= e0) | ((u32)(pv[v].y <= e0) << 1) | ((u32)(pv[v].z <= e0) << 2) | ((u32)(pv[v].w <= e0) << 3);
         } else {  // the group holding the part's first element: mask what lies in front of it
           const u32 idx = gbase + lane * 4;
-          m0 = __ballot_sync(0xffffffffu, pv[v].x <= e0 && idx + 0 >= e0);
-          m1 = __ballot_sync(0xffffffffu, pv[v].y <= e0 && idx + 1 >= e0);
-          m2 = __ballot_sync(0xffffffffu, pv[v].z <= e0 && idx + 2 >= e0);
-          m3 = __ballot_sync(0xffffffffu, pv[v].w <= e0 && idx + 3 >= e0);
+          nib = (u32)(pv[v].x <= e0 && idx + 0 >= e0) | ((u32)(pv[v].y <= e0 && idx + 1 >= e0) << 1) | ((u32)(pv[v].z <= e0 && idx + 2 >= e0) << 2) |
+                ((u32)(pv[v].w <= e0 && idx + 3 >= e0) << 3);
         }
-        if (lane == 0) {
-          *reinterpret_cast<uint4*>(&s_mask[g * 4]) = make_uint4(m0, m1, m2, m3);
-          s_cum[g] = wsum;  // prefix inside the warp's run; the warp's base is added after the barrier
-        }
-        wsum += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        s_nib[g * 32 + lane] = (unsigned char)nib;
+        const u32 pc = (u32)__popc(nib);
+        if (v < 4) pkA += pc << (8 * v); else pkB += pc << (8 * (v - 4));
+      }
+      {
+        const u32 A = __reduce_add_sync(0xffffffffu, pkA);
+        const u32 B = (nv > 4) ? __reduce_add_sync(0xffffffffu, pkB) : 0u;
+        // lane v: flags in the warp's groups before group v (prefix inside the warp's run; the warp's base is added after the barrier)
+        const u32 mA = lane >= 4 ? 0xffffffffu : ((1u << (8 * lane)) - 1u);
+        const u32 mB = lane <= 4 ? 0u : (lane >= 8 ? 0xffffffffu : ((1u << (8 * (lane - 4))) - 1u));
+        if (lane < (int)nv) s_cum[warp * nv + lane] = __dp4a(A & mA, 0x01010101u, __dp4a(B & mB, 0x01010101u, 0u));
+        wsum = __dp4a(A, 0x01010101u, __dp4a(B, 0x01010101u, 0u));
       }
       if (lane == 0) s_wtot[warp] = wsum;
       PT(0);
@@ -667,7 +693,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
           if (lane == 0) {
             s_cum[ngroups] = tot_c;
             // sentinel masks behind the last group (prefix lookups at x == CE)
-            s_mask[ngroups * 4] = 0; s_mask[ngroups * 4 + 1] = 0; s_mask[ngroups * 4 + 2] = 0; s_mask[ngroups * 4 + 3] = 0;
+            *reinterpret_cast<uint4*>(&s_mask[ngroups * 8]) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(&s_mask[ngroups * 8 + 4]) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
       }
@@ -709,7 +736,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         tile_tot += v;
       }
       auto feasible_pw = [&](u32 jp, u32 pj, u32 w) -> bool {
-        const u32 g = grun + base_c + stream_prefix(s_mask, s_cum, pj - e_c);
+        const u32 g = grun + base_c + stream_prefix_nib(s_mask, s_cum, pj - e_c);
         return cost_leq(stream_cost<T>(s, (i64)jp - (i64)j, (i64)w - wj, (i64)g), c);
       };
       // monotone costs: the feasible boundaries of this CTA form a prefix [ja, ja + cnt); every thread stashes the
@@ -795,6 +822,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
           nbs += q.y;
           if (q.x > 0) { pcur = q.z; wcur = q.w; }  // the last CTA with a feasible boundary wins
         }
+        PT(7);
       } else {
         if (tid < BS_CLUSTER) {
           *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
@@ -843,6 +871,16 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   if (writer) {
     node_c[node] = c;
     node_res[node] = (!broke && feasible) ? 2 : 1;
+#ifdef CPB_PROBE_TIMING
+    if (node - node_base < 16) {
+      unsigned long long* g = g_probe_node[node - node_base];
+      g[0] += (unsigned long long)(clock64() - t_node0); g[1] += sstep; g[2] += parts_run; g[3] += 1;
+    }
+    if (node == node_base) {
+      for (int i = 0; i < 8; ++i) g_probe_t[i] += s_pt[i];
+      g_probe_n += sstep;
+    }
+#endif
   }
   cluster.sync();
 }
@@ -1754,8 +1792,17 @@ void probe_timing_dump() {
   unsigned long long t[8], n;
   cudaMemcpyFromSymbol(t, g_probe_t, sizeof(t));
   cudaMemcpyFromSymbol(&n, g_probe_n, sizeof(n));
-  const char* names[6] = {"loads+ballots", "syncthreads", "scan(warp0)", "push+cluster.sync#1", "boundaries", "push+cluster.sync#2"};
-  for (int i = 0; i < 6; ++i) std::printf("probe_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / (double)std::max<unsigned long long>(n, 1));
+  {
+    unsigned long long nd[16][4];
+    cudaMemcpyFromSymbol(nd, g_probe_node, sizeof(nd));
+    for (int i = 0; i < 16; ++i)
+      if (nd[i][3]) std::printf("probe_timing slot %2d: launches %llu, per launch: %.0f cycles, %.1f super-steps, %.1f parts, %.0f cycles/super-step\n", i, nd[i][3],
+                                (double)nd[i][0] / nd[i][3], (double)nd[i][1] / nd[i][3], (double)nd[i][2] / nd[i][3], (double)nd[i][0] / std::max<unsigned long long>(nd[i][1], 1));
+    unsigned long long z[16][4] = {{0}};
+    cudaMemcpyToSymbol(g_probe_node, z, sizeof(z));
+  }
+  const char* names[8] = {"loads+flags", "syncthreads", "scan(warp0)", "push+exchange 1", "boundaries", "push+exchange 2", "between super-steps", "read exchange 2"};
+  for (int i = 0; i < 8; ++i) std::printf("probe_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / (double)std::max<unsigned long long>(n, 1));
   std::printf("probe_timing super-steps %llu\n", n);
   unsigned long long parts[4];
   cudaMemcpyFromSymbol(parts, g_probe_parts, sizeof(parts));
