@@ -1345,7 +1345,9 @@ __global__ void k_ub_splits(const __grid_constant__ DevStream s, int is_float, i
   spl[k] = (k == 0) ? 1 : (k == K ? (int)n1 : (int)lo);
   if (k < K) cnt[k] = 0;
 }
-__global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStream s, const int* __restrict__ spl, u32* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStream s, const int* __restrict__ spl, u32* __restrict__ cnt,
+                                                  const int* __restrict__ stop = nullptr) {
+  if (stop && *stop) return;
   const int k = blockIdx.y;
   const u32 j = (u32)spl[k];
   const u32 e0 = __ldg(s.P + j), e1 = __ldg(s.P + (u32)spl[k + 1]);
@@ -1373,6 +1375,11 @@ __global__ void __launch_bounds__(256) k_ub_count(const __grid_constant__ DevStr
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
 }
+__global__ void k_ub_zero(u32* __restrict__ cnt, int K, const int* __restrict__ stop) {
+  if (*stop) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) cnt[k] = 0;
+}
 __global__ void k_ub_max(const __grid_constant__ DevStream s, int is_float, int K, const int* __restrict__ spl, const u32* __restrict__ cnt,
                          double* __restrict__ out) {
   __shared__ double sm[32];
@@ -1391,6 +1398,161 @@ __global__ void k_ub_max(const __grid_constant__ DevStream s, int is_float, int 
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmax(best, sm[w]);
     out[0] = best;
   }
+}
+
+// ---- refinement of the bounding partition (round 2).  A partition whose parts all cost the same is optimal for a cost that
+//      grows with the part (a partition with a smaller bottleneck would have to end every part earlier, including the last),
+//      so the bound is tight when the exact part costs are balanced.  One refinement step rescales the additive weight U
+//      inside every part so that the part weighs its exact cost, and cuts the rescaled weight greedily at the smallest
+//      threshold that needs at most K parts (a column heavier than the mean share stays alone -- equal-share cuts cannot do
+//      that); the new partition is evaluated exactly by k_ub_count again.  On R-MAT the first bound is 20-40 % above the
+//      optimum, one or two steps bring it within ~1 % (scratch/ub_refine_proto.py), which lets one round of speculated
+//      thresholds finish the bisection.  Only the plan depends on the bound.
+static constexpr int UB_G = 32768;      // grid points of the rescaled weight (uniform in weight)
+static constexpr int UB_T = 1024;       // candidate thresholds of the parametric search, one per thread
+static constexpr int UB_KMAX = 4096;    // parts (the candidates' cut lists live in a [UB_T][K + 1] scratch array)
+struct UbCtl { double best; double total; double tlo; int stop; int pad; };
+
+// exact part costs -> ctl.best = min(ctl.best, bottleneck); prefix S[k] of (cost - alpha), per-part scale of U
+__global__ void __launch_bounds__(1024) k_ub_prepare(const __grid_constant__ DevStream s, int is_float, int K, const int* __restrict__ spl,
+                                                     const u32* __restrict__ cnt, double* __restrict__ S, double* __restrict__ scale,
+                                                     UbCtl* __restrict__ ctl, double* __restrict__ out, int first, double tol) {
+  __shared__ double sm[32];
+  __shared__ double s_carry;
+  double cf[4];
+  for (int t = 0; t < 4; ++t) cf[t] = is_float ? s.cf[t] : (double)s.ci[t];
+  double ucf[4] = {cf[0], cf[1], cf[2], cf[3]};
+  if (!(ucf[1] + ucf[2] + ucf[3] > 0)) { ucf[1] = 1; ucf[2] = 0; ucf[3] = 0; }
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  double best = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += 1024) {
+    const int k = k0 + tid;
+    double wk = 0;
+    if (k < K) {
+      const u32 a = (u32)spl[k], b = (u32)spl[k + 1];
+      const double c = cf[0] + (double)(b - a) * cf[1] + ((double)__ldg(s.Wt + b) - (double)__ldg(s.Wt + a)) * cf[2] + (double)cnt[k] * cf[3];
+      best = fmax(best, c);
+      wk = fmax(c - cf[0], 0.0);
+      const double du = ub_weight(s, ucf, b) - ub_weight(s, ucf, a);
+      scale[k] = du > 0 ? wk / du : 0.0;
+    }
+    double inc = wk;  // inclusive scan over the 1024 threads
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    double wb = s_carry;
+    for (int q = 0; q < w; ++q) wb += sm[q];
+    if (k < K) S[k] = wb + inc - wk;
+    __syncthreads();
+    if (tid == 1023) s_carry = wb + inc;
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) sm[w] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 1; q < 32; ++q) best = fmax(best, sm[q]);
+    const double total = s_carry;
+    S[K] = total;
+    const double prev = first ? 0.0 : ctl->best;
+    const double b = first ? best : fmin(prev, best);
+    ctl->best = b;
+    ctl->total = total;
+    ctl->tlo = total / (double)K;
+    if (first) ctl->stop = 0;
+    // balanced well inside the bisection's tolerance, or the last step gained less than 0.3 %: nothing left to gain
+    if (!(best - cf[0] > (1.0 + fmax(0.004, tol)) * (total / (double)K))) ctl->stop = 1;
+    if (!first && !(best < 0.997 * prev)) ctl->stop = 1;
+    out[0] = b;
+    out[1] = ctl->stop ? 1.0 : 0.0;
+  }
+}
+
+// grid point i = the last column boundary whose rescaled weight is at most i / UB_G of the total
+__global__ void __launch_bounds__(256) k_ub_grid(const __grid_constant__ DevStream s, int is_float, int K, const int* __restrict__ spl,
+                                                 const double* __restrict__ S, const double* __restrict__ scale, const UbCtl* __restrict__ ctl,
+                                                 u32* __restrict__ gx, float* __restrict__ gw) {
+  if (ctl->stop) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i > UB_G) return;
+  double cf[4];
+  for (int t = 0; t < 4; ++t) cf[t] = is_float ? s.cf[t] : (double)s.ci[t];
+  if (!(cf[1] + cf[2] + cf[3] > 0)) { cf[1] = 1; cf[2] = 0; cf[3] = 0; }
+  const double total = S[K];
+  const double target = total * ((double)i / (double)UB_G);
+  int lo = 0, hi = K;  // largest k < K with S[k] <= target (k = K - 1 at the very end)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (S[mid] <= target) lo = mid; else hi = mid;
+  }
+  const int k = lo;
+  const u32 a = (u32)spl[k], b = (u32)spl[k + 1];
+  const double ua = ub_weight(s, cf, a), sc = scale[k];
+  u32 x = a;
+  if (i == UB_G) x = s.n + 1;
+  else if (sc > 0) {
+    const double ut = ua + (target - S[k]) / sc;
+    u32 l = a, h = b;  // largest x in [a, b] with U(x) <= ut
+    while (l < h) {
+      const u32 mid = l + ((h - l + 1) >> 1);
+      if (ub_weight(s, cf, mid) <= ut) l = mid; else h = mid - 1;
+    }
+    x = l;
+  }
+  gx[i] = x;
+  // rescaled weight at x: x lies in [a, b] of part k
+  gw[i] = (float)(i == UB_G ? total : S[k] + sc * (ub_weight(s, cf, x) - ua));
+}
+
+// parametric search: thread t cuts the grid greedily at threshold T_t (geometric ladder from the mean share to eight times
+// the mean share: a column may outweigh the mean share by far); the smallest threshold that places every
+// column in at most K parts gives the new partition
+__global__ void __launch_bounds__(UB_T) k_ub_greedy(int K, const UbCtl* __restrict__ ctl, const u32* __restrict__ gx, const float* __restrict__ gw_g,
+                                                    u32* __restrict__ cuts, int* __restrict__ spl) {
+  extern __shared__ float s_gw[];  // UB_G + 1
+  __shared__ int s_first;
+  if (ctl->stop) return;
+  const int tid = threadIdx.x;
+  for (int i = tid; i <= UB_G; i += UB_T) s_gw[i] = gw_g[i];
+  if (tid == 0) s_first = UB_T;
+  __syncthreads();
+  const float total = s_gw[UB_G];
+  const double tlo = ctl->tlo;
+  const float T = (float)(tlo * exp2(3.0 * (double)tid / (double)(UB_T - 1)));
+  const float w0 = total / (float)UB_G;
+  u32* my = cuts + (size_t)tid * (K + 1);
+  int i = 0;
+  bool ok = true;
+  my[0] = 0;
+  for (int k = 1; k <= K; ++k) {
+    if (i < UB_G) {
+      const float target = s_gw[i] + T;
+      int lo = i, hi = UB_G;  // largest index with s_gw <= target
+      const int g = min(UB_G, i + (int)(T / w0));
+      if (s_gw[g] <= target) { lo = g; const int g2 = min(UB_G, g + 8); if (s_gw[g2] > target) hi = g2; }
+      else { hi = g; const int g2 = max(i, g - 8); if (s_gw[g2] <= target) lo = g2; }
+      while (lo < hi) {
+        const int mid = lo + ((hi - lo + 1) >> 1);
+        if (s_gw[mid] <= target) lo = mid; else hi = mid - 1;
+      }
+      // (grid points that share a column boundary carry the same weight: move to the last of them)
+      if (lo == i) { ok = false; break; }  // one step outweighs T
+      i = lo;
+    }
+    my[k] = (u32)i;
+  }
+  ok = ok && i == UB_G;
+  if (ok) atomicMin(&s_first, tid);
+  __syncthreads();
+  const int best = s_first;
+  if (best >= UB_T) return;  // no candidate placed every column: keep the partition
+  const u32* src = cuts + (size_t)best * (K + 1);
+  for (int k = tid; k <= K; k += UB_T) spl[k] = (k == 0) ? 1 : (int)gx[src[k]];
 }
 
 // The same bound for the models probed through the dominance index: parts cut at equal shares of (columns + pins),
@@ -1525,15 +1687,51 @@ static void stream_view(Oracle& f, DevStream& ds) {
   for (int t = 0; t < 4; ++t) { ds.cf[t] = f.dev.cf[t]; ds.ci[t] = f.dev.ci[t]; }
 }
 
-// planner's upper bound (see k_ub_splits) into d_out[0]; asynchronous
-static void launch_upper_bound(Oracle& f, const DevStream& ds, i64 K, double* d_out) {
+// planner's upper bound (see k_ub_splits, k_ub_prepare) into d_out[0]; d_out[1] = 1 when the bounding partition is balanced
+// (or cannot be refined); asynchronous
+struct UbWork {
+  DBuf<int> spl;
+  DBuf<u32> cnt;
+  DBuf<double> S, scale;
+  DBuf<UbCtl> ctl;
+  unsigned slices = 1;
+  int steps = 0;
+};
+static void launch_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps, double* d_out, UbWork& w) {
   ProfScope pk("probe_plan_bound");
-  DBuf<int> ub_spl(K + 1);
-  DBuf<u32> ub_cnt(K);
-  CPB_LAUNCH(k_ub_splits, (unsigned)((K + 1 + 255) / 256), 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get());
-  const unsigned slices = (unsigned)std::min<i64>(64, std::max<i64>(1, ((i64)ctx().sm_count * 8 + K - 1) / K));
-  CPB_LAUNCH(k_ub_count, dim3(slices, (unsigned)K, 1), 256, 0, ds, ub_spl.get(), ub_cnt.get());
-  CPB_LAUNCH(k_ub_max, 1, 256, 0, ds, f.dev.is_float, (int)K, ub_spl.get(), ub_cnt.get(), d_out);
+  w.spl.alloc(K + 1);
+  w.cnt.alloc(K);
+  CPB_LAUNCH(k_ub_splits, (unsigned)((K + 1 + 255) / 256), 256, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get());
+  w.slices = (unsigned)std::min<i64>(64, std::max<i64>(1, ((i64)ctx().sm_count * 8 + K - 1) / K));
+  CPB_LAUNCH(k_ub_count, dim3(w.slices, (unsigned)K, 1), 256, 0, ds, w.spl.get(), w.cnt.get(), (const int*)nullptr);
+  w.steps = (K <= UB_KMAX && f.A->n >= 4 * K) ? env_int("CPB_UB_REFINE", 3) : 0;
+  if (w.steps <= 0) {
+    CPB_LAUNCH(k_ub_max, 1, 256, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get(), d_out);
+    return;
+  }
+  w.S.alloc(K + 1);
+  w.scale.alloc(K);
+  w.ctl.alloc(1);
+  CPB_LAUNCH(k_ub_prepare, 1, 1024, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get(), w.S.get(), w.scale.get(), w.ctl.get(), d_out, 1, eps / 4);
+}
+// refinement steps of the bounding partition (the host saw that it is not balanced); asynchronous
+static void refine_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps, double* d_out, UbWork& w) {
+  ProfScope pk("probe_plan_bound");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPB_CUDA(cudaFuncSetAttribute(k_ub_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UB_G + 1) * sizeof(float))));
+    attr_set = true;
+  }
+  DBuf<u32> gx(UB_G + 1), cuts((size_t)UB_T * (K + 1));
+  DBuf<float> gw(UB_G + 1);
+  int* const stop = &w.ctl.get()->stop;
+  for (int it = 0; it < w.steps; ++it) {
+    CPB_LAUNCH(k_ub_grid, (UB_G + 256) / 256, 256, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.S.get(), w.scale.get(), w.ctl.get(), gx.get(), gw.get());
+    CPB_LAUNCH(k_ub_greedy, 1, UB_T, (UB_G + 1) * sizeof(float), (int)K, w.ctl.get(), gx.get(), gw.get(), cuts.get(), w.spl.get());
+    CPB_LAUNCH(k_ub_zero, (unsigned)((K + 255) / 256), 256, 0, w.cnt.get(), (int)K, stop);
+    CPB_LAUNCH(k_ub_count, dim3(w.slices, (unsigned)K, 1), 256, 0, ds, w.spl.get(), w.cnt.get(), stop);
+    CPB_LAUNCH(k_ub_prepare, 1, 1024, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get(), w.S.get(), w.scale.get(), w.ctl.get(), d_out, 0, eps / 4);
+  }
 }
 
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
@@ -1561,15 +1759,18 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     }
     trace_mark("links");
     const bool want_ub = run->adaptive && K >= 2 && K <= 65535 && A.n >= 1;  // (K is the y extent of the counting grid)
-    DBuf<double> ub_out(1);
+    DBuf<double> ub_out(2);
+    UbWork ubw;
+    double h_ub[2] = {0, 1};
     for (int attempt = 0; attempt < 2; ++attempt) {
       stream_view(f, run->ds);
-      if (want_ub) launch_upper_bound(f, run->ds, K, ub_out.get());
+      if (want_ub) launch_upper_bound(f, run->ds, K, eps, ub_out.get(), ubw);
       u32 info[2] = {0, 0}, n_over = 0;
       CPB_CUDA(cudaMemcpyAsync(info, f.ls->first_count.get(), sizeof(info), cudaMemcpyDeviceToHost, ctx().stream));
       if (dia) CPB_CUDA(cudaMemcpyAsync(&n_over, f.overpos.get() + A.n, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
-      if (want_ub) CPB_CUDA(cudaMemcpyAsync(&run->ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+      if (want_ub) CPB_CUDA(cudaMemcpyAsync(h_ub, ub_out.get(), (ubw.steps > 0 ? 2 : 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
       CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      run->ub = h_ub[0];
       if (f.ls->speculative && !dia) A.max_row_deg = (i64)info[1];
       if (f.ls->speculative && info[1] > LT_MAX_DEG) {  // a heavy row: the row-segment kernels did nothing -> stable sort
         ProfScope prof("oracle_stripe");
@@ -1580,6 +1781,13 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
       f.ls->speculative = false;
       f.ls->h_first_count = info[0];
       if (dia) f.h_n_over = n_over;
+      if (want_ub && ubw.steps > 0 && h_ub[1] == 0.0) {
+        // the bounding partition is not balanced: refine it (a second, short round trip -- only where it can save a round)
+        refine_upper_bound(f, run->ds, K, eps, ub_out.get(), ubw);
+        CPB_CUDA(cudaMemcpyAsync(h_ub, ub_out.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+        CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+        run->ub = h_ub[0];
+      }
       break;
     }
   } else {
