@@ -535,7 +535,7 @@ __device__ __forceinline__ void bulk_load(u32 dst, const void* src, u32 bytes, u
 }
 
 #ifdef CPB_PROBE_TIMING
-__device__ unsigned long long g_probe_t[8];
+__device__ unsigned long long g_probe_t[16];
 __device__ unsigned long long g_probe_n;
 __device__ unsigned long long g_probe_parts[4];  // per slot 0..3: parts started
 __device__ unsigned long long g_probe_node[16][4];  // per slot: cycles of its cluster, super-steps, parts, launches
@@ -587,8 +587,8 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   if (AX) cluster.sync();  // every CTA's mbarriers exist before a peer's st.async can reach them
   u32 sstep = 0;
 #ifdef CPB_PROBE_TIMING
-  __shared__ unsigned long long s_pt[8];
-  if (tid == 0) for (int i = 0; i < 8; ++i) s_pt[i] = 0;
+  __shared__ unsigned long long s_pt[16];
+  if (tid == 0) for (int i = 0; i < 16; ++i) s_pt[i] = 0;
   const long long t_node0 = clock64();
   unsigned long long t_last = clock64();
   u32 parts_run = 0;
@@ -614,6 +614,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     u32 jlast = j;
     u32 grun = 0;
     bool first = true, missed = false;
+    PT(10);
     for (u32 e_tile = e0 & ~3u;;) {  // 16-byte aligned tiles; elements left of e0 are masked out
       const u32 CE = (u32)SP_THREADS * 4u * nv;  // elements of this CTA in this super-step
       const u32 TE = CE * BS_CLUSTER;
@@ -858,6 +859,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       nv_est = missed ? (u32)SP_VEC : max(min(max(want, 2u), (u32)SP_VEC), nv_est > 2u ? nv_est - 1u : 2u);
       nv = nv_est;
     }
+    PT(8);
     if (k == K) { feasible = (jlast == n1); break; }
     if (jlast == n1) {  // every column is placed: the remaining parts are empty (their cost was tested at the loop top)
       if (writer)
@@ -867,6 +869,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     }
     if (writer) spl[k + 1] = (int)jlast;
     j = jlast;
+    PT(9);
   }
   if (writer) {
     node_c[node] = c;
@@ -877,7 +880,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       g[0] += (unsigned long long)(clock64() - t_node0); g[1] += sstep; g[2] += parts_run; g[3] += 1;
     }
     if (node == node_base) {
-      for (int i = 0; i < 8; ++i) g_probe_t[i] += s_pt[i];
+      for (int i = 0; i < 16; ++i) g_probe_t[i] += s_pt[i];
       g_probe_n += sstep;
     }
 #endif
@@ -1997,7 +2000,7 @@ void ring_timing_dump() {
   cudaMemcpyToSymbol(g_ring_n, z, sizeof(n));
 }
 void probe_timing_dump() {
-  unsigned long long t[8], n;
+  unsigned long long t[16], n;
   cudaMemcpyFromSymbol(t, g_probe_t, sizeof(t));
   cudaMemcpyFromSymbol(&n, g_probe_n, sizeof(n));
   {
@@ -2009,8 +2012,9 @@ void probe_timing_dump() {
     unsigned long long z[16][4] = {{0}};
     cudaMemcpyToSymbol(g_probe_node, z, sizeof(z));
   }
-  const char* names[8] = {"loads+flags", "syncthreads", "scan(warp0)", "push+exchange 1", "boundaries", "push+exchange 2", "between super-steps", "read exchange 2"};
-  for (int i = 0; i < 8; ++i) std::printf("probe_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / (double)std::max<unsigned long long>(n, 1));
+  const char* names[11] = {"loads+flags", "syncthreads", "scan(warp0)", "push+exchange 1", "boundaries", "push+exchange 2", "top of the tile loop", "read exchange 2",
+                           "loop exit + tile estimate", "part bookkeeping", "top of the part loop"};
+  for (int i = 0; i < 11; ++i) std::printf("probe_timing %-22s %8.1f cycles/super-step\n", names[i], (double)t[i] / (double)std::max<unsigned long long>(n, 1));
   std::printf("probe_timing super-steps %llu\n", n);
   unsigned long long parts[4];
   cudaMemcpyFromSymbol(parts, g_probe_parts, sizeof(parts));

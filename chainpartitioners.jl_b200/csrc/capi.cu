@@ -577,6 +577,7 @@ int cpb_partition_stripe(cpb_oracle* f, int method, const cpb_constraint* con, d
     case CPB_SPLIT_DYNAMIC_BOTTLENECK: case CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER: solve_dynamic(*f->O, false, con, K, spl_out); break;
     case CPB_SPLIT_DYNAMIC_TOTAL: case CPB_SPLIT_DYNAMIC_TOTAL_CHUNKER: solve_dynamic(*f->O, true, con, K, spl_out); break;
     case CPB_SPLIT_CONVEX_TOTAL: solve_convex_splitter(*f->O, con, K, spl_out); break;
+    case CPB_SPLIT_CONCAVE_TOTAL: solve_concave_splitter(*f->O, con, K, spl_out); break;
     case CPB_SPLIT_BISECT_COST: solve_bisect(*f->O, false, eps, K, spl_out); break;
     case CPB_SPLIT_LAZY_BISECT_COST: solve_bisect(*f->O, true, eps, K, spl_out); break;
     case CPB_SPLIT_BISECT_INDEX: solve_bisect_index(*f->O, K, spl_out); break;

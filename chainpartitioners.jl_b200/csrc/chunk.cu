@@ -775,7 +775,11 @@ void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, dou
       }
       return;
     }
-    default: throw Error(CPB_ERR_UNSUPPORTED, "pack_stripe method not built on the device (ConcaveTotalChunker: no affine model is strictly concave, see DESIGN.md)");
+    case CPB_PACK_CONCAVE_TOTAL:  // ConcaveTotalChunker.jl:9-24 (concave.cu: the queue routine, one device thread)
+      CPB_REQUIRE(f != nullptr, "pack_stripe: this method needs a cost oracle");
+      solve_concave_chunker(*f, con, h_spl_out, K_out);
+      return;
+    default: throw Error(CPB_ERR_UNSUPPORTED, "unknown pack_stripe method");
   }
 }
 

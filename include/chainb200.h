@@ -166,6 +166,7 @@ enum {
   CPB_SPLIT_LAZY_BISECT_COST = 3,   /* LazyBisectCostBottleneckSplitter(f, eps)  LazyBisectCostBottleneckSplitter.jl:8-70,140-258,260-388 */
   CPB_SPLIT_EQUI = 5,               /* EquiSplitter()                            EquiPartitioner.jl:3-9 */
   CPB_SPLIT_CONVEX_TOTAL = 8,       /* partition_stripe(A, K, ConvexTotalSplitter(f))  ConvexTotalChunker.jl:26-55 (quadrangle-inequality models) */
+  CPB_SPLIT_CONCAVE_TOTAL = 9,      /* partition_stripe(A, K, ConcaveTotalSplitter(f))  ConcaveTotalChunker.jl:26-55, 143-181 (sequential queue routine, one device thread) */
   /* partition_stripe(A, K, ::AbstractDynamicChunker) DynamicSplitter.jl:52-87,249-314: the same K-part recurrence
      and `<=` tie rule as the splitter form with the part index as the inner loop -> identical split vectors */
   CPB_SPLIT_DYNAMIC_BOTTLENECK_CHUNKER = 10, /* partition_stripe(A, K, DynamicBottleneckChunker(f)) */

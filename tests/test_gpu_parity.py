@@ -443,8 +443,8 @@ def test_pack_infeasible_and_unsupported():
     with pytest.raises(cp.CpbError) as e:
         cp.pack_stripe(A, cp.DynamicTotalChunker(cp.ConstrainedCost(cp.AffineConnectivityModel(0, 0, 0, 1), cp.AffineWorkModel(5, 1, 0), 3)))
     assert e.value.code == -4
-    with pytest.raises(cp.CpbError):
-        cp.pack_stripe(A, cp.ConcaveTotalChunker(cp.AffineWorkModel(1, 1, 1)))
+    with pytest.raises(cp.CpbError):  # ConcaveTotalChunker.jl:9 has no ConstrainedCost method
+        cp.pack_stripe(A, cp.ConcaveTotalChunker(cp.ConstrainedCost(cp.AffineWorkModel(1, 1, 1), cp.VertexCount(), 3)))
 
 
 def test_config4_downscaled(ref):
@@ -541,6 +541,34 @@ def test_constrained_convex_total_splitter(ref, fixtures):
         spec = cp.ConstrainedCost(cp.AffineConnectivityModel(0, 3, 1, 3), cp.AffineWorkModel(0, 1, 1), int(np.ceil((B.n + B.nnz) / K * 1.5)))
         for mk in (cp.ConvexTotalSplitter, cp.DynamicTotalSplitter):
             assert np.array_equal(cp.partition_stripe(B, K, mk(spec)).spl, ref.partition_stripe(B, K, mk(spec)).spl), (K, mk.__name__, "pin-weighted")
+
+
+def test_concave_total_chunker_and_splitter(ref, fixtures):
+    """a23: pack_stripe(A, ConcaveTotalChunker(f)) (ConcaveTotalChunker.jl:9-24), partition_stripe(A, K, ConcaveTotalSplitter(f))
+    (:26-55) and its ConstrainedCost form (:143-181).  The device runs the reference's queue routine (:57-114) step by step, so
+    the split vectors equal the restated algorithm's for ANY model -- concave (work model: modular; tabulated column-block
+    model with a concave beta(w)), or not (connectivity: the result is then whatever the queue leaves, and still identical)."""
+    rng = np.random.default_rng(2300)
+    mats = [sprand(rng, 6, 1, 0.5), sprand(rng, 6, 2, 0.5), sprand(rng, 6, 11, 0.3), sprand(rng, 30, 120, 0.1), fixtures["Pajek/GD99_c"], synth.laplacian5(12),
+            cp.SparseMatrixCSC(5, 4, [1, 1, 1, 1, 1], np.zeros(0, dtype=np.int64))]
+    concave_tab = cp.ColumnBlockComponentCostModel(int, 7, lambda w: int(20 * np.sqrt(w)))  # concave beta_col(w)
+    models = [cp.AffineWorkModel(3, 1, 2), cp.AffineWorkModel(0, 0, 0), cp.AffineWorkModel(0.5, 0.25, 1.5), cp.AffineConnectivityModel(0, 10, 1, 100),
+              cp.AffineConnectivityModel(0.5, 0.25, 1.5, 3.0), concave_tab]
+    for A in mats:
+        for f in models:
+            g, r = cp.pack_stripe(A, cp.ConcaveTotalChunker(f)), ref.pack_stripe(A, cp.ConcaveTotalChunker(f))
+            assert g.K == r.K and np.array_equal(g.spl, r.spl), (A.n, f, g.spl, r.spl)
+            for K in (1, 2, 3, 5, 16):
+                mtd = cp.ConcaveTotalSplitter(f)
+                g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                assert np.array_equal(g.spl, r.spl), (A.n, f, K, g.spl, r.spl)
+        for f in models[:5]:
+            for w, w_max in [(cp.VertexCount(), 3), (cp.AffineWorkModel(0, 1, 0), 8), (cp.AffineWorkModel(1, 2, 0), 9), (cp.AffineWorkModel(0, 1, 1), 12),
+                             (cp.AffineWorkModel(5, 1, 0), 3)]:
+                for K in (1, 2, 4, 9):
+                    mtd = cp.ConcaveTotalSplitter(cp.ConstrainedCost(f, w, w_max))
+                    g, r = cp.partition_stripe(A, K, mtd), ref.partition_stripe(A, K, mtd)
+                    assert np.array_equal(g.spl, r.spl), (A.n, f, w_max, K, g.spl, r.spl)
 
 
 def test_dynamic_chunker_kform(ref, fixtures):
