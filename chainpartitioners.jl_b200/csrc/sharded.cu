@@ -21,6 +21,7 @@
 #include <vector>
 #include "engine.cuh"
 #include "primitives.cuh"
+#include "onesweep.cuh"
 
 namespace cpb {
 
@@ -186,9 +187,29 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 void fill_chunk_cols_public(LinkStream& ls);  // links.cu
 
+// run heads of the packed (row << 32 | local position) pairs: as k_shard_heads
+__global__ void k_shard_heads_pairs(const u64* __restrict__ sorted, size_t cnt, const u32* __restrict__ carry, u32* __restrict__ prev_blk,
+                                    u32* __restrict__ first_count) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 firsts = 0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < cnt; p += stride) {
+    const u64 cur = sorted[p];
+    const u32 r = (u32)(cur >> 32);
+    if (p == 0 || (u32)(sorted[p - 1] >> 32) != r) {
+      const u32 c = carry ? carry[r] : 0u;
+      if (c) prev_blk[(u32)cur] = c;
+      firsts += c == 0u;
+    }
+  }
+  firsts = __reduce_add_sync(0xffffffffu, firsts);
+  if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
+}
+
 // one block's share of the construction: sort, in-block links, last positions
 struct BlockWork {
   DBuf<u32> k0, v0, k1, v1, last_local;
+  DBuf<u64> pa, pb;      // one-sweep form: packed pairs
+  u64* sorted = nullptr;  // (row << 32 | local position), sorted
   u32 *sk = nullptr, *sq = nullptr;
   size_t cntL = 0;
 };
@@ -198,16 +219,25 @@ static void block_local_links(const u32* row_blk, size_t cntL, u32 q_lo, size_t 
   w.last_local.alloc(std::max<size_t>(m, 1));
   CPB_CUDA(cudaMemsetAsync(w.last_local.get(), 0, std::max<size_t>(m, 1) * sizeof(u32), ctx().stream));
   if (!cntL) return;
+  const char* wmin_env = std::getenv("CPB_WINDOWED_SCATTER_MIN");
+  const size_t wmin = wmin_env ? (size_t)std::atoll(wmin_env) : ((size_t)1 << 25);
+  u32* const prev_blk = prev_full + q_lo;
+  const char* os_env = std::getenv("CPB_ONESWEEP");
+  if (onesweep_supported(cntL) && !(os_env && os_env[0] == '0')) {
+    // one-sweep radix passes on packed pairs (onesweep.cu): in-block links (run heads: 0 for now) and last positions
+    w.pa.alloc(cntL);
+    w.pb.alloc(cntL);
+    w.sorted = onesweep_links(row_blk, cntL, bits_for(m ? m - 1 : 0), nullptr, /*as_pos=*/true, q_lo, prev_blk, nullptr, w.last_local.get(), wmin, w.pa.get(),
+                              w.pb.get());
+    return;
+  }
   w.k0.alloc(cntL); w.v0.alloc(cntL); w.k1.alloc(cntL); w.v1.alloc(cntL);
   const int which = radix_sort_pairs_iota(row_blk, w.k0.get(), w.v0.get(), w.k1.get(), w.v1.get(), cntL, bits_for(m ? m - 1 : 0));
   w.sk = which ? w.k1.get() : w.k0.get();
   w.sq = which ? w.v1.get() : w.v0.get();
   u32* const other_k = which ? w.k0.get() : w.k1.get();
   u32* const other_v = which ? w.v0.get() : w.v1.get();
-  u32* const prev_blk = prev_full + q_lo;
   CPB_LAUNCH(k_shard_link_values, grid_for(cntL), 256, 0, w.sk, w.sq, cntL, q_lo, other_k, w.last_local.get());
-  const char* wmin_env = std::getenv("CPB_WINDOWED_SCATTER_MIN");
-  const size_t wmin = wmin_env ? (size_t)std::atoll(wmin_env) : ((size_t)1 << 25);
   if (wmin > 0 && cntL >= wmin) {
     // the block's links no longer fit L2: group the (position, link) pairs by windows of the link array first (see links.cu)
     DBuf<u32> pk2(cntL);
@@ -219,7 +249,9 @@ static void block_local_links(const u32* row_blk, size_t cntL, u32 q_lo, size_t 
   }
 }
 static void block_heads(const BlockWork& w, const u32* carry_in, u32 q_lo, u32* prev_full, u32* first_count) {
-  if (w.cntL) CPB_LAUNCH(k_shard_heads, grid_for(w.cntL), 256, 0, w.sk, w.sq, w.cntL, carry_in, prev_full + q_lo, first_count);
+  if (!w.cntL) return;
+  if (w.sorted) CPB_LAUNCH(k_shard_heads_pairs, grid_for(w.cntL), 256, 0, w.sorted, w.cntL, carry_in, prev_full + q_lo, first_count);
+  else CPB_LAUNCH(k_shard_heads, grid_for(w.cntL), 256, 0, w.sk, w.sq, w.cntL, carry_in, prev_full + q_lo, first_count);
 }
 
 static std::unique_ptr<LinkStream> new_link_stream(const Matrix& A, size_t min_entries) {
