@@ -1700,14 +1700,15 @@ struct UbWork {
   unsigned slices = 1;
   int steps = 0;
 };
-static void launch_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps, double* d_out, UbWork& w) {
+static void launch_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps, int nodes, double* d_out, UbWork& w) {
   ProfScope pk("probe_plan_bound");
   w.spl.alloc(K + 1);
   w.cnt.alloc(K);
   CPB_LAUNCH(k_ub_splits, (unsigned)((K + 1 + 255) / 256), 256, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get());
   w.slices = (unsigned)std::min<i64>(64, std::max<i64>(1, ((i64)ctx().sm_count * 8 + K - 1) / K));
   CPB_LAUNCH(k_ub_count, dim3(w.slices, (unsigned)K, 1), 256, 0, ds, w.spl.get(), w.cnt.get(), (const int*)nullptr);
-  w.steps = (K <= UB_KMAX && f.A->n >= 4 * K) ? env_int("CPB_UB_REFINE", 3) : 0;
+  // (a round of 60 or more thresholds -- four ranks or more -- covers a loose bound as well as one of 15 covers a tight one)
+  w.steps = (K <= UB_KMAX && f.A->n >= 4 * K && nodes < 60) ? env_int("CPB_UB_REFINE", 3) : 0;
   if (w.steps <= 0) {
     CPB_LAUNCH(k_ub_max, 1, 256, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get(), d_out);
     return;
@@ -1767,7 +1768,7 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     double h_ub[2] = {0, 1};
     for (int attempt = 0; attempt < 2; ++attempt) {
       stream_view(f, run->ds);
-      if (want_ub) launch_upper_bound(f, run->ds, K, eps, ub_out.get(), ubw);
+      if (want_ub) launch_upper_bound(f, run->ds, K, eps, nodes, ub_out.get(), ubw);
       u32 info[2] = {0, 0}, n_over = 0;
       CPB_CUDA(cudaMemcpyAsync(info, f.ls->first_count.get(), sizeof(info), cudaMemcpyDeviceToHost, ctx().stream));
       if (dia) CPB_CUDA(cudaMemcpyAsync(&n_over, f.overpos.get() + A.n, sizeof(u32), cudaMemcpyDeviceToHost, ctx().stream));
