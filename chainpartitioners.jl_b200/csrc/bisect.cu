@@ -412,9 +412,11 @@ static constexpr int SP_THREADS = 1024;
 #ifndef CPB_SP_VEC
 #define CPB_SP_VEC 8
 #endif
-static constexpr int SP_VEC = CPB_SP_VEC;               // 128-bit loads per thread per super-step
-static constexpr int SP_CE = SP_THREADS * SP_VEC * 4;  // 32768 elements per CTA per super-step
-static constexpr int SP_GROUPS = SP_VEC * 32;          // 128-element groups per CTA (one warp-wide uint4 load each)
+static constexpr int SP_VEC = CPB_SP_VEC;               // 128-bit loads per thread per register tile
+static constexpr int SP_SUB = 2;                       // register tiles per super-step at most
+static constexpr int SP_NVMAX = SP_VEC * SP_SUB;       // 128-bit loads per thread per super-step at most
+static constexpr int SP_CE = SP_THREADS * SP_VEC * 4;  // 32768 elements per CTA per register tile
+static constexpr int SP_GROUPS = SP_NVMAX * 32;        // 128-element groups per CTA (one warp-wide uint4 load each) at most
 
 // `prev < j` count among the first x elements of this CTA's slice, from the per-group masks
 __device__ __forceinline__ u32 stream_prefix(const u32* s_mask, const u32* s_cum, u32 x) {
@@ -634,49 +636,61 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       //      reductions.  (Round 1 formed the masks with 4 ballots per group: 1024 VOTEs per CTA and super-step on the SM's one
       //      address-divergence unit -- ~3 cycles each, measured with scratch/ubench -- were what bounded this phase.) ----
       u32 wsum = 0;
-      // all loads of the super-step are issued before the first compare (one exposed memory latency instead of nv)
-      uint4 pv[SP_VEC];
+      // A part longer than one register tile (8 vector loads per thread) takes up to SP_SUB tiles in the same super-step:
+      // the flags live in shared memory, only the loads repeat -- one more load phase instead of a whole second super-step
+      // with its two exchanges (parts of 262 k - 524 k elements: config 5, a quarter of config 3's parts).
+      unsigned char* const s_nib = reinterpret_cast<unsigned char*>(s_mask);
+      u32 pk[SP_SUB * 2];  // flag counts of the warp's groups, one byte per group (<= 128 each)
 #pragma unroll
-      for (int v = 0; v < SP_VEC; ++v) {
-        pv[v] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // (beyond the end: never counted)
-        if (v < (int)nv) {
-          const u32 idx = e_c + (warp * nv + v) * 128 + lane * 4;
-          if ((u64)idx + 4 <= Ne) {
-            pv[v] = __ldg(reinterpret_cast<const uint4*>(s.prev + idx));
-          } else {
-            if (idx < Ne) pv[v].x = __ldg(s.prev + idx);
-            if (idx + 1 < Ne) pv[v].y = __ldg(s.prev + idx + 1);
-            if (idx + 2 < Ne) pv[v].z = __ldg(s.prev + idx + 2);
+      for (int i = 0; i < SP_SUB * 2; ++i) pk[i] = 0;
+#pragma unroll
+      for (int sub = 0; sub < SP_SUB; ++sub) {
+        if ((u32)sub * SP_VEC >= nv) break;
+        // all loads of the tile are issued before the first compare (one exposed memory latency instead of nv)
+        uint4 pv[SP_VEC];
+#pragma unroll
+        for (int v = 0; v < SP_VEC; ++v) {
+          pv[v] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // (beyond the end: never counted)
+          if ((u32)(sub * SP_VEC + v) < nv) {
+            const u32 idx = e_c + (warp * nv + sub * SP_VEC + v) * 128 + lane * 4;
+            if ((u64)idx + 4 <= Ne) {
+              pv[v] = __ldg(reinterpret_cast<const uint4*>(s.prev + idx));
+            } else {
+              if (idx < Ne) pv[v].x = __ldg(s.prev + idx);
+              if (idx + 1 < Ne) pv[v].y = __ldg(s.prev + idx + 1);
+              if (idx + 2 < Ne) pv[v].z = __ldg(s.prev + idx + 2);
+            }
           }
         }
-      }
-      unsigned char* const s_nib = reinterpret_cast<unsigned char*>(s_mask);
-      u32 pkA = 0, pkB = 0;  // flag counts of the warp's groups, one byte per group (<= 128 each)
 #pragma unroll
-      for (int v = 0; v < SP_VEC; ++v) {
-        if (v >= (int)nv) break;
-        const u32 g = warp * nv + v;
-        const u32 gbase = e_c + g * 128;  // first element of the group (warp-uniform)
-        u32 nib;
-        if (gbase >= e0) {
-          nib = (u32)(pv[v].x <= e0) | ((u32)(pv[v].y <= e0) << 1) | ((u32)(pv[v].z <= e0) << 2) | ((u32)(pv[v].w <= e0) << 3);
-        } else {  // the group holding the part's first element: mask what lies in front of it
-          const u32 idx = gbase + lane * 4;
-          nib = (u32)(pv[v].x <= e0 && idx + 0 >= e0) | ((u32)(pv[v].y <= e0 && idx + 1 >= e0) << 1) | ((u32)(pv[v].z <= e0 && idx + 2 >= e0) << 2) |
-                ((u32)(pv[v].w <= e0 && idx + 3 >= e0) << 3);
+        for (int v = 0; v < SP_VEC; ++v) {
+          if ((u32)(sub * SP_VEC + v) >= nv) break;
+          const u32 g = warp * nv + sub * SP_VEC + v;
+          const u32 gbase = e_c + g * 128;  // first element of the group (warp-uniform)
+          u32 nib;
+          if (gbase >= e0) {
+            nib = (u32)(pv[v].x <= e0) | ((u32)(pv[v].y <= e0) << 1) | ((u32)(pv[v].z <= e0) << 2) | ((u32)(pv[v].w <= e0) << 3);
+          } else {  // the group holding the part's first element: mask what lies in front of it
+            const u32 idx = gbase + lane * 4;
+            nib = (u32)(pv[v].x <= e0 && idx + 0 >= e0) | ((u32)(pv[v].y <= e0 && idx + 1 >= e0) << 1) | ((u32)(pv[v].z <= e0 && idx + 2 >= e0) << 2) |
+                  ((u32)(pv[v].w <= e0 && idx + 3 >= e0) << 3);
+          }
+          s_nib[g * 32 + lane] = (unsigned char)nib;
+          pk[(sub * SP_VEC + v) >> 2] += (u32)__popc(nib) << (8 * (v & 3));
         }
-        s_nib[g * 32 + lane] = (unsigned char)nib;
-        const u32 pc = (u32)__popc(nib);
-        if (v < 4) pkA += pc << (8 * v); else pkB += pc << (8 * (v - 4));
       }
       {
-        const u32 A = __reduce_add_sync(0xffffffffu, pkA);
-        const u32 B = (nv > 4) ? __reduce_add_sync(0xffffffffu, pkB) : 0u;
         // lane v: flags in the warp's groups before group v (prefix inside the warp's run; the warp's base is added after the barrier)
-        const u32 mA = lane >= 4 ? 0xffffffffu : ((1u << (8 * lane)) - 1u);
-        const u32 mB = lane <= 4 ? 0u : (lane >= 8 ? 0xffffffffu : ((1u << (8 * (lane - 4))) - 1u));
-        if (lane < (int)nv) s_cum[warp * nv + lane] = __dp4a(A & mA, 0x01010101u, __dp4a(B & mB, 0x01010101u, 0u));
-        wsum = __dp4a(A, 0x01010101u, __dp4a(B, 0x01010101u, 0u));
+        u32 pre = 0;
+#pragma unroll
+        for (int i = 0; i < SP_SUB * 2; ++i) {
+          if ((u32)(4 * i) >= nv) break;
+          const u32 R = __reduce_add_sync(0xffffffffu, pk[i]);
+          const u32 m = lane >= 4 * (i + 1) ? 0xffffffffu : (lane <= 4 * i ? 0u : ((1u << (8 * (lane - 4 * i))) - 1u));
+          pre = __dp4a(R & m, 0x01010101u, pre);
+          wsum = __dp4a(R, 0x01010101u, wsum);
+        }
+        if (lane < (int)nv) s_cum[warp * nv + lane] = pre;
       }
       if (lane == 0) s_wtot[warp] = wsum;
       PT(0);
@@ -849,14 +863,14 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       if ((u64)e_tile + TE >= Ne) break;       // streamed to the end: jlast == n + 1
       grun += tile_tot;
       e_tile += TE;
-      nv = SP_VEC;                             // the part is longer than estimated: full-size tiles from here on
+      nv = SP_NVMAX;                           // the part is longer than estimated: full-size tiles from here on
       missed = true;
     }
     {  // size the next part's first tile from this part (+1/8 slack); a miss (second super-step needed) resets
        // the estimate to the full tile, from where it shrinks by one vector load per part at most
       const u32 elems = pcur - e0;
       const u32 want = (elems + (elems >> 3) + 3u) / ((u32)SP_THREADS * 4u * BS_CLUSTER) + 1u;
-      nv_est = missed ? (u32)SP_VEC : max(min(max(want, 2u), (u32)SP_VEC), nv_est > 2u ? nv_est - 1u : 2u);
+      nv_est = missed ? (u32)SP_NVMAX : max(min(max(want, 2u), (u32)SP_NVMAX), nv_est > 2u ? nv_est - 1u : 2u);
       nv = nv_est;
     }
     PT(8);
