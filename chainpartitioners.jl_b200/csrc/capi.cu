@@ -449,9 +449,12 @@ int cpb_oracle_create(cpb_matrix* A, const cpb_model* mdl, const int64_t* pi_spl
   CPB_API_BEGIN
   ensure_context();
   CPB_REQUIRE(A && mdl && out, "NULL argument");
+  trace_mark("enter");
   auto h = std::make_unique<cpb_oracle>();
   h->O = oracle_create(A->M, mdl, pi_spl, pi_K);
   *out = h.release();
+  trace_mark("exit");
+  trace_flush("oracle_create");
   CPB_API_END
 }
 
@@ -755,6 +758,8 @@ int cpb_pack_stripe(cpb_matrix* A, cpb_oracle* f, int method, const cpb_constrai
   CPB_API_BEGIN
   ensure_context();
   CPB_REQUIRE(A && spl_out && K_out, "NULL argument");
+  trace_mark("enter");
+  struct TraceEnd { ~TraceEnd() { trace_mark("exit"); trace_flush("pack_stripe"); } } trace_end;
   solve_pack(A->M, f ? f->O.get() : nullptr, method, con, rho, w_max, spl_out, K_out, n_nets_out);
   CPB_API_END
 }

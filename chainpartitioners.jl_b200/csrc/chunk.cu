@@ -623,6 +623,7 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
   }
 
   // ---- window_cost_table ----
+  trace_mark("checks");
   TableModel tm{};
   tm.kind = mdl.kind; tm.W = W; tm.R = 1;
   tm.fa = mdl.coef[0]; tm.fbv = mdl.coef[1]; tm.fbp = mdl.coef[2]; tm.fbn = mdl.coef[3];
@@ -650,7 +651,9 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
       DBuf<u32> ids(N2), pos2((size_t)n + 1), prev(N2), colidx2(N2);
       if (N) CPB_LAUNCH(k_collapse_emit, grid_for(N), 256, 0, A.row.get(), f.pi_asg.get(), keep.get(), scan.get(), N, ids.get());
       CPB_LAUNCH(k_collapse_pos, grid_for((size_t)n + 1), 256, 0, A.pos.get(), scan.get(), n, pos2.get());
+      trace_mark("collapse");
       compute_prev_links(pos2.get(), ids.get(), Kp, n, N2, prev.get(), colidx2.get());
+      trace_mark("links");
       // per-part weights beta_row[r](u_k)
       const int U = mdl.u_tab + 1;
       std::vector<i64> hbr((size_t)R * U);
@@ -679,6 +682,7 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
       tm.beta_col = tabs.get() + (W + 1);
     }
   }
+  trace_mark("window_hist");
   const size_t cells = ((size_t)n + 1) * W;
   DBuf<u32> ptr((size_t)n + 3);
   if (!is_f) {
@@ -687,6 +691,7 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
       ProfScope prof("window_cost_table");
       CPB_LAUNCH(k_cost_table<i64>, grid_for(cells), 256, 0, A.pos.get(), n, tm, G.get(), C.get(), (i64)CH_INF);
     }
+    trace_mark("cost_table");
     {
       ProfScope prof("chunk_dp_window", (double)cells * 8.0 + (double)(n + 1) * 12.0);
       if (W <= 8) run_dp_blocks<8>(C.get(), n, W, cst.get(), ptr.get());
@@ -713,8 +718,10 @@ static void pack_dynamic(Matrix& A, Oracle& f, int method, const cpb_constraint*
     if (!(last < INFINITY)) throw Error(CPB_ERR_INFEASIBLE, "width constraint cannot be met (reference: @assert j0 < j')");
     if (method == CPB_PACK_CONVEX_TOTAL) CPB_LAUNCH(k_convex_ptr<double>, grid_for(n), 256, 0, C.get(), cst.get(), n, W, ptr.get());
   }
+  trace_mark("chunk_dp");
   ProfScope prof("unravel_chunks");
   *K_out = unravel_chain<-1>(ptr.get(), n, W, h_spl_out);
+  trace_mark("unravel");
 }
 
 void solve_pack(Matrix& A, Oracle* f, int method, const cpb_constraint* con, double rho, i64 w_max, int64_t* h_spl_out,

@@ -507,11 +507,38 @@ __global__ void k_gather_cols(const u32* __restrict__ sq, const u32* __restrict_
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) out[p] = colidx[sq[p]];
 }
 
+// the same from packed (row << 32 | position) pairs (one-sweep sort)
+__global__ void k_gather_cols_pairs(const u64* __restrict__ sorted, const u32* __restrict__ colidx, size_t N, u32* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += stride) out[p] = colidx[(u32)sorted[p]];
+}
+__global__ void k_segment_starts_pairs(const u64* __restrict__ sorted, size_t n, u32* __restrict__ P, u32 domain) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += stride) {
+    const i64 lo = (p == 0) ? 0 : (i64)(u32)(sorted[p - 1] >> 32) + 1;
+    const i64 hi = (p == n) ? (i64)domain : (i64)(u32)(sorted[p] >> 32);
+    for (i64 x = lo; x <= hi; ++x) P[x] = (u32)p;
+  }
+}
+
 std::unique_ptr<Matrix> adjoint_pattern(const Matrix& A) {
   auto B = std::make_unique<Matrix>();
   B->m = A.n; B->n = A.m; B->N = A.N;
   const size_t N = (size_t)A.N;
   ProfScope prof("adjointpattern", (double)(2 * N + A.n + A.m + 2) * 4.0);
+  const char* os_env = std::getenv("CPB_ONESWEEP");
+  if (onesweep_supported(N) && !(os_env && os_env[0] == '0')) {
+    DBuf<u64> a(N), b(N);
+    const u64* sorted = onesweep_sort_iota(A.row.get(), N, bits_for(A.m ? A.m - 1 : 0), a.get(), b.get());
+    DBuf<u32> colidx(N);
+    expand_columns(A.pos.get(), (u32)A.n, colidx.get(), N);
+    B->row.alloc(N);
+    CPB_LAUNCH(k_gather_cols_pairs, grid_for(N), 256, 0, sorted, colidx.get(), N, B->row.get());
+    B->pos.alloc((size_t)A.m + 1);
+    const unsigned grid = (unsigned)std::min<size_t>((N + 1 + 255) / 256, (size_t)ctx().sm_count * 16);
+    CPB_LAUNCH(k_segment_starts_pairs, grid, 256, 0, sorted, N, B->pos.get(), (u32)A.m);
+    return B;
+  }
   TransposeOrder t;
   transpose_order(A.row.get(), N, A.m ? A.m - 1 : 0, t);
   DBuf<u32> colidx(N);
