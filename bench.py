@@ -50,7 +50,9 @@ NOTES = {
     "k_lt_link": "build_links: every slot scans its row segment for the largest position below its own and writes the link",
     "k_lt_count": "build_links: row histogram (one atomic per nonzero)",
     "k_rs_scatter": "stable radix scatter of (row, position) pairs inside build_links (rows heavier than 128 nonzeros)",
-    "k_os_scatter": "one-sweep stable radix scatter (decoupled look-back) of (row, position) pairs inside build_links",
+    "k_os_pass": "build_links (rows heavier than 128 nonzeros): one-sweep stable radix pass on packed (row, position) pairs, one read + one write "
+                 "per 8-bit pass, tile prefixes by decoupled look-back (csrc/onesweep.cu)",
+    "k_os_hist": "build_links: digit histograms of all radix passes in one sweep over the rows",
     "k_link_prev": "links from the row-sorted pairs + windowed scatter back into column order",
     "k_wm_level": "one bit level of the wavelet-matrix dominance index",
     "k_expand_columns": "column of every nonzero from the offsets (marks + running maximum per tile)",

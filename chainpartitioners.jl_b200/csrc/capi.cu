@@ -286,9 +286,14 @@ static void upload_index_array(const i64* h_src, size_t n, u32* d_dst, i64 lo, i
     return;
   }
   uint64_t acc = 0;
-  for (size_t off = 0; off < n; off += PACK_CHUNK_ELEMS) {
+  static const size_t chunk_elems = [] {  // (CPB_PACK_CHUNK: elements per staged chunk, for measurements; at most what a staging buffer holds)
+    const char* e = std::getenv("CPB_PACK_CHUNK");
+    const size_t v = e ? (size_t)std::atoll(e) : PACK_CHUNK_ELEMS;
+    return std::min(std::max(v, (size_t)1 << 16), H2D_CHUNK / sizeof(u32));
+  }();
+  for (size_t off = 0; off < n; off += chunk_elems) {
     const int b = stage_acquire();
-    const size_t cnt = std::min(PACK_CHUNK_ELEMS, n - off);
+    const size_t cnt = std::min(chunk_elems, n - off);
     acc |= host_pack((uint32_t*)g_stage[b], reinterpret_cast<const int64_t*>(h_src + off), cnt);
     CPB_CUDA(cudaMemcpyAsync(d_dst + off, g_stage[b], cnt * sizeof(u32), cudaMemcpyHostToDevice, ctx().stream));
     stage_release(b);
