@@ -1752,9 +1752,21 @@ static void refine_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps
   }
 }
 
+// The device's part searches count the feasible samples of an INCREASING predicate.  The reference's windowed binary search
+// (BisectCost...:22-39) is path dependent for a cost that shrinks as the part grows (a work model with a negative beta --
+// bound_stripe accepts it, WorkCosts.jl:37-51), so such models are refused instead of answered differently.
+static void require_monotone_cost(const Oracle& f) {
+  if (f.mdl.kind == CPB_MODEL_COLBLOCK || f.mdl.kind == CPB_MODEL_BLOCK) return;  // (tabulated: checked by the bound)
+  for (int t = 1; t <= 3; ++t)
+    if (f.mdl.coef[t] < 0)
+      throw Error(CPB_ERR_UNSUPPORTED, "bisection on the device needs a cost that grows with the part (beta >= 0); a shrinking cost makes the reference's "
+                                       "windowed search path dependent");
+}
+
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
+  require_monotone_cost(f);
   const Matrix& A = *f.A;
   CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
   auto run = std::make_unique<BisectRun>();
@@ -2065,6 +2077,7 @@ void solve_bisect_index(Oracle& f, i64 K, int64_t* h_spl_out) {
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
   const Matrix& A = *f.A;
   CPB_REQUIRE(A.n + 1 < ((i64)1 << 31) && K + 2 < ((i64)1 << 30), "problem too large for 32-bit split points");
+  require_monotone_cost(f);
   oracle_ensure_ranks(f);
   double bnd[2];
   oracle_bound(f, K, bnd);  // (c_lo, c_hi) ./ 1 -- also checks beta >= 0, which the monotone part searches need

@@ -38,7 +38,16 @@ static void init_context(int device) {
   CPB_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   CPB_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (g_ctx.stream && g_ctx.device != device) { cudaStreamDestroy(g_ctx.stream); g_ctx.stream = nullptr; }
+  if (g_ctx.stream && g_ctx.device != device) {
+    // switching devices: the cached large blocks belong to the old device -- hand them back before anything can reuse them
+    // (handles created on the old device stay valid only on it: chainb200.h, "Lifetimes")
+    cudaSetDevice(g_ctx.device);
+    cudaStreamSynchronize(g_ctx.stream);
+    big_trim();
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr;
+    CPB_CUDA(cudaSetDevice(device));
+  }
   g_ctx.device = device;
   g_ctx.sm_count = prop.multiProcessorCount;
   if (!g_ctx.stream) CPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
@@ -473,6 +482,9 @@ int cpb_oracle_query_device(cpb_oracle* f, int64_t Q, const int64_t* d_j, const 
   CPB_API_BEGIN
   ensure_context();
   CPB_REQUIRE(f && (Q == 0 || (d_j && d_jp && d_cost_out)), "NULL argument");
+  if (f->O->mdl.kind >= CPB_MODEL_PRIMCONN && f->O->mdl.kind <= CPB_MODEL_SECEDGE)
+    // (this entry point carries no part index: the row-partition-aware oracles would silently answer for part 1 -- ADVICE r1)
+    throw Error(CPB_ERR_UNSUPPORTED, "cpb_oracle_query_device has no part index: use cpb_oracle_query for the row-partition-aware models");
   oracle_query(*f->O, Q, (const i64*)d_j, (const i64*)d_jp, d_cost_out);
   CPB_API_END
 }

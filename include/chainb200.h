@@ -18,6 +18,21 @@
  *   - handles own device memory only; host arrays are never retained after a call returns;
  *   - one CUDA stream per library instance; calls are serialised; there is NO CPU fallback: every
  *     compute entry point fails with CPB_ERR_CUDA when no device is usable.
+ *
+ * Lifetimes
+ *   - a cpb_matrix must outlive every cpb_oracle / cpb_prefix created from it (the oracle reads the
+ *     matrix's device arrays; destroy oracles first).  Handles belong to the device that was current
+ *     when they were created: cpb_init(other_device) releases the library's cached blocks and
+ *     recreates the stream, and handles of the old device must not be used (or destroyed) after it.
+ *
+ * Streams
+ *   - entry points that take HOST arrays return when their results are in those arrays.
+ *   - entry points that take or fill DEVICE arrays (cpb_matrix_create_device,
+ *     cpb_oracle_query_device, cpb_links_partial, cpb_oracle_set_links, cpb_bisect_probe and the
+ *     other stepwise bisection calls) ENQUEUE work on the library's own non-blocking stream and may
+ *     return before it has run: arrays produced on another stream (torch's, the caller's) must be
+ *     complete before the call, and cpb_synchronize() must return before another stream reads
+ *     what the call wrote.
  */
 #ifndef CHAINB200_H
 #define CHAINB200_H

@@ -172,6 +172,31 @@ def test_envelope_bound_is_the_oracle_form(ref, fixtures):
                 assert np.array_equal(cp.partition_stripe(A, 5, mtd).spl, ref.partition_stripe(A, 5, mtd).spl)
 
 
+def test_refusals_named_by_the_round1_review(fixtures):
+    """(1) a work model with a negative beta shrinks as the part grows -- the reference's windowed search is path
+    dependent there, the device refuses instead of answering differently; (2) the device-array query entry point has no part
+    index and must not answer for part 1 on the row-partition-aware models."""
+    import torch
+
+    A = fixtures["LPnetlib/lp_blend"]
+    for mtd in (cp.BisectCostBottleneckSplitter(cp.AffineWorkModel(100, -1, 0), 0.01), cp.LazyBisectCostBottleneckSplitter(cp.AffineWorkModel(100, 0, -1), 0.01),
+                cp.BisectIndexBottleneckSplitter(cp.AffineWorkModel(100, -1, 0))):
+        with pytest.raises(cp.CpbError) as e:
+            cp.partition_stripe(A, 4, mtd)
+        assert e.value.code == -2
+    B = fixtures["Pajek/GD99_c"]
+    m = B.m
+    Pi = cp.SplitPartition(3, np.array([1, 1 + m // 3, 1 + 2 * m // 3, m + 1], dtype=np.int64))  # a row partition
+    ocl = cp.oracle_stripe(cp.AffinePrimaryConnectivityModel(0, 1, 1, 1, 3), B, Pi)
+    d = torch.ones(4, dtype=torch.int64, device="cuda")
+    out = torch.zeros(4, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    with pytest.raises(cp.CpbError) as e:
+        ocl.query_device(d.data_ptr(), d.data_ptr(), out.data_ptr(), 4)
+    assert e.value.code == -2
+    ocl.close()
+
+
 def test_bound_and_objective(ref, fixtures):
     rng = np.random.default_rng(104)
     for A in small_matrices(fixtures):
