@@ -1428,7 +1428,7 @@ __global__ void k_ub_max(const __grid_constant__ DevStream s, int is_float, int 
 static constexpr int UB_G = 32768;      // grid points of the rescaled weight (uniform in weight)
 static constexpr int UB_T = 1024;       // candidate thresholds of the parametric search, one per thread
 static constexpr int UB_KMAX = 4096;    // parts (the candidates' cut lists live in a [UB_T][K + 1] scratch array)
-struct UbCtl { double best; double total; double tlo; int stop; int pad; };
+struct UbCtl { double best; double total; double tlo; double tstar; int stop; int pad; };
 
 // exact part costs -> ctl.best = min(ctl.best, bottleneck); prefix S[k] of (cost - alpha), per-part scale of U
 __global__ void __launch_bounds__(1024) k_ub_prepare(const __grid_constant__ DevStream s, int is_float, int K, const int* __restrict__ spl,
@@ -1443,6 +1443,7 @@ __global__ void __launch_bounds__(1024) k_ub_prepare(const __grid_constant__ Dev
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s_carry = 0;
   double best = 0;
+  int single = 0;  // the costliest part seen by this thread is one column wide
   __syncthreads();
   for (int k0 = 0; k0 < K; k0 += 1024) {
     const int k = k0 + tid;
@@ -1450,7 +1451,7 @@ __global__ void __launch_bounds__(1024) k_ub_prepare(const __grid_constant__ Dev
     if (k < K) {
       const u32 a = (u32)spl[k], b = (u32)spl[k + 1];
       const double c = cf[0] + (double)(b - a) * cf[1] + ((double)__ldg(s.Wt + b) - (double)__ldg(s.Wt + a)) * cf[2] + (double)cnt[k] * cf[3];
-      best = fmax(best, c);
+      if (c > best || (c == best && b - a == 1)) { single = (b - a == 1) ? 1 : 0; best = c; }
       wk = fmax(c - cf[0], 0.0);
       const double du = ub_weight(s, ucf, b) - ub_weight(s, ucf, a);
       scale[k] = du > 0 ? wk / du : 0.0;
@@ -1469,11 +1470,17 @@ __global__ void __launch_bounds__(1024) k_ub_prepare(const __grid_constant__ Dev
     if (tid == 1023) s_carry = wb + inc;
     __syncthreads();
   }
-  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if (lane == 0) sm[w] = best;
+  __shared__ int sm_single[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int os = __shfl_xor_sync(0xffffffffu, single, o);
+    if (ob > best || (ob == best && os)) { best = ob; single = os; }
+  }
+  if (lane == 0) { sm[w] = best; sm_single[w] = single; }
   __syncthreads();
   if (tid == 0) {
-    for (int q = 1; q < 32; ++q) best = fmax(best, sm[q]);
+    for (int q = 1; q < 32; ++q)
+      if (sm[q] > best || (sm[q] == best && sm_single[q])) { best = sm[q]; single = sm_single[q]; }
     const double total = s_carry;
     S[K] = total;
     const double prev = first ? 0.0 : ctl->best;
@@ -1481,10 +1488,15 @@ __global__ void __launch_bounds__(1024) k_ub_prepare(const __grid_constant__ Dev
     ctl->best = b;
     ctl->total = total;
     ctl->tlo = total / (double)K;
-    if (first) ctl->stop = 0;
+    if (first) { ctl->stop = 0; ctl->tstar = 0; }
     // balanced well inside the bisection's tolerance, or the last step gained less than 0.3 %: nothing left to gain
     if (!(best - cf[0] > (1.0 + fmax(0.004, tol)) * (total / (double)K))) ctl->stop = 1;
     if (!first && !(best < 0.997 * prev)) ctl->stop = 1;
+    // the costliest part is a single column: no partition can do better than that column alone -- the bound is the optimum
+    if (single) ctl->stop = 1;
+    // the step's greedy threshold on the rescaled weight predicted this bottleneck within 1 %: the weight model is consistent
+    // with the exact costs, another step would cut at the same places
+    if (!first && best - cf[0] <= 1.01 * ctl->tstar) ctl->stop = 1;
     out[0] = b;
     out[1] = ctl->stop ? 1.0 : 0.0;
   }
@@ -1529,7 +1541,7 @@ __global__ void __launch_bounds__(256) k_ub_grid(const __grid_constant__ DevStre
 // parametric search: thread t cuts the grid greedily at threshold T_t (geometric ladder from the mean share to eight times
 // the mean share: a column may outweigh the mean share by far); the smallest threshold that places every
 // column in at most K parts gives the new partition
-__global__ void __launch_bounds__(UB_T) k_ub_greedy(int K, const UbCtl* __restrict__ ctl, const u32* __restrict__ gx, const float* __restrict__ gw_g,
+__global__ void __launch_bounds__(UB_T) k_ub_greedy(int K, UbCtl* __restrict__ ctl, const u32* __restrict__ gx, const float* __restrict__ gw_g,
                                                     u32* __restrict__ cuts, int* __restrict__ spl) {
   extern __shared__ float s_gw[];  // UB_G + 1
   __shared__ int s_first;
@@ -1568,6 +1580,7 @@ __global__ void __launch_bounds__(UB_T) k_ub_greedy(int K, const UbCtl* __restri
   __syncthreads();
   const int best = s_first;
   if (best >= UB_T) return;  // no candidate placed every column: keep the partition
+  if (tid == best) ctl->tstar = (double)T;
   const u32* src = cuts + (size_t)best * (K + 1);
   for (int k = tid; k <= K; k += UB_T) spl[k] = (k == 0) ? 1 : (int)gx[src[k]];
 }
@@ -1749,6 +1762,12 @@ static void refine_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps
     CPB_LAUNCH(k_ub_zero, (unsigned)((K + 255) / 256), 256, 0, w.cnt.get(), (int)K, stop);
     CPB_LAUNCH(k_ub_count, dim3(w.slices, (unsigned)K, 1), 256, 0, ds, w.spl.get(), w.cnt.get(), stop);
     CPB_LAUNCH(k_ub_prepare, 1, 1024, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get(), w.S.get(), w.scale.get(), w.ctl.get(), d_out, 0, eps / 4);
+    if (env_int("CPB_UB_DEBUG", 0)) {  // (measurements: the state after every step)
+      UbCtl h{};
+      CPB_CUDA(cudaMemcpyAsync(&h, w.ctl.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
+      CPB_CUDA(cudaStreamSynchronize(ctx().stream));
+      std::fprintf(stderr, "[cpb ub] step %d: best %.0f, greedy threshold %.0f, mean share %.0f, stop %d\n", it + 1, h.best, h.tstar, h.tlo, h.stop);
+    }
   }
 }
 
