@@ -549,8 +549,9 @@ __device__ unsigned long long g_probe_node[16][4];  // per slot: cycles of its c
 
 // AX: the two exchanges of a super-step as remote st.async stores that complete a transaction count on every peer's
 // mbarrier (no barrier.cluster, no fence in front of it, no L1 invalidation); !AX: DSMEM stores + cluster barriers.
-template <class T, bool AX>
-__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS, 1)
+// CL: CTAs per cluster (8, or 16 = the non-portable size; set by the launch attribute)
+template <class T, bool AX, int CL>
+__global__ void __launch_bounds__(SP_THREADS, 1)
     k_probe_stream(const __grid_constant__ DevStream s, int K, double eps1, const BisectState* __restrict__ st,
                    int* __restrict__ node_spl, int* __restrict__ node_res, double* __restrict__ node_c,
                    const int* __restrict__ node_ids, int node_base) {
@@ -558,9 +559,9 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   __shared__ u32 s_cum[SP_GROUPS + 1];
   __shared__ double s_c;
   __shared__ int s_valid;
-  __shared__ u32 s_xa[2][BS_CLUSTER];     // per-CTA `prev < j` totals of the tile
-  __shared__ u32 s_xb[2][4][BS_CLUSTER];  // per-CTA (feasible boundaries, boundaries, P and Wt at the last feasible one)
-  __shared__ __align__(16) u32 s_xv[2][BS_CLUSTER][4];  // the same, one 16-byte record per CTA (AX)
+  __shared__ u32 s_xa[2][CL];     // per-CTA `prev < j` totals of the tile
+  __shared__ u32 s_xb[2][4][CL];  // per-CTA (feasible boundaries, boundaries, P and Wt at the last feasible one)
+  __shared__ __align__(16) u32 s_xv[2][CL][4];  // the same, one 16-byte record per CTA (AX)
   __shared__ __align__(8) unsigned long long s_mb[2][2];  // [exchange][super-step parity] (AX)
   __shared__ u32 s_pj[2 * SP_THREADS];    // (P, Wt) of every thread's boundary candidate, pass 1 | pass 2
   __shared__ u32 s_w[2 * SP_THREADS];
@@ -569,7 +570,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int node = node_base + blockIdx.x / BS_CLUSTER;
+  const int node = node_base + blockIdx.x / CL;
   const bool writer = crank == 0 && tid == 0;
   if (tid == 0) {
     s_valid = node_threshold(st, eps1, node_ids[node], &s_c);
@@ -619,7 +620,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     PT(10);
     for (u32 e_tile = e0 & ~3u;;) {  // 16-byte aligned tiles; elements left of e0 are masked out
       const u32 CE = (u32)SP_THREADS * 4u * nv;  // elements of this CTA in this super-step
-      const u32 TE = CE * BS_CLUSTER;
+      const u32 TE = CE * CL;
       const u32 ngroups = nv * 32u;
 #ifdef CPB_PROBE_TIMING
       PT(6);  // between the super-steps (part bookkeeping)
@@ -716,10 +717,10 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       PT(2);
       const u32 xpar = (sstep >> 1) & 1u;
       if (AX) {
-        if (tid == 0) { mbar_expect_tx(smem_addr(&s_mb[0][ph]), 4u * BS_CLUSTER); mbar_expect_tx(smem_addr(&s_mb[1][ph]), 16u * BS_CLUSTER); }
-        if (tid < BS_CLUSTER) st_async_u32(map_peer(smem_addr(&s_xa[ph][crank]), tid), tot_c, map_peer(smem_addr(&s_mb[0][ph]), tid));
+        if (tid == 0) { mbar_expect_tx(smem_addr(&s_mb[0][ph]), 4u * CL); mbar_expect_tx(smem_addr(&s_mb[1][ph]), 16u * CL); }
+        if (tid < CL) st_async_u32(map_peer(smem_addr(&s_xa[ph][crank]), tid), tot_c, map_peer(smem_addr(&s_mb[0][ph]), tid));
       } else {
-        if (tid < BS_CLUSTER) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
+        if (tid < CL) *cluster.map_shared_rank(&s_xa[ph][crank], tid) = tot_c;
         cluster.barrier_arrive();  // split barrier: the boundary offsets below are fetched while the totals travel
       }
       const u32 nb = (jb >= ja) ? jb - ja + 1 : 0;
@@ -745,7 +746,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       PT(3);
       u32 base_c = 0, tile_tot = 0;
 #pragma unroll
-      for (int p = 0; p < BS_CLUSTER; ++p) {
+      for (int p = 0; p < CL; ++p) {
         const u32 v = s_xa[ph][p];
         if (p < (int)crank) base_c += v;
         tile_tot += v;
@@ -827,11 +828,11 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
       PT(4);
       u32 feas = 0, nbs = 0;
       if (AX) {
-        if (tid < BS_CLUSTER) st_async_v4(map_peer(smem_addr(&s_xv[ph][crank][0]), tid), cnt, nb, lastp, lastw, map_peer(smem_addr(&s_mb[1][ph]), tid));
+        if (tid < CL) st_async_v4(map_peer(smem_addr(&s_xv[ph][crank][0]), tid), cnt, nb, lastp, lastw, map_peer(smem_addr(&s_mb[1][ph]), tid));
         mbar_wait_cluster(smem_addr(&s_mb[1][ph]), xpar, 6u, sstep, nv, e0, e_tile);
         PT(5);
 #pragma unroll
-        for (int p = 0; p < BS_CLUSTER; ++p) {
+        for (int p = 0; p < CL; ++p) {
           const uint4 q = *reinterpret_cast<const uint4*>(&s_xv[ph][p][0]);
           feas += q.x;
           nbs += q.y;
@@ -839,7 +840,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         }
         PT(7);
       } else {
-        if (tid < BS_CLUSTER) {
+        if (tid < CL) {
           *cluster.map_shared_rank(&s_xb[ph][0][crank], tid) = cnt;
           *cluster.map_shared_rank(&s_xb[ph][1][crank], tid) = nb;
           *cluster.map_shared_rank(&s_xb[ph][2][crank], tid) = lastp;
@@ -848,7 +849,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
         cluster.sync();
         PT(5);
 #pragma unroll
-        for (int p = 0; p < BS_CLUSTER; ++p) {
+        for (int p = 0; p < CL; ++p) {
           const u32 cp = s_xb[ph][0][p];
           feas += cp;
           nbs += s_xb[ph][1][p];
@@ -869,7 +870,7 @@ __global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(SP_THREADS,
     {  // size the next part's first tile from this part (+1/8 slack); a miss (second super-step needed) resets
        // the estimate to the full tile, from where it shrinks by one vector load per part at most
       const u32 elems = pcur - e0;
-      const u32 want = (elems + (elems >> 3) + 3u) / ((u32)SP_THREADS * 4u * BS_CLUSTER) + 1u;
+      const u32 want = (elems + (elems >> 3) + 3u) / ((u32)SP_THREADS * 4u * CL) + 1u;
       nv_est = missed ? (u32)SP_NVMAX : max(min(max(want, 2u), (u32)SP_NVMAX), nv_est > 2u ? nv_est - 1u : 2u);
       nv = nv_est;
     }
@@ -1976,14 +1977,36 @@ void bisect_probe(BisectRun& run, int node_lo, int node_hi) {
       // algorithmic bytes of one fused pass over the links for the thresholds of this launch
       ProfScope pk("k_probe_stream", (double)(f.ls->Ne + f.A->n + 1) * 4.0 + (double)cnt * (K + 1) * 8.0);
       const bool ax = env_int("CPB_PROBE_ASYNC", 1) != 0;  // exchanges by st.async + mbarrier (0: DSMEM stores + cluster barriers)
+      const int cl = env_int("CPB_PROBE_CLUSTER", 8) == 16 ? 16 : 8;  // CTAs per threshold (16: the non-portable cluster size)
       ring_debug_arm();
-      if (f.dev.is_float)
-        if (ax) CPB_LAUNCH((k_probe_stream<double, true>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
-        else CPB_LAUNCH((k_probe_stream<double, false>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
-      else if (ax)
-        CPB_LAUNCH((k_probe_stream<i64, true>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
-      else
-        CPB_LAUNCH((k_probe_stream<i64, false>), cnt * BS_CLUSTER, SP_THREADS, 0, run.ds, K, run.eps1, run.st.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
+      auto launch = [&](auto kern, int CLv) {
+        static bool attr16_set = false;
+        if (CLv == 16) CPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        (void)attr16_set;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(cnt * CLv), 1, 1);
+        cfg.blockDim = dim3(SP_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = ctx().stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CLv;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CPB_CUDA(cudaLaunchKernelEx(&cfg, kern, run.ds, K, run.eps1, (const BisectState*)run.st.get(), run.node_spl, run.node_res, run.node_c, (const int*)run.ids.get(), base));
+        ctx().launches += 1;
+      };
+      if (f.dev.is_float) {
+        if (cl == 16) launch(k_probe_stream<double, true, 16>, 16);
+        else if (ax) launch(k_probe_stream<double, true, 8>, 8);
+        else launch(k_probe_stream<double, false, 8>, 8);
+      } else {
+        if (cl == 16) launch(k_probe_stream<i64, true, 16>, 16);
+        else if (ax) launch(k_probe_stream<i64, true, 8>, 8);
+        else launch(k_probe_stream<i64, false, 8>, 8);
+      }
     } else if (f.dev.is_float) {
       CPB_LAUNCH(k_bisect_round<double>, cnt * BS_CLUSTER, BS_THREADS, 0, f.dev, K, run.eps1, run.st.get(), run.hint_lo.get(), run.hint_hi.get(), run.node_spl, run.node_res, run.node_c, run.ids.get(), base);
     } else {
@@ -2086,7 +2109,7 @@ int probe_cluster_capacity(bool stream) {
     cfg.blockDim = dim3(PR_THREADS, 1, 1);
     cfg.dynamicSmemBytes = PR_RING_BYTES;
     CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_probe_ring<i64>, &cfg));
-  } else if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, (k_probe_stream<i64, true>), &cfg));
+  } else if (stream) CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, (k_probe_stream<i64, true, 8>), &cfg));
   else CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_bisect_round<i64>, &cfg));
   return n;
 }

@@ -132,12 +132,15 @@ def rand_splitter(rng, f, decreasing, constrained_ok, large=False):
                            cp.DynamicBottleneckSplitter(f)])
     return rng.choice([cp.DynamicBottleneckSplitter(spec), cp.DynamicTotalSplitter(spec), cp.DynamicBottleneckChunker(spec), cp.DynamicTotalChunker(spec),
                        cp.BisectCostBottleneckSplitter(f, eps), cp.LazyBisectCostBottleneckSplitter(f, eps), cp.BisectIndexBottleneckSplitter(f),
-                       cp.ConvexTotalSplitter(spec), cp.EquiSplitter()])
+                       cp.ConvexTotalSplitter(spec), cp.ConcaveTotalSplitter(spec), cp.EquiSplitter()])
 
 
 def rand_packer(rng, A):
     w_max = int(rng.integers(1, 12))
-    r = rng.integers(0, 6)
+    r = rng.integers(0, 7)
+    if r == 6:  # ConcaveTotalChunker.jl:9-24 (any random-access model: the device follows the queue routine step by step)
+        f = rng.choice([cp.AffineConnectivityModel(*coefs(rng, 4)), cp.AffineWorkModel(*coefs(rng, 3)), cp.ColumnBlockComponentCostModel(int, 5, lambda w: int(9 * np.sqrt(w)))])
+        return cp.ConcaveTotalChunker(f), False
     if r == 0:
         return cp.OverlapChunker(float(rng.choice([0.0, 0.3, 0.7, 0.9, 1.0])), w_max), False
     if r == 1:
