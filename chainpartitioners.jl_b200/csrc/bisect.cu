@@ -1905,6 +1905,11 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
     while (h.c_lo * run->eps1 < h.c_hi) {
       const double c = (h.c_lo + h.c_hi) / 2;
       if (!(c >= safe)) break;
+      // (the argument above needs an infeasible probe to end the loop.  bound_stripe's lower bound is not a bound for every
+      //  model -- the envelope's (c_hi - alpha) / K can exceed the optimum, EnvelopeCosts.jl:30-42 -- and then the loop ends
+      //  on the INITIAL c_lo with feasible probes only: the probe that would end the loop is its last feasible one and runs
+      //  for real.  Found by tests/fuzz_parity.py, seed 41.)
+      if (!(h.c_lo * run->eps1 < c)) break;
       h.c_hi = c;
       h.probes += 1;
     }

@@ -172,6 +172,23 @@ def test_envelope_bound_is_the_oracle_form(ref, fixtures):
                 assert np.array_equal(cp.partition_stripe(A, 5, mtd).spl, ref.partition_stripe(A, 5, mtd).spl)
 
 
+def test_prewalk_never_skips_the_last_feasible_probe(ref):
+    """Fuzzer find (seed 41): bound_stripe's lower bound alpha + fld(c_hi - alpha, K) is not a bound for the envelope model (it
+    can exceed the optimum), so the bisection can end on its INITIAL c_lo after feasible probes only -- the probe that ends
+    the loop is then the last feasible one and must run for real even when the planner's bound already says "feasible"."""
+    import json
+    import os
+
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "envelope_prewalk_case.json")))
+    A = cp.SparseMatrixCSC(d["m"], d["n"], d["colptr"], np.array(d["rowval"], dtype=np.int64))
+    f = cp.AffineEnvelopeModel(1.5, 1.0, 1.5, 3.0)
+    for eps in (0.3, 0.1, 0.01, 0.001):
+        for K in (2, 5, 9):
+            for mk in (cp.BisectCostBottleneckSplitter, cp.LazyBisectCostBottleneckSplitter):
+                g, r = cp.partition_stripe(A, K, mk(f, eps)), ref.partition_stripe(A, K, mk(f, eps))
+                assert np.array_equal(g.spl, r.spl), (eps, K, mk.__name__, g.spl, r.spl)
+
+
 def test_refusals_named_by_the_round1_review(fixtures):
     """(1) a work model with a negative beta shrinks as the part grows -- the reference's windowed search is path
     dependent there, the device refuses instead of answering differently; (2) the device-array query entry point has no part
