@@ -1539,23 +1539,22 @@ __global__ void __launch_bounds__(256) k_ub_grid(const __grid_constant__ DevStre
   gw[i] = (float)(i == UB_G ? total : S[k] + sc * (ub_weight(s, cf, x) - ua));
 }
 
-// parametric search: thread t cuts the grid greedily at threshold T_t (geometric ladder from the mean share to eight times
+// parametric search: candidate t cuts the grid greedily at threshold T_t (geometric ladder from the mean share to eight times
 // the mean share: a column may outweigh the mean share by far); the smallest threshold that places every
 // column in at most K parts gives the new partition
-__global__ void __launch_bounds__(UB_T) k_ub_greedy(int K, UbCtl* __restrict__ ctl, const u32* __restrict__ gx, const float* __restrict__ gw_g,
-                                                    u32* __restrict__ cuts, int* __restrict__ spl) {
+static constexpr int UB_CTA = 32;  // candidate thresholds per CTA: one warp per SM walks the grid out of its own shared-memory copy
+__global__ void __launch_bounds__(UB_CTA) k_ub_greedy(int K, UbCtl* __restrict__ ctl, const float* __restrict__ gw_g, u32* __restrict__ cuts, int* __restrict__ first) {
   extern __shared__ float s_gw[];  // UB_G + 1
-  __shared__ int s_first;
   if (ctl->stop) return;
   const int tid = threadIdx.x;
-  for (int i = tid; i <= UB_G; i += UB_T) s_gw[i] = gw_g[i];
-  if (tid == 0) s_first = UB_T;
+  for (int i = tid; i <= UB_G; i += UB_CTA) s_gw[i] = gw_g[i];
   __syncthreads();
+  const int t = blockIdx.x * UB_CTA + tid;  // candidate index 0 .. UB_T - 1
   const float total = s_gw[UB_G];
   const double tlo = ctl->tlo;
-  const float T = (float)(tlo * exp2(3.0 * (double)tid / (double)(UB_T - 1)));
+  const float T = (float)(tlo * exp2(3.0 * (double)t / (double)(UB_T - 1)));
   const float w0 = total / (float)UB_G;
-  u32* my = cuts + (size_t)tid * (K + 1);
+  u32* my = cuts + (size_t)t * (K + 1);
   int i = 0;
   bool ok = true;
   my[0] = 0;
@@ -1570,20 +1569,27 @@ __global__ void __launch_bounds__(UB_T) k_ub_greedy(int K, UbCtl* __restrict__ c
         const int mid = lo + ((hi - lo + 1) >> 1);
         if (s_gw[mid] <= target) lo = mid; else hi = mid - 1;
       }
-      // (grid points that share a column boundary carry the same weight: move to the last of them)
+      // (grid points that share a column boundary carry the same weight: the search lands on the last of them)
       if (lo == i) { ok = false; break; }  // one step outweighs T
       i = lo;
     }
     my[k] = (u32)i;
   }
-  ok = ok && i == UB_G;
-  if (ok) atomicMin(&s_first, tid);
+  if (ok && i == UB_G) atomicMin(first, t);
+}
+// the smallest threshold that placed every column gives the new partition (none: the partition stays)
+__global__ void __launch_bounds__(1024) k_ub_apply(int K, UbCtl* __restrict__ ctl, const u32* __restrict__ gx, const u32* __restrict__ cuts, int* __restrict__ first,
+                                                   int* __restrict__ spl) {
+  if (ctl->stop) return;
+  const int best = *first;
   __syncthreads();
-  const int best = s_first;
-  if (best >= UB_T) return;  // no candidate placed every column: keep the partition
-  if (tid == best) ctl->tstar = (double)T;
+  if (threadIdx.x == 0) {
+    *first = UB_T;  // (armed for the next step)
+    if (best < UB_T) ctl->tstar = ctl->tlo * exp2(3.0 * (double)best / (double)(UB_T - 1));
+  }
+  if (best >= UB_T) return;
   const u32* src = cuts + (size_t)best * (K + 1);
-  for (int k = tid; k <= K; k += UB_T) spl[k] = (k == 0) ? 1 : (int)gx[src[k]];
+  for (int k = threadIdx.x; k <= K; k += 1024) spl[k] = (k == 0) ? 1 : (int)gx[src[k]];
 }
 
 // The same bound for the models probed through the dominance index: parts cut at equal shares of (columns + pins),
@@ -1756,10 +1762,14 @@ static void refine_upper_bound(Oracle& f, const DevStream& ds, i64 K, double eps
   }
   DBuf<u32> gx(UB_G + 1), cuts((size_t)UB_T * (K + 1));
   DBuf<float> gw(UB_G + 1);
+  DBuf<int> first(1);
+  const int armed = UB_T;
+  CPB_CUDA(cudaMemcpyAsync(first.get(), &armed, sizeof(int), cudaMemcpyHostToDevice, ctx().stream));
   int* const stop = &w.ctl.get()->stop;
   for (int it = 0; it < w.steps; ++it) {
     CPB_LAUNCH(k_ub_grid, (UB_G + 256) / 256, 256, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.S.get(), w.scale.get(), w.ctl.get(), gx.get(), gw.get());
-    CPB_LAUNCH(k_ub_greedy, 1, UB_T, (UB_G + 1) * sizeof(float), (int)K, w.ctl.get(), gx.get(), gw.get(), cuts.get(), w.spl.get());
+    CPB_LAUNCH(k_ub_greedy, UB_T / UB_CTA, UB_CTA, (UB_G + 1) * sizeof(float), (int)K, w.ctl.get(), gw.get(), cuts.get(), first.get());
+    CPB_LAUNCH(k_ub_apply, 1, 1024, 0, (int)K, w.ctl.get(), gx.get(), cuts.get(), first.get(), w.spl.get());
     CPB_LAUNCH(k_ub_zero, (unsigned)((K + 255) / 256), 256, 0, w.cnt.get(), (int)K, stop);
     CPB_LAUNCH(k_ub_count, dim3(w.slices, (unsigned)K, 1), 256, 0, ds, w.spl.get(), w.cnt.get(), stop);
     CPB_LAUNCH(k_ub_prepare, 1, 1024, 0, ds, f.dev.is_float, (int)K, w.spl.get(), w.cnt.get(), w.S.get(), w.scale.get(), w.ctl.get(), d_out, 0, eps / 4);
