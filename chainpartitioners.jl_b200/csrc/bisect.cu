@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1)
       // ---- flags of `prev <= e0`: each warp owns nv consecutive 128-element groups (one warp-wide 128-bit load per group);
       //      every lane stores the nibble of its four compares as one byte, the group totals come from two packed warp
       //      reductions.  (Round 1 formed the masks with 4 ballots per group: 1024 VOTEs per CTA and super-step on the SM's one
-      //      address-divergence unit -- ~3 cycles each, measured with scratch/ubench -- were what bounded this phase.) ----
+      //      address-divergence unit -- ~3 cycles each, measured with tools/ubench -- were what bounded this phase.) ----
       u32 wsum = 0;
       // A part longer than one register tile (8 vector loads per thread) takes up to SP_SUB tiles in the same super-step:
       // the flags live in shared memory, only the loads repeat -- one more load phase instead of a whole second super-step
@@ -1424,7 +1424,7 @@ __global__ void k_ub_max(const __grid_constant__ DevStream s, int is_float, int 
 //      inside every part so that the part weighs its exact cost, and cuts the rescaled weight greedily at the smallest
 //      threshold that needs at most K parts (a column heavier than the mean share stays alone -- equal-share cuts cannot do
 //      that); the new partition is evaluated exactly by k_ub_count again.  On R-MAT the first bound is 20-40 % above the
-//      optimum, one or two steps bring it within ~1 % (scratch/ub_refine_proto.py), which lets one round of speculated
+//      optimum, one or two steps bring it within ~1 % (tools/ub_refine_proto.py), which lets one round of speculated
 //      thresholds finish the bisection.  Only the plan depends on the bound.
 static constexpr int UB_G = 32768;      // grid points of the rescaled weight (uniform in weight)
 static constexpr int UB_T = 1024;       // candidate thresholds of the parametric search, one per thread

@@ -131,7 +131,7 @@ __device__ __forceinline__ void os_tile_body(const u32* __restrict__ keys32, con
   }
 
   // rank inside the warp: the lanes holding the same digit in a round form a group; the group reads the warp's count of the
-  // digit so far, its first lane adds the group's size.  Two ways to find the group (measured on B200: scratch/ubench/,
+  // digit so far, its first lane adds the group's size.  Two ways to find the group (measured on B200: tools/ubench/,
   // profiles/r02_session2.md section 2): MATCH.ANY costs ~2 cycles per DISTINCT value on the SM's one address-divergence unit (61
   // cycles for random 8-bit digits, 1.7 ms per pass at 2.6e8 pairs; cheaper for skewed digits); through shared memory
   // -- every lane ORs its bit into the (warp, digit) mask word and reads it back, the first lane clears it -- costs
