@@ -450,7 +450,7 @@ __device__ __forceinline__ u32 stream_prefix_nib(const u32* s_mask, const u32* s
 struct DevStream {
   const u32* prev;    // [Ne] 1 + position of the previous nonzero of the same row (0 = none): "its column lies left of the part"
                       //      is simply prev <= first position of the part
-  const u32* colidx;  // [Ne]
+  const u32* colq;    // [ceil(Ne / LS_COLQ) + 1] 0-based column of every LS_COLQ-th element (LinkStream::colq)
   const u32* P;       // element offsets of the column boundaries, 1 <= x <= n+1
   const u32* Wt;      // prefix of the pin-like term, 1 <= x <= n+1
   const u32* chunk_col;  // [ceil(Ne / LS_CHUNK) + 1] column of the first element of every LS_CHUNK-element chunk (ring probes)
@@ -547,6 +547,26 @@ __device__ unsigned long long g_probe_node[16][4];  // per slot: cycles of its c
 #define PT(i) do {} while (0)
 #endif
 
+// 0-based columns of the elements e1, e2 < Ne (use1 / use2: which are wanted): the largest c with P[c + 1] <= e, searched by the
+// whole warp (32 probes per step, counted with a warp reduction -- no vote) between the columns the per-128-element table
+// brackets it with; both searches advance together so that their loads overlap.  Warp-uniform arguments.
+__device__ __forceinline__ void stream_cols_of(const DevStream& s, bool use1, u32 e1, bool use2, u32 e2, int lane, u32& c1, u32& c2) {
+  u32 lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+  if (use1) { lo1 = __ldg(s.colq + e1 / LS_COLQ); hi1 = __ldg(s.colq + e1 / LS_COLQ + 1); }  // (behind the end the table holds n - 1)
+  if (use2) { lo2 = __ldg(s.colq + e2 / LS_COLQ); hi2 = __ldg(s.colq + e2 / LS_COLQ + 1); }
+  while (hi1 > lo1 || hi2 > lo2) {
+    const u32 st1 = (hi1 - lo1 + 31u) / 32u, st2 = (hi2 - lo2 + 31u) / 32u;
+    const u64 p1 = (u64)lo1 + (u64)(lane + 1) * st1, p2 = (u64)lo2 + (u64)(lane + 1) * st2;  // this lane's probes; those that hold form a prefix
+    const bool ok1 = hi1 > lo1 && p1 <= hi1 && __ldg(s.P + p1 + 1) <= e1;
+    const bool ok2 = hi2 > lo2 && p2 <= hi2 && __ldg(s.P + p2 + 1) <= e2;
+    const u32 cnt = __reduce_add_sync(0xffffffffu, (ok1 ? 1u : 0u) | (ok2 ? 0x10000u : 0u));
+    if (hi1 > lo1) { const u32 nlo = lo1 + (cnt & 0xffffu) * st1; hi1 = (u32)min((u64)hi1, (u64)nlo + st1 - 1); lo1 = nlo; }
+    if (hi2 > lo2) { const u32 nlo = lo2 + (cnt >> 16) * st2; hi2 = (u32)min((u64)hi2, (u64)nlo + st2 - 1); lo2 = nlo; }
+  }
+  c1 = lo1;
+  c2 = lo2;
+}
+
 // AX: the two exchanges of a super-step as remote st.async stores that complete a transaction count on every peer's
 // mbarrier (no barrier.cluster, no fence in front of it, no L1 invalidation); !AX: DSMEM stores + cluster barriers.
 // CL: CTAs per cluster (8, or 16 = the non-portable size; set by the launch attribute)
@@ -626,12 +646,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1)
       PT(6);  // between the super-steps (part bookkeeping)
 #endif
       const u32 e_c = e_tile + crank * CE;
-      // ---- column boundaries whose element offset falls into (e_c, e_c + CE] (loads issued ahead of the tile) ----
-      u32 ja, jb;
-      if (first && crank == 0) ja = j + 1;
-      else ja = (e_c < Ne) ? __ldg(s.colidx + e_c) + 2 : n1 + 1;
-      if (e_c >= Ne && !(first && crank == 0)) jb = 0;
-      else jb = ((u64)e_c + CE >= Ne) ? n1 : __ldg(s.colidx + e_c + CE) + 1;
+      // ---- column boundaries whose element offset falls into (e_c, e_c + CE] ----
+      u32 ja = 0, jb = 0;  // (found below, while the tile's loads are in flight)
       // ---- flags of `prev <= e0`: each warp owns nv consecutive 128-element groups (one warp-wide 128-bit load per group);
       //      every lane stores the nibble of its four compares as one byte, the group totals come from two packed warp
       //      reductions.  (Round 1 formed the masks with 4 ballots per group: 1024 VOTEs per CTA and super-step on the SM's one
@@ -662,6 +678,14 @@ __global__ void __launch_bounds__(SP_THREADS, 1)
               if (idx + 2 < Ne) pv[v].z = __ldg(s.prev + idx + 2);
             }
           }
+        }
+        if (sub == 0) {  // the columns of the slice's two ends: two short cooperative searches behind the tile's loads
+          const bool head = first && crank == 0;
+          const bool want_a = !head && e_c < Ne, want_b = (head || e_c < Ne) && (u64)e_c + CE < Ne;
+          u32 ca = 0, cb = 0;
+          stream_cols_of(s, want_a, e_c, want_b, e_c + CE, lane, ca, cb);
+          ja = head ? j + 1 : (e_c < Ne ? ca + 2 : n1 + 1);
+          jb = (e_c >= Ne && !head) ? 0u : (((u64)e_c + CE >= Ne) ? n1 : cb + 1);
         }
 #pragma unroll
         for (int v = 0; v < SP_VEC; ++v) {
@@ -1714,7 +1738,7 @@ static void plan_round(BisectRun& run) {
 static void stream_view(Oracle& f, DevStream& ds) {
   const Matrix& A = *f.A;
   ds.prev = f.ls->prev.get();
-  ds.colidx = f.ls->colidx.get();
+  ds.colq = f.ls->colq.get();
   ds.chunk_col = f.ls->chunk_col.get();
   ds.P = f.ls->P;
   ds.Wt = (f.dev.kind == CPB_MODEL_MONOSYM) ? f.overpos.get() - 1 : A.pos.get() - 1;

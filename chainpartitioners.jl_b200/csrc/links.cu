@@ -215,19 +215,39 @@ __global__ void k_lt_link(const u32* __restrict__ T, const u32* __restrict__ hea
   if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(first_count, firsts);
 }
 
-// chunk_col[g] = colidx[g * LS_CHUNK] for every chunk that starts inside the array
-__global__ void k_chunk_cols(const u32* __restrict__ colidx, size_t Ne, u32* __restrict__ chunk_col, u32 nchunks) {
+// colq[g] = 0-based column of element g * LS_COLQ = the largest c with P[c + 1] <= g * LS_COLQ (P[x] = elements in columns < x,
+// 1-based), n - 1 behind the end of the array
+__global__ void k_colq(const u32* __restrict__ P, u32 n, size_t Ne, u32* __restrict__ colq, u32 G) {
+  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  const size_t e = (size_t)g * LS_COLQ;
+  u32 c = n ? n - 1 : 0;
+  if (e < Ne && n) {
+    u32 lo = 0, hi = n - 1;  // P[1] = 0 <= e
+    while (lo < hi) {
+      const u32 mid = lo + ((hi - lo + 1) >> 1);
+      if ((size_t)__ldg(P + mid + 1) <= e) lo = mid; else hi = mid - 1;
+    }
+    c = lo;
+  }
+  colq[g] = c;
+}
+// chunk_col[g] = column of element g * LS_CHUNK for every chunk that starts inside the array (0 behind it)
+__global__ void k_chunk_cols(const u32* __restrict__ colq, size_t Ne, u32* __restrict__ chunk_col, u32 nchunks) {
   const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g > nchunks) return;
   const size_t x = (size_t)g * LS_CHUNK;
-  chunk_col[g] = x < Ne ? colidx[x] : 0u;
+  chunk_col[g] = x < Ne ? colq[x / LS_COLQ] : 0u;
 }
-static void fill_chunk_cols(LinkStream& ls) {
+static void fill_chunk_cols(LinkStream& ls, u32 n) {
+  const u32 G = (u32)((ls.Ne + LS_COLQ - 1) / LS_COLQ);
+  ls.colq.alloc((size_t)G + 2);
+  CPB_LAUNCH(k_colq, (G + 1) / 256 + 1, 256, 0, ls.P, n, ls.Ne, ls.colq.get(), G + 1);
   const u32 nchunks = (u32)((ls.Ne + LS_CHUNK - 1) / LS_CHUNK);
   ls.chunk_col.alloc((size_t)nchunks + 1);
-  CPB_LAUNCH(k_chunk_cols, nchunks / 256 + 1, 256, 0, ls.colidx.get(), ls.Ne, ls.chunk_col.get(), nchunks);
+  CPB_LAUNCH(k_chunk_cols, nchunks / 256 + 1, 256, 0, ls.colq.get(), ls.Ne, ls.chunk_col.get(), nchunks);
 }
-void fill_chunk_cols_public(LinkStream& ls) { fill_chunk_cols(ls); }
+void fill_chunk_cols_public(LinkStream& ls, u32 n) { fill_chunk_cols(ls, n); }
 static size_t padded_links(size_t Ne) { return (Ne + LS_CHUNK - 1) / LS_CHUNK * LS_CHUNK + LS_CHUNK; }  // whole chunks (bulk copies read them whole)
 
 static u32 read_u32(const u32* d) {
@@ -247,7 +267,8 @@ static u32 read_u32(const u32* d) {
 bool compute_prev_links(const u32* pos, const u32* row, u32 nrow, u32 ncol, size_t N, u32* prev, u32* colidx, u32* first_count,
                         i64 row_lo, i64 row_hi, bool defer_check, bool force_sort, bool as_pos, i64* max_deg_cache) {
   ProfScope prof("build_links", (double)(2 * N + ncol + 1) * 4.0);
-  {
+  CPB_REQUIRE(colidx || as_pos, "column-valued links need the column array");
+  if (colidx) {
     ProfScope pk("k_expand_columns", (double)N * 4.0 + (double)ncol * 4.0);
     expand_columns(pos, ncol, colidx, N);
   }
@@ -353,12 +374,12 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
   if (!dia) {
     ls->Ne = N;
     ls->prev.alloc(padded_links(N));
-    ls->colidx.alloc(N);
+    if (!as_pos) ls->colidx.alloc(N);
     ls->first_count.alloc(2);
-    ls->speculative = compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi,
-                                         defer_check, force_sort, as_pos, &A.max_row_deg);
+    ls->speculative = compute_prev_links(A.pos.get(), A.row.get(), m, n, N, ls->prev.get(), as_pos ? nullptr : ls->colidx.get(), ls->first_count.get(), row_lo,
+                                         row_hi, defer_check, force_sort, as_pos, &A.max_row_deg);
     ls->P = A.pos.get() - 1;  // P[x] = pos[x-1]
-    fill_chunk_cols(*ls);
+    fill_chunk_cols(*ls, n);
     return ls;
   }
   CPB_REQUIRE(A.m >= A.n, "dianetcount needs m >= n");
@@ -378,12 +399,12 @@ std::unique_ptr<LinkStream> build_link_stream(const Matrix& A, bool dia, i64 row
   i64 heavy_hint = A.max_row_deg > (i64)LT_MAX_DEG ? A.max_row_deg : -1;  // A + I only adds entries: a heavy row of A stays heavy
   ls->Ne = N2;
   ls->prev.alloc(padded_links(N2));
-  ls->colidx.alloc(N2);
+  if (!as_pos) ls->colidx.alloc(N2);
   ls->first_count.alloc(2);
-  ls->speculative = compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), ls->colidx.get(), ls->first_count.get(), row_lo, row_hi, defer_check,
-                                       force_sort, as_pos, &heavy_hint);
+  ls->speculative = compute_prev_links(pos2, row2.get(), m, n, N2, ls->prev.get(), as_pos ? nullptr : ls->colidx.get(), ls->first_count.get(), row_lo, row_hi,
+                                       defer_check, force_sort, as_pos, &heavy_hint);
   ls->P = ls->P_own.get();  // P[x] = pos2[x-1]
-  fill_chunk_cols(*ls);
+  fill_chunk_cols(*ls, n);
   return ls;
 }
 
