@@ -21,7 +21,7 @@ __all__ = [
     "pack_stripe", "partition_plaid", "pack_plaid", "bottleneck_value", "total_value", "pincount", "netcount",
     "dianetcount", "selfnetcount", "selfpincount", "PrefixMatrix", "dominancecount", "dominancesum", "rookcount", "rooksum", "profile_enable", "profile_reset", "profile_get",
     "Communicator", "ShardedMatrix", "partition_stripe_sharded", "partition_stripe_sharded_emulated", "sharded_stats", "shard_range",
-    "launch_count", "probe_cluster_capacity", "bisect_stats", "bisect_plan", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "trim_memory", "library_path", "load_library", "CpbError",
+    "launch_count", "probe_cluster_capacity", "bisect_stats", "bisect_plan", "bisect_prewalk", "timer_start", "timer_stop", "StepwiseBisection", "StripeOracle", "init", "synchronize", "trim_memory", "library_path", "load_library", "CpbError",
 ]
 
 I64 = np.int64
@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cpb_oracle_create", "cpb_oracle_destroy", "cpb_oracle_query", "cpb_oracle_query_device", "cpb_count_query",
     "cpb_bound_stripe", "cpb_objective", "cpb_partition_stripe", "cpb_pack_stripe", "cpb_profile_enable",
     "cpb_profile_reset", "cpb_profile_get", "cpb_launch_count", "cpb_timer_start", "cpb_timer_stop",
-    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_bisect_plan", "cpb_probe_cluster_capacity",
+    "cpb_bisect_begin", "cpb_bisect_probe", "cpb_bisect_advance", "cpb_bisect_finish", "cpb_bisect_stats", "cpb_bisect_plan", "cpb_bisect_prewalk", "cpb_probe_cluster_capacity",
     "cpb_comm_unique_id", "cpb_comm_init", "cpb_comm_destroy", "cpb_comm_info", "cpb_shard_range", "cpb_sharded_matrix_create", "cpb_sharded_matrix_destroy",
     "cpb_partition_stripe_sharded", "cpb_partition_stripe_sharded_emulated", "cpb_sharded_stats",
     "cpb_links_partial", "cpb_oracle_set_links", "cpb_prefix_create", "cpb_prefix_query", "cpb_prefix_destroy", "cpb_matrix_permute", "cpb_trim_memory", "cpb_matrix_create_i32",
@@ -808,6 +808,16 @@ def bisect_plan(c_lo: float, c_hi: float, eps: float, nodes: int, c_lo0: float =
     lib.cpb_bisect_plan.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
     _check(lib.cpb_bisect_plan(c_lo, c_hi, eps, nodes, c_lo if c_lo0 is None else c_lo0, c_hi if c_hi0 is None else c_hi0, upper_bound, ids))
     return [int(x) for x in ids]
+
+
+def bisect_prewalk(c_lo: float, c_hi: float, eps: float, upper_bound: float):
+    """-> (c_hi after the probes the bound settles, their number) (``cpb_bisect_prewalk``; host-only)."""
+    out = ctypes.c_double()
+    n = ctypes.c_int32()
+    lib = load_library()
+    lib.cpb_bisect_prewalk.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)]
+    _check(lib.cpb_bisect_prewalk(c_lo, c_hi, eps, upper_bound, ctypes.byref(out), ctypes.byref(n)))
+    return out.value, n.value
 
 
 def bisect_stats() -> dict:

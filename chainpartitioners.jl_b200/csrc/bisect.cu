@@ -1818,6 +1818,28 @@ static void require_monotone_cost(const Oracle& f) {
                                        "windowed search path dependent");
 }
 
+// The leading probes of the sequential loop that the planner's bound settles (see bisect_begin): walks them with the loop's own
+// expressions and returns the c_hi they leave and their number.  Pure host arithmetic (cpb_bisect_prewalk exposes it to the
+// CPU tests).
+void bisect_prewalk(double c_lo, double c_hi, double eps, double ub, double* c_hi_out, int* probes_out) {
+  const double eps1 = 1 + eps;
+  const double safe = ub * eps1 * eps1;
+  int probes = 0;
+  while (c_lo * eps1 < c_hi) {
+    const double c = (c_lo + c_hi) / 2;
+    if (!(c >= safe)) break;
+    // (the argument needs an infeasible probe to end the loop.  bound_stripe's lower bound is not a bound for every model -- the
+    //  envelope's (c_hi - alpha) / K can exceed the optimum, EnvelopeCosts.jl:30-42 -- and then the loop ends on the INITIAL c_lo
+    //  with feasible probes only: the probe that would end the loop is its last feasible one and runs for real.  Found by
+    //  tests/fuzz_parity.py, seed 41.)
+    if (!(c_lo * eps1 < c)) break;
+    c_hi = c;
+    probes += 1;
+  }
+  *c_hi_out = c_hi;
+  *probes_out = probes;
+}
+
 BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int* d_node_res, double* d_node_c, int* d_node_spl) {
   CPB_REQUIRE(K >= 1, "K must be >= 1");
   CPB_REQUIRE(f.dev.kind != CPB_MODEL_BLOCK, "bisection needs a random-access oracle");
@@ -1936,18 +1958,9 @@ BisectRun* bisect_begin(Oracle& f, bool lazy, double eps, i64 K, int nodes, int*
   // infeasible (or initial) c_lo above ub, which no threshold below the optimum is.  On R-MAT scale 24 this skips 5 of 13
   // probes and the remaining 8 fit one round of 15 speculated thresholds instead of two.
   if (run->ub > 0 && eps >= 1e-12 && env_int("CPB_BISECT_PREWALK", 1) != 0) {
-    const double safe = run->ub * run->eps1 * run->eps1;
-    while (h.c_lo * run->eps1 < h.c_hi) {
-      const double c = (h.c_lo + h.c_hi) / 2;
-      if (!(c >= safe)) break;
-      // (the argument above needs an infeasible probe to end the loop.  bound_stripe's lower bound is not a bound for every
-      //  model -- the envelope's (c_hi - alpha) / K can exceed the optimum, EnvelopeCosts.jl:30-42 -- and then the loop ends
-      //  on the INITIAL c_lo with feasible probes only: the probe that would end the loop is its last feasible one and runs
-      //  for real.  Found by tests/fuzz_parity.py, seed 41.)
-      if (!(h.c_lo * run->eps1 < c)) break;
-      h.c_hi = c;
-      h.probes += 1;
-    }
+    int walked = 0;
+    bisect_prewalk(h.c_lo, h.c_hi, eps, run->ub, &h.c_hi, &walked);
+    h.probes += walked;
   }
   h.done = !(h.c_lo * run->eps1 < h.c_hi);
   run->done = h.done != 0;

@@ -676,6 +676,15 @@ int cpb_bisect_plan(double c_lo, double c_hi, double eps, int nodes, double c_lo
   CPB_API_END
 }
 
+int cpb_bisect_prewalk(double c_lo, double c_hi, double eps, double upper_bound, double* c_hi_out, int32_t* probes_out) {
+  CPB_API_BEGIN
+  CPB_REQUIRE(c_hi_out && probes_out, "NULL argument");
+  int probes = 0;
+  bisect_prewalk(c_lo, c_hi, eps, upper_bound, c_hi_out, &probes);
+  *probes_out = probes;
+  CPB_API_END
+}
+
 int cpb_bisect_stats(double out[8]) {
   CPB_API_BEGIN
   CPB_REQUIRE(out, "NULL argument");

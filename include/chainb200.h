@@ -231,6 +231,10 @@ int cpb_bisect_finish(cpb_bisect* b, int64_t* spl_out);
  * optimum from above.  The set always contains the root and is closed under taking parents; which nodes are in it never
  * changes the result, only how many rounds the bisection needs. */
 int cpb_bisect_plan(double c_lo, double c_hi, double eps, int nodes, double c_lo0, double c_hi0, double upper_bound, int32_t* ids_out);
+/* Host-only: the leading probes of the loop BisectCostBottleneckSplitter.jl:41-60 that an upper bound on the optimal bottleneck
+ * settles without running them (every threshold >= upper_bound (1 + eps)^2 is feasible and cannot be the last feasible probe --
+ * unless it is the probe that ends the loop, which is left to run).  Returns the c_hi they leave and their number. */
+int cpb_bisect_prewalk(double c_lo, double c_hi, double eps, double upper_bound, double* c_hi_out, int32_t* probes_out);
 /* Diagnostics of the most recently finished bisection of this process: out[0] = rounds (batches of concurrent
  * probes), out[1] = probes the sequential loop of the reference would have run, out[2] = thresholds probed
  * speculatively in total, out[3] = initial c_lo, out[4] = initial c_hi, out[5] = the planner's upper bound (0 = none), out[6] = final c_lo,

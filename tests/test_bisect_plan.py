@@ -74,3 +74,35 @@ def test_tight_upper_bound_saves_rounds():
     assert tight == 1 and tight < no_bound <= full_tree
     # a useless bound (3 x the optimum) must not cost more than one round over the prior without a bound
     assert by_rounds(c_lo, c_hi, eps, cstar, 15, cstar * 3)[3] <= no_bound + 1
+
+
+def test_prewalk_keeps_the_reference_result():
+    """cpb_bisect_prewalk walks the loop's leading probes that an upper bound ub >= c* settles (all feasible).  Whatever the
+    bracket -- including a c_lo ABOVE the optimum, which bound_stripe produces for the envelope model (found by the fuzzer) --
+    the loop continued from the prewalked state must end in the same bracket as the sequential loop, and the loop's LAST
+    feasible probe (whose split vector is the result) must not be among the prewalked ones."""
+    rng = np.random.default_rng(77)
+    for _ in range(4000):
+        eps = float(rng.choice([0.3, 0.1, 0.01, 0.001]))
+        c_lo = float(rng.uniform(1, 1e7))
+        c_hi = c_lo * float(np.exp(rng.uniform(0, math.log(2000))))
+        # the optimum anywhere around the bracket: below c_lo (invalid lower bound), inside, or at c_hi
+        cstar = c_lo * float(np.exp(rng.uniform(-0.5, math.log(c_hi / c_lo))))
+        ub = cstar * float(rng.choice([1.0, 1.0001, 1.01, 1.3, 3.0]))
+        # sequential loop, recording the probes
+        lo, hi, seq = c_lo, c_hi, []
+        while lo * (1 + eps) < hi:
+            c = (lo + hi) / 2
+            ok = c >= cstar
+            seq.append((c, ok))
+            if ok:
+                hi = c
+            else:
+                lo = c
+        hi2, walked = cp.bisect_prewalk(c_lo, c_hi, eps, ub)
+        assert 0 <= walked <= len(seq)
+        assert all(ok for _, ok in seq[:walked])                      # only feasible probes are settled
+        assert hi2 == (seq[walked - 1][0] if walked else c_hi)          # ... with the loop's own thresholds
+        feas = [i for i, (_, ok) in enumerate(seq) if ok]
+        if feas:
+            assert feas[-1] >= walked, (c_lo, c_hi, eps, cstar, ub)    # the last feasible probe still runs for real
