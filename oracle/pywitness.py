@@ -303,6 +303,77 @@ def chunk_convex(cst, ptr, f, j0, jp1, ftr):  # ConvexTotalChunker.jl:57-112; ft
                     ftr.append((jp - 1, h))
 
 
+def chunk_concave(cst, ptr, f, j0, jp1):  # ConcaveTotalChunker.jl:57-114; the CircularDeque as a collections.deque
+    from collections import deque
+
+    ftr = deque()
+    ftr.append((j0, j0 + 1))
+    for jp in range(j0 + 1, jp1 + 1):
+        (j, h) = ftr[0]
+        c = f(j, jp)
+        c2 = f(jp - 1, jp)
+        if c2 <= c:
+            if c2 <= cst[jp]:
+                cst[jp] = c2
+                ptr[jp] = jp - 1
+            ftr.clear()
+            ftr.append((jp - 1, jp + 1))
+        else:
+            if c <= cst[jp]:
+                cst[jp] = c
+                ptr[jp] = j
+            while True:
+                (j, h) = ftr[-1]
+                if f(jp - 1, h) <= f(j, h):
+                    ftr.pop()
+                else:
+                    break
+            (j, h) = ftr[-1]
+            h_lo = h + 1
+            h_hi = jp1
+            while h_lo <= h_hi:
+                h = (h_lo + h_hi) >> 1
+                if f(jp - 1, h) > f(j, h):
+                    h_lo = h + 1
+                else:
+                    h_hi = h - 1
+            h = h_lo
+            if h != jp1 + 1:
+                ftr.append((jp - 1, h))
+            (j, _) = ftr.popleft()
+            if not ftr or ftr[0][1] != jp + 1:
+                ftr.appendleft((j, jp + 1))
+
+
+def concave_total_chunker(f: Conn):  # ConcaveTotalChunker.jl:9-24
+    n = f.n
+    INF = float("inf")  # typemax(cost_type): compares like the reference's sentinel, never enters a sum
+    spl = [0] * (n + 2)
+    cst = [INF] * (n + 2)
+    cst[1] = 0
+    chunk_concave(cst, spl, lambda j, jp: cst[j] + f(j, jp), 1, n + 1)
+    return unravel_chunks(spl, n)
+
+
+def concave_total_splitter(f: Conn, K):  # ConcaveTotalChunker.jl:26-55
+    n = f.n
+    if K == 1:
+        return [1, n + 1]
+    INF = float("inf")
+    ptr = [[0] * (n + 2) for _ in range(K + 1)]
+    cst = [[INF] * (n + 2) for _ in range(K + 1)]
+    for jp in range(1, n + 2):
+        cst[1][jp] = f(1, jp)
+        ptr[1][jp] = 1
+    for k in range(2, K + 1):
+        fp = lambda j, jp, k=k: cst[k - 1][j] + f(j, jp)
+        for jp in range(1, n + 2):
+            cst[k][jp] = fp(jp, jp)
+            ptr[k][jp] = jp
+        chunk_concave(cst[k], ptr[k], fp, 1, n + 1)
+    return unravel_splits(K, n, ptr)
+
+
 def convex_total_chunker_constrained(f: Conn, w_max):  # ConvexTotalChunker.jl:141-165 + 211-265, w = VertexCount()
     n = f.n
     w = lambda j, jp: jp - j

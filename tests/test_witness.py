@@ -64,3 +64,22 @@ def test_chunkers_agree(ref, seed):
         exp = ref.pack_stripe(A, cp.OverlapChunker(rho, w_max), n_nets=nn)
         spl, nets = wit.overlap_chunker(A, rho, w_max)
         assert spl == exp.spl.tolist() and nets == nn[0].tolist(), ("overlap", A.colptr, A.rowval, rho, w_max)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_concave_forms_agree(ref, seed):
+    """a23: the queue routine chunk_concave! (ConcaveTotalChunker.jl:57-114) and its two unconstrained callers, transliterated
+    independently in Python, against the C++ oracle that checks the device -- on connectivity costs (not concave: the result is
+    then whatever the queue leaves, which is exactly what has to be reproduced), ties included."""
+    rng = np.random.default_rng(3000 + seed)
+    for _ in range(60):
+        A = random_matrix(rng)
+        coef, mdl = random_model(rng)
+        f = wit.Conn(A, coef)
+        got = wit.concave_total_chunker(f)
+        exp = ref.pack_stripe(A, cp.ConcaveTotalChunker(mdl))
+        assert got == exp.spl.tolist(), ("concave chunker", A.colptr, A.rowval, coef)
+        K = int(rng.integers(1, 7))
+        got = wit.concave_total_splitter(f, K)
+        exp = ref.partition_stripe(A, K, cp.ConcaveTotalSplitter(mdl))
+        assert got == exp.spl.tolist(), ("concave splitter", A.colptr, A.rowval, coef, K)
